@@ -1,0 +1,138 @@
+"""ctypes binding of include/flacb200.h (libflacb200.so).
+
+This is the only way Python reaches the engine: through the same C ABI a Rust/C++ host would bind.
+There is no CPU fallback -- loading fails loudly when the library or the GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflacb200.so")
+
+HOST, DEVICE = 0, 1
+PCM_BYTES_LE, PCM_BYTES_BE, PCM_I32_INTERLEAVED, PCM_I32_PLANAR = 0, 1, 2, 3
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("block_size", C.c_uint16),
+        ("max_lpc_order", C.c_uint8),
+        ("max_partition_order", C.c_uint8),
+        ("mid_side", C.c_uint8),
+        ("exhaustive_channel_correlation", C.c_uint8),
+        ("window_kind", C.c_uint8),
+        ("reserved0", C.c_uint8),
+        ("tukey_p", C.c_float),
+    ]
+
+
+class StreamParams(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_uint32),
+        ("bits_per_sample", C.c_uint32),
+        ("channels", C.c_uint32),
+        ("subset", C.c_uint32),
+        ("max_block_size", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class Segment(C.Structure):
+    _fields_ = [("pcm_offset", C.c_uint64), ("n_pcm_frames", C.c_uint64), ("first_frame_number", C.c_uint64)]
+
+
+class DecodeSegment(C.Structure):
+    _fields_ = [("byte_offset", C.c_uint64), ("byte_length", C.c_uint64), ("pcm_offset", C.c_uint64),
+                ("n_pcm_frames", C.c_uint64)]
+
+
+class SubframeInfo(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32), ("order", C.c_int32), ("wasted", C.c_int32), ("bps", C.c_int32),
+        ("precision", C.c_int32), ("shift", C.c_int32), ("coefs", C.c_int32 * 32),
+        ("coding_method", C.c_int32), ("partition_order", C.c_int32),
+        ("rice", C.c_uint8 * 64), ("kind", C.c_uint8 * 64), ("bits", C.c_uint64),
+    ]
+
+
+class FrameInfo(C.Structure):
+    _fields_ = [("channel_assignment", C.c_int32), ("channels", C.c_int32), ("frame_bytes", C.c_uint32),
+                ("sub", SubframeInfo * 8)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("kernel_ms", C.c_float * 8),
+                ("kernel_launches", C.c_uint32 * 8), ("launches", C.c_uint32)]
+
+
+EXPORTS = [
+    "flacb200_options_default", "flacb200_options_fast", "flacb200_options_best", "flacb200_engine_create",
+    "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_encode",
+    "flacb200_encode_bound", "flacb200_encode_last_info", "flacb200_decode", "flacb200_set_profiling",
+    "flacb200_last_timings", "flacb200_synth_pcm", "flacb200_host_alloc", "flacb200_host_free",
+    "flacb200_device_alloc", "flacb200_device_free", "flacb200_memcpy", "flacb200_synchronize", "flacb200_strerror",
+    "flacb200_version",
+]
+
+_lib = None
+
+
+class FlacB200Error(RuntimeError):
+    def __init__(self, code: int, what: str = ""):
+        self.code = code
+        name = lib().flacb200_strerror(code).decode() if _lib is not None else str(code)
+        super().__init__(f"{what}: error {code} ({name})")
+
+
+def lib():
+    """Load libflacb200.so (built in-tree by flac_codec_b200/build.py). Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m flac_codec_b200.build` (nvcc, sm_100a). "
+                          "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64p, u32p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    for n in ("flacb200_options_default", "flacb200_options_fast", "flacb200_options_best"):
+        getattr(L, n).argtypes = [C.POINTER(Options)]
+        getattr(L, n).restype = None
+    L.flacb200_engine_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.flacb200_engine_destroy.argtypes = [vp]
+    L.flacb200_engine_destroy.restype = None
+    L.flacb200_engine_set_stream.argtypes = [vp, vp]
+    L.flacb200_engine_set_chunk_frames.argtypes = [vp, C.c_uint32]
+    L.flacb200_encode.argtypes = [vp, C.POINTER(Options), C.POINTER(StreamParams), vp, C.c_size_t, C.c_int, C.c_int,
+                                  C.c_uint64, C.POINTER(Segment), C.c_size_t, vp, C.c_size_t, C.c_int, u32p, C.c_size_t,
+                                  u64p, u64p]
+    L.flacb200_encode_bound.argtypes = [C.POINTER(Options), C.POINTER(StreamParams), C.POINTER(Segment), C.c_size_t]
+    L.flacb200_encode_bound.restype = C.c_size_t
+    L.flacb200_encode_last_info.argtypes = [vp, C.POINTER(FrameInfo), C.c_size_t, u64p]
+    L.flacb200_decode.argtypes = [vp, C.POINTER(StreamParams), vp, C.c_size_t, C.c_int, C.POINTER(DecodeSegment),
+                                  C.c_size_t, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, u64p, u64p, u64p]
+    L.flacb200_set_profiling.argtypes = [vp, C.c_int]
+    L.flacb200_last_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.flacb200_synth_pcm.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_uint64]
+    L.flacb200_host_alloc.argtypes = [C.c_size_t]
+    L.flacb200_host_alloc.restype = vp
+    L.flacb200_host_free.argtypes = [vp]
+    L.flacb200_host_free.restype = None
+    L.flacb200_device_alloc.argtypes = [vp, C.c_size_t]
+    L.flacb200_device_alloc.restype = vp
+    L.flacb200_device_free.argtypes = [vp, vp]
+    L.flacb200_device_free.restype = None
+    L.flacb200_memcpy.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
+    L.flacb200_synchronize.argtypes = [vp]
+    L.flacb200_strerror.argtypes = [C.c_int]
+    L.flacb200_strerror.restype = C.c_char_p
+    L.flacb200_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise FlacB200Error(code, what)

@@ -1,0 +1,610 @@
+// engine.cu -- host side of libflacb200.so: the C ABI of include/flacb200.h.
+//
+// One engine = one CUDA device + one stream + grow-only scratch.  The engine cuts segments into
+// blocks, uploads PCM once, runs the kernel pipeline of encode_kernels.cu / decode_kernels.cu per
+// launch group and returns frames (or PCM) plus per-frame sizes.  There is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/flacb200.h"
+#include "common.cuh"
+
+namespace flacb200 {
+// encode_kernels.cu
+void launch_planes(const EncCfg&, const FrameDesc*, const uint8_t*, int32_t*, uint32_t*, unsigned long long*, cudaStream_t);
+void launch_lpc(const EncCfg&, const FrameDesc*, const int32_t*, const uint32_t*, const unsigned long long*, const double*, LpcRec*, cudaStream_t);
+bool residual_uses_smem(const EncCfg&);
+cudaError_t launch_residual(const EncCfg&, const FrameDesc*, const int32_t*, const uint32_t*, const unsigned long long*, const LpcRec*, CandRec*,
+                            int32_t*, cudaStream_t);
+void launch_decide_scan(const EncCfg&, const FrameDesc*, const CandRec*, const unsigned long long*, FrameRec*, uint32_t*, unsigned long long*,
+                        uint8_t*, cudaStream_t);
+cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
+// synth.cu
+cudaError_t launch_synth(uint8_t* pcm, unsigned long long first_track, unsigned long long n_tracks, unsigned long long n_pcm_frames,
+                         uint32_t channels, uint32_t sample_rate, uint32_t bps, unsigned long long seed, const int32_t* lut, cudaStream_t st);
+// decode_kernels.cu
+struct DecodeArgs;
+int decode_impl(flacb200_engine* e, const flacb200_stream_params* params, const void* frames, size_t frames_bytes, int frames_location,
+                const flacb200_decode_segment* segments, size_t n_segments, void* pcm_out, size_t pcm_out_bytes, int pcm_kind,
+                int pcm_location, uint64_t planar_stride, uint64_t* n_frames, uint64_t* n_pcm_frames, uint64_t* bad_frame);
+}   // namespace flacb200
+
+using namespace flacb200;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct flacb200_engine {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint32_t chunk_frames = 0;
+    bool profiling = false, keep_info = true;
+    DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, dec[12];
+    std::map<uint32_t, uint32_t> win_off;   // block length -> offset in doubles
+    std::vector<double> win_host;
+    flacb200_options win_opt{};
+    bool win_dirty = false;
+    flacb200_timings tm{};
+    cudaEvent_t ev[32] = {};
+    // last-call debug info
+    std::vector<CandRec> info_cands;
+    std::vector<FrameRec> info_frecs;
+    EncCfg info_cfg{};
+    uint64_t info_frames = 0;
+    void* host_stage = nullptr;
+    size_t host_stage_cap = 0;
+};
+
+static int cuda_err(cudaError_t e) { return e == cudaSuccess ? 0 : FLACB200_E_CUDA_BASE - (int)e; }
+#define CK(x)                                 \
+    do {                                      \
+        cudaError_t _e = (x);                 \
+        if (_e != cudaSuccess) return cuda_err(_e); \
+    } while (0)
+
+static int ensure(DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes + 256);
+        if (e != cudaSuccess) return FLACB200_E_OUT_OF_MEMORY;
+        want = bytes + 256;
+    }
+    b.cap = want;
+    return 0;
+}
+#define ENS(buf, bytes)                  \
+    do {                                 \
+        int _r = ensure(buf, bytes);     \
+        if (_r) return _r;               \
+    } while (0)
+
+extern "C" {
+
+void flacb200_options_default(flacb200_options* o)
+{
+    memset(o, 0, sizeof(*o));
+    o->block_size = 4096;
+    o->max_lpc_order = 8;
+    o->max_partition_order = 5;
+    o->mid_side = 1;
+    o->exhaustive_channel_correlation = 1;
+    o->window_kind = 2;
+    o->tukey_p = 0.5f;
+}
+
+void flacb200_options_fast(flacb200_options* o)
+{
+    flacb200_options_default(o);
+    o->block_size = 1152;
+    o->mid_side = 0;
+    o->max_partition_order = 3;
+    o->max_lpc_order = 0;
+    o->exhaustive_channel_correlation = 0;
+}
+
+void flacb200_options_best(flacb200_options* o)
+{
+    flacb200_options_default(o);
+    o->max_partition_order = 6;
+    o->max_lpc_order = 12;
+}
+
+int flacb200_engine_create(int device, flacb200_engine** out)
+{
+    if (!out) return FLACB200_E_BAD_ARGUMENT;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return FLACB200_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return FLACB200_E_BAD_ARGUMENT;
+    CK(cudaSetDevice(device));
+    flacb200_engine* e = new flacb200_engine();
+    e->device = device;
+    cudaError_t err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) {
+        delete e;
+        return cuda_err(err);
+    }
+    e->stream = e->own_stream;
+    for (auto& ev : e->ev) cudaEventCreate(&ev);
+    *out = e;
+    return 0;
+}
+
+void flacb200_engine_destroy(flacb200_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->pcm, &e->planes, &e->masks, &e->lpcs, &e->cands, &e->frecs, &e->descs, &e->out, &e->fbytes, &e->totals, &e->winpool,
+                      &e->scratch, &e->lut};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (auto& b : e->dec)
+        if (b.p) cudaFree(b.p);
+    for (auto& ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->host_stage) cudaFreeHost(e->host_stage);
+    cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int flacb200_engine_set_stream(flacb200_engine* e, void* cuda_stream)
+{
+    if (!e) return FLACB200_E_BAD_ARGUMENT;
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return 0;
+}
+
+int flacb200_engine_set_chunk_frames(flacb200_engine* e, uint32_t frames)
+{
+    if (!e) return FLACB200_E_BAD_ARGUMENT;
+    e->chunk_frames = frames;
+    return 0;
+}
+
+int flacb200_set_profiling(flacb200_engine* e, int enable)
+{
+    if (!e) return FLACB200_E_BAD_ARGUMENT;
+    e->profiling = enable != 0;
+    return 0;
+}
+
+int flacb200_last_timings(flacb200_engine* e, flacb200_timings* t)
+{
+    if (!e || !t) return FLACB200_E_BAD_ARGUMENT;
+    *t = e->tm;
+    return 0;
+}
+
+static size_t frame_bound(uint32_t n, uint32_t channels, uint32_t bps)
+{
+    // header <= 16 bytes, per subframe 8 + 32 header bits + n * (bps + 1), CRC-16
+    return 16 + (size_t)channels * (((size_t)n * (bps + 1) + 40 + 7) / 8) + 2 + 4;
+}
+
+size_t flacb200_encode_bound(const flacb200_options* opt, const flacb200_stream_params* params, const flacb200_segment* segments,
+                             size_t n_segments)
+{
+    if (!opt || !params || !segments) return 0;
+    size_t total = 0;
+    const uint32_t bs = opt->block_size;
+    for (size_t s = 0; s < n_segments; s++) {
+        const uint64_t nf = bs ? (segments[s].n_pcm_frames + bs - 1) / bs : 0;
+        total += nf * frame_bound(bs, params->channels, params->bits_per_sample);
+    }
+    return total + 64;
+}
+
+}   // extern "C"
+
+// Window::generate (src/encode.rs:1725-1783).  Tables are built on the host with the C library's cos()
+// (what the reference's f64::cos lowers to on Linux) and uploaded: the device never evaluates cos.
+static void make_window(const flacb200_options& o, uint32_t n, double* w)
+{
+    auto fill1 = [&]() { for (uint32_t i = 0; i < n; i++) w[i] = 1.0; };
+    auto hann = [&]() {
+        const double np = (double)n - 1.0;
+        for (uint32_t i = 0; i < n; i++) w[i] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)i / np);
+    };
+    if (o.window_kind == 0) { fill1(); return; }
+    if (o.window_kind == 1) { hann(); return; }
+    float p = o.tukey_p;
+    if (p != p) p = 0.5f;   // NaN -> Tukey(0.5)  :1778
+    if (p <= 0.0f) { fill1(); return; }
+    if (p >= 1.0f) { hann(); return; }
+    const double t = (double)p / 2.0 * (double)n;
+    const uint64_t tt = (uint64_t)t;
+    fill1();
+    if (tt == 0) return;
+    const uint64_t np = tt - 1;
+    if (np > n || np > n - np) return;
+    for (uint64_t k = 0; k < np; k++) {
+        const double x = 0.5 - 0.5 * cos(M_PI * (double)k / (double)np);   // :1764
+        w[k] = x;
+        w[n - 1 - k] = x;
+    }
+}
+
+static uint32_t window_offset(flacb200_engine* e, const flacb200_options& o, uint32_t n)
+{
+    if (memcmp(&e->win_opt, &o, sizeof(o)) != 0 &&
+        (e->win_opt.window_kind != o.window_kind || e->win_opt.tukey_p != o.tukey_p)) {
+        e->win_off.clear();
+        e->win_host.clear();
+    }
+    e->win_opt = o;
+    auto it = e->win_off.find(n);
+    if (it != e->win_off.end()) return it->second;
+    const uint32_t off = (uint32_t)e->win_host.size();
+    e->win_host.resize(off + ((n + 3) & ~3u));
+    make_window(o, n, e->win_host.data() + off);
+    e->win_off[n] = off;
+    e->win_dirty = true;
+    return off;
+}
+
+static void time_mark(flacb200_engine* e, int idx)
+{
+    if (e->profiling) cudaEventRecord(e->ev[idx], e->stream);
+}
+
+extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, const flacb200_stream_params* params, const void* pcm,
+                               size_t pcm_bytes, int pcm_kind, int pcm_location, uint64_t planar_stride, const flacb200_segment* segments,
+                               size_t n_segments, void* out, size_t out_capacity, int out_location, uint32_t* frame_bytes,
+                               size_t frame_bytes_capacity, uint64_t* n_frames_out, uint64_t* total_bytes_out)
+{
+    if (!e || !opt || !params || !segments || (!pcm && pcm_bytes)) return FLACB200_E_BAD_ARGUMENT;
+    if (params->channels < 1 || params->channels > 8) return 30;            // ExcessiveChannels (src/encode.rs:1904-1908)
+    if (params->bits_per_sample < 1 || params->bits_per_sample > 32) return 33;   // InvalidBitsPerSample
+    if (params->sample_rate >= (1u << 20)) return 26;                        // InvalidSampleRate (:1899-1902)
+    if (opt->block_size == 0) return 24;                                     // InvalidBlockSize
+    if (opt->max_lpc_order > 32 || opt->max_partition_order > 15) return FLACB200_E_BAD_ARGUMENT;
+    if (pcm_kind < 0 || pcm_kind > 3) return FLACB200_E_BAD_ARGUMENT;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    memset(&e->tm, 0, sizeof(e->tm));
+
+    EncCfg cfg{};
+    cfg.channels = params->channels;
+    cfg.bps = params->bits_per_sample;
+    cfg.sample_rate = params->sample_rate;
+    cfg.subset = params->subset;
+    cfg.block_size = opt->block_size;
+    cfg.bpad = (opt->block_size + 31u) & ~31u;
+    cfg.max_lpc_order = opt->max_lpc_order;
+    cfg.max_porder = std::min<uint32_t>(opt->max_partition_order, MAX_PORDER);
+    cfg.use_rice2 = cfg.bps > 16;   // src/encode.rs:1965, :1115
+    cfg.pcm_kind = (uint32_t)pcm_kind;
+    cfg.bytes_per_sample = pcm_kind <= 1 ? (cfg.bps + 7) / 8 : 4;
+    cfg.planar_stride = planar_stride;
+    if (cfg.channels == 2 && cfg.bps < 32) {   // side needs bps + 1 <= 32 (:2715, :2473)
+        if (opt->exhaustive_channel_correlation) cfg.mode = opt->mid_side ? MODE_EXH_MID_SIDE : MODE_EXH_SIDE;
+        else cfg.mode = opt->mid_side ? MODE_FAST_MID_SIDE : MODE_FAST_SIDE;
+        cfg.nslots = 4;
+    } else {
+        cfg.mode = MODE_INDEPENDENT;
+        cfg.nslots = cfg.channels;
+    }
+    if (cfg.subset) {   // FlacStreamWriter::write validation (:1128-1137)
+        const uint32_t b = cfg.bps;
+        if (!(b == 8 || b == 12 || b == 16 || b == 20 || b == 24 || b == 32)) return 28;   // NonSubsetBitsPerSample
+        const uint32_t r = cfg.sample_rate;
+        static const uint32_t common[] = {88200, 176400, 192000, 8000, 16000, 22050, 24000, 32000, 44100, 48000, 96000};
+        bool ok = false;
+        for (uint32_t c : common) ok |= (r == c);
+        ok |= (r % 1000 == 0 && r / 1000 < 255) || (r % 10 == 0 && r / 10 < 65535) || r < 65535;
+        if (!ok) return 27;   // NonSubsetSampleRate
+    }
+
+    // ---- cut segments into blocks ----
+    std::vector<FrameDesc> descs;
+    const uint32_t bs = opt->block_size;
+    const size_t sample_bytes = (size_t)cfg.bytes_per_sample;
+    uint64_t max_index = 0;
+    for (size_t s = 0; s < n_segments; s++) {
+        const flacb200_segment& sg = segments[s];
+        uint64_t done = 0, fn = sg.first_frame_number;
+        while (done < sg.n_pcm_frames) {
+            const uint32_t n = (uint32_t)std::min<uint64_t>(bs, sg.n_pcm_frames - done);
+            if (fn > 0xFFFFFFFFFull) return 38;   // ExcessiveFrameNumber
+            FrameDesc d;
+            d.pcm_off = sg.pcm_offset + done;
+            d.fnum = fn++;
+            d.n = n;
+            d.win_off = opt->max_lpc_order ? window_offset(e, *opt, n) : 0;
+            descs.push_back(d);
+            done += n;
+        }
+        max_index = std::max<uint64_t>(max_index, sg.pcm_offset + sg.n_pcm_frames);
+    }
+    const uint64_t nframes = descs.size();
+    if (n_frames_out) *n_frames_out = nframes;
+    if (total_bytes_out) *total_bytes_out = 0;
+    if (nframes == 0) return 0;
+    if (pcm_kind == FLACB200_PCM_I32_PLANAR) {
+        if (max_index > planar_stride || (size_t)planar_stride * cfg.channels * 4 > pcm_bytes) return FLACB200_E_BAD_ARGUMENT;
+    } else if (max_index * cfg.channels * sample_bytes > pcm_bytes) {
+        return FLACB200_E_BAD_ARGUMENT;
+    }
+    const size_t bound = (size_t)nframes * frame_bound(bs, cfg.channels, cfg.bps) + 64;
+
+    // ---- device buffers ----
+    uint32_t chunk = e->chunk_frames ? e->chunk_frames : 2048;
+    chunk = (uint32_t)std::min<uint64_t>(std::min<uint32_t>(chunk, 32768), nframes);
+    const size_t ncand_chunk = (size_t)chunk * cfg.nslots;
+    ENS(e->descs, nframes * sizeof(FrameDesc));
+    ENS(e->planes, ncand_chunk * cfg.bpad * sizeof(int32_t));
+    ENS(e->masks, (size_t)chunk * (cfg.nslots * sizeof(uint32_t) + 4 * sizeof(unsigned long long)) + 64);
+    ENS(e->lpcs, ncand_chunk * sizeof(LpcRec));
+    ENS(e->cands, ncand_chunk * sizeof(CandRec));
+    ENS(e->frecs, (size_t)chunk * sizeof(FrameRec));
+    ENS(e->fbytes, nframes * sizeof(uint32_t));
+    ENS(e->totals, 64);
+    ENS(e->out, bound + 64);
+    const bool need_scratch = !residual_uses_smem(cfg);
+    if (need_scratch) ENS(e->scratch, ncand_chunk * 2 * cfg.bpad * sizeof(int32_t));
+    if (e->win_dirty || (opt->max_lpc_order && e->winpool.cap < e->win_host.size() * sizeof(double))) {
+        ENS(e->winpool, std::max<size_t>(e->win_host.size() * sizeof(double), 64));
+        CK(cudaMemcpyAsync(e->winpool.p, e->win_host.data(), e->win_host.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // win_host is pageable and may be reallocated by a later call
+        e->win_dirty = false;
+    }
+    const uint8_t* d_pcm;
+    if (e->profiling) cudaEventRecord(e->ev[20], st);
+    if (pcm_location == FLACB200_HOST) {
+        ENS(e->pcm, pcm_bytes + 16);
+        CK(cudaMemcpyAsync(e->pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
+        d_pcm = (const uint8_t*)e->pcm.p;
+    } else {
+        d_pcm = (const uint8_t*)pcm;
+    }
+    CK(cudaMemcpyAsync(e->descs.p, descs.data(), nframes * sizeof(FrameDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(e->totals.p, 0, 64, st));
+    if (e->profiling) cudaEventRecord(e->ev[21], st);
+
+    uint32_t* d_ormask = (uint32_t*)e->masks.p;
+    unsigned long long* d_abssum = (unsigned long long*)((uint8_t*)e->masks.p + (((size_t)chunk * cfg.nslots * sizeof(uint32_t) + 15) & ~(size_t)15));
+    const size_t masks_bytes = (((size_t)chunk * cfg.nslots * sizeof(uint32_t) + 15) & ~(size_t)15) + (size_t)chunk * 4 * sizeof(unsigned long long);
+    const bool keep = e->keep_info && nframes <= 65536;
+    if (keep) {
+        e->info_cands.resize(nframes * cfg.nslots);
+        e->info_frecs.resize(nframes);
+        e->info_cfg = cfg;
+        e->info_frames = nframes;
+    } else {
+        e->info_frames = 0;
+    }
+    float kms[8] = {0};
+    uint32_t launches = 0;
+    time_mark(e, 0);
+    cudaEventRecord(e->ev[22], st);
+    for (uint64_t base = 0; base < nframes; base += chunk) {
+        EncCfg c = cfg;
+        c.nframes = (uint32_t)std::min<uint64_t>(chunk, nframes - base);
+        const FrameDesc* dd = (const FrameDesc*)e->descs.p + base;
+        CK(cudaMemsetAsync(e->masks.p, 0, masks_bytes, st));
+        time_mark(e, 1);
+        launch_planes(c, dd, d_pcm, (int32_t*)e->planes.p, d_ormask, d_abssum, st);
+        time_mark(e, 2);
+        launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st);
+        time_mark(e, 3);
+        CK(launch_residual(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p,
+                           (int32_t*)e->scratch.p, st));
+        time_mark(e, 4);
+        launch_decide_scan(c, dd, (const CandRec*)e->cands.p, d_abssum, (FrameRec*)e->frecs.p, (uint32_t*)e->fbytes.p + base,
+                           (unsigned long long*)e->totals.p, (uint8_t*)e->out.p, st);
+        time_mark(e, 5);
+        CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, (uint8_t*)e->out.p, st));
+        time_mark(e, 6);
+        launches += 8;
+        if (keep) {
+            CK(cudaMemcpyAsync(e->info_cands.data() + base * cfg.nslots, e->cands.p, (size_t)c.nframes * cfg.nslots * sizeof(CandRec),
+                               cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(e->info_frecs.data() + base, e->frecs.p, (size_t)c.nframes * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
+        }
+        if (e->profiling) {
+            CK(cudaStreamSynchronize(st));
+            for (int k = 0; k < 5; k++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, e->ev[k + 1], e->ev[k + 2]);
+                kms[k] += ms;
+            }
+        }
+    }
+    cudaEventRecord(e->ev[23], st);
+    CK(cudaGetLastError());
+
+    // ---- results ----
+    unsigned long long totals[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(totals, e->totals.p, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    if (frame_bytes) {
+        const size_t cnt = std::min<size_t>(frame_bytes_capacity, nframes);
+        CK(cudaMemcpyAsync(frame_bytes, e->fbytes.p, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    const uint64_t total = totals[0];
+    if (total_bytes_out) *total_bytes_out = total;
+    if (keep) {
+        for (uint64_t f = 0; f < nframes; f++)
+            if (e->info_frecs[f].err) return FLACB200_E_BAD_ARGUMENT;
+    }
+    if (out) {
+        if (total > out_capacity) return FLACB200_E_OUTPUT_TOO_SMALL;
+        if (e->profiling) cudaEventRecord(e->ev[24], st);
+        CK(cudaMemcpyAsync(out, e->out.p, total, out_location == FLACB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+        if (e->profiling) cudaEventRecord(e->ev[25], st);
+        CK(cudaStreamSynchronize(st));
+    }
+    cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
+    e->tm.launches = launches;
+    if (e->profiling) {
+        for (int k = 0; k < 5; k++) e->tm.kernel_ms[k] = kms[k];
+        cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[20], e->ev[21]);
+        if (out) cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[24], e->ev[25]);
+    }
+    return 0;
+}
+
+extern "C" int flacb200_encode_last_info(flacb200_engine* e, flacb200_frame_info* infos, size_t capacity, uint64_t* n_frames)
+{
+    if (!e) return FLACB200_E_BAD_ARGUMENT;
+    if (n_frames) *n_frames = e->info_frames;
+    if (!infos) return 0;
+    const EncCfg& cfg = e->info_cfg;
+    for (uint64_t f = 0; f < e->info_frames && f < capacity; f++) {
+        const FrameRec& fr = e->info_frecs[f];
+        flacb200_frame_info& fi = infos[f];
+        memset(&fi, 0, sizeof(fi));
+        fi.channel_assignment = fr.assignment;
+        fi.channels = fr.nsub;
+        fi.frame_bytes = fr.frame_bytes;
+        for (uint32_t k = 0; k < fr.nsub; k++) {
+            const CandRec& c = e->info_cands[f * cfg.nslots + fr.slot[k]];
+            flacb200_subframe_info& s = fi.sub[k];
+            s.type = c.type;
+            s.wasted = c.wasted;
+            s.bps = c.bps;
+            s.bits = c.bits;
+            if (c.type >= 2) {
+                s.order = c.order;
+                s.coding_method = c.method;
+                s.partition_order = c.porder_w;
+                for (uint32_t j = 0; j < c.nparts && j < 64; j++) {
+                    const uint8_t r = c.rice[j];
+                    s.kind[j] = r < 0x40 ? 0 : ((r & 0x40) ? 1 : 2);
+                    s.rice[j] = r < 0x40 ? r : (r & 31);
+                }
+            }
+            if (c.type == 3) {
+                s.precision = c.precision;
+                s.shift = c.shift;
+                for (uint32_t j = 0; j < c.order; j++) s.coefs[j] = c.q[j];
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params* params, const void* frames, size_t frames_bytes,
+                               int frames_location, const flacb200_decode_segment* segments, size_t n_segments, void* pcm_out,
+                               size_t pcm_out_bytes, int pcm_kind, int pcm_location, uint64_t planar_stride, uint64_t* n_frames,
+                               uint64_t* n_pcm_frames, uint64_t* bad_frame)
+{
+    return decode_impl(e, params, frames, frames_bytes, frames_location, segments, n_segments, pcm_out, pcm_out_bytes, pcm_kind, pcm_location,
+                       planar_stride, n_frames, n_pcm_frames, bad_frame);
+}
+
+extern "C" int flacb200_synth_pcm(flacb200_engine* e, void* pcm_device, uint64_t first_track, uint64_t n_tracks, uint64_t n_pcm_frames,
+                                  uint32_t channels, uint32_t sample_rate, uint32_t bits_per_sample, uint64_t seed)
+{
+    if (!e || !pcm_device || channels < 1 || channels > 8 || bits_per_sample < 8 || bits_per_sample > 32) return FLACB200_E_BAD_ARGUMENT;
+    CK(cudaSetDevice(e->device));
+    if (!e->lut.p) {
+        ENS(e->lut, 4096 * sizeof(int32_t));
+        std::vector<int32_t> lut(4096);
+        for (int k = 0; k < 4096; k++) lut[k] = (int32_t)llround(sin(2.0 * M_PI * (double)k / 4096.0) * (double)((1 << 30) - 1));
+        CK(cudaMemcpy(e->lut.p, lut.data(), lut.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    CK(launch_synth((uint8_t*)pcm_device, first_track, n_tracks, n_pcm_frames, channels, sample_rate, bits_per_sample, seed,
+                    (const int32_t*)e->lut.p, e->stream));
+    return 0;
+}
+
+extern "C" void* flacb200_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void flacb200_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" void* flacb200_device_alloc(flacb200_engine* e, size_t bytes)
+{
+    if (!e) return nullptr;
+    cudaSetDevice(e->device);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void flacb200_device_free(flacb200_engine* e, void* p)
+{
+    if (e && p) {
+        cudaSetDevice(e->device);
+        cudaFree(p);
+    }
+}
+
+extern "C" int flacb200_memcpy(flacb200_engine* e, void* dst, const void* src, size_t bytes, int kind)
+{
+    if (!e) return FLACB200_E_BAD_ARGUMENT;
+    CK(cudaSetDevice(e->device));
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(dst, src, bytes, k, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int flacb200_synchronize(flacb200_engine* e)
+{
+    if (!e) return FLACB200_E_BAD_ARGUMENT;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" const char* flacb200_strerror(int code)
+{
+    static const char* names[] = {"Ok", "Io", "Utf8", "MissingFlacTag", "MissingStreaminfo", "MultipleStreaminfo", "MultipleSeekTable",
+                                  "MultipleVorbisComment", "InvalidSeekTableSize", "InvalidSeekTablePoint", "Cuesheet", "InvalidPictureType",
+                                  "MultiplePngIcon", "MultipleGeneralIcon", "ReservedMetadataBlock", "InvalidMetadataBlock",
+                                  "InvalidMetadataBlockSize", "InsufficientApplicationBlock", "ExcessiveVorbisEntries", "ExcessiveStringLength",
+                                  "ExcessivePictureSize", "ShortBlock", "ExcessiveBlockSize", "InvalidSyncCode", "InvalidBlockSize",
+                                  "BlockSizeMismatch", "InvalidSampleRate", "NonSubsetSampleRate", "NonSubsetBitsPerSample", "SampleRateMismatch",
+                                  "ExcessiveChannels", "InvalidChannels", "ChannelsMismatch", "InvalidBitsPerSample", "ExcessiveBps",
+                                  "BitsPerSampleMismatch", "InvalidFrameNumber", "InvalidSeek", "ExcessiveFrameNumber", "Crc8Mismatch",
+                                  "Crc16Mismatch", "InvalidSubframeHeader", "InvalidSubframeHeaderType", "ExcessiveWastedBits", "MissingResiduals",
+                                  "InvalidCodingMethod", "InvalidPartitionOrder", "InvalidFixedOrder", "InvalidLpcOrder", "InvalidQlpPrecision",
+                                  "NegativeLpcShift", "NoBestLpcOrder", "InsufficientLpcSamples", "ZeroLpCoefficients", "LpNegativeShiftError",
+                                  "AccumulatorOverflow", "TooManySamples", "ExcessiveTotalSamples", "NoSamples", "SampleCountMismatch",
+                                  "ResidualOverflow", "SamplesNotDivisibleByChannels", "InvalidTotalBytes", "InvalidTotalSamples",
+                                  "ChannelCountMismatch", "ChannelLengthMismatch"};
+    if (code >= 0 && code <= 65) return names[code];
+    switch (code) {
+    case FLACB200_E_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case FLACB200_E_BAD_ARGUMENT: return "bad argument";
+    case FLACB200_E_OUT_OF_MEMORY: return "out of device memory";
+    case FLACB200_E_OUTPUT_TOO_SMALL: return "output buffer too small";
+    default: break;
+    }
+    if (code <= FLACB200_E_CUDA_BASE) return cudaGetErrorString((cudaError_t)(FLACB200_E_CUDA_BASE - code));
+    return "unknown error";
+}
+
+extern "C" const char* flacb200_version(void) { return "flacb200 0.1.0 (sm_100a)"; }

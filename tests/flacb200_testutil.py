@@ -81,7 +81,7 @@ def synth_pcm(track, channels, n, sample_rate, bps, seed=20261017):
             ph = (idx * d0 + ((idx * idx) >> np.uint64(1)) * dd) & np.uint64(0xFFFFFFFF)
             acc += (lut[(ph >> np.uint64(32 - SINE_LUT_BITS)).astype(np.int64)] * np.int64(154)) >> np.int64(10)  # 0.15
             # scale from 31-bit to bps
-            sig = acc >> np.int64(31 - bps)
+            sig = (acc >> np.int64(31 - bps)) if bps <= 31 else (acc << np.int64(bps - 31))
             if c == 1 and base is not None:
                 sig = (base * np.int64(819)) >> np.int64(10)  # 0.8 * channel 0
             if c == 0:
