@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 FLAC frame engine (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            GPU arm (one process per GPU under torchrun)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    reference CPU arm (the oracle port, all host cores)
+
+Workload (BASELINE.json configs[3], "C4"): batch encode of synthetic 3-minute 48 kHz / 24-bit stereo
+tracks at Options::best() (block 4096, max LPC order 12, partition order <= 6), 128 tracks per GPU, so
+8 GPUs encode the 1024 tracks the config names; tracks shard across ranks with no collective (weak
+scaling).  A step = one pass of the encode path over the rank's whole batch.
+  value : Msamples/s (single-channel samples), PCM resident in HBM, frames left in HBM
+  e2e   : same metric through the C ABI with HOST buffers (pinned PCM in, frames out)
+  decode: the decode path over the frames produced by the encode step (reported beside the headline)
+Only the cpu_baseline / --impl reference legs execute anything under oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATE, BPS, CH = 48000, 24, 2
+SECONDS = 180
+TRACKS_PER_GPU = 128
+SEED = 20261017
+METRIC = "encode_msamples_per_s"
+UNIT = "Msamples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tracks-per-gpu", type=int, default=TRACKS_PER_GPU)
+    ap.add_argument("--seconds", type=int, default=SECONDS)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"C4 batch encode: {args.tracks_per_gpu} tracks/GPU x {args.seconds} s {RATE // 1000} kHz/{BPS}-bit "
+                    f"stereo synthetic PCM, Options::best (block 4096, LPC<=12, partition order<=6)",
+        "tracks_total": args.tracks_per_gpu * n_gpus,
+        "tracks_per_gpu": args.tracks_per_gpu,
+        "track_seconds": args.seconds,
+        "sample_rate": RATE, "bits_per_sample": BPS, "channels": CH,
+        "options": "best",
+        "parallelism": f"tracks sharded over {n_gpus} GPU(s), no collective",
+        "l2": "inputs (6.6 GB/GPU) far exceed the 126 MB L2; no flush needed",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the samples taken under load (upper half of the clock samples is the loaded region)
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_encode_rate(pcm_i32_tracks, cores, target_seconds):
+    """Times the oracle (CPU restatement of the reference encoder, frames encoded concurrently the way
+    rayon/file-level parallelism would) on a bounded sample.  Returns (Msamples/s, sample description)."""
+    import numpy as np
+
+    from oracle import oracle as fo
+
+    opt = fo.options("best")
+    # probe 2 s of audio to size the sample
+    probe = pcm_i32_tracks[0][: RATE * 2 * CH]
+    t0 = time.perf_counter()
+    fo.encode_frames_only(opt, RATE, BPS, CH, probe, nthreads=cores)
+    rate = probe.size / (time.perf_counter() - t0)
+    want = int(rate * target_seconds)
+    done, t_total, ntr = 0, 0.0, 0
+    for x in pcm_i32_tracks:
+        take = min(x.size, max(want - done, 0))
+        take -= take % (CH * 4096)
+        if take <= 0:
+            break
+        t0 = time.perf_counter()
+        fo.encode_frames_only(opt, RATE, BPS, CH, x[:take], nthreads=cores)
+        t_total += time.perf_counter() - t0
+        done += take
+        ntr += 1
+    return done / t_total / 1e6, f"{done // CH} PCM frames ({done / CH / RATE:.1f} s of audio) from {ntr} track(s) of the same workload"
+
+
+def host_tracks_numpy(n_tracks, seconds):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from flacb200_testutil import synth_pcm
+
+    return [synth_pcm(t, CH, RATE * seconds, RATE, BPS, SEED).reshape(-1) for t in range(n_tracks)]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    # a bounded sample of the workload: the first track(s), generated by the numpy statement of the generator
+    tracks = host_tracks_numpy(1, min(args.seconds, 60))
+    from oracle import oracle as fo
+
+    opt = fo.options("best")
+    x = tracks[0]
+    t0 = time.perf_counter()
+    fo.encode_frames_only(opt, RATE, BPS, CH, x[: RATE * 2 * CH], nthreads=cores)
+    rate = RATE * 2 * CH / (time.perf_counter() - t0)
+    per_step = int(min(x.size, max(rate * 4.0, CH * 4096 * cores)))   # ~4 s of CPU work per step
+    per_step -= per_step % (CH * 4096)
+    per_step = max(per_step, CH * 4096)
+    for _ in range(args.warmup):
+        fo.encode_frames_only(opt, RATE, BPS, CH, x[:per_step], nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fo.encode_frames_only(opt, RATE, BPS, CH, x[:per_step], nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt / 1e6
+    sample = f"{per_step // CH} PCM frames ({per_step / CH / RATE:.1f} s of one track) per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32/i64 residuals, f64 LPC analysis", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference crate is Rust and cannot be built in this image; this arm times oracle/ (C restatement "
+                "of its encoder, frames encoded concurrently with OpenMP on all host cores)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from flac_codec_b200 import Engine, Options, _abi
+
+    eng = Engine(local)
+    eng.set_keep_info(False)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    opt = Options.best()
+    n_tracks, n = args.tracks_per_gpu, RATE * args.seconds
+    first_track = rank * n_tracks
+    bytes_per_pcm_frame = CH * 3
+    pcm_bytes = n_tracks * n * bytes_per_pcm_frame
+    samples_per_step = n_tracks * n * CH          # single-channel samples this rank encodes per step
+    segs = [(t * n, n, 0) for t in range(n_tracks)]
+    d_pcm = eng.device_alloc(pcm_bytes)
+    eng.synth_pcm(d_pcm, first_track, n_tracks, n, CH, RATE, BPS, SEED)
+    out_cap = pcm_bytes + pcm_bytes // 8 + (1 << 20)
+    d_out = eng.device_alloc(out_cap)
+    eng.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return eng.encode(opt, RATE, BPS, CH, d_pcm, pcm_bytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.DEVICE, out=d_out,
+                          out_capacity=out_cap, out_location=_abi.DEVICE, want_sizes=False)
+
+    eng.set_profiling(True)
+    for _ in range(args.warmup):
+        _, _, flac_bytes = step()
+    clocks = Clocks(local)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = np.zeros(8)
+    kernel_launches = np.zeros(8, dtype=np.int64)
+    launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        _, _, flac_bytes = step()
+        tm = eng.timings()
+        kernel_ms += np.array(list(tm.kernel_ms))
+        kernel_launches += np.array(list(tm.kernel_launches))
+        launches += tm.launches
+    ev1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = samples_per_step * world / (ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel: algorithmic bytes of one launch / its average duration ----
+    names = ["k_planes", "k_lpc", "k_residual", "k_decide+k_scan+k_zero", "k_pack+k_crc16"]
+    top = int(np.argmax(kernel_ms[:5]))
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes_step = pcm_bytes + flac_bytes          # PCM read once + frames written once
+    groups = max(int(kernel_launches[top] // max({0: 1, 1: 1, 2: 1, 3: 3, 4: 2}[top], 1)), 1)
+    avg_ms = kernel_ms[top] / groups                 # average duration of one launch (group) of the top kernel
+    alg_bytes_launch = alg_bytes_step * args.steps / groups
+    achieved = alg_bytes_launch / (avg_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        "algorithmic_bytes_per_sample": alg_bytes_step / samples_per_step,
+        "kernel_share_of_step": {names[k]: kernel_ms[k] / max(kernel_ms[:5].sum(), 1e-9) for k in range(5)},
+        "kernel_ms_per_step": {names[k]: kernel_ms[k] / args.steps for k in range(5)},
+        "whole_path_frac": (alg_bytes_step / (ms_per_step * 1e-3) / 1e9) / peak,
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "i32/i64 residuals, f64 LPC analysis", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clk, "gpu_launches": int(launches), "roofline": roofline,
+        "compression_ratio": flac_bytes / pcm_bytes,
+    }
+
+    # ---- e2e: host PCM -> frames in host memory, copies inside the timed region ----
+    if not args.no_e2e:
+        L = _abi.lib()
+        h_pcm_p = L.flacb200_host_alloc(pcm_bytes)
+        h_out_p = L.flacb200_host_alloc(out_cap)
+        if not h_pcm_p or not h_out_p:
+            raise SystemExit("bench.py: pinned host allocation failed")
+        eng.memcpy(h_pcm_p, d_pcm, pcm_bytes, 2)
+        eng.set_profiling(False)
+
+        def e2e_step():
+            return eng.encode(opt, RATE, BPS, CH, h_pcm_p, pcm_bytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.HOST,
+                              out=h_out_p, out_capacity=out_cap, out_location=_abi.HOST, want_sizes=True)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            _, sizes, total = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(dt.item()) / args.e2e_steps * 1e3
+        line["e2e"] = {"value": samples_per_step * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
+                       "h2d_bytes_per_step": int(pcm_bytes), "d2h_bytes_per_step": int(total + 4 * len(sizes)),
+                       "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+                       "api": "flacb200_encode(host PCM -> host frames + frame sizes)"}
+        L.flacb200_host_free(h_pcm_p)
+        L.flacb200_host_free(h_out_p)
+
+    # ---- CPU baseline on rank 0 at N=1: the oracle on all host cores over a bounded sample ----
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        take = min(n, RATE * 60)
+        host = np.zeros(take * bytes_per_pcm_frame, dtype=np.uint8)
+        eng.memcpy(host, d_pcm, host.nbytes, 2)
+        from oracle import oracle as fo
+
+        x = fo.bytes_to_samples(host.tobytes(), 3)
+        v, sample = cpu_encode_rate([x], cores, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    eng.device_free(d_pcm)
+    eng.device_free(d_out)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

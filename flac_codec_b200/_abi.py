@@ -69,7 +69,7 @@ class Timings(C.Structure):
 
 EXPORTS = [
     "flacb200_options_default", "flacb200_options_fast", "flacb200_options_best", "flacb200_engine_create",
-    "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_encode",
+    "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_engine_set_keep_info", "flacb200_encode",
     "flacb200_encode_bound", "flacb200_encode_last_info", "flacb200_decode", "flacb200_set_profiling",
     "flacb200_last_timings", "flacb200_synth_pcm", "flacb200_host_alloc", "flacb200_host_free",
     "flacb200_device_alloc", "flacb200_device_free", "flacb200_memcpy", "flacb200_synchronize", "flacb200_strerror",
@@ -104,6 +104,7 @@ def lib():
     L.flacb200_engine_destroy.restype = None
     L.flacb200_engine_set_stream.argtypes = [vp, vp]
     L.flacb200_engine_set_chunk_frames.argtypes = [vp, C.c_uint32]
+    L.flacb200_engine_set_keep_info.argtypes = [vp, C.c_int]
     L.flacb200_encode.argtypes = [vp, C.POINTER(Options), C.POINTER(StreamParams), vp, C.c_size_t, C.c_int, C.c_int,
                                   C.c_uint64, C.POINTER(Segment), C.c_size_t, vp, C.c_size_t, C.c_int, u32p, C.c_size_t,
                                   u64p, u64p]

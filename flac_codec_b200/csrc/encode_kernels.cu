@@ -737,6 +737,7 @@ __global__ void __launch_bounds__(1024) k_scan(uint32_t nframes, FrameRec* __res
         if (f < nframes) {
             frecs[f].out_off = carry + wsum[wid] + (incl - v);
             if (frame_bytes_out) frame_bytes_out[f] = (uint32_t)v;
+            if (frecs[f].err) totals[3] = 1;   // sticky error word read back by the host
         }
         carry += tile_total;
         __syncthreads();

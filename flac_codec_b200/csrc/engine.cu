@@ -53,6 +53,7 @@ struct flacb200_engine {
     bool win_dirty = false;
     flacb200_timings tm{};
     cudaEvent_t ev[32] = {};
+    std::vector<cudaEvent_t> evpool;   // per-kernel timing events (profiling only), grown on demand
     // last-call debug info
     std::vector<CandRec> info_cands;
     std::vector<FrameRec> info_frecs;
@@ -159,6 +160,7 @@ void flacb200_engine_destroy(flacb200_engine* e)
         if (b.p) cudaFree(b.p);
     for (auto& ev : e->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->evpool) cudaEventDestroy(ev);
     if (e->host_stage) cudaFreeHost(e->host_stage);
     cudaStreamDestroy(e->own_stream);
     delete e;
@@ -175,6 +177,13 @@ int flacb200_engine_set_chunk_frames(flacb200_engine* e, uint32_t frames)
 {
     if (!e) return FLACB200_E_BAD_ARGUMENT;
     e->chunk_frames = frames;
+    return 0;
+}
+
+int flacb200_engine_set_keep_info(flacb200_engine* e, int enable)
+{
+    if (!e) return FLACB200_E_BAD_ARGUMENT;
+    e->keep_info = enable != 0;
     return 0;
 }
 
@@ -259,9 +268,17 @@ static uint32_t window_offset(flacb200_engine* e, const flacb200_options& o, uin
     return off;
 }
 
-static void time_mark(flacb200_engine* e, int idx)
+// per-kernel timing: events are recorded back to back on the engine's stream and read after the call's
+// final synchronisation, so profiling adds no host synchronisation inside the timed region
+static void time_mark(flacb200_engine* e, size_t idx)
 {
-    if (e->profiling) cudaEventRecord(e->ev[idx], e->stream);
+    if (!e->profiling) return;
+    while (e->evpool.size() <= idx) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->evpool.push_back(ev);
+    }
+    cudaEventRecord(e->evpool[idx], e->stream);
 }
 
 extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, const flacb200_stream_params* params, const void* pcm,
@@ -381,7 +398,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     uint32_t* d_ormask = (uint32_t*)e->masks.p;
     unsigned long long* d_abssum = (unsigned long long*)((uint8_t*)e->masks.p + (((size_t)chunk * cfg.nslots * sizeof(uint32_t) + 15) & ~(size_t)15));
     const size_t masks_bytes = (((size_t)chunk * cfg.nslots * sizeof(uint32_t) + 15) & ~(size_t)15) + (size_t)chunk * 4 * sizeof(unsigned long long);
-    const bool keep = e->keep_info && nframes <= 65536;
+    const bool keep = e->keep_info && nframes <= 65536;   // flacb200_engine_set_keep_info
     if (keep) {
         e->info_cands.resize(nframes * cfg.nslots);
         e->info_frecs.resize(nframes);
@@ -390,48 +407,41 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     } else {
         e->info_frames = 0;
     }
-    float kms[8] = {0};
     uint32_t launches = 0;
-    time_mark(e, 0);
+    size_t nchunks = 0;
     cudaEventRecord(e->ev[22], st);
     for (uint64_t base = 0; base < nframes; base += chunk) {
         EncCfg c = cfg;
         c.nframes = (uint32_t)std::min<uint64_t>(chunk, nframes - base);
         const FrameDesc* dd = (const FrameDesc*)e->descs.p + base;
         CK(cudaMemsetAsync(e->masks.p, 0, masks_bytes, st));
-        time_mark(e, 1);
+        const size_t eb = nchunks * 6;
+        time_mark(e, eb + 0);
         launch_planes(c, dd, d_pcm, (int32_t*)e->planes.p, d_ormask, d_abssum, st);
-        time_mark(e, 2);
+        time_mark(e, eb + 1);
         launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st);
-        time_mark(e, 3);
+        time_mark(e, eb + 2);
         CK(launch_residual(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p,
                            (int32_t*)e->scratch.p, st));
-        time_mark(e, 4);
+        time_mark(e, eb + 3);
         launch_decide_scan(c, dd, (const CandRec*)e->cands.p, d_abssum, (FrameRec*)e->frecs.p, (uint32_t*)e->fbytes.p + base,
                            (unsigned long long*)e->totals.p, (uint8_t*)e->out.p, st);
-        time_mark(e, 5);
+        time_mark(e, eb + 4);
         CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, (uint8_t*)e->out.p, st));
-        time_mark(e, 6);
+        time_mark(e, eb + 5);
+        nchunks++;
         launches += 8;
         if (keep) {
             CK(cudaMemcpyAsync(e->info_cands.data() + base * cfg.nslots, e->cands.p, (size_t)c.nframes * cfg.nslots * sizeof(CandRec),
                                cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(e->info_frecs.data() + base, e->frecs.p, (size_t)c.nframes * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
         }
-        if (e->profiling) {
-            CK(cudaStreamSynchronize(st));
-            for (int k = 0; k < 5; k++) {
-                float ms = 0;
-                cudaEventElapsedTime(&ms, e->ev[k + 1], e->ev[k + 2]);
-                kms[k] += ms;
-            }
-        }
     }
     cudaEventRecord(e->ev[23], st);
     CK(cudaGetLastError());
 
     // ---- results ----
-    unsigned long long totals[3] = {0, 0, 0};
+    unsigned long long totals[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(totals, e->totals.p, sizeof(totals), cudaMemcpyDeviceToHost, st));
     if (frame_bytes) {
         const size_t cnt = std::min<size_t>(frame_bytes_capacity, nframes);
@@ -440,10 +450,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     CK(cudaStreamSynchronize(st));
     const uint64_t total = totals[0];
     if (total_bytes_out) *total_bytes_out = total;
-    if (keep) {
-        for (uint64_t f = 0; f < nframes; f++)
-            if (e->info_frecs[f].err) return FLACB200_E_BAD_ARGUMENT;
-    }
+    if (totals[3]) return FLACB200_E_BAD_ARGUMENT;   // a frame referenced a candidate that was never encoded
     if (out) {
         if (total > out_capacity) return FLACB200_E_OUTPUT_TOO_SMALL;
         if (e->profiling) cudaEventRecord(e->ev[24], st);
@@ -454,7 +461,14 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
     e->tm.launches = launches;
     if (e->profiling) {
-        for (int k = 0; k < 5; k++) e->tm.kernel_ms[k] = kms[k];
+        static const uint32_t per_chunk[5] = {1, 1, 1, 3, 2};   // planes, lpc, residual, decide+scan+zero, pack+crc16
+        for (size_t ck = 0; ck < nchunks; ck++)
+            for (int k = 0; k < 5; k++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, e->evpool[ck * 6 + k], e->evpool[ck * 6 + k + 1]);
+                e->tm.kernel_ms[k] += ms;
+                e->tm.kernel_launches[k] += per_chunk[k];
+            }
         cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[20], e->ev[21]);
         if (out) cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[24], e->ev[25]);
     }

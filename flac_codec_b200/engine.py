@@ -121,6 +121,9 @@ class Engine:
     def set_chunk_frames(self, n: int):
         check(_abi.lib().flacb200_engine_set_chunk_frames(self._h, n), "set_chunk_frames")
 
+    def set_keep_info(self, on: bool):
+        check(_abi.lib().flacb200_engine_set_keep_info(self._h, int(on)), "set_keep_info")
+
     def set_profiling(self, on: bool):
         check(_abi.lib().flacb200_set_profiling(self._h, int(on)), "set_profiling")
 

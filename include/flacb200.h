@@ -86,6 +86,9 @@ void flacb200_engine_destroy(flacb200_engine* e);
 int flacb200_engine_set_stream(flacb200_engine* e, void* cuda_stream);
 /* Frames processed per internal launch group (bounds scratch memory); 0 = default */
 int flacb200_engine_set_chunk_frames(flacb200_engine* e, uint32_t frames);
+/* Keep per-subframe decisions of each encode call for flacb200_encode_last_info (default on, calls of
+ * at most 65536 frames); switch off on throughput paths -- it costs a device-to-host copy per group. */
+int flacb200_engine_set_keep_info(flacb200_engine* e, int enable);
 
 /*
  * Encode: batch form of Encoder::encode / encode_frame (src/encode.rs:1997, :2259) and, with
@@ -156,7 +159,7 @@ int flacb200_decode(flacb200_engine* e, const flacb200_stream_params* params, co
 typedef struct flacb200_timings {
     float total_ms;        /* first kernel launch to last kernel end */
     float h2d_ms, d2h_ms;  /* copies, when the call had host buffers */
-    float kernel_ms[8];    /* encode: planes, lpc, residual, decide+scan, pack; decode: index, parse, restore, emit */
+    float kernel_ms[8];    /* encode: planes, lpc, residual, decide+scan+zero, pack+crc16; decode: see DESIGN.md */
     uint32_t kernel_launches[8];
     uint32_t launches;     /* kernels launched by the call */
 } flacb200_timings;

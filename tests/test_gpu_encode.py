@@ -1,0 +1,263 @@
+"""GPU encode parity (through the C ABI): frames must be byte-identical to the CPU oracle's for the
+same blocks and options, and must decode losslessly through the oracle's (independently pinned)
+decoder.  The matrix replays the reference's tests/format.rs cases."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from flacb200_testutil import ROOT, generate_sine_1, generate_sine_2, ref_file, synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from flac_codec_b200 import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def fo():
+    from oracle import oracle
+
+    return oracle
+
+
+def _probe():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_probe
+
+    return parity_probe
+
+
+def check(eng, fo, opt, rate, bps, channels, x, label="", first_frame_number=0, pcm_kind=None):
+    """GPU frames == oracle frames, and oracle-decode(GPU frames) == x."""
+    x = np.ascontiguousarray(x, dtype=np.int32).reshape(-1)
+    same, n, gpu, ref = _probe().compare(eng, opt, rate, bps, channels, x, label, first_frame_number, verbose=True,
+                                         pcm_kind=pcm_kind)
+    assert same == n, f"{label}: {same}/{n} frames identical"
+    assert gpu == ref
+    # lossless through the oracle decoder, frame by frame (subset semantics: no STREAMINFO needed
+    # when the header carries rate and bps; otherwise give it a STREAMINFO)
+    si = fo.Streaminfo()
+    si.min_block_size = si.max_block_size = opt.c.block_size
+    si.sample_rate, si.channels, si.bps = rate, channels, bps
+    si.total_samples = x.size // channels
+    pos, done = 0, 0
+    total = x.size // channels
+    while done < total:
+        planar, h, used = fo.decode_frame(gpu[pos:], si, total - done)
+        blk = x.reshape(-1, channels)[done:done + h.block_size].T
+        assert np.array_equal(planar, blk), f"{label}: frame at byte {pos} does not round-trip"
+        pos += used
+        done += h.block_size
+    assert pos == len(gpu)
+
+
+def test_bench_signals_all_presets(eng, fo):
+    from flac_codec_b200 import Options
+
+    cases = [
+        ("16b stereo default", Options.default(), 44100, 16, 2, synth_pcm(0, 2, 44100 * 2 + 100, 44100, 16)),
+        ("24b stereo best", Options.best(), 48000, 24, 2, synth_pcm(1, 2, 48000 * 2 + 77, 48000, 24)),
+        ("16b mono default", Options.default(), 44100, 16, 1, synth_pcm(2, 1, 50000, 44100, 16)),
+        ("16b stereo fast", Options.fast(), 44100, 16, 2, synth_pcm(3, 2, 50000, 44100, 16)),
+        ("24b 8ch best", Options.best(), 96000, 24, 8, synth_pcm(4, 8, 20000, 96000, 24)),
+        ("32b stereo best lpc32", Options.best().max_lpc_order(32), 192000, 32, 2, synth_pcm(5, 2, 30000, 192000, 32)),
+        ("16b stereo no-mid-side", Options.default().mid_side(False), 44100, 16, 2, synth_pcm(6, 2, 30000, 44100, 16)),
+        ("16b stereo fast-corr mid-side", Options.default().fast_channel_correlation(True), 44100, 16, 2,
+         synth_pcm(7, 2, 30000, 44100, 16)),
+        ("16b stereo hann", Options.default().window("hann"), 44100, 16, 2, synth_pcm(8, 2, 20000, 44100, 16)),
+        ("16b stereo rectangle", Options.default().window("rectangle"), 44100, 16, 2, synth_pcm(9, 2, 20000, 44100, 16)),
+        ("12b mono streaminfo-bps", Options.default(), 37, 13, 1, synth_pcm(10, 1, 9000, 44100, 13)),
+    ]
+    for label, opt, rate, bps, ch, x in cases:
+        check(eng, fo, opt, rate, bps, ch, x, label)
+
+
+# tests/format.rs:208 test_roundtrip (36 fixtures x 3 presets)
+@pytest.mark.parametrize("channels", [1, 2, 4, 8])
+@pytest.mark.parametrize("bps", [8, 16, 24])
+def test_reference_roundtrip_fixtures(eng, fo, channels, bps):
+    from flac_codec_b200 import Options
+
+    for frames in (1, 111, 4777):
+        raw = ref_file(f"roundtrip-{channels}-{bps}-{frames}.raw")
+        x = fo.bytes_to_samples(raw, bps // 8)
+        for preset in ("default", "fast", "best"):
+            check(eng, fo, Options(preset), 44100, bps, channels, x, f"roundtrip-{channels}-{bps}-{frames} {preset}")
+
+
+# tests/format.rs:85 test_blocksize_variations
+def test_blocksize_variations(eng, fo):
+    from flac_codec_b200 import Options
+
+    data = fo.bytes_to_samples(ref_file("noise32.raw"), 1)
+    for blocksize in range(16, 34):
+        for lpc_order in [0, 1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32]:
+            opt = Options.best().max_lpc_order(lpc_order or None).block_size(blocksize)
+            check(eng, fo, opt, 44100, 8, 1, data, f"bs{blocksize} lpc{lpc_order}")
+
+
+# tests/format.rs:137 test_fractional
+def test_fractional(eng, fo):
+    from flac_codec_b200 import Options
+
+    rng = np.random.default_rng(42)
+    noise = rng.integers(-32768, 32767, size=16390 * 2, endpoint=True).astype(np.int32)
+    cases = [(33, [31, 32, 33, 34, 35, 2046, 2049]), (256, [254, 255, 256, 257, 258, 511, 513, 4098]),
+             (2048, [1022, 2047, 2048, 2049, 4097]), (4608, [1023, 4607, 4608, 4609, 8193, 16386])]
+    for blocksize, counts in cases:
+        opt = Options.default().block_size(blocksize)
+        for samples in counts:
+            check(eng, fo, opt, 44100, 16, 2, noise[: samples * 2], f"fractional bs{blocksize} n{samples}")
+
+
+# tests/format.rs:438 test_full_scale_deflection
+@pytest.mark.parametrize("bps", [8, 16, 24, 32])
+def test_full_scale_deflection(eng, fo, bps):
+    from flac_codec_b200 import Options
+
+    hi, lo = (1 << (bps - 1)) - 1, -(1 << (bps - 1))
+    patterns = [[hi] * 2, [lo] * 2, [hi, lo], [lo, hi], [hi, hi, lo], [lo, lo, hi], [hi, lo, lo], [lo, hi, hi],
+                [hi, hi, lo, lo], [hi, lo, hi, hi, lo, lo, hi]]
+    for k, pat in enumerate(patterns):
+        x = np.array((pat * 1200)[:4096 + 37], dtype=np.int32)
+        for preset in ("default", "best"):
+            check(eng, fo, Options(preset), 44100, bps, 1, x, f"fsd{bps} p{k} mono {preset}")
+            check(eng, fo, Options(preset), 44100, bps, 2, x[: 2 * (len(x) // 2)], f"fsd{bps} p{k} stereo {preset}")
+
+
+# tests/format.rs:624 test_wasted_bits
+def test_wasted_bits(eng, fo):
+    from flac_codec_b200 import Options
+
+    x = fo.bytes_to_samples(ref_file("wasted-bits.raw"), 2)
+    check(eng, fo, Options.default(), 44100, 16, 1, x, "wasted-bits")
+    infos, n = eng.last_info()
+    assert n == 1 and infos[0].sub[0].wasted == 2
+
+
+# tests/format.rs:777 test_sine_wave_streams
+@pytest.mark.parametrize("bps", [8, 16, 24, 32])
+def test_sine_streams(eng, fo, bps):
+    from flac_codec_b200 import Options
+
+    fs = float((1 << (bps - 1)) - 1)
+    for f1, a1, f2, a2 in [(441.0, 0.50, 441.0, 0.49), (441.0, 0.61, 661.5, 0.37), (8820.0, 0.70, 4410.0, 0.29)]:
+        x = generate_sine_1(fs, 48000.0, 20000, f1, a1, f2, a2)
+        check(eng, fo, Options.default(), 48000, bps, 1, x, f"sine1 {bps} {f1}")
+    for f1, a1, f2, a2, fm in [(441.0, 0.50, 441.0, 0.49, 1.0), (441.0, 0.61, 661.5, 0.37, 2.0),
+                               (8820.0, 0.70, 4410.0, 0.29, 0.5)]:
+        x = generate_sine_2(fs, 44100.0, 20000, f1, a1, f2, a2, fm)
+        for preset in ("default", "best", "fast"):
+            check(eng, fo, Options(preset), 44100, bps, 2, x, f"sine2 {bps} {f1} {preset}")
+
+
+# tests/format.rs:1248-1384 test_noise_*
+@pytest.mark.parametrize("bps", [8, 16, 24, 32])
+@pytest.mark.parametrize("channels", [1, 2, 4, 8])
+def test_noise(eng, fo, bps, channels):
+    from flac_codec_b200 import Options
+
+    rng = np.random.default_rng(bps * 10 + channels)
+    lo, hi = -(1 << (bps - 1)), (1 << (bps - 1)) - 1
+    n = 70000
+    x = rng.integers(lo, hi, size=n * channels, endpoint=True).astype(np.int64).astype(np.int32)
+    for preset, bs in (("default", 4096), ("fast", 32), ("best", 32768), ("default", 65535)):
+        m = n if bs >= 4096 else 1000
+        check(eng, fo, Options(preset).block_size(bs), 44100, bps, channels, x[: m * channels], f"noise {bps}/{channels} {preset} {bs}")
+
+
+def test_pcm_layouts_and_frame_numbers(eng, fo):
+    """bytes LE/BE, i32 interleaved and planar inputs give the same frames; frame numbers beyond one
+    UTF-8 byte are coded like the reference (src/stream.rs:1266-1326)."""
+    from flac_codec_b200 import Options, _abi
+
+    x = synth_pcm(11, 2, 30000, 48000, 24)
+    for kind in (_abi.PCM_BYTES_LE, _abi.PCM_BYTES_BE, _abi.PCM_I32_INTERLEAVED):
+        check(eng, fo, Options.best(), 48000, 24, 2, x, f"layout {kind}", pcm_kind=kind)
+    check(eng, fo, Options.default(), 44100, 16, 2, synth_pcm(12, 2, 9000, 44100, 16), "fn 127", first_frame_number=126)
+    check(eng, fo, Options.default(), 44100, 16, 2, synth_pcm(12, 2, 9000, 44100, 16), "fn 2^31", first_frame_number=(1 << 31) - 1)
+    # planar
+    planar = np.ascontiguousarray(x.T)
+    ref, ref_sizes = fo.encode_frames_only(fo.options("best"), 48000, 24, 2, x.reshape(-1))
+    data, sizes, total = eng.encode(Options.best(), 48000, 24, 2, planar, planar.nbytes, _abi.PCM_I32_PLANAR,
+                                    [(0, x.shape[0], 0)], planar_stride=x.shape[0])
+    assert data.tobytes() == ref
+
+
+def test_multi_segment_batch_and_device_buffers(eng, fo):
+    """Several tracks in one call (the C4 shape), PCM generated on the device, output left on the device."""
+    from flac_codec_b200 import Options, _abi
+
+    rate, bps, ch, n, tracks = 48000, 24, 2, 48000 + 1234, 5
+    nbytes = tracks * n * ch * 3
+    d_pcm = eng.device_alloc(nbytes)
+    eng.synth_pcm(d_pcm, 3, tracks, n, ch, rate, bps)
+    host = np.zeros(nbytes, dtype=np.uint8)
+    eng.memcpy(host, d_pcm, nbytes, 2)
+    # the device generator is bit-identical to the numpy statement
+    for t in range(tracks):
+        want = synth_pcm(3 + t, ch, n, rate, bps)
+        got = fo.bytes_to_samples(host[t * n * ch * 3:(t + 1) * n * ch * 3].tobytes(), 3).reshape(-1, ch)
+        assert np.array_equal(got, want), f"synth track {t}"
+    segs = [(t * n, n, 0) for t in range(tracks)]
+    opt = Options.best()
+    cap = 2 * nbytes
+    d_out = eng.device_alloc(cap)
+    _, sizes, total = eng.encode(opt, rate, bps, ch, d_pcm, nbytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.DEVICE,
+                                 out=d_out, out_capacity=cap, out_location=_abi.DEVICE)
+    got = np.zeros(total, dtype=np.uint8)
+    eng.memcpy(got, d_out, total, 2)
+    ref = b""
+    for t in range(tracks):
+        r, _ = fo.encode_frames_only(fo.options("best"), rate, bps, ch, synth_pcm(3 + t, ch, n, rate, bps).reshape(-1))
+        ref += r
+    assert got.tobytes() == ref
+    eng.device_free(d_pcm)
+    eng.device_free(d_out)
+    # small launch groups give the same bytes
+    eng.set_chunk_frames(7)
+    data, sizes2, total2 = eng.encode(opt, rate, bps, ch, host, nbytes, _abi.PCM_BYTES_LE, segs)
+    eng.set_chunk_frames(0)
+    assert data.tobytes() == ref and sizes2.tolist() == sizes.tolist()
+
+
+def test_subset_stream_writer_semantics(eng, fo):
+    """FlacStreamWriter::write (src/encode.rs:1094): subset header rules and errors."""
+    from flac_codec_b200 import Options, _abi
+
+    x = synth_pcm(13, 2, 4096, 44100, 16)
+    raw = np.frombuffer(fo.samples_to_bytes(x.reshape(-1), 2), dtype=np.uint8).copy()
+    data, sizes, total = eng.encode(Options.default(), 44100, 16, 2, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, 4096, 5)],
+                                    subset=True)
+    planar = np.ascontiguousarray(x.T)
+    ref = fo.encode_frame(fo.options("default"), 44100, 16, planar, frame_number=5, subset=True)
+    assert data.tobytes() == ref
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.encode(Options.default(), 44100, 13, 2, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, 4096, 0)], subset=True)
+    assert ei.value.code == 28   # NonSubsetBitsPerSample
+
+
+def test_argument_errors(eng):
+    from flac_codec_b200 import Options, _abi
+
+    raw = np.zeros(64, dtype=np.uint8)
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.encode(Options.default(), 44100, 16, 9, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, 1, 0)])
+    assert ei.value.code == 30   # ExcessiveChannels
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.encode(Options.default(), 44100, 33, 2, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, 1, 0)])
+    assert ei.value.code == 33   # InvalidBitsPerSample
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.encode(Options.default(), 44100, 16, 2, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, 1000, 0)])
+    assert ei.value.code == -2   # pcm buffer too small
+    # empty input: no frames, no error
+    data, sizes, total = eng.encode(Options.default(), 44100, 16, 2, raw, 0, _abi.PCM_BYTES_LE, [(0, 0, 0)])
+    assert total == 0 and len(sizes) == 0
