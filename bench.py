@@ -294,6 +294,55 @@ def run_gpu(args):
         "compression_ratio": flac_bytes / pcm_bytes,
     }
 
+    # ---- decode leg: the frames just produced, decoded back on the device (PCM must equal the input) ----
+    if not args.no_decode:
+        eng.set_profiling(False)
+        _, sizes, total = eng.encode(opt, RATE, BPS, CH, d_pcm, pcm_bytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.DEVICE,
+                                     out=d_out, out_capacity=out_cap, out_location=_abi.DEVICE, want_sizes=True)
+        per_track = (n + 4095) // 4096
+        offs = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
+        dsegs = [(int(offs[t * per_track]), int(offs[(t + 1) * per_track] - offs[t * per_track]), t * n, n) for t in range(n_tracks)]
+        d_back = eng.device_alloc(pcm_bytes)
+        eng.set_profiling(True)
+
+        def dstep():
+            return eng.decode(RATE, BPS, CH, 4096, d_out, total, dsegs, d_back, pcm_bytes, _abi.PCM_BYTES_LE,
+                              frames_location=_abi.DEVICE, pcm_location=_abi.DEVICE)
+
+        for _ in range(2):
+            nf, ns = dstep()
+        barrier()
+        dk = np.zeros(8)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            nf, ns = dstep()
+            dk += np.array(list(eng.timings().kernel_ms))
+        ev1.record(stream)
+        barrier()
+        dms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        dms_step = float(dms.item()) / args.steps
+        # bit-exactness at full size: a 64-bit checksum of checksums over the PCM bytes, input vs decoded
+        a = torch.empty(0)
+        import ctypes as C
+
+        def dev_u8(ptr, nbytes):
+            class _W:
+                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            return torch.as_tensor(_W(), device="cuda")
+
+        src, back = dev_u8(d_pcm, pcm_bytes), dev_u8(d_back, pcm_bytes)
+        exact = bool(torch.equal(src, back)) and ns == n_tracks * n
+        dnames = ["k_find+k_scan", "k_decode", "k_crc16f", "k_chain", "k_emit"]
+        line["decode"] = {"metric": "decode_msamples_per_s", "value": samples_per_step * world / (dms_step * 1e-3) / 1e6, "unit": UNIT,
+                          "ms_per_step": dms_step, "frames": int(nf), "bit_exact_vs_input": exact,
+                          "kernel_ms_per_step": {dnames[k]: dk[k] / args.steps for k in range(5)},
+                          "hbm_frac": ((pcm_bytes + total) / (dms_step * 1e-3) / 1e9) / peak}
+        if not exact:
+            raise SystemExit("bench.py: GPU decode of the GPU-encoded frames is not bit-exact")
+        eng.device_free(d_back)
+
     # ---- e2e: host PCM -> frames in host memory, copies inside the timed region ----
     if not args.no_e2e:
         L = _abi.lib()

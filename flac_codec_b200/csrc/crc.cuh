@@ -1,0 +1,97 @@
+// crc.cuh -- warp-cooperative CRC-16 (poly 0x8005, init 0, MSB first; src/crc.rs:144-188).
+//
+// A frame is read as coalesced 32-bit words: lane l owns words l, l+32, l+64, ... of the frame body and
+// folds them with Horner steps  acc = acc * x^1024 + F(word)  (x^1024: the 128 bytes between two words of
+// one lane), F(word) = word(x) * x^16 mod P.  The 32 lane results are shifted to the end of the message
+// with x^(32 d) (d = words that follow the lane's last word) and XOR-reduced.  All constants live in a
+// small shared-memory block built once per CTA.
+#pragma once
+#include "common.cuh"
+
+namespace flacb200 {
+
+struct Crc16Tables {
+    uint16_t byte_tab[256];   // classic table: crc of one byte
+    uint16_t mul_lo[256];     // (i) * x^1024 mod P
+    uint16_t mul_hi[256];     // (i << 8) * x^1024 mod P
+    uint16_t xd[33];          // x^(32 d) mod P, d = 0..32
+    uint16_t xb[4];           // x^(8 t) mod P, t = 0..3
+};
+
+// x^(8 n) mod P by square-and-multiply
+__device__ inline uint32_t gf16_xpow8(uint32_t n)
+{
+    uint32_t r = 1, b = 0x0100;   // x^8
+    while (n) {
+        if (n & 1u) r = gf16_mulmod(r, b);
+        b = gf16_mulmod(b, b);
+        n >>= 1;
+    }
+    return r;
+}
+
+// all threads of the CTA call this once (followed by __syncthreads by the caller)
+__device__ inline void crc16_tables_init(Crc16Tables& t)
+{
+    const uint32_t x1024 = gf16_xpow8(128);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        t.byte_tab[i] = crc16_table_entry(i);
+        t.mul_lo[i] = (uint16_t)gf16_mulmod(i, x1024);
+        t.mul_hi[i] = (uint16_t)gf16_mulmod(i << 8, x1024);
+    }
+    for (uint32_t i = threadIdx.x; i < 33; i += blockDim.x) t.xd[i] = (uint16_t)gf16_xpow8(4 * i);
+    if (threadIdx.x < 4) t.xb[threadIdx.x] = (uint16_t)gf16_xpow8(threadIdx.x);
+}
+
+__device__ inline uint32_t crc16_byte(const Crc16Tables& t, uint32_t crc, uint32_t b)
+{
+    return (t.byte_tab[((crc >> 8) ^ b) & 0xff] ^ (crc << 8)) & 0xffffu;
+}
+
+// CRC-16 of bytes[start, start + len) computed by one warp (all 32 lanes must call; all get the result).
+// `bytes` must be 4-byte aligned (the buffer base); start and len are arbitrary.
+__device__ inline uint32_t crc16_warp(const Crc16Tables& t, const uint8_t* __restrict__ bytes, unsigned long long start,
+                                      unsigned long long len)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long end = start + len;
+    unsigned long long a = (start + 3) & ~3ull;   // first aligned byte
+    if (a > end) a = end;
+    const uint32_t head = (uint32_t)(a - start);
+    const unsigned long long nwords = (end - a) >> 2;
+    const uint32_t tail = (uint32_t)((end - a) & 3);
+    uint32_t acc = 0;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(bytes + a);
+    unsigned long long last = 0;
+    bool any = false;
+    for (unsigned long long i = lane; i < nwords; i += 32) {
+        const uint32_t v = w[i];   // memory order = message order: byte 0 is the low byte
+        uint32_t f = t.byte_tab[v & 0xff];
+        f = crc16_byte(t, f, (v >> 8) & 0xff);
+        f = crc16_byte(t, f, (v >> 16) & 0xff);
+        f = crc16_byte(t, f, v >> 24);
+        acc = (t.mul_hi[acc >> 8] ^ t.mul_lo[acc & 0xff]) ^ f;
+        last = i;
+        any = true;
+    }
+    uint32_t part = 0;
+    if (any) {
+        const unsigned long long after = nwords - 1 - last;   // words that follow this lane's last word (0..31)
+        part = gf16_mulmod(acc, t.xd[(uint32_t)after]);
+        if (tail) part = gf16_mulmod(part, t.xb[tail]);
+    }
+    if (lane == 0) {
+        // head bytes sit before everything else: shift them over body and tail
+        uint32_t h = 0;
+        for (uint32_t i = 0; i < head; i++) h = crc16_byte(t, h, bytes[start + i]);
+        if (head && (nwords || tail)) h = gf16_mulmod(h, gf16_xpow8((uint32_t)(nwords * 4 + tail)));
+        uint32_t tl = 0;
+        for (uint32_t i = 0; i < tail; i++) tl = crc16_byte(t, tl, bytes[a + nwords * 4 + i]);
+        part ^= h ^ tl;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
+    return part & 0xffffu;
+}
+
+}   // namespace flacb200

@@ -1,0 +1,45 @@
+// decode.cuh -- structures shared by the decode kernels (decode_kernels.cu) and the host engine (engine.cu).
+#pragma once
+#include "common.cuh"
+
+namespace flacb200 {
+
+struct DecCfg {
+    uint32_t channels, bps, sample_rate, subset, max_block_size;
+    uint32_t nslots;    // scratch planes per frame: channels (+1 "high word" plane for a 33-bit side channel)
+    uint32_t bstride;   // samples per scratch plane (multiple of 4)
+    uint32_t pcm_kind, bytes_per_sample;
+    uint32_t nseg;
+    unsigned long long planar_stride;
+    unsigned long long nbytes;       // size of the frames buffer
+    unsigned long long out_samples;  // capacity of the PCM output in inter-channel samples
+};
+
+struct DecSeg {
+    unsigned long long byte_off, byte_end, pcm_off, n_pcm;
+};
+
+struct FrameCand {
+    unsigned long long off;
+    uint32_t block_size;
+    uint32_t seg;
+    uint8_t hdr_len, assignment, pad0, pad1;
+    uint32_t pad2;
+};
+
+struct DecRec {
+    unsigned long long end;   // one past the frame's CRC-16
+    uint32_t err;             // 0 or the flac_codec::Error ordinal
+    uint32_t wide;            // 1: the side channel is 33 bits wide, its high words are in the extra plane
+};
+
+struct ChainState {
+    unsigned long long expect_off;    // a chain continues into the next group at this byte offset ...
+    unsigned long long seg_samples;   // ... with this many samples of its segment already decoded
+    unsigned long long frames_total, samples_total;
+    unsigned long long err_frame;
+    uint32_t expect_seg, active, err, pad;
+};
+
+
+}   // namespace flacb200

@@ -1,10 +1,1069 @@
-// decode_kernels.cu -- placeholder until the decode pipeline lands (next commit)
-#include "../../include/flacb200.h"
+// decode_kernels.cu -- sm_100a kernels of the FLAC frame decoder.
+//
+// FLAC frames carry no length field, and the reference reads them strictly serially
+// (Decoder::read_frame, src/decode.rs:1388).  Here every byte position is tested for a frame header
+// in parallel, every candidate is decoded speculatively, and the serial walk is re-established
+// afterwards as a linked list (frame -> candidate that starts where it ends) that is ranked by
+// pointer jumping.  Pipeline (one stream):
+//   k_find<0>   tile scan for sync code + full header validation + CRC-8, per-tile counts   [HBM-bound]
+//   k_scan_u32  exclusive scan of the tile counts
+//   k_find<1>   same test, ordered compaction of FrameCand records
+//   then per group of candidates (as many as the scratch budget allows, so that one thread per frame fills the GPU):
+//   k_decode    thread per candidate: subframe headers, Rice/escape residuals, fixed/LPC
+//               restoration (history ring in shared memory), wasted-bit shift -> planar scratch
+//   k_crc16f    warp per candidate: CRC-16 over [start, end) must leave residue 0
+//   k_chain     single CTA, slices of 16384 candidates: links, pointer jumping from the segment heads, ShortBlock/total-sample
+//               rules, output positions (segmented scan of block sizes), first error in stream order
+//   k_emit      stereo restoration + interleave + narrowing to the caller's PCM layout (Frame::to_buf)
 #include "common.cuh"
+#include "crc.cuh"
+#include "decode.cuh"
+
 namespace flacb200 {
-int decode_impl(flacb200_engine*, const flacb200_stream_params*, const void*, size_t, int, const flacb200_decode_segment*, size_t, void*, size_t,
-                int, int, uint64_t, uint64_t*, uint64_t*, uint64_t*)
+
+
+// ------------------------------------------------------------------------------------------------
+// FrameHeader::parse + STREAMINFO cross-checks + CRC-8  (src/stream.rs:214-240, :279-313, :151-163)
+// Returns 0 and fills the fields, or the Error ordinal.  `avail` = bytes from d to the segment end.
+// ------------------------------------------------------------------------------------------------
+__device__ uint32_t parse_frame_header(const uint8_t* __restrict__ d, unsigned long long avail, const DecCfg& cfg, uint32_t* block_size,
+                                       uint32_t* hdr_len, uint32_t* assignment)
 {
-    return FLACB200_E_BAD_ARGUMENT;
+    if (avail < 4) return 1;   // Io (UnexpectedEof)
+    const uint32_t b0 = d[0], b1 = d[1], b2 = d[2], b3 = d[3];
+    if (b0 != 0xFF || (b1 & 0xFE) != 0xF8) return 23;   // InvalidSyncCode
+    const uint32_t bsc = b2 >> 4, src = b2 & 15, ca = b3 >> 4, bpc = (b3 >> 1) & 7;
+    if (bsc == 0) return 24;   // InvalidBlockSize
+    uint32_t rate = 0, rate_kind = 0;
+    switch (src) {
+    case 0:
+        if (cfg.subset) return 27;   // NonSubsetSampleRate
+        rate = cfg.sample_rate;
+        break;
+    case 1: rate = 88200; break;   case 2: rate = 176400; break;  case 3: rate = 192000; break;  case 4: rate = 8000; break;
+    case 5: rate = 16000; break;   case 6: rate = 22050; break;   case 7: rate = 24000; break;   case 8: rate = 32000; break;
+    case 9: rate = 44100; break;   case 10: rate = 48000; break;  case 11: rate = 96000; break;
+    case 12: rate_kind = 1; break; case 13: rate_kind = 2; break; case 14: rate_kind = 3; break;
+    default: return 26;   // InvalidSampleRate
+    }
+    if (ca > 10) return 31;   // InvalidChannels
+    uint32_t bps;
+    switch (bpc) {
+    case 0:
+        if (cfg.subset) return 28;   // NonSubsetBitsPerSample
+        bps = cfg.bps;
+        break;
+    case 1: bps = 8; break;  case 2: bps = 12; break; case 3: return 33;   // InvalidBitsPerSample
+    case 4: bps = 16; break; case 5: bps = 20; break; case 6: bps = 24; break; default: bps = 32; break;
+    }
+    // frame number (src/stream.rs:1246-1264); the reserved bit before it is skipped unchecked (:226)
+    unsigned long long n = 4;
+    if (avail < 5) return 1;
+    const uint32_t f0 = d[4];
+    uint32_t ones = 0;
+    while (ones < 8 && (f0 & (0x80u >> ones))) ones++;
+    if (ones == 0) n += 1;
+    else {
+        if (ones == 1 || ones > 7) return 36;   // InvalidFrameNumber
+        if (n + ones > avail) return 1;
+        for (uint32_t i = 1; i < ones; i++)
+            if ((d[4 + i] & 0xC0) != 0x80) return 36;
+        n += ones;
+    }
+    uint32_t bs;
+    if (bsc == 6) {
+        if (n + 1 > avail) return 1;
+        bs = (uint32_t)d[n] + 1;
+        n += 1;
+    } else if (bsc == 7) {
+        if (n + 2 > avail) return 1;
+        const uint32_t v = ((uint32_t)d[n] << 8) | d[n + 1];
+        if (v == 0xFFFF) return 24;
+        bs = v + 1;
+        n += 2;
+    } else {
+        bs = bsc == 1 ? 192u : bsc <= 5 ? (576u << (bsc - 2)) : (256u << (bsc - 8));
+    }
+    if (rate_kind == 1) {
+        if (n + 1 > avail) return 1;
+        rate = (uint32_t)d[n] * 1000;
+        n += 1;
+    } else if (rate_kind) {
+        if (n + 2 > avail) return 1;
+        rate = ((uint32_t)d[n] << 8) | d[n + 1];
+        if (rate_kind == 3) rate *= 10;
+        n += 2;
+    }
+    if (n + 1 > avail) return 1;
+    n += 1;   // CRC-8
+    const uint32_t channels = ca <= 7 ? ca + 1 : 2;
+    if (!cfg.subset) {   // src/stream.rs:291-312, in this order
+        if (cfg.max_block_size && bs > cfg.max_block_size) return 25;   // BlockSizeMismatch
+        if (rate != cfg.sample_rate) return 29;                         // SampleRateMismatch
+        if (channels != cfg.channels) return 32;                        // ChannelsMismatch
+        if (bps != cfg.bps) return 35;                                  // BitsPerSampleMismatch
+    } else {
+        // the batch API decodes into one buffer of fixed shape: subset frames must agree with it too
+        if (channels != cfg.channels) return 32;
+        if (bps != cfg.bps) return 35;
+    }
+    uint8_t crc = 0;
+    for (uint32_t i = 0; i < (uint32_t)n; i++) crc = crc8_update(crc, d[i]);
+    if (crc != 0) return 39;   // Crc8Mismatch
+    *block_size = bs;
+    *hdr_len = (uint32_t)n;
+    *assignment = ca;
+    return 0;
 }
+
+__device__ inline uint32_t find_segment(const DecSeg* __restrict__ segs, uint32_t nseg, unsigned long long off)
+{
+    // last segment with byte_off <= off (segments are sorted and disjoint); nseg if none contains off
+    uint32_t lo = 0, hi = nseg;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (segs[mid].byte_off <= off) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo == 0) return nseg;
+    const uint32_t s = lo - 1;
+    return off < segs[s].byte_end ? s : nseg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_find: candidate frame starts.  Tile of FIND_TILE bytes per CTA, 32 bytes per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t FIND_THREADS = 256;
+constexpr uint32_t FIND_TILE = FIND_THREADS * 32;
+
+template <int WRITE>
+__global__ void __launch_bounds__(FIND_THREADS) k_find(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
+                                                       uint32_t* __restrict__ tile_counts, const uint32_t* __restrict__ tile_base,
+                                                       FrameCand* __restrict__ cands, uint32_t* __restrict__ max_bs)
+{
+    __shared__ uint32_t wsum[FIND_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long p0 = (unsigned long long)blockIdx.x * FIND_TILE + (unsigned long long)tid * 32;
+    uint32_t w[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) w[k] = 0;
+    if (p0 + 36 <= cfg.nbytes) {
+        const uint4 a = *reinterpret_cast<const uint4*>(bytes + p0), b = *reinterpret_cast<const uint4*>(bytes + p0 + 16);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        w[8] = *reinterpret_cast<const uint32_t*>(bytes + p0 + 32);
+    } else {
+        for (uint32_t i = 0; i < 33; i++)
+            if (p0 + i < cfg.nbytes) w[i >> 2] |= (uint32_t)bytes[p0 + i] << (8 * (i & 3));
+    }
+    // bit i of `hits`: bytes p0+i, p0+i+1 look like a sync code (0xFF, 0b1111100x)
+    uint32_t hits = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const uint32_t pair = __funnelshift_r(w[i >> 2], w[(i >> 2) + 1], 8 * (i & 3)) & 0xffffu;
+        if ((pair & 0xfeffu) == 0xf8ffu) hits |= 1u << i;
+    }
+    uint32_t valid = 0;
+    FrameCand found[4];   // at most 4 candidates per 32 bytes are kept (a header is >= 6 bytes; both passes apply the same cap)
+    uint32_t nfound = 0;
+    while (hits && valid < 4) {
+        const uint32_t i = (uint32_t)__ffs((int)hits) - 1u;
+        hits &= hits - 1;
+        const unsigned long long off = p0 + i;
+        const uint32_t s = find_segment(segs, cfg.nseg, off);
+        if (s == cfg.nseg) continue;
+        uint32_t bs, hl, ca;
+        if (parse_frame_header(bytes + off, segs[s].byte_end - off, cfg, &bs, &hl, &ca) != 0) continue;
+        valid++;
+        if (WRITE) {
+            FrameCand c;
+            c.off = off; c.block_size = bs; c.seg = s; c.hdr_len = (uint8_t)hl; c.assignment = (uint8_t)ca;
+            c.pad0 = c.pad1 = 0; c.pad2 = 0;
+            found[nfound++] = c;
+        } else {
+            atomicMax(max_bs, bs);
+        }
+    }
+    // ordered rank of this thread's candidates inside the tile
+    uint32_t incl = valid;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (uint32_t k = 0; k < FIND_THREADS / 32; k++) {
+        if (k < wid) before += wsum[k];
+        total += wsum[k];
+    }
+    if (!WRITE) {
+        if (tid == 0) tile_counts[blockIdx.x] = total;
+        return;
+    }
+    uint32_t rank = tile_base[blockIdx.x] + before + incl - valid;
+    for (uint32_t k = 0; k < nfound; k++) cands[rank + k] = found[k];
+}
+
+// exclusive scan of n counts (single CTA of 1024 threads); total written to out[n]
+__global__ void __launch_bounds__(1024) k_scan_u32(uint32_t n, const uint32_t* __restrict__ in, uint32_t* __restrict__ out)
+{
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t tile_total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t v = i < n ? in[i] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t ws = wsum[lane];
+            uint32_t wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (uint32_t)o) wi += t;
+            }
+            wsum[lane] = wi - ws;
+            if (lane == 31) tile_total = wi;
+        }
+        __syncthreads();
+        if (i < n) out[i] = carry + wsum[wid] + incl - v;
+        carry += tile_total;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bit reader over the frames buffer: 128-bit loads, 64-bit MSB-aligned window with >= 32 valid bits
+// ------------------------------------------------------------------------------------------------
+struct BitReader {
+    const uint8_t* bytes;
+    unsigned long long nbytes;   // bytes that may be read
+    unsigned long long widx;     // next 32-bit word to fetch
+    unsigned long long endbit;   // bit position of the segment end
+    unsigned long long buf;
+    uint4 q;
+    uint32_t cnt;
+    uint32_t err;
+
+    __device__ inline void load_vec(unsigned long long vidx)
+    {
+        const unsigned long long b = vidx << 4;
+        if (b + 16 <= nbytes) q = *reinterpret_cast<const uint4*>(bytes + b);
+        else {
+            uint32_t t[4] = {0, 0, 0, 0};
+            for (uint32_t i = 0; i < 16; i++)
+                if (b + i < nbytes) t[i >> 2] |= (uint32_t)bytes[b + i] << (8 * (i & 3));
+            q = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+    }
+    __device__ inline uint32_t fetch()
+    {
+        const uint32_t sub = (uint32_t)(widx & 3);
+        if (sub == 0) load_vec(widx >> 2);
+        const uint32_t v = sub == 0 ? q.x : sub == 1 ? q.y : sub == 2 ? q.z : q.w;
+        widx++;
+        return __byte_perm(v, 0, 0x0123);
+    }
+    __device__ inline void init(unsigned long long bitpos)
+    {
+        err = 0;
+        widx = bitpos >> 5;
+        load_vec(widx >> 2);
+        const uint32_t hi = fetch_noload(), skip = (uint32_t)(bitpos & 31);
+        const uint32_t lo = fetch();
+        buf = (((unsigned long long)hi << 32) | lo) << skip;
+        cnt = 64 - skip;
+        if (cnt < 32) refill();
+    }
+    __device__ inline uint32_t fetch_noload()
+    {
+        const uint32_t sub = (uint32_t)(widx & 3);
+        const uint32_t v = sub == 0 ? q.x : sub == 1 ? q.y : sub == 2 ? q.z : q.w;
+        widx++;
+        return __byte_perm(v, 0, 0x0123);
+    }
+    __device__ inline void refill()
+    {
+        const uint32_t w = fetch();
+        buf |= (unsigned long long)w << (32 - cnt);
+        cnt += 32;
+    }
+    __device__ inline unsigned long long position() const { return (widx << 5) - cnt; }
+    __device__ inline void consume(uint32_t n)   // n <= 32, cnt >= 32
+    {
+        buf <<= n;
+        cnt -= n;
+        if (cnt < 32) refill();
+    }
+    __device__ inline uint32_t get(uint32_t n)   // n in 0..=32
+    {
+        if (n == 0) return 0;
+        const uint32_t v = (uint32_t)(buf >> (64 - n));
+        consume(n);
+        return v;
+    }
+    __device__ inline int32_t get_signed(uint32_t n)   // n in 1..=32
+    {
+        const uint32_t v = get(n);
+        return (int32_t)(v << (32 - n)) >> (32 - n);
+    }
+    __device__ inline long long get_signed64(uint32_t n)   // n in 1..=33
+    {
+        if (n <= 32) return get_signed(n);
+        const unsigned long long hi = get(n - 32);
+        const unsigned long long v = (hi << 32) | get(32);
+        return (long long)(v << (64 - n)) >> (64 - n);
+    }
+    __device__ inline uint32_t unary()   // read_unary::<1>: zeros up to the next one bit
+    {
+        uint32_t qv = 0;
+        for (;;) {
+            const uint32_t top = (uint32_t)(buf >> 32);
+            if (top) {
+                const uint32_t lz = (uint32_t)__clz((int)top);
+                consume(lz + 1);
+                return qv + lz;
+            }
+            qv += 32;
+            consume(32);
+            if (position() > endbit) {
+                err = 1;
+                return qv;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// k_decode: read_subframes (src/decode.rs:1494-1856), one thread per candidate frame
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t DEC_THREADS = 128;
+
+struct PlaneWriter {
+    int32_t* plane;
+    uint32_t i, wasted;
+    int32_t o0, o1, o2;
+    __device__ inline void push(int32_t v)
+    {
+        v = (int32_t)((uint32_t)v << wasted);   // `<<= wasted_bps`  src/decode.rs:1671
+        const uint32_t ph = i & 3;
+        if (ph == 0) o0 = v;
+        else if (ph == 1) o1 = v;
+        else if (ph == 2) o2 = v;
+        else *reinterpret_cast<int4*>(plane + (i - 3)) = make_int4(o0, o1, o2, v);
+        i++;
+    }
+    __device__ inline void flush()
+    {
+        const uint32_t ph = i & 3, b = i - ph;
+        if (ph >= 1) plane[b] = o0;
+        if (ph >= 2) plane[b + 1] = o1;
+        if (ph >= 3) plane[b + 2] = o2;
+    }
+};
+
+// One subframe whose samples fit 32 bits.  hist/coef are this thread's columns of the shared rings.
+__device__ uint32_t decode_subframe(BitReader& br, uint32_t bps, uint32_t n, int32_t* __restrict__ plane, int32_t* hist, int16_t* coef)
+{
+    // SubframeHeader (src/stream.rs:1382-1395, :1537-1553)
+    const uint32_t h = br.get(8);
+    if (h & 0x80) return 41;   // InvalidSubframeHeader
+    const uint32_t type = (h >> 1) & 0x3f;
+    uint32_t wasted = 0;
+    if (h & 1) wasted = br.unary() + 1;
+    if (br.err) return br.err;
+    uint32_t kind, order = 0;
+    if (type == 0) kind = 0;
+    else if (type == 1) kind = 1;
+    else if (type >= 8 && type <= 12) { kind = 2; order = type - 8; }
+    else if (type >= 32) { kind = 3; order = type - 31; }
+    else return 42;   // InvalidSubframeHeaderType
+    if (wasted >= bps) return 43;   // ExcessiveWastedBits (src/decode.rs:1644)
+    const uint32_t ebps = bps - wasted;
+    PlaneWriter pw;
+    pw.plane = plane; pw.i = 0; pw.wasted = wasted; pw.o0 = pw.o1 = pw.o2 = 0;
+    if (kind == 0) {
+        const int32_t v = br.get_signed(ebps);
+        for (uint32_t i = 0; i < n; i++) pw.push(v);
+        pw.flush();
+        return br.position() > br.endbit ? 1u : 0u;
+    }
+    if (kind == 1) {
+        for (uint32_t i = 0; i < n; i++) pw.push(br.get_signed(ebps));
+        pw.flush();
+        return br.position() > br.endbit ? 1u : 0u;
+    }
+    if (order > n) return kind == 2 ? 47u : 48u;   // InvalidFixedOrder / InvalidLpcOrder
+    for (uint32_t i = 0; i < order; i++) {         // warm-up samples
+        const int32_t v = br.get_signed(ebps);
+        hist[(i & 31) * DEC_THREADS] = v;
+        pw.push(v);
+    }
+    uint32_t shift = 0;
+    if (kind == 2) {
+        const int16_t fc[4][4] = {{1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};   // src/stream.rs:1534
+        for (uint32_t j = 0; j < order; j++) coef[j * DEC_THREADS] = fc[order - 1][j];
+    } else {
+        const uint32_t prec = br.get(4) + 1;
+        if (prec > 15) return 49;   // InvalidQlpPrecision
+        const int32_t sh = br.get_signed(5);
+        if (sh < 0) return 50;      // NegativeLpcShift
+        shift = (uint32_t)sh;
+        for (uint32_t j = 0; j < order; j++) coef[j * DEC_THREADS] = (int16_t)br.get_signed(prec);
+    }
+    if (br.position() > br.endbit) return 1;
+    // read_residuals (src/decode.rs:1800-1856)
+    const uint32_t method = br.get(2);
+    if (method > 1) return 45;   // InvalidCodingMethod
+    const uint32_t hb = method ? 5u : 4u, esc_code = method ? 31u : 15u;
+    const uint32_t porder = br.get(4);
+    const uint32_t nres = n - order;
+    const uint32_t chunk = n >> porder;
+    if (chunk == 0) return 46;   // InvalidPartitionOrder (rchunks_mut(0) panics in the reference)
+    if ((nres + chunk - 1) / chunk != (1u << porder)) return 46;
+    uint32_t part_end = 0;       // residual index where the next partition starts
+    uint32_t next_len = nres - ((1u << porder) - 1) * chunk;   // the first partition is short by `order`
+    uint32_t mode = 0, k = 0;    // mode 0 rice(k), 1 escaped(k bits), 2 all zero
+    for (uint32_t idx = 0; idx < nres; idx++) {
+        if (idx == part_end) {   // ResidualPartitionHeader (src/stream.rs:1586-1600)
+            k = br.get(hb);
+            mode = 0;
+            if (k == esc_code) {
+                k = br.get(5);
+                mode = k ? 1 : 2;
+            }
+            part_end += next_len;
+            next_len = chunk;
+            if (br.position() > br.endbit) return 1;
+        }
+        int32_t r;
+        if (mode == 0) {
+            uint32_t msb, lsb;
+            const uint32_t top = (uint32_t)(br.buf >> 32);
+            const uint32_t lz = (uint32_t)__clz((int)top);
+            if (top != 0 && lz + 1 + k <= 32) {   // whole code inside the 32-bit window
+                msb = lz;
+                lsb = k ? ((top << (lz + 1)) >> (32 - k)) : 0u;
+                br.consume(lz + 1 + k);
+            } else {
+                msb = br.unary();
+                if (br.err) return br.err;
+                lsb = br.get(k);
+            }
+            const uint32_t u = (msb << k) | lsb;   // src/decode.rs:1827
+            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+        } else if (mode == 1) {
+            r = br.get_signed(k);
+        } else {
+            r = 0;
+        }
+        const uint32_t s = order + idx;
+        long long sum = 0;
+        for (uint32_t j = 0; j < order; j++)   // predict (src/decode.rs:1738-1752)
+            sum += (long long)hist[((s - 1 - j) & 31) * DEC_THREADS] * (long long)coef[j * DEC_THREADS];
+        const int32_t x = (int32_t)((uint32_t)r + (uint32_t)(unsigned long long)(sum >> shift));
+        hist[(s & 31) * DEC_THREADS] = x;
+        pw.push(x);
+    }
+    pw.flush();
+    return br.position() > br.endbit ? 1u : 0u;
+}
+
+// The 33-bit side channel of a 32-bit stereo-decorrelated stream (src/decode.rs:1528-1546): i64 samples,
+// low words to `plane`, high words to `plane_hi`.  Rare: plain loops over global memory.
+__device__ uint32_t decode_subframe_wide(BitReader& br, uint32_t bps, uint32_t n, int32_t* __restrict__ plane, int32_t* __restrict__ plane_hi)
+{
+    const uint32_t h = br.get(8);
+    if (h & 0x80) return 41;
+    const uint32_t type = (h >> 1) & 0x3f;
+    uint32_t wasted = 0;
+    if (h & 1) wasted = br.unary() + 1;
+    if (br.err) return br.err;
+    uint32_t kind, order = 0;
+    if (type == 0) kind = 0;
+    else if (type == 1) kind = 1;
+    else if (type >= 8 && type <= 12) { kind = 2; order = type - 8; }
+    else if (type >= 32) { kind = 3; order = type - 31; }
+    else return 42;
+    if (wasted >= bps) return 43;
+    const uint32_t ebps = bps - wasted;
+    auto put = [&](uint32_t i, long long v) {
+        plane[i] = (int32_t)(uint32_t)(unsigned long long)v;
+        plane_hi[i] = (int32_t)(v >> 32);
+    };
+    auto at = [&](uint32_t i) -> long long { return (long long)(((unsigned long long)(uint32_t)plane_hi[i] << 32) | (uint32_t)plane[i]); };
+    if (kind == 0) {
+        const long long v = br.get_signed64(ebps);
+        for (uint32_t i = 0; i < n; i++) put(i, v);
+    } else if (kind == 1) {
+        for (uint32_t i = 0; i < n; i++) put(i, br.get_signed64(ebps));
+    } else {
+        if (order > n) return kind == 2 ? 47u : 48u;
+        for (uint32_t i = 0; i < order; i++) put(i, br.get_signed64(ebps));
+        long long cf[32];
+        uint32_t shift = 0;
+        if (kind == 2) {
+            const long long fc[4][4] = {{1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+            for (uint32_t j = 0; j < order; j++) cf[j] = fc[order - 1][j];
+        } else {
+            const uint32_t prec = br.get(4) + 1;
+            if (prec > 15) return 49;
+            const int32_t sh = br.get_signed(5);
+            if (sh < 0) return 50;
+            shift = (uint32_t)sh;
+            for (uint32_t j = 0; j < order; j++) cf[j] = br.get_signed(prec);
+        }
+        if (br.position() > br.endbit) return 1;
+        const uint32_t method = br.get(2);
+        if (method > 1) return 45;
+        const uint32_t hb = method ? 5u : 4u, esc_code = method ? 31u : 15u;
+        const uint32_t porder = br.get(4);
+        const uint32_t nres = n - order;
+        const uint32_t chunk = n >> porder;
+        if (chunk == 0) return 46;
+        if ((nres + chunk - 1) / chunk != (1u << porder)) return 46;
+        uint32_t part_end = 0, next_len = nres - ((1u << porder) - 1) * chunk, mode = 0, k = 0;
+        for (uint32_t idx = 0; idx < nres; idx++) {
+            if (idx == part_end) {
+                k = br.get(hb);
+                mode = 0;
+                if (k == esc_code) {
+                    k = br.get(5);
+                    mode = k ? 1 : 2;
+                }
+                part_end += next_len;
+                next_len = chunk;
+                if (br.position() > br.endbit) return 1;
+            }
+            long long r;
+            if (mode == 0) {
+                const uint32_t msb = br.unary();
+                if (br.err) return br.err;
+                const uint32_t u = (msb << k) | br.get(k);
+                r = (u & 1) ? -(long long)(u >> 1) - 1 : (long long)(u >> 1);
+            } else if (mode == 1) r = br.get_signed(k);
+            else r = 0;
+            const uint32_t s = order + idx;
+            long long sum = 0;
+            for (uint32_t j = 0; j < order; j++) sum += at(s - 1 - j) * cf[j];
+            put(s, r + (sum >> shift));
+        }
+    }
+    if (wasted)
+        for (uint32_t i = 0; i < n; i++) put(i, (long long)((unsigned long long)at(i) << wasted));
+    return br.position() > br.endbit ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(DEC_THREADS) k_decode(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
+                                                       const FrameCand* __restrict__ cands, uint32_t ncand, int32_t* __restrict__ planes,
+                                                       DecRec* __restrict__ recs)
+{
+    __shared__ int32_t s_hist[32 * DEC_THREADS];
+    __shared__ int16_t s_coef[32 * DEC_THREADS];
+    const uint32_t c = blockIdx.x * DEC_THREADS + threadIdx.x;
+    if (c >= ncand) return;
+    const FrameCand fc = cands[c];
+    const DecSeg sg = segs[fc.seg];
+    BitReader br;
+    br.bytes = bytes;
+    br.nbytes = cfg.nbytes;
+    br.endbit = sg.byte_end * 8;
+    br.init((fc.off + fc.hdr_len) * 8);
+    const uint32_t n = fc.block_size;
+    int32_t* base = planes + (size_t)c * cfg.nslots * cfg.bstride;
+    int32_t* hist = s_hist + threadIdx.x;
+    int16_t* coef = s_coef + threadIdx.x;
+    uint32_t err = 0, wide = 0;
+    if (n > cfg.bstride) err = 25;   // cannot happen when max_block_size was honoured
+    const uint32_t ca = fc.assignment;
+    if (!err) {
+        if (ca <= 7) {
+            for (uint32_t ch = 0; ch <= ca && !err; ch++) err = decode_subframe(br, cfg.bps, n, base + (size_t)ch * cfg.bstride, hist, coef);
+        } else {
+            // 8: left, side   9: side, right   10: mid, side   (src/decode.rs:1512-1626)
+            const uint32_t side_first = ca == 9;
+            wide = cfg.bps == 32;
+            for (uint32_t ch = 0; ch < 2 && !err; ch++) {
+                const bool is_side = (ch == 0) == (side_first != 0);
+                if (is_side && wide) err = decode_subframe_wide(br, cfg.bps + 1, n, base + (size_t)ch * cfg.bstride, base + (size_t)2 * cfg.bstride);
+                else err = decode_subframe(br, is_side ? cfg.bps + 1 : cfg.bps, n, base + (size_t)ch * cfg.bstride, hist, coef);
+            }
+        }
+    }
+    DecRec rec;
+    rec.err = err;
+    rec.wide = wide;
+    rec.end = 0;
+    if (!err) {
+        const unsigned long long end = ((br.position() + 7) >> 3) + 2;   // byte_align; CRC-16  (:1629-1630)
+        if (end > sg.byte_end) rec.err = 1;
+        rec.end = end;
+    }
+    recs[c] = rec;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_crc16f: CRC-16 residue of [off, end) must be 0 (src/decode.rs:1429); warp per candidate
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t CRCF_THREADS = 256;
+
+__global__ void __launch_bounds__(CRCF_THREADS) k_crc16f(const uint8_t* __restrict__ bytes, const FrameCand* __restrict__ cands, uint32_t ncand,
+                                                        DecRec* __restrict__ recs)
+{
+    __shared__ Crc16Tables tabs;
+    crc16_tables_init(tabs);
+    __syncthreads();
+    const uint32_t c = blockIdx.x * (CRCF_THREADS / 32) + (threadIdx.x >> 5);
+    if (c >= ncand) return;
+    if (recs[c].err) return;
+    const unsigned long long off = cands[c].off, end = recs[c].end;
+    const uint32_t crc = crc16_warp(tabs, bytes, off, end - off);
+    if ((threadIdx.x & 31) == 0 && crc != 0) recs[c].err = 40;   // Crc16Mismatch
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_chain: the serial frame walk, re-established in parallel for one group of candidates
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t CHAIN_THREADS = 1024;
+constexpr uint32_t CHAIN_MAX = 16384;   // candidates per slice (links are 16-bit indices)
+constexpr uint32_t CHAIN_PER = CHAIN_MAX / CHAIN_THREADS;
+constexpr uint32_t CHAIN_NONE = 0xFFFFu;
+
+struct ChainSmem {
+    uint16_t jump[2][CHAIN_MAX];
+    uint32_t pref[CHAIN_MAX];      // inclusive prefix of marked block sizes
+    uint16_t errpref[CHAIN_MAX];   // inclusive prefix of marked-and-failed
+    uint8_t mark[CHAIN_MAX];
+    uint8_t flag[CHAIN_MAX];       // bit0: successor lives in a later slice, bit1: link broken
+    unsigned long long wsum[32];
+    unsigned long long first_err;  // (candidate index << 32) | code, minimum wins
+    unsigned long long miss;
+    uint32_t carry;
+    ChainState st;
+};
+
+__device__ inline uint32_t find_cand(const FrameCand* __restrict__ cands, uint32_t n, unsigned long long off)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cands[mid].off < off) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < n && cands[lo].off == off) ? lo : CHAIN_NONE;
+}
+
+// first candidate of the slice that belongs to segment `seg` (candidates are sorted by offset, hence by segment)
+__device__ inline uint32_t first_of_segment(const FrameCand* __restrict__ cands, uint32_t upto, uint32_t seg)
+{
+    uint32_t lo = 0, hi = upto;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cands[mid].seg < seg) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// block-wide inclusive scan of one value per thread (1024 threads)
+__device__ inline unsigned long long block_scan_incl(unsigned long long v, unsigned long long* wsum)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned long long ws = wsum[lane];
+        unsigned long long wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (uint32_t)o) wi += t;
+        }
+        wsum[lane] = wi - ws;
+    }
+    __syncthreads();
+    return incl + wsum[wid];
+}
+
+// One slice of n (<= CHAIN_MAX) candidates.  first_off/next_off: byte offsets of this slice's and of the next
+// slice's first candidate (next_off = ~0 for the very last slice).  sm.st is the walk state carried between slices.
+__device__ void chain_slice(ChainSmem& sm, const DecCfg& cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
+                            const FrameCand* __restrict__ cands, DecRec* __restrict__ recs, uint32_t n, unsigned long long first_off,
+                            unsigned long long next_off, bool is_first, unsigned long long* __restrict__ pos_out)
+{
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        sm.first_err = ~0ull;
+        sm.miss = ~0ull;
+        sm.carry = CHAIN_NONE;
+    }
+    __syncthreads();
+    const ChainState st = sm.st;
+    const bool active = st.active != 0;
+    // ---- heads and links ----
+    for (uint32_t c = tid; c < n; c += CHAIN_THREADS) {
+        uint16_t nx = CHAIN_NONE;
+        uint8_t mark = 0, flag = 0;
+        const FrameCand fc = cands[c];
+        const DecRec r = recs[c];
+        const DecSeg sg = segs[fc.seg];
+        if (fc.off == sg.byte_off) mark = 1;
+        if (active && fc.seg == st.expect_seg && fc.off == st.expect_off) mark = 1;
+        if (r.err == 0 && r.end < sg.byte_end) {
+            if (r.end >= next_off) flag = 1;
+            else {
+                const uint32_t t = find_cand(cands, n, r.end);
+                if (t != CHAIN_NONE && cands[t].seg == fc.seg) nx = (uint16_t)t;
+                else flag = 2;
+            }
+        }
+        sm.jump[0][c] = nx;
+        sm.mark[c] = mark;
+        sm.flag[c] = flag;
+    }
+    __syncthreads();
+    // ---- pointer jumping: after round k every frame within 2^(k+1) - 1 links of a head is marked ----
+    uint32_t cur = 0;
+    for (uint32_t span = 1; span < n; span <<= 1) {
+        for (uint32_t c = tid; c < n; c += CHAIN_THREADS) {
+            const uint16_t j = sm.jump[cur][c];
+            if (j != CHAIN_NONE && sm.mark[c]) sm.mark[j] = 1;
+            sm.jump[cur ^ 1][c] = j == CHAIN_NONE ? (uint16_t)CHAIN_NONE : sm.jump[cur][j];
+        }
+        cur ^= 1;
+        __syncthreads();
+    }
+    // ---- sample positions: prefix sums of block sizes over marked frames, rebased per segment ----
+    {
+        unsigned long long tv = 0;
+        for (uint32_t k = 0; k < CHAIN_PER; k++) {
+            const uint32_t c = tid * CHAIN_PER + k;
+            if (c < n && sm.mark[c]) tv += cands[c].block_size;
+        }
+        unsigned long long run = block_scan_incl(tv, sm.wsum) - tv;
+        for (uint32_t k = 0; k < CHAIN_PER; k++) {
+            const uint32_t c = tid * CHAIN_PER + k;
+            if (c < n && sm.mark[c]) run += cands[c].block_size;
+            if (c < CHAIN_MAX) sm.pref[c] = (uint32_t)run;
+        }
+    }
+    __syncthreads();
+    // ---- per-frame rules that need the stream position (src/decode.rs:1402-1410) ----
+    unsigned long long te = 0;
+    uint32_t ebits = 0;
+    for (uint32_t k = 0; k < CHAIN_PER; k++) {
+        const uint32_t c = tid * CHAIN_PER + k;
+        if (c >= n) continue;
+        if (!sm.mark[c]) {
+            pos_out[c] = ~0ull;
+            continue;
+        }
+        const FrameCand fc = cands[c];
+        const DecSeg sg = segs[fc.seg];
+        const uint32_t lo = first_of_segment(cands, c, fc.seg);
+        unsigned long long pos = (unsigned long long)(sm.pref[c] - fc.block_size - (lo ? sm.pref[lo - 1] : 0u));
+        if (active && fc.seg == st.expect_seg) pos += st.seg_samples;
+        DecRec r = recs[c];
+        uint32_t err = r.err;
+        if (sg.n_pcm && pos >= sg.n_pcm) {   // Some(0) => Ok(None): the stream was already complete
+            pos_out[c] = ~0ull;
+            sm.mark[c] = 0;
+            continue;
+        }
+        if (sg.n_pcm) {
+            const unsigned long long remaining = sg.n_pcm - pos;
+            if (!(fc.block_size == remaining || fc.block_size > 14)) err = 21;   // ShortBlock
+            else if (fc.block_size > remaining && err == 0) err = 59;             // SampleCountMismatch
+        }
+        if (err == 0 && sg.pcm_off + pos + fc.block_size > cfg.out_samples) err = 0x80000000u;   // output too small
+        recs[c].err = err;
+        pos_out[c] = err ? ~0ull : sg.pcm_off + pos;
+        if (err) {
+            te++;
+            ebits |= 1u << k;
+            continue;
+        }
+        const bool done = sg.n_pcm != 0 && pos + fc.block_size >= sg.n_pcm;
+        if (sm.flag[c] & 2) {   // the bytes after this frame are not a valid frame header
+            uint32_t bs, hl, ca;
+            uint32_t he = parse_frame_header(bytes + r.end, sg.byte_end - r.end, cfg, &bs, &hl, &ca);
+            const bool eof_ok = sg.n_pcm == 0 && he == 1 && sg.byte_end - r.end < 16;   // src/decode.rs:1416
+            if (!eof_ok && !done) {
+                if (he == 0) he = 23;
+                atomicMin(&sm.first_err, ((unsigned long long)c << 32) | 0x40000000u | he);   // error of the NEXT frame
+            }
+        } else if (r.end == sg.byte_end) {
+            if (sg.n_pcm && !done) atomicMin(&sm.first_err, ((unsigned long long)c << 32) | 0x40000000u | 1u);   // Io: ends early
+        } else if ((sm.flag[c] & 1) && !done) {
+            sm.carry = c;   // at most one chain leaves a slice (segments are disjoint and sorted)
+        }
+    }
+    {
+        unsigned long long erun = block_scan_incl(te, sm.wsum) - te;
+        for (uint32_t k = 0; k < CHAIN_PER; k++) {
+            const uint32_t c = tid * CHAIN_PER + k;
+            if (ebits & (1u << k)) erun++;
+            sm.errpref[c] = (uint16_t)erun;
+        }
+    }
+    __syncthreads();
+    // frames behind a failed frame of the same segment were never reached by the reference
+    unsigned long long emitted = 0, samples = 0;
+    for (uint32_t k = 0; k < CHAIN_PER; k++) {
+        const uint32_t c = tid * CHAIN_PER + k;
+        if (c >= n || !sm.mark[c]) continue;
+        const FrameCand fc = cands[c];
+        const uint32_t lo = first_of_segment(cands, c, fc.seg);
+        const uint32_t errs_before = (uint32_t)(c ? sm.errpref[c - 1] : 0) - (uint32_t)(lo ? sm.errpref[lo - 1] : 0);
+        const uint32_t err = recs[c].err;
+        if (errs_before) {
+            pos_out[c] = ~0ull;
+            sm.mark[c] = 2;   // dropped
+            if (sm.carry == c) sm.carry = CHAIN_NONE;
+        } else if (err) {
+            atomicMin(&sm.first_err, ((unsigned long long)c << 32) | (err & 0xBFFFFFFFu));
+        } else {
+            emitted++;
+            samples += fc.block_size;
+        }
+    }
+    emitted = block_scan_incl(emitted, sm.wsum);
+    __syncthreads();
+    samples = block_scan_incl(samples, sm.wsum);
+    // segment heads that fall into this slice's byte range but are not candidates at all
+    for (uint32_t s = tid; s < cfg.nseg; s += CHAIN_THREADS) {
+        const DecSeg sg = segs[s];
+        if (sg.byte_end <= sg.byte_off) continue;
+        const bool mine = (is_first || sg.byte_off >= first_off) && sg.byte_off < next_off;
+        if (mine && find_cand(cands, n, sg.byte_off) == CHAIN_NONE) atomicMin(&sm.miss, (unsigned long long)s);
+    }
+    __syncthreads();
+    if (tid == CHAIN_THREADS - 1) {
+        ChainState ns = st;
+        uint32_t err = 0;
+        unsigned long long err_frame = 0;
+        const unsigned long long ferr = sm.first_err;
+        if (ferr != ~0ull) {
+            const uint32_t c = (uint32_t)(ferr >> 32);
+            const uint32_t code = (uint32_t)ferr;
+            if (sm.mark[c] == 1) {
+                unsigned long long before = 0;   // emitted frames of this slice that precede the failing one
+                for (uint32_t i = 0; i < c; i++) before += (sm.mark[i] == 1 && recs[i].err == 0) ? 1 : 0;
+                if (code & 0x40000000u) before += 1;   // the failing frame is the one after c
+                err = (code & 0x80000000u) ? 0x80000000u : (code & 0x3FFFFFFFu);
+                err_frame = st.frames_total + before;
+            }
+        }
+        // the chain that was expected to continue in this slice
+        if (active && st.expect_off < next_off && find_cand(cands, n, st.expect_off) == CHAIN_NONE) {
+            const DecSeg sg = segs[st.expect_seg];
+            uint32_t bs, hl, ca;
+            const uint32_t he = parse_frame_header(bytes + st.expect_off, sg.byte_end - st.expect_off, cfg, &bs, &hl, &ca);
+            const bool eof_ok = sg.n_pcm == 0 && he == 1 && sg.byte_end - st.expect_off < 16;
+            if (!eof_ok) {
+                err = he ? he : 23;
+                err_frame = st.frames_total;
+            }
+        }
+        if (sm.miss != ~0ull && err == 0) {
+            const DecSeg sg = segs[(uint32_t)sm.miss];
+            uint32_t bs, hl, ca;
+            const uint32_t he = parse_frame_header(bytes + sg.byte_off, sg.byte_end - sg.byte_off, cfg, &bs, &hl, &ca);
+            const bool eof_ok = sg.n_pcm == 0 && he == 1 && sg.byte_end - sg.byte_off < 16;
+            if (!eof_ok) {
+                err = he ? he : 23;
+                err_frame = st.frames_total;
+            }
+        }
+        if (ns.err == 0 && err) {
+            ns.err = err;
+            ns.err_frame = err_frame;
+        }
+        ns.frames_total = st.frames_total + emitted;
+        ns.samples_total = st.samples_total + samples;
+        const bool keep_waiting = active && st.expect_off >= next_off;
+        if (sm.carry != CHAIN_NONE) {
+            const uint32_t c = sm.carry;
+            const FrameCand fc = cands[c];
+            ns.active = 1;
+            ns.expect_seg = fc.seg;
+            ns.expect_off = recs[c].end;
+            ns.seg_samples = pos_out[c] - segs[fc.seg].pcm_off + fc.block_size;
+        } else if (!keep_waiting) {
+            ns.active = 0;
+        }
+        sm.st = ns;
+    }
+    __syncthreads();
+}
+
+// single CTA; dynamic shared memory = sizeof(ChainSmem).  Walks the candidates [0, ntotal) of one decode group in
+// slices; `group_first`/`group_last` say whether earlier/later groups exist (for the byte-range ownership of heads).
+__global__ void __launch_bounds__(CHAIN_THREADS) k_chain(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
+                                                        const FrameCand* __restrict__ cands, DecRec* __restrict__ recs, uint32_t ntotal,
+                                                        const FrameCand* __restrict__ after, uint32_t group_first,
+                                                        unsigned long long* __restrict__ pos_out, ChainState* __restrict__ state)
+{
+    extern __shared__ __align__(16) uint8_t chain_dyn[];
+    ChainSmem& sm = *reinterpret_cast<ChainSmem*>(chain_dyn);
+    if (threadIdx.x == 0) sm.st = *state;
+    __syncthreads();
+    const unsigned long long after_off = after ? after->off : ~0ull;   // first candidate of the next group
+    uint32_t s0 = 0;
+    do {
+        const uint32_t n = min(CHAIN_MAX, ntotal - s0);
+        const unsigned long long first_off = n ? cands[s0].off : 0;
+        const unsigned long long next_off = s0 + n < ntotal ? cands[s0 + n].off : after_off;
+        chain_slice(sm, cfg, bytes, segs, cands + s0, recs + s0, n, first_off, next_off, group_first && s0 == 0, pos_out + s0);
+        s0 += n;
+    } while (s0 < ntotal);
+    if (threadIdx.x == 0) *state = sm.st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_emit: stereo restoration (src/decode.rs:1524-1626) + Frame::to_buf (src/audio.rs:110-134)
+// ------------------------------------------------------------------------------------------------
+__device__ inline void store_sample(uint8_t* __restrict__ out, const DecCfg& cfg, unsigned long long idx, uint32_t ch, int32_t v)
+{
+    switch (cfg.pcm_kind) {
+    case 2: reinterpret_cast<int32_t*>(out)[idx * cfg.channels + ch] = v; return;
+    case 3: reinterpret_cast<int32_t*>(out)[(unsigned long long)ch * cfg.planar_stride + idx] = v; return;
+    default: break;
+    }
+    uint8_t* p = out + (idx * cfg.channels + ch) * cfg.bytes_per_sample;
+    const uint32_t u = (uint32_t)v;
+    const bool be = cfg.pcm_kind == 1;
+    switch (cfg.bytes_per_sample) {
+    case 1: p[0] = (uint8_t)u; break;
+    case 2:
+        if (be) { p[0] = (uint8_t)(u >> 8); p[1] = (uint8_t)u; }
+        else { p[0] = (uint8_t)u; p[1] = (uint8_t)(u >> 8); }
+        break;
+    case 3:
+        if (be) { p[0] = (uint8_t)(u >> 16); p[1] = (uint8_t)(u >> 8); p[2] = (uint8_t)u; }
+        else { p[0] = (uint8_t)u; p[1] = (uint8_t)(u >> 8); p[2] = (uint8_t)(u >> 16); }
+        break;
+    default:
+        if (be) { p[0] = (uint8_t)(u >> 24); p[1] = (uint8_t)(u >> 16); p[2] = (uint8_t)(u >> 8); p[3] = (uint8_t)u; }
+        else { p[0] = (uint8_t)u; p[1] = (uint8_t)(u >> 8); p[2] = (uint8_t)(u >> 16); p[3] = (uint8_t)(u >> 24); }
+    }
+}
+
+// grid (ncand, ceil(bstride / 256))
+__global__ void __launch_bounds__(256) k_emit(DecCfg cfg, const FrameCand* __restrict__ cands, const DecRec* __restrict__ recs,
+                                              const unsigned long long* __restrict__ pos, const int32_t* __restrict__ planes,
+                                              uint8_t* __restrict__ out)
+{
+    const uint32_t c = blockIdx.x;
+    const unsigned long long p = pos[c];
+    if (p == ~0ull) return;
+    const FrameCand fc = cands[c];
+    const uint32_t i = blockIdx.y * 256 + threadIdx.x;
+    if (i >= fc.block_size) return;
+    const int32_t* base = planes + (size_t)c * cfg.nslots * cfg.bstride;
+    const uint32_t ca = fc.assignment;
+    if (ca <= 7) {
+        for (uint32_t ch = 0; ch <= ca; ch++) store_sample(out, cfg, p + i, ch, base[(size_t)ch * cfg.bstride + i]);
+        return;
+    }
+    const int32_t a = base[i], b = base[cfg.bstride + i];
+    int32_t l, r;
+    if (recs[c].wide) {
+        const long long hi = base[(size_t)2 * cfg.bstride + i];
+        if (ca == 8) {          // left, side(33 bit): right = left - side
+            const long long side = (long long)(((unsigned long long)hi << 32) | (uint32_t)b);
+            l = a;
+            r = (int32_t)((long long)a - side);
+        } else if (ca == 9) {   // side(33 bit), right: left = side + right
+            const long long side = (long long)(((unsigned long long)hi << 32) | (uint32_t)a);
+            l = (int32_t)(side + (long long)b);
+            r = b;
+        } else {                // mid, side(33 bit)   :1612-1622
+            const long long side = (long long)(((unsigned long long)hi << 32) | (uint32_t)b);
+            const long long sum = (long long)a * 2 + (side < 0 ? (-side) % 2 : side % 2);
+            l = (int32_t)((sum + side) >> 1);
+            r = (int32_t)((sum - side) >> 1);
+        }
+    } else if (ca == 8) {
+        l = a;
+        r = (int32_t)((uint32_t)a - (uint32_t)b);
+    } else if (ca == 9) {
+        l = (int32_t)((uint32_t)a + (uint32_t)b);
+        r = b;
+    } else {
+        const int32_t sum = (int32_t)((uint32_t)a * 2u + (uint32_t)(b & 1));   // side.abs() % 2 == side & 1  (:1599)
+        l = (int32_t)((uint32_t)sum + (uint32_t)b) >> 1;
+        r = (int32_t)((uint32_t)sum - (uint32_t)b) >> 1;
+    }
+    store_sample(out, cfg, p + i, 0, l);
+    store_sample(out, cfg, p + i, 1, r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers (called from engine.cu)
+// ------------------------------------------------------------------------------------------------
+uint32_t find_tiles(unsigned long long nbytes) { return (uint32_t)((nbytes + FIND_TILE - 1) / FIND_TILE); }
+
+void launch_find_count(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, uint32_t* tile_counts, uint32_t* tile_base, uint32_t* max_bs,
+                       cudaStream_t st)
+{
+    const uint32_t tiles = find_tiles(cfg.nbytes);
+    k_find<0><<<tiles, FIND_THREADS, 0, st>>>(cfg, bytes, segs, tile_counts, nullptr, nullptr, max_bs);
+    k_scan_u32<<<1, 1024, 0, st>>>(tiles, tile_counts, tile_base);
+}
+
+void launch_find_write(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const uint32_t* tile_base, FrameCand* cands, cudaStream_t st)
+{
+    k_find<1><<<find_tiles(cfg.nbytes), FIND_THREADS, 0, st>>>(cfg, bytes, segs, nullptr, tile_base, cands, nullptr);
+}
+
+void launch_decode(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes, DecRec* recs,
+                   cudaStream_t st)
+{
+    k_decode<<<(n + DEC_THREADS - 1) / DEC_THREADS, DEC_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, recs);
+}
+
+void launch_crc16f(const uint8_t* bytes, const FrameCand* cands, uint32_t n, DecRec* recs, cudaStream_t st)
+{
+    k_crc16f<<<(n + CRCF_THREADS / 32 - 1) / (CRCF_THREADS / 32), CRCF_THREADS, 0, st>>>(bytes, cands, n, recs);
+}
+
+cudaError_t launch_chain(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, DecRec* recs, uint32_t n,
+                         const FrameCand* after, uint32_t group_first, unsigned long long* pos, ChainState* state, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_chain<<<1, CHAIN_THREADS, sizeof(ChainSmem), st>>>(cfg, bytes, segs, cands, recs, n, after, group_first, pos, state);
+    return cudaGetLastError();
+}
+
+void launch_emit(const DecCfg& cfg, const FrameCand* cands, const DecRec* recs, const unsigned long long* pos, const int32_t* planes, uint32_t n,
+                 uint8_t* out, cudaStream_t st)
+{
+    dim3 grid(n, (cfg.bstride + 255) / 256);
+    k_emit<<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
+}
+
+
 }   // namespace flacb200

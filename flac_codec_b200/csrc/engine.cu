@@ -13,6 +13,7 @@
 
 #include "../../include/flacb200.h"
 #include "common.cuh"
+#include "decode.cuh"
 
 namespace flacb200 {
 // encode_kernels.cu
@@ -28,10 +29,14 @@ cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, con
 cudaError_t launch_synth(uint8_t* pcm, unsigned long long first_track, unsigned long long n_tracks, unsigned long long n_pcm_frames,
                          uint32_t channels, uint32_t sample_rate, uint32_t bps, unsigned long long seed, const int32_t* lut, cudaStream_t st);
 // decode_kernels.cu
-struct DecodeArgs;
-int decode_impl(flacb200_engine* e, const flacb200_stream_params* params, const void* frames, size_t frames_bytes, int frames_location,
-                const flacb200_decode_segment* segments, size_t n_segments, void* pcm_out, size_t pcm_out_bytes, int pcm_kind,
-                int pcm_location, uint64_t planar_stride, uint64_t* n_frames, uint64_t* n_pcm_frames, uint64_t* bad_frame);
+uint32_t find_tiles(unsigned long long nbytes);
+void launch_find_count(const DecCfg&, const uint8_t*, const DecSeg*, uint32_t*, uint32_t*, uint32_t*, cudaStream_t);
+void launch_find_write(const DecCfg&, const uint8_t*, const DecSeg*, const uint32_t*, FrameCand*, cudaStream_t);
+void launch_decode(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, DecRec*, cudaStream_t);
+void launch_crc16f(const uint8_t*, const FrameCand*, uint32_t, DecRec*, cudaStream_t);
+cudaError_t launch_chain(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, DecRec*, uint32_t, const FrameCand*, uint32_t,
+                         unsigned long long*, ChainState*, cudaStream_t);
+void launch_emit(const DecCfg&, const FrameCand*, const DecRec*, const unsigned long long*, const int32_t*, uint32_t, uint8_t*, cudaStream_t);
 }   // namespace flacb200
 
 using namespace flacb200;
@@ -517,11 +522,169 @@ extern "C" int flacb200_encode_last_info(flacb200_engine* e, flacb200_frame_info
 
 extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params* params, const void* frames, size_t frames_bytes,
                                int frames_location, const flacb200_decode_segment* segments, size_t n_segments, void* pcm_out,
-                               size_t pcm_out_bytes, int pcm_kind, int pcm_location, uint64_t planar_stride, uint64_t* n_frames,
-                               uint64_t* n_pcm_frames, uint64_t* bad_frame)
+                               size_t pcm_out_bytes, int pcm_kind, int pcm_location, uint64_t planar_stride, uint64_t* n_frames_out,
+                               uint64_t* n_pcm_out, uint64_t* bad_frame)
 {
-    return decode_impl(e, params, frames, frames_bytes, frames_location, segments, n_segments, pcm_out, pcm_out_bytes, pcm_kind, pcm_location,
-                       planar_stride, n_frames, n_pcm_frames, bad_frame);
+    if (!e || !params || !segments || (!frames && frames_bytes) || (!pcm_out && pcm_out_bytes)) return FLACB200_E_BAD_ARGUMENT;
+    if (params->channels < 1 || params->channels > 8) return 30;
+    if (params->bits_per_sample < 1 || params->bits_per_sample > 32) return 33;
+    if (pcm_kind < 0 || pcm_kind > 3 || n_segments > 0xFFFFFFF0ull) return FLACB200_E_BAD_ARGUMENT;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    memset(&e->tm, 0, sizeof(e->tm));
+    if (n_frames_out) *n_frames_out = 0;
+    if (n_pcm_out) *n_pcm_out = 0;
+    if (bad_frame) *bad_frame = 0;
+
+    DecCfg cfg{};
+    cfg.channels = params->channels;
+    cfg.bps = params->bits_per_sample;
+    cfg.sample_rate = params->sample_rate;
+    cfg.subset = params->subset;
+    cfg.max_block_size = params->max_block_size;
+    cfg.pcm_kind = (uint32_t)pcm_kind;
+    cfg.bytes_per_sample = pcm_kind <= 1 ? (cfg.bps + 7) / 8 : 4;
+    cfg.planar_stride = planar_stride;
+    cfg.nbytes = frames_bytes;
+    cfg.nseg = (uint32_t)n_segments;
+    cfg.nslots = cfg.channels + ((cfg.channels == 2 && cfg.bps == 32) ? 1 : 0);
+    if (pcm_kind == FLACB200_PCM_I32_PLANAR) {
+        if ((size_t)planar_stride * cfg.channels * 4 > pcm_out_bytes) return FLACB200_E_BAD_ARGUMENT;
+        cfg.out_samples = planar_stride;
+    } else {
+        cfg.out_samples = pcm_out_bytes / ((size_t)cfg.channels * cfg.bytes_per_sample);
+    }
+    // segments: sorted by byte offset, disjoint, inside the buffer
+    std::vector<DecSeg> segs(n_segments);
+    uint64_t prev_end = 0, extent = 0;
+    bool extent_known = true;
+    for (size_t s = 0; s < n_segments; s++) {
+        const flacb200_decode_segment& g = segments[s];
+        if (g.byte_offset < prev_end || g.byte_offset + g.byte_length > frames_bytes || g.byte_offset + g.byte_length < g.byte_offset)
+            return FLACB200_E_BAD_ARGUMENT;
+        segs[s] = DecSeg{g.byte_offset, g.byte_offset + g.byte_length, g.pcm_offset, g.n_pcm_frames};
+        prev_end = g.byte_offset + g.byte_length;
+        if (g.n_pcm_frames) extent = std::max<uint64_t>(extent, g.pcm_offset + g.n_pcm_frames);
+        else extent_known = false;
+    }
+    if (n_segments == 0 || frames_bytes == 0) return 0;
+
+    // ---- buffers ----
+    const uint8_t* d_bytes;
+    if (e->profiling) cudaEventRecord(e->ev[20], st);
+    if (frames_location == FLACB200_HOST || ((uintptr_t)frames & 15)) {
+        ENS(e->dec[0], frames_bytes + 64);
+        CK(cudaMemcpyAsync(e->dec[0].p, frames, frames_bytes, frames_location == FLACB200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+        d_bytes = (const uint8_t*)e->dec[0].p;
+    } else {
+        d_bytes = (const uint8_t*)frames;
+    }
+    uint8_t* d_out;
+    if (pcm_location == FLACB200_HOST) {
+        ENS(e->dec[1], pcm_out_bytes + 64);
+        d_out = (uint8_t*)e->dec[1].p;
+    } else {
+        d_out = (uint8_t*)pcm_out;
+    }
+    ENS(e->dec[2], n_segments * sizeof(DecSeg));
+    CK(cudaMemcpyAsync(e->dec[2].p, segs.data(), n_segments * sizeof(DecSeg), cudaMemcpyHostToDevice, st));
+    if (e->profiling) cudaEventRecord(e->ev[21], st);
+    const DecSeg* d_segs = (const DecSeg*)e->dec[2].p;
+    const uint32_t tiles = find_tiles(frames_bytes);
+    ENS(e->dec[3], (size_t)(tiles + 2) * 4);        // per-tile counts
+    ENS(e->dec[4], (size_t)(tiles + 2) * 4);        // exclusive scan (+ total)
+    ENS(e->dec[5], 256);                            // [0] max block size; ChainState at +64
+    CK(cudaMemsetAsync(e->dec[5].p, 0, 256, st));
+    uint32_t* d_maxbs = (uint32_t*)e->dec[5].p;
+    ChainState* d_state = (ChainState*)((uint8_t*)e->dec[5].p + 64);
+
+    cudaEventRecord(e->ev[22], st);
+    size_t ev = 0;
+    time_mark(e, ev++);
+    launch_find_count(cfg, d_bytes, d_segs, (uint32_t*)e->dec[3].p, (uint32_t*)e->dec[4].p, d_maxbs, st);
+    uint32_t ncand = 0, max_bs = 0;
+    CK(cudaMemcpyAsync(&ncand, (uint32_t*)e->dec[4].p + tiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&max_bs, d_maxbs, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t launches = 2;
+    ENS(e->dec[6], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(FrameCand));
+    ENS(e->dec[7], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(DecRec));
+    ENS(e->dec[8], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(unsigned long long));
+    FrameCand* d_cands = (FrameCand*)e->dec[6].p;
+    DecRec* d_recs = (DecRec*)e->dec[7].p;
+    unsigned long long* d_pos = (unsigned long long*)e->dec[8].p;
+    if (ncand) {
+        launch_find_write(cfg, d_bytes, d_segs, (const uint32_t*)e->dec[4].p, d_cands, st);
+        launches++;
+    }
+    time_mark(e, ev++);
+    cfg.bstride = (std::max<uint32_t>(max_bs, 4) + 3u) & ~3u;
+    // one thread decodes one frame, so a group should hold enough frames to fill the GPU; the scratch budget bounds it
+    const size_t per_frame = (size_t)cfg.nslots * cfg.bstride * sizeof(int32_t);
+    size_t budget = (size_t)6 << 30;
+    uint32_t group = (uint32_t)std::min<size_t>(std::max<size_t>(budget / per_frame, 1), std::max<uint32_t>(ncand, 1));
+    if (e->chunk_frames) group = std::min<uint32_t>(group, e->chunk_frames);
+    ENS(e->dec[9], (size_t)group * per_frame);
+    size_t ngroups = 0;
+    uint32_t g0 = 0;
+    do {
+        const uint32_t n = std::min<uint32_t>(group, ncand - g0);
+        const FrameCand* after = g0 + n < ncand ? d_cands + g0 + n : nullptr;
+        if (n) {
+            launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, st);
+            time_mark(e, ev++);
+            launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, st);
+            time_mark(e, ev++);
+        }
+        CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, st));
+        if (n) {
+            time_mark(e, ev++);
+            launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
+            time_mark(e, ev++);
+            launches += 4;
+            ngroups++;
+        } else {
+            launches += 1;
+        }
+        g0 += n;
+    } while (g0 < ncand);
+    cudaEventRecord(e->ev[23], st);
+    CK(cudaGetLastError());
+    ChainState state;
+    CK(cudaMemcpyAsync(&state, d_state, sizeof(state), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_frames_out) *n_frames_out = state.frames_total;
+    if (n_pcm_out) *n_pcm_out = state.samples_total;
+    cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
+    e->tm.launches = launches;
+    if (e->profiling) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->evpool[0], e->evpool[1]);
+        e->tm.kernel_ms[0] = ms;
+        e->tm.kernel_launches[0] = ncand ? 3 : 2;
+        for (size_t g = 0; g < ngroups; g++)
+            for (int k = 0; k < 4; k++) {
+                cudaEventElapsedTime(&ms, e->evpool[1 + g * 4 + k], e->evpool[2 + g * 4 + k]);
+                e->tm.kernel_ms[1 + k] += ms;
+                e->tm.kernel_launches[1 + k] += 1;
+            }
+        cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[20], e->ev[21]);
+    }
+    if (pcm_location == FLACB200_HOST) {
+        size_t bytes = pcm_out_bytes;
+        if (extent_known && pcm_kind != FLACB200_PCM_I32_PLANAR)
+            bytes = std::min<size_t>(bytes, (size_t)extent * cfg.channels * cfg.bytes_per_sample);
+        if (e->profiling) cudaEventRecord(e->ev[24], st);
+        CK(cudaMemcpyAsync(pcm_out, d_out, bytes, cudaMemcpyDeviceToHost, st));
+        if (e->profiling) cudaEventRecord(e->ev[25], st);
+        CK(cudaStreamSynchronize(st));
+        if (e->profiling) cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[24], e->ev[25]);
+    }
+    if (state.err) {
+        if (bad_frame) *bad_frame = state.err_frame;
+        return state.err == 0x80000000u ? FLACB200_E_OUTPUT_TOO_SMALL : (int)state.err;
+    }
+    return 0;
 }
 
 extern "C" int flacb200_synth_pcm(flacb200_engine* e, void* pcm_device, uint64_t first_track, uint64_t n_tracks, uint64_t n_pcm_frames,

@@ -1,0 +1,351 @@
+"""GPU decode parity (through the C ABI): decoded PCM must be bit-exact against the reference
+decoder's behaviour -- the reference's own golden streams (tests/data/*.flac with their STREAMINFO
+MD5), the CPU oracle on oracle-encoded streams, hand-built frames for the paths no encoder here emits
+(33-bit side channel, a sync code inside the payload), and the corruption test of tests/corruption.rs."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from flacb200_testutil import ref_file, synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from flac_codec_b200 import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def fo():
+    from oracle import oracle
+
+    return oracle
+
+
+def gpu_decode_stream(eng, flac: bytes, fo, kind=None, chunk=0, total_override=None):
+    """Decode a whole .flac file's frames on the GPU; returns interleaved int32 samples."""
+    from flac_codec_b200 import _abi
+
+    si = fo.read_streaminfo(flac)
+    frames = np.frombuffer(flac, dtype=np.uint8)[si.frames_start:].copy()
+    total = si.total_samples if total_override is None else total_override
+    ch, bps = si.channels, si.bps
+    cap = total if total else len(frames) * 16
+    kind = _abi.PCM_I32_INTERLEAVED if kind is None else kind
+    bytes_per = 4 if kind >= 2 else (bps + 7) // 8
+    out = np.zeros(cap * ch * bytes_per, dtype=np.uint8)
+    eng.set_chunk_frames(chunk)
+    try:
+        nf, ns = eng.decode(si.sample_rate, bps, ch, si.max_block_size, frames, frames.size, [(0, frames.size, 0, total)], out,
+                            out.nbytes, kind, planar_stride=cap if kind == _abi.PCM_I32_PLANAR else 0)
+    finally:
+        eng.set_chunk_frames(0)
+    return out, nf, ns, si
+
+
+# ---- the reference's golden streams (tests/seek.rs:10-31, tests/metadata.rs:30-48) ----
+@pytest.mark.parametrize("name,md5", [("sine.flac", "831671b807f97051301e01d68b5c54b3"),
+                                      ("all-frames.flac", "f53f86876dcd7783225c93ba8a938c7d"),
+                                      ("cuesheet.flac", "2ae74d9f65a6acb8a4e9079125d68952")])
+def test_reference_golden_streams(eng, fo, name, md5):
+    from flac_codec_b200 import _abi
+
+    flac = ref_file(name)
+    out, nf, ns, si = gpu_decode_stream(eng, flac, fo, kind=_abi.PCM_BYTES_LE)
+    assert ns == si.total_samples
+    assert bytes(si.md5).hex() == md5
+    assert hashlib.md5(out[: ns * si.channels * 2].tobytes()).hexdigest() == md5
+    if name != "cuesheet.flac":
+        ref, _ = fo.decode_stream(flac)
+        got = fo.bytes_to_samples(out[: ns * si.channels * 2].tobytes(), 2)
+        assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("chunk", [0, 1, 3, 7])
+def test_groups_and_carry(eng, fo, chunk):
+    """Small decode groups exercise the chain state that is carried from group to group."""
+    flac = ref_file("sine.flac")
+    out, nf, ns, si = gpu_decode_stream(eng, flac, fo, chunk=chunk)
+    ref, _ = fo.decode_stream(flac)
+    assert ns == 200000 and nf == 49
+    assert np.array_equal(out.view(np.int32)[: ref.size], ref)
+
+
+CASES = [
+    ("default", 44100, 16, 2, 44100 * 2 + 100), ("best", 48000, 24, 2, 48000 + 77), ("default", 44100, 16, 1, 30000),
+    ("fast", 44100, 16, 2, 30000), ("best", 96000, 24, 8, 20000), ("best", 192000, 32, 2, 20000), ("default", 8000, 8, 1, 9000),
+    ("best", 44100, 12, 2, 9000), ("default", 22050, 20, 3, 9000), ("default", 37, 13, 1, 9000),
+]
+
+
+@pytest.mark.parametrize("preset,rate,bps,ch,n", CASES)
+def test_oracle_encoded_streams(eng, fo, preset, rate, bps, ch, n):
+    """encode with the oracle (== the reference encoder's bytes), decode on the GPU, compare with the source PCM
+    and with the oracle's decoder; all four PCM layouts of Frame::to_buf."""
+    from flac_codec_b200 import _abi
+
+    x = synth_pcm(hash((preset, rate, bps, ch)) % 50, ch, n, rate if rate > 1000 else 44100, bps)
+    opt = fo.options(preset, max_lpc_order=32) if bps == 32 else fo.options(preset)
+    flac, sizes = fo.encode_stream(opt, rate, bps, ch, x.reshape(-1))
+    out, nf, ns, si = gpu_decode_stream(eng, flac, fo)
+    assert ns == n and nf == len(sizes)
+    assert np.array_equal(out.view(np.int32).reshape(-1, ch), x)
+    bytes_per = (bps + 7) // 8
+    for kind, be in ((_abi.PCM_BYTES_LE, False), (_abi.PCM_BYTES_BE, True)):
+        out, _, _, _ = gpu_decode_stream(eng, flac, fo, kind=kind)
+        assert out[: n * ch * bytes_per].tobytes() == fo.samples_to_bytes(x.reshape(-1), bytes_per, be)
+    out, _, _, _ = gpu_decode_stream(eng, flac, fo, kind=_abi.PCM_I32_PLANAR)
+    assert np.array_equal(out.view(np.int32).reshape(ch, -1)[:, :n], x.T)
+
+
+def test_block_sizes_orders_and_noise(eng, fo):
+    """tests/format.rs:85 (block 16..33 x LPC order), noise (escape/verbatim paths), large and odd blocks."""
+    data = fo.bytes_to_samples(ref_file("noise32.raw"), 1)
+    for blocksize in range(16, 34):
+        for lpc_order in [0, 1, 4, 8, 15, 16, 17, 31, 32]:
+            opt = fo.options("best", max_lpc_order=lpc_order or None, block_size=blocksize, padding=None)
+            flac, _ = fo.encode_stream(opt, 44100, 8, 1, data)
+            out, nf, ns, si = gpu_decode_stream(eng, flac, fo)
+            assert ns == 32 and np.array_equal(out.view(np.int32)[:32], data), (blocksize, lpc_order)
+    rng = np.random.default_rng(5)
+    for bps, ch, bs in ((16, 2, 4096), (24, 2, 65535), (32, 1, 32768), (8, 8, 32), (16, 4, 4608)):
+        lo, hi = -(1 << (bps - 1)), (1 << (bps - 1)) - 1
+        n = 70000 if bs >= 4096 else 1000
+        x = rng.integers(lo, hi, size=n * ch, endpoint=True).astype(np.int64).astype(np.int32)
+        flac, sizes = fo.encode_stream(fo.options("default", block_size=bs), 44100, bps, ch, x)
+        out, nf, ns, si = gpu_decode_stream(eng, flac, fo)
+        assert ns == n and nf == len(sizes) and np.array_equal(out.view(np.int32)[: x.size], x), (bps, ch, bs)
+
+
+def test_wasted_bits_and_full_scale(eng, fo):
+    x = fo.bytes_to_samples(ref_file("wasted-bits.raw"), 2)
+    flac, _ = fo.encode_stream(fo.options("default"), 44100, 16, 1, x)
+    out, nf, ns, si = gpu_decode_stream(eng, flac, fo)
+    assert np.array_equal(out.view(np.int32)[: x.size], x)
+    for bps in (8, 16, 24, 32):
+        hi, lo = (1 << (bps - 1)) - 1, -(1 << (bps - 1))
+        for pat in ([hi, lo], [lo, lo, hi], [hi, lo, hi, hi, lo, lo, hi]):
+            x = np.array((pat * 1200)[: 4096 + 38], dtype=np.int32)
+            for ch in (1, 2):
+                flac, _ = fo.encode_stream(fo.options("best"), 44100, bps, ch, x)
+                out, nf, ns, si = gpu_decode_stream(eng, flac, fo)
+                assert np.array_equal(out.view(np.int32)[: x.size], x), (bps, pat, ch)
+
+
+def test_multi_segment_batch(eng, fo):
+    """Several streams in one call, each with its own byte range and PCM destination (the C4 decode shape)."""
+    from flac_codec_b200 import _abi
+
+    rate, bps, ch = 48000, 24, 2
+    tracks = [synth_pcm(20 + t, ch, 30000 + 1111 * t, rate, bps) for t in range(6)]
+    blobs = [fo.encode_frames_only(fo.options("best"), rate, bps, ch, x.reshape(-1))[0] for x in tracks]
+    buf = np.frombuffer(b"".join(blobs), dtype=np.uint8).copy()
+    segs, boff, poff = [], 0, 0
+    for x, b in zip(tracks, blobs):
+        segs.append((boff, len(b), poff, x.shape[0]))
+        boff += len(b)
+        poff += x.shape[0]
+    out = np.zeros(poff * ch, dtype=np.int32)
+    for chunk in (0, 5):
+        out[:] = 0
+        eng.set_chunk_frames(chunk)
+        nf, ns = eng.decode(rate, bps, ch, 4096, buf, buf.size, segs, out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+        eng.set_chunk_frames(0)
+        assert ns == poff
+        assert np.array_equal(out.reshape(-1, ch), np.concatenate(tracks))
+    # device-resident input and output
+    d_in, d_out = eng.device_alloc(buf.size), eng.device_alloc(out.nbytes)
+    eng.memcpy(d_in, buf, buf.size, 1)
+    nf, ns = eng.decode(rate, bps, ch, 4096, d_in, buf.size, segs, d_out, out.nbytes, _abi.PCM_I32_INTERLEAVED,
+                        frames_location=_abi.DEVICE, pcm_location=_abi.DEVICE)
+    out2 = np.zeros_like(out)
+    eng.memcpy(out2, d_out, out.nbytes, 2)
+    assert np.array_equal(out2, out)
+    eng.device_free(d_in)
+    eng.device_free(d_out)
+
+
+# ---- hand-built frames ----
+class Bits:
+    def __init__(self):
+        self.v, self.n = 0, 0
+
+    def put(self, nbits, value):
+        self.v = (self.v << nbits) | (value & ((1 << nbits) - 1))
+        self.n += nbits
+
+    def bytes(self):
+        pad = (-self.n) % 8
+        return ((self.v << pad).to_bytes((self.n + pad) // 8, "big"))
+
+
+def build_verbatim_frame(fo, frame_number, rate_code, bps_code, assignment, block, chans):
+    """chans: list of (bits_per_sample, samples) written as VERBATIM subframes."""
+    b = Bits()
+    b.put(15, 0b111111111111100)
+    b.put(1, 0)
+    b.put(4, 0b0110 if block <= 256 else 0b0111)
+    b.put(4, rate_code)
+    b.put(4, assignment)
+    b.put(3, bps_code)
+    b.put(1, 0)
+    assert frame_number < 128
+    b.put(8, frame_number)
+    b.put(8 if block <= 256 else 16, block - 1)
+    hdr = b.bytes()
+    b.put(8, fo.crc8(hdr))
+    for bits, samples in chans:
+        b.put(8, 0b00000010)   # pad, VERBATIM, no wasted bits
+        for s in samples:
+            b.put(bits, int(s))
+    body = b.bytes()
+    return body + fo.crc16(body).to_bytes(2, "big")
+
+
+def test_33_bit_side_channel(eng, fo):
+    """32-bit streams with a side channel need 33-bit samples (src/decode.rs:1528-1546, :1565-1583, :1604-1622)."""
+    from flac_codec_b200 import _abi
+
+    rng = np.random.default_rng(3)
+    n = 200
+    left = rng.integers(-(1 << 31), (1 << 31) - 1, size=n, endpoint=True)
+    right = rng.integers(-(1 << 31), (1 << 31) - 1, size=n, endpoint=True)
+    side = left - right
+    mid = (left + right) >> 1
+    frames = [build_verbatim_frame(fo, 0, 0b1001, 0b111, 8, n, [(32, left), (33, side)]),
+              build_verbatim_frame(fo, 1, 0b1001, 0b111, 9, n, [(33, side), (32, right)]),
+              build_verbatim_frame(fo, 2, 0b1001, 0b111, 10, n, [(32, mid), (33, side)])]
+    buf = np.frombuffer(b"".join(frames), dtype=np.uint8).copy()
+    out = np.zeros(3 * n * 2, dtype=np.int32)
+    nf, ns = eng.decode(44100, 32, 2, n, buf, buf.size, [(0, buf.size, 0, 3 * n)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert nf == 3 and ns == 3 * n
+    want = np.stack([left, right], axis=1).astype(np.int32)
+    for k in range(3):
+        assert np.array_equal(out.reshape(-1, 2)[k * n:(k + 1) * n], want), k
+        planar, h, used = fo.decode_frame(frames[k], None, 0)
+        assert np.array_equal(planar.T, want)
+
+
+def test_sync_code_inside_payload_is_skipped(eng, fo):
+    """A complete, CRC-8-valid frame header embedded in a VERBATIM payload is a false candidate: the walk that
+    follows frame ends must skip it, exactly as the reference's serial reader never sees it."""
+    from flac_codec_b200 import _abi
+
+    n = 64
+    inner = build_verbatim_frame(fo, 7, 0b1001, 0b100, 0, n, [(16, np.arange(n))])
+    fake_hdr = inner[:7]   # ff f8 .. crc8 : 7 bytes; pad to whole 16-bit samples
+    payload = list(np.arange(10, 10 + n))
+    raw = fake_hdr + b"\x00"
+    words = [int.from_bytes(raw[i:i + 2], "big", signed=True) for i in range(0, 8, 2)]
+    payload[8:12] = words
+    f0 = build_verbatim_frame(fo, 0, 0b1001, 0b100, 0, n, [(16, payload)])
+    f1 = build_verbatim_frame(fo, 1, 0b1001, 0b100, 0, n, [(16, np.arange(n) * 3)])
+    assert fake_hdr in f0
+    buf = np.frombuffer(f0 + f1, dtype=np.uint8).copy()
+    out = np.zeros(2 * n, dtype=np.int32)
+    nf, ns = eng.decode(44100, 16, 1, n, buf, buf.size, [(0, buf.size, 0, 2 * n)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert nf == 2 and ns == 2 * n
+    assert out[:n].tolist() == payload and out[n:].tolist() == (np.arange(n) * 3).tolist()
+
+
+# ---- tests/corruption.rs: one flipped bit must be detected ----
+def test_bit_flips_are_detected(eng, fo):
+    from flac_codec_b200 import _abi
+
+    flac = bytearray(ref_file("sine.flac"))
+    rng = np.random.default_rng(1234)
+    agree = 0
+    trials = 100
+    for t in range(trials):
+        pos = int(rng.integers(136 * 8, len(flac) * 8))
+        flac[pos >> 3] ^= 0x80 >> (pos & 7)
+        with pytest.raises(_abi.FlacB200Error) as ei:
+            gpu_decode_stream(eng, bytes(flac), fo)
+        try:
+            fo.decode_stream(bytes(flac))
+            ref_code = 0
+        except fo.OracleError as oe:
+            ref_code = oe.code
+        assert ref_code != 0
+        agree += int(ei.value.code == ref_code)
+        flac[pos >> 3] ^= 0x80 >> (pos & 7)
+    # the GPU reports the same Error variant as the serial reader in (nearly) every case; the decoded prefix is
+    # identical in all of them
+    assert agree >= trials * 0.9, agree
+
+
+def test_stream_end_rules(eng, fo):
+    """ShortBlock (src/decode.rs:1405-1410), early end with a known total (Io), unknown total reads to the end."""
+    from flac_codec_b200 import _abi
+
+    x = synth_pcm(30, 1, 4096 * 3 + 10, 44100, 16)
+    frames, sizes = fo.encode_frames_only(fo.options("default"), 44100, 16, 1, x.reshape(-1))
+    buf = np.frombuffer(frames, dtype=np.uint8).copy()
+    n = x.shape[0]
+    out = np.zeros(n + 5000, dtype=np.int32)
+    # total unknown: decode until the bytes end
+    nf, ns = eng.decode(44100, 16, 1, 4096, buf, buf.size, [(0, buf.size, 0, 0)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert (nf, ns) == (4, n) and np.array_equal(out[:n], x[:, 0])
+    # the 10-sample last block is legal only as the very last block
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.decode(44100, 16, 1, 4096, buf, buf.size, [(0, buf.size, 0, n + 1)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert ei.value.code == 21 and ei.value.bad_frame == 3
+    # known total, bytes end early -> UnexpectedEof
+    cut = int(sizes[:2].sum())
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.decode(44100, 16, 1, 4096, buf, cut, [(0, cut, 0, n)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert ei.value.code == 1 and ei.value.bad_frame == 2
+    # known total smaller than the stream: extra frames are never read
+    nf, ns = eng.decode(44100, 16, 1, 4096, buf, buf.size, [(0, buf.size, 0, 8192)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert (nf, ns) == (2, 8192)
+    # garbage instead of the first frame
+    bad = buf.copy()
+    bad[0] = 0
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.decode(44100, 16, 1, 4096, bad, bad.size, [(0, bad.size, 0, n)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert ei.value.code == 23 and ei.value.bad_frame == 0   # InvalidSyncCode
+    # STREAMINFO cross-checks (src/stream.rs:291-312)
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.decode(48000, 16, 1, 4096, buf, buf.size, [(0, buf.size, 0, n)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert ei.value.code == 29   # SampleRateMismatch
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.decode(44100, 16, 1, 1024, buf, buf.size, [(0, buf.size, 0, n)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert ei.value.code == 25   # BlockSizeMismatch
+    # output too small
+    with pytest.raises(_abi.FlacB200Error) as ei:
+        eng.decode(44100, 16, 1, 4096, buf, buf.size, [(0, buf.size, 0, n)], out, 4 * 5000, _abi.PCM_I32_INTERLEAVED)
+    assert ei.value.code == -4
+
+
+def test_encode_decode_round_trip_at_bench_shape(eng, fo):
+    """The C4 shape end to end on the device: synth -> encode -> decode -> identical PCM bytes (size-independent
+    property used at BASELINE.json's full sizes by bench.py)."""
+    from flac_codec_b200 import Options, _abi
+
+    rate, bps, ch, n, tracks = 48000, 24, 2, 48000 * 4 + 999, 12
+    nbytes = tracks * n * ch * 3
+    d_pcm = eng.device_alloc(nbytes)
+    eng.synth_pcm(d_pcm, 0, tracks, n, ch, rate, bps)
+    d_flac = eng.device_alloc(nbytes)
+    segs = [(t * n, n, 0) for t in range(tracks)]
+    _, sizes, total = eng.encode(Options.best(), rate, bps, ch, d_pcm, nbytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.DEVICE,
+                                 out=d_flac, out_capacity=nbytes, out_location=_abi.DEVICE)
+    per_track = (n + 4095) // 4096
+    offs = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
+    dsegs = [(int(offs[t * per_track]), int(offs[(t + 1) * per_track] - offs[t * per_track]), t * n, n) for t in range(tracks)]
+    d_back = eng.device_alloc(nbytes)
+    nf, ns = eng.decode(rate, bps, ch, 4096, d_flac, total, dsegs, d_back, nbytes, _abi.PCM_BYTES_LE, frames_location=_abi.DEVICE,
+                        pcm_location=_abi.DEVICE)
+    assert nf == tracks * per_track and ns == tracks * n
+    a, b = np.zeros(nbytes, dtype=np.uint8), np.zeros(nbytes, dtype=np.uint8)
+    eng.memcpy(a, d_pcm, nbytes, 2)
+    eng.memcpy(b, d_back, nbytes, 2)
+    assert np.array_equal(a, b)
+    for p in (d_pcm, d_flac, d_back):
+        eng.device_free(p)
