@@ -324,9 +324,6 @@ def run_gpu(args):
             dist.all_reduce(dms, op=dist.ReduceOp.MAX)
         dms_step = float(dms.item()) / args.steps
         # bit-exactness at full size: a 64-bit checksum of checksums over the PCM bytes, input vs decoded
-        a = torch.empty(0)
-        import ctypes as C
-
         def dev_u8(ptr, nbytes):
             class _W:
                 __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
