@@ -206,6 +206,24 @@ __host__ __device__ inline uint32_t gf16_mulmod(uint32_t a, uint32_t b)
     return r;
 }
 
+// ---- wide integer helpers ----
+// d = a * b + c with 32-bit signed a, b and a 64-bit accumulator: one IMAD.WIDE (the C++ form (long long)a * b
+// compiles to a four-instruction 64 x 64 multiply)
+__device__ inline long long mad_wide_s32(int32_t a, int32_t b, long long c)
+{
+    long long d;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
+// acc + v for a 32-bit v and a 64-bit accumulator in one IMAD.WIDE.U32
+__device__ inline unsigned long long acc_u32(unsigned long long acc, uint32_t v)
+{
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(d) : "r"(v), "l"(acc));
+    return d;
+}
+
 // ---- misc ------------------------------------------------------------------------------------
 __host__ __device__ inline uint32_t lpc_precision_for(uint32_t n)   // src/encode.rs:3305-3315
 {
@@ -215,6 +233,7 @@ __host__ __device__ inline uint32_t lpc_precision_for(uint32_t n)   // src/encod
 __device__ inline uint32_t uabs32(int32_t v) { return v < 0 ? 0u - (uint32_t)v : (uint32_t)v; }
 
 // zig-zag exactly as src/encode.rs:3845-3849 (u32 arithmetic)
-__device__ inline uint32_t zigzag32(int32_t s) { return s < 0 ? ((((uint32_t)(-(long long)s)) - 1u) << 1) + 1u : ((uint32_t)s) << 1; }
+// (for s < 0: ((-s - 1) << 1) + 1 == ~(2 s); for s >= 0: 2 s)
+__device__ inline uint32_t zigzag32(int32_t s) { return ((uint32_t)s << 1) ^ (uint32_t)(s >> 31); }
 
 }   // namespace flacb200

@@ -470,7 +470,7 @@ __device__ uint32_t decode_subframe(BitReader& br, uint32_t bps, uint32_t n, int
         const uint32_t s = order + idx;
         long long sum = 0;
         for (uint32_t j = 0; j < order; j++)   // predict (src/decode.rs:1738-1752)
-            sum += (long long)hist[((s - 1 - j) & 31) * DEC_THREADS] * (long long)coef[j * DEC_THREADS];
+            sum = mad_wide_s32(hist[((s - 1 - j) & 31) * DEC_THREADS], coef[j * DEC_THREADS], sum);
         const int32_t x = (int32_t)((uint32_t)r + (uint32_t)(unsigned long long)(sum >> shift));
         hist[(s & 31) * DEC_THREADS] = x;
         pw.push(x);

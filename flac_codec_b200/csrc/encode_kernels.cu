@@ -15,7 +15,10 @@
 //   k_crc16     CTA per frame: chunked CRC-16 combined with x^(8 len) mod P
 //
 // Reference statements followed by each kernel are cited inline (paths relative to flac-codec 1.3.2).
+#include <type_traits>
+
 #include "common.cuh"
+#include "crc.cuh"
 
 namespace flacb200 {
 
@@ -553,7 +556,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual(EncCfg cfg, const Fram
         uint32_t bad = 0;
         for (uint32_t i = order + tid; i < n; i += RES_THREADS) {
             long long sum = 0;
-            for (uint32_t j = 0; j < order; j++) sum += (long long)xs[i - 1 - j] * (long long)lp.q[j];   // :3187-3192
+            for (uint32_t j = 0; j < order; j++) sum = mad_wide_s32(xs[i - 1 - j], lp.q[j], sum);   // :3187-3192
             const int32_t pred = (int32_t)(uint32_t)(unsigned long long)(sum >> shift);             // `as i32`
             const long long rr = (long long)xs[i] - (long long)pred;
             if (rr < INT32_MIN || rr > INT32_MAX) bad = 1;                                         // checked_sub -> ResidualOverflow
@@ -884,7 +887,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack(EncCfg cfg, uint32_t nsub
                         }
                     } else {
                         long long sum = 0;
-                        for (uint32_t j = 0; j < order; j++) sum += (long long)X(ia - 1 - j) * (long long)cr.q[j];
+                        for (uint32_t j = 0; j < order; j++) sum = mad_wide_s32(X(ia - 1 - j), cr.q[j], sum);
                         d = (long long)X(ia) - (long long)(int32_t)(uint32_t)(unsigned long long)(sum >> shift);
                     }
                     r[e] = (int32_t)d;
@@ -999,6 +1002,9 @@ __global__ void __launch_bounds__(CRC_THREADS) k_crc16(const FrameRec* __restric
     }
 }
 
+uint32_t pack_cap_words(const EncCfg& cfg);
+#include "encode_fast.inl"
+
 // ------------------------------------------------------------------------------------------------
 // launch wrappers (called from engine.cu)
 // ------------------------------------------------------------------------------------------------
@@ -1015,8 +1021,6 @@ void launch_lpc(const EncCfg& cfg, const FrameDesc* descs, const int32_t* planes
     const uint32_t ncand = cfg.nframes * cfg.nslots;
     k_lpc<<<(ncand + LPC_WARPS - 1) / LPC_WARPS, 32 * LPC_WARPS, 0, st>>>(cfg, descs, planes, ormask, abssum, winpool, lpcs, ncand);
 }
-
-constexpr uint32_t SMEM_LIMIT = 200 * 1024;
 
 bool residual_uses_smem(const EncCfg& cfg) { return (size_t)cfg.bpad * 8 <= 96 * 1024; }
 

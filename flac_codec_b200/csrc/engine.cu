@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -25,6 +26,10 @@ cudaError_t launch_residual(const EncCfg&, const FrameDesc*, const int32_t*, con
 void launch_decide_scan(const EncCfg&, const FrameDesc*, const CandRec*, const unsigned long long*, FrameRec*, uint32_t*, unsigned long long*,
                         uint8_t*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
+bool analyze_fast_ok(const EncCfg&);
+cudaError_t launch_pack2_crc(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
+cudaError_t launch_lpc2(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, cudaStream_t);
+cudaError_t launch_analyze(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, cudaStream_t);
 // synth.cu
 cudaError_t launch_synth(uint8_t* pcm, unsigned long long first_track, unsigned long long n_tracks, unsigned long long n_pcm_frames,
                          uint32_t channels, uint32_t sample_rate, uint32_t bps, unsigned long long seed, const int32_t* lut, cudaStream_t st);
@@ -367,11 +372,21 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     const size_t bound = (size_t)nframes * frame_bound(bs, cfg.channels, cfg.bps) + 64;
 
     // ---- device buffers ----
-    uint32_t chunk = e->chunk_frames ? e->chunk_frames : 2048;
+    // kernel selection: the register-tiled kernels cover the common shapes; FLACB200_LEGACY (bit mask: 1 analyze,
+    // 2 lpc, 4 pack) forces the generic kernels, which the parity tests use to cover both paths
+    const char* legacy_env = getenv("FLACB200_LEGACY");
+    const unsigned legacy = legacy_env ? (unsigned)strtoul(legacy_env, nullptr, 0) : 0u;
+    const bool fast_analyze = analyze_fast_ok(cfg) && !(legacy & 1u);
+    const bool fast_lpc = cfg.max_lpc_order >= 1 && !(legacy & 2u);
+    const bool fast_pack = analyze_fast_ok(cfg) && !(legacy & 4u);
+    const bool need_planes = !(fast_analyze && fast_pack && (fast_lpc || cfg.max_lpc_order == 0));
+    // launch group: without the int32 planes a group costs ~250 bytes per candidate, so it can be large enough to fill
+    // the GPU even for the warp-per-8-candidates LPC kernel; with planes it is sized to stay near the L2 capacity
+    uint32_t chunk = e->chunk_frames ? e->chunk_frames : (need_planes ? 2048 : 32768);
     chunk = (uint32_t)std::min<uint64_t>(std::min<uint32_t>(chunk, 32768), nframes);
     const size_t ncand_chunk = (size_t)chunk * cfg.nslots;
     ENS(e->descs, nframes * sizeof(FrameDesc));
-    ENS(e->planes, ncand_chunk * cfg.bpad * sizeof(int32_t));
+    if (need_planes) ENS(e->planes, ncand_chunk * cfg.bpad * sizeof(int32_t));
     ENS(e->masks, (size_t)chunk * (cfg.nslots * sizeof(uint32_t) + 4 * sizeof(unsigned long long)) + 64);
     ENS(e->lpcs, ncand_chunk * sizeof(LpcRec));
     ENS(e->cands, ncand_chunk * sizeof(CandRec));
@@ -422,17 +437,21 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         CK(cudaMemsetAsync(e->masks.p, 0, masks_bytes, st));
         const size_t eb = nchunks * 6;
         time_mark(e, eb + 0);
-        launch_planes(c, dd, d_pcm, (int32_t*)e->planes.p, d_ormask, d_abssum, st);
+        if (need_planes) launch_planes(c, dd, d_pcm, (int32_t*)e->planes.p, d_ormask, d_abssum, st);
         time_mark(e, eb + 1);
-        launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st);
+        if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st));
+        else launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st);
         time_mark(e, eb + 2);
-        CK(launch_residual(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p,
-                           (int32_t*)e->scratch.p, st));
+        if (fast_analyze) CK(launch_analyze(c, dd, d_pcm, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p, d_abssum, st));
+        else
+            CK(launch_residual(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p,
+                               (int32_t*)e->scratch.p, st));
         time_mark(e, eb + 3);
         launch_decide_scan(c, dd, (const CandRec*)e->cands.p, d_abssum, (FrameRec*)e->frecs.p, (uint32_t*)e->fbytes.p + base,
                            (unsigned long long*)e->totals.p, (uint8_t*)e->out.p, st);
         time_mark(e, eb + 4);
-        CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, (uint8_t*)e->out.p, st));
+        if (fast_pack) CK(launch_pack2_crc(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, (uint8_t*)e->out.p, st));
+        else CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, (uint8_t*)e->out.p, st));
         time_mark(e, eb + 5);
         nchunks++;
         launches += 8;

@@ -261,3 +261,23 @@ def test_argument_errors(eng):
     # empty input: no frames, no error
     data, sizes, total = eng.encode(Options.default(), 44100, 16, 2, raw, 0, _abi.PCM_BYTES_LE, [(0, 0, 0)])
     assert total == 0 and len(sizes) == 0
+
+
+def test_generic_kernels_give_the_same_bytes(eng, fo, monkeypatch):
+    """The engine picks register-tiled kernels for blocks <= 4096 / samples <= 28 bits / LPC order <= 16 and generic
+    ones otherwise; FLACB200_LEGACY forces the generic kernels so that both paths are checked on the same inputs."""
+    from flac_codec_b200 import Options
+
+    cases = [
+        ("16b stereo default", Options.default(), 44100, 16, 2, synth_pcm(0, 2, 44100 + 100, 44100, 16)),
+        ("24b stereo best", Options.best(), 48000, 24, 2, synth_pcm(1, 2, 48000 + 77, 48000, 24)),
+        ("16b mono default", Options.default(), 44100, 16, 1, synth_pcm(2, 1, 30000, 44100, 16)),
+        ("24b 8ch best", Options.best(), 96000, 24, 8, synth_pcm(4, 8, 12000, 96000, 24)),
+        ("16b stereo fast-corr", Options.default().fast_channel_correlation(True), 44100, 16, 2, synth_pcm(7, 2, 30000, 44100, 16)),
+        ("8b stereo bs 33", Options.best().block_size(33), 44100, 8, 2, synth_pcm(8, 2, 3000, 44100, 8)),
+    ]
+    for mask in ("7", "1", "2", "4"):
+        monkeypatch.setenv("FLACB200_LEGACY", mask)
+        for label, opt, rate, bps, ch, x in cases:
+            check(eng, fo, opt, rate, bps, ch, x, f"legacy={mask} {label}")
+    monkeypatch.delenv("FLACB200_LEGACY")
