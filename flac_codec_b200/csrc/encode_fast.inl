@@ -13,19 +13,6 @@ constexpr int AN_TILE = AN_THREADS * AN_SPT;    // 4096: largest block of the fa
 constexpr int AN_PAD = 32;                      // zero samples in front of every plane (history of the first thread)
 constexpr int AN_STRIDE = AN_TILE + AN_PAD;
 
-struct AnSmem {
-    unsigned long long chunk_sum[2 * MAX_PARTS];   // two residual sets (fixed, LPC) are searched together
-    unsigned long long acc[8];
-    unsigned long long absum[4];
-    uint32_t part_est[256];
-    uint8_t part_code[256];
-    uint32_t ord_est[16], ord_cnt[16], ord_ok[16];
-    uint32_t orm[4];
-    uint32_t flag, flag2[2];
-    RiceChoice fixed, lpc;
-    int16_t q[MAX_LPC];
-};
-
 // ---- packed PCM -> 16 consecutive inter-channel samples of C channels (Frame::fill_from_buf, src/audio.rs:149-187) ----
 template <int C, int B>
 __device__ inline void load16(const uint8_t* __restrict__ p, bool big_endian, int32_t* __restrict__ v)
@@ -109,24 +96,54 @@ __device__ inline void block_add(unsigned long long* slot, unsigned long long v)
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(slot, v);
 }
 
-// ---- best_partitions + try_reduce_rice + exact size, on residuals held in registers ----
-// Searches NS (1 or 2) residual sets of the same block at once -- the fixed and the LPC residuals of a candidate --
-// so that both share every barrier.  r[k][e] is the residual of sample i0 + e in set k; only samples in [o[k], n) count.
+// ------------------------------------------------------------------------------------------------
+// k_analyze: encode_subframe (src/encode.rs:2849-2980) without emitting bits -- ONE WARP PER CANDIDATE.
+//
+// The block is cut into 16-sample tiles; in round r lane l owns tile 32 r + l, so a round's PCM loads are one
+// contiguous 128-bit-per-lane read.  A tile's history (the fixed differences and the LPC FIR look back <= 16 samples)
+// is the left neighbour's tile, fetched with warp shuffles -- the samples never touch shared memory.  Everything that
+// used to be a CTA-wide barrier is a warp shuffle; warps never wait for each other.
+//   pass 1: |residual| sums of fixed orders 0..4 and of the LPC residual, per finest Rice partition
+//           (24-bit limbs in warp-private shared memory, native 32-bit atomics) + the totals that pick the fixed order
+//   then  : partition tree, Partition::new for every (order, partition), first-minimum partition order
+//   pass 2: residuals of the chosen fixed order and of the LPC predictor again, exact Rice bit counts
+// Wasted bits are assumed 0 while the OR mask is gathered in pass 1; a candidate that has some restarts once.
+// ------------------------------------------------------------------------------------------------
+constexpr int AW_WARPS = 4;
+constexpr int AW_SETS = 6;   // fixed orders 0..4, LPC
 
-// rare: a thread's 16 samples straddle a boundary of the finest partition (block length not a multiple of 16 << p_max)
-__device__ __noinline__ void chunk_sums_slow(const int32_t* r, uint32_t i0, uint32_t lo, uint32_t hi, uint32_t cf, unsigned long long* chunk_sum)
+struct AwSmem {   // per warp
+    uint32_t limb_lo[AW_SETS][MAX_PARTS], limb_hi[AW_SETS][MAX_PARTS];
+    unsigned long long tree[2][128];   // [set][ (1 << p) - 1 + j ]: sum |r| of partition j at order p
+    uint32_t part_est[2][128];
+    uint8_t part_code[2][128];
+    unsigned long long u[5];   // per fixed order k: sum |r| of the samples in [k, kmax)
+    RiceChoice choice[2];
+};
+
+struct AwSmemLimbs {
+    uint32_t* lo;
+    uint32_t* hi;
+};
+
+// rare path: a 16-sample tile that straddles a partition boundary, contains samples before the predictor order, or is cut by the block end
+__device__ __noinline__ void aw_tile_sums_slow(const int32_t* r, uint32_t i0, uint32_t first, uint32_t end, uint32_t cf, uint32_t* lo, uint32_t* hi)
 {
-    for (uint32_t i = lo; i < hi; i++)
-        if (r[i - i0]) atomicAdd(&chunk_sum[i / cf], (unsigned long long)uabs32(r[i - i0]));
+    for (uint32_t i = max(i0, first); i < min(i0 + 16u, end); i++) {
+        const uint32_t v = uabs32(r[i - i0]);
+        if (v) {
+            atomicAdd(&lo[i / cf], v & 0xFFFFFFu);
+            atomicAdd(&hi[i / cf], v >> 24);
+        }
+    }
 }
 
-// rare: partial thread, escaped partition, or more than one partition inside the thread's samples
-__device__ __noinline__ void exact_bits_slow(const int32_t* r, uint32_t i0, uint32_t lo, uint32_t hi, uint32_t cp, uint32_t j0, const uint8_t* rice,
-                                             unsigned long long* bits_out, uint32_t* bad_out)
+__device__ __noinline__ void aw_tile_bits_slow(const int32_t* r, uint32_t i0, uint32_t first, uint32_t end, uint32_t cp, uint32_t j0,
+                                               const uint8_t* rice, unsigned long long* bits_io, uint32_t* bad_io)
 {
-    unsigned long long bits = 0;
-    uint32_t bad = 0;
-    for (uint32_t i = lo; i < hi; i++) {
+    unsigned long long bits = *bits_io;
+    uint32_t bad = *bad_io;
+    for (uint32_t i = max(i0, first); i < min(i0 + 16u, end); i++) {
         const uint32_t c = rice[i / cp - j0];
         const int32_t s = r[i - i0];
         if (c < 0x40) bits += (zigzag32(s) >> c) + 1u + c;
@@ -136,288 +153,407 @@ __device__ __noinline__ void exact_bits_slow(const int32_t* r, uint32_t i0, uint
             if (s < -(1 << (w - 1)) || s > (1 << (w - 1)) - 1) bad = 1;   // write_signed_counted fails
         }
     }
-    *bits_out = bits;
-    *bad_out = bad;
+    *bits_io = bits;
+    *bad_io = bad;
 }
 
-template <int NS>
-__device__ void rice_search_regs(const int32_t (*r)[AN_SPT], uint32_t i0, const uint32_t* o, uint32_t n, const EncCfg& cfg, AnSmem& sm,
-                                 RiceChoice* const* outs)
+// pass-1 work of a rare tile (first tile of the block, tile cut by the block end, tile straddling a partition boundary):
+// fixed orders 0..4 and the LPC residual rl, sample by sample
+__device__ __noinline__ void aw_pass1_tile_slow(const int32_t* x, const int32_t* h, const int32_t* rl, bool have_lpc, uint32_t order, uint32_t i0,
+                                                uint32_t n, uint32_t kmax, uint32_t cf, AwSmemLimbs limbs, unsigned long long* u)
 {
-    const uint32_t tid = threadIdx.x;
+    int32_t r[5][16];
+    int32_t p1 = h[15] - h[14], p2 = p1 - (h[14] - h[13]), p3 = p2 - ((h[14] - h[13]) - (h[13] - h[12]));
+    int32_t prev = h[15];
+    for (int e = 0; e < 16; e++) {
+        const int32_t e1 = x[e] - prev, e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
+        prev = x[e]; p1 = e1; p2 = e2; p3 = e3;
+        r[0][e] = x[e]; r[1][e] = e1; r[2][e] = e2; r[3][e] = e3; r[4][e] = e4;
+    }
+    for (uint32_t k = 0; k < 5; k++) {
+        aw_tile_sums_slow(r[k], i0, k, n, cf, limbs.lo + k * MAX_PARTS, limbs.hi + k * MAX_PARTS);
+        if (i0 == 0) {   // what set k counts but the order comparison (:3062-3073, samples >= kmax only) does not
+            unsigned long long v = 0;
+            for (uint32_t i = k; i < kmax && i < 16 && i < n; i++) v += uabs32(r[k][i]);
+            u[k] = v;
+        }
+    }
+    if (have_lpc) aw_tile_sums_slow(rl, i0, order, n, cf, limbs.lo + 5 * MAX_PARTS, limbs.hi + 5 * MAX_PARTS);
+}
+
+__device__ inline void aw_add_limbs(uint32_t* lo, uint32_t* hi, uint32_t chunk, unsigned long long v)
+{
+    if (v) {
+        atomicAdd(&lo[chunk], (uint32_t)v & 0xFFFFFFu);
+        atomicAdd(&hi[chunk], (uint32_t)(v >> 24));
+    }
+}
+
+// best_partitions + try_reduce_rice (src/encode.rs:3865-3942) for one residual set, by one warp.
+// tree[] holds the per-partition sums of every order; fills ch (rice[], geometry, method) -- not the size.
+__device__ void aw_choose_partitions(const EncCfg& cfg, uint32_t n, uint32_t o, uint32_t p_max, const unsigned long long* tree, uint32_t* part_est,
+                                     uint8_t* part_code, RiceChoice& ch)
+{
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t rice_max = cfg.use_rice2 ? 31u : 15u;
+    for (uint32_t t = lane; t < 127; t += 32) {   // (order p, partition j)
+        const uint32_t p = 31u - (uint32_t)__clz((int)(t + 1));
+        const uint32_t j = t + 1 - (1u << p);
+        uint8_t code = 0xFE;
+        uint32_t est = 0;
+        if (p <= p_max) {
+            const uint32_t cp = n >> p;
+            const uint32_t a = j * cp, b = a + cp;
+            if (b > o) code = partition_code(tree[t], b - max(a, o), rice_max, &est);
+        }
+        part_code[t] = code;
+        part_est[t] = est;
+    }
+    __syncwarp();
+    // lane p < 7 totals order p
+    uint32_t est = 0, cnt = 0, bad = 0;
+    if (lane <= p_max) {
+        const uint32_t base = (1u << lane) - 1;
+        for (uint32_t j = 0; j < (1u << lane); j++) {
+            const uint8_t c = part_code[base + j];
+            if (c == 0xFE) continue;
+            if (c == 0xFF) bad = 1;
+            cnt++;
+            est += part_est[base + j];
+        }
+    }
+    const bool ok = lane <= p_max && !bad && cnt != 0 && (cnt & (cnt - 1)) == 0;   // :3880-3881
+    const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+    if (okmask == 0) {   // unwrap_or_else (:3887): one partition escaped at 31 bits
+        if (lane == 0) {
+            ch.porder_g = 0; ch.porder_w = 0; ch.nparts = 1; ch.rice[0] = 0x40 | 31;
+            ch.method = cfg.use_rice2 ? 1 : 0;
+        }
+        __syncwarp();
+        return;
+    }
+    const uint32_t best_est = __reduce_min_sync(0xffffffffu, ok ? est : 0xFFFFFFFFu);
+    const uint32_t best_p = (uint32_t)__ffs((int)(__ballot_sync(0xffffffffu, ok && est == best_est))) - 1u;   // first minimum :3885
+    const uint32_t best_count = __shfl_sync(0xffffffffu, cnt, best_p);
+    const uint32_t base = (1u << best_p) - 1, j0 = (1u << best_p) - best_count;
+    uint32_t big = 0;
+    for (uint32_t j = lane; j < best_count; j += 32) {
+        const uint8_t c = part_code[base + j0 + j];
+        ch.rice[j] = c;
+        if (c < 0x40 && c >= 15) big = 1;
+    }
+    big = __any_sync(0xffffffffu, big);
+    if (lane == 0) {
+        ch.porder_g = (uint8_t)best_p;
+        ch.nparts = (uint8_t)best_count;
+        ch.porder_w = (uint8_t)(31u - (uint32_t)__clz((int)best_count));   // partitions.len().ilog2() :3902
+        ch.method = (cfg.use_rice2 && big) ? 1 : 0;                         // try_reduce_rice :3929-3942
+    }
+    __syncwarp();
+}
+
+// the candidate's 16 samples starting at i0 (zeros past the block end), before the wasted-bit shift
+template <bool STEREO>
+__device__ inline void aw_load_tile(const EncCfg& cfg, const FrameDesc& d, const uint8_t* __restrict__ pcm, uint32_t slot, uint32_t i0, int32_t* x)
+{
+    if (STEREO) {
+        int32_t a[16], b[16];
+        load_thread_samples<2>(cfg, d, pcm, i0, 0, a, b);
+        switch (slot) {   // uniform across the warp
+        case 0:
+#pragma unroll
+            for (int e = 0; e < 16; e++) x[e] = a[e];
+            break;
+        case 1:
+#pragma unroll
+            for (int e = 0; e < 16; e++) x[e] = b[e];
+            break;
+        case 2:
+#pragma unroll
+            for (int e = 0; e < 16; e++) x[e] = (a[e] + b[e]) >> 1;   // :2721
+            break;
+        default:
+#pragma unroll
+            for (int e = 0; e < 16; e++) x[e] = a[e] - b[e];          // :2734
+            break;
+        }
+    } else if (cfg.channels == 1) {
+        int32_t b[1];
+        load_thread_samples<1>(cfg, d, pcm, i0, 0, x, b);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = i0 + e < d.n ? load_pcm_sample(pcm, cfg, d.pcm_off + i0 + e, slot) : 0;
+    }
+}
+
+// HB: the launch's max LPC order rounded up to 4/8/12/16 (one instantiation per launch keeps the instruction
+// footprint small; predictors of lower order run with zero coefficients)
+template <int HB, bool STEREO>
+__device__ void aw_candidate(const EncCfg& cfg, const FrameDesc& d, const uint8_t* __restrict__ pcm, uint32_t slot, uint32_t full_bps,
+                             const LpcRec& lp, AwSmem& sm, CandRec* __restrict__ rec)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = d.n;
+    const uint32_t rounds = ((n + 15) / 16 + 31) / 32;   // in round r lane l owns the 16-sample tile r * 32 + l: coalesced PCM loads
     uint32_t p_max = (uint32_t)__ffs((int)n) - 1u;
     if (p_max > cfg.max_porder) p_max = cfg.max_porder;
     if (p_max > MAX_PORDER) p_max = MAX_PORDER;
-    const uint32_t cf = n >> p_max;   // finest chunk
-    const bool cf_pow2 = (cf & (cf - 1)) == 0;
-    const uint32_t cf_shift = 31u - (uint32_t)__clz((int)cf);
-    if (tid < NS * MAX_PARTS) sm.chunk_sum[tid] = 0;
-    if (tid < 2) { sm.acc[tid] = 0; sm.flag2[tid] = 0; }
-    __syncthreads();
-    uint32_t lo[NS], hi[NS];
-    bool full[NS];
-#pragma unroll
-    for (int k = 0; k < NS; k++) {
-        lo[k] = max(i0, o[k]);
-        hi[k] = min(i0 + AN_SPT, n);
-        full[k] = lo[k] == i0 && hi[k] == i0 + AN_SPT;   // all 16 samples are residuals
-        if (lo[k] < hi[k]) {
-            const uint32_t m_lo = cf_pow2 ? lo[k] >> cf_shift : lo[k] / cf, m_hi = cf_pow2 ? (hi[k] - 1) >> cf_shift : (hi[k] - 1) / cf;
-            if (m_lo == m_hi) {
-                unsigned long long sum = 0;
-                if (full[k]) {
-#pragma unroll
-                    for (int e = 0; e < AN_SPT; e++) sum = acc_u32(sum, uabs32(r[k][e]));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < AN_SPT; e++)
-                        if (i0 + e >= lo[k] && i0 + e < hi[k]) sum += uabs32(r[k][e]);
-                }
-                if (sum) atomicAdd(&sm.chunk_sum[k * MAX_PARTS + m_lo], sum);
-            } else {
-                int32_t tmp[AN_SPT];   // a copy: taking the address of r itself would push the register tile into local memory
-#pragma unroll
-                for (int e = 0; e < AN_SPT; e++) tmp[e] = r[k][e];
-                chunk_sums_slow(tmp, i0, lo[k], hi[k], cf, sm.chunk_sum + k * MAX_PARTS);
-            }
-        }
-    }
-    __syncthreads();
-    {   // threads 0..126 -> (order p, partition j) of set 0, threads 128..254 -> set 1
-        const uint32_t k = tid >> 7, t = tid & 127;
-        if (k < (uint32_t)NS && t < 127) {
-            const uint32_t p = 31u - (uint32_t)__clz((int)(t + 1));
-            const uint32_t j = t + 1 - (1u << p);
-            uint8_t code = 0xFE;
-            uint32_t est = 0;
-            if (p <= p_max) {
-                const uint32_t cp = n >> p;
-                const uint32_t a = j * cp, b = a + cp;
-                if (b > o[k]) {
-                    const uint32_t span = 1u << (p_max - p);
-                    const unsigned long long* cs = sm.chunk_sum + k * MAX_PARTS;
-                    unsigned long long sum = 0;
-                    for (uint32_t m = j * span; m < (j + 1) * span; m++) sum += cs[m];
-                    code = partition_code(sum, b - max(a, o[k]), rice_max, &est);
-                }
-            }
-            sm.part_code[tid] = code;
-            sm.part_est[tid] = est;
-        }
-    }
-    __syncthreads();
-    {   // warp p sums the estimates of partition order p (both sets)
-        const uint32_t p = tid >> 5, lane = tid & 31;
-        if (p <= p_max) {
-#pragma unroll
-            for (int k = 0; k < NS; k++) {
-                const uint32_t base = k * 128 + (1u << p) - 1, cnt_all = 1u << p;
-                uint32_t est = 0, cnt = 0, bad = 0;
-                for (uint32_t j = lane; j < cnt_all; j += 32) {
-                    const uint8_t c = sm.part_code[base + j];
-                    if (c == 0xFE) continue;
-                    if (c == 0xFF) bad = 1;
-                    cnt++;
-                    est += sm.part_est[base + j];
-                }
-                est = __reduce_add_sync(0xffffffffu, est);
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                bad = __reduce_or_sync(0xffffffffu, bad);
-                if (lane == 0) {
-                    sm.ord_est[k * 8 + p] = est;
-                    sm.ord_cnt[k * 8 + p] = cnt;
-                    sm.ord_ok[k * 8 + p] = (!bad && cnt != 0 && (cnt & (cnt - 1)) == 0) ? 1u : 0u;   // :3880-3881
-                }
-            }
-        }
-    }
-    __syncthreads();
-    uint32_t porder_g[NS], nparts[NS], method[NS];
-#pragma unroll
-    for (int k = 0; k < NS; k++) {
-        RiceChoice& out = *outs[k];
-        bool have = false;
-        uint32_t best_est = 0, best_p = 0, best_count = 0;
-        for (uint32_t p = 0; p <= p_max; p++) {
-            if (!sm.ord_ok[k * 8 + p]) continue;
-            const uint32_t est = sm.ord_est[k * 8 + p];
-            if (!have || est < best_est) { have = true; best_est = est; best_p = p; best_count = sm.ord_cnt[k * 8 + p]; }   // first minimum :3885
-        }
-        if (!have) {   // unwrap_or_else (:3887): one partition escaped at 31 bits
-            porder_g[k] = 0; nparts[k] = 1;
-            method[k] = cfg.use_rice2 ? 1 : 0;
-            if (tid == 0) { out.porder_g = 0; out.porder_w = 0; out.nparts = 1; out.rice[0] = 0x40 | 31; }
-        } else {
-            porder_g[k] = best_p; nparts[k] = best_count;
-            const uint32_t base = k * 128 + (1u << best_p) - 1, j0 = (1u << best_p) - best_count;
-            uint32_t big = 0;
-            if (tid < best_count) {
-                const uint8_t c = sm.part_code[base + j0 + tid];
-                out.rice[tid] = c;
-                big = (c < 0x40 && c >= 15) ? 1u : 0u;
-            }
-            if (__any_sync(0xffffffffu, big) && (tid & 31) == 0) atomicOr(&sm.flag2[k], 1u);
-            if (tid == 0) {
-                out.porder_g = (uint8_t)best_p;
-                out.nparts = (uint8_t)best_count;
-                out.porder_w = (uint8_t)(31u - (uint32_t)__clz((int)best_count));   // partitions.len().ilog2() :3902
-            }
-            method[k] = 2;   // resolved after the barrier
-        }
-    }
-    __syncthreads();
-    // exact size: what Partition::to_writer will emit (:3834-3863), plus the partition headers
-#pragma unroll
-    for (int k = 0; k < NS; k++) {
-        RiceChoice& out = *outs[k];
-        if (method[k] == 2) method[k] = (cfg.use_rice2 && (sm.flag2[k] & 1u)) ? 1 : 0;   // try_reduce_rice :3929-3942
-        const uint32_t cp = n >> porder_g[k];
-        const uint32_t j0 = (1u << porder_g[k]) - nparts[k];
-        const bool cp_pow2 = (cp & (cp - 1)) == 0;
-        const uint32_t cp_shift = 31u - (uint32_t)__clz((int)cp);
-        unsigned long long bits = 0;
-        uint32_t bad = 0;
-        if (lo[k] < hi[k]) {
-            const uint32_t ja = cp_pow2 ? lo[k] >> cp_shift : lo[k] / cp, jb = cp_pow2 ? (hi[k] - 1) >> cp_shift : (hi[k] - 1) / cp;
-            const uint32_t c = out.rice[ja - j0];
-            if (full[k] && ja == jb && c < 0x40) {   // the common case: 16 Rice codes with one parameter
-#pragma unroll
-                for (int e = 0; e < AN_SPT; e++) bits = acc_u32(bits, zigzag32(r[k][e]) >> c);
-                bits += (unsigned long long)(AN_SPT * (1u + c));
-            } else {
-                int32_t tmp[AN_SPT];
-#pragma unroll
-                for (int e = 0; e < AN_SPT; e++) tmp[e] = r[k][e];
-                exact_bits_slow(tmp, i0, lo[k], hi[k], cp, j0, out.rice, &bits, &bad);
-            }
-        }
-        if (tid < nparts[k]) bits += (out.rice[tid] < 0x40) ? (method[k] ? 5u : 4u) : (method[k] ? 10u : 9u);   // partition headers
-        block_add(&sm.acc[k], bits);
-        if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) atomicOr(&sm.flag2[k], 2u);
-    }
-    __syncthreads();
-    if (tid < (uint32_t)NS) {
-        RiceChoice& out = *outs[tid];
-        out.resid_bits = (uint32_t)sm.acc[tid] + 2 + 4;   // + coding method + partition order
-        out.fail = (sm.flag2[tid] & 2u) ? 1u : 0u;
-        out.method = (uint8_t)(tid == 0 ? method[0] : method[NS - 1]);
-    }
-    __syncthreads();
-}
-
-// One candidate channel: encode_subframe (src/encode.rs:2849-2980) without emitting bits.
-// plane: the candidate's samples in shared memory (AN_PAD zeros in front); HB: LPC order rounded up to 4/8/12/16.
-template <int HB>
-__device__ void analyze_candidate(const EncCfg& cfg, AnSmem& sm, const int32_t* __restrict__ plane, uint32_t n, uint32_t full_bps, uint32_t mask,
-                                  const LpcRec& lp, CandRec* __restrict__ rec)
-{
-    const uint32_t tid = threadIdx.x, i0 = tid * AN_SPT;
-    const uint32_t wasted = (mask & 1u) ? 0u : (uint32_t)__ffs((int)mask) - 1u;   // :2878-2898
-    const uint32_t bps = full_bps - wasted;
-    const bool interior = i0 >= 4 && i0 + AN_SPT <= n;   // every sample of the thread counts everywhere
-    // register window: w[HB + e] = x[i0 + e] >> wasted, w[HB - 1 - j] = x[i0 - 1 - j]
-    int32_t w[HB + AN_SPT];
-#pragma unroll
-    for (int k = 0; k < (HB + AN_SPT) / 4; k++) {
-        const int4 t = reinterpret_cast<const int4*>(plane + (int)i0 - HB)[k];
-        w[4 * k] = t.x >> wasted; w[4 * k + 1] = t.y >> wasted; w[4 * k + 2] = t.z >> wasted; w[4 * k + 3] = t.w >> wasted;
-    }
-    // ---- LPC residuals first (encode_lpc_subframe :3090-3136, :3174-3203); lp.ok is uniform across the CTA ----
-    int32_t r[2][AN_SPT];   // [0] fixed, [1] LPC
-    bool lpc_ok = lp.ok != 0;
-    if (tid < 8) sm.acc[tid] = 0;
-    if (tid == 0) sm.flag = 0;
-    if (lpc_ok && tid < MAX_LPC) sm.q[tid] = tid < lp.order ? lp.q[tid] : (int16_t)0;
-    __syncthreads();
-    // ---- encode_fixed_subframe (:3020-3088).  Samples are <= 28 bits wide here, so no difference up to order 4
-    // can leave i32 (checked_sub never fails) and plain 32-bit arithmetic is exact. ----
+    const uint32_t cf = n >> p_max;   // finest partition
+    const bool cf16 = (cf & 15u) == 0;
     const uint32_t kmax = min(4u, n - 1);
+    const bool have_lpc = lp.ok != 0;
+    const uint32_t order = have_lpc ? lp.order : 0, shift = lp.shift;
+    int32_t q[HB];
+#pragma unroll
+    for (int j = 0; j < HB; j++) q[j] = (have_lpc && (uint32_t)j < order) ? (int32_t)lp.q[j] : 0;
+
+    uint32_t wasted = 0, mask = 0, ovf = 0, fo = 0, bps = full_bps;
+    bool lpc_ok = have_lpc;
     unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-    const int32_t h1 = w[HB - 1] - w[HB - 2], h1b = w[HB - 2] - w[HB - 3], h1c = w[HB - 3] - w[HB - 4];
-    const int32_t h2 = h1 - h1b, h2b = h1b - h1c, h3 = h2 - h2b;   // differences of the samples just before i0
-    if (interior) {
-        int32_t p1 = h1, p2 = h2, p3 = h3;
+    unsigned long long bits_f = 0, bits_l = 0;
+    uint32_t bad_f = 0, bad_l = 0;
+    uint32_t cpf = n, j0f = 0, cpl = n, j0l = 0;
+    bool cpf16 = false, cpl16 = false;
+    // stage 0: pass 1 assuming no wasted bits; stage 1: pass 1 again with the wasted bits shifted out (rare);
+    // stage 2: pass 2 (exact sizes).  One loop body serves all stages so that the FIR code exists once.
+    for (int stage = 0; stage < 3; stage++) {
+        if (stage == 1 && wasted == 0) continue;
+        if (stage < 2) {
+            for (uint32_t t = lane; t < AW_SETS * MAX_PARTS; t += 32) {
+                (&sm.limb_lo[0][0])[t] = 0;
+                (&sm.limb_hi[0][0])[t] = 0;
+            }
+            if (lane < 5) sm.u[lane] = 0;
+            mask = 0; ovf = 0;
+            __syncwarp();
+        } else {
+            // ---- between the passes: fixed order, partition trees, Rice parameters ----
+            if (mask == 0) {   // all samples zero -> CONSTANT (:2870, :2883)
+                if (lane == 0) {
+                    rec->type = 0; rec->order = 0; rec->wasted = 0; rec->bps = (uint8_t)full_bps;
+                    rec->bits = 8 + full_bps;
+                }
+                return;
+            }
+            bps = full_bps - wasted;
+            __syncwarp();
+            {   // sums over the common tail = everything set k counted, minus its samples before kmax
+                unsigned long long tk[5];
 #pragma unroll
-        for (int e = 0; e < AN_SPT; e++) {
-            const int32_t e1 = w[HB + e] - w[HB + e - 1], e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
-            p1 = e1; p2 = e2; p3 = e3;
-            s0 = acc_u32(s0, uabs32(w[HB + e])); s1 = acc_u32(s1, uabs32(e1)); s2 = acc_u32(s2, uabs32(e2));
-            s3 = acc_u32(s3, uabs32(e3)); s4 = acc_u32(s4, uabs32(e4));
-        }
-    } else {
-        int32_t p1 = h1, p2 = h2, p3 = h3;
-#pragma unroll
-        for (int e = 0; e < AN_SPT; e++) {
-            const int32_t e1 = w[HB + e] - w[HB + e - 1], e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
-            p1 = e1; p2 = e2; p3 = e3;
-            const uint32_t i = i0 + e;
-            if (i >= kmax && i < n) {
-                s0 += uabs32(w[HB + e]); s1 += uabs32(e1); s2 += uabs32(e2); s3 += uabs32(e3); s4 += uabs32(e4);
+                for (int k = 0; k < 5; k++) {
+                    unsigned long long v = 0;
+                    for (uint32_t j = lane; j < MAX_PARTS; j += 32) v += (unsigned long long)sm.limb_lo[k][j] + ((unsigned long long)sm.limb_hi[k][j] << 24);
+                    tk[k] = warp_sum_u64(v) - sm.u[k];
+                }
+                s0 = tk[0]; s1 = tk[1]; s2 = tk[2]; s3 = tk[3]; s4 = tk[4];
+            }
+            {   // first minimum among the orders that exist (:3065-3075)
+                unsigned long long best = s0;
+                if (kmax >= 1 && s1 < best) { best = s1; fo = 1; }
+                if (kmax >= 2 && s2 < best) { best = s2; fo = 2; }
+                if (kmax >= 3 && s3 < best) { best = s3; fo = 3; }
+                if (kmax >= 4 && s4 < best) { best = s4; fo = 4; }
+            }
+            lpc_ok = have_lpc && !__any_sync(0xffffffffu, ovf >> 31);   // ResidualOverflow
+            __syncwarp();
+            const uint32_t nleaf = 1u << p_max;
+            for (uint32_t k = 0; k < 2; k++) {
+                const uint32_t set = k == 0 ? fo : 5;
+                for (uint32_t j = lane; j < nleaf; j += 32)
+                    sm.tree[k][nleaf - 1 + j] = (unsigned long long)sm.limb_lo[set][j] + ((unsigned long long)sm.limb_hi[set][j] << 24);
+            }
+            __syncwarp();
+            for (int p = (int)p_max - 1; p >= 0; p--) {
+                const uint32_t base = (1u << p) - 1, child = (2u << p) - 1;
+                for (uint32_t j = lane; j < (1u << p); j += 32) {
+                    sm.tree[0][base + j] = sm.tree[0][child + 2 * j] + sm.tree[0][child + 2 * j + 1];
+                    sm.tree[1][base + j] = sm.tree[1][child + 2 * j] + sm.tree[1][child + 2 * j + 1];
+                }
+                __syncwarp();
+            }
+            aw_choose_partitions(cfg, n, fo, p_max, sm.tree[0], sm.part_est[0], sm.part_code[0], sm.choice[0]);
+            if (lpc_ok) aw_choose_partitions(cfg, n, order, p_max, sm.tree[1], sm.part_est[1], sm.part_code[1], sm.choice[1]);
+            cpf = n >> sm.choice[0].porder_g;
+            j0f = (1u << sm.choice[0].porder_g) - sm.choice[0].nparts;
+            cpf16 = (cpf & 15u) == 0;
+            if (lpc_ok) {
+                cpl = n >> sm.choice[1].porder_g;
+                j0l = (1u << sm.choice[1].porder_g) - sm.choice[1].nparts;
+                cpl16 = (cpl & 15u) == 0;
             }
         }
-    }
-    block_add(&sm.acc[2], s0); block_add(&sm.acc[3], s1); block_add(&sm.acc[4], s2); block_add(&sm.acc[5], s3); block_add(&sm.acc[6], s4);
-    if (lpc_ok) {
-        const uint32_t order = lp.order, shift = lp.shift;
-        int32_t q[HB];
+        int32_t carry[16];   // lane 31's tile of the previous round: the history of lane 0
 #pragma unroll
-        for (int j = 0; j < HB; j++) q[j] = sm.q[j];
-        uint32_t ovf = 0;
+        for (int e = 0; e < 16; e++) carry[e] = 0;
+        for (uint32_t rd = 0; rd < rounds; rd++) {
+            const uint32_t i0 = (rd * 32 + lane) * 16;
+            const bool live = i0 < n;
+            int32_t x[16], h[16];   // h: the 16 samples before the tile (after the wasted-bit shift) = the left neighbour's tile
 #pragma unroll
-        for (int e = 0; e < AN_SPT; e++) {
-            long long sum = 0;
+            for (int e = 0; e < 16; e++) x[e] = 0;
+            if (live) aw_load_tile<STEREO>(cfg, d, pcm, slot, i0, x);
 #pragma unroll
-            for (int j = 0; j < HB; j++) sum = mad_wide_s32(w[HB + e - 1 - j], q[j], sum);   // :3187-3192
-            const int32_t pred = (int32_t)(uint32_t)(unsigned long long)(sum >> shift);     // `as i32`
-            const int32_t x = w[HB + e];
-            const int32_t rr = (int32_t)((uint32_t)x - (uint32_t)pred);
-            const uint32_t o1 = (uint32_t)((x ^ pred) & (x ^ rr));                          // sign bit: checked_sub overflowed
-            if (interior && i0 >= order) ovf |= o1;
-            else if (i0 + e >= order && i0 + e < n) ovf |= o1;
-            r[1][e] = rr;
+            for (int e = 0; e < 16; e++) { mask |= (uint32_t)x[e]; x[e] >>= wasted; }   // :2878-2898 (mask only meaningful in stage 0)
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int32_t up = __shfl_up_sync(0xffffffffu, x[e], 1);
+                h[e] = lane == 0 ? carry[e] : up;
+                carry[e] = __shfl_sync(0xffffffffu, x[e], 31);
+            }
+            if (!live) continue;
+            const bool tail = i0 + 16 > n;   // tile cut by the block end: rare, sample-by-sample path
+            // ---- LPC residuals (:3174-3203) ----
+            int32_t rl[16];
+            if (lpc_ok) {
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    long long sum = 0;
+#pragma unroll
+                    for (int j = 0; j < HB; j++) sum = mad_wide_s32(e - 1 - j >= 0 ? x[e - 1 - j >= 0 ? e - 1 - j : 0] : h[16 + e - 1 - j >= 0 ? 16 + e - 1 - j : 0], q[j], sum);
+                    const int32_t pred = (int32_t)(uint32_t)(unsigned long long)(sum >> shift);   // `as i32`
+                    const int32_t rr = (int32_t)((uint32_t)x[e] - (uint32_t)pred);
+                    rl[e] = rr;
+                    if (stage < 2) {   // checked_sub: sign bit set when it overflowed; only samples in [order, n) count
+                        const uint32_t o1 = (uint32_t)((x[e] ^ pred) & (x[e] ^ rr));
+                        if (!tail && (i0 != 0 || (uint32_t)e >= order)) ovf |= o1;
+                        else if (i0 + e >= order && i0 + e < n) ovf |= o1;
+                    }
+                }
+            }
+            // ---- fixed differences (:3039-3060); <= 28-bit samples cannot overflow i32 up to order 4 ----
+            int32_t p1 = h[15] - h[14], p2 = p1 - (h[14] - h[13]), p3 = p2 - ((h[14] - h[13]) - (h[13] - h[12]));
+            if (stage < 2) {
+                const uint32_t chunk = i0 / cf;
+                if (!tail && (cf16 || (i0 + 15) / cf == chunk)) {
+                    unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, al = 0;
+                    int32_t prev = h[15];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const int32_t e1 = x[e] - prev, e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
+                        prev = x[e]; p1 = e1; p2 = e2; p3 = e3;
+                        a0 = acc_u32(a0, uabs32(x[e])); a1 = acc_u32(a1, uabs32(e1)); a2 = acc_u32(a2, uabs32(e2));
+                        a3 = acc_u32(a3, uabs32(e3)); a4 = acc_u32(a4, uabs32(e4));
+                        if (lpc_ok) al = acc_u32(al, uabs32(rl[e]));
+                    }
+                    if (i0 == 0) {
+                        // the block's first tile (n >= 16 here, so kmax == 4): with zero history the differences of the first
+                        // samples are these closed forms.  Set k does not count samples before k; the order comparison
+                        // (:3062-3073) does not count samples before kmax either -- remembered in sm.u[] for later.
+                        const int32_t y0 = x[0], y1 = x[1], y2 = x[2], y3 = x[3];
+                        const uint32_t f11 = uabs32(y1 - y0), f12 = uabs32(y2 - y1), f13 = uabs32(y3 - y2);
+                        const uint32_t f21 = uabs32(y1 - 2 * y0), f22 = uabs32(y2 - 2 * y1 + y0), f23 = uabs32(y3 - 2 * y2 + y1);
+                        const uint32_t f31 = uabs32(y1 - 3 * y0), f32 = uabs32(y2 - 3 * y1 + 3 * y0), f33 = uabs32(y3 - 3 * y2 + 3 * y1 - y0);
+                        const uint32_t f41 = uabs32(y1 - 4 * y0), f42 = uabs32(y2 - 4 * y1 + 6 * y0), f43 = uabs32(y3 - 4 * y2 + 6 * y1 - 4 * y0);
+                        const unsigned long long f0 = uabs32(y0);
+                        a1 -= f0;
+                        a2 -= f0 + f21;
+                        a3 -= f0 + f31 + f32;
+                        a4 -= f0 + f41 + f42 + f43;
+                        sm.u[0] = f0 + uabs32(y1) + uabs32(y2) + uabs32(y3);
+                        sm.u[1] = (unsigned long long)f11 + f12 + f13;
+                        sm.u[2] = (unsigned long long)f22 + f23;
+                        sm.u[3] = f33;
+                        sm.u[4] = 0;
+                        if (lpc_ok) {
+#pragma unroll
+                            for (int e = 0; e < 16; e++)
+                                if ((uint32_t)e < order) al -= uabs32(rl[e]);
+                        }
+                    }
+                    aw_add_limbs(sm.limb_lo[0], sm.limb_hi[0], chunk, a0);
+                    aw_add_limbs(sm.limb_lo[1], sm.limb_hi[1], chunk, a1);
+                    aw_add_limbs(sm.limb_lo[2], sm.limb_hi[2], chunk, a2);
+                    aw_add_limbs(sm.limb_lo[3], sm.limb_hi[3], chunk, a3);
+                    aw_add_limbs(sm.limb_lo[4], sm.limb_hi[4], chunk, a4);
+                    if (lpc_ok) aw_add_limbs(sm.limb_lo[5], sm.limb_hi[5], chunk, al);
+                } else {
+                    // copies: taking the address of the register tiles themselves would push them into local memory for good
+                    int32_t tx[16], th[16], tl[16];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) { tx[e] = x[e]; th[e] = h[e]; tl[e] = lpc_ok ? rl[e] : 0; }
+                    AwSmemLimbs limbs = {&sm.limb_lo[0][0], &sm.limb_hi[0][0]};
+                    aw_pass1_tile_slow(tx, th, tl, lpc_ok, order, i0, n, kmax, cf, limbs, sm.u);
+                }
+            } else {
+                // ---- pass 2: exact size of both residual blocks (what Partition::to_writer will emit, :3834-3863) ----
+                int32_t rf[16];
+                {
+                    int32_t prev = h[15];
+                    switch (fo) {   // uniform across the warp
+                    case 0:
+#pragma unroll
+                        for (int e = 0; e < 16; e++) rf[e] = x[e];
+                        break;
+                    case 1:
+#pragma unroll
+                        for (int e = 0; e < 16; e++) { rf[e] = x[e] - prev; prev = x[e]; }
+                        break;
+                    default:
+#pragma unroll
+                        for (int e = 0; e < 16; e++) {
+                            const int32_t e1 = x[e] - prev, e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
+                            prev = x[e]; p1 = e1; p2 = e2; p3 = e3;
+                            rf[e] = fo == 2 ? e2 : fo == 3 ? e3 : e4;
+                        }
+                        break;
+                    }
+                }
+                const RiceChoice& chf = sm.choice[0];
+                const uint32_t pf = i0 / cpf;
+                const uint32_t codef = chf.rice[pf - j0f >= chf.nparts ? 0 : pf - j0f];
+                if (!tail && i0 != 0 && (cpf16 || (i0 + 15) / cpf == pf) && codef < 0x40) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) bits_f = acc_u32(bits_f, zigzag32(rf[e]) >> codef);
+                    bits_f += 16u * (1u + codef);
+                } else {
+                    int32_t tmp[16];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) tmp[e] = rf[e];
+                    unsigned long long tb = 0;
+                    uint32_t tbad = 0;
+                    aw_tile_bits_slow(tmp, i0, fo, n, cpf, j0f, chf.rice, &tb, &tbad);
+                    bits_f += tb;
+                    bad_f |= tbad;
+                }
+                if (lpc_ok) {
+                    const RiceChoice& chl = sm.choice[1];
+                    const uint32_t pl = i0 / cpl;
+                    const uint32_t codel = chl.rice[pl - j0l >= chl.nparts ? 0 : pl - j0l];
+                    if (!tail && i0 != 0 && (cpl16 || (i0 + 15) / cpl == pl) && codel < 0x40) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) bits_l = acc_u32(bits_l, zigzag32(rl[e]) >> codel);
+                        bits_l += 16u * (1u + codel);
+                    } else {
+                        int32_t tmp[16];
+#pragma unroll
+                        for (int e = 0; e < 16; e++) tmp[e] = rl[e];
+                        unsigned long long tb = 0;
+                        uint32_t tbad = 0;
+                        aw_tile_bits_slow(tmp, i0, order, n, cpl, j0l, chl.rice, &tb, &tbad);
+                        bits_l += tb;
+                        bad_l |= tbad;
+                    }
+                }
+            }
         }
-        if (__any_sync(0xffffffffu, ovf >> 31) && (tid & 31) == 0) atomicOr(&sm.flag, 4u);   // ResidualOverflow
-    }
-    __syncthreads();
-    s0 = sm.acc[2]; s1 = sm.acc[3]; s2 = sm.acc[4]; s3 = sm.acc[5]; s4 = sm.acc[6];
-    if (sm.flag & 4u) lpc_ok = false;
-    uint32_t fo = 0;   // first minimum among the orders that exist (:3065-3075)
-    {
-        unsigned long long best = s0;
-        if (kmax >= 1 && s1 < best) { best = s1; fo = 1; }
-        if (kmax >= 2 && s2 < best) { best = s2; fo = 2; }
-        if (kmax >= 3 && s3 < best) { best = s3; fo = 3; }
-        if (kmax >= 4 && s4 < best) { best = s4; fo = 4; }
-    }
-    // residuals of the chosen fixed order (fo is uniform across the CTA)
-    if (fo == 0) {
-#pragma unroll
-        for (int e = 0; e < AN_SPT; e++) r[0][e] = w[HB + e];
-    } else if (fo == 1) {
-#pragma unroll
-        for (int e = 0; e < AN_SPT; e++) r[0][e] = w[HB + e] - w[HB + e - 1];
-    } else {
-        int32_t p1 = h1, p2 = h2, p3 = h3;
-#pragma unroll
-        for (int e = 0; e < AN_SPT; e++) {
-            const int32_t e1 = w[HB + e] - w[HB + e - 1], e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
-            p1 = e1; p2 = e2; p3 = e3;
-            r[0][e] = fo == 2 ? e2 : fo == 3 ? e3 : e4;
+        if (stage < 2) {
+            mask = __reduce_or_sync(0xffffffffu, mask);
+            if (stage == 0) wasted = (mask == 0 || (mask & 1u)) ? 0u : (uint32_t)__ffs((int)mask) - 1u;
         }
     }
-    const uint32_t orders[2] = {fo, lp.order};
-    RiceChoice* outs[2] = {&sm.fixed, &sm.lpc};
-    if (lpc_ok) rice_search_regs<2>(r, i0, orders, n, cfg, sm, outs);
-    else rice_search_regs<1>(r, i0, orders, n, cfg, sm, outs);
+    const RiceChoice& cf_ = sm.choice[0];
+    const RiceChoice& cl_ = sm.choice[1];
+    // partition headers: 4/5-bit parameter (+ 5-bit escape width)
+    for (uint32_t j = lane; j < cf_.nparts; j += 32) bits_f += (cf_.rice[j] < 0x40) ? (cf_.method ? 5u : 4u) : (cf_.method ? 10u : 9u);
+    if (lpc_ok)
+        for (uint32_t j = lane; j < cl_.nparts; j += 32) bits_l += (cl_.rice[j] < 0x40) ? (cl_.method ? 5u : 4u) : (cl_.method ? 10u : 9u);
+    bits_f = warp_sum_u64(bits_f);
+    bits_l = warp_sum_u64(bits_l);
+    const bool fixed_ok = !__any_sync(0xffffffffu, bad_f);
+    if (__any_sync(0xffffffffu, bad_l)) lpc_ok = false;
     const uint32_t hdr_bits = 8 + wasted;   // pad + type + wasted flag (+ unary(wasted - 1)) (src/stream.rs:1397)
-    const bool fixed_ok = sm.fixed.fail == 0;
-    const uint32_t fixed_bits = hdr_bits + fo * bps + sm.fixed.resid_bits;
-    uint32_t lpc_bits = 0;
-    if (lpc_ok) {
-        if (sm.lpc.fail) lpc_ok = false;
-        lpc_bits = hdr_bits + lp.order * bps + 4 + 5 + lp.order * lp.precision + sm.lpc.resid_bits;
-    }
+    const uint32_t fixed_bits = hdr_bits + fo * bps + (uint32_t)bits_f + 6;
+    const uint32_t lpc_bits = hdr_bits + order * bps + 4 + 5 + order * lp.precision + (uint32_t)bits_l + 6;
     // ---- choose (:2929-2979): fixed wins ties; VERBATIM unless strictly smaller ----
     const uint32_t verbatim_len = n * bps;
     int pick = -1;   // 0 fixed, 1 lpc
@@ -426,8 +562,8 @@ __device__ void analyze_candidate(const EncCfg& cfg, AnSmem& sm, const int32_t* 
     else if (lpc_ok) pick = 1;
     const uint32_t best_bits = pick == 1 ? lpc_bits : fixed_bits;
     if (pick >= 0 && !(best_bits < verbatim_len)) pick = -1;
-    const RiceChoice& ch = pick == 1 ? sm.lpc : sm.fixed;
-    if (tid == 0) {
+    const RiceChoice& ch = pick == 1 ? sm.choice[1] : sm.choice[0];
+    if (lane == 0) {
         rec->wasted = (uint8_t)wasted;
         rec->bps = (uint8_t)bps;
         if (pick < 0) {
@@ -442,99 +578,56 @@ __device__ void analyze_candidate(const EncCfg& cfg, AnSmem& sm, const int32_t* 
         }
     }
     if (pick >= 0) {
-        if (tid < MAX_PARTS) rec->rice[tid] = ch.rice[tid];
-        if (tid < MAX_LPC) rec->q[tid] = lp.q[tid];
+        for (uint32_t j = lane; j < MAX_PARTS; j += 32) rec->rice[j] = ch.rice[j];
+        if (lane < MAX_LPC) rec->q[lane] = lp.q[lane];
     }
-    __syncthreads();
+    __syncwarp();
 }
 
-// grid: frames (STEREO: L/R/M/S candidates of a two-channel frame) or frames * channels (one channel per CTA)
-// dynamic smem: nplanes * AN_STRIDE int32
+// one warp per candidate: grid = ceil(ncand / AW_WARPS)
 template <bool STEREO>
-__global__ void __launch_bounds__(AN_THREADS, 2) k_analyze(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
+__global__ void __launch_bounds__(32 * AW_WARPS, 4) k_analyze(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
                                                           const LpcRec* __restrict__ lpcs, CandRec* __restrict__ out,
-                                                          unsigned long long* __restrict__ abssum)
+                                                          unsigned long long* __restrict__ abssum, uint32_t ncand)
 {
-    extern __shared__ __align__(16) int32_t an_planes[];
-    __shared__ AnSmem sm;
-    const uint32_t tid = threadIdx.x, i0 = tid * AN_SPT;
-    const uint32_t f = STEREO ? blockIdx.x : blockIdx.x / cfg.channels;
-    const uint32_t ch = STEREO ? 0 : blockIdx.x % cfg.channels;
+    __shared__ AwSmem sm_all[AW_WARPS];
+    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cand = blockIdx.x * AW_WARPS + wid;
+    if (cand >= ncand) return;
+    AwSmem& sm = sm_all[wid];
+    const uint32_t f = cand / cfg.nslots, slot = cand % cfg.nslots;
     const FrameDesc d = descs[f];
-    const uint32_t n = d.n;
-    constexpr int NPL = STEREO ? 4 : 1;
-    if (tid < AN_PAD) {
-#pragma unroll
-        for (int p = 0; p < NPL; p++) an_planes[p * AN_STRIDE + tid] = 0;
-    }
-    if (tid < 4) { sm.orm[tid] = 0; sm.absum[tid] = 0; }
-    __syncthreads();
-    int32_t a[AN_SPT], b[AN_SPT];
-    if (STEREO) load_thread_samples<2>(cfg, d, pcm, i0, 0, a, b);
-    else if (cfg.channels == 1) load_thread_samples<1>(cfg, d, pcm, i0, 0, a, b);
-    else {
-#pragma unroll
-        for (int e = 0; e < AN_SPT; e++) a[e] = i0 + e < n ? load_pcm_sample(pcm, cfg, d.pcm_off + i0 + e, ch) : 0;
-    }
-    if (i0 + AN_SPT > n) {
-#pragma unroll
-        for (int e = 0; e < AN_SPT; e++)
-            if (i0 + e >= n) { a[e] = 0; if (STEREO) b[e] = 0; }
-    }
-    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-    store16(an_planes + AN_PAD + i0, a);
-#pragma unroll
-    for (int e = 0; e < AN_SPT; e++) o0 |= (uint32_t)a[e];
+    CandRec* rec = out + cand;
     if (STEREO) {
-        store16(an_planes + AN_STRIDE + AN_PAD + i0, b);
-        int32_t m[AN_SPT], s[AN_SPT];
-        unsigned long long sl = 0, sr = 0, smid = 0, sside = 0;
-#pragma unroll
-        for (int e = 0; e < AN_SPT; e++) {
-            m[e] = (a[e] + b[e]) >> 1;   // :2721
-            s[e] = a[e] - b[e];          // :2734
-            o1 |= (uint32_t)b[e]; o2 |= (uint32_t)m[e]; o3 |= (uint32_t)s[e];
-            sl += uabs32(a[e]); sr += uabs32(b[e]); smid += uabs32(m[e]); sside += uabs32(s[e]);
-        }
-        store16(an_planes + 2 * AN_STRIDE + AN_PAD + i0, m);
-        store16(an_planes + 3 * AN_STRIDE + AN_PAD + i0, s);
         if (cfg.mode == MODE_FAST_MID_SIDE || cfg.mode == MODE_FAST_SIDE) {   // correlate_channels abs sums (:2475-2503)
-            block_add(&sm.absum[0], sl); block_add(&sm.absum[1], sr); block_add(&sm.absum[2], smid); block_add(&sm.absum[3], sside);
-        }
-    }
-    o0 = __reduce_or_sync(0xffffffffu, o0);
-    if (STEREO) { o1 = __reduce_or_sync(0xffffffffu, o1); o2 = __reduce_or_sync(0xffffffffu, o2); o3 = __reduce_or_sync(0xffffffffu, o3); }
-    if ((tid & 31) == 0) {
-        if (o0) atomicOr(&sm.orm[0], o0);
-        if (STEREO) { if (o1) atomicOr(&sm.orm[1], o1); if (o2) atomicOr(&sm.orm[2], o2); if (o3) atomicOr(&sm.orm[3], o3); }
-    }
-    __syncthreads();
-    if (STEREO && tid < 4 && abssum) abssum[(size_t)f * 4 + tid] = sm.absum[tid];
-    for (uint32_t slot = 0; slot < (uint32_t)NPL; slot++) {
-        const uint32_t cand = STEREO ? f * 4 + slot : blockIdx.x;
-        CandRec* rec = out + cand;
-        if (STEREO && !slot_active(cfg, sm.absum, slot)) {
-            if (tid == 0) { rec->type = 0xFF; rec->bits = 0; }
-            continue;
-        }
-        const uint32_t full_bps = STEREO ? cand_bps(cfg, slot) : cfg.bps;
-        const uint32_t mask = sm.orm[slot];
-        if (mask == 0) {   // all samples zero -> CONSTANT (:2870, :2883)
-            if (tid == 0) {
-                rec->type = 0; rec->order = 0; rec->wasted = 0; rec->bps = (uint8_t)full_bps;
-                rec->bits = 8 + full_bps;
+            unsigned long long sl = 0, sr = 0, smid = 0, sside = 0;
+            for (uint32_t i0 = lane * 16; i0 < d.n; i0 += 32 * 16) {
+                int32_t a[16], b[16];
+                load_thread_samples<2>(cfg, d, pcm, i0, 0, a, b);
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    sl += uabs32(a[e]); sr += uabs32(b[e]); smid += uabs32((a[e] + b[e]) >> 1); sside += uabs32(a[e] - b[e]);
+                }
             }
-            continue;
+            unsigned long long sums[4] = {warp_sum_u64(sl), warp_sum_u64(sr), warp_sum_u64(smid), warp_sum_u64(sside)};
+            if (slot == 0 && lane < 4) abssum[(size_t)f * 4 + lane] = sums[lane];
+            if (!slot_active(cfg, sums, slot)) {
+                if (lane == 0) { rec->type = 0xFF; rec->bits = 0; }
+                return;
+            }
+        } else if (cfg.mode == MODE_EXH_SIDE && slot == 2) {
+            if (lane == 0) { rec->type = 0xFF; rec->bits = 0; }
+            return;
         }
-        const LpcRec lp = lpcs[cand];
-        const int32_t* plane = an_planes + slot * AN_STRIDE + AN_PAD;
-        const uint32_t hb = lp.ok ? (lp.order + 3u) >> 2 : 1u;
-        switch (hb) {
-        case 1: analyze_candidate<4>(cfg, sm, plane, n, full_bps, mask, lp, rec); break;
-        case 2: analyze_candidate<8>(cfg, sm, plane, n, full_bps, mask, lp, rec); break;
-        case 3: analyze_candidate<12>(cfg, sm, plane, n, full_bps, mask, lp, rec); break;
-        default: analyze_candidate<16>(cfg, sm, plane, n, full_bps, mask, lp, rec); break;
-        }
+    }
+    const uint32_t full_bps = STEREO ? cand_bps(cfg, slot) : cfg.bps;
+    const LpcRec lp = lpcs[cand];
+    const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;   // uniform for the whole launch
+    switch (hb) {
+    case 1: aw_candidate<4, STEREO>(cfg, d, pcm, slot, full_bps, lp, sm, rec); break;
+    case 2: aw_candidate<8, STEREO>(cfg, d, pcm, slot, full_bps, lp, sm, rec); break;
+    case 3: aw_candidate<12, STEREO>(cfg, d, pcm, slot, full_bps, lp, sm, rec); break;
+    default: aw_candidate<16, STEREO>(cfg, d, pcm, slot, full_bps, lp, sm, rec); break;
     }
 }
 
@@ -547,16 +640,10 @@ bool analyze_fast_ok(const EncCfg& cfg)
 cudaError_t launch_analyze(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const LpcRec* lpcs, CandRec* cands,
                            unsigned long long* abssum, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_analyze<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * AN_STRIDE * 4);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    if (cfg.mode != MODE_INDEPENDENT)
-        k_analyze<true><<<cfg.nframes, AN_THREADS, 4 * AN_STRIDE * 4, st>>>(cfg, descs, pcm, lpcs, cands, abssum);
-    else
-        k_analyze<false><<<cfg.nframes * cfg.channels, AN_THREADS, AN_STRIDE * 4, st>>>(cfg, descs, pcm, lpcs, cands, abssum);
+    const uint32_t ncand = cfg.nframes * cfg.nslots;
+    const uint32_t grid = (ncand + AW_WARPS - 1) / AW_WARPS;
+    if (cfg.mode != MODE_INDEPENDENT) k_analyze<true><<<grid, 32 * AW_WARPS, 0, st>>>(cfg, descs, pcm, lpcs, cands, abssum, ncand);
+    else k_analyze<false><<<grid, 32 * AW_WARPS, 0, st>>>(cfg, descs, pcm, lpcs, cands, abssum, ncand);
     return cudaGetLastError();
 }
 
