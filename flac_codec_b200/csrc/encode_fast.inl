@@ -210,17 +210,22 @@ __device__ void aw_choose_partitions(const EncCfg& cfg, uint32_t n, uint32_t o, 
         part_est[t] = est;
     }
     __syncwarp();
-    // lane p < 7 totals order p
+    // lane p ends up with the totals of order p; every order is summed by the whole warp
     uint32_t est = 0, cnt = 0, bad = 0;
-    if (lane <= p_max) {
-        const uint32_t base = (1u << lane) - 1;
-        for (uint32_t j = 0; j < (1u << lane); j++) {
+    for (uint32_t p = 0; p <= p_max; p++) {
+        const uint32_t base = (1u << p) - 1;
+        uint32_t e1 = 0, c1 = 0, b1 = 0;
+        for (uint32_t j = lane; j < (1u << p); j += 32) {
             const uint8_t c = part_code[base + j];
             if (c == 0xFE) continue;
-            if (c == 0xFF) bad = 1;
-            cnt++;
-            est += part_est[base + j];
+            if (c == 0xFF) b1 = 1;
+            c1++;
+            e1 += part_est[base + j];
         }
+        e1 = __reduce_add_sync(0xffffffffu, e1);
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        b1 = __reduce_or_sync(0xffffffffu, b1);
+        if (lane == p) { est = e1; cnt = c1; bad = b1; }
     }
     const bool ok = lane <= p_max && !bad && cnt != 0 && (cnt & (cnt - 1)) == 0;   // :3880-3881
     const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
@@ -405,6 +410,7 @@ __device__ void aw_candidate(const EncCfg& cfg, const FrameDesc& d, const uint8_
             // ---- LPC residuals (:3174-3203) ----
             int32_t rl[16];
             if (lpc_ok) {
+                uint32_t om = 0;
 #pragma unroll
                 for (int e = 0; e < 16; e++) {
                     long long sum = 0;
@@ -413,11 +419,12 @@ __device__ void aw_candidate(const EncCfg& cfg, const FrameDesc& d, const uint8_
                     const int32_t pred = (int32_t)(uint32_t)(unsigned long long)(sum >> shift);   // `as i32`
                     const int32_t rr = (int32_t)((uint32_t)x[e] - (uint32_t)pred);
                     rl[e] = rr;
-                    if (stage < 2) {   // checked_sub: sign bit set when it overflowed; only samples in [order, n) count
-                        const uint32_t o1 = (uint32_t)((x[e] ^ pred) & (x[e] ^ rr));
-                        if (!tail && (i0 != 0 || (uint32_t)e >= order)) ovf |= o1;
-                        else if (i0 + e >= order && i0 + e < n) ovf |= o1;
-                    }
+                    om |= (((uint32_t)((x[e] ^ pred) & (x[e] ^ rr))) >> 31) << e;   // checked_sub: sign bit set when it overflowed
+                }
+                if (stage < 2 && om) {   // only samples in [order, n) count
+                    const uint32_t first = order > i0 ? min(order - i0, 16u) : 0u, last = min(16u, n - i0);
+                    const uint32_t valid = (last >= 16 ? 0xFFFFu : (1u << last) - 1u) & ~((1u << first) - 1u);
+                    if (om & valid) ovf = 0x80000000u;
                 }
             }
             // ---- fixed differences (:3039-3060); <= 28-bit samples cannot overflow i32 up to order 4 ----
@@ -714,6 +721,7 @@ __global__ void __launch_bounds__(32 * L2_WARPS) k_lpc2(EncCfg cfg, const FrameD
     const bool live = g < ncs;
     if (!live) { g = 0; m = 0; }
     const bool stereo4 = cfg.mode != MODE_INDEPENDENT && (cpw & 3u) == 0;   // whole L/R/M/S frames per warp
+    const bool rawmode = stereo4 && cfg.pcm_kind <= 1 && (reinterpret_cast<uintptr_t>(pcm) & 1) == 0;   // packed bytes, 16-bit loads
     if (lane < ncs) out[c0 + lane].ok = 0;
     // per-candidate block lengths; the warp iterates over the longest
     uint32_t nmax = 0;
@@ -728,9 +736,29 @@ __global__ void __launch_bounds__(32 * L2_WARPS) k_lpc2(EncCfg cfg, const FrameD
         if (pass == 1 && shift_mask == 0) break;
         int32_t px[L2_MAXC];   // samples of the tile being prefetched, one per candidate
         double pw[L2_MAXC];    // and their window values
+        uint32_t raw[L2_MAXC / 4][4];   // rawmode: the frame's 2 * B PCM bytes as 16-bit halves, decoded only in store_tile
         auto fetch_tile = [&](uint32_t tile) {   // global loads only: nothing here waits for them
             const uint32_t idx = tile * 32 + lane;
-            if (stereo4) {
+            if (rawmode) {
+#pragma unroll
+                for (int fi = 0; fi < L2_MAXC / 4; fi++) {
+                    const uint32_t c = fi * 4;
+                    double wv = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) raw[fi][k] = 0;
+                    if (c < ncs) {
+                        const FrameDesc d = descs[(c0 + c) >> 2];
+                        if (idx < d.n && d.n > M) {
+                            const uint16_t* p16 = reinterpret_cast<const uint16_t*>(pcm + (d.pcm_off + idx) * (unsigned long long)(2 * cfg.bytes_per_sample));
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if ((uint32_t)k < cfg.bytes_per_sample) raw[fi][k] = p16[k];
+                            wv = winpool[d.win_off + idx];
+                        }
+                    }
+                    pw[c] = pw[c + 1] = pw[c + 2] = pw[c + 3] = wv;
+                }
+            } else if (stereo4) {
 #pragma unroll
                 for (int fi = 0; fi < L2_MAXC / 4; fi++) {
                     const uint32_t c = fi * 4;
@@ -772,6 +800,26 @@ __global__ void __launch_bounds__(32 * L2_WARPS) k_lpc2(EncCfg cfg, const FrameD
         };
         auto store_tile = [&](uint32_t tile) {
             const uint32_t pos = (tile & 3) * 32 + lane;
+            if (rawmode) {   // first use of the prefetched bytes (Frame::fill_from_buf, src/audio.rs:149-187)
+                const uint32_t B = cfg.bytes_per_sample, sh = 32 - 8 * B;
+#pragma unroll
+                for (int fi = 0; fi < L2_MAXC / 4; fi++) {
+                    const unsigned long long wide = (unsigned long long)(raw[fi][0] | (raw[fi][1] << 16)) |
+                                                    ((unsigned long long)(raw[fi][2] | (raw[fi][3] << 16)) << 32);
+                    uint32_t lw = (uint32_t)wide, rw = (uint32_t)(wide >> (8 * B));   // low B bytes: the sample in memory order
+                    int32_t l, r;
+                    if (cfg.pcm_kind == 1) {
+                        l = (int32_t)__byte_perm(lw, 0, 0x0123) >> sh;
+                        r = (int32_t)__byte_perm(rw, 0, 0x0123) >> sh;
+                    } else {
+                        l = (int32_t)(lw << sh) >> sh;
+                        r = (int32_t)(rw << sh) >> sh;
+                    }
+                    px[fi * 4] = l; px[fi * 4 + 1] = r; px[fi * 4 + 2] = (l + r) >> 1; px[fi * 4 + 3] = l - r;
+                }
+#pragma unroll
+                for (int c = (L2_MAXC / 4) * 4; c < L2_MAXC; c++) { px[c] = 0; pw[c] = 0.0; }
+            }
 #pragma unroll
             for (int c = 0; c < L2_MAXC; c++) {
                 if ((uint32_t)c >= ncs || (pass == 1 && !((shift_mask >> c) & 1u))) continue;
@@ -1117,7 +1165,7 @@ __global__ void __launch_bounds__(AN_THREADS) k_pack2(EncCfg cfg, uint32_t nsub_
                     r[e] = (int32_t)((uint32_t)w[AN_SPT + e] - (uint32_t)(unsigned long long)(sum >> shift));
                 }
             };
-            switch ((order + 3) >> 2) {
+            switch ((cfg.max_lpc_order + 3) >> 2) {   // uniform for the launch: one FIR body in the instruction cache
             case 1: fir(std::integral_constant<int, 4>{}); break;
             case 2: fir(std::integral_constant<int, 8>{}); break;
             case 3: fir(std::integral_constant<int, 12>{}); break;

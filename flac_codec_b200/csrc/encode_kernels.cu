@@ -311,6 +311,9 @@ __device__ inline uint8_t partition_code(unsigned long long sum, uint32_t len, u
     if (sum > samples) {
         // ceil(log2(sum / samples)) == min{k : samples << k >= sum}; equality with the reference's f64 form
         // is checked in tests/test_oracle_kat.py::test_rice_parameter_integer_equivalence
+        // start from the bit-length difference (at most one below the answer), then step
+        const uint32_t lg_sum = 63u - (uint32_t)__clzll((long long)sum), lg_n = 31u - (uint32_t)__clz((int)samples);
+        rice = lg_sum > lg_n ? lg_sum - lg_n : 0u;
         while (((unsigned long long)samples << rice) < sum) rice++;
         if (rice >= rice_max) {
             const uint32_t escape = (63u - (uint32_t)__clzll((long long)sum)) + 2u;   // ilog2(sum) + 2 (:3787)
