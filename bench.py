@@ -349,6 +349,15 @@ def run_gpu(args):
             raise SystemExit("bench.py: pinned host allocation failed")
         eng.memcpy(h_pcm_p, d_pcm, pcm_bytes, 2)
         eng.set_profiling(False)
+        # the link itself, for context: plain pinned copies of the same buffers
+        scratch_d = eng.device_alloc(pcm_bytes)
+        t0 = time.perf_counter()
+        eng.memcpy(scratch_d, h_pcm_p, pcm_bytes, 1)
+        h2d_gbs = pcm_bytes / (time.perf_counter() - t0) / 1e9
+        t0 = time.perf_counter()
+        eng.memcpy(h_out_p, scratch_d, min(out_cap, pcm_bytes), 2)
+        d2h_gbs = min(out_cap, pcm_bytes) / (time.perf_counter() - t0) / 1e9
+        eng.device_free(scratch_d)
 
         def e2e_step():
             return eng.encode(opt, RATE, BPS, CH, h_pcm_p, pcm_bytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.HOST,
@@ -366,7 +375,7 @@ def run_gpu(args):
         e2e_ms = float(dt.item()) / args.e2e_steps * 1e3
         line["e2e"] = {"value": samples_per_step * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": int(pcm_bytes), "d2h_bytes_per_step": int(total + 4 * len(sizes)),
-                       "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+                       "ms_per_step": e2e_ms, "steps": args.e2e_steps, "pinned_copy_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs},
                        "api": "flacb200_encode(host PCM -> host frames + frame sizes)"}
         L.flacb200_host_free(h_pcm_p)
         L.flacb200_host_free(h_out_p)

@@ -710,7 +710,7 @@ __global__ void k_decide(EncCfg cfg, const FrameDesc* __restrict__ descs, const 
 // single CTA of 1024 threads: out_off = totals[0] + exclusive scan of frame_bytes; then totals[0] += sum,
 // totals[1] = first byte of this group, totals[2] = one past its last byte (read by k_zero)
 __global__ void __launch_bounds__(1024) k_scan(uint32_t nframes, FrameRec* __restrict__ frecs, uint32_t* __restrict__ frame_bytes_out,
-                                               unsigned long long* __restrict__ totals)
+                                               unsigned long long* __restrict__ totals, unsigned long long* __restrict__ mapped_total)
 {
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long tile_total;
@@ -752,6 +752,7 @@ __global__ void __launch_bounds__(1024) k_scan(uint32_t nframes, FrameRec* __res
         totals[0] = carry;
         totals[1] = start;
         totals[2] = carry;
+        if (mapped_total) *mapped_total = carry;   // host-mapped: the cumulative size reaches the host without a copy
     }
 }
 
@@ -1047,10 +1048,11 @@ cudaError_t launch_residual(const EncCfg& cfg, const FrameDesc* descs, const int
 }
 
 void launch_decide_scan(const EncCfg& cfg, const FrameDesc* descs, const CandRec* cands, const unsigned long long* abssum,
-                        FrameRec* frecs, uint32_t* frame_bytes_out, unsigned long long* totals, uint8_t* out, cudaStream_t st)
+                        FrameRec* frecs, uint32_t* frame_bytes_out, unsigned long long* totals, unsigned long long* mapped_total, uint8_t* out,
+                        cudaStream_t st)
 {
     k_decide<<<(cfg.nframes + 127) / 128, 128, 0, st>>>(cfg, descs, cands, abssum, frecs);
-    k_scan<<<1, 1024, 0, st>>>(cfg.nframes, frecs, frame_bytes_out, totals);
+    k_scan<<<1, 1024, 0, st>>>(cfg.nframes, frecs, frame_bytes_out, totals, mapped_total);
     k_zero<<<148 * 4, 256, 0, st>>>(out, totals);
 }
 

@@ -24,7 +24,7 @@ bool residual_uses_smem(const EncCfg&);
 cudaError_t launch_residual(const EncCfg&, const FrameDesc*, const int32_t*, const uint32_t*, const unsigned long long*, const LpcRec*, CandRec*,
                             int32_t*, cudaStream_t);
 void launch_decide_scan(const EncCfg&, const FrameDesc*, const CandRec*, const unsigned long long*, FrameRec*, uint32_t*, unsigned long long*,
-                        uint8_t*, cudaStream_t);
+                        unsigned long long*, uint8_t*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 bool analyze_fast_ok(const EncCfg&);
 cudaError_t launch_pack2_crc(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
@@ -54,6 +54,11 @@ struct DevBuf {
 struct flacb200_engine {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host<->device copies overlapped with the kernels of other launch groups
+    std::vector<cudaEvent_t> pipe_ev;                      // per group: input landed, group done
+    unsigned long long* h_totals = nullptr;                // pinned + mapped: cumulative output bytes after each group,
+    unsigned long long* d_h_totals = nullptr;              // written by k_scan itself (no trip through the copy queue)
+    size_t h_totals_cap = 0;
     uint32_t chunk_frames = 0;
     bool profiling = false, keep_info = true;
     DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, dec[12];
@@ -152,6 +157,8 @@ int flacb200_engine_create(int device, flacb200_engine** out)
         return cuda_err(err);
     }
     e->stream = e->own_stream;
+    cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
     for (auto& ev : e->ev) cudaEventCreate(&ev);
     *out = e;
     return 0;
@@ -172,6 +179,10 @@ void flacb200_engine_destroy(flacb200_engine* e)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->evpool) cudaEventDestroy(ev);
     if (e->host_stage) cudaFreeHost(e->host_stage);
+    if (e->h_totals) cudaFreeHost(e->h_totals);
+    for (auto& ev : e->pipe_ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(e->copy_in);
+    cudaStreamDestroy(e->copy_out);
     cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -393,7 +404,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     ENS(e->frecs, (size_t)chunk * sizeof(FrameRec));
     ENS(e->fbytes, nframes * sizeof(uint32_t));
     ENS(e->totals, 64);
-    ENS(e->out, bound + 64);
+    if (!(out && out_location == FLACB200_DEVICE && out_capacity >= bound + 64 && ((uintptr_t)out & 15) == 0)) ENS(e->out, bound + 64);
     const bool need_scratch = !residual_uses_smem(cfg);
     if (need_scratch) ENS(e->scratch, ncand_chunk * 2 * cfg.bpad * sizeof(int32_t));
     if (e->win_dirty || (opt->max_lpc_order && e->winpool.cap < e->win_host.size() * sizeof(double))) {
@@ -403,16 +414,53 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         e->win_dirty = false;
     }
     const uint8_t* d_pcm;
+    // small uploads first: queued behind the bulk PCM copies they would hold the first launch group back
+    CK(cudaMemcpyAsync(e->descs.p, descs.data(), nframes * sizeof(FrameDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(e->totals.p, 0, 64, st));
     if (e->profiling) cudaEventRecord(e->ev[20], st);
+    const size_t ngroups = (size_t)((nframes + chunk - 1) / chunk);
+    // host buffers: the copies run on their own streams, one launch group at a time, so that the PCM of group k + 1 is
+    // uploaded and the frames of group k - 1 are downloaded while group k is being encoded
+    const bool pipe_in = pcm_location == FLACB200_HOST && pcm_kind != FLACB200_PCM_I32_PLANAR && ngroups > 1;
+    const bool pipe_out = out && out_location == FLACB200_HOST && ngroups > 1;
+    if (pipe_in || pipe_out) {
+        while (e->pipe_ev.size() < 2 * ngroups) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->pipe_ev.push_back(ev);
+        }
+        if (e->h_totals_cap < ngroups) {
+            if (e->h_totals) cudaFreeHost(e->h_totals);
+            e->h_totals = nullptr;
+            CK(cudaHostAlloc((void**)&e->h_totals, (ngroups + 16) * sizeof(unsigned long long), cudaHostAllocMapped));
+            CK(cudaHostGetDevicePointer((void**)&e->d_h_totals, e->h_totals, 0));
+            e->h_totals_cap = ngroups + 16;
+        }
+    }
     if (pcm_location == FLACB200_HOST) {
         ENS(e->pcm, pcm_bytes + 16);
-        CK(cudaMemcpyAsync(e->pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
         d_pcm = (const uint8_t*)e->pcm.p;
+        if (!pipe_in) CK(cudaMemcpyAsync(e->pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
+        else {
+            const size_t fb = (size_t)cfg.channels * sample_bytes;   // bytes per inter-channel sample
+            for (size_t g = 0; g < ngroups; g++) {
+                const uint64_t b0 = g * (uint64_t)chunk, b1 = std::min<uint64_t>(b0 + chunk, nframes);
+                uint64_t lo = ~0ull, hi = 0;
+                for (uint64_t f = b0; f < b1; f++) {
+                    lo = std::min<uint64_t>(lo, descs[f].pcm_off);
+                    hi = std::max<uint64_t>(hi, descs[f].pcm_off + descs[f].n);
+                }
+                CK(cudaMemcpyAsync((uint8_t*)e->pcm.p + lo * fb, (const uint8_t*)pcm + lo * fb, (hi - lo) * fb, cudaMemcpyHostToDevice, e->copy_in));
+                CK(cudaEventRecord(e->pipe_ev[2 * g], e->copy_in));
+            }
+        }
     } else {
         d_pcm = (const uint8_t*)pcm;
     }
-    CK(cudaMemcpyAsync(e->descs.p, descs.data(), nframes * sizeof(FrameDesc), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(e->totals.p, 0, 64, st));
+    // frames go straight into the caller's device buffer when it can hold the worst case
+    uint8_t* d_out = (uint8_t*)e->out.p;
+    const bool direct_out = out && out_location == FLACB200_DEVICE && out_capacity >= bound + 64 && ((uintptr_t)out & 15) == 0;
+    if (direct_out) d_out = (uint8_t*)out;
     if (e->profiling) cudaEventRecord(e->ev[21], st);
 
     uint32_t* d_ormask = (uint32_t*)e->masks.p;
@@ -429,11 +477,13 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     }
     uint32_t launches = 0;
     size_t nchunks = 0;
+    bool pipe_overflow = false;
     cudaEventRecord(e->ev[22], st);
     for (uint64_t base = 0; base < nframes; base += chunk) {
         EncCfg c = cfg;
         c.nframes = (uint32_t)std::min<uint64_t>(chunk, nframes - base);
         const FrameDesc* dd = (const FrameDesc*)e->descs.p + base;
+        if (pipe_in) CK(cudaStreamWaitEvent(st, e->pipe_ev[2 * nchunks], 0));
         CK(cudaMemsetAsync(e->masks.p, 0, masks_bytes, st));
         const size_t eb = nchunks * 6;
         time_mark(e, eb + 0);
@@ -448,13 +498,28 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
                                (int32_t*)e->scratch.p, st));
         time_mark(e, eb + 3);
         launch_decide_scan(c, dd, (const CandRec*)e->cands.p, d_abssum, (FrameRec*)e->frecs.p, (uint32_t*)e->fbytes.p + base,
-                           (unsigned long long*)e->totals.p, (uint8_t*)e->out.p, st);
+                           (unsigned long long*)e->totals.p, pipe_out ? e->d_h_totals + nchunks : nullptr, d_out, st);
         time_mark(e, eb + 4);
-        if (fast_pack) CK(launch_pack2_crc(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, (uint8_t*)e->out.p, st));
-        else CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, (uint8_t*)e->out.p, st));
+        if (fast_pack) CK(launch_pack2_crc(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
+        else CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
         time_mark(e, eb + 5);
+        if (pipe_out) {
+            // frames of this group occupy [h_totals[g - 1], h_totals[g]); the host learns the bounds one group late and
+            // queues the download on the output stream while the next group is already running
+            CK(cudaEventRecord(e->pipe_ev[2 * nchunks + 1], st));
+            if (nchunks >= 1) {
+                const size_t g = nchunks - 1;
+                CK(cudaEventSynchronize(e->pipe_ev[2 * g + 1]));
+                const unsigned long long a = g ? e->h_totals[g - 1] : 0, b = e->h_totals[g];
+                if (b > out_capacity) pipe_overflow = true;
+                else if (b > a) {
+                    CK(cudaStreamWaitEvent(e->copy_out, e->pipe_ev[2 * g + 1], 0));
+                    CK(cudaMemcpyAsync((uint8_t*)out + a, d_out + a, b - a, cudaMemcpyDeviceToHost, e->copy_out));
+                }
+            }
+        }
         nchunks++;
-        launches += 8;
+        launches += (need_planes ? 1u : 0u) + 7u;
         if (keep) {
             CK(cudaMemcpyAsync(e->info_cands.data() + base * cfg.nslots, e->cands.p, (size_t)c.nframes * cfg.nslots * sizeof(CandRec),
                                cudaMemcpyDeviceToHost, st));
@@ -476,9 +541,18 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     if (total_bytes_out) *total_bytes_out = total;
     if (totals[3]) return FLACB200_E_BAD_ARGUMENT;   // a frame referenced a candidate that was never encoded
     if (out) {
-        if (total > out_capacity) return FLACB200_E_OUTPUT_TOO_SMALL;
+        if (total > out_capacity || pipe_overflow) {
+            if (pipe_out) cudaStreamSynchronize(e->copy_out);
+            return FLACB200_E_OUTPUT_TOO_SMALL;
+        }
         if (e->profiling) cudaEventRecord(e->ev[24], st);
-        CK(cudaMemcpyAsync(out, e->out.p, total, out_location == FLACB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+        if (pipe_out) {   // the last group's frames; everything before is already on its way
+            const unsigned long long a = nchunks >= 2 ? e->h_totals[nchunks - 2] : 0;
+            if (total > a) CK(cudaMemcpyAsync((uint8_t*)out + a, d_out + a, total - a, cudaMemcpyDeviceToHost, e->copy_out));
+            CK(cudaStreamSynchronize(e->copy_out));
+        } else if (!direct_out) {
+            CK(cudaMemcpyAsync(out, d_out, total, out_location == FLACB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+        }
         if (e->profiling) cudaEventRecord(e->ev[25], st);
         CK(cudaStreamSynchronize(st));
     }
