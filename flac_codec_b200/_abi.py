@@ -67,7 +67,36 @@ class Timings(C.Structure):
                 ("kernel_launches", C.c_uint32 * 8), ("launches", C.c_uint32)]
 
 
+class WriterOptions(C.Structure):
+    _fields_ = [("frame", Options), ("padding", C.c_int32), ("seektable_kind", C.c_uint32), ("seektable_n", C.c_uint32),
+                ("launch_frames", C.c_uint32)]
+
+
+class WriterStats(C.Structure):
+    _fields_ = [("pcm_frames_written", C.c_uint64), ("frames_written", C.c_uint64), ("frame_bytes_written", C.c_uint64),
+                ("min_frame_size", C.c_uint32), ("max_frame_size", C.c_uint32), ("launches", C.c_uint32),
+                ("md5", C.c_uint8 * 16)]
+
+
+class Streaminfo(C.Structure):
+    _fields_ = [("min_block_size", C.c_uint16), ("max_block_size", C.c_uint16), ("min_frame_size", C.c_uint32),
+                ("max_frame_size", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("bits_per_sample", C.c_uint32), ("total_samples", C.c_uint64), ("md5", C.c_uint8 * 16),
+                ("frames_start", C.c_uint64), ("n_seekpoints", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class SeekPoint(C.Structure):
+    _fields_ = [("sample_offset", C.c_uint64), ("byte_offset", C.c_uint64), ("frame_samples", C.c_uint32),
+                ("placeholder", C.c_uint32)]
+
+
 EXPORTS = [
+    "flacb200_writer_options_default", "flacb200_writer_options_fast", "flacb200_writer_options_best", "flacb200_writer_open",
+    "flacb200_writer_close", "flacb200_total_from_bytes", "flacb200_total_from_samples", "flacb200_writer_header",
+    "flacb200_writer_write_bytes", "flacb200_writer_write_samples", "flacb200_writer_write_channels", "flacb200_writer_drain",
+    "flacb200_writer_flush", "flacb200_writer_finalize", "flacb200_writer_get_stats", "flacb200_read_streaminfo",
+    "flacb200_reader_open", "flacb200_reader_close", "flacb200_reader_info", "flacb200_reader_seektable", "flacb200_reader_read",
+    "flacb200_reader_seek", "flacb200_reader_verify", "flacb200_md5",
     "flacb200_options_default", "flacb200_options_fast", "flacb200_options_best", "flacb200_engine_create",
     "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_engine_set_keep_info", "flacb200_encode",
     "flacb200_encode_bound", "flacb200_encode_last_info", "flacb200_decode", "flacb200_set_profiling",
@@ -130,6 +159,35 @@ def lib():
     L.flacb200_strerror.argtypes = [C.c_int]
     L.flacb200_strerror.restype = C.c_char_p
     L.flacb200_version.restype = C.c_char_p
+    # ---- include/flacb200_stream.h ----
+    u8pp, szp = C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)
+    for n in ("flacb200_writer_options_default", "flacb200_writer_options_fast", "flacb200_writer_options_best"):
+        getattr(L, n).argtypes = [C.POINTER(WriterOptions)]
+        getattr(L, n).restype = None
+    L.flacb200_writer_open.argtypes = [vp, C.POINTER(WriterOptions), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(vp)]
+    L.flacb200_writer_close.argtypes = [vp]
+    L.flacb200_writer_close.restype = None
+    L.flacb200_total_from_bytes.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, u64p]
+    L.flacb200_total_from_samples.argtypes = [C.c_uint64, C.c_uint32, u64p]
+    L.flacb200_writer_header.argtypes = [vp, u8pp, szp]
+    L.flacb200_writer_write_bytes.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    L.flacb200_writer_write_samples.argtypes = [vp, vp, C.c_size_t]
+    L.flacb200_writer_write_channels.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_size_t]
+    L.flacb200_writer_drain.argtypes = [vp, u8pp, szp]
+    L.flacb200_writer_flush.argtypes = [vp]
+    L.flacb200_writer_finalize.argtypes = [vp]
+    L.flacb200_writer_get_stats.argtypes = [vp, C.POINTER(WriterStats)]
+    L.flacb200_read_streaminfo.argtypes = [vp, C.c_size_t, C.POINTER(Streaminfo)]
+    L.flacb200_reader_open.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp)]
+    L.flacb200_reader_close.argtypes = [vp]
+    L.flacb200_reader_close.restype = None
+    L.flacb200_reader_info.argtypes = [vp, C.POINTER(Streaminfo)]
+    L.flacb200_reader_seektable.argtypes = [vp, C.POINTER(SeekPoint), C.c_size_t, szp]
+    L.flacb200_reader_read.argtypes = [vp, vp, C.c_size_t, C.c_int, szp]
+    L.flacb200_reader_seek.argtypes = [vp, C.c_uint64]
+    L.flacb200_reader_verify.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint8 * 16)]
+    L.flacb200_md5.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint8 * 16)]
+    L.flacb200_md5.restype = None
     _lib = L
     return L
 

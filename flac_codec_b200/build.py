@@ -1,17 +1,23 @@
-"""Builds libflacb200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""Builds libflacb200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
+
+Each source is compiled to build/<name>.o (in parallel, only when it or a header changed) and the objects are
+linked into flac_codec_b200/libflacb200.so."""
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "..", "build", "flacb200")
 LIB = os.path.join(HERE, "libflacb200.so")
-SOURCES = ["engine.cu", "encode_kernels.cu", "decode_kernels.cu", "synth.cu"]
+SOURCES = ["engine.cu", "encode_kernels.cu", "decode_kernels.cu", "synth.cu", "stream.cpp"]
+HEADERS = [os.path.join(HERE, "..", "include", h) for h in ("flacb200.h", "flacb200_stream.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ]
 
 
@@ -22,25 +28,52 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+def _ccbin() -> list:
+    # the distro g++ (the image's /opt/gcc wrapper lacks some runtime pieces)
+    return ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+
+
+def _shared_deps() -> list:
+    return HEADERS + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inl", ".h", ".hpp"))]
+
+
+def _obj(src: str) -> str:
+    return os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+
+
+def _stale(src: str) -> bool:
+    o = _obj(src)
+    if not os.path.exists(o):
+        return True
+    t = os.path.getmtime(o)
+    return any(os.path.getmtime(d) > t for d in [os.path.join(CSRC, src)] + _shared_deps())
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "flacb200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + HEADERS
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    # the distro g++ (the image's /opt/gcc wrapper lacks some runtime pieces)
-    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
-    cmd = [_nvcc(), *flags, *ccbin, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd, cwd=CSRC)
+    os.makedirs(OBJ, exist_ok=True)
+    todo = [s for s in SOURCES if force or _stale(s)]
+
+    def compile_one(src: str):
+        cmd = [_nvcc(), *NVCC_FLAGS, *_ccbin(), "-c", "-o", _obj(src), os.path.join(CSRC, src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        subprocess.check_call(cmd, cwd=CSRC)
+
+    with ThreadPoolExecutor(max_workers=max(len(todo), 1)) as ex:
+        list(ex.map(compile_one, todo))
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", *_ccbin(), "-shared", "-o", LIB] + [_obj(s) for s in SOURCES]
+    subprocess.check_call(link, cwd=CSRC)
     return LIB
 
 

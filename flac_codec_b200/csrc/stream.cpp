@@ -1,0 +1,821 @@
+// stream.cpp -- stream-level host layer of libflacb200.so (include/flacb200_stream.h).
+//
+// The reference's writer facades feed one block at a time into Encoder::encode (src/encode.rs:1997); here the
+// same facade state (partial-block buffer, MD5, seek points, STREAMINFO bookkeeping) sits in front of the batch
+// engine: blocks are collected in pinned memory and encoded `launch_frames` at a time by flacb200_encode, while
+// the MD5 of the same bytes is computed on a host thread.  The reader parses the metadata blocks on the host and
+// decodes all frames of the file image in one flacb200_decode call.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <future>
+#include <vector>
+
+#include "../../include/flacb200_stream.h"
+
+namespace {
+
+// flac_codec::Error ordinals used here (src/lib.rs:57-193, 1-based; see flacb200_strerror)
+enum : int {
+    E_IO = 1, E_MISSING_FLAC_TAG = 3, E_MISSING_STREAMINFO = 4, E_MULTIPLE_STREAMINFO = 5, E_MULTIPLE_SEEKTABLE = 6,
+    E_INVALID_SEEKTABLE_SIZE = 8, E_INVALID_SEEKTABLE_POINT = 9, E_RESERVED_METADATA_BLOCK = 14, E_INVALID_METADATA_BLOCK = 15,
+    E_INVALID_METADATA_BLOCK_SIZE = 16, E_INVALID_SAMPLE_RATE = 26, E_EXCESSIVE_CHANNELS = 30, E_INVALID_BPS = 33,
+    E_INVALID_SEEK = 37, E_EXCESSIVE_TOTAL_SAMPLES = 57, E_NO_SAMPLES = 58, E_SAMPLE_COUNT_MISMATCH = 59,
+    E_SAMPLES_NOT_DIVISIBLE = 61, E_INVALID_TOTAL_BYTES = 62, E_INVALID_TOTAL_SAMPLES = 63, E_CHANNEL_COUNT_MISMATCH = 64,
+    E_CHANNEL_LENGTH_MISMATCH = 65,
+};
+
+constexpr uint64_t MAX_SAMPLES = 1ull << 36;             // Encoder::MAX_SAMPLES: STREAMINFO keeps 36 bits
+constexpr size_t MAX_SEEK_POINTS = (1u << 24) / 18;      // SeekTable::MAX_POINTS (src/metadata/mod.rs:1989)
+constexpr uint32_t MAX_FRAME_SIZE = (1u << 24) - 1;      // Streaminfo::MAX_FRAME_SIZE
+
+// ---- MD5 (RFC 1321), the sum STREAMINFO stores over the little-endian PCM (src/encode.rs:1292-1318) ----
+struct Md5 {
+    uint32_t a = 0x67452301u, b = 0xefcdab89u, c = 0x98badcfeu, d = 0x10325476u;
+    uint64_t total = 0;
+    uint8_t tail[64];
+    uint32_t ntail = 0;
+
+    static inline uint32_t rol(uint32_t v, int s) { return (v << s) | (v >> (32 - s)); }
+
+    void block(const uint8_t* p)
+    {
+        static const uint32_t K[64] = {
+            0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8, 0x8b44f7af, 0xffff5bb1,
+            0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821, 0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453,
+            0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a, 0xfffa3942,
+            0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70, 0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05,
+            0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665, 0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d,
+            0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+        static const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
+                                  4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+        uint32_t m[16];
+        for (int i = 0; i < 16; i++) m[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+        uint32_t A = a, B = b, C = c, D = d;
+        for (int i = 0; i < 64; i++) {
+            uint32_t f;
+            int g;
+            if (i < 16) { f = (B & C) | (~B & D); g = i; }
+            else if (i < 32) { f = (D & B) | (~D & C); g = (5 * i + 1) & 15; }
+            else if (i < 48) { f = B ^ C ^ D; g = (3 * i + 5) & 15; }
+            else { f = C ^ (B | ~D); g = (7 * i) & 15; }
+            const uint32_t t = D;
+            D = C;
+            C = B;
+            B = B + rol(A + f + K[i] + m[g], S[i]);
+            A = t;
+        }
+        a += A; b += B; c += C; d += D;
+    }
+
+    void update(const uint8_t* p, size_t n)
+    {
+        total += n;
+        if (ntail) {
+            const size_t take = std::min<size_t>(64 - ntail, n);
+            memcpy(tail + ntail, p, take);
+            ntail += (uint32_t)take;
+            p += take;
+            n -= take;
+            if (ntail < 64) return;
+            block(tail);
+            ntail = 0;
+        }
+        while (n >= 64) {
+            block(p);
+            p += 64;
+            n -= 64;
+        }
+        if (n) {
+            memcpy(tail, p, n);
+            ntail = (uint32_t)n;
+        }
+    }
+
+    void final(uint8_t out[16]) const   // does not disturb the running state (md5.clone().finalize(), :2100)
+    {
+        Md5 t = *this;
+        const uint64_t bits = t.total * 8;
+        uint8_t pad[72] = {0x80};
+        const size_t padlen = (t.ntail < 56 ? 56 : 120) - t.ntail;
+        t.update(pad, padlen);
+        uint8_t len[8];
+        for (int i = 0; i < 8; i++) len[i] = (uint8_t)(bits >> (8 * i));
+        t.update(len, 8);
+        const uint32_t v[4] = {t.a, t.b, t.c, t.d};
+        for (int i = 0; i < 4; i++)
+            for (int k = 0; k < 4; k++) out[4 * i + k] = (uint8_t)(v[i] >> (8 * k));
+    }
+};
+
+void put_be(uint8_t* p, uint64_t v, int bytes)
+{
+    for (int i = 0; i < bytes; i++) p[i] = (uint8_t)(v >> (8 * (bytes - 1 - i)));
+}
+
+uint64_t get_be(const uint8_t* p, int bytes)
+{
+    uint64_t v = 0;
+    for (int i = 0; i < bytes; i++) v = (v << 8) | p[i];
+    return v;
+}
+
+struct SeekPt {
+    uint64_t sample_offset, byte_offset;
+    uint32_t frame_samples;
+};
+
+// growable byte buffer, pinned when a device is present (cudaMemcpyAsync from pageable memory is staged and slow)
+struct HostBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0, len = 0;
+    bool pinned = false;
+    ~HostBuf() { release(); }
+    void release()
+    {
+        if (!p) return;
+        if (pinned) flacb200_host_free(p);
+        else free(p);
+        p = nullptr;
+        cap = len = 0;
+    }
+    bool reserve(size_t want, bool try_pinned)
+    {
+        if (want <= cap) return true;
+        size_t ncap = std::max<size_t>(want, cap + cap / 2 + 4096);
+        uint8_t* np = nullptr;
+        bool npinned = false;
+        if (try_pinned) {
+            np = (uint8_t*)flacb200_host_alloc(ncap);
+            npinned = np != nullptr;
+        }
+        if (!np) np = (uint8_t*)malloc(ncap);
+        if (!np) return false;
+        if (len) memcpy(np, p, len);
+        const size_t keep = len;
+        release();
+        p = np;
+        cap = ncap;
+        len = keep;
+        pinned = npinned;
+        return true;
+    }
+};
+
+}   // namespace
+
+// =================================================================================================
+// writer
+// =================================================================================================
+struct flacb200_writer {
+    flacb200_engine* engine = nullptr;
+    flacb200_writer_options opt{};
+    uint32_t rate = 0, bps = 0, channels = 0, bytes_per_sample = 0, block_size = 0, launch_frames = 0;
+    uint64_t total = 0;             // expected inter-channel samples, 0 = unknown
+    size_t pcm_frame_bytes = 0, block_bytes = 0;
+    HostBuf pending;                // little-endian packed PCM not yet encoded (whole samples)
+    uint8_t partial[8] = {0};            // bytes of an incomplete sample handed to write_bytes
+    uint32_t npartial = 0;
+    HostBuf stage;                  // output of one flacb200_encode call
+    std::vector<uint8_t> ready;     // frames not yet drained
+    std::vector<uint8_t> drained;   // storage behind the pointer returned by drain
+    std::vector<uint32_t> sizes;
+    std::vector<SeekPt> points;     // one per frame (Encoder::encode pushes one per frame, :1999)
+    std::vector<uint8_t> header;
+    size_t n_placeholders = 0;
+    bool have_seektable = false, finalized = false, failed = false;
+    uint64_t pcm_frames_encoded = 0, frames = 0, frame_bytes = 0, next_frame_number = 0;
+    uint32_t min_frame = 0, max_frame = 0, launches = 0;
+    Md5 md5;
+    uint8_t md5_final[16] = {0};
+    bool md5_known = false;
+};
+
+namespace {
+
+// SeekTableInterval::filter (src/encode.rs:1338-1358)
+template <class GetPoint>
+void seek_filter(const flacb200_writer_options& o, uint32_t rate, size_t n, GetPoint get, std::vector<size_t>& keep)
+{
+    keep.clear();
+    if (o.seektable_kind == 1) {
+        const uint64_t nth = (uint64_t)((uint32_t)(uint8_t)o.seektable_n * rate);
+        uint64_t offset = 0;
+        for (size_t i = 0; i < n; i++) {
+            const SeekPt p = get(i);
+            if (offset >= p.sample_offset && offset < p.sample_offset + p.frame_samples) {
+                offset += nth;
+                keep.push_back(i);
+            }
+        }
+    } else if (o.seektable_kind == 2) {
+        const size_t step = o.seektable_n ? o.seektable_n : 1;
+        for (size_t i = 0; i < n; i += step) keep.push_back(i);
+    }
+}
+
+void put_seekpoint(uint8_t* p, const SeekPt* s)
+{
+    if (s) {
+        put_be(p, s->sample_offset, 8);
+        put_be(p + 8, s->byte_offset, 8);
+        put_be(p + 16, s->frame_samples, 2);
+    } else {   // SeekPoint::Placeholder
+        put_be(p, ~0ull, 8);
+        put_be(p + 8, 0, 8);
+        put_be(p + 16, 0, 2);
+    }
+}
+
+// write_blocks (src/metadata/mod.rs:904-976): "fLaC", STREAMINFO, [SEEKTABLE], [PADDING] in the order Encoder::new
+// sorts them (:1944-1951); at finalize the defined seek points replace the placeholders (:2041-2051) or, when no
+// placeholder table exists, a table is carved out of the padding and appended after it (:2053-2072).
+void build_header(flacb200_writer& w, bool final_pass)
+{
+    const flacb200_writer_options& o = w.opt;
+    const bool padding = o.padding > 0;
+    size_t pad_body = padding ? (size_t)o.padding : 0;
+    std::vector<size_t> keep;
+    bool table_after_padding = false;
+    if (final_pass && o.seektable_kind) {
+        seek_filter(o, w.rate, w.points.size(), [&](size_t i) { return w.points[i]; }, keep);
+        if (!w.have_seektable && padding) {
+            if (keep.size() > MAX_SEEK_POINTS) keep.resize(MAX_SEEK_POINTS);
+            const size_t table_size = 4 + 18 * keep.size();   // MetadataBlock::total_size(): header + body
+            if (pad_body >= table_size) {
+                table_after_padding = true;
+                pad_body -= table_size;
+            }
+        }
+    }
+    std::vector<uint8_t>& h = w.header;
+    h.clear();
+    h.insert(h.end(), {'f', 'L', 'a', 'C'});
+    auto block_header = [&](uint8_t type, bool last, size_t body) {
+        uint8_t b[4];
+        b[0] = (uint8_t)((last ? 0x80 : 0) | type);
+        put_be(b + 1, body, 3);
+        h.insert(h.end(), b, b + 4);
+    };
+    // STREAMINFO (src/metadata/mod.rs:1742-1760)
+    block_header(0, !(w.have_seektable || padding), 34);
+    {
+        uint8_t b[34];
+        put_be(b, w.block_size, 2);
+        put_be(b + 2, w.block_size, 2);
+        put_be(b + 4, w.min_frame, 3);
+        put_be(b + 7, w.max_frame, 3);
+        const uint64_t total = final_pass ? w.pcm_frames_encoded : w.total;
+        const uint64_t v = ((uint64_t)w.rate << 44) | ((uint64_t)(w.channels - 1) << 41) | ((uint64_t)(w.bps - 1) << 36) | (total & 0xFFFFFFFFFull);
+        put_be(b + 10, v, 8);
+        if (w.md5_known) memcpy(b + 18, w.md5_final, 16);
+        else memset(b + 18, 0, 16);
+        h.insert(h.end(), b, b + 34);
+    }
+    if (w.have_seektable) {
+        block_header(3, !padding, 18 * w.n_placeholders);
+        const size_t at = h.size();
+        h.resize(at + 18 * w.n_placeholders);
+        for (size_t i = 0; i < w.n_placeholders; i++)
+            put_seekpoint(h.data() + at + 18 * i, (final_pass && i < keep.size()) ? &w.points[keep[i]] : nullptr);
+    }
+    if (padding) {
+        block_header(1, !table_after_padding, pad_body);
+        h.resize(h.size() + pad_body, 0);
+        if (table_after_padding) {
+            block_header(3, true, 18 * keep.size());
+            const size_t at = h.size();
+            h.resize(at + 18 * keep.size());
+            for (size_t i = 0; i < keep.size(); i++) put_seekpoint(h.data() + at + 18 * i, &w.points[keep[i]]);
+        }
+    }
+}
+
+int writer_reserve_pending(flacb200_writer& w, size_t extra)
+{
+    if (!w.pending.reserve(w.pending.len + extra, w.engine != nullptr)) return FLACB200_E_OUT_OF_MEMORY;
+    return 0;
+}
+
+// Encodes the first n_pcm inter-channel samples of `pending` (whole blocks, or the final short block).
+int writer_encode(flacb200_writer& w, uint64_t n_pcm)
+{
+    if (n_pcm == 0) return 0;
+    if (!w.engine) return FLACB200_E_NO_DEVICE;
+    const size_t nbytes = (size_t)n_pcm * w.pcm_frame_bytes;
+    const uint64_t nblocks = (n_pcm + w.block_size - 1) / w.block_size;
+    flacb200_stream_params prm{};
+    prm.sample_rate = w.rate;
+    prm.bits_per_sample = w.bps;
+    prm.channels = w.channels;
+    flacb200_segment seg{0, n_pcm, w.next_frame_number};
+    const size_t bound = flacb200_encode_bound(&w.opt.frame, &prm, &seg, 1);
+    if (!w.stage.reserve(bound, true)) return FLACB200_E_OUT_OF_MEMORY;
+    const size_t first = w.sizes.size();
+    w.sizes.resize(first + nblocks);
+    // MD5 of exactly these bytes, concurrently with the GPU (FlacByteWriter::write :369, update_md5 :1292)
+    std::future<void> md5_job = std::async(std::launch::async, [&w, nbytes] { w.md5.update(w.pending.p, nbytes); });
+    uint64_t nf = 0, total = 0;
+    flacb200_engine_set_keep_info(w.engine, 0);
+    const int rc = flacb200_encode(w.engine, &w.opt.frame, &prm, w.pending.p, nbytes, FLACB200_PCM_BYTES_LE, FLACB200_HOST, 0, &seg, 1,
+                                   w.stage.p, w.stage.cap, FLACB200_HOST, w.sizes.data() + first, nblocks, &nf, &total);
+    md5_job.get();
+    w.launches++;
+    if (rc) {
+        w.sizes.resize(first);
+        return rc;
+    }
+    w.ready.insert(w.ready.end(), w.stage.p, w.stage.p + total);
+    uint64_t done = 0;
+    for (uint64_t f = 0; f < nf; f++) {
+        const uint32_t s = w.sizes[first + f];
+        const uint32_t n = (uint32_t)std::min<uint64_t>(w.block_size, n_pcm - done);
+        w.points.push_back(SeekPt{w.pcm_frames_encoded + done, w.frame_bytes, n});   // :1999-2003 (offsets count from the first frame)
+        w.frame_bytes += s;
+        if (s < MAX_FRAME_SIZE && s != 0) {   // encode_frame tail (:2413-2436)
+            w.min_frame = w.min_frame == 0 ? s : std::min(w.min_frame, s);
+            w.max_frame = w.max_frame == 0 ? s : std::max(w.max_frame, s);
+        }
+        done += n;
+    }
+    w.pcm_frames_encoded += n_pcm;
+    w.frames += nf;
+    w.next_frame_number += nf;
+    // keep what was not encoded
+    const size_t rest = w.pending.len - nbytes;
+    if (rest) memmove(w.pending.p, w.pending.p + nbytes, rest);
+    w.pending.len = rest;
+    return 0;
+}
+
+// Encoder::encode's running-total check (:2006-2011), applied to the blocks that become complete with this write
+int writer_after_append(flacb200_writer& w, bool force)
+{
+    const uint64_t whole = w.pending.len / w.block_bytes;
+    if (w.total && w.pcm_frames_encoded + whole * w.block_size > w.total) {
+        w.failed = true;
+        return E_EXCESSIVE_TOTAL_SAMPLES;
+    }
+    if (whole && (force || whole >= w.launch_frames)) {
+        const int rc = writer_encode(w, whole * w.block_size);
+        if (rc) w.failed = true;
+        return rc;
+    }
+    return 0;
+}
+
+}   // namespace
+
+extern "C" {
+
+void flacb200_writer_options_default(flacb200_writer_options* o)
+{
+    memset(o, 0, sizeof(*o));
+    flacb200_options_default(&o->frame);
+    o->padding = 4096;       // Options::default(): Padding { size: 4096 } (:1392)
+    o->seektable_kind = 1;   // SeekTableInterval::default(): every 10 seconds (:1329)
+    o->seektable_n = 10;
+}
+
+void flacb200_writer_options_fast(flacb200_writer_options* o)
+{
+    flacb200_writer_options_default(o);
+    flacb200_options_fast(&o->frame);
+}
+
+void flacb200_writer_options_best(flacb200_writer_options* o)
+{
+    flacb200_writer_options_default(o);
+    flacb200_options_best(&o->frame);
+}
+
+int flacb200_total_from_bytes(uint64_t total_bytes, uint32_t bits_per_sample, uint32_t channels, uint64_t* pcm_frames)
+{
+    if (bits_per_sample < 1 || bits_per_sample > 32) return E_INVALID_BPS;
+    const uint64_t bytes_per_sample = (bits_per_sample + 7) / 8;
+    if (channels == 0 || total_bytes % channels || (total_bytes / channels) % bytes_per_sample) return E_SAMPLES_NOT_DIVISIBLE;   // :170-175
+    const uint64_t n = total_bytes / channels / bytes_per_sample;
+    if (n == 0) return E_INVALID_TOTAL_BYTES;
+    if (pcm_frames) *pcm_frames = n;
+    return 0;
+}
+
+int flacb200_total_from_samples(uint64_t total_samples, uint32_t channels, uint64_t* pcm_frames)
+{
+    if (channels == 0 || total_samples % channels) return E_SAMPLES_NOT_DIVISIBLE;   // :516-519
+    const uint64_t n = total_samples / channels;
+    if (n == 0) return E_INVALID_TOTAL_SAMPLES;
+    if (pcm_frames) *pcm_frames = n;
+    return 0;
+}
+
+int flacb200_writer_open(flacb200_engine* engine, const flacb200_writer_options* opt, uint32_t sample_rate, uint32_t bits_per_sample,
+                         uint32_t channels, uint64_t total_pcm_frames, flacb200_writer** out)
+{
+    if (!opt || !out) return FLACB200_E_BAD_ARGUMENT;
+    if (bits_per_sample < 1 || bits_per_sample > 32) return E_INVALID_BPS;   // SignedBitCount<32>::try_from (:151)
+    if (opt->frame.block_size < 16) return FLACB200_E_BAD_ARGUMENT;          // OptionsError::InvalidBlockSize (:1418)
+    if (sample_rate >= (1u << 20)) return E_INVALID_SAMPLE_RATE;             // :1899-1902
+    if (channels < 1 || channels > 8) return E_EXCESSIVE_CHANNELS;           // :1904-1908
+    if (total_pcm_frames >= MAX_SAMPLES) return E_EXCESSIVE_TOTAL_SAMPLES;   // :1909-1915
+    flacb200_writer* w = new flacb200_writer();
+    w->engine = engine;
+    w->opt = *opt;
+    w->rate = sample_rate;
+    w->bps = bits_per_sample;
+    w->channels = channels;
+    w->total = total_pcm_frames;
+    w->bytes_per_sample = (bits_per_sample + 7) / 8;
+    w->block_size = opt->frame.block_size;
+    w->launch_frames = opt->launch_frames ? opt->launch_frames : 4096;
+    w->pcm_frame_bytes = (size_t)w->bytes_per_sample * channels;
+    w->block_bytes = w->pcm_frame_bytes * w->block_size;
+    // placeholder SEEKTABLE sized from the expected total (:1920-1939)
+    if (total_pcm_frames && opt->seektable_kind) {
+        const uint64_t bs = w->block_size, nblocks = (total_pcm_frames + bs - 1) / bs;
+        std::vector<size_t> keep;
+        seek_filter(*opt, sample_rate, (size_t)nblocks, [&](size_t i) {   // EncoderSeekPoint::placeholders (:2131)
+            const uint64_t off = (uint64_t)i * bs;
+            return SeekPt{off, 0, (uint32_t)std::min<uint64_t>(bs, total_pcm_frames - off)};
+        }, keep);
+        w->n_placeholders = std::min(keep.size(), MAX_SEEK_POINTS);
+        w->have_seektable = true;
+    }
+    build_header(*w, false);
+    *out = w;
+    return 0;
+}
+
+void flacb200_writer_close(flacb200_writer* w) { delete w; }
+
+int flacb200_writer_header(flacb200_writer* w, const uint8_t** bytes, size_t* len)
+{
+    if (!w || !bytes || !len) return FLACB200_E_BAD_ARGUMENT;
+    *bytes = w->header.data();
+    *len = w->header.size();
+    return 0;
+}
+
+int flacb200_writer_write_bytes(flacb200_writer* w, const uint8_t* pcm, size_t n, int big_endian)
+{
+    if (!w || (!pcm && n)) return FLACB200_E_BAD_ARGUMENT;
+    if (w->finalized || w->failed) return FLACB200_E_BAD_ARGUMENT;
+    const uint32_t B = w->bytes_per_sample;
+    int rc = writer_reserve_pending(*w, n + 4);
+    if (rc) return rc;
+    uint8_t* dst = w->pending.p + w->pending.len;
+    size_t added = 0;
+    auto emit = [&](const uint8_t* s) {   // Endianness::bytes_to_le (src/byteorder.rs:181)
+        if (big_endian) for (uint32_t k = 0; k < B; k++) dst[added + k] = s[B - 1 - k];
+        else memcpy(dst + added, s, B);
+        added += B;
+    };
+    if (w->npartial) {
+        while (n && w->npartial < B) {
+            w->partial[(w->npartial++) & 7] = *pcm++;
+            n--;
+        }
+        if (w->npartial == B) {
+            emit(w->partial);
+            w->npartial = 0;
+        }
+    }
+    const size_t whole = n / B;
+    if (!big_endian || B == 1) {
+        memcpy(dst + added, pcm, whole * B);
+        added += whole * B;
+    } else {
+        for (size_t i = 0; i < whole; i++) emit(pcm + i * B);
+    }
+    for (size_t i = whole * B; i < n; i++) w->partial[(w->npartial++) & 7] = pcm[i];
+    w->pending.len += added;
+    return writer_after_append(*w, false);
+}
+
+int flacb200_writer_write_samples(flacb200_writer* w, const int32_t* s, size_t n)
+{
+    if (!w || (!s && n)) return FLACB200_E_BAD_ARGUMENT;
+    if (w->finalized || w->failed) return FLACB200_E_BAD_ARGUMENT;
+    const uint32_t B = w->bytes_per_sample;
+    int rc = writer_reserve_pending(*w, n * B);
+    if (rc) return rc;
+    uint8_t* dst = w->pending.p + w->pending.len;
+    for (size_t i = 0; i < n; i++) {   // update_md5's byte form (:1292-1318): the low B bytes, little endian
+        const uint32_t v = (uint32_t)s[i];
+        for (uint32_t k = 0; k < B; k++) dst[i * B + k] = (uint8_t)(v >> (8 * k));
+    }
+    w->pending.len += n * B;
+    return writer_after_append(*w, false);
+}
+
+int flacb200_writer_write_channels(flacb200_writer* w, const int32_t* const* ch, uint32_t nch, size_t n)
+{
+    if (!w || (!ch && nch)) return FLACB200_E_BAD_ARGUMENT;
+    if (w->finalized || w->failed) return FLACB200_E_BAD_ARGUMENT;
+    if (nch != w->channels) return E_CHANNEL_COUNT_MISMATCH;   // FlacChannelWriter::write (:845-849)
+    const uint32_t B = w->bytes_per_sample;
+    int rc = writer_reserve_pending(*w, n * nch * B);
+    if (rc) return rc;
+    uint8_t* dst = w->pending.p + w->pending.len;
+    for (size_t i = 0; i < n; i++)
+        for (uint32_t c = 0; c < nch; c++) {
+            const uint32_t v = (uint32_t)ch[c][i];
+            for (uint32_t k = 0; k < B; k++) *dst++ = (uint8_t)(v >> (8 * k));
+        }
+    w->pending.len += n * nch * B;
+    return writer_after_append(*w, false);
+}
+
+int flacb200_writer_drain(flacb200_writer* w, const uint8_t** frames, size_t* len)
+{
+    if (!w || !frames || !len) return FLACB200_E_BAD_ARGUMENT;
+    w->drained.swap(w->ready);
+    w->ready.clear();
+    *frames = w->drained.data();
+    *len = w->drained.size();
+    return 0;
+}
+
+int flacb200_writer_flush(flacb200_writer* w)
+{
+    if (!w) return FLACB200_E_BAD_ARGUMENT;
+    if (w->finalized || w->failed) return 0;
+    return writer_after_append(*w, true);
+}
+
+int flacb200_writer_finalize(flacb200_writer* w)
+{
+    if (!w) return FLACB200_E_BAD_ARGUMENT;
+    if (w->finalized) return 0;   // Finalized::Finalized: second call is a no-op (:236)
+    if (w->failed) return FLACB200_E_BAD_ARGUMENT;
+    w->finalized = true;
+    // whole blocks first, then the final short block truncated to whole PCM frames (:240-258, :591-609)
+    const uint64_t pcm = w->pending.len / w->pcm_frame_bytes;
+    if (w->total && w->pcm_frames_encoded + pcm > w->total) return E_EXCESSIVE_TOTAL_SAMPLES;
+    int rc = writer_encode(*w, pcm);
+    if (rc) return rc;
+    w->pending.len = 0;
+    // Encoder::finalize_inner (:2024-2110)
+    if (w->total) {
+        if (w->total != w->pcm_frames_encoded) return E_SAMPLE_COUNT_MISMATCH;
+    } else {
+        if (w->pcm_frames_encoded >= MAX_SAMPLES) return E_EXCESSIVE_TOTAL_SAMPLES;
+        if (w->pcm_frames_encoded == 0) return E_NO_SAMPLES;
+    }
+    w->md5.final(w->md5_final);
+    w->md5_known = true;
+    build_header(*w, true);
+    return 0;
+}
+
+int flacb200_writer_get_stats(flacb200_writer* w, flacb200_writer_stats* s)
+{
+    if (!w || !s) return FLACB200_E_BAD_ARGUMENT;
+    memset(s, 0, sizeof(*s));
+    s->pcm_frames_written = w->pcm_frames_encoded;
+    s->frames_written = w->frames;
+    s->frame_bytes_written = w->frame_bytes;
+    s->min_frame_size = w->min_frame;
+    s->max_frame_size = w->max_frame;
+    s->launches = w->launches;
+    if (w->md5_known) memcpy(s->md5, w->md5_final, 16);
+    return 0;
+}
+
+void flacb200_md5(const uint8_t* data, size_t len, uint8_t out[16])
+{
+    Md5 m;
+    m.update(data, len);
+    m.final(out);
+}
+
+}   // extern "C"
+
+// =================================================================================================
+// reader
+// =================================================================================================
+struct flacb200_reader {
+    flacb200_engine* engine = nullptr;
+    const uint8_t* flac = nullptr;
+    size_t len = 0;
+    flacb200_streaminfo si{};
+    std::vector<flacb200_seekpoint> seektable;
+    HostBuf pcm;                 // decoded little-endian packed PCM of the whole stream
+    bool decoded = false;
+    int decode_error = 0;        // error of the first bad frame ...
+    uint64_t valid_pcm = 0;      // ... which the reference reaches after this many inter-channel samples
+    uint64_t total_pcm = 0;
+    uint64_t pos = 0;            // read position in single-channel samples
+};
+
+namespace {
+
+// BlockIterator (src/metadata/mod.rs:482-646) reduced to what a decoder needs: STREAMINFO first, at most one
+// SEEKTABLE, block types validated, every other block skipped.
+int parse_metadata(const uint8_t* f, size_t len, flacb200_streaminfo* si, std::vector<flacb200_seekpoint>* table)
+{
+    if (len < 4) return E_IO;
+    if (memcmp(f, "fLaC", 4) != 0) return E_MISSING_FLAC_TAG;
+    size_t p = 4;
+    bool first = true, seektable_seen = false;
+    memset(si, 0, sizeof(*si));
+    for (;;) {
+        if (p + 4 > len) return first ? E_MISSING_STREAMINFO : E_IO;
+        const bool last = (f[p] >> 7) != 0;
+        const uint32_t type = f[p] & 0x7F;
+        const size_t blen = (size_t)get_be(f + p + 1, 3);
+        p += 4;
+        if (first) {
+            if (type != 0 || blen != 34 || p + blen > len) return E_MISSING_STREAMINFO;
+            const uint8_t* b = f + p;
+            si->min_block_size = (uint16_t)get_be(b, 2);
+            si->max_block_size = (uint16_t)get_be(b + 2, 2);
+            si->min_frame_size = (uint32_t)get_be(b + 4, 3);
+            si->max_frame_size = (uint32_t)get_be(b + 7, 3);
+            const uint64_t v = get_be(b + 10, 8);
+            si->sample_rate = (uint32_t)(v >> 44);
+            si->channels = (uint32_t)((v >> 41) & 7) + 1;
+            si->bits_per_sample = (uint32_t)((v >> 36) & 31) + 1;
+            si->total_samples = v & 0xFFFFFFFFFull;
+            memcpy(si->md5, b + 18, 16);
+            first = false;
+        } else {
+            if (type >= 7 && type <= 126) return E_RESERVED_METADATA_BLOCK;   // src/metadata/mod.rs:313
+            if (type == 127) return E_INVALID_METADATA_BLOCK;
+            if (p + blen > len) return E_IO;
+            if (type == 0) return E_MULTIPLE_STREAMINFO;
+            if (type == 3) {
+                if (seektable_seen) return E_MULTIPLE_SEEKTABLE;
+                seektable_seen = true;
+                if (blen % 18) return E_INVALID_SEEKTABLE_SIZE;   // :2005
+                uint64_t last_off = 0;
+                bool have_last = false;
+                for (size_t i = 0; i < blen / 18; i++) {
+                    const uint8_t* s = f + p + 18 * i;
+                    flacb200_seekpoint sp{get_be(s, 8), get_be(s + 8, 8), (uint32_t)get_be(s + 16, 2), 0};
+                    sp.placeholder = sp.sample_offset == ~0ull;
+                    if (!sp.placeholder) {   // defined points must increase (Contiguous, :2001-2003)
+                        if (have_last && sp.sample_offset <= last_off) return E_INVALID_SEEKTABLE_POINT;
+                        last_off = sp.sample_offset;
+                        have_last = true;
+                    }
+                    if (table) table->push_back(sp);
+                }
+                si->n_seekpoints = (uint32_t)(blen / 18);
+            }
+        }
+        p += blen;
+        if (last) break;
+    }
+    si->frames_start = p;
+    return 0;
+}
+
+int reader_decode_all(flacb200_reader& r)
+{
+    if (r.decoded) return 0;
+    if (!r.engine) return FLACB200_E_NO_DEVICE;
+    const flacb200_streaminfo& si = r.si;
+    const size_t B = (si.bits_per_sample + 7) / 8, fb = B * si.channels;
+    const size_t nbytes = r.len - (size_t)si.frames_start;
+    flacb200_stream_params prm{};
+    prm.sample_rate = si.sample_rate;
+    prm.bits_per_sample = si.bits_per_sample;
+    prm.channels = si.channels;
+    prm.max_block_size = si.max_block_size;
+    uint64_t cap_pcm = si.total_samples ? si.total_samples : std::max<uint64_t>((uint64_t)nbytes * 8 / fb + si.max_block_size, 65536);
+    for (int attempt = 0; attempt < 12; attempt++) {
+        if (!r.pcm.reserve((size_t)cap_pcm * fb + 64, true)) return FLACB200_E_OUT_OF_MEMORY;
+        flacb200_decode_segment seg{0, nbytes, 0, si.total_samples};
+        uint64_t nf = 0, ns = 0, bad = 0;
+        const int rc = flacb200_decode(r.engine, &prm, r.flac + si.frames_start, nbytes, FLACB200_HOST, &seg, 1, r.pcm.p, (size_t)cap_pcm * fb,
+                                       FLACB200_PCM_BYTES_LE, FLACB200_HOST, 0, &nf, &ns, &bad);
+        if (rc == FLACB200_E_OUTPUT_TOO_SMALL && !si.total_samples) {   // unsized stream: grow and retry
+            cap_pcm *= 4;
+            continue;
+        }
+        if (rc < 0) return rc;
+        r.decoded = true;
+        r.decode_error = rc;
+        // frames in front of the first bad one are delivered before the error surfaces, as with the serial reader
+        r.valid_pcm = rc ? std::min<uint64_t>(ns, (si.min_block_size == si.max_block_size ? bad * si.max_block_size : 0)) : ns;
+        r.total_pcm = r.valid_pcm;
+        r.pcm.len = (size_t)r.valid_pcm * fb;
+        return 0;
+    }
+    return FLACB200_E_OUTPUT_TOO_SMALL;
+}
+
+}   // namespace
+
+extern "C" {
+
+int flacb200_read_streaminfo(const uint8_t* flac, size_t len, flacb200_streaminfo* si)
+{
+    if (!flac || !si) return FLACB200_E_BAD_ARGUMENT;
+    return parse_metadata(flac, len, si, nullptr);
+}
+
+int flacb200_reader_open(flacb200_engine* engine, const uint8_t* flac, size_t len, flacb200_reader** out)
+{
+    if (!flac || !out) return FLACB200_E_BAD_ARGUMENT;
+    flacb200_reader* r = new flacb200_reader();
+    r->engine = engine;
+    r->flac = flac;
+    r->len = len;
+    const int rc = parse_metadata(flac, len, &r->si, &r->seektable);
+    if (rc) {
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return 0;
+}
+
+void flacb200_reader_close(flacb200_reader* r) { delete r; }
+
+int flacb200_reader_info(flacb200_reader* r, flacb200_streaminfo* si)
+{
+    if (!r || !si) return FLACB200_E_BAD_ARGUMENT;
+    *si = r->si;
+    return 0;
+}
+
+int flacb200_reader_seektable(flacb200_reader* r, flacb200_seekpoint* points, size_t capacity, size_t* n_points)
+{
+    if (!r) return FLACB200_E_BAD_ARGUMENT;
+    if (n_points) *n_points = r->seektable.size();
+    if (points)
+        for (size_t i = 0; i < r->seektable.size() && i < capacity; i++) points[i] = r->seektable[i];
+    return 0;
+}
+
+int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm_kind, size_t* n_out)
+{
+    if (!r || (!out && capacity) || !n_out) return FLACB200_E_BAD_ARGUMENT;
+    if (pcm_kind != FLACB200_PCM_BYTES_LE && pcm_kind != FLACB200_PCM_BYTES_BE && pcm_kind != FLACB200_PCM_I32_INTERLEAVED)
+        return FLACB200_E_BAD_ARGUMENT;
+    *n_out = 0;
+    int rc = reader_decode_all(*r);
+    if (rc) return rc;
+    const size_t B = (r->si.bits_per_sample + 7) / 8;
+    const uint64_t end = r->valid_pcm * r->si.channels;   // in single-channel samples
+    if (r->pos >= end) return r->decode_error;             // the bad frame is reached only now (0 = clean end of stream)
+    const uint8_t* src = r->pcm.p + (size_t)r->pos * B;
+    size_t n;
+    if (pcm_kind == FLACB200_PCM_I32_INTERLEAVED) {
+        n = (size_t)std::min<uint64_t>(capacity, end - r->pos);
+        int32_t* o = (int32_t*)out;
+        const uint32_t sh = 32 - 8 * (uint32_t)B;
+        for (size_t i = 0; i < n; i++) {
+            uint32_t v = 0;
+            for (size_t k = 0; k < B; k++) v |= (uint32_t)src[i * B + k] << (8 * k);
+            o[i] = (int32_t)(v << sh) >> sh;
+        }
+        *n_out = n;
+    } else {
+        n = (size_t)std::min<uint64_t>(capacity / B, end - r->pos);
+        uint8_t* o = (uint8_t*)out;
+        if (pcm_kind == FLACB200_PCM_BYTES_LE || B == 1) memcpy(o, src, n * B);
+        else
+            for (size_t i = 0; i < n; i++)
+                for (size_t k = 0; k < B; k++) o[i * B + k] = src[i * B + (B - 1 - k)];
+        *n_out = n * B;
+    }
+    r->pos += n;
+    return 0;
+}
+
+int flacb200_reader_seek(flacb200_reader* r, uint64_t pcm_frame)
+{
+    if (!r) return FLACB200_E_BAD_ARGUMENT;
+    // Decoder::seek (src/decode.rs:1452-1491): a sample beyond the stream is InvalidSeek
+    const uint64_t total = r->si.total_samples;
+    if (total) {
+        if (pcm_frame > total) return E_INVALID_SEEK;
+    } else {
+        const int rc = reader_decode_all(*r);
+        if (rc) return rc;
+        if (pcm_frame > r->total_pcm) return E_INVALID_SEEK;
+    }
+    r->pos = pcm_frame * r->si.channels;
+    return 0;
+}
+
+int flacb200_reader_verify(flacb200_reader* r, int* result, uint8_t md5_out[16])
+{
+    if (!r || !result) return FLACB200_E_BAD_ARGUMENT;
+    int rc = reader_decode_all(*r);
+    if (rc) return rc;
+    if (r->decode_error) return r->decode_error;
+    uint8_t sum[16];
+    flacb200_md5(r->pcm.p, r->pcm.len, sum);
+    if (md5_out) memcpy(md5_out, sum, 16);
+    static const uint8_t zero[16] = {0};
+    if (memcmp(r->si.md5, zero, 16) == 0) *result = 2;        // Verified::NoMD5
+    else *result = memcmp(r->si.md5, sum, 16) == 0 ? 0 : 1;   // MD5Match / MD5Mismatch
+    return 0;
+}
+
+}   // extern "C"

@@ -1,0 +1,140 @@
+/*
+ * flacb200_stream.h -- stream-level C ABI of libflacb200.so: the host side of the reference's writer and
+ * reader facades, on top of the batch frame engine of flacb200.h.
+ *
+ * What each handle replaces in tuffy/flac-codec 1.3.2 (paths relative to the reference tree):
+ *   flacb200_writer   FlacByteWriter / FlacSampleWriter / FlacChannelWriter -> Encoder
+ *                     src/encode.rs:103-405, :431-628, :713-893, Encoder::new/encode/finalize_inner :1882-2110
+ *   flacb200_reader   FlacByteReader / FlacSampleReader -> Decoder
+ *                     src/decode.rs:103-371, :384-620, Decoder::read_frame :1388, verify :1282-1309
+ *   (FlacStreamWriter / FlacStreamReader, src/encode.rs:1063-1290 and src/decode.rs:1158-1268, have no stream state
+ *    besides the frame number: they map to flacb200_encode / flacb200_decode with params.subset = 1.)
+ *
+ * The handles keep the reference's observable behaviour -- same metadata blocks ("fLaC", STREAMINFO, SEEKTABLE
+ * placeholder, PADDING; src/encode.rs:1920-1951, src/metadata/mod.rs:904-976), same buffering of partial blocks, same
+ * MD5 and seek points, same errors (return value = 1-based ordinal of flac_codec::Error, as in flacb200.h) -- but
+ * encode `launch_frames` blocks per GPU launch instead of one frame per call.  Byte sinks/sources stay with the
+ * caller (the Rust shim owns `W: Write + Seek` / `R: Read`): a writer hands out byte ranges to append and, at
+ * finalize, the metadata to rewrite at the stream start; a reader is given the whole file image.
+ *
+ * Handles are not thread-safe (the reference's `&mut self`).  Without a GPU every data call fails with
+ * FLACB200_E_NO_DEVICE; only the metadata helpers (writer header, reader open/info, md5) run on the host alone.
+ */
+#ifndef FLACB200_STREAM_H
+#define FLACB200_STREAM_H
+
+#include "flacb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* flac_codec::encode::Options (src/encode.rs:1363-1408): frame options + the container options */
+typedef struct flacb200_writer_options {
+    flacb200_options frame;
+    int32_t padding;          /* PADDING block size in bytes; < 0 = no padding block (Options::no_padding :1510) */
+    uint32_t seektable_kind;  /* 0 none, 1 every seektable_n seconds, 2 every seektable_n frames (SeekTableInterval :1321) */
+    uint32_t seektable_n;
+    uint32_t launch_frames;   /* blocks buffered per GPU launch; 0 = default (4096) */
+} flacb200_writer_options;
+
+void flacb200_writer_options_default(flacb200_writer_options* o); /* Options::default(): padding 4096, seektable 10 s */
+void flacb200_writer_options_fast(flacb200_writer_options* o);
+void flacb200_writer_options_best(flacb200_writer_options* o);
+
+typedef struct flacb200_writer flacb200_writer;
+
+/* Encoder::new (src/encode.rs:1882).  total_pcm_frames: inter-channel samples expected, 0 = unknown
+ * (the facades' total_bytes / total_samples divided down by the caller; flacb200_total_from_bytes/_samples
+ * reproduce their checks).  engine may be NULL for header-only use. */
+int flacb200_writer_open(flacb200_engine* engine, const flacb200_writer_options* opt, uint32_t sample_rate,
+                         uint32_t bits_per_sample, uint32_t channels, uint64_t total_pcm_frames, flacb200_writer** out);
+void flacb200_writer_close(flacb200_writer* w); /* does NOT finalize (a Rust Drop impl calls finalize first) */
+
+/* FlacByteWriter::new / FlacSampleWriter::new argument checks (src/encode.rs:170-178, :516-521):
+ * 0 and *pcm_frames on success, else SamplesNotDivisibleByChannels / InvalidTotalBytes / InvalidTotalSamples */
+int flacb200_total_from_bytes(uint64_t total_bytes, uint32_t bits_per_sample, uint32_t channels, uint64_t* pcm_frames);
+int flacb200_total_from_samples(uint64_t total_samples, uint32_t channels, uint64_t* pcm_frames);
+
+/* The metadata blocks as they stand now ("fLaC" + STREAMINFO [+ SEEKTABLE] [+ PADDING]): what Encoder::new writes
+ * before the first frame, and after flacb200_writer_finalize what finalize_inner rewrites at the stream start
+ * (same length unless a SEEKTABLE was carved out of the PADDING, in which case it is still the same length).
+ * The pointer stays valid until the next call on the writer. */
+int flacb200_writer_header(flacb200_writer* w, const uint8_t** bytes, size_t* len);
+
+/* FlacByteWriter::write (:347), FlacSampleWriter::write (:560), FlacChannelWriter::write (:832).
+ * Input is copied; whole blocks are encoded whenever launch_frames of them are buffered. */
+int flacb200_writer_write_bytes(flacb200_writer* w, const uint8_t* pcm, size_t n_bytes, int big_endian);
+int flacb200_writer_write_samples(flacb200_writer* w, const int32_t* interleaved, size_t n_samples);
+int flacb200_writer_write_channels(flacb200_writer* w, const int32_t* const* channels, uint32_t n_channels,
+                                   size_t n_per_channel);
+
+/* Frames completed since the last drain, to be appended to the byte sink.  Valid until the next call on w. */
+int flacb200_writer_drain(flacb200_writer* w, const uint8_t** frames, size_t* len);
+/* Encode everything buffered that forms whole blocks now (std::io::Write::flush never emits a partial block). */
+int flacb200_writer_flush(flacb200_writer* w);
+
+/* finalize_inner (:236, :587, :2024): encodes the final short block, checks/updates the sample count
+ * (SampleCountMismatch, NoSamples, ExcessiveTotalSamples), stores the MD5, fills the seek table.  Afterwards
+ * flacb200_writer_drain returns the last frames and flacb200_writer_header the final metadata. */
+int flacb200_writer_finalize(flacb200_writer* w);
+
+typedef struct flacb200_writer_stats {
+    uint64_t pcm_frames_written, frames_written, frame_bytes_written;
+    uint32_t min_frame_size, max_frame_size;
+    uint32_t launches;       /* flacb200_encode calls issued */
+    uint8_t md5[16];
+} flacb200_writer_stats;
+int flacb200_writer_get_stats(flacb200_writer* w, flacb200_writer_stats* s);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+
+/* Streaminfo (src/metadata/mod.rs:1640-1760) + where the frames start */
+typedef struct flacb200_streaminfo {
+    uint16_t min_block_size, max_block_size;
+    uint32_t min_frame_size, max_frame_size;
+    uint32_t sample_rate;
+    uint32_t channels;
+    uint32_t bits_per_sample;
+    uint64_t total_samples;   /* inter-channel samples, 0 = unknown */
+    uint8_t md5[16];
+    uint64_t frames_start;    /* byte offset of the first frame */
+    uint32_t n_seekpoints;
+    uint32_t reserved;
+} flacb200_streaminfo;
+
+/* metadata walk of FlacByteReader::new -> BlockList::read (src/metadata/mod.rs:482-646); host only */
+int flacb200_read_streaminfo(const uint8_t* flac, size_t len, flacb200_streaminfo* si);
+
+typedef struct flacb200_seekpoint {
+    uint64_t sample_offset, byte_offset;
+    uint32_t frame_samples, placeholder;
+} flacb200_seekpoint;
+
+typedef struct flacb200_reader flacb200_reader;
+
+/* FlacByteReader::new / FlacSampleReader::new over a file image that stays valid while the reader lives.
+ * engine may be NULL for metadata-only use. */
+int flacb200_reader_open(flacb200_engine* engine, const uint8_t* flac, size_t len, flacb200_reader** out);
+void flacb200_reader_close(flacb200_reader* r);
+int flacb200_reader_info(flacb200_reader* r, flacb200_streaminfo* si);
+int flacb200_reader_seektable(flacb200_reader* r, flacb200_seekpoint* points, size_t capacity, size_t* n_points);
+
+/* Decodes the whole stream on the GPU at the first call (all frames in one batch), then serves PCM like
+ * FlacSampleReader::read / FlacByteReader::read: up to `capacity` single-channel samples (or bytes) from the
+ * current position, *n_out = how many were delivered (0 at the end of the stream).
+ * pcm_kind: FLACB200_PCM_BYTES_LE / _BE (capacity and *n_out in bytes) or FLACB200_PCM_I32_INTERLEAVED (in samples). */
+int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm_kind, size_t* n_out);
+/* Decoder::seek (src/decode.rs:1452): position in inter-channel samples; beyond the end -> InvalidSeek */
+int flacb200_reader_seek(flacb200_reader* r, uint64_t pcm_frame);
+/* verify (src/decode.rs:1282-1309): decode everything and compare the MD5 of the little-endian PCM with STREAMINFO.
+ * *result: 0 MD5Match, 1 MD5Mismatch, 2 NoMD5 (all-zero sum stored) */
+int flacb200_reader_verify(flacb200_reader* r, int* result, uint8_t md5_out[16]);
+
+/* MD5 as the encoder/verify use it (host); exported for the shim and the tests */
+void flacb200_md5(const uint8_t* data, size_t len, uint8_t out[16]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

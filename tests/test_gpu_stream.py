@@ -1,0 +1,245 @@
+"""GPU parity of the stream-level facades (include/flacb200_stream.h, flac_codec_b200/stream.py): whole .flac
+files written through FlacByteWriter / FlacSampleWriter / FlacChannelWriter must equal the oracle's
+FlacSampleWriter restatement (fo_encode_stream: metadata blocks, seek table, MD5, frames) byte for byte, whatever
+the write granularity and launch size; readers must return the reference fixtures' PCM (MD5 pinned by
+tests/seek.rs:29-31 and STREAMINFO) and reproduce the reference's error behaviour."""
+import hashlib
+import io
+
+import numpy as np
+import pytest
+
+from flacb200_testutil import ref_file, synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fo():
+    from oracle import oracle
+
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def st():
+    from flac_codec_b200 import stream
+
+    return stream
+
+
+def _options(preset, padding="default", seektable="default", block=None):
+    from flac_codec_b200 import Options
+
+    o = Options(preset)
+    if block:
+        o.block_size(block)
+    if padding is None:
+        o.no_padding()
+    elif padding != "default":
+        o.with_padding(padding)
+    if seektable is None:
+        o.no_seektable()
+    elif seektable != "default":
+        (o.seektable_seconds if seektable[0] == "seconds" else o.seektable_frames)(seektable[1])
+    return o
+
+
+def _fo_options(fo, preset, padding="default", seektable="default", block=None):
+    kw = {}
+    if block:
+        kw["block_size"] = block
+    if padding is None:
+        kw["padding"] = -1
+    elif padding != "default":
+        kw["padding"] = padding if padding > 0 else -1     # Options::padding(0) removes the block (src/encode.rs:1493)
+    if seektable is None:
+        kw["seektable_kind"] = 0
+    elif seektable != "default":
+        kw["seektable_kind"] = 1 if seektable[0] == "seconds" else 2
+        kw["seektable_n"] = seektable[1]
+    return fo.options(preset, **kw)
+
+
+CASES = [
+    # preset, rate, bps, ch, n, total_known, padding, seektable, block, launch_frames, write chunk (pcm frames)
+    ("default", 44100, 16, 2, 44100 * 3 + 17, True, "default", "default", None, 0, 10000),
+    ("default", 44100, 16, 2, 44100 * 3 + 17, False, "default", "default", None, 7, 4096),
+    ("best", 48000, 24, 2, 48000 * 2 + 1, True, "default", ("seconds", 1), None, 5, 777),
+    ("best", 48000, 24, 2, 48000 * 2 + 1, False, 64, ("seconds", 1), None, 3, 48000 * 2 + 1),     # padding too small for the table
+    ("fast", 8000, 8, 1, 30000, True, None, ("frames", 3), None, 4, 1),                            # byte-at-a-time style writes
+    ("fast", 8000, 8, 1, 30000, False, None, ("frames", 3), None, 4, 999),                        # no padding, no placeholder: no table
+    ("default", 96000, 24, 8, 96000 // 2 + 5, True, 1000, None, 1024, 2, 5000),
+    ("default", 44100, 16, 2, 4096 * 6, True, "default", ("frames", 2), None, 2, 4096),           # exact multiple of the block size
+    ("best", 192000, 32, 2, 40000, False, "default", ("seconds", 1), 4608, 0, 12345),
+    ("default", 22050, 12, 3, 50000, True, 0, "default", 576, 16, 3333),
+]
+
+
+@pytest.mark.parametrize("preset,rate,bps,ch,n,known,padding,seektable,block,launch,chunk", CASES)
+def test_sample_writer_files_equal_oracle(fo, st, preset, rate, bps, ch, n, known, padding, seektable, block, launch, chunk):
+    x = synth_pcm(1, ch, n, rate, bps).reshape(-1)
+    ref, ref_sizes = fo.encode_stream(_fo_options(fo, preset, padding, seektable, block), rate, bps, ch, x, total_known=known)
+    sink = io.BytesIO()
+    w = st.FlacSampleWriter(sink, _options(preset, padding, seektable, block), rate, bps, ch, x.size if known else None,
+                            launch_frames=launch)
+    for i in range(0, n, chunk):
+        w.write(x[i * ch:(i + chunk) * ch])
+    w.finalize()
+    s = w.stats()
+    w.close()
+    got = sink.getvalue()
+    assert len(got) == len(ref)
+    assert got == ref
+    assert s.frames_written == len(ref_sizes) and s.pcm_frames_written == n
+    B = (bps + 7) // 8
+    assert bytes(s.md5) == hashlib.md5(fo.samples_to_bytes(x, B)).digest()
+    # and the file decodes to the input through the oracle's pinned decoder, MD5 included
+    y, si, md5 = fo.decode_stream(got, want_md5=True)
+    assert np.array_equal(y, x) and bytes(si.md5) == md5
+
+
+@pytest.mark.parametrize("endian", ["little", "big"])
+@pytest.mark.parametrize("bps", [8, 16, 24, 32])
+def test_byte_writer_and_channel_writer(fo, st, endian, bps):
+    rate, ch, n = 32000, 2, 20000
+    x = synth_pcm(2, ch, n, rate, bps)
+    ref, _ = fo.encode_stream(fo.options("default"), rate, bps, ch, x.reshape(-1), total_known=True)
+    B = (bps + 7) // 8
+    raw = fo.samples_to_bytes(x.reshape(-1), B, big_endian=(endian == "big"))
+    sink = io.BytesIO()
+    from flac_codec_b200 import Options
+
+    with st.FlacByteWriter(sink, Options.default(), rate, bps, ch, len(raw), endian=endian, launch_frames=2) as w:
+        for i in range(0, len(raw), 7001):      # splits samples across writes
+            assert w.write(raw[i:i + 7001]) == len(raw[i:i + 7001])
+    assert sink.getvalue() == ref
+    sink = io.BytesIO()
+    with st.FlacChannelWriter(sink, Options.default(), rate, bps, ch, n, launch_frames=3) as w:
+        for i in range(0, n, 2500):
+            w.write([x[i:i + 2500, c] for c in range(ch)])
+    assert sink.getvalue() == ref
+
+
+def test_writer_errors(fo, st):
+    from flac_codec_b200 import Options
+    from flac_codec_b200._abi import FlacB200Error
+
+    x = synth_pcm(0, 2, 10000, 44100, 16).reshape(-1)
+    # more samples than announced: Encoder::encode -> ExcessiveTotalSamples (src/encode.rs:2006-2011)
+    w = st.FlacSampleWriter(io.BytesIO(), Options.default(), 44100, 16, 2, 4096 * 2, launch_frames=64)
+    with pytest.raises(FlacB200Error) as e:
+        w.write(x)
+    assert e.value.code == 57
+    w.close()
+    # fewer: finalize -> SampleCountMismatch (:2080-2084)
+    w = st.FlacSampleWriter(io.BytesIO(), Options.default(), 44100, 16, 2, x.size + 2)
+    w.write(x)
+    with pytest.raises(FlacB200Error) as e:
+        w.finalize()
+    assert e.value.code == 59
+    w.close()
+    # nothing written: NoSamples (:2089)
+    w = st.FlacSampleWriter(io.BytesIO(), Options.default(), 44100, 16, 2, None)
+    with pytest.raises(FlacB200Error) as e:
+        w.finalize()
+    assert e.value.code == 58
+    w.close()
+    with pytest.raises(FlacB200Error) as e:
+        st.FlacSampleWriter(io.BytesIO(), Options.default(), 44100, 16, 2, 7)
+    assert e.value.code == 61
+    w = st.FlacChannelWriter(io.BytesIO(), Options.default(), 44100, 16, 2, None)
+    with pytest.raises(FlacB200Error) as e:
+        w.write([x[:10]])
+    assert e.value.code == 64
+    with pytest.raises(FlacB200Error) as e:
+        w.write([x[:10], x[:9]])
+    assert e.value.code == 65
+    w.close()
+
+
+def test_stream_writer_subset_frames(fo, st):
+    from flac_codec_b200 import Options
+    from flac_codec_b200._abi import FlacB200Error
+
+    sink = io.BytesIO()
+    w = st.FlacStreamWriter(sink, Options.default())
+    x = synth_pcm(3, 2, 3000, 44100, 16)
+    w.write(44100, 2, 16, x[:1000].reshape(-1))
+    w.write_cdda(x[1000:].reshape(-1))
+    ref = b""
+    for k, blk in enumerate((x[:1000], x[1000:])):
+        ref += fo.encode_frame(fo.options("default", block_size=len(blk)), 44100, 16, blk.T, frame_number=k, subset=True)
+    assert sink.getvalue() == ref
+    r = st.FlacStreamReader(sink.getvalue(), 44100, 2, 16)
+    assert np.array_equal(r.read_all(3000).reshape(-1, 2), x)
+    with pytest.raises(FlacB200Error) as e:
+        w.write(44100, 2, 17, x[:10].reshape(-1))     # NonSubsetBitsPerSample (:1134)
+    assert e.value.code == 28
+    with pytest.raises(FlacB200Error) as e:
+        w.write(44100, 2, 16, x.reshape(-1)[:11])     # SamplesNotDivisibleByChannels (:1108)
+    assert e.value.code == 61
+
+
+@pytest.mark.parametrize("name,md5", [("sine.flac", "831671b807f97051301e01d68b5c54b3"), ("all-frames.flac", None),
+                                      ("cuesheet.flac", None), ("seektable.flac", None)])
+def test_readers_on_reference_fixtures(fo, st, name, md5):
+    flac = ref_file(name)
+    y, si, oracle_md5 = fo.decode_stream(flac, want_md5=True)
+    r = st.FlacSampleReader(io.BytesIO(flac))
+    assert (r.channel_count(), r.sample_rate(), r.bits_per_sample(), r.total_samples()) == (si.channels, si.sample_rate, si.bps,
+                                                                                             si.total_samples or None)
+    got = r.read_to_end()
+    assert np.array_equal(got, y)
+    status, sum_ = r.verify()
+    assert sum_ == oracle_md5
+    if md5:
+        assert sum_.hex() == md5
+    assert status == ("MD5Match" if any(bytes(si.md5)) else "NoMD5")
+    # seek (tests/seek.rs): position in inter-channel samples, then the same samples as the full decode
+    total = len(y) // si.channels
+    for pos in (0, 1, total // 3, total - 1, total):
+        r.seek(pos)
+        a = r.read(4096)
+        assert np.array_equal(a, y[pos * si.channels:pos * si.channels + 4096])
+    from flac_codec_b200._abi import FlacB200Error
+
+    with pytest.raises(FlacB200Error) as e:
+        r.seek(total + 1)
+    assert e.value.code == 37     # InvalidSeek
+    r.close()
+    B = (si.bps + 7) // 8
+    for endian in ("little", "big"):
+        rb = st.FlacByteReader(flac, endian=endian)
+        assert rb.read() == fo.samples_to_bytes(y, B, big_endian=(endian == "big"))
+        assert rb.decoded_len() == (len(y) * B if si.total_samples else None)
+        rb.close()
+    assert st.verify(flac) == ("MD5Match" if any(bytes(si.md5)) else "NoMD5")
+
+
+def test_reader_surfaces_corruption_after_the_good_frames(fo, st):
+    from flac_codec_b200 import Options
+    from flac_codec_b200._abi import FlacB200Error
+
+    x = synth_pcm(5, 2, 4096 * 6, 44100, 16).reshape(-1)
+    flac, sizes = fo.encode_stream(fo.options("default"), 44100, 16, 2, x, total_known=True)
+    si = fo.read_streaminfo(flac)
+    bad = bytearray(flac)
+    bad[si.frames_start + int(sizes[:3].sum()) + int(sizes[3]) // 2] ^= 0x10     # inside frame 3
+    r = st.FlacSampleReader(bytes(bad))
+    got = []
+    with pytest.raises(FlacB200Error) as e:
+        while True:
+            a = r.read(5000)
+            if a.size == 0:
+                break
+            got.append(a.copy())
+    assert e.value.code in (39, 40)     # Crc8Mismatch / Crc16Mismatch, as the oracle reports
+    assert np.array_equal(np.concatenate(got), x[:3 * 4096 * 2])
+    with pytest.raises(FlacB200Error):
+        r.verify()
+    r.close()
+    # a different MD5 in STREAMINFO: Verified::MD5Mismatch
+    wrong = bytearray(flac)
+    wrong[4 + 4 + 18] ^= 0xFF
+    assert st.verify(bytes(wrong)) == "MD5Mismatch"
