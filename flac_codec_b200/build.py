@@ -53,8 +53,8 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + HEADERS
-    return any(os.path.getmtime(d) > t for d in deps)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + HEADERS + [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))]
+    return any(os.path.getmtime(d) > t for d in deps) or not os.path.exists(os.path.join(HERE, "..", "build", "flacb200_wav2flac"))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -74,7 +74,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(compile_one, todo))
     link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", *_ccbin(), "-shared", "-o", LIB] + [_obj(s) for s in SOURCES]
     subprocess.check_call(link, cwd=CSRC)
+    build_host_tools()
     return LIB
+
+
+HOST = os.path.join(HERE, "host")
+WAV2FLAC = os.path.join(HERE, "..", "build", "flacb200_wav2flac")
+
+
+def build_host_tools() -> str:
+    """The C++ host layer above the C ABI: flacb200.hpp facades + the wav2flac/flac2wav front end."""
+    os.makedirs(os.path.dirname(WAV2FLAC), exist_ok=True)
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-std=c++17", "-O2", "-Wall", "-o", WAV2FLAC, os.path.join(HOST, "wav2flac.cpp"), "-L" + HERE,
+                           "-lflacb200", "-Wl,-rpath,$ORIGIN/../flac_codec_b200"])
+    return WAV2FLAC
 
 
 if __name__ == "__main__":

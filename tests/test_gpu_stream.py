@@ -243,3 +243,25 @@ def test_reader_surfaces_corruption_after_the_good_frames(fo, st):
     wrong = bytearray(flac)
     wrong[4 + 4 + 18] ^= 0xFF
     assert st.verify(bytes(wrong)) == "MD5Mismatch"
+
+
+def test_cpp_host_front_end_wav2flac_roundtrip(fo, tmp_path):
+    """The C++ facades (flac_codec_b200/host/flacb200.hpp) through the wav2flac/flac2wav front end
+    (examples/wav2flac.rs, examples/flac2wav.rs): file equals the oracle's FlacByteWriter restatement; WAV survives."""
+    import struct
+    import subprocess
+
+    from flac_codec_b200 import build
+
+    exe = build.build_host_tools()
+    rate, bps, ch, n = 44100, 16, 2, 44100 * 2 + 123
+    x = synth_pcm(7, ch, n, rate, bps).reshape(-1)
+    raw = fo.samples_to_bytes(x, 2)
+    wav = (b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, ch, rate, rate * ch * 2, ch * 2, bps)
+           + b"data" + struct.pack("<I", len(raw)) + raw)
+    (tmp_path / "in.wav").write_bytes(wav)
+    subprocess.check_call([exe, "encode", str(tmp_path / "in.wav"), str(tmp_path / "out.flac")])
+    ref, _ = fo.encode_stream(fo.options("default"), rate, bps, ch, x, total_known=True)
+    assert (tmp_path / "out.flac").read_bytes() == ref
+    subprocess.check_call([exe, "decode", str(tmp_path / "out.flac"), str(tmp_path / "back.wav")])
+    assert (tmp_path / "back.wav").read_bytes() == wav
