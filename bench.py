@@ -143,6 +143,27 @@ def cpu_encode_rate(pcm_i32_tracks, cores, target_seconds):
     return done / t_total / 1e6, f"{done // CH} PCM frames ({done / CH / RATE:.1f} s of audio) from {ntr} track(s) of the same workload"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` at this workload's launch-group size, from the
+    newest committed `ncu --set full` summary under profiles/ (bytes), or None."""
+    import csv
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full_summary.csv")), reverse=True):
+        try:
+            with open(path, newline="") as f:
+                rows = list(csv.reader(f))
+            hdr, units = rows[0], rows[1]
+            ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if kernel.split("+")[0] in r[ik]:
+                    return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+        except (OSError, ValueError, KeyError, IndexError):
+            continue
+    return None
+
+
 def host_tracks_numpy(n_tracks, seconds):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from flacb200_testutil import synth_pcm
@@ -263,7 +284,8 @@ def run_gpu(args):
     value = samples_per_step * world / (ms_per_step * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel: algorithmic bytes of one launch / its average duration ----
-    names = ["k_planes", "k_lpc", "k_residual", "k_decide+k_scan+k_zero", "k_pack+k_crc16"]
+    # the C4 shape runs the register-tiled kernels (encode_fast.inl); slot 0 (k_planes) is only used by the generic path
+    names = ["k_planes", "k_lpc2", "k_analyze", "k_decide+k_scan+k_zero", "k_pack2+k_crc16w"]
     top = int(np.argmax(kernel_ms[:5]))
     peaks = {}
     try:
@@ -279,7 +301,7 @@ def run_gpu(args):
     achieved = alg_bytes_launch / (avg_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        "traffic": ncu_traffic(names[top]), "algorithmic_bytes_per_launch": alg_bytes_launch, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
         "algorithmic_bytes_per_sample": alg_bytes_step / samples_per_step,
         "kernel_share_of_step": {names[k]: kernel_ms[k] / max(kernel_ms[:5].sum(), 1e-9) for k in range(5)},
         "kernel_ms_per_step": {names[k]: kernel_ms[k] / args.steps for k in range(5)},

@@ -1,0 +1,382 @@
+// encode_frame.cu -- k_pack3: one CTA assembles one whole frame in shared memory (same shapes as the other
+// register-tiled kernels: block <= 4096 samples, samples <= 28 bits, LPC order <= 16).
+//
+// Bit emission of encode_frame (src/encode.rs:2282-2436): frame header, then per subframe the header, warm-up samples,
+// LPC parameters and the partitioned Rice residual block (:2982-3136, :3834-3863, :3944-3961), zero padding to a byte,
+// CRC-16 (src/crc.rs:144-188).  One WARP per subframe: in round r lane l owns the 16-sample tile 32 r + l (history of the
+// fixed differences / the FIR comes from the left neighbour by shuffle, as in k_analyze), computes its residuals and code
+// lengths, a warp scan turns the lengths into bit positions, and every code is OR-ed into the frame image with one or two
+// shared-memory atomics -- no per-thread word state machine, no divergent flushes.  The finished image is CRC-ed by the
+// same warps (ranges of words, combined with x^(8 len) mod P) and copied out with coalesced 32-bit stores; only the up to
+// three bytes at either end that share a word with the neighbouring frames are stored bytewise.  Nothing else writes the
+// output, so it needs neither zeroing (k_zero) nor atomics, and no separate CRC kernel.
+
+#include "common.cuh"
+#include "crc.cuh"
+#include "tiles.cuh"
+
+namespace flacb200 {
+
+bool analyze_fast_ok(const EncCfg& cfg);   // encode_kernels.cu
+
+__device__ Crc16Tables g_crc16_tabs;   // built once per device by k_crc16_tables_init
+
+__global__ void k_crc16_tables_init()
+{
+    crc16_tables_init(g_crc16_tabs);
+}
+
+// OR the low nbits (1..32) of v into the big-endian bit image `words` at bit position pos
+__device__ inline void p3_put(uint32_t* words, uint32_t pos, uint32_t nbits, uint32_t v)
+{
+    const uint32_t w = pos >> 5, off = pos & 31;
+    const unsigned long long wide = ((unsigned long long)v) << (64u - nbits - off);
+    const uint32_t hi = (uint32_t)(wide >> 32), lo = (uint32_t)wide;
+    if (hi) atomicOr(words + w, hi);
+    if (lo) atomicOr(words + w + 1, lo);
+}
+
+__device__ inline void p3_put_masked(uint32_t* words, uint32_t pos, uint32_t nbits, uint32_t v)
+{
+    if (nbits == 0) return;
+    if (nbits < 32) v &= (1u << nbits) - 1u;
+    p3_put(words, pos, nbits, v);
+}
+
+// CRC-16 of the message bytes held in words[w0 .. w0 + nw) (big-endian words: the first message byte is the top byte).
+// One warp, all lanes call and get the result.
+__device__ inline uint32_t p3_crc_words(const Crc16Tables& t, const uint32_t* words, uint32_t w0, uint32_t nw)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t acc = 0, last = 0;
+    bool any = false;
+    for (uint32_t i = lane; i < nw; i += 32) {
+        const uint32_t v = words[w0 + i];
+        uint32_t f = t.byte_tab[v >> 24];
+        f = crc16_byte(t, f, (v >> 16) & 0xff);
+        f = crc16_byte(t, f, (v >> 8) & 0xff);
+        f = crc16_byte(t, f, v & 0xff);
+        acc = (t.mul_hi[acc >> 8] ^ t.mul_lo[acc & 0xff]) ^ f;   // acc * x^1024 + F(word): 32 words lie between two words of a lane
+        last = i;
+        any = true;
+    }
+    uint32_t part = any ? gf16_mulmod(acc, t.xd[nw - 1 - last]) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
+    return part & 0xffffu;
+}
+
+struct P3Smem {
+    Crc16Tables tabs;
+    uint32_t crc_part[MAX_CH];
+    FrameRec fr;
+    CandRec cr[MAX_CH];
+};
+
+// the residual block of one FIXED / LPC subframe; pos = bit position of the first residual partition header
+template <int HB, bool STEREO>
+__device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const uint8_t* __restrict__ pcm, uint32_t slot, const CandRec& cr,
+                                    uint32_t* words, uint32_t pos)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = d.n, wasted = cr.wasted, order = cr.order, shift = cr.shift;
+    const bool lpc = cr.type == 3;
+    const uint32_t rounds = ((n + 15) / 16 + 31) / 32;
+    const uint32_t cp = n >> cr.porder_g;                      // samples per partition (the first one holds cp - order residuals)
+    const uint32_t j0 = (1u << cr.porder_g) - cr.nparts;
+    const bool cp16 = (cp & 15u) == 0;
+    const uint32_t hb = cr.method ? 5u : 4u, escape_code = cr.method ? 31u : 15u;
+    int32_t q[HB];
+#pragma unroll
+    for (int j = 0; j < HB; j++) q[j] = (lpc && (uint32_t)j < order) ? (int32_t)cr.q[j] : 0;
+    int32_t carry[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) carry[e] = 0;
+    uint32_t base = pos;
+    for (uint32_t rd = 0; rd < rounds; rd++) {
+        const uint32_t i0 = (rd * 32 + lane) * 16;
+        const bool live = i0 < n;
+        int32_t x[16], h[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = 0;
+        if (live) aw_load_tile<STEREO>(cfg, d, pcm, slot, i0, x);
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            x[e] >>= wasted;   // :2891
+            const int32_t up = __shfl_up_sync(0xffffffffu, x[e], 1);
+            h[e] = lane == 0 ? carry[e] : up;
+            carry[e] = __shfl_sync(0xffffffffu, x[e], 31);
+        }
+        int32_t r[16];
+        if (lpc) {   // LpcSubframeParameters::encode_residuals (:3174-3203)
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                long long sum = 0;
+#pragma unroll
+                for (int j = 0; j < HB; j++) sum = mad_wide_s32(e - 1 - j >= 0 ? x[e - 1 - j >= 0 ? e - 1 - j : 0] : h[16 + e - 1 - j >= 0 ? 16 + e - 1 - j : 0], q[j], sum);
+                r[e] = (int32_t)((uint32_t)x[e] - (uint32_t)(unsigned long long)(sum >> shift));
+            }
+        } else {     // fixed differences (:3039-3060)
+            int32_t x1 = h[15], x2 = h[14], x3 = h[13], x4 = h[12];
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int32_t x0 = x[e];
+                r[e] = order == 0 ? x0 : order == 1 ? x0 - x1 : order == 2 ? x0 - 2 * x1 + x2 : order == 3 ? x0 - 3 * x1 + 3 * x2 - x3
+                                                                                                           : x0 - 4 * x1 + 6 * x2 - 4 * x3 + x4;
+                x4 = x3; x3 = x2; x2 = x1; x1 = x0;
+            }
+        }
+        // ---- code lengths of this lane's tile ----
+        const uint32_t lo_i = max(i0, order), hi_i = min(i0 + 16u, n);   // residuals exist for [lo_i, hi_i)
+        const uint32_t pj = live ? i0 / cp : 0u;
+        const bool uniform = live && i0 >= order && i0 + 16 <= n && (cp16 || (i0 + 15) / cp == pj);
+        const uint32_t cc0 = cr.rice[live ? min(pj - j0, (uint32_t)MAX_PARTS - 1) : 0u];
+        uint32_t tsum = 0;
+        uint32_t len[16];
+        if (uniform && cc0 < 0x40) {   // the common tile: one Rice parameter for all 16 residuals (:3845-3851)
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                len[e] = (zigzag32(r[e]) >> cc0) + 1u + cc0;
+                tsum += len[e];
+            }
+            if (i0 == max(pj * cp, order)) tsum += hb;   // ResidualPartitionHeader (src/stream.rs:1603-1619) rides in front
+        } else if (live) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const uint32_t i = i0 + e;
+                uint32_t l = 0;
+                if (i >= lo_i && i < hi_i) {
+                    const uint32_t p = i / cp;
+                    const uint32_t cc = cr.rice[p - j0];
+                    if (cc < 0x40) l = (zigzag32(r[e]) >> cc) + 1u + cc;
+                    else if (cc & 0x40) l = cc & 31u;
+                    if (i == max(p * cp, order)) l += (cc < 0x40) ? hb : hb + 5u;
+                }
+                len[e] = l;
+                tsum += l;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) len[e] = 0;
+        }
+        // ---- bit positions: exclusive scan over the lanes, running base over the rounds ----
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        uint32_t p = base + incl - tsum;
+        base += __shfl_sync(0xffffffffu, incl, 31);
+        // ---- emission ----
+        if (uniform && cc0 < 0x40) {
+            if (i0 == max(pj * cp, order)) {
+                p3_put(words, p, hb, cc0);
+                p += hb;
+            }
+            const uint32_t stop = 1u << cc0, mask = stop - 1u;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const uint32_t u = zigzag32(r[e]);
+                p3_put(words, p + (u >> cc0), cc0 + 1u, stop | (u & mask));   // unary zeros, stop bit, cc0 LSBs
+                p += len[e];
+            }
+        } else if (live) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const uint32_t i = i0 + e;
+                if (i < lo_i || i >= hi_i) continue;
+                const uint32_t pi = i / cp;
+                const uint32_t cc = cr.rice[pi - j0];
+                uint32_t at = p;
+                if (i == max(pi * cp, order)) {
+                    if (cc < 0x40) { p3_put(words, at, hb, cc); at += hb; }
+                    else { p3_put(words, at, hb, escape_code); p3_put_masked(words, at + hb, 5, (cc & 0x40) ? (cc & 31u) : 0u); at += hb + 5; }
+                }
+                if (cc < 0x40) {
+                    const uint32_t u = zigzag32(r[e]);
+                    p3_put(words, at + (u >> cc), cc + 1u, (1u << cc) | (u & ((1u << cc) - 1u)));
+                } else if (cc & 0x40) {
+                    p3_put_masked(words, at, cc & 31u, (uint32_t)r[e]);   // escaped: raw two's complement (:3857)
+                }
+                p += len[e];
+            }
+        }
+    }
+}
+
+// grid = frames of the launch group; block = 32 * (subframes per frame); dynamic smem = image words
+template <int HB, bool STEREO>
+__global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
+                                              const CandRec* __restrict__ cands, const FrameRec* __restrict__ frecs, uint8_t* __restrict__ out)
+{
+    extern __shared__ __align__(16) uint32_t p3_words[];
+    __shared__ P3Smem sm;
+    const uint32_t f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+    // ---- stage the frame record, its subframes' candidate records and the CRC tables; clear the image ----
+    for (uint32_t i = tid; i < sizeof(FrameRec) / 4; i += nthreads) reinterpret_cast<uint32_t*>(&sm.fr)[i] = reinterpret_cast<const uint32_t*>(frecs + f)[i];
+    for (uint32_t i = tid; i < sizeof(Crc16Tables) / 4; i += nthreads)
+        reinterpret_cast<uint32_t*>(&sm.tabs)[i] = reinterpret_cast<const uint32_t*>(&g_crc16_tabs)[i];
+    __syncthreads();
+    const FrameRec& fr = sm.fr;
+    const uint32_t nsub = fr.nsub;
+    const uint32_t frame_bytes = fr.frame_bytes;
+    const uint32_t img_words = min((frame_bytes + 3) / 4 + 2, cap_words);
+    for (uint32_t i = tid; i < img_words; i += nthreads) p3_words[i] = 0;
+    for (uint32_t c = wid; c < nsub; c += nwarps) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(cands + (size_t)f * cfg.nslots + fr.slot[c]);
+        for (uint32_t i = lane; i < sizeof(CandRec) / 4; i += 32) reinterpret_cast<uint32_t*>(&sm.cr[c])[i] = src[i];
+    }
+    __syncthreads();
+    if (fr.err || (frame_bytes + 3) / 4 + 2 > cap_words) return;   // k_scan has already raised the sticky error word
+    const FrameDesc d = descs[f];
+    const uint32_t n = d.n;
+    // ---- frame header (src/stream.rs:242-276; bytes prepared by k_decide) ----
+    if (tid < fr.hdr_len) p3_put(p3_words, 8 * tid, 8, fr.hdr[tid]);
+    // ---- subframes: one warp each ----
+    for (uint32_t c = wid; c < nsub; c += nwarps) {
+        const CandRec& cr = sm.cr[c];
+        const uint32_t slot = fr.slot[c];
+        const uint32_t wasted = cr.wasted, bps = cr.bps, type = cr.type, order = type >= 2 ? cr.order : 0u;
+        uint32_t pos = fr.sub_bit[c];
+        if (lane == 0) {   // SubframeHeader (src/stream.rs:1397-1413): pad, 6-bit type, wasted flag, unary(wasted - 1)
+            const uint32_t code = type == 0 ? 0u : type == 1 ? 1u : type == 2 ? 8u + order : 31u + order;
+            p3_put_masked(p3_words, pos, 8, (code << 1) | (wasted ? 1u : 0u));
+            if (wasted) p3_put(p3_words, pos + 8 + (wasted - 1), 1, 1);
+        }
+        pos += 8 + wasted;
+        if (type == 0) {   // CONSTANT (:2982-2998): the first sample
+            if (lane == 0) {
+                int32_t x[16];
+                aw_load_tile<STEREO>(cfg, d, pcm, slot, 0, x);
+                p3_put_masked(p3_words, pos, bps, (uint32_t)(x[0] >> wasted));
+            }
+            continue;
+        }
+        if (type == 1) {   // VERBATIM (:3000-3018)
+            for (uint32_t i0 = lane * 16; i0 < n; i0 += 32 * 16) {
+                int32_t x[16];
+                aw_load_tile<STEREO>(cfg, d, pcm, slot, i0, x);
+#pragma unroll
+                for (int e = 0; e < 16; e++)
+                    if (i0 + e < n) p3_put_masked(p3_words, pos + (i0 + e) * bps, bps, (uint32_t)(x[e] >> wasted));
+            }
+            continue;
+        }
+        if (lane == 0) {   // warm-up samples (:3083, :3118); order <= 16 = one tile
+            int32_t x[16];
+            aw_load_tile<STEREO>(cfg, d, pcm, slot, 0, x);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                if ((uint32_t)e < order) p3_put_masked(p3_words, pos + e * bps, bps, (uint32_t)(x[e] >> wasted));
+        }
+        pos += order * bps;
+        if (type == 3) {   // :3122-3133
+            const uint32_t prec = cr.precision;
+            if (lane == 0) {
+                p3_put_masked(p3_words, pos, 4, prec - 1);
+                p3_put_masked(p3_words, pos + 4, 5, cr.shift);
+            }
+            if (lane < order) p3_put_masked(p3_words, pos + 9 + lane * prec, prec, (uint32_t)(int32_t)cr.q[lane]);
+            pos += 9 + order * prec;
+        }
+        if (lane == 0) {   // residual block header (:3944-3961)
+            p3_put_masked(p3_words, pos, 2, cr.method);
+            p3_put_masked(p3_words, pos + 2, 4, cr.porder_w);
+        }
+        pos += 6;
+        p3_residuals<HB, STEREO>(cfg, d, pcm, slot, cr, p3_words, pos);
+    }
+    __syncthreads();
+    // ---- CRC-16 over everything but the last two bytes (src/encode.rs:2408-2409) ----
+    const uint32_t body = frame_bytes - 2;
+    const uint32_t bw = body >> 2, btail = body & 3;
+    {
+        // warp w takes words [w * per, (w + 1) * per), per a multiple of 32
+        const uint32_t per = (((bw + nwarps - 1) / nwarps) + 31u) & ~31u;
+        const uint32_t a = min(wid * per, bw), b = min(a + per, bw);
+        const uint32_t part = p3_crc_words(sm.tabs, p3_words, a, b - a);
+        if (lane == 0) sm.crc_part[wid] = part;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t crc = 0;
+            for (uint32_t w = 0; w < nwarps; w++) {
+                const uint32_t wa = min(w * per, bw), wb = min(wa + per, bw);
+                if (wb > wa) crc = gf16_mulmod(crc, gf16_xpow8((wb - wa) * 4)) ^ sm.crc_part[w];
+            }
+            for (uint32_t t = 0; t < btail; t++) crc = crc16_byte(sm.tabs, crc, (p3_words[bw] >> (24 - 8 * t)) & 0xff);
+            p3_put(p3_words, body * 8, 16, crc);
+        }
+        __syncthreads();
+    }
+    // ---- copy out ----
+    const unsigned long long o = fr.out_off;
+    const unsigned long long A = (o + 3) & ~3ull, B = (o + frame_bytes) & ~3ull;
+    auto frame_byte = [&](uint32_t b) -> uint8_t { return (uint8_t)(p3_words[b >> 2] >> (24 - 8 * (b & 3))); };
+    if (A >= B) {
+        for (uint32_t b = tid; b < frame_bytes; b += nthreads) out[o + b] = frame_byte(b);
+        return;
+    }
+    const uint32_t head = (uint32_t)(A - o), tail0 = (uint32_t)(B - o);
+    if (tid < head) out[o + tid] = frame_byte(tid);
+    if (tid < frame_bytes - tail0) out[B + tid] = frame_byte(tail0 + tid);
+    uint32_t* gw = reinterpret_cast<uint32_t*>(out + A);
+    const uint32_t nfull = (uint32_t)((B - A) >> 2);
+    const uint32_t sh = head & 3;   // frame byte index of the first full word (mod 4)
+    for (uint32_t j = tid; j < nfull; j += nthreads) {
+        const uint32_t b = head + 4 * j, idx = b >> 2;
+        const uint32_t be = sh ? __funnelshift_l(p3_words[idx + 1], p3_words[idx], 8 * sh) : p3_words[idx];
+        gw[j] = __byte_perm(be, 0, 0x0123);
+    }
+}
+
+uint32_t pack3_cap_words(const EncCfg& cfg)
+{
+    const uint32_t nsub = cfg.mode == MODE_INDEPENDENT ? cfg.channels : 2;
+    // header <= 16 bytes; a subframe is never larger than VERBATIM + 1 bit (8 + wasted + n * bps bits, src/encode.rs:2971); CRC-16
+    const size_t bits = 16 * 8 + (size_t)nsub * (40 + (size_t)cfg.block_size * (cfg.bps + 1)) + 16;
+    return (uint32_t)((bits + 31) / 32 + 4);
+}
+
+bool pack3_ok(const EncCfg& cfg) { return analyze_fast_ok(cfg) && (size_t)pack3_cap_words(cfg) * 4 <= 200 * 1024; }
+
+cudaError_t launch_pack3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const CandRec* cands, const FrameRec* frecs, uint8_t* out,
+                         cudaStream_t st)
+{
+    const uint32_t nsub = cfg.mode == MODE_INDEPENDENT ? cfg.channels : 2;
+    const uint32_t cap_words = pack3_cap_words(cfg);
+    const size_t smem = (size_t)cap_words * 4;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool ready[64] = {};
+    if (dev >= 0 && dev < 64 && !ready[dev]) {
+        k_crc16_tables_init<<<1, 256, 0, st>>>();
+        ready[dev] = true;
+    }
+    const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
+#define FLACB200_P3(HBV, ST)                                                                                                         \
+    do {                                                                                                                             \
+        cudaError_t e_ = cudaFuncSetAttribute(k_pack3<HBV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);            \
+        if (e_ != cudaSuccess) return e_;                                                                                            \
+        k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, smem, st>>>(cfg, cap_words, descs, pcm, cands, frecs, out);                       \
+    } while (0)
+    if (cfg.mode != MODE_INDEPENDENT) {
+        switch (hb) {
+        case 1: FLACB200_P3(4, true); break;
+        case 2: FLACB200_P3(8, true); break;
+        case 3: FLACB200_P3(12, true); break;
+        default: FLACB200_P3(16, true); break;
+        }
+    } else {
+        switch (hb) {
+        case 1: FLACB200_P3(4, false); break;
+        case 2: FLACB200_P3(8, false); break;
+        case 3: FLACB200_P3(12, false); break;
+        default: FLACB200_P3(16, false); break;
+        }
+    }
+#undef FLACB200_P3
+    return cudaGetLastError();
+}
+
+}   // namespace flacb200

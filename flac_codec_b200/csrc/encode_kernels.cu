@@ -19,38 +19,9 @@
 
 #include "common.cuh"
 #include "crc.cuh"
+#include "tiles.cuh"
 
 namespace flacb200 {
-
-// ------------------------------------------------------------------------------------------------
-// PCM load: Frame::fill_from_buf / fill_from_samples / fill_from_channels  (src/audio.rs:149-225)
-// ------------------------------------------------------------------------------------------------
-__device__ inline int32_t load_pcm_sample(const uint8_t* __restrict__ pcm, const EncCfg& c, unsigned long long idx, uint32_t ch)
-{
-    switch (c.pcm_kind) {
-    case 2: return reinterpret_cast<const int32_t*>(pcm)[idx * c.channels + ch];
-    case 3: return reinterpret_cast<const int32_t*>(pcm)[(unsigned long long)ch * c.planar_stride + idx];
-    default: break;
-    }
-    const uint8_t* p = pcm + (idx * c.channels + ch) * c.bytes_per_sample;
-    uint32_t v;
-    switch (c.bytes_per_sample) {
-    case 1: return (int32_t)(int8_t)p[0];
-    case 2: {
-        uint32_t raw = *reinterpret_cast<const uint16_t*>(p);
-        if (c.pcm_kind == 1) raw = ((raw & 0xff) << 8) | (raw >> 8);
-        return (int32_t)(int16_t)raw;
-    }
-    case 3:
-        v = c.pcm_kind == 1 ? ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | p[2]
-                            : ((uint32_t)p[2] << 16) | ((uint32_t)p[1] << 8) | p[0];
-        return (int32_t)(v << 8) >> 8;
-    default:
-        v = c.pcm_kind == 1 ? ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]
-                            : ((uint32_t)p[3] << 24) | ((uint32_t)p[2] << 16) | ((uint32_t)p[1] << 8) | p[0];
-        return (int32_t)v;
-    }
-}
 
 // grid (ceil(block_size / 256), F), block 256
 __global__ void __launch_bounds__(256) k_planes(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
@@ -1049,11 +1020,11 @@ cudaError_t launch_residual(const EncCfg& cfg, const FrameDesc* descs, const int
 
 void launch_decide_scan(const EncCfg& cfg, const FrameDesc* descs, const CandRec* cands, const unsigned long long* abssum,
                         FrameRec* frecs, uint32_t* frame_bytes_out, unsigned long long* totals, unsigned long long* mapped_total, uint8_t* out,
-                        cudaStream_t st)
+                        bool zero_output, cudaStream_t st)
 {
     k_decide<<<(cfg.nframes + 127) / 128, 128, 0, st>>>(cfg, descs, cands, abssum, frecs);
     k_scan<<<1, 1024, 0, st>>>(cfg.nframes, frecs, frame_bytes_out, totals, mapped_total);
-    k_zero<<<148 * 4, 256, 0, st>>>(out, totals);
+    if (zero_output) k_zero<<<148 * 4, 256, 0, st>>>(out, totals);   // the OR-ing packers need it; k_pack3 writes whole frames
 }
 
 uint32_t pack_cap_words(const EncCfg& cfg) { return (uint32_t)(((size_t)cfg.bpad * (cfg.bps + 1) + 512) / 32 + 8); }

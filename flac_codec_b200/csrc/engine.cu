@@ -24,7 +24,9 @@ bool residual_uses_smem(const EncCfg&);
 cudaError_t launch_residual(const EncCfg&, const FrameDesc*, const int32_t*, const uint32_t*, const unsigned long long*, const LpcRec*, CandRec*,
                             int32_t*, cudaStream_t);
 void launch_decide_scan(const EncCfg&, const FrameDesc*, const CandRec*, const unsigned long long*, FrameRec*, uint32_t*, unsigned long long*,
-                        unsigned long long*, uint8_t*, cudaStream_t);
+                        unsigned long long*, uint8_t*, bool, cudaStream_t);
+bool pack3_ok(const EncCfg&);
+cudaError_t launch_pack3(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 bool analyze_fast_ok(const EncCfg&);
 cudaError_t launch_pack2_crc(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
@@ -390,6 +392,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     const bool fast_analyze = analyze_fast_ok(cfg) && !(legacy & 1u);
     const bool fast_lpc = cfg.max_lpc_order >= 1 && !(legacy & 2u);
     const bool fast_pack = analyze_fast_ok(cfg) && !(legacy & 4u);
+    const bool frame_pack = fast_pack && pack3_ok(cfg) && !(legacy & 8u);   // k_pack3: whole frames, CRC fused, no pre-zeroed output
     const bool need_planes = !(fast_analyze && fast_pack && (fast_lpc || cfg.max_lpc_order == 0));
     // launch group: without the int32 planes a group costs ~250 bytes per candidate, so it can be large enough to fill
     // the GPU even for the warp-per-8-candidates LPC kernel; with planes it is sized to stay near the L2 capacity
@@ -498,9 +501,10 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
                                (int32_t*)e->scratch.p, st));
         time_mark(e, eb + 3);
         launch_decide_scan(c, dd, (const CandRec*)e->cands.p, d_abssum, (FrameRec*)e->frecs.p, (uint32_t*)e->fbytes.p + base,
-                           (unsigned long long*)e->totals.p, pipe_out ? e->d_h_totals + nchunks : nullptr, d_out, st);
+                           (unsigned long long*)e->totals.p, pipe_out ? e->d_h_totals + nchunks : nullptr, d_out, !frame_pack, st);
         time_mark(e, eb + 4);
-        if (fast_pack) CK(launch_pack2_crc(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
+        if (frame_pack) CK(launch_pack3(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
+        else if (fast_pack) CK(launch_pack2_crc(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
         else CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
         time_mark(e, eb + 5);
         if (pipe_out) {
@@ -519,7 +523,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
             }
         }
         nchunks++;
-        launches += (need_planes ? 1u : 0u) + 7u;
+        launches += (need_planes ? 1u : 0u) + (frame_pack ? 5u : 7u);
         if (keep) {
             CK(cudaMemcpyAsync(e->info_cands.data() + base * cfg.nslots, e->cands.p, (size_t)c.nframes * cfg.nslots * sizeof(CandRec),
                                cudaMemcpyDeviceToHost, st));
@@ -559,7 +563,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
     e->tm.launches = launches;
     if (e->profiling) {
-        static const uint32_t per_chunk[5] = {1, 1, 1, 3, 2};   // planes, lpc, residual, decide+scan+zero, pack+crc16
+        const uint32_t per_chunk[5] = {need_planes ? 1u : 0u, 1, 1, frame_pack ? 2u : 3u, frame_pack ? 1u : 2u};   // planes, lpc, analyze, decide+scan(+zero), pack(+crc16)
         for (size_t ck = 0; ck < nchunks; ck++)
             for (int k = 0; k < 5; k++) {
                 float ms = 0;
