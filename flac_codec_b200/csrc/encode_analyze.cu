@@ -1,0 +1,557 @@
+// encode_analyze.cu -- k_analyze3: encode_subframe (src/encode.rs:2849-2980) without emitting bits, ONE CTA PER FRAME.
+//
+// The candidates of a frame (stereo: L, R, M = (L + R) >> 1, S = L - R; otherwise two channels per CTA) share one
+// unpacking of the packed PCM: the CTA writes the two source channels once into shared memory as int32 planes in a
+// tile-transposed layout (tile = 16 samples; chunk c of tile t sits at ((t / 32) * 4 + c) * 128 + (t % 32) * 4 words,
+// so that the 128-bit loads of 32 lanes that own 32 consecutive tiles are conflict free) and every candidate reads
+// its tiles AND their history from there -- no per-candidate unpacking, no shuffles.
+//
+// Two warps work on one candidate (alternating rounds of 32 tiles) and meet on a named barrier:
+//   pass 1: |residual| sums of the fixed orders 0..4 and of the LPC residual per finest Rice partition (24-bit limbs,
+//           shared-memory atomics), the OR mask (wasted bits), checked_sub overflow; the LPC residuals are parked in
+//           shared memory as int16 (flag if one does not fit)
+//   then  : fixed order (:3062-3075), partition trees, Partition::new for every (order, partition), first-minimum
+//           partition order (:3865-3942) -- by the candidate's first warp
+//   pass 2: exact Rice bit counts (what Partition::to_writer will emit, :3834-3863): the fixed residual is rebuilt from
+//           the planes (<= 4 subtractions), the LPC residual is read back from the int16 copy -- the FIR runs once per
+//           candidate instead of twice (it is recomputed only for the rare candidate whose residuals overflow int16)
+// Wasted bits are assumed 0 in pass 1; a candidate that has some repeats pass 1 with the shift applied.
+#include "common.cuh"
+#include "tiles.cuh"
+#include "rice.cuh"
+
+namespace flacb200 {
+
+bool analyze_fast_ok(const EncCfg& cfg);   // encode_kernels.cu
+
+constexpr int A3_WPC = 2;        // warps per candidate
+constexpr int A3_SETS = 6;       // fixed orders 0..4, LPC
+constexpr int A3_PLANE = 4096;   // samples per plane (largest block of the register-tiled kernels)
+
+struct A3Cand {   // per candidate, shared by its warps
+    uint32_t limb_lo[A3_SETS][MAX_PARTS], limb_hi[A3_SETS][MAX_PARTS];
+    unsigned long long tree[2][128];   // [set][(1 << p) - 1 + j]: sum |r| of partition j at order p
+    uint32_t part_est[2][128];
+    uint8_t part_code[2][128];
+    unsigned long long u[5];           // per fixed order k: sum |r| of the samples in [k, kmax)
+    RiceChoice choice[2];
+    unsigned long long bits_f, bits_l;
+    uint32_t mask, ovf, bad16, bad_f, bad_l;
+    uint32_t fo, lpc_ok;               // decisions of the first warp, read by the second
+};
+
+__device__ inline void a3_pair_sync(uint32_t cand)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(1u + cand), "r"(32u * A3_WPC) : "memory");
+}
+
+__device__ inline uint32_t a3_tile_base(uint32_t t) { return ((t >> 5) * 128u + (t & 31u)) * 4u; }   // word index of chunk 0
+
+// chunk c (4 samples) of tile t of the candidate; slot selects the stereo combination (uniform across the warp)
+template <bool STEREO>
+__device__ inline void a3_chunk(const int32_t* __restrict__ planes, uint32_t slot, uint32_t t, int c, int32_t* v)
+{
+    const uint32_t w = a3_tile_base(t) + (uint32_t)c * 128u;
+    if (STEREO) {
+        if (slot < 2) {
+            const int4 a = *reinterpret_cast<const int4*>(planes + slot * A3_PLANE + w);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        } else {
+            const int4 a = *reinterpret_cast<const int4*>(planes + w);
+            const int4 b = *reinterpret_cast<const int4*>(planes + A3_PLANE + w);
+            if (slot == 2) { v[0] = (a.x + b.x) >> 1; v[1] = (a.y + b.y) >> 1; v[2] = (a.z + b.z) >> 1; v[3] = (a.w + b.w) >> 1; }   // :2721
+            else { v[0] = a.x - b.x; v[1] = a.y - b.y; v[2] = a.z - b.z; v[3] = a.w - b.w; }                                        // :2734
+        }
+    } else {
+        const int4 a = *reinterpret_cast<const int4*>(planes + slot * A3_PLANE + w);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+}
+
+// HB: the launch's max LPC order rounded up to 4/8/12/16
+template <int HB, bool STEREO>
+__device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_t* __restrict__ planes, uint4* __restrict__ res16, uint32_t slot,
+                             uint32_t pslot, uint32_t cand, uint32_t wsub, uint32_t full_bps, const LpcRec& lp, A3Cand& sm, CandRec* __restrict__ rec)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = d.n;
+    const uint32_t rounds = ((n + 15) / 16 + 31) / 32;
+    uint32_t p_max = (uint32_t)__ffs((int)n) - 1u;
+    if (p_max > cfg.max_porder) p_max = cfg.max_porder;
+    if (p_max > MAX_PORDER) p_max = MAX_PORDER;
+    const uint32_t cf = n >> p_max;   // finest partition
+    const bool cf16 = (cf & 15u) == 0;
+    const uint32_t kmax = min(4u, n - 1);
+    const bool have_lpc = lp.ok != 0;
+    const uint32_t order = have_lpc ? lp.order : 0, shift = lp.shift;
+    int32_t q[HB];
+#pragma unroll
+    for (int j = 0; j < HB; j++) q[j] = (have_lpc && (uint32_t)j < order) ? (int32_t)lp.q[j] : 0;
+
+    uint32_t wasted = 0, fo = 0, bps = full_bps;
+    bool lpc_ok = have_lpc, use16 = false;
+    unsigned long long bits_f = 0, bits_l = 0;
+    uint32_t bad_f = 0, bad_l = 0;
+    uint32_t cpf = n, j0f = 0, cpl = n, j0l = 0;
+    bool cpf16 = false, cpl16 = false;
+    // stage 0: pass 1 assuming no wasted bits; stage 1: pass 1 again with the wasted bits shifted out (rare);
+    // stage 2: pass 2 (exact sizes).  One loop body serves all stages so that the FIR code exists once.
+    for (int stage = 0; stage < 3; stage++) {
+        if (stage == 1 && wasted == 0) continue;
+        uint32_t mask = 0, ovf = 0, b16 = 0;
+        if (stage < 2) {
+            if (wsub == 0) {
+                for (uint32_t t = lane; t < A3_SETS * MAX_PARTS; t += 32) {
+                    (&sm.limb_lo[0][0])[t] = 0;
+                    (&sm.limb_hi[0][0])[t] = 0;
+                }
+                if (lane < 5) sm.u[lane] = 0;
+                if (lane == 0) { sm.mask = 0; sm.ovf = 0; sm.bad16 = 0; sm.bad_f = 0; sm.bad_l = 0; sm.bits_f = 0; sm.bits_l = 0; }
+            }
+            a3_pair_sync(cand);
+        } else {
+            // ---- between the passes: fixed order, partition trees, Rice parameters (first warp of the candidate) ----
+            if (sm.mask == 0) {   // all samples zero -> CONSTANT (:2870, :2883)
+                if (wsub == 0 && lane == 0) {
+                    rec->type = 0; rec->order = 0; rec->wasted = 0; rec->bps = (uint8_t)full_bps;
+                    rec->bits = 8 + full_bps;
+                }
+                return;
+            }
+            bps = full_bps - wasted;
+            if (wsub == 0) {
+                unsigned long long s0, s1, s2, s3, s4;
+                {   // sums over the common tail = everything set k counted, minus its samples before kmax
+                    unsigned long long tk[5];
+#pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        unsigned long long v = 0;
+                        for (uint32_t j = lane; j < MAX_PARTS; j += 32) v += (unsigned long long)sm.limb_lo[k][j] + ((unsigned long long)sm.limb_hi[k][j] << 24);
+                        tk[k] = warp_sum_u64(v) - sm.u[k];
+                    }
+                    s0 = tk[0]; s1 = tk[1]; s2 = tk[2]; s3 = tk[3]; s4 = tk[4];
+                }
+                {   // first minimum among the orders that exist (:3065-3075)
+                    unsigned long long best = s0;
+                    fo = 0;
+                    if (kmax >= 1 && s1 < best) { best = s1; fo = 1; }
+                    if (kmax >= 2 && s2 < best) { best = s2; fo = 2; }
+                    if (kmax >= 3 && s3 < best) { best = s3; fo = 3; }
+                    if (kmax >= 4 && s4 < best) { best = s4; fo = 4; }
+                }
+                lpc_ok = have_lpc && sm.ovf == 0;   // ResidualOverflow
+                __syncwarp();
+                const uint32_t nleaf = 1u << p_max;
+                for (uint32_t k = 0; k < 2; k++) {
+                    const uint32_t set = k == 0 ? fo : 5;
+                    for (uint32_t j = lane; j < nleaf; j += 32)
+                        sm.tree[k][nleaf - 1 + j] = (unsigned long long)sm.limb_lo[set][j] + ((unsigned long long)sm.limb_hi[set][j] << 24);
+                }
+                __syncwarp();
+                for (int p = (int)p_max - 1; p >= 0; p--) {
+                    const uint32_t base = (1u << p) - 1, child = (2u << p) - 1;
+                    for (uint32_t j = lane; j < (1u << p); j += 32) {
+                        sm.tree[0][base + j] = sm.tree[0][child + 2 * j] + sm.tree[0][child + 2 * j + 1];
+                        sm.tree[1][base + j] = sm.tree[1][child + 2 * j] + sm.tree[1][child + 2 * j + 1];
+                    }
+                    __syncwarp();
+                }
+                aw_choose_partitions(cfg, n, fo, p_max, sm.tree[0], sm.part_est[0], sm.part_code[0], sm.choice[0]);
+                if (lpc_ok) aw_choose_partitions(cfg, n, order, p_max, sm.tree[1], sm.part_est[1], sm.part_code[1], sm.choice[1]);
+                if (lane == 0) { sm.fo = fo; sm.lpc_ok = lpc_ok ? 1u : 0u; }
+            }
+            a3_pair_sync(cand);
+            fo = sm.fo;
+            lpc_ok = sm.lpc_ok != 0;
+            use16 = sm.bad16 == 0;
+            cpf = n >> sm.choice[0].porder_g;
+            j0f = (1u << sm.choice[0].porder_g) - sm.choice[0].nparts;
+            cpf16 = (cpf & 15u) == 0;
+            if (lpc_ok) {
+                cpl = n >> sm.choice[1].porder_g;
+                j0l = (1u << sm.choice[1].porder_g) - sm.choice[1].nparts;
+                cpl16 = (cpl & 15u) == 0;
+            }
+        }
+        for (uint32_t rd = wsub; rd < rounds; rd += A3_WPC) {
+            const uint32_t t = rd * 32 + lane, i0 = t * 16;
+            if (i0 >= n) continue;
+            const bool tail = i0 + 16 > n;   // tile cut by the block end: rare, sample-by-sample path
+            const bool fir = lpc_ok && (stage < 2 || !use16);
+            int32_t x[16], h[16];
+#pragma unroll
+            for (int c = 0; c < 4; c++) a3_chunk<STEREO>(planes, pslot, t, c, x + 4 * c);
+#pragma unroll
+            for (int e = 0; e < 16; e++) h[e] = 0;
+            if (t > 0) {
+                // the fixed differences look back 4 samples, the FIR HB
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c == 3 || (fir && c >= 4 - HB / 4)) a3_chunk<STEREO>(planes, pslot, t - 1, c, h + 4 * c);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e++) { mask |= (uint32_t)x[e]; x[e] >>= wasted; h[e] >>= wasted; }   // :2878-2898
+            // ---- LPC residuals (:3174-3203) ----
+            int32_t rl[16];
+            if (fir) {
+                uint32_t om = 0, o16 = 0;
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    long long sum = 0;
+#pragma unroll
+                    for (int j = 0; j < HB; j++) sum = mad_wide_s32(e - 1 - j >= 0 ? x[e - 1 - j >= 0 ? e - 1 - j : 0] : h[16 + e - 1 - j >= 0 ? 16 + e - 1 - j : 0], q[j], sum);
+                    const int32_t pred = (int32_t)(uint32_t)(unsigned long long)(sum >> shift);   // `as i32`
+                    const int32_t rr = (int32_t)((uint32_t)x[e] - (uint32_t)pred);
+                    rl[e] = rr;
+                    om |= (((uint32_t)((x[e] ^ pred) & (x[e] ^ rr))) >> 31) << e;   // checked_sub: sign bit set when it overflowed
+                    o16 |= ((((uint32_t)rr + 0x8000u) & 0xFFFF0000u) ? 1u : 0u) << e;
+                }
+                if (stage < 2) {
+                    if (om | o16) {   // only samples in [order, n) count
+                        const uint32_t first = order > i0 ? min(order - i0, 16u) : 0u, last = min(16u, n - i0);
+                        const uint32_t valid = (last >= 16 ? 0xFFFFu : (1u << last) - 1u) & ~((1u << first) - 1u);
+                        if (om & valid) ovf = 1;
+                        if (o16 & valid) b16 = 1;
+                    }
+                    // park the residuals as int16 pairs (two 16-byte chunks per tile, conflict-free for 32 consecutive tiles)
+                    uint4 lo4, hi4;
+                    lo4.x = __byte_perm((uint32_t)rl[0], (uint32_t)rl[1], 0x5410); lo4.y = __byte_perm((uint32_t)rl[2], (uint32_t)rl[3], 0x5410);
+                    lo4.z = __byte_perm((uint32_t)rl[4], (uint32_t)rl[5], 0x5410); lo4.w = __byte_perm((uint32_t)rl[6], (uint32_t)rl[7], 0x5410);
+                    hi4.x = __byte_perm((uint32_t)rl[8], (uint32_t)rl[9], 0x5410); hi4.y = __byte_perm((uint32_t)rl[10], (uint32_t)rl[11], 0x5410);
+                    hi4.z = __byte_perm((uint32_t)rl[12], (uint32_t)rl[13], 0x5410); hi4.w = __byte_perm((uint32_t)rl[14], (uint32_t)rl[15], 0x5410);
+                    res16[(rd * 2 + 0) * 32 + lane] = lo4;
+                    res16[(rd * 2 + 1) * 32 + lane] = hi4;
+                }
+            } else if (lpc_ok) {   // pass 2: the int16 copy
+                const uint4 lo4 = res16[(rd * 2 + 0) * 32 + lane], hi4 = res16[(rd * 2 + 1) * 32 + lane];
+                const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    rl[2 * k] = (int32_t)(w[k] << 16) >> 16;
+                    rl[2 * k + 1] = (int32_t)w[k] >> 16;
+                }
+            }
+            // ---- fixed differences (:3039-3060); <= 28-bit samples cannot overflow i32 up to order 4 ----
+            int32_t p1 = h[15] - h[14], p2 = p1 - (h[14] - h[13]), p3 = p2 - ((h[14] - h[13]) - (h[13] - h[12]));
+            if (stage < 2) {
+                const uint32_t chunk = i0 / cf;
+                if (!tail && (cf16 || (i0 + 15) / cf == chunk)) {
+                    // per-tile sums in 32 bits: |e_k| < 2^(28 + k) would overflow over 16 samples only for k >= 3, which are
+                    // summed in two halves; the LPC residual is unbounded and keeps a 64-bit accumulator
+                    uint32_t a0 = 0, a1 = 0, a2 = 0, a3a = 0, a3b = 0, a4a = 0, a4b = 0;
+                    unsigned long long al = 0;
+                    int32_t prev = h[15];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const int32_t e1 = x[e] - prev, e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
+                        prev = x[e]; p1 = e1; p2 = e2; p3 = e3;
+                        a0 += uabs32(x[e]); a1 += uabs32(e1); a2 += uabs32(e2);
+                        if (e < 8) { a3a += uabs32(e3); a4a += uabs32(e4); }
+                        else { a3b += uabs32(e3); a4b += uabs32(e4); }
+                        if (lpc_ok) al = acc_u32(al, uabs32(rl[e]));
+                    }
+                    unsigned long long s0 = a0, s1 = a1, s2 = a2, s3 = (unsigned long long)a3a + a3b, s4 = (unsigned long long)a4a + a4b;
+                    if (i0 == 0) {
+                        // the block's first tile (n >= 16 here, so kmax == 4): with zero history the differences of the first
+                        // samples are these closed forms.  Set k does not count samples before k; the order comparison
+                        // (:3062-3073) does not count samples before kmax either -- remembered in sm.u[] for later.
+                        const int32_t y0 = x[0], y1 = x[1], y2 = x[2], y3 = x[3];
+                        const uint32_t f11 = uabs32(y1 - y0), f12 = uabs32(y2 - y1), f13 = uabs32(y3 - y2);
+                        const uint32_t f21 = uabs32(y1 - 2 * y0), f22 = uabs32(y2 - 2 * y1 + y0), f23 = uabs32(y3 - 2 * y2 + y1);
+                        const uint32_t f31 = uabs32(y1 - 3 * y0), f32 = uabs32(y2 - 3 * y1 + 3 * y0), f33 = uabs32(y3 - 3 * y2 + 3 * y1 - y0);
+                        const uint32_t f41 = uabs32(y1 - 4 * y0), f42 = uabs32(y2 - 4 * y1 + 6 * y0), f43 = uabs32(y3 - 4 * y2 + 6 * y1 - 4 * y0);
+                        const unsigned long long f0 = uabs32(y0);
+                        s1 -= f0;
+                        s2 -= f0 + f21;
+                        s3 -= f0 + f31 + f32;
+                        s4 -= f0 + f41 + f42 + f43;
+                        sm.u[0] = f0 + uabs32(y1) + uabs32(y2) + uabs32(y3);
+                        sm.u[1] = (unsigned long long)f11 + f12 + f13;
+                        sm.u[2] = (unsigned long long)f22 + f23;
+                        sm.u[3] = f33;
+                        sm.u[4] = 0;
+                        if (lpc_ok) {
+#pragma unroll
+                            for (int e = 0; e < 16; e++)
+                                if ((uint32_t)e < order) al -= uabs32(rl[e]);
+                        }
+                    }
+                    aw_add_limbs(sm.limb_lo[0], sm.limb_hi[0], chunk, s0);
+                    aw_add_limbs(sm.limb_lo[1], sm.limb_hi[1], chunk, s1);
+                    aw_add_limbs(sm.limb_lo[2], sm.limb_hi[2], chunk, s2);
+                    aw_add_limbs(sm.limb_lo[3], sm.limb_hi[3], chunk, s3);
+                    aw_add_limbs(sm.limb_lo[4], sm.limb_hi[4], chunk, s4);
+                    if (lpc_ok) aw_add_limbs(sm.limb_lo[5], sm.limb_hi[5], chunk, al);
+                } else {
+                    // copies: taking the address of the register tiles themselves would push them into local memory for good
+                    int32_t tx[16], th[16], tl[16];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) { tx[e] = x[e]; th[e] = h[e]; tl[e] = lpc_ok ? rl[e] : 0; }
+                    AwSmemLimbs limbs = {&sm.limb_lo[0][0], &sm.limb_hi[0][0]};
+                    aw_pass1_tile_slow(tx, th, tl, lpc_ok, order, i0, n, kmax, cf, limbs, sm.u);
+                }
+            } else {
+                // ---- pass 2: exact size of both residual blocks (what Partition::to_writer will emit, :3834-3863) ----
+                int32_t rf[16];
+                {
+                    int32_t prev = h[15];
+                    switch (fo) {   // uniform across the warp
+                    case 0:
+#pragma unroll
+                        for (int e = 0; e < 16; e++) rf[e] = x[e];
+                        break;
+                    case 1:
+#pragma unroll
+                        for (int e = 0; e < 16; e++) { rf[e] = x[e] - prev; prev = x[e]; }
+                        break;
+                    default:
+#pragma unroll
+                        for (int e = 0; e < 16; e++) {
+                            const int32_t e1 = x[e] - prev, e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
+                            prev = x[e]; p1 = e1; p2 = e2; p3 = e3;
+                            rf[e] = fo == 2 ? e2 : fo == 3 ? e3 : e4;
+                        }
+                        break;
+                    }
+                }
+                const RiceChoice& chf = sm.choice[0];
+                const uint32_t pf = i0 / cpf;
+                const uint32_t codef = chf.rice[pf - j0f >= chf.nparts ? 0 : pf - j0f];
+                if (!tail && i0 != 0 && (cpf16 || (i0 + 15) / cpf == pf) && codef < 0x40) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) bits_f = acc_u32(bits_f, zigzag32(rf[e]) >> codef);
+                    bits_f += 16u * (1u + codef);
+                } else {
+                    int32_t tmp[16];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) tmp[e] = rf[e];
+                    unsigned long long tb = 0;
+                    uint32_t tbad = 0;
+                    aw_tile_bits_slow(tmp, i0, fo, n, cpf, j0f, chf.rice, &tb, &tbad);
+                    bits_f += tb;
+                    bad_f |= tbad;
+                }
+                if (lpc_ok) {
+                    const RiceChoice& chl = sm.choice[1];
+                    const uint32_t pl = i0 / cpl;
+                    const uint32_t codel = chl.rice[pl - j0l >= chl.nparts ? 0 : pl - j0l];
+                    if (!tail && i0 != 0 && (cpl16 || (i0 + 15) / cpl == pl) && codel < 0x40) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) bits_l = acc_u32(bits_l, zigzag32(rl[e]) >> codel);
+                        bits_l += 16u * (1u + codel);
+                    } else {
+                        int32_t tmp[16];
+#pragma unroll
+                        for (int e = 0; e < 16; e++) tmp[e] = rl[e];
+                        unsigned long long tb = 0;
+                        uint32_t tbad = 0;
+                        aw_tile_bits_slow(tmp, i0, order, n, cpl, j0l, chl.rice, &tb, &tbad);
+                        bits_l += tb;
+                        bad_l |= tbad;
+                    }
+                }
+            }
+        }
+        if (stage < 2) {
+            mask = __reduce_or_sync(0xffffffffu, mask);
+            ovf = __reduce_or_sync(0xffffffffu, ovf);
+            b16 = __reduce_or_sync(0xffffffffu, b16);
+            if (lane == 0) {
+                if (mask) atomicOr(&sm.mask, mask);
+                if (ovf) atomicOr(&sm.ovf, 1u);
+                if (b16) atomicOr(&sm.bad16, 1u);
+            }
+            a3_pair_sync(cand);
+            if (stage == 0) {
+                const uint32_t m = sm.mask;
+                wasted = (m == 0 || (m & 1u)) ? 0u : (uint32_t)__ffs((int)m) - 1u;
+                if (wasted) a3_pair_sync(cand);   // both warps have read the flags before the next stage clears them
+            }
+        }
+    }
+    // ---- totals of both warps ----
+    bits_f = warp_sum_u64(bits_f);
+    bits_l = warp_sum_u64(bits_l);
+    bad_f = __any_sync(0xffffffffu, bad_f) ? 1u : 0u;
+    bad_l = __any_sync(0xffffffffu, bad_l) ? 1u : 0u;
+    if (lane == 0) {
+        if (bits_f) atomicAdd(&sm.bits_f, bits_f);
+        if (bits_l) atomicAdd(&sm.bits_l, bits_l);
+        if (bad_f) atomicOr(&sm.bad_f, 1u);
+        if (bad_l) atomicOr(&sm.bad_l, 1u);
+    }
+    a3_pair_sync(cand);
+    if (wsub != 0) return;
+    const RiceChoice& cf_ = sm.choice[0];
+    const RiceChoice& cl_ = sm.choice[1];
+    // partition headers: 4/5-bit parameter (+ 5-bit escape width)
+    uint32_t hf = 0, hl = 0;
+    for (uint32_t j = lane; j < cf_.nparts; j += 32) hf += (cf_.rice[j] < 0x40) ? (cf_.method ? 5u : 4u) : (cf_.method ? 10u : 9u);
+    if (lpc_ok)
+        for (uint32_t j = lane; j < cl_.nparts; j += 32) hl += (cl_.rice[j] < 0x40) ? (cl_.method ? 5u : 4u) : (cl_.method ? 10u : 9u);
+    hf = __reduce_add_sync(0xffffffffu, hf);
+    hl = __reduce_add_sync(0xffffffffu, hl);
+    const unsigned long long tot_f = sm.bits_f + hf, tot_l = sm.bits_l + hl;
+    const bool fixed_ok = sm.bad_f == 0;
+    if (sm.bad_l) lpc_ok = false;
+    const uint32_t hdr_bits = 8 + wasted;   // pad + type + wasted flag (+ unary(wasted - 1)) (src/stream.rs:1397)
+    const uint32_t fixed_bits = hdr_bits + fo * bps + (uint32_t)tot_f + 6;
+    const uint32_t lpc_bits = hdr_bits + order * bps + 4 + 5 + order * lp.precision + (uint32_t)tot_l + 6;
+    // ---- choose (:2929-2979): fixed wins ties; VERBATIM unless strictly smaller ----
+    const uint32_t verbatim_len = n * bps;
+    int pick = -1;   // 0 fixed, 1 lpc
+    if (fixed_ok && lpc_ok) pick = lpc_bits < fixed_bits ? 1 : 0;
+    else if (fixed_ok) pick = 0;
+    else if (lpc_ok) pick = 1;
+    const uint32_t best_bits = pick == 1 ? lpc_bits : fixed_bits;
+    if (pick >= 0 && !(best_bits < verbatim_len)) pick = -1;
+    const RiceChoice& ch = pick == 1 ? sm.choice[1] : sm.choice[0];
+    if (lane == 0) {
+        rec->wasted = (uint8_t)wasted;
+        rec->bps = (uint8_t)bps;
+        if (pick < 0) {
+            rec->type = 1; rec->order = 0;
+            rec->bits = hdr_bits + verbatim_len;
+        } else {
+            rec->type = pick == 1 ? 3 : 2;
+            rec->order = pick == 1 ? lp.order : (uint8_t)fo;
+            rec->precision = lp.precision; rec->shift = lp.shift;
+            rec->method = ch.method; rec->porder_w = ch.porder_w; rec->porder_g = ch.porder_g; rec->nparts = ch.nparts;
+            rec->bits = best_bits;
+        }
+    }
+    if (pick >= 0) {
+        for (uint32_t j = lane; j < MAX_PARTS; j += 32) rec->rice[j] = ch.rice[j];
+        if (lane < MAX_LPC) rec->q[lane] = lp.q[lane];
+    }
+}
+
+template <bool STEREO>
+__host__ __device__ constexpr int a3_cands() { return STEREO ? 4 : 2; }
+
+template <bool STEREO>
+__host__ __device__ constexpr size_t a3_smem_bytes()
+{
+    return (size_t)2 * A3_PLANE * 4 + (size_t)a3_cands<STEREO>() * A3_PLANE * 2 + (size_t)a3_cands<STEREO>() * sizeof(A3Cand);
+}
+
+// STEREO: grid = frames, block = 256 (4 candidates x 2 warps).  Otherwise: grid = frames * ceil(channels / 2), block = 128.
+template <int HB, bool STEREO>
+__global__ void __launch_bounds__(32 * A3_WPC * (STEREO ? 4 : 2), STEREO ? 2 : 4)
+    k_analyze3(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm, const LpcRec* __restrict__ lpcs,
+               CandRec* __restrict__ out, unsigned long long* __restrict__ abssum)
+{
+    constexpr int NC = a3_cands<STEREO>();
+    extern __shared__ __align__(16) uint8_t a3_dyn[];
+    int32_t* planes = reinterpret_cast<int32_t*>(a3_dyn);
+    uint4* res16_all = reinterpret_cast<uint4*>(a3_dyn + (size_t)2 * A3_PLANE * 4);
+    A3Cand* cands_sm = reinterpret_cast<A3Cand*>(a3_dyn + (size_t)2 * A3_PLANE * 4 + (size_t)NC * A3_PLANE * 2);
+    __shared__ unsigned long long abs4[4];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t groups = STEREO ? 1u : (cfg.channels + 1u) / 2u;
+    const uint32_t f = blockIdx.x / groups, g = blockIdx.x % groups;
+    const FrameDesc d = descs[f];
+    const uint32_t n = d.n;
+    const uint32_t ch0 = STEREO ? 0u : 2u * g;
+    const bool fast_modes = STEREO && (cfg.mode == MODE_FAST_MID_SIDE || cfg.mode == MODE_FAST_SIDE);
+    if (tid < 4) abs4[tid] = 0;
+    if (fast_modes) __syncthreads();
+    // ---- unpack the two source channels once (Frame::fill_from_buf, src/audio.rs:149-187) ----
+    {
+        unsigned long long sl = 0, sr = 0, smid = 0, sside = 0;
+        const uint32_t ntiles = (n + 15) / 16;
+        for (uint32_t t = tid; t < ntiles; t += blockDim.x) {
+            int32_t a[16], b[16];
+            const uint32_t i0 = t * 16;
+            if (STEREO || cfg.channels == 1) {
+                if (STEREO) load_thread_samples<2>(cfg, d, pcm, i0, 0, a, b);
+                else load_thread_samples<1>(cfg, d, pcm, i0, 0, a, b);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const bool ok = i0 + e < n;
+                    a[e] = ok ? load_pcm_sample(pcm, cfg, d.pcm_off + i0 + e, ch0) : 0;
+                    b[e] = (ok && ch0 + 1 < cfg.channels) ? load_pcm_sample(pcm, cfg, d.pcm_off + i0 + e, ch0 + 1) : 0;
+                }
+            }
+            const uint32_t w = a3_tile_base(t);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                *reinterpret_cast<int4*>(planes + w + c * 128) = make_int4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+                if (STEREO || cfg.channels > 1) *reinterpret_cast<int4*>(planes + A3_PLANE + w + c * 128) = make_int4(b[4 * c], b[4 * c + 1], b[4 * c + 2], b[4 * c + 3]);
+            }
+            if (fast_modes) {   // correlate_channels abs sums (:2475-2503)
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    sl += uabs32(a[e]); sr += uabs32(b[e]); smid += uabs32((a[e] + b[e]) >> 1); sside += uabs32(a[e] - b[e]);
+                }
+            }
+        }
+        if (fast_modes) {
+            sl = warp_sum_u64(sl); sr = warp_sum_u64(sr); smid = warp_sum_u64(smid); sside = warp_sum_u64(sside);
+            if (lane == 0) { atomicAdd(&abs4[0], sl); atomicAdd(&abs4[1], sr); atomicAdd(&abs4[2], smid); atomicAdd(&abs4[3], sside); }
+        }
+    }
+    __syncthreads();
+    const uint32_t cand = wid / A3_WPC, wsub = wid % A3_WPC;
+    const uint32_t slot = STEREO ? cand : ch0 + cand;
+    if (!STEREO && slot >= cfg.channels) return;
+    CandRec* rec = out + (size_t)f * cfg.nslots + slot;
+    if (STEREO) {
+        if (fast_modes) {
+            unsigned long long sums[4] = {abs4[0], abs4[1], abs4[2], abs4[3]};
+            if (tid < 4) abssum[(size_t)f * 4 + tid] = sums[tid];
+            if (!slot_active(cfg, sums, slot)) {
+                if (wsub == 0 && lane == 0) { rec->type = 0xFF; rec->bits = 0; }
+                return;
+            }
+        } else if (cfg.mode == MODE_EXH_SIDE && slot == 2) {
+            if (wsub == 0 && lane == 0) { rec->type = 0xFF; rec->bits = 0; }
+            return;
+        }
+    }
+    const uint32_t full_bps = STEREO ? cand_bps(cfg, slot) : cfg.bps;
+    const LpcRec lp = lpcs[(size_t)f * cfg.nslots + slot];
+    a3_candidate<HB, STEREO>(cfg, d, planes, res16_all + (size_t)cand * (A3_PLANE * 2 / 16), slot, STEREO ? slot : cand, cand, wsub, full_bps, lp,
+                             cands_sm[cand], rec);
+}
+
+// per-tile 32-bit sums of the fixed residuals need |x| < 2^25 (see pass 1)
+bool analyze3_ok(const EncCfg& cfg)
+{
+    const uint32_t widest = cfg.bps + (cfg.mode != MODE_INDEPENDENT ? 1u : 0u);
+    return analyze_fast_ok(cfg) && widest <= 26;
+}
+
+cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const LpcRec* lpcs, CandRec* cands,
+                            unsigned long long* abssum, cudaStream_t st)
+{
+    const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
+#define FLACB200_A3(HBV, ST)                                                                                                          \
+    do {                                                                                                                              \
+        const size_t smem_ = a3_smem_bytes<ST>();                                                                                     \
+        cudaError_t e_ = cudaFuncSetAttribute(k_analyze3<HBV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);          \
+        if (e_ != cudaSuccess) return e_;                                                                                             \
+        const uint32_t groups_ = ST ? 1u : (cfg.channels + 1u) / 2u;                                                                  \
+        k_analyze3<HBV, ST><<<cfg.nframes * groups_, 32 * A3_WPC * (ST ? 4 : 2), smem_, st>>>(cfg, descs, pcm, lpcs, cands, abssum);  \
+    } while (0)
+    if (cfg.mode != MODE_INDEPENDENT) {
+        switch (hb) {
+        case 1: FLACB200_A3(4, true); break;
+        case 2: FLACB200_A3(8, true); break;
+        case 3: FLACB200_A3(12, true); break;
+        default: FLACB200_A3(16, true); break;
+        }
+    } else {
+        switch (hb) {
+        case 1: FLACB200_A3(4, false); break;
+        case 2: FLACB200_A3(8, false); break;
+        case 3: FLACB200_A3(12, false); break;
+        default: FLACB200_A3(16, false); break;
+        }
+    }
+#undef FLACB200_A3
+    return cudaGetLastError();
+}
+
+}   // namespace flacb200

@@ -39,142 +39,6 @@ struct AwSmem {   // per warp
     RiceChoice choice[2];
 };
 
-struct AwSmemLimbs {
-    uint32_t* lo;
-    uint32_t* hi;
-};
-
-// rare path: a 16-sample tile that straddles a partition boundary, contains samples before the predictor order, or is cut by the block end
-__device__ __noinline__ void aw_tile_sums_slow(const int32_t* r, uint32_t i0, uint32_t first, uint32_t end, uint32_t cf, uint32_t* lo, uint32_t* hi)
-{
-    for (uint32_t i = max(i0, first); i < min(i0 + 16u, end); i++) {
-        const uint32_t v = uabs32(r[i - i0]);
-        if (v) {
-            atomicAdd(&lo[i / cf], v & 0xFFFFFFu);
-            atomicAdd(&hi[i / cf], v >> 24);
-        }
-    }
-}
-
-__device__ __noinline__ void aw_tile_bits_slow(const int32_t* r, uint32_t i0, uint32_t first, uint32_t end, uint32_t cp, uint32_t j0,
-                                               const uint8_t* rice, unsigned long long* bits_io, uint32_t* bad_io)
-{
-    unsigned long long bits = *bits_io;
-    uint32_t bad = *bad_io;
-    for (uint32_t i = max(i0, first); i < min(i0 + 16u, end); i++) {
-        const uint32_t c = rice[i / cp - j0];
-        const int32_t s = r[i - i0];
-        if (c < 0x40) bits += (zigzag32(s) >> c) + 1u + c;
-        else if (c & 0x40) {
-            const uint32_t w = c & 31u;
-            bits += w;
-            if (s < -(1 << (w - 1)) || s > (1 << (w - 1)) - 1) bad = 1;   // write_signed_counted fails
-        }
-    }
-    *bits_io = bits;
-    *bad_io = bad;
-}
-
-// pass-1 work of a rare tile (first tile of the block, tile cut by the block end, tile straddling a partition boundary):
-// fixed orders 0..4 and the LPC residual rl, sample by sample
-__device__ __noinline__ void aw_pass1_tile_slow(const int32_t* x, const int32_t* h, const int32_t* rl, bool have_lpc, uint32_t order, uint32_t i0,
-                                                uint32_t n, uint32_t kmax, uint32_t cf, AwSmemLimbs limbs, unsigned long long* u)
-{
-    int32_t r[5][16];
-    int32_t p1 = h[15] - h[14], p2 = p1 - (h[14] - h[13]), p3 = p2 - ((h[14] - h[13]) - (h[13] - h[12]));
-    int32_t prev = h[15];
-    for (int e = 0; e < 16; e++) {
-        const int32_t e1 = x[e] - prev, e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
-        prev = x[e]; p1 = e1; p2 = e2; p3 = e3;
-        r[0][e] = x[e]; r[1][e] = e1; r[2][e] = e2; r[3][e] = e3; r[4][e] = e4;
-    }
-    for (uint32_t k = 0; k < 5; k++) {
-        aw_tile_sums_slow(r[k], i0, k, n, cf, limbs.lo + k * MAX_PARTS, limbs.hi + k * MAX_PARTS);
-        if (i0 == 0) {   // what set k counts but the order comparison (:3062-3073, samples >= kmax only) does not
-            unsigned long long v = 0;
-            for (uint32_t i = k; i < kmax && i < 16 && i < n; i++) v += uabs32(r[k][i]);
-            u[k] = v;
-        }
-    }
-    if (have_lpc) aw_tile_sums_slow(rl, i0, order, n, cf, limbs.lo + 5 * MAX_PARTS, limbs.hi + 5 * MAX_PARTS);
-}
-
-__device__ inline void aw_add_limbs(uint32_t* lo, uint32_t* hi, uint32_t chunk, unsigned long long v)
-{
-    if (v) {
-        atomicAdd(&lo[chunk], (uint32_t)v & 0xFFFFFFu);
-        atomicAdd(&hi[chunk], (uint32_t)(v >> 24));
-    }
-}
-
-// best_partitions + try_reduce_rice (src/encode.rs:3865-3942) for one residual set, by one warp.
-// tree[] holds the per-partition sums of every order; fills ch (rice[], geometry, method) -- not the size.
-__device__ void aw_choose_partitions(const EncCfg& cfg, uint32_t n, uint32_t o, uint32_t p_max, const unsigned long long* tree, uint32_t* part_est,
-                                     uint8_t* part_code, RiceChoice& ch)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t rice_max = cfg.use_rice2 ? 31u : 15u;
-    for (uint32_t t = lane; t < 127; t += 32) {   // (order p, partition j)
-        const uint32_t p = 31u - (uint32_t)__clz((int)(t + 1));
-        const uint32_t j = t + 1 - (1u << p);
-        uint8_t code = 0xFE;
-        uint32_t est = 0;
-        if (p <= p_max) {
-            const uint32_t cp = n >> p;
-            const uint32_t a = j * cp, b = a + cp;
-            if (b > o) code = partition_code(tree[t], b - max(a, o), rice_max, &est);
-        }
-        part_code[t] = code;
-        part_est[t] = est;
-    }
-    __syncwarp();
-    // lane p ends up with the totals of order p; every order is summed by the whole warp
-    uint32_t est = 0, cnt = 0, bad = 0;
-    for (uint32_t p = 0; p <= p_max; p++) {
-        const uint32_t base = (1u << p) - 1;
-        uint32_t e1 = 0, c1 = 0, b1 = 0;
-        for (uint32_t j = lane; j < (1u << p); j += 32) {
-            const uint8_t c = part_code[base + j];
-            if (c == 0xFE) continue;
-            if (c == 0xFF) b1 = 1;
-            c1++;
-            e1 += part_est[base + j];
-        }
-        e1 = __reduce_add_sync(0xffffffffu, e1);
-        c1 = __reduce_add_sync(0xffffffffu, c1);
-        b1 = __reduce_or_sync(0xffffffffu, b1);
-        if (lane == p) { est = e1; cnt = c1; bad = b1; }
-    }
-    const bool ok = lane <= p_max && !bad && cnt != 0 && (cnt & (cnt - 1)) == 0;   // :3880-3881
-    const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-    if (okmask == 0) {   // unwrap_or_else (:3887): one partition escaped at 31 bits
-        if (lane == 0) {
-            ch.porder_g = 0; ch.porder_w = 0; ch.nparts = 1; ch.rice[0] = 0x40 | 31;
-            ch.method = cfg.use_rice2 ? 1 : 0;
-        }
-        __syncwarp();
-        return;
-    }
-    const uint32_t best_est = __reduce_min_sync(0xffffffffu, ok ? est : 0xFFFFFFFFu);
-    const uint32_t best_p = (uint32_t)__ffs((int)(__ballot_sync(0xffffffffu, ok && est == best_est))) - 1u;   // first minimum :3885
-    const uint32_t best_count = __shfl_sync(0xffffffffu, cnt, best_p);
-    const uint32_t base = (1u << best_p) - 1, j0 = (1u << best_p) - best_count;
-    uint32_t big = 0;
-    for (uint32_t j = lane; j < best_count; j += 32) {
-        const uint8_t c = part_code[base + j0 + j];
-        ch.rice[j] = c;
-        if (c < 0x40 && c >= 15) big = 1;
-    }
-    big = __any_sync(0xffffffffu, big);
-    if (lane == 0) {
-        ch.porder_g = (uint8_t)best_p;
-        ch.nparts = (uint8_t)best_count;
-        ch.porder_w = (uint8_t)(31u - (uint32_t)__clz((int)best_count));   // partitions.len().ilog2() :3902
-        ch.method = (cfg.use_rice2 && big) ? 1 : 0;                         // try_reduce_rice :3929-3942
-    }
-    __syncwarp();
-}
-
 // HB: the launch's max LPC order rounded up to 4/8/12/16 (one instantiation per launch keeps the instruction
 // footprint small; predictors of lower order run with zero coefficients)
 template <int HB, bool STEREO>

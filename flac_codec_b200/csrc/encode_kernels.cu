@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "crc.cuh"
 #include "tiles.cuh"
+#include "rice.cuh"
 
 namespace flacb200 {
 
@@ -254,13 +255,6 @@ __global__ void __launch_bounds__(32 * LPC_WARPS) k_lpc(EncCfg cfg, const FrameD
 // ------------------------------------------------------------------------------------------------
 constexpr int RES_THREADS = 256;
 
-struct RiceChoice {
-    uint32_t resid_bits;   // bits of the whole residual block incl. method/order/partition headers
-    uint32_t fail;
-    uint8_t method, porder_w, porder_g, nparts;
-    uint8_t rice[MAX_PARTS];
-};
-
 struct ResSmem {
     unsigned long long red[RES_THREADS / 32];
     uint32_t red32[RES_THREADS / 32];
@@ -270,34 +264,6 @@ struct ResSmem {
     RiceChoice fixed, lpc;
     uint32_t flags;
 };
-
-// Partition::new (src/encode.rs:3765-3831): code and estimated bits of one partition
-__device__ inline uint8_t partition_code(unsigned long long sum, uint32_t len, uint32_t rice_max, uint32_t* est)
-{
-    *est = 0;
-    const uint32_t samples = len & 0xffffu;   // `as u16`
-    if (samples == 0) return 0xFF;
-    if (sum == 0) return 0x80;                // all-zero partition (:3826)
-    uint32_t rice = 0;
-    if (sum > samples) {
-        // ceil(log2(sum / samples)) == min{k : samples << k >= sum}; equality with the reference's f64 form
-        // is checked in tests/test_oracle_kat.py::test_rice_parameter_integer_equivalence
-        // start from the bit-length difference (at most one below the answer), then step
-        const uint32_t lg_sum = 63u - (uint32_t)__clzll((long long)sum), lg_n = 31u - (uint32_t)__clz((int)samples);
-        rice = lg_sum > lg_n ? lg_sum - lg_n : 0u;
-        while (((unsigned long long)samples << rice) < sum) rice++;
-        if (rice >= rice_max) {
-            const uint32_t escape = (63u - (uint32_t)__clzll((long long)sum)) + 2u;   // ilog2(sum) + 2 (:3787)
-            if (escape > 31) return 0xFF;
-            *est = escape * samples;
-            return (uint8_t)(0x40 | escape);
-        }
-    }
-    const unsigned long long t = rice > 0 ? (sum >> (rice - 1)) : (sum << 1);   // :3811-3815
-    if (t > 0xffffffffull) return 0xFF;
-    *est = 4u + ((1u + rice) * samples) + (uint32_t)t - (samples / 2u);
-    return (uint8_t)rice;
-}
 
 // best_partitions + try_reduce_rice (src/encode.rs:3865-3942) and the exact size of the residual block.
 // r: L residuals of a block of n samples with predictor order o.  All threads of the CTA must call.

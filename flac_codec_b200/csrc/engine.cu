@@ -26,6 +26,8 @@ cudaError_t launch_residual(const EncCfg&, const FrameDesc*, const int32_t*, con
 void launch_decide_scan(const EncCfg&, const FrameDesc*, const CandRec*, const unsigned long long*, FrameRec*, uint32_t*, unsigned long long*,
                         unsigned long long*, uint8_t*, bool, cudaStream_t);
 bool pack3_ok(const EncCfg&);
+bool analyze3_ok(const EncCfg&);
+cudaError_t launch_analyze3(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, cudaStream_t);
 cudaError_t launch_pack3(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 bool analyze_fast_ok(const EncCfg&);
@@ -392,6 +394,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     const bool fast_analyze = analyze_fast_ok(cfg) && !(legacy & 1u);
     const bool fast_lpc = cfg.max_lpc_order >= 1 && !(legacy & 2u);
     const bool fast_pack = analyze_fast_ok(cfg) && !(legacy & 4u);
+    const bool frame_analyze = fast_analyze && analyze3_ok(cfg) && !(legacy & 16u);   // k_analyze3: CTA per frame, shared unpack
     const bool frame_pack = fast_pack && pack3_ok(cfg) && !(legacy & 8u);   // k_pack3: whole frames, CRC fused, no pre-zeroed output
     const bool need_planes = !(fast_analyze && fast_pack && (fast_lpc || cfg.max_lpc_order == 0));
     // launch group: without the int32 planes a group costs ~250 bytes per candidate, so it can be large enough to fill
@@ -495,7 +498,8 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st));
         else launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st);
         time_mark(e, eb + 2);
-        if (fast_analyze) CK(launch_analyze(c, dd, d_pcm, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p, d_abssum, st));
+        if (frame_analyze) CK(launch_analyze3(c, dd, d_pcm, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p, d_abssum, st));
+        else if (fast_analyze) CK(launch_analyze(c, dd, d_pcm, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p, d_abssum, st));
         else
             CK(launch_residual(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p,
                                (int32_t*)e->scratch.p, st));
