@@ -80,6 +80,7 @@ struct flacb200_engine {
     uint64_t info_frames = 0;
     void* host_stage = nullptr;
     size_t host_stage_cap = 0;
+    std::vector<FrameDesc> descs_host;
 };
 
 static int cuda_err(cudaError_t e) { return e == cudaSuccess ? 0 : FLACB200_E_CUDA_BASE - (int)e; }
@@ -355,21 +356,29 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     }
 
     // ---- cut segments into blocks ----
-    std::vector<FrameDesc> descs;
+    std::vector<FrameDesc>& descs = e->descs_host;   // kept between calls: no reallocation on the steady-state path
+    descs.clear();
     const uint32_t bs = opt->block_size;
     const size_t sample_bytes = (size_t)cfg.bytes_per_sample;
-    uint64_t max_index = 0;
+    uint64_t max_index = 0, want = 0;
+    for (size_t s = 0; s < n_segments; s++) want += (segments[s].n_pcm_frames + bs - 1) / bs;
+    descs.reserve(want);
+    uint32_t win_n = 0, win_o = 0;   // the window table is looked up once per distinct block length, not per frame
     for (size_t s = 0; s < n_segments; s++) {
         const flacb200_segment& sg = segments[s];
         uint64_t done = 0, fn = sg.first_frame_number;
         while (done < sg.n_pcm_frames) {
             const uint32_t n = (uint32_t)std::min<uint64_t>(bs, sg.n_pcm_frames - done);
             if (fn > 0xFFFFFFFFFull) return 38;   // ExcessiveFrameNumber
+            if (opt->max_lpc_order && n != win_n) {
+                win_o = window_offset(e, *opt, n);
+                win_n = n;
+            }
             FrameDesc d;
             d.pcm_off = sg.pcm_offset + done;
             d.fnum = fn++;
             d.n = n;
-            d.win_off = opt->max_lpc_order ? window_offset(e, *opt, n) : 0;
+            d.win_off = win_o;
             descs.push_back(d);
             done += n;
         }
