@@ -176,26 +176,26 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    # a bounded sample of the workload: the first track(s), generated by the numpy statement of the generator
-    tracks = host_tracks_numpy(1, min(args.seconds, 60))
+    # a bounded sample of the workload: the first tracks (60 s of each), generated by the numpy statement of the generator
     from oracle import oracle as fo
 
     opt = fo.options("best")
-    x = tracks[0]
-    t0 = time.perf_counter()
-    fo.encode_frames_only(opt, RATE, BPS, CH, x[: RATE * 2 * CH], nthreads=cores)
-    rate = RATE * 2 * CH / (time.perf_counter() - t0)
-    per_step = int(min(x.size, max(rate * 4.0, CH * 4096 * cores)))   # ~4 s of CPU work per step
-    per_step -= per_step % (CH * 4096)
-    per_step = max(per_step, CH * 4096)
+    n_tracks = 8
+    tracks = host_tracks_numpy(n_tracks, min(args.seconds, 60))
+    per_step = sum(x.size for x in tracks)
+
+    def one_step():
+        for x in tracks:   # file-level batches, every frame of a track encoded concurrently (OpenMP) on all host cores
+            fo.encode_frames_only(opt, RATE, BPS, CH, x, nthreads=cores)
+
     for _ in range(args.warmup):
-        fo.encode_frames_only(opt, RATE, BPS, CH, x[:per_step], nthreads=cores)
+        one_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fo.encode_frames_only(opt, RATE, BPS, CH, x[:per_step], nthreads=cores)
+        one_step()
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt / 1e6
-    sample = f"{per_step // CH} PCM frames ({per_step / CH / RATE:.1f} s of one track) per step"
+    sample = f"{n_tracks} tracks x {min(args.seconds, 60)} s ({per_step // CH} PCM frames) of the same workload per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",

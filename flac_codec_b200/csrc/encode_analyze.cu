@@ -47,24 +47,36 @@ __device__ inline void a3_pair_sync(uint32_t cand)
 
 __device__ inline uint32_t a3_tile_base(uint32_t t) { return ((t >> 5) * 128u + (t & 31u)) * 4u; }   // word index of chunk 0
 
-// chunk c (4 samples) of tile t of the candidate; slot selects the stereo combination (uniform across the warp)
+// chunks [c0, 4) of tile t of the candidate into v[4 c0 .. 16); slot selects the stereo combination (uniform across the
+// warp): one branch per tile, the chunk loads inside are straight-line 128-bit shared loads
 template <bool STEREO>
-__device__ inline void a3_chunk(const int32_t* __restrict__ planes, uint32_t slot, uint32_t t, int c, int32_t* v)
+__device__ inline void a3_tile(const int32_t* __restrict__ planes, uint32_t slot, uint32_t t, int c0, int32_t* v)
 {
-    const uint32_t w = a3_tile_base(t) + (uint32_t)c * 128u;
-    if (STEREO) {
-        if (slot < 2) {
-            const int4 a = *reinterpret_cast<const int4*>(planes + slot * A3_PLANE + w);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        } else {
-            const int4 a = *reinterpret_cast<const int4*>(planes + w);
-            const int4 b = *reinterpret_cast<const int4*>(planes + A3_PLANE + w);
-            if (slot == 2) { v[0] = (a.x + b.x) >> 1; v[1] = (a.y + b.y) >> 1; v[2] = (a.z + b.z) >> 1; v[3] = (a.w + b.w) >> 1; }   // :2721
-            else { v[0] = a.x - b.x; v[1] = a.y - b.y; v[2] = a.z - b.z; v[3] = a.w - b.w; }                                        // :2734
+    const uint32_t w = a3_tile_base(t);
+    if (!STEREO || slot < 2) {
+        const int32_t* p = planes + slot * A3_PLANE + w;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (c < c0) continue;
+            const int4 a = *reinterpret_cast<const int4*>(p + c * 128);
+            v[4 * c] = a.x; v[4 * c + 1] = a.y; v[4 * c + 2] = a.z; v[4 * c + 3] = a.w;
         }
-    } else {
-        const int4 a = *reinterpret_cast<const int4*>(planes + slot * A3_PLANE + w);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else if (slot == 2) {   // mid (:2721)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (c < c0) continue;
+            const int4 a = *reinterpret_cast<const int4*>(planes + w + c * 128);
+            const int4 b = *reinterpret_cast<const int4*>(planes + A3_PLANE + w + c * 128);
+            v[4 * c] = (a.x + b.x) >> 1; v[4 * c + 1] = (a.y + b.y) >> 1; v[4 * c + 2] = (a.z + b.z) >> 1; v[4 * c + 3] = (a.w + b.w) >> 1;
+        }
+    } else {                  // side (:2734)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (c < c0) continue;
+            const int4 a = *reinterpret_cast<const int4*>(planes + w + c * 128);
+            const int4 b = *reinterpret_cast<const int4*>(planes + A3_PLANE + w + c * 128);
+            v[4 * c] = a.x - b.x; v[4 * c + 1] = a.y - b.y; v[4 * c + 2] = a.z - b.z; v[4 * c + 3] = a.w - b.w;
+        }
     }
 }
 
@@ -106,7 +118,10 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     (&sm.limb_hi[0][0])[t] = 0;
                 }
                 if (lane < 5) sm.u[lane] = 0;
-                if (lane == 0) { sm.mask = 0; sm.ovf = 0; sm.bad16 = 0; sm.bad_f = 0; sm.bad_l = 0; sm.bits_f = 0; sm.bits_l = 0; }
+                if (lane == 0) {
+                    if (stage == 0) sm.mask = 0;   // the OR mask is gathered in stage 0 only
+                    sm.ovf = 0; sm.bad16 = 0; sm.bad_f = 0; sm.bad_l = 0; sm.bits_f = 0; sm.bits_l = 0;
+                }
             }
             a3_pair_sync(cand);
         } else {
@@ -119,7 +134,8 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                 return;
             }
             bps = full_bps - wasted;
-            if (wsub == 0) {
+            const uint32_t nleaf = 1u << p_max;
+            if (wsub == 0) {   // first warp: the fixed predictor
                 unsigned long long s0, s1, s2, s3, s4;
                 {   // sums over the common tail = everything set k counted, minus its samples before kmax
                     unsigned long long tk[5];
@@ -139,26 +155,30 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     if (kmax >= 3 && s3 < best) { best = s3; fo = 3; }
                     if (kmax >= 4 && s4 < best) { best = s4; fo = 4; }
                 }
-                lpc_ok = have_lpc && sm.ovf == 0;   // ResidualOverflow
-                __syncwarp();
-                const uint32_t nleaf = 1u << p_max;
-                for (uint32_t k = 0; k < 2; k++) {
-                    const uint32_t set = k == 0 ? fo : 5;
-                    for (uint32_t j = lane; j < nleaf; j += 32)
-                        sm.tree[k][nleaf - 1 + j] = (unsigned long long)sm.limb_lo[set][j] + ((unsigned long long)sm.limb_hi[set][j] << 24);
-                }
+                for (uint32_t j = lane; j < nleaf; j += 32)
+                    sm.tree[0][nleaf - 1 + j] = (unsigned long long)sm.limb_lo[fo][j] + ((unsigned long long)sm.limb_hi[fo][j] << 24);
                 __syncwarp();
                 for (int p = (int)p_max - 1; p >= 0; p--) {
                     const uint32_t base = (1u << p) - 1, child = (2u << p) - 1;
-                    for (uint32_t j = lane; j < (1u << p); j += 32) {
-                        sm.tree[0][base + j] = sm.tree[0][child + 2 * j] + sm.tree[0][child + 2 * j + 1];
-                        sm.tree[1][base + j] = sm.tree[1][child + 2 * j] + sm.tree[1][child + 2 * j + 1];
-                    }
+                    for (uint32_t j = lane; j < (1u << p); j += 32) sm.tree[0][base + j] = sm.tree[0][child + 2 * j] + sm.tree[0][child + 2 * j + 1];
                     __syncwarp();
                 }
                 aw_choose_partitions(cfg, n, fo, p_max, sm.tree[0], sm.part_est[0], sm.part_code[0], sm.choice[0]);
-                if (lpc_ok) aw_choose_partitions(cfg, n, order, p_max, sm.tree[1], sm.part_est[1], sm.part_code[1], sm.choice[1]);
-                if (lane == 0) { sm.fo = fo; sm.lpc_ok = lpc_ok ? 1u : 0u; }
+                if (lane == 0) sm.fo = fo;
+            } else {           // second warp: the LPC predictor
+                lpc_ok = have_lpc && sm.ovf == 0;   // ResidualOverflow
+                if (lpc_ok) {
+                    for (uint32_t j = lane; j < nleaf; j += 32)
+                        sm.tree[1][nleaf - 1 + j] = (unsigned long long)sm.limb_lo[5][j] + ((unsigned long long)sm.limb_hi[5][j] << 24);
+                    __syncwarp();
+                    for (int p = (int)p_max - 1; p >= 0; p--) {
+                        const uint32_t base = (1u << p) - 1, child = (2u << p) - 1;
+                        for (uint32_t j = lane; j < (1u << p); j += 32) sm.tree[1][base + j] = sm.tree[1][child + 2 * j] + sm.tree[1][child + 2 * j + 1];
+                        __syncwarp();
+                    }
+                    aw_choose_partitions(cfg, n, order, p_max, sm.tree[1], sm.part_est[1], sm.part_code[1], sm.choice[1]);
+                }
+                if (lane == 0) sm.lpc_ok = lpc_ok ? 1u : 0u;
             }
             a3_pair_sync(cand);
             fo = sm.fo;
@@ -179,22 +199,24 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
             const bool tail = i0 + 16 > n;   // tile cut by the block end: rare, sample-by-sample path
             const bool fir = lpc_ok && (stage < 2 || !use16);
             int32_t x[16], h[16];
-#pragma unroll
-            for (int c = 0; c < 4; c++) a3_chunk<STEREO>(planes, pslot, t, c, x + 4 * c);
+            a3_tile<STEREO>(planes, pslot, t, 0, x);
 #pragma unroll
             for (int e = 0; e < 16; e++) h[e] = 0;
-            if (t > 0) {
-                // the fixed differences look back 4 samples, the FIR HB
-#pragma unroll
-                for (int c = 0; c < 4; c++)
-                    if (c == 3 || (fir && c >= 4 - HB / 4)) a3_chunk<STEREO>(planes, pslot, t - 1, c, h + 4 * c);
+            if (t > 0) {   // the fixed differences look back 4 samples, the FIR HB
+                if (fir) a3_tile<STEREO>(planes, pslot, t - 1, 4 - HB / 4, h);
+                else a3_tile<STEREO>(planes, pslot, t - 1, 3, h);
             }
+            if (stage == 0) {
 #pragma unroll
-            for (int e = 0; e < 16; e++) { mask |= (uint32_t)x[e]; x[e] >>= wasted; h[e] >>= wasted; }   // :2878-2898
+                for (int e = 0; e < 16; e++) mask |= (uint32_t)x[e];
+            } else if (wasted) {   // :2878-2898
+#pragma unroll
+                for (int e = 0; e < 16; e++) { x[e] >>= wasted; h[e] >>= wasted; }
+            }
             // ---- LPC residuals (:3174-3203) ----
             int32_t rl[16];
             if (fir) {
-                uint32_t om = 0, o16 = 0;
+                uint32_t oacc = 0, sacc = 0;   // OR of the checked_sub overflow signs / of the bits that do not fit int16
 #pragma unroll
                 for (int e = 0; e < 16; e++) {
                     long long sum = 0;
@@ -203,15 +225,19 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     const int32_t pred = (int32_t)(uint32_t)(unsigned long long)(sum >> shift);   // `as i32`
                     const int32_t rr = (int32_t)((uint32_t)x[e] - (uint32_t)pred);
                     rl[e] = rr;
-                    om |= (((uint32_t)((x[e] ^ pred) & (x[e] ^ rr))) >> 31) << e;   // checked_sub: sign bit set when it overflowed
-                    o16 |= ((((uint32_t)rr + 0x8000u) & 0xFFFF0000u) ? 1u : 0u) << e;
+                    oacc |= (uint32_t)((x[e] ^ pred) & (x[e] ^ rr));   // checked_sub: sign bit set when it overflowed
+                    sacc |= (uint32_t)rr + 0x8000u;
                 }
                 if (stage < 2) {
-                    if (om | o16) {   // only samples in [order, n) count
+                    if (((oacc >> 31) | (sacc >> 16)) != 0) {   // rare: look again, only samples in [order, n) count
                         const uint32_t first = order > i0 ? min(order - i0, 16u) : 0u, last = min(16u, n - i0);
-                        const uint32_t valid = (last >= 16 ? 0xFFFFu : (1u << last) - 1u) & ~((1u << first) - 1u);
-                        if (om & valid) ovf = 1;
-                        if (o16 & valid) b16 = 1;
+#pragma unroll
+                        for (int e = 0; e < 16; e++) {
+                            if ((uint32_t)e < first || (uint32_t)e >= last) continue;
+                            const int32_t pred = (int32_t)((uint32_t)x[e] - (uint32_t)rl[e]);
+                            if (((x[e] ^ pred) & (x[e] ^ rl[e])) < 0) ovf = 1;
+                            if (((uint32_t)rl[e] + 0x8000u) >> 16) b16 = 1;
+                        }
                     }
                     // park the residuals as int16 pairs (two 16-byte chunks per tile, conflict-free for 32 consecutive tiles)
                     uint4 lo4, hi4;
@@ -318,9 +344,10 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                 const uint32_t pf = i0 / cpf;
                 const uint32_t codef = chf.rice[pf - j0f >= chf.nparts ? 0 : pf - j0f];
                 if (!tail && i0 != 0 && (cpf16 || (i0 + 15) / cpf == pf) && codef < 0x40) {
+                    uint32_t ta[4] = {0, 0, 0, 0};   // |rf| <= 2^28 here (25-bit samples): four shifted zig-zags fit 32 bits
 #pragma unroll
-                    for (int e = 0; e < 16; e++) bits_f = acc_u32(bits_f, zigzag32(rf[e]) >> codef);
-                    bits_f += 16u * (1u + codef);
+                    for (int e = 0; e < 16; e++) ta[e >> 2] += zigzag32(rf[e]) >> codef;
+                    bits_f += ((unsigned long long)ta[0] + ta[1]) + ((unsigned long long)ta[2] + ta[3]) + 16u * (1u + codef);
                 } else {
                     int32_t tmp[16];
 #pragma unroll
@@ -336,9 +363,16 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     const uint32_t pl = i0 / cpl;
                     const uint32_t codel = chl.rice[pl - j0l >= chl.nparts ? 0 : pl - j0l];
                     if (!tail && i0 != 0 && (cpl16 || (i0 + 15) / cpl == pl) && codel < 0x40) {
+                        if (use16) {   // |rl| < 2^15: the whole tile fits 32 bits
+                            uint32_t ta = 0;
 #pragma unroll
-                        for (int e = 0; e < 16; e++) bits_l = acc_u32(bits_l, zigzag32(rl[e]) >> codel);
-                        bits_l += 16u * (1u + codel);
+                            for (int e = 0; e < 16; e++) ta += zigzag32(rl[e]) >> codel;
+                            bits_l += ta + 16u * (1u + codel);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; e++) bits_l = acc_u32(bits_l, zigzag32(rl[e]) >> codel);
+                            bits_l += 16u * (1u + codel);
+                        }
                     } else {
                         int32_t tmp[16];
 #pragma unroll
@@ -516,11 +550,11 @@ __global__ void __launch_bounds__(32 * A3_WPC * (STEREO ? 4 : 2), STEREO ? 2 : 4
                              cands_sm[cand], rec);
 }
 
-// per-tile 32-bit sums of the fixed residuals need |x| < 2^25 (see pass 1)
+// the 32-bit per-tile sums of the fixed residuals (passes 1 and 2) need |x| < 2^24: 24-bit stereo with its 25-bit side
 bool analyze3_ok(const EncCfg& cfg)
 {
     const uint32_t widest = cfg.bps + (cfg.mode != MODE_INDEPENDENT ? 1u : 0u);
-    return analyze_fast_ok(cfg) && widest <= 26;
+    return analyze_fast_ok(cfg) && widest <= 25;
 }
 
 cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const LpcRec* lpcs, CandRec* cands,

@@ -21,9 +21,12 @@ bool analyze_fast_ok(const EncCfg& cfg);   // encode_kernels.cu
 
 __device__ Crc16Tables g_crc16_tabs;   // built once per device by k_crc16_tables_init
 
+__device__ uint16_t g_crc16_xblk[1024];   // x^(1024 j) mod P: shifts a CRC over j blocks of 32 words
+
 __global__ void k_crc16_tables_init()
 {
     crc16_tables_init(g_crc16_tabs);
+    for (uint32_t j = threadIdx.x; j < 1024; j += blockDim.x) g_crc16_xblk[j] = (uint16_t)gf16_xpow8(128 * j);
 }
 
 // OR the low nbits (1..32) of v into the big-endian bit image `words` at bit position pos
@@ -32,8 +35,14 @@ __device__ inline void p3_put(uint32_t* words, uint32_t pos, uint32_t nbits, uin
     const uint32_t w = pos >> 5, off = pos & 31;
     const unsigned long long wide = ((unsigned long long)v) << (64u - nbits - off);
     const uint32_t hi = (uint32_t)(wide >> 32), lo = (uint32_t)wide;
-    if (hi) atomicOr(words + w, hi);
-    if (lo) atomicOr(words + w + 1, lo);
+    // reductions without a return value; the second word is touched only when the code straddles (predicated, no branch)
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(words + w);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "red.shared.or.b32 [%0], %1;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p red.shared.or.b32 [%0+4], %2;\n\t}"
+        ::"r"(a), "r"(hi), "r"(lo) : "memory");
 }
 
 __device__ inline void p3_put_masked(uint32_t* words, uint32_t pos, uint32_t nbits, uint32_t v)
@@ -302,7 +311,12 @@ __global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words
             uint32_t crc = 0;
             for (uint32_t w = 0; w < nwarps; w++) {
                 const uint32_t wa = min(w * per, bw), wb = min(wa + per, bw);
-                if (wb > wa) crc = gf16_mulmod(crc, gf16_xpow8((wb - wa) * 4)) ^ sm.crc_part[w];
+                if (wb > wa) {   // ranges are whole blocks of 32 words except the last: shift by the table, then by the odd words
+                    const uint32_t len = wb - wa;
+                    crc = gf16_mulmod(crc, g_crc16_xblk[len >> 5]);
+                    if (len & 31u) crc = gf16_mulmod(crc, sm.tabs.xd[len & 31u]);
+                    crc ^= sm.crc_part[w];
+                }
             }
             for (uint32_t t = 0; t < btail; t++) crc = crc16_byte(sm.tabs, crc, (p3_words[bw] >> (24 - 8 * t)) & 0xff);
             p3_put(p3_words, body * 8, 16, crc);

@@ -102,10 +102,8 @@ static __device__ __noinline__ void aw_pass1_tile_slow(const int32_t* x, const i
 
 __device__ inline void aw_add_limbs(uint32_t* lo, uint32_t* hi, uint32_t chunk, unsigned long long v)
 {
-    if (v) {
-        atomicAdd(&lo[chunk], (uint32_t)v & 0xFFFFFFu);
-        atomicAdd(&hi[chunk], (uint32_t)(v >> 24));
-    }
+    atomicAdd(&lo[chunk], (uint32_t)v & 0xFFFFFFu);   // unconditional: a branch costs more than an atomic that adds 0
+    atomicAdd(&hi[chunk], (uint32_t)(v >> 24));
 }
 
 // best_partitions + try_reduce_rice (src/encode.rs:3865-3942) for one residual set, by one warp.
