@@ -225,6 +225,22 @@ __device__ inline unsigned long long acc_u32(unsigned long long acc, uint32_t v)
 }
 
 // ---- misc ------------------------------------------------------------------------------------
+// f64::total_cmp ordering key
+__device__ inline long long total_key(double v)
+{
+    long long x = __double_as_longlong(v);
+    x ^= (long long)((unsigned long long)(x >> 63) >> 1);
+    return x;
+}
+
+__device__ inline int32_t f64_as_i32_sat(double v)
+{
+    if (v != v) return 0;
+    if (v >= 2147483647.0) return 2147483647;
+    if (v <= -2147483648.0) return (-2147483647 - 1);
+    return (int32_t)v;
+}
+
 __host__ __device__ inline uint32_t lpc_precision_for(uint32_t n)   // src/encode.rs:3305-3315
 {
     return n <= 192 ? 7 : n <= 384 ? 8 : n <= 576 ? 9 : n <= 1152 ? 10 : n <= 2304 ? 11 : n <= 4608 ? 12 : 13;

@@ -111,22 +111,6 @@ __device__ inline void levinson(const double* R, int upto, double* ca, double* c
     *cur = a;
 }
 
-// f64::total_cmp ordering key
-__device__ inline long long total_key(double v)
-{
-    long long x = __double_as_longlong(v);
-    x ^= (long long)((unsigned long long)(x >> 63) >> 1);
-    return x;
-}
-
-__device__ inline int32_t f64_as_i32_sat(double v)
-{
-    if (v != v) return 0;
-    if (v >= 2147483647.0) return 2147483647;
-    if (v <= -2147483648.0) return (-2147483647 - 1);
-    return (int32_t)v;
-}
-
 // grid ceil(ncand / LPC_WARPS), block 32 * LPC_WARPS
 __global__ void __launch_bounds__(32 * LPC_WARPS) k_lpc(EncCfg cfg, const FrameDesc* __restrict__ descs, const int32_t* __restrict__ planes,
                                                        const uint32_t* __restrict__ ormask, const unsigned long long* __restrict__ abssum,

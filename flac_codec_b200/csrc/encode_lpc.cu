@@ -1,0 +1,308 @@
+// encode_lpc.cu -- k_lpc3: LpcParameters::best (src/encode.rs:3292-3332) for stereo frames straight from the packed
+// PCM, with the global loads taken out of the FP64 loop by an asynchronous staging pipeline.
+//
+// Same arithmetic as k_lpc2 (encode_fast.inl): the reference's autocorrelation is a strict left-to-right f64 sum per lag
+// (:3491-3497), so each lag is one sequential chain of separately rounded DMUL + DADD; a lane owns FOUR consecutive lags
+// of one candidate, four lanes make a candidate, a warp runs the 8 candidates (L, R, M, S of two frames) from per-candidate
+// rings of windowed samples in shared memory (four 32-sample tiles + mirrors of two).
+//
+// What is new: a tile's raw PCM bytes (32 samples x 2 channels) and its window values travel global -> shared with
+// cp.async (16-byte chunks, zero-filled past the block end) into a two-slot staging area per warp, two tiles ahead of the
+// tile being computed; the lanes never wait on a global load inside the FP64 loop (k_lpc2 spent a third of its stall
+// cycles there), and no registers are held for prefetched samples.
+#include "common.cuh"
+#include "tiles.cuh"
+
+namespace flacb200 {
+
+constexpr int L3_WARPS = 5;       // 5 warps x 14.4 KB: three CTAs per SM
+constexpr int L3_RING = 192;      // 4 tiles + mirrors of tiles 0 and 1
+constexpr int L3_CD = L3_RING + 1;   // doubles per candidate (+ 1: bank skew between candidates)
+constexpr int L3_CANDS = 8;       // candidates per warp = two stereo frames
+constexpr int L3_STAGE_BYTES = 2 * 2 * 512;   // 2 slots x 2 frames x (256 B PCM + 256 B window)
+
+__device__ inline void l3_cp16(uint32_t dst, const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ inline void l3_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ inline void l3_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// dynamic smem: L3_WARPS * (L3_CANDS * L3_CD * 8 + L3_STAGE_BYTES) bytes
+__global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
+                                                         const double* __restrict__ winpool, LpcRec* __restrict__ out, uint32_t nframes)
+{
+    extern __shared__ __align__(16) uint8_t l3_dyn[];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t M = cfg.max_lpc_order;
+    const uint32_t f0 = (blockIdx.x * L3_WARPS + wid) * 2;   // first frame of this warp
+    if (f0 >= nframes) return;
+    const uint32_t nfr = min(2u, nframes - f0);
+    uint8_t* wsm = l3_dyn + (size_t)wid * (L3_CANDS * L3_CD * 8 + L3_STAGE_BYTES);
+    double* wbase = reinterpret_cast<double*>(wsm);
+    uint8_t* stage = wsm + L3_CANDS * L3_CD * 8;
+    const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t g = lane >> 2, m = lane & 3;   // candidate, lag group
+    const bool live = g < nfr * 4;
+    const uint32_t B = cfg.bytes_per_sample, TB = 64 * B;   // bytes of one 32-sample stereo tile
+    const bool big = cfg.pcm_kind == 1;
+    // the warp's two frames
+    const uint8_t* fp[2];
+    const double* wp[2];
+    uint32_t fn[2];
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        const FrameDesc d = descs[f0 + ((uint32_t)f < nfr ? f : 0)];
+        fp[f] = pcm + d.pcm_off * (unsigned long long)(2 * B);
+        wp[f] = winpool + d.win_off;
+        fn[f] = ((uint32_t)f < nfr && d.n > M) ? d.n : 0u;   // n <= M: InsufficientLpcSamples (:3300), nothing to analyse
+    }
+    if (lane < nfr * 4) out[(size_t)f0 * 4 + lane].ok = 0;
+    const uint32_t nmax = max(fn[0], fn[1]);
+    const uint32_t ntiles = (nmax + 31) / 32;
+    const uint32_t per_frame = 4 * B + 16;   // 16-byte chunks per frame and tile: PCM, then window
+
+    // global -> staging slot (tile & 1); bytes past the end of the block are zero-filled
+    auto issue = [&](uint32_t tile) {
+        const uint32_t slot_sa = stage_sa + (tile & 1u) * 1024u;
+        for (uint32_t c = lane; c < 2 * per_frame; c += 32) {
+            const uint32_t f = c >= per_frame ? 1u : 0u, k = c - f * per_frame;
+            const uint32_t nf = f ? fn[1] : fn[0];
+            if (k < 4 * B) {
+                const uint8_t* src = f ? fp[1] : fp[0];
+                const uint32_t off = tile * TB + k * 16, total = nf * 2 * B;
+                const uint32_t bytes = off < total ? min(16u, total - off) : 0u;
+                l3_cp16(slot_sa + f * 512 + k * 16, src + (bytes ? off : 0u), bytes);
+            } else {
+                const double* src = f ? wp[1] : wp[0];
+                const uint32_t kk = k - 4 * B, i = tile * 32 + kk * 2;
+                const uint32_t bytes = i < nf ? min(16u, (nf - i) * 8) : 0u;
+                l3_cp16(slot_sa + f * 512 + 256 + kk * 16, src + (bytes ? i : 0u), bytes);
+            }
+        }
+        l3_commit();
+    };
+
+    uint32_t shift_mask = 0;   // bit c: candidate c must be redone with its wasted bits shifted out
+    uint32_t wasted_of[L3_CANDS], masks[L3_CANDS];
+#pragma unroll
+    for (int c = 0; c < L3_CANDS; c++) { wasted_of[c] = 0; masks[c] = 0; }
+    double acc0 = -0.0, acc1 = -0.0, acc2 = -0.0, acc3 = -0.0;   // Iterator::sum::<f64>() folds from -0.0
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1 && shift_mask == 0) break;
+        // staging slot -> the 8 rings: Frame::fill_from_buf (src/audio.rs:149-187), decorrelation (:2721, :2734), Window::apply (:1799)
+        auto store = [&](uint32_t tile) {
+            const uint8_t* slot = stage + (tile & 1u) * 1024u;
+            const uint32_t pos = (tile & 3) * 32 + lane;
+            const uint32_t sh = 32 - 8 * B;
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+                const uint16_t* p16 = reinterpret_cast<const uint16_t*>(slot + f * 512 + lane * 2 * B);
+                uint32_t raw[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((uint32_t)k < B) raw[k] = p16[k];
+                const double wv = *reinterpret_cast<const double*>(slot + f * 512 + 256 + lane * 8);
+                const unsigned long long wide = (unsigned long long)(raw[0] | (raw[1] << 16)) | ((unsigned long long)(raw[2] | (raw[3] << 16)) << 32);
+                const uint32_t lw = (uint32_t)wide, rw = (uint32_t)(wide >> (8 * B));   // low B bytes: the sample in memory order
+                int32_t l, r;
+                if (big) {
+                    l = (int32_t)__byte_perm(lw, 0, 0x0123) >> sh;
+                    r = (int32_t)__byte_perm(rw, 0, 0x0123) >> sh;
+                } else {
+                    l = (int32_t)(lw << sh) >> sh;
+                    r = (int32_t)(rw << sh) >> sh;
+                }
+                const int32_t px[4] = {l, r, (l + r) >> 1, l - r};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = f * 4 + k;
+                    if (pass == 1 && !((shift_mask >> c) & 1u)) continue;
+                    if (pass == 0) masks[c] |= (uint32_t)px[k];
+                    const double v = __dmul_rn((double)(px[k] >> wasted_of[c]), wv);
+                    double* ring = wbase + (size_t)c * L3_CD;
+                    ring[pos] = v;
+                    if ((tile & 3) < 2) ring[128 + pos] = v;   // mirrors of tiles 0 and 1 (mod 4)
+                }
+            }
+        };
+        // prologue: tiles 0..2 into the rings, tile 3 in flight
+        issue(0);
+        issue(1);
+        l3_wait<0>();
+        __syncwarp();
+        store(0);
+        store(1);
+        __syncwarp();
+        issue(2);
+        issue(3);
+        l3_wait<1>();
+        __syncwarp();
+        store(2);
+        __syncwarp();
+        acc0 = acc1 = acc2 = acc3 = -0.0;
+        const double* ring = wbase + (size_t)g * L3_CD;
+        for (uint32_t t = 0; t < ntiles; t++) {
+            issue(t + 4);   // lands two tiles of FP64 work later
+            const double* pa = ring + (t & 3) * 32;
+            const double* pb = pa + 4 * m;
+            double b0 = pb[0], b1 = pb[1], b2 = pb[2];
+#pragma unroll
+            for (int s = 0; s < 32; s++) {   // autocorrelate :3491-3497, four lags per lane
+                const double a = pa[s], b3 = pb[s + 3];
+                acc0 = __dadd_rn(acc0, __dmul_rn(a, b0));
+                acc1 = __dadd_rn(acc1, __dmul_rn(a, b1));
+                acc2 = __dadd_rn(acc2, __dmul_rn(a, b2));
+                acc3 = __dadd_rn(acc3, __dmul_rn(a, b3));
+                b0 = b1; b1 = b2; b2 = b3;
+            }
+            l3_wait<1>();   // tile t + 3 has landed (only tile t + 4 may still be in flight)
+            __syncwarp();
+            store(t + 3);   // replaces tile t - 1; tiles t + 1 and t + 2 stay resident
+            __syncwarp();
+        }
+        l3_wait<0>();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < L3_CANDS; c++) masks[c] = __reduce_or_sync(0xffffffffu, masks[c]);
+        // the rings are dead now: R[] goes on top of them
+        const bool mine_redo = (shift_mask >> g) & 1u;
+        if (live && (pass == 0 || mine_redo)) {
+            double* Rg = wbase + (size_t)g * L3_CD;
+            if (4 * m + 0 <= M) Rg[4 * m + 0] = acc0;
+            if (4 * m + 1 <= M) Rg[4 * m + 1] = acc1;
+            if (4 * m + 2 <= M) Rg[4 * m + 2] = acc2;
+            if (4 * m + 3 <= M) Rg[4 * m + 3] = acc3;
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int c = 0; c < L3_CANDS; c++) {
+                const uint32_t mk = masks[c];
+                wasted_of[c] = (mk == 0 || (mk & 1u)) ? 0u : (uint32_t)__ffs((int)mk) - 1u;   // :2878-2898
+                if (wasted_of[c]) shift_mask |= 1u << c;
+            }
+        }
+        __syncwarp();
+    }
+    // a second pass rebuilds only the rings of the shifted candidates (store skips the others), so the R[] that the
+    // untouched candidates parked on top of their own rings is still intact here
+    __syncwarp();
+    // ---- per candidate: Levinson-Durbin on the group's first lane, order estimate on all its lanes ----
+    double* base = wbase + (size_t)g * L3_CD;
+    double* Rv = base;              // M + 1
+    double* errv = Rv + (M + 1);    // M
+    double* bitsv = errv + M;       // M
+    double* sets = bitsv + M;       // M (M + 1) / 2: coefficient set of every order, triangular
+    uint32_t mask = 0, wasted = 0;
+#pragma unroll
+    for (int c = 0; c < L3_CANDS; c++)
+        if ((uint32_t)c == g) { mask = masks[c]; wasted = wasted_of[c]; }
+    const uint32_t cand = f0 * 4 + g;
+    const uint32_t n = (g >> 2) ? fn[1] : fn[0];
+    const bool run = live && mask != 0 && n > M;   // all-zero candidates become CONSTANT (:2883)
+    const uint32_t bps = cand_bps(cfg, g & 3) - wasted;
+    const uint32_t precision = lpc_precision_for(n);
+    if (run && m == 0) {   // lp_coefficients (:3536-3580), every order's set kept
+        const double* R = Rv;
+        double* a = sets;   // order 1
+        double k = __ddiv_rn(R[1], R[0]);
+        a[0] = k;
+        errv[0] = __dmul_rn(R[0], __dsub_rn(1.0, __dmul_rn(k, k)));
+        for (uint32_t i = 1; i < M; i++) {
+            double* b = a + i;   // the set of order i + 1 follows the i entries of order i
+            double s = -0.0;
+            for (uint32_t j = 0; j < i; j++) s = __dadd_rn(s, __dmul_rn(R[i - j], a[j]));
+            const double q = __dsub_rn(R[i + 1], s);
+            k = __ddiv_rn(q, errv[i - 1]);
+            for (uint32_t j = 0; j < i; j++) b[j] = __dsub_rn(a[j], __dmul_rn(k, a[i - 1 - j]));
+            b[i] = k;
+            errv[i] = __dmul_rn(errv[i - 1], __dsub_rn(1.0, __dmul_rn(k, k)));
+            a = b;
+        }
+    }
+    __syncwarp();
+    if (run) {   // subframe_bits_by_order (:3656-3686): this lane's orders 4m + 1 .. 4m + 4
+        const double error_scale = __ddiv_rn(0.5, (double)n);
+        const double divisor = 2.0 * 0.693147180559945309417232121458176568;
+        for (uint32_t o = 4 * m + 1; o <= min(4 * m + 4, M); o++) {
+            const double bpr = __ddiv_rn(log(__dmul_rn(errv[o - 1], error_scale)), divisor);
+            bitsv[o - 1] = fma(bpr, (double)(n - o), (double)(o * (bps + precision)));
+        }
+    }
+    __syncwarp();
+    if (run && m == 0) {
+        int best = 0;   // compute_best_order (:3688-3702): take_while(err > 0), first minimum under total_cmp
+        double best_bits = 0.0;
+        for (uint32_t o = 1; o <= M; o++) {
+            if (!(errv[o - 1] > 0.0)) break;
+            const double b = bitsv[o - 1];
+            if (best == 0 || total_key(b) < total_key(best_bits)) { best = (int)o; best_bits = b; }
+        }
+        if (best != 0) {
+            const double* cur = sets + (size_t)best * (best - 1) / 2;
+            // quantize (:3334-3401)
+            double l = fabs(cur[0]);
+            for (int j = 1; j < best; j++) {
+                const double a = fabs(cur[j]);
+                if (total_key(a) >= total_key(l)) l = a;
+            }
+            if (l > 0.0) {
+                const int32_t max_coeff = (1 << (precision - 1)) - 1, min_coeff = -(1 << (precision - 1));
+                const int32_t lg = f64_as_i32_sat(floor(log2(l)));
+                long long sh = (long long)((int32_t)precision - 1) - (long long)lg - 1;   // :3360
+                if (sh > 15) sh = 15;
+                if (sh >= -16) {
+                    LpcRec rec;
+                    double error = 0.0;
+                    if (sh >= 0) {
+                        const double scale = (double)(1 << sh);
+                        for (int j = 0; j < best; j++) {
+                            const double sum = fma(cur[j], scale, error);   // mul_add :3372
+                            int32_t q = f64_as_i32_sat(round(sum));
+                            q = q < min_coeff ? min_coeff : (q > max_coeff ? max_coeff : q);
+                            error = __dsub_rn(sum, (double)q);
+                            rec.q[j] = (int16_t)q;
+                        }
+                        rec.shift = (uint8_t)sh;
+                    } else {
+                        const double scale = (double)(1 << (-sh));
+                        for (int j = 0; j < best; j++) {
+                            const double sum = __dadd_rn(__ddiv_rn(cur[j], scale), error);   // :3391
+                            int32_t q = f64_as_i32_sat(round(sum));
+                            q = q < min_coeff ? min_coeff : (q > max_coeff ? max_coeff : q);
+                            error = __dsub_rn(sum, (double)q);
+                            rec.q[j] = (int16_t)q;
+                        }
+                        rec.shift = 0;
+                    }
+                    for (int j = best; j < MAX_LPC; j++) rec.q[j] = 0;
+                    rec.ok = 1;
+                    rec.order = (uint8_t)best;
+                    rec.precision = (uint8_t)precision;
+                    rec.pad = 0;
+                    out[cand] = rec;
+                }
+            }
+        }
+    }
+}
+
+// stereo frames (L, R, M, S slots), packed byte PCM, 16-byte aligned blocks, order <= 15 (four lanes x four lags)
+bool lpc3_ok(const EncCfg& cfg, bool blocks_aligned16)
+{
+    return cfg.mode != MODE_INDEPENDENT && cfg.nslots == 4 && cfg.pcm_kind <= 1 && cfg.max_lpc_order >= 1 && cfg.max_lpc_order <= 15 &&
+           blocks_aligned16;
+}
+
+cudaError_t launch_lpc3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const double* winpool, LpcRec* lpcs, cudaStream_t st)
+{
+    const size_t smem = (size_t)L3_WARPS * (L3_CANDS * L3_CD * 8 + L3_STAGE_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_lpc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t nwarps = (cfg.nframes + 1) / 2;
+    k_lpc3<<<(nwarps + L3_WARPS - 1) / L3_WARPS, 32 * L3_WARPS, smem, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes);
+    return cudaGetLastError();
+}
+
+}   // namespace flacb200

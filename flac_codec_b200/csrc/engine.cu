@@ -27,6 +27,8 @@ void launch_decide_scan(const EncCfg&, const FrameDesc*, const CandRec*, const u
                         unsigned long long*, uint8_t*, bool, cudaStream_t);
 bool pack3_ok(const EncCfg&);
 bool analyze3_ok(const EncCfg&);
+bool lpc3_ok(const EncCfg&, bool);
+cudaError_t launch_lpc3(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, cudaStream_t);
 cudaError_t launch_analyze3(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, cudaStream_t);
 cudaError_t launch_pack3(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
@@ -364,6 +366,8 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     for (size_t s = 0; s < n_segments; s++) want += (segments[s].n_pcm_frames + bs - 1) / bs;
     descs.reserve(want);
     uint32_t win_n = 0, win_o = 0;   // the window table is looked up once per distinct block length, not per frame
+    uint64_t misalign = 0;           // OR of every block's byte offset: k_lpc3 copies 16-byte chunks
+    const uint64_t pcm_frame_bytes = (uint64_t)cfg.channels * cfg.bytes_per_sample;
     for (size_t s = 0; s < n_segments; s++) {
         const flacb200_segment& sg = segments[s];
         uint64_t done = 0, fn = sg.first_frame_number;
@@ -379,6 +383,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
             d.fnum = fn++;
             d.n = n;
             d.win_off = win_o;
+            misalign |= d.pcm_off * pcm_frame_bytes;
             descs.push_back(d);
             done += n;
         }
@@ -473,6 +478,8 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         d_pcm = (const uint8_t*)pcm;
     }
     // frames go straight into the caller's device buffer when it can hold the worst case
+    // k_lpc3: cp.async staging needs every block of the (packed, stereo) PCM on a 16-byte boundary
+    const bool staged_lpc = fast_lpc && !(legacy & 32u) && lpc3_ok(cfg, ((misalign | (uint64_t)(uintptr_t)d_pcm) & 15u) == 0);
     uint8_t* d_out = (uint8_t*)e->out.p;
     const bool direct_out = out && out_location == FLACB200_DEVICE && out_capacity >= bound + 64 && ((uintptr_t)out & 15) == 0;
     if (direct_out) d_out = (uint8_t*)out;
@@ -504,7 +511,8 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         time_mark(e, eb + 0);
         if (need_planes) launch_planes(c, dd, d_pcm, (int32_t*)e->planes.p, d_ormask, d_abssum, st);
         time_mark(e, eb + 1);
-        if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st));
+        if (staged_lpc) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st));
+        else if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st));
         else launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st);
         time_mark(e, eb + 2);
         if (frame_analyze) CK(launch_analyze3(c, dd, d_pcm, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p, d_abssum, st));
