@@ -17,7 +17,7 @@ namespace flacb200 {
 
 constexpr int L3_WARPS = 5;       // 5 warps x 14.4 KB: three CTAs per SM
 constexpr int L3_RING = 192;      // 4 tiles + mirrors of tiles 0 and 1
-constexpr int L3_CD = L3_RING + 1;   // doubles per candidate (+ 1: bank skew between candidates)
+constexpr int L3_CD = L3_RING + 2;   // doubles per candidate (+ 2: bank skew between candidates that keeps 16-byte alignment)
 constexpr int L3_CANDS = 8;       // candidates per warp = two stereo frames
 constexpr int L3_STAGE_BYTES = 2 * 2 * 512;   // 2 slots x 2 frames x (256 B PCM + 256 B window)
 
@@ -63,23 +63,34 @@ __global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const Fra
     const uint32_t ntiles = (nmax + 31) / 32;
     const uint32_t per_frame = 4 * B + 16;   // 16-byte chunks per frame and tile: PCM, then window
 
-    // global -> staging slot (tile & 1); bytes past the end of the block are zero-filled
+    // global -> staging slot (tile & 1); bytes past the end of the block are zero-filled.  A lane copies the same (at most
+    // two) 16-byte chunks of every tile: chunk c of the 2 * per_frame chunks is PCM (k < 4 B) or window of frame c / per_frame.
+    const uint8_t* csrc[2];
+    uint32_t cdst[2], cstride[2], ctotal[2], coff[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t c = lane + 32 * j;
+        const bool on = c < 2 * per_frame;
+        const uint32_t f = c >= per_frame ? 1u : 0u, k = c - f * per_frame;
+        const uint32_t nf = f ? fn[1] : fn[0];
+        if (k < 4 * B) {
+            csrc[j] = f ? fp[1] : fp[0];
+            cdst[j] = f * 512 + k * 16; cstride[j] = TB; coff[j] = k * 16; ctotal[j] = on ? nf * 2 * B : 0u;
+        } else {
+            const uint32_t kk = k - 4 * B;
+            csrc[j] = reinterpret_cast<const uint8_t*>(f ? wp[1] : wp[0]);
+            cdst[j] = f * 512 + 256 + kk * 16; cstride[j] = 256; coff[j] = kk * 16; ctotal[j] = on ? nf * 8 : 0u;
+        }
+    }
+    const bool two = lane + 32 < 2 * per_frame;
     auto issue = [&](uint32_t tile) {
         const uint32_t slot_sa = stage_sa + (tile & 1u) * 1024u;
-        for (uint32_t c = lane; c < 2 * per_frame; c += 32) {
-            const uint32_t f = c >= per_frame ? 1u : 0u, k = c - f * per_frame;
-            const uint32_t nf = f ? fn[1] : fn[0];
-            if (k < 4 * B) {
-                const uint8_t* src = f ? fp[1] : fp[0];
-                const uint32_t off = tile * TB + k * 16, total = nf * 2 * B;
-                const uint32_t bytes = off < total ? min(16u, total - off) : 0u;
-                l3_cp16(slot_sa + f * 512 + k * 16, src + (bytes ? off : 0u), bytes);
-            } else {
-                const double* src = f ? wp[1] : wp[0];
-                const uint32_t kk = k - 4 * B, i = tile * 32 + kk * 2;
-                const uint32_t bytes = i < nf ? min(16u, (nf - i) * 8) : 0u;
-                l3_cp16(slot_sa + f * 512 + 256 + kk * 16, src + (bytes ? i : 0u), bytes);
-            }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (j == 1 && !two) break;
+            const uint32_t off = tile * cstride[j] + coff[j];
+            const uint32_t bytes = off < ctotal[j] ? min(16u, ctotal[j] - off) : 0u;
+            l3_cp16(slot_sa + cdst[j], csrc[j] + (bytes ? off : 0u), bytes);
         }
         l3_commit();
     };
@@ -96,6 +107,7 @@ __global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const Fra
             const uint8_t* slot = stage + (tile & 1u) * 1024u;
             const uint32_t pos = (tile & 3) * 32 + lane;
             const uint32_t sh = 32 - 8 * B;
+            const bool mirror = (tile & 3) < 2;   // mirrors of tiles 0 and 1 (mod 4)
 #pragma unroll
             for (int f = 0; f < 2; f++) {
                 const uint16_t* p16 = reinterpret_cast<const uint16_t*>(slot + f * 512 + lane * 2 * B);
@@ -115,15 +127,26 @@ __global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const Fra
                     r = (int32_t)(rw << sh) >> sh;
                 }
                 const int32_t px[4] = {l, r, (l + r) >> 1, l - r};
+                if (pass == 0) {   // common pass: no wasted bits assumed, OR masks gathered on the fly
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int c = f * 4 + k;
-                    if (pass == 1 && !((shift_mask >> c) & 1u)) continue;
-                    if (pass == 0) masks[c] |= (uint32_t)px[k];
-                    const double v = __dmul_rn((double)(px[k] >> wasted_of[c]), wv);
-                    double* ring = wbase + (size_t)c * L3_CD;
-                    ring[pos] = v;
-                    if ((tile & 3) < 2) ring[128 + pos] = v;   // mirrors of tiles 0 and 1 (mod 4)
+                    for (int k = 0; k < 4; k++) {
+                        const int c = f * 4 + k;
+                        masks[c] |= (uint32_t)px[k];
+                        const double v = __dmul_rn((double)px[k], wv);
+                        double* ring = wbase + (size_t)c * L3_CD;
+                        ring[pos] = v;
+                        if (mirror) ring[128 + pos] = v;
+                    }
+                } else {           // rare pass: only the candidates that have wasted bits, shifted (:2891)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int c = f * 4 + k;
+                        if (!((shift_mask >> c) & 1u)) continue;
+                        const double v = __dmul_rn((double)(px[k] >> wasted_of[c]), wv);
+                        double* ring = wbase + (size_t)c * L3_CD;
+                        ring[pos] = v;
+                        if (mirror) ring[128 + pos] = v;
+                    }
                 }
             }
         };
@@ -147,15 +170,21 @@ __global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const Fra
             issue(t + 4);   // lands two tiles of FP64 work later
             const double* pa = ring + (t & 3) * 32;
             const double* pb = pa + 4 * m;
-            double b0 = pb[0], b1 = pb[1], b2 = pb[2];
+            const double2 b01 = *reinterpret_cast<const double2*>(pb), b23 = *reinterpret_cast<const double2*>(pb + 2);
+            double b0 = b01.x, b1 = b01.y, b2 = b23.x, b3 = b23.y;
 #pragma unroll
-            for (int s = 0; s < 32; s++) {   // autocorrelate :3491-3497, four lags per lane
-                const double a = pa[s], b3 = pb[s + 3];
-                acc0 = __dadd_rn(acc0, __dmul_rn(a, b0));
-                acc1 = __dadd_rn(acc1, __dmul_rn(a, b1));
-                acc2 = __dadd_rn(acc2, __dmul_rn(a, b2));
-                acc3 = __dadd_rn(acc3, __dmul_rn(a, b3));
-                b0 = b1; b1 = b2; b2 = b3;
+            for (int s = 0; s < 32; s += 2) {   // autocorrelate :3491-3497, four lags per lane, two samples per 128-bit load
+                const double2 a = *reinterpret_cast<const double2*>(pa + s);
+                const double2 bn = *reinterpret_cast<const double2*>(pb + s + 4);
+                acc0 = __dadd_rn(acc0, __dmul_rn(a.x, b0));
+                acc1 = __dadd_rn(acc1, __dmul_rn(a.x, b1));
+                acc2 = __dadd_rn(acc2, __dmul_rn(a.x, b2));
+                acc3 = __dadd_rn(acc3, __dmul_rn(a.x, b3));
+                acc0 = __dadd_rn(acc0, __dmul_rn(a.y, b1));
+                acc1 = __dadd_rn(acc1, __dmul_rn(a.y, b2));
+                acc2 = __dadd_rn(acc2, __dmul_rn(a.y, b3));
+                acc3 = __dadd_rn(acc3, __dmul_rn(a.y, bn.x));
+                b0 = b2; b1 = b3; b2 = bn.x; b3 = bn.y;
             }
             l3_wait<1>();   // tile t + 3 has landed (only tile t + 4 may still be in flight)
             __syncwarp();
