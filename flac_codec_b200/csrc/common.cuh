@@ -225,6 +225,19 @@ __device__ inline unsigned long long acc_u32(unsigned long long acc, uint32_t v)
 }
 
 // ---- misc ------------------------------------------------------------------------------------
+// division by a warp-uniform runtime divisor that is nearly always a power of two (partition sizes n >> p)
+struct UDiv {
+    uint32_t d, sh;   // sh = log2(d) when d is a power of two, else 32
+};
+__device__ inline UDiv udiv_make(uint32_t d)
+{
+    UDiv u;
+    u.d = d;
+    u.sh = (d != 0 && (d & (d - 1)) == 0) ? 31u - (uint32_t)__clz((int)d) : 32u;
+    return u;
+}
+__device__ inline uint32_t udiv(uint32_t x, UDiv u) { return u.sh < 32 ? x >> u.sh : x / u.d; }
+
 // f64::total_cmp ordering key
 __device__ inline long long total_key(double v)
 {

@@ -255,16 +255,20 @@ struct BitReader {
     uint32_t cnt;
     uint32_t err;
 
-    __device__ inline void load_vec(unsigned long long vidx)
+    uint4 qn;   // the vector after q, requested one vector (128 bits of stream) before it is needed
+    __device__ inline uint4 read_vec(unsigned long long vidx) const
     {
         const unsigned long long b = vidx << 4;
-        if (b + 16 <= nbytes) q = *reinterpret_cast<const uint4*>(bytes + b);
-        else {
-            uint32_t t[4] = {0, 0, 0, 0};
-            for (uint32_t i = 0; i < 16; i++)
-                if (b + i < nbytes) t[i >> 2] |= (uint32_t)bytes[b + i] << (8 * (i & 3));
-            q = make_uint4(t[0], t[1], t[2], t[3]);
-        }
+        if (b + 16 <= nbytes) return *reinterpret_cast<const uint4*>(bytes + b);
+        uint32_t t[4] = {0, 0, 0, 0};
+        for (uint32_t i = 0; i < 16; i++)
+            if (b + i < nbytes) t[i >> 2] |= (uint32_t)bytes[b + i] << (8 * (i & 3));
+        return make_uint4(t[0], t[1], t[2], t[3]);
+    }
+    __device__ inline void load_vec(unsigned long long vidx)   // q = vector vidx (already in flight), qn = the next one
+    {
+        q = qn;
+        qn = read_vec(vidx + 1);
     }
     __device__ inline uint32_t fetch()
     {
@@ -278,6 +282,7 @@ struct BitReader {
     {
         err = 0;
         widx = bitpos >> 5;
+        qn = read_vec(widx >> 2);
         load_vec(widx >> 2);
         const uint32_t hi = fetch_noload(), skip = (uint32_t)(bitpos & 31);
         const uint32_t lo = fetch();
@@ -372,8 +377,175 @@ struct PlaneWriter {
     }
 };
 
+struct ResidualSpec {
+    uint32_t n, order, nres, chunk, porder, hb, esc_code, shift;
+};
+
+// read_residuals (src/decode.rs:1800-1856) + predict (:1738-1752) for one subframe.
+// HB > 0: predictor order <= HB, coefficients and the last HB samples live in registers; samples are produced in blocks
+// of 8 with static register indexing.  HB == 0: no predictor.  HB < 0: any order, rings in shared memory.
+// rare paths of the residual loop
+// Rice code that does not fit the 32-bit window: returns msb, lsb through u
+__device__ inline uint32_t rice_slow(BitReader& br, uint32_t k, uint32_t* u)
+{
+    const uint32_t msb = br.unary();
+    if (br.err) return br.err;
+    *u = (msb << k) | br.get(k);   // src/decode.rs:1827
+    return 0;
+}
+
+// ResidualPartitionHeader (src/stream.rs:1586-1600): returns (mode << 8) | k, or 0xFFFFFFFF past the segment end
+__device__ inline uint32_t partition_header(BitReader& br, uint32_t hb, uint32_t esc_code)
+{
+    uint32_t k = br.get(hb), mode = 0;
+    if (k == esc_code) {
+        k = br.get(5);
+        mode = k ? 1 : 2;
+    }
+    if (br.position() > br.endbit) return 0xFFFFFFFFu;
+    return (mode << 8) | k;
+}
+
+template <int HB>
+__device__ __forceinline__ uint32_t residual_loop_body(BitReader& br, PlaneWriter& pw, const ResidualSpec& rs, int32_t* hist, int16_t* coef);
+
+template <int HB>
+static __device__ __noinline__ uint32_t residual_loop(BitReader& br_io, PlaneWriter& pw_io, const ResidualSpec& rs, int32_t* hist, int16_t* coef)
+{
+    // the reader/writer state is copied into locals whose address never escapes (registers) and written back at the end;
+    // through the references every access would be a local-memory round trip
+    BitReader br = br_io;
+    PlaneWriter pw = pw_io;
+    const uint32_t rc = residual_loop_body<HB>(br, pw, rs, hist, coef);
+    br_io = br;
+    pw_io = pw;
+    return rc;
+}
+
+template <int HB>
+__device__ __forceinline__ uint32_t residual_loop_body(BitReader& br, PlaneWriter& pw, const ResidualSpec& rs, int32_t* hist, int16_t* coef)
+{
+    constexpr int W = HB > 0 ? HB : 1;
+    constexpr int BLK = 4;   // samples per unrolled block = one 128-bit store; the window shifts by BLK registers after each
+    int32_t q[W], w[W + BLK];   // w[W - 1] is the newest sample at the start of a block
+    if (HB > 0) {
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            q[j] = (uint32_t)j < rs.order ? (int32_t)coef[j * DEC_THREADS] : 0;
+            w[W - 1 - j] = (uint32_t)j < rs.order ? hist[((rs.order - 1 - j) & 31) * DEC_THREADS] : 0;   // warm-up samples
+        }
+    }
+    pw.flush();   // warm-up samples that did not fill a group of four; from here on samples are stored directly
+    int32_t* const plane = pw.plane;
+    const uint32_t wasted = pw.wasted;
+    uint32_t part_end = 0;       // residual index where the next partition starts
+    uint32_t next_len = rs.nres - ((1u << rs.porder) - 1) * rs.chunk;   // the first partition is short by `order`
+    uint32_t mode = 0, k = 0;    // mode 0 rice(k), 1 escaped(k bits), 2 all zero
+    uint32_t idx = 0;
+    uint32_t fail = 0;
+    // one residual (read_residuals, src/decode.rs:1800-1856)
+    auto residual = [&]() -> int32_t {
+        if (idx == part_end) {
+            const uint32_t ph = partition_header(br, rs.hb, rs.esc_code);
+            if (ph == 0xFFFFFFFFu) fail = 1;
+            k = ph & 0x1f;
+            mode = (ph >> 8) & 3;
+            part_end += next_len;
+            next_len = rs.chunk;
+        }
+        int32_t r;
+        if (mode == 0) {
+            uint32_t u;
+            const uint32_t top = (uint32_t)(br.buf >> 32);
+            const uint32_t lz = (uint32_t)__clz((int)top);
+            if (top != 0 && lz + 1 + k <= 32) {   // whole code inside the 32-bit window
+                const uint32_t lsb = k ? ((top << (lz + 1)) >> (32 - k)) : 0u;
+                u = (lz << k) | lsb;               // src/decode.rs:1827
+                br.consume(lz + 1 + k);
+            } else {
+                u = 0;
+                const uint32_t e2 = rice_slow(br, k, &u);
+                if (e2) fail = e2;
+            }
+            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+        } else if (mode == 1) {
+            r = br.get_signed(k);
+        } else {
+            r = 0;
+        }
+        idx++;
+        return r;
+    };
+    // predict (src/decode.rs:1738-1752) for one sample whose W predecessors are w[base .. base + W)
+    // single samples: until the sample index is a multiple of four, and the tail
+    auto single = [&]() {
+        const uint32_t sidx = rs.order + idx;
+        const int32_t r = residual();
+        int32_t x;
+        if (HB > 0) {
+            long long sum = 0;
+#pragma unroll
+            for (int j = 0; j < W; j++) sum = mad_wide_s32(w[W - 1 - j], q[j], sum);
+            x = (int32_t)((uint32_t)r + (uint32_t)(unsigned long long)(sum >> rs.shift));
+#pragma unroll
+            for (int j = 0; j + 1 < W; j++) w[j] = w[j + 1];
+            w[W - 1] = x;
+        } else if (HB == 0) {
+            x = r;
+        } else {
+            long long sum = 0;
+            for (uint32_t j = 0; j < rs.order; j++)
+                sum = mad_wide_s32(hist[((sidx - 1 - j) & 31) * DEC_THREADS], coef[j * DEC_THREADS], sum);
+            x = (int32_t)((uint32_t)r + (uint32_t)(unsigned long long)(sum >> rs.shift));
+            hist[(sidx & 31) * DEC_THREADS] = x;
+        }
+        plane[sidx] = (int32_t)((uint32_t)x << wasted);   // `<<= wasted_bps`  src/decode.rs:1671
+    };
+    while (idx < rs.nres && ((rs.order + idx) & 3u) != 0) {
+        single();
+        if (fail) return fail;
+    }
+    while (idx + BLK <= rs.nres) {
+        const uint32_t sidx = rs.order + idx;
+        int32_t xs[BLK];
+#pragma unroll
+        for (int e = 0; e < BLK; e++) {
+            const int32_t r = residual();
+            int32_t x;
+            if (HB > 0) {
+                long long sum = 0;
+#pragma unroll
+                for (int j = 0; j < W; j++) sum = mad_wide_s32(w[W + e - 1 - j], q[j], sum);
+                x = (int32_t)((uint32_t)r + (uint32_t)(unsigned long long)(sum >> rs.shift));
+                w[W + e] = x;
+            } else if (HB == 0) {
+                x = r;
+            } else {
+                long long sum = 0;
+                for (uint32_t j = 0; j < rs.order; j++)
+                    sum = mad_wide_s32(hist[((sidx + e - 1 - j) & 31) * DEC_THREADS], coef[j * DEC_THREADS], sum);
+                x = (int32_t)((uint32_t)r + (uint32_t)(unsigned long long)(sum >> rs.shift));
+                hist[((sidx + e) & 31) * DEC_THREADS] = x;
+            }
+            xs[e] = (int32_t)((uint32_t)x << wasted);
+        }
+        if (fail) return fail;
+        *reinterpret_cast<int4*>(plane + sidx) = make_int4(xs[0], xs[1], xs[2], xs[3]);
+        if (HB > 0) {
+#pragma unroll
+            for (int j = 0; j < W; j++) w[j] = w[j + BLK];
+        }
+    }
+    while (idx < rs.nres) {
+        single();
+        if (fail) return fail;
+    }
+    pw.i = 0;   // everything is in the plane; nothing left for flush()
+    return 0;
+}
+
 // One subframe whose samples fit 32 bits.  hist/coef are this thread's columns of the shared rings.
-__device__ uint32_t decode_subframe(BitReader& br, uint32_t bps, uint32_t n, int32_t* __restrict__ plane, int32_t* hist, int16_t* coef)
+static __device__ __noinline__ uint32_t decode_subframe(BitReader& br, uint32_t bps, uint32_t n, int32_t* __restrict__ plane, int32_t* hist, int16_t* coef)
 {
     // SubframeHeader (src/stream.rs:1382-1395, :1537-1553)
     const uint32_t h = br.get(8);
@@ -431,50 +603,19 @@ __device__ uint32_t decode_subframe(BitReader& br, uint32_t bps, uint32_t n, int
     const uint32_t chunk = n >> porder;
     if (chunk == 0) return 46;   // InvalidPartitionOrder (rchunks_mut(0) panics in the reference)
     if ((nres + chunk - 1) / chunk != (1u << porder)) return 46;
-    uint32_t part_end = 0;       // residual index where the next partition starts
-    uint32_t next_len = nres - ((1u << porder) - 1) * chunk;   // the first partition is short by `order`
-    uint32_t mode = 0, k = 0;    // mode 0 rice(k), 1 escaped(k bits), 2 all zero
-    for (uint32_t idx = 0; idx < nres; idx++) {
-        if (idx == part_end) {   // ResidualPartitionHeader (src/stream.rs:1586-1600)
-            k = br.get(hb);
-            mode = 0;
-            if (k == esc_code) {
-                k = br.get(5);
-                mode = k ? 1 : 2;
-            }
-            part_end += next_len;
-            next_len = chunk;
-            if (br.position() > br.endbit) return 1;
-        }
-        int32_t r;
-        if (mode == 0) {
-            uint32_t msb, lsb;
-            const uint32_t top = (uint32_t)(br.buf >> 32);
-            const uint32_t lz = (uint32_t)__clz((int)top);
-            if (top != 0 && lz + 1 + k <= 32) {   // whole code inside the 32-bit window
-                msb = lz;
-                lsb = k ? ((top << (lz + 1)) >> (32 - k)) : 0u;
-                br.consume(lz + 1 + k);
-            } else {
-                msb = br.unary();
-                if (br.err) return br.err;
-                lsb = br.get(k);
-            }
-            const uint32_t u = (msb << k) | lsb;   // src/decode.rs:1827
-            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-        } else if (mode == 1) {
-            r = br.get_signed(k);
-        } else {
-            r = 0;
-        }
-        const uint32_t s = order + idx;
-        long long sum = 0;
-        for (uint32_t j = 0; j < order; j++)   // predict (src/decode.rs:1738-1752)
-            sum = mad_wide_s32(hist[((s - 1 - j) & 31) * DEC_THREADS], coef[j * DEC_THREADS], sum);
-        const int32_t x = (int32_t)((uint32_t)r + (uint32_t)(unsigned long long)(sum >> shift));
-        hist[(s & 31) * DEC_THREADS] = x;
-        pw.push(x);
+    // predict (src/decode.rs:1738-1752): orders up to 16 keep the coefficients and a sliding window of samples in
+    // registers (blocks of 8 samples, static indexing); longer predictors use the shared-memory rings
+    const ResidualSpec rs = {n, order, nres, chunk, porder, hb, esc_code, shift};
+    uint32_t rc;
+    switch (order == 0 ? 0u : (order + 3u) >> 2) {
+    case 0: rc = residual_loop<0>(br, pw, rs, hist, coef); break;
+    case 1: rc = residual_loop<4>(br, pw, rs, hist, coef); break;
+    case 2: rc = residual_loop<8>(br, pw, rs, hist, coef); break;
+    case 3: rc = residual_loop<12>(br, pw, rs, hist, coef); break;
+    case 4: rc = residual_loop<16>(br, pw, rs, hist, coef); break;
+    default: rc = residual_loop<-1>(br, pw, rs, hist, coef); break;
     }
+    if (rc) return rc;
     pw.flush();
     return br.position() > br.endbit ? 1u : 0u;
 }

@@ -16,6 +16,8 @@
 //           the planes (<= 4 subtractions), the LPC residual is read back from the int16 copy -- the FIR runs once per
 //           candidate instead of twice (it is recomputed only for the rare candidate whose residuals overflow int16)
 // Wasted bits are assumed 0 in pass 1; a candidate that has some repeats pass 1 with the shift applied.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tiles.cuh"
 #include "rice.cuh"
@@ -93,6 +95,8 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
     if (p_max > MAX_PORDER) p_max = MAX_PORDER;
     const uint32_t cf = n >> p_max;   // finest partition
     const bool cf16 = (cf & 15u) == 0;
+    const UDiv dcf = udiv_make(cf);
+    UDiv dcpf = dcf, dcpl = dcf;
     const uint32_t kmax = min(4u, n - 1);
     const bool have_lpc = lp.ok != 0;
     const uint32_t order = have_lpc ? lp.order : 0, shift = lp.shift;
@@ -187,10 +191,12 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
             cpf = n >> sm.choice[0].porder_g;
             j0f = (1u << sm.choice[0].porder_g) - sm.choice[0].nparts;
             cpf16 = (cpf & 15u) == 0;
+            dcpf = udiv_make(cpf);
             if (lpc_ok) {
                 cpl = n >> sm.choice[1].porder_g;
                 j0l = (1u << sm.choice[1].porder_g) - sm.choice[1].nparts;
                 cpl16 = (cpl & 15u) == 0;
+                dcpl = udiv_make(cpl);
             }
         }
         for (uint32_t rd = wsub; rd < rounds; rd += A3_WPC) {
@@ -260,8 +266,8 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
             // ---- fixed differences (:3039-3060); <= 28-bit samples cannot overflow i32 up to order 4 ----
             int32_t p1 = h[15] - h[14], p2 = p1 - (h[14] - h[13]), p3 = p2 - ((h[14] - h[13]) - (h[13] - h[12]));
             if (stage < 2) {
-                const uint32_t chunk = i0 / cf;
-                if (!tail && (cf16 || (i0 + 15) / cf == chunk)) {
+                const uint32_t chunk = udiv(i0, dcf);
+                if (!tail && (cf16 || udiv(i0 + 15, dcf) == chunk)) {
                     // per-tile sums in 32 bits: |e_k| < 2^(28 + k) would overflow over 16 samples only for k >= 3, which are
                     // summed in two halves; the LPC residual is unbounded and keeps a 64-bit accumulator
                     uint32_t a0 = 0, a1 = 0, a2 = 0, a3a = 0, a3b = 0, a4a = 0, a4b = 0;
@@ -341,9 +347,9 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     }
                 }
                 const RiceChoice& chf = sm.choice[0];
-                const uint32_t pf = i0 / cpf;
+                const uint32_t pf = udiv(i0, dcpf);
                 const uint32_t codef = chf.rice[pf - j0f >= chf.nparts ? 0 : pf - j0f];
-                if (!tail && i0 != 0 && (cpf16 || (i0 + 15) / cpf == pf) && codef < 0x40) {
+                if (!tail && i0 != 0 && (cpf16 || udiv(i0 + 15, dcpf) == pf) && codef < 0x40) {
                     uint32_t ta[4] = {0, 0, 0, 0};   // |rf| <= 2^28 here (25-bit samples): four shifted zig-zags fit 32 bits
 #pragma unroll
                     for (int e = 0; e < 16; e++) ta[e >> 2] += zigzag32(rf[e]) >> codef;
@@ -360,9 +366,9 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                 }
                 if (lpc_ok) {
                     const RiceChoice& chl = sm.choice[1];
-                    const uint32_t pl = i0 / cpl;
+                    const uint32_t pl = udiv(i0, dcpl);
                     const uint32_t codel = chl.rice[pl - j0l >= chl.nparts ? 0 : pl - j0l];
-                    if (!tail && i0 != 0 && (cpl16 || (i0 + 15) / cpl == pl) && codel < 0x40) {
+                    if (!tail && i0 != 0 && (cpl16 || udiv(i0 + 15, dcpl) == pl) && codel < 0x40) {
                         if (use16) {   // |rl| < 2^15: the whole tile fits 32 bits
                             uint32_t ta = 0;
 #pragma unroll
@@ -561,9 +567,10 @@ cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uin
                             unsigned long long* abssum, cudaStream_t st)
 {
     const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
+    static const size_t pad_ = getenv("FLACB200_A3_SMEM_PAD") ? (size_t)atoi(getenv("FLACB200_A3_SMEM_PAD")) : 0;   // occupancy experiments
 #define FLACB200_A3(HBV, ST)                                                                                                          \
     do {                                                                                                                              \
-        const size_t smem_ = a3_smem_bytes<ST>();                                                                                     \
+        const size_t smem_ = a3_smem_bytes<ST>() + pad_;                                                                              \
         cudaError_t e_ = cudaFuncSetAttribute(k_analyze3<HBV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);          \
         if (e_ != cudaSuccess) return e_;                                                                                             \
         const uint32_t groups_ = ST ? 1u : (cfg.channels + 1u) / 2u;                                                                  \

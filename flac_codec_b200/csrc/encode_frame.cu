@@ -94,6 +94,7 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
     const uint32_t cp = n >> cr.porder_g;                      // samples per partition (the first one holds cp - order residuals)
     const uint32_t j0 = (1u << cr.porder_g) - cr.nparts;
     const bool cp16 = (cp & 15u) == 0;
+    const UDiv dcp = udiv_make(cp);
     const uint32_t hb = cr.method ? 5u : 4u, escape_code = cr.method ? 31u : 15u;
     int32_t q[HB];
 #pragma unroll
@@ -137,8 +138,8 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
         }
         // ---- code lengths of this lane's tile ----
         const uint32_t lo_i = max(i0, order), hi_i = min(i0 + 16u, n);   // residuals exist for [lo_i, hi_i)
-        const uint32_t pj = live ? i0 / cp : 0u;
-        const bool uniform = live && i0 >= order && i0 + 16 <= n && (cp16 || (i0 + 15) / cp == pj);
+        const uint32_t pj = live ? udiv(i0, dcp) : 0u;
+        const bool uniform = live && i0 >= order && i0 + 16 <= n && (cp16 || udiv(i0 + 15, dcp) == pj);
         const uint32_t cc0 = cr.rice[live ? min(pj - j0, (uint32_t)MAX_PARTS - 1) : 0u];
         uint32_t tsum = 0;
         uint32_t len[16];
@@ -155,7 +156,7 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
                 const uint32_t i = i0 + e;
                 uint32_t l = 0;
                 if (i >= lo_i && i < hi_i) {
-                    const uint32_t p = i / cp;
+                    const uint32_t p = udiv(i, dcp);
                     const uint32_t cc = cr.rice[p - j0];
                     if (cc < 0x40) l = (zigzag32(r[e]) >> cc) + 1u + cc;
                     else if (cc & 0x40) l = cc & 31u;
@@ -195,7 +196,7 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
             for (int e = 0; e < 16; e++) {
                 const uint32_t i = i0 + e;
                 if (i < lo_i || i >= hi_i) continue;
-                const uint32_t pi = i / cp;
+                const uint32_t pi = udiv(i, dcp);
                 const uint32_t cc = cr.rice[pi - j0];
                 uint32_t at = p;
                 if (i == max(pi * cp, order)) {

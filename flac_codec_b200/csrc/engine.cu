@@ -413,7 +413,10 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     const bool need_planes = !(fast_analyze && fast_pack && (fast_lpc || cfg.max_lpc_order == 0));
     // launch group: without the int32 planes a group costs ~250 bytes per candidate, so it can be large enough to fill
     // the GPU even for the warp-per-8-candidates LPC kernel; with planes it is sized to stay near the L2 capacity
-    uint32_t chunk = e->chunk_frames ? e->chunk_frames : (need_planes ? 2048 : 32768);
+    // with host buffers the groups are also the grain of the copy/compute pipeline: smaller groups shorten its fill and
+    // drain (first upload before any kernel, last kernels + download after the last upload)
+    const bool host_io = pcm_location == FLACB200_HOST || (out && out_location == FLACB200_HOST);
+    uint32_t chunk = e->chunk_frames ? e->chunk_frames : (need_planes ? 2048 : (host_io ? 8192 : 32768));
     chunk = (uint32_t)std::min<uint64_t>(std::min<uint32_t>(chunk, 32768), nframes);
     const size_t ncand_chunk = (size_t)chunk * cfg.nslots;
     ENS(e->descs, nframes * sizeof(FrameDesc));

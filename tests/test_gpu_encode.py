@@ -276,8 +276,47 @@ def test_generic_kernels_give_the_same_bytes(eng, fo, monkeypatch):
         ("16b stereo fast-corr", Options.default().fast_channel_correlation(True), 44100, 16, 2, synth_pcm(7, 2, 30000, 44100, 16)),
         ("8b stereo bs 33", Options.best().block_size(33), 44100, 8, 2, synth_pcm(8, 2, 3000, 44100, 8)),
     ]
-    for mask in ("7", "1", "2", "4"):
+    # 1/2/4: generic analyze / lpc / pack; 8: k_pack2 instead of k_pack3; 16: k_analyze instead of k_analyze3;
+    # 32: k_lpc2 instead of k_lpc3; 56: all second-generation register-tiled kernels; 63: everything generic
+    for mask in ("7", "1", "2", "4", "8", "16", "32", "56", "63"):
         monkeypatch.setenv("FLACB200_LEGACY", mask)
         for label, opt, rate, bps, ch, x in cases:
             check(eng, fo, opt, rate, bps, ch, x, f"legacy={mask} {label}")
     monkeypatch.delenv("FLACB200_LEGACY")
+
+
+def test_frame_kernels_edge_shapes(eng, fo):
+    """Shapes that steer the CTA-per-frame kernels (k_lpc3 / k_analyze3 / k_pack3) through their rare paths: PCM that is
+    not 16-byte aligned per block (k_lpc3 falls back to k_lpc2), wasted bits (second pass), residuals that overflow the
+    int16 copy (FIR recomputed in pass 2), escapes / verbatim / constant subframes, short final blocks, odd block sizes."""
+    from flac_codec_b200 import Options, _abi
+
+    rng = np.random.default_rng(5)
+    # (a) segment that starts at an odd PCM frame: blocks are not 16-byte aligned
+    x = synth_pcm(11, 2, 30000, 48000, 24)
+    raw = np.frombuffer(fo.samples_to_bytes(x.reshape(-1), 3), dtype=np.uint8)
+    data, sizes, total = eng.encode(Options.best(), 48000, 24, 2, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(1, 30000 - 1, 0)])
+    ref, ref_sizes = fo.encode_frames_only(fo.options("best"), 48000, 24, 2, x[1:].reshape(-1))
+    assert data.tobytes() == ref and sizes.tolist() == ref_sizes.tolist()
+    # (b) wasted bits in one channel only, and in mid/side
+    y = synth_pcm(12, 2, 20000, 48000, 24)
+    y[:, 0] = (y[:, 0] >> 5) << 5
+    check(eng, fo, Options.best(), 48000, 24, 2, y, "wasted left")
+    y[:, 1] = (y[:, 1] >> 3) << 3
+    check(eng, fo, Options.best(), 48000, 24, 2, y, "wasted both")
+    # (c) loud noise and full-scale square bursts: residuals beyond int16, escapes and VERBATIM
+    z = rng.integers(-(1 << 23), 1 << 23, size=(3 * 4096 + 100, 2), dtype=np.int64).astype(np.int32)
+    z[4096:8192] = np.where((np.arange(4096) // 37) % 2 == 0, (1 << 23) - 1, -(1 << 23))[:, None]
+    z[9000:9400] = 0
+    check(eng, fo, Options.best(), 48000, 24, 2, z, "noise + square")
+    check(eng, fo, Options.default(), 44100, 16, 2, (z >> 8), "noise + square 16-bit")
+    # (d) silence, then a frame boundary inside a tone; block sizes that are not multiples of 16 or of 2^p
+    w = synth_pcm(13, 2, 11111, 44100, 16)
+    w[:5000] = 0
+    for bs in (4096, 4095, 1000, 576, 17):
+        check(eng, fo, Options.best().block_size(bs), 44100, 16, 2, w, f"block {bs}")
+    # (e) 3 and 5 channels (independent mode, odd channel group), big-endian bytes
+    for ch in (3, 5):
+        v = synth_pcm(14, ch, 9000, 48000, 24)
+        check(eng, fo, Options.best(), 48000, 24, ch, v, f"{ch} channels")
+        check(eng, fo, Options.best(), 48000, 24, ch, v, f"{ch} channels BE", pcm_kind=_abi.PCM_BYTES_BE)
