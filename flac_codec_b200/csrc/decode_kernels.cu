@@ -1199,9 +1199,89 @@ cudaError_t launch_chain(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* 
     return cudaGetLastError();
 }
 
+// k_emit4: the common layouts (1 or 2 channels, 2 or 3 bytes per sample, packed bytes) with four samples per thread:
+// 128-bit plane loads, the group's 4 * C * B output bytes assembled in registers and stored as whole 32-bit words.
+// A frame whose output position is not word aligned falls back to sample-by-sample stores.
+template <int C, int B>
+__global__ void __launch_bounds__(256) k_emit4(DecCfg cfg, const FrameCand* __restrict__ cands, const DecRec* __restrict__ recs,
+                                               const unsigned long long* __restrict__ pos, const int32_t* __restrict__ planes,
+                                               uint8_t* __restrict__ out)
+{
+    const uint32_t c = blockIdx.x;
+    const unsigned long long p = pos[c];
+    if (p == ~0ull) return;
+    const FrameCand fc = cands[c];
+    const uint32_t i = (blockIdx.y * 256 + threadIdx.x) * 4;
+    if (i >= fc.block_size) return;
+    const int32_t* base = planes + (size_t)c * cfg.nslots * cfg.bstride;
+    const uint32_t ca = fc.assignment;
+    int32_t v[4][C];
+    {
+        const int4 a = *reinterpret_cast<const int4*>(base + i);
+        const int32_t av[4] = {a.x, a.y, a.z, a.w};
+        if (C == 1) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) v[s][0] = av[s];
+        } else {
+            const int4 b = *reinterpret_cast<const int4*>(base + cfg.bstride + i);
+            const int32_t bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                int32_t l, r;
+                if (ca <= 7) { l = av[s]; r = bv[s]; }
+                else if (ca == 8) { l = av[s]; r = (int32_t)((uint32_t)av[s] - (uint32_t)bv[s]); }    // src/decode.rs:1524-1626
+                else if (ca == 9) { l = (int32_t)((uint32_t)av[s] + (uint32_t)bv[s]); r = bv[s]; }
+                else {
+                    const int32_t sum = (int32_t)((uint32_t)av[s] * 2u + (uint32_t)(bv[s] & 1));
+                    l = (int32_t)((uint32_t)sum + (uint32_t)bv[s]) >> 1;
+                    r = (int32_t)((uint32_t)sum - (uint32_t)bv[s]) >> 1;
+                }
+                v[s][0] = l;
+                v[s][C - 1] = r;
+            }
+        }
+    }
+    const unsigned long long byte0 = (p + i) * (unsigned long long)(C * B);
+    const bool be = cfg.pcm_kind == 1;
+    if ((byte0 & 3) == 0 && i + 4 <= fc.block_size) {
+        uint32_t w[C * B];   // Frame::to_buf (src/audio.rs:110-134): 4 samples x C channels x B bytes
+#pragma unroll
+        for (int k = 0; k < C * B; k++) w[k] = 0;
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+            for (int ch = 0; ch < C; ch++)
+#pragma unroll
+                for (int k = 0; k < B; k++) {
+                    const int idx = (s * C + ch) * B + k;
+                    const uint32_t byte = ((uint32_t)v[s][ch] >> (8 * (be ? B - 1 - k : k))) & 0xffu;
+                    w[idx >> 2] |= byte << (8 * (idx & 3));
+                }
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + byte0);
+#pragma unroll
+        for (int k = 0; k < C * B; k++) dst[k] = w[k];
+    } else {
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+            if (i + s < fc.block_size)
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) store_sample(out, cfg, p + i + s, ch, v[s][ch]);
+    }
+}
+
 void launch_emit(const DecCfg& cfg, const FrameCand* cands, const DecRec* recs, const unsigned long long* pos, const int32_t* planes, uint32_t n,
                  uint8_t* out, cudaStream_t st)
 {
+    const bool packed = cfg.pcm_kind <= 1 && cfg.nslots == cfg.channels && (cfg.bytes_per_sample == 2 || cfg.bytes_per_sample == 3) &&
+                        (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (cfg.bstride & 3) == 0;
+    if (packed && cfg.channels <= 2) {
+        dim3 grid(n, (cfg.bstride / 4 + 255) / 256);
+        if (cfg.channels == 1 && cfg.bytes_per_sample == 2) k_emit4<1, 2><<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
+        else if (cfg.channels == 1) k_emit4<1, 3><<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
+        else if (cfg.bytes_per_sample == 2) k_emit4<2, 2><<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
+        else k_emit4<2, 3><<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
+        return;
+    }
     dim3 grid(n, (cfg.bstride + 255) / 256);
     k_emit<<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
 }
