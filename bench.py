@@ -284,8 +284,9 @@ def run_gpu(args):
     value = samples_per_step * world / (ms_per_step * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel: algorithmic bytes of one launch / its average duration ----
-    # the C4 shape runs the register-tiled kernels (encode_fast.inl); slot 0 (k_planes) is only used by the generic path
-    names = ["k_planes", "k_lpc2", "k_analyze", "k_decide+k_scan+k_zero", "k_pack2+k_crc16w"]
+    # the C4 shape runs the CTA-per-frame kernels (encode_lpc.cu, encode_analyze.cu, encode_frame.cu); slot 0 (k_planes) is
+    # only used by the generic path
+    names = ["k_planes", "k_lpc3", "k_analyze3", "k_decide+k_scan", "k_pack3"]
     top = int(np.argmax(kernel_ms[:5]))
     peaks = {}
     try:
@@ -295,7 +296,7 @@ def run_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes_step = pcm_bytes + flac_bytes          # PCM read once + frames written once
-    groups = max(int(kernel_launches[top] // max({0: 1, 1: 1, 2: 1, 3: 3, 4: 2}[top], 1)), 1)
+    groups = max(int(kernel_launches[top] // max({0: 1, 1: 1, 2: 1, 3: 2, 4: 1}[top], 1)), 1)
     avg_ms = kernel_ms[top] / groups                 # average duration of one launch (group) of the top kernel
     alg_bytes_launch = alg_bytes_step * args.steps / groups
     achieved = alg_bytes_launch / (avg_ms * 1e-3) / 1e9
