@@ -601,7 +601,8 @@ struct flacb200_reader {
     size_t len = 0;
     flacb200_streaminfo si{};
     std::vector<flacb200_seekpoint> seektable;
-    HostBuf pcm;                 // decoded little-endian packed PCM of the whole stream
+    HostBuf pcm;                 // decoded PCM of the whole stream: packed little-endian bytes, or i32 when the first read asked for that
+    int cached_kind = FLACB200_PCM_BYTES_LE;
     bool decoded = false;
     int decode_error = 0;        // error of the first bad frame ...
     uint64_t valid_pcm = 0;      // ... which the reference reaches after this many inter-channel samples
@@ -672,12 +673,13 @@ int parse_metadata(const uint8_t* f, size_t len, flacb200_streaminfo* si, std::v
     return 0;
 }
 
-int reader_decode_all(flacb200_reader& r)
+int reader_decode_all(flacb200_reader& r, int want_kind)
 {
     if (r.decoded) return 0;
     if (!r.engine) return FLACB200_E_NO_DEVICE;
     const flacb200_streaminfo& si = r.si;
-    const size_t B = (si.bits_per_sample + 7) / 8, fb = B * si.channels;
+    r.cached_kind = want_kind == FLACB200_PCM_I32_INTERLEAVED ? FLACB200_PCM_I32_INTERLEAVED : FLACB200_PCM_BYTES_LE;
+    const size_t B = r.cached_kind == FLACB200_PCM_I32_INTERLEAVED ? 4 : (si.bits_per_sample + 7) / 8, fb = B * si.channels;
     const size_t nbytes = r.len - (size_t)si.frames_start;
     flacb200_stream_params prm{};
     prm.sample_rate = si.sample_rate;
@@ -690,7 +692,7 @@ int reader_decode_all(flacb200_reader& r)
         flacb200_decode_segment seg{0, nbytes, 0, si.total_samples};
         uint64_t nf = 0, ns = 0, bad = 0;
         const int rc = flacb200_decode(r.engine, &prm, r.flac + si.frames_start, nbytes, FLACB200_HOST, &seg, 1, r.pcm.p, (size_t)cap_pcm * fb,
-                                       FLACB200_PCM_BYTES_LE, FLACB200_HOST, 0, &nf, &ns, &bad);
+                                       r.cached_kind, FLACB200_HOST, 0, &nf, &ns, &bad);
         if (rc == FLACB200_E_OUTPUT_TOO_SMALL && !si.total_samples) {   // unsized stream: grow and retry
             cap_pcm *= 4;
             continue;
@@ -757,30 +759,36 @@ int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm
     if (pcm_kind != FLACB200_PCM_BYTES_LE && pcm_kind != FLACB200_PCM_BYTES_BE && pcm_kind != FLACB200_PCM_I32_INTERLEAVED)
         return FLACB200_E_BAD_ARGUMENT;
     *n_out = 0;
-    int rc = reader_decode_all(*r);
+    int rc = reader_decode_all(*r, pcm_kind);
     if (rc) return rc;
-    const size_t B = (r->si.bits_per_sample + 7) / 8;
+    const size_t B = (r->si.bits_per_sample + 7) / 8;          // bytes per sample of the byte layouts
+    const bool cache_i32 = r->cached_kind == FLACB200_PCM_I32_INTERLEAVED;
+    const size_t CB = cache_i32 ? 4 : B;                        // bytes per sample in the cache
     const uint64_t end = r->valid_pcm * r->si.channels;   // in single-channel samples
     if (r->pos >= end) return r->decode_error;             // the bad frame is reached only now (0 = clean end of stream)
-    const uint8_t* src = r->pcm.p + (size_t)r->pos * B;
+    const uint8_t* src = r->pcm.p + (size_t)r->pos * CB;
     size_t n;
     if (pcm_kind == FLACB200_PCM_I32_INTERLEAVED) {
         n = (size_t)std::min<uint64_t>(capacity, end - r->pos);
         int32_t* o = (int32_t*)out;
-        const uint32_t sh = 32 - 8 * (uint32_t)B;
-        for (size_t i = 0; i < n; i++) {
-            uint32_t v = 0;
-            for (size_t k = 0; k < B; k++) v |= (uint32_t)src[i * B + k] << (8 * k);
-            o[i] = (int32_t)(v << sh) >> sh;
+        if (cache_i32) memcpy(o, src, n * 4);
+        else {
+            const uint32_t sh = 32 - 8 * (uint32_t)B;
+            for (size_t i = 0; i < n; i++) {
+                uint32_t v = 0;
+                for (size_t k = 0; k < B; k++) v |= (uint32_t)src[i * B + k] << (8 * k);
+                o[i] = (int32_t)(v << sh) >> sh;
+            }
         }
         *n_out = n;
     } else {
         n = (size_t)std::min<uint64_t>(capacity / B, end - r->pos);
         uint8_t* o = (uint8_t*)out;
-        if (pcm_kind == FLACB200_PCM_BYTES_LE || B == 1) memcpy(o, src, n * B);
+        const bool be = pcm_kind == FLACB200_PCM_BYTES_BE;
+        if (!cache_i32 && (!be || B == 1)) memcpy(o, src, n * B);
         else
-            for (size_t i = 0; i < n; i++)
-                for (size_t k = 0; k < B; k++) o[i * B + k] = src[i * B + (B - 1 - k)];
+            for (size_t i = 0; i < n; i++)      // Frame::to_buf (src/audio.rs:110-134)
+                for (size_t k = 0; k < B; k++) o[i * B + k] = src[i * CB + (be ? B - 1 - k : k)];
         *n_out = n * B;
     }
     r->pos += n;
@@ -795,7 +803,7 @@ int flacb200_reader_seek(flacb200_reader* r, uint64_t pcm_frame)
     if (total) {
         if (pcm_frame > total) return E_INVALID_SEEK;
     } else {
-        const int rc = reader_decode_all(*r);
+        const int rc = reader_decode_all(*r, r->cached_kind);
         if (rc) return rc;
         if (pcm_frame > r->total_pcm) return E_INVALID_SEEK;
     }
@@ -806,11 +814,25 @@ int flacb200_reader_seek(flacb200_reader* r, uint64_t pcm_frame)
 int flacb200_reader_verify(flacb200_reader* r, int* result, uint8_t md5_out[16])
 {
     if (!r || !result) return FLACB200_E_BAD_ARGUMENT;
-    int rc = reader_decode_all(*r);
+    int rc = reader_decode_all(*r, r->cached_kind);
     if (rc) return rc;
     if (r->decode_error) return r->decode_error;
     uint8_t sum[16];
-    flacb200_md5(r->pcm.p, r->pcm.len, sum);
+    if (r->cached_kind == FLACB200_PCM_I32_INTERLEAVED) {   // MD5 runs over the packed little-endian form (src/decode.rs:1297)
+        const size_t B = (r->si.bits_per_sample + 7) / 8, total = (size_t)r->valid_pcm * r->si.channels;
+        Md5 m;
+        uint8_t buf[4096 * 4];
+        for (size_t done = 0; done < total;) {
+            const size_t take = std::min<size_t>(4096, total - done);
+            for (size_t i = 0; i < take; i++)
+                for (size_t k = 0; k < B; k++) buf[i * B + k] = r->pcm.p[(done + i) * 4 + k];
+            m.update(buf, take * B);
+            done += take;
+        }
+        m.final(sum);
+    } else {
+        flacb200_md5(r->pcm.p, r->pcm.len, sum);
+    }
     if (md5_out) memcpy(md5_out, sum, 16);
     static const uint8_t zero[16] = {0};
     if (memcmp(r->si.md5, zero, 16) == 0) *result = 2;        // Verified::NoMD5
