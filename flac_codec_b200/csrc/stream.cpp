@@ -41,31 +41,55 @@ struct Md5 {
 
     void block(const uint8_t* p)
     {
-        static const uint32_t K[64] = {
-            0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8, 0x8b44f7af, 0xffff5bb1,
-            0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821, 0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453,
-            0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a, 0xfffa3942,
-            0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70, 0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05,
-            0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665, 0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d,
-            0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
-        static const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
-                                  4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+        // fully unrolled rounds: the per-stream MD5 is the serial tail of a single-stream encode (the GPU work of a 60 s
+        // track is shorter than hashing its 10 MB), so the constants and rotations are compile-time here
         uint32_t m[16];
-        for (int i = 0; i < 16; i++) m[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+        memcpy(m, p, 64);   // little-endian host
         uint32_t A = a, B = b, C = c, D = d;
-        for (int i = 0; i < 64; i++) {
-            uint32_t f;
-            int g;
-            if (i < 16) { f = (B & C) | (~B & D); g = i; }
-            else if (i < 32) { f = (D & B) | (~D & C); g = (5 * i + 1) & 15; }
-            else if (i < 48) { f = B ^ C ^ D; g = (3 * i + 5) & 15; }
-            else { f = C ^ (B | ~D); g = (7 * i) & 15; }
-            const uint32_t t = D;
-            D = C;
-            C = B;
-            B = B + rol(A + f + K[i] + m[g], S[i]);
-            A = t;
-        }
+#define FLACB200_MD5_STEP(f, w, x, y, z, k, t, sft) \
+    w += f(x, y, z) + m[k] + t;                     \
+    w = rol(w, sft) + x;
+#define FLACB200_F(x, y, z) (z ^ (x & (y ^ z)))
+#define FLACB200_G(x, y, z) (y ^ (z & (x ^ y)))
+#define FLACB200_H(x, y, z) (x ^ y ^ z)
+#define FLACB200_I(x, y, z) (y ^ (x | ~z))
+        FLACB200_MD5_STEP(FLACB200_F, A, B, C, D, 0, 0xd76aa478u, 7)  FLACB200_MD5_STEP(FLACB200_F, D, A, B, C, 1, 0xe8c7b756u, 12)
+        FLACB200_MD5_STEP(FLACB200_F, C, D, A, B, 2, 0x242070dbu, 17) FLACB200_MD5_STEP(FLACB200_F, B, C, D, A, 3, 0xc1bdceeeu, 22)
+        FLACB200_MD5_STEP(FLACB200_F, A, B, C, D, 4, 0xf57c0fafu, 7)  FLACB200_MD5_STEP(FLACB200_F, D, A, B, C, 5, 0x4787c62au, 12)
+        FLACB200_MD5_STEP(FLACB200_F, C, D, A, B, 6, 0xa8304613u, 17) FLACB200_MD5_STEP(FLACB200_F, B, C, D, A, 7, 0xfd469501u, 22)
+        FLACB200_MD5_STEP(FLACB200_F, A, B, C, D, 8, 0x698098d8u, 7)  FLACB200_MD5_STEP(FLACB200_F, D, A, B, C, 9, 0x8b44f7afu, 12)
+        FLACB200_MD5_STEP(FLACB200_F, C, D, A, B, 10, 0xffff5bb1u, 17) FLACB200_MD5_STEP(FLACB200_F, B, C, D, A, 11, 0x895cd7beu, 22)
+        FLACB200_MD5_STEP(FLACB200_F, A, B, C, D, 12, 0x6b901122u, 7) FLACB200_MD5_STEP(FLACB200_F, D, A, B, C, 13, 0xfd987193u, 12)
+        FLACB200_MD5_STEP(FLACB200_F, C, D, A, B, 14, 0xa679438eu, 17) FLACB200_MD5_STEP(FLACB200_F, B, C, D, A, 15, 0x49b40821u, 22)
+        FLACB200_MD5_STEP(FLACB200_G, A, B, C, D, 1, 0xf61e2562u, 5)  FLACB200_MD5_STEP(FLACB200_G, D, A, B, C, 6, 0xc040b340u, 9)
+        FLACB200_MD5_STEP(FLACB200_G, C, D, A, B, 11, 0x265e5a51u, 14) FLACB200_MD5_STEP(FLACB200_G, B, C, D, A, 0, 0xe9b6c7aau, 20)
+        FLACB200_MD5_STEP(FLACB200_G, A, B, C, D, 5, 0xd62f105du, 5)  FLACB200_MD5_STEP(FLACB200_G, D, A, B, C, 10, 0x02441453u, 9)
+        FLACB200_MD5_STEP(FLACB200_G, C, D, A, B, 15, 0xd8a1e681u, 14) FLACB200_MD5_STEP(FLACB200_G, B, C, D, A, 4, 0xe7d3fbc8u, 20)
+        FLACB200_MD5_STEP(FLACB200_G, A, B, C, D, 9, 0x21e1cde6u, 5)  FLACB200_MD5_STEP(FLACB200_G, D, A, B, C, 14, 0xc33707d6u, 9)
+        FLACB200_MD5_STEP(FLACB200_G, C, D, A, B, 3, 0xf4d50d87u, 14) FLACB200_MD5_STEP(FLACB200_G, B, C, D, A, 8, 0x455a14edu, 20)
+        FLACB200_MD5_STEP(FLACB200_G, A, B, C, D, 13, 0xa9e3e905u, 5) FLACB200_MD5_STEP(FLACB200_G, D, A, B, C, 2, 0xfcefa3f8u, 9)
+        FLACB200_MD5_STEP(FLACB200_G, C, D, A, B, 7, 0x676f02d9u, 14) FLACB200_MD5_STEP(FLACB200_G, B, C, D, A, 12, 0x8d2a4c8au, 20)
+        FLACB200_MD5_STEP(FLACB200_H, A, B, C, D, 5, 0xfffa3942u, 4)  FLACB200_MD5_STEP(FLACB200_H, D, A, B, C, 8, 0x8771f681u, 11)
+        FLACB200_MD5_STEP(FLACB200_H, C, D, A, B, 11, 0x6d9d6122u, 16) FLACB200_MD5_STEP(FLACB200_H, B, C, D, A, 14, 0xfde5380cu, 23)
+        FLACB200_MD5_STEP(FLACB200_H, A, B, C, D, 1, 0xa4beea44u, 4)  FLACB200_MD5_STEP(FLACB200_H, D, A, B, C, 4, 0x4bdecfa9u, 11)
+        FLACB200_MD5_STEP(FLACB200_H, C, D, A, B, 7, 0xf6bb4b60u, 16) FLACB200_MD5_STEP(FLACB200_H, B, C, D, A, 10, 0xbebfbc70u, 23)
+        FLACB200_MD5_STEP(FLACB200_H, A, B, C, D, 13, 0x289b7ec6u, 4) FLACB200_MD5_STEP(FLACB200_H, D, A, B, C, 0, 0xeaa127fau, 11)
+        FLACB200_MD5_STEP(FLACB200_H, C, D, A, B, 3, 0xd4ef3085u, 16) FLACB200_MD5_STEP(FLACB200_H, B, C, D, A, 6, 0x04881d05u, 23)
+        FLACB200_MD5_STEP(FLACB200_H, A, B, C, D, 9, 0xd9d4d039u, 4)  FLACB200_MD5_STEP(FLACB200_H, D, A, B, C, 12, 0xe6db99e5u, 11)
+        FLACB200_MD5_STEP(FLACB200_H, C, D, A, B, 15, 0x1fa27cf8u, 16) FLACB200_MD5_STEP(FLACB200_H, B, C, D, A, 2, 0xc4ac5665u, 23)
+        FLACB200_MD5_STEP(FLACB200_I, A, B, C, D, 0, 0xf4292244u, 6)  FLACB200_MD5_STEP(FLACB200_I, D, A, B, C, 7, 0x432aff97u, 10)
+        FLACB200_MD5_STEP(FLACB200_I, C, D, A, B, 14, 0xab9423a7u, 15) FLACB200_MD5_STEP(FLACB200_I, B, C, D, A, 5, 0xfc93a039u, 21)
+        FLACB200_MD5_STEP(FLACB200_I, A, B, C, D, 12, 0x655b59c3u, 6) FLACB200_MD5_STEP(FLACB200_I, D, A, B, C, 3, 0x8f0ccc92u, 10)
+        FLACB200_MD5_STEP(FLACB200_I, C, D, A, B, 10, 0xffeff47du, 15) FLACB200_MD5_STEP(FLACB200_I, B, C, D, A, 1, 0x85845dd1u, 21)
+        FLACB200_MD5_STEP(FLACB200_I, A, B, C, D, 8, 0x6fa87e4fu, 6)  FLACB200_MD5_STEP(FLACB200_I, D, A, B, C, 15, 0xfe2ce6e0u, 10)
+        FLACB200_MD5_STEP(FLACB200_I, C, D, A, B, 6, 0xa3014314u, 15) FLACB200_MD5_STEP(FLACB200_I, B, C, D, A, 13, 0x4e0811a1u, 21)
+        FLACB200_MD5_STEP(FLACB200_I, A, B, C, D, 4, 0xf7537e82u, 6)  FLACB200_MD5_STEP(FLACB200_I, D, A, B, C, 11, 0xbd3af235u, 10)
+        FLACB200_MD5_STEP(FLACB200_I, C, D, A, B, 2, 0x2ad7d2bbu, 15) FLACB200_MD5_STEP(FLACB200_I, B, C, D, A, 9, 0xeb86d391u, 21)
+#undef FLACB200_MD5_STEP
+#undef FLACB200_F
+#undef FLACB200_G
+#undef FLACB200_H
+#undef FLACB200_I
         a += A; b += B; c += C; d += D;
     }
 
