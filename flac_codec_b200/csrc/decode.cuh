@@ -33,6 +33,13 @@ struct DecRec {
     uint32_t wide;            // 1: the side channel is 33 bits wide, its high words are in the extra plane
 };
 
+// per subframe, written by k_parse and read by k_restore (decode_parse.cu)
+struct SubRec {
+    uint8_t kind;      // 0 constant, 1 verbatim, 2 fixed, 3 lpc; 0xFF: frame left to k_decode (33-bit side channel)
+    uint8_t order, shift, wasted;
+    int16_t coef[32];
+};
+
 struct ChainState {
     unsigned long long expect_off;    // a chain continues into the next group at this byte offset ...
     unsigned long long seg_samples;   // ... with this many samples of its segment already decoded

@@ -707,13 +707,14 @@ __device__ uint32_t decode_subframe_wide(BitReader& br, uint32_t bps, uint32_t n
 
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
                                                        const FrameCand* __restrict__ cands, uint32_t ncand, int32_t* __restrict__ planes,
-                                                       DecRec* __restrict__ recs)
+                                                       DecRec* __restrict__ recs, uint32_t only_wide)
 {
     __shared__ int32_t s_hist[32 * DEC_THREADS];
     __shared__ int16_t s_coef[32 * DEC_THREADS];
     const uint32_t c = blockIdx.x * DEC_THREADS + threadIdx.x;
     if (c >= ncand) return;
     const FrameCand fc = cands[c];
+    if (only_wide && !(fc.assignment >= 8 && cfg.bps == 32)) return;   // every other frame went through k_parse / k_restore
     const DecSeg sg = segs[fc.seg];
     BitReader br;
     br.bytes = bytes;
@@ -1176,9 +1177,9 @@ void launch_find_write(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* se
 }
 
 void launch_decode(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes, DecRec* recs,
-                   cudaStream_t st)
+                   bool only_wide, cudaStream_t st)
 {
-    k_decode<<<(n + DEC_THREADS - 1) / DEC_THREADS, DEC_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, recs);
+    k_decode<<<(n + DEC_THREADS - 1) / DEC_THREADS, DEC_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, recs, only_wide ? 1u : 0u);
 }
 
 void launch_crc16f(const uint8_t* bytes, const FrameCand* cands, uint32_t n, DecRec* recs, cudaStream_t st)

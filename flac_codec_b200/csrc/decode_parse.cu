@@ -1,0 +1,416 @@
+// decode_parse.cu -- k_parse + k_restore: read_subframes (src/decode.rs:1494-1856) split into a bit-serial half and
+// an arithmetic half, both with WARP-UNIFORM control flow.
+//
+// The serial dependency of a FLAC frame is the bit position: a Rice code can only be found once every code before it
+// has been measured, and subframes carry no length.  A thread per candidate frame is therefore the natural grain of
+// the bit walk -- but a general per-thread decoder (k_decode, decode_kernels.cu) diverges: the 32 lanes of a warp sit
+// in different subframe kinds, predictor orders, partitions and refill states, so the warp executes them one after
+// the other (measured: ~1750 cycles per sample and lane).  Here the walk is written as ONE loop over the sample index
+// s that all lanes of a warp run in lockstep:
+//
+//   k_parse    lane per candidate frame.  Per subframe: header (:1635-1676), then for s = 0 .. n: one "token" per lane
+//              -- a warm-up/verbatim sample (raw bits), a Rice code (:1825-1827), an escaped residual (raw bits), or a
+//              constant -- with the rare events (LPC parameters + residual coding header at s == order, partition headers
+//              at s == j * (n >> partition order); :1698-1733, :1800-1822) handled when a lane reaches them.  The bit
+//              window is two 32-bit big-endian words and a bit offset (one funnel shift per look), the word after them
+//              is requested one word ahead.  Output: the plane of each subframe holds [warm-up | residuals] (stored as
+//              aligned 128-bit groups, every lane at the same s), plus a SubRec (kind, order, shift, wasted bits,
+//              coefficients) per subframe and the DecRec (end offset, error) per frame.
+//   k_restore  lane per subframe: predict (:1738-1752) in place over the plane, coefficients and a sliding window of
+//              samples in registers, four samples per 128-bit load/store, then `<<= wasted` (:1671).  The predictor
+//              length is the warp's largest order rounded up to a multiple of four (shorter predictors run with zero
+//              coefficients), so the loop is uniform as well.  Fixed predictors are LPC with the FIXED_COEFFS
+//              (src/stream.rs:1534) and shift 0; constant and verbatim subframes are order 0.
+//
+// Frames whose side channel is 33 bits wide (32-bit streams with stereo decorrelation, :1528-1546) stay with k_decode.
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace flacb200 {
+
+constexpr uint32_t PARSE_THREADS = 64;
+constexpr uint32_t RESTORE_THREADS = 64;
+
+enum : uint32_t { TK_RAW = 0, TK_RICE = 1, TK_FILL = 2 };
+
+__constant__ int16_t c_fixed_coeffs[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};   // src/stream.rs:1534
+
+// two consecutive big-endian words of the stream (w0, w1) and a bit offset pos < 32 into w0; the two words after them
+// are in flight as raw little-endian loads (r1, r2) and are byte-swapped only when they move into w1, so that a load
+// has two word periods to land.  Words are addressed relative to the lane's first word (32-bit index, one compare
+// against the number of whole words left in the buffer).
+// the last, partial word of the buffer (little-endian like a whole-word load); zero beyond it.  A free function taking
+// values: a member would take the address of the lane state and push all of it into local memory.
+static __device__ __noinline__ uint32_t load_tail_word(const uint8_t* bytes, unsigned long long nbytes, unsigned long long word)
+{
+    const unsigned long long b = word << 2;
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < 4; k++)
+        if (b + k < nbytes) v |= (uint32_t)bytes[b + k] << (8 * k);
+    return v;
+}
+
+struct LaneBits {
+    const uint32_t* base;         // word `first` of the buffer
+    const uint8_t* bytes;
+    unsigned long long nbytes, first;
+    uint32_t limit;               // whole words available from `first` on (clamped to 32 bits)
+    uint32_t rel;                 // w0 is word first + rel
+    uint32_t w0, w1, r1, r2, pos;
+
+    __device__ __forceinline__ uint32_t load_raw(uint32_t i) const { return i < limit ? __ldg(base + i) : load_tail_word(bytes, nbytes, first + i); }
+    __device__ __forceinline__ void init(const uint8_t* buf, unsigned long long buf_bytes, unsigned long long bitpos)
+    {
+        bytes = buf;
+        nbytes = buf_bytes;
+        first = bitpos >> 5;
+        base = reinterpret_cast<const uint32_t*>(buf) + first;
+        const unsigned long long whole = buf_bytes >> 2;
+        limit = whole > first ? (uint32_t)min(whole - first, 0xFFFFFFFFull) : 0u;
+        rel = 0;
+        pos = (uint32_t)(bitpos & 31);
+        w0 = __byte_perm(load_raw(0), 0, 0x0123);
+        w1 = __byte_perm(load_raw(1), 0, 0x0123);
+        r1 = load_raw(2);
+        r2 = load_raw(3);
+    }
+    __device__ __forceinline__ unsigned long long position() const { return ((first + rel) << 5) + pos; }
+    __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(w1, w0, pos); }   // the next 32 bits
+    __device__ __forceinline__ void skip(uint32_t n)   // n <= 32
+    {
+        pos += n;
+        if (pos >= 32) {
+            w0 = w1;
+            w1 = __byte_perm(r1, 0, 0x0123);
+            r1 = r2;
+            rel++;
+            r2 = load_raw(rel + 3);
+            pos -= 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t n)   // n in 0..=32
+    {
+        const uint32_t v = __funnelshift_lc(window(), 0, n);   // window >> (32 - n), 0 for n == 0
+        skip(n);
+        return v;
+    }
+    __device__ __forceinline__ int32_t get_signed(uint32_t n)   // n in 1..=32
+    {
+        const uint32_t v = get(n);
+        return (int32_t)(v << (32 - n)) >> (32 - n);
+    }
+};
+
+// state of the subframe a lane is walking
+struct LaneSub {
+    uint32_t kind;      // 0 constant, 1 verbatim, 2 fixed, 3 lpc
+    uint32_t order, n;
+    uint32_t tk, k;     // current token kind and its bit count (raw: width, rice: parameter)
+    int32_t fill;       // TK_FILL value
+    uint32_t ev_s;      // sample index of the next event (0xFFFFFFFF: none)
+    uint32_t started;   // the residual coding header has been read
+    uint32_t hb, esc, chunk, ebps;
+};
+
+// the events of a predictive subframe: at s == order the LPC parameters (:1706-1729) and the residual coding header
+// (:1806-1822), then (and at every later partition boundary) a ResidualPartitionHeader (src/stream.rs:1586-1600).
+// Returns 0 or the Error ordinal.
+__device__ __forceinline__ uint32_t parse_event(LaneBits& br, LaneSub& sf, unsigned long long endbit, SubRec* __restrict__ rec)
+{
+    if (!sf.started) {
+        sf.started = 1;
+        if (sf.kind == 3) {
+            const uint32_t prec = br.get(4) + 1;
+            if (prec > 15) return 49;   // InvalidQlpPrecision
+            const int32_t sh = br.get_signed(5);
+            if (sh < 0) return 50;      // NegativeLpcShift
+            rec->shift = (uint8_t)sh;
+            for (uint32_t j = 0; j < sf.order; j++) rec->coef[j] = (int16_t)br.get_signed(prec);
+        } else {
+            rec->shift = 0;
+            for (uint32_t j = 0; j < sf.order; j++) rec->coef[j] = c_fixed_coeffs[sf.order][j];
+        }
+        if (br.position() > endbit) return 1;
+        const uint32_t method = br.get(2);
+        if (method > 1) return 45;   // InvalidCodingMethod
+        sf.hb = method ? 5u : 4u;
+        sf.esc = method ? 31u : 15u;
+        const uint32_t porder = br.get(4);
+        const uint32_t nres = sf.n - sf.order;
+        sf.chunk = sf.n >> porder;
+        if (sf.chunk == 0) return 46;   // InvalidPartitionOrder (rchunks_mut(0) panics in the reference)
+        if ((nres + sf.chunk - 1) / sf.chunk != (1u << porder)) return 46;
+        sf.ev_s = 0;   // the first partition ends at sample `chunk`
+    }
+    uint32_t k = br.get(sf.hb);
+    sf.tk = TK_RICE;
+    if (k == sf.esc) {
+        k = br.get(5);
+        sf.tk = k ? TK_RAW : TK_FILL;
+        sf.fill = 0;
+    }
+    sf.k = k;
+    if (br.position() > endbit) return 1;
+    sf.ev_s += sf.chunk;
+    if (sf.ev_s >= sf.n) sf.ev_s = 0xFFFFFFFFu;
+    return 0;
+}
+
+// SubframeHeader (src/stream.rs:1382-1395, :1537-1553) and what precedes the sample loop.  Returns 0 or the ordinal.
+__device__ __forceinline__ uint32_t parse_subframe_header(LaneBits& br, LaneSub& sf, uint32_t bps, uint32_t n, unsigned long long endbit,
+                                                           SubRec* __restrict__ rec)
+{
+    const uint32_t h = br.get(8);
+    if (h & 0x80) return 41;   // InvalidSubframeHeader
+    const uint32_t type = (h >> 1) & 0x3f;
+    uint32_t wasted = 0;
+    if (h & 1) {               // unary(wasted - 1)
+        uint32_t q = 0;
+        for (;;) {
+            const uint32_t win = br.window();
+            if (win) {
+                const uint32_t lz = (uint32_t)__clz((int)win);
+                br.skip(lz + 1);
+                q += lz;
+                break;
+            }
+            q += 32;
+            br.skip(32);
+            if (br.position() > endbit) return 1;
+        }
+        wasted = q + 1;
+    }
+    uint32_t kind, order = 0;
+    if (type == 0) kind = 0;
+    else if (type == 1) kind = 1;
+    else if (type >= 8 && type <= 12) { kind = 2; order = type - 8; }
+    else if (type >= 32) { kind = 3; order = type - 31; }
+    else return 42;            // InvalidSubframeHeaderType
+    if (wasted >= bps) return 43;   // ExcessiveWastedBits (src/decode.rs:1644)
+    sf.ebps = bps - wasted;
+    sf.kind = kind;
+    sf.order = order;
+    sf.n = n;
+    sf.started = kind < 2;   // no residual coding header to come
+    sf.ev_s = 0xFFFFFFFFu;
+    sf.fill = 0;
+    rec->kind = (uint8_t)kind;
+    rec->order = (uint8_t)order;
+    rec->wasted = (uint8_t)wasted;
+    rec->shift = 0;
+    if (kind == 0) {
+        sf.tk = TK_FILL;
+        sf.k = 0;
+        sf.fill = br.get_signed(sf.ebps);
+        rec->order = 0;
+        return 0;
+    }
+    sf.tk = TK_RAW;   // warm-up samples or the verbatim block: `ebps` bits each
+    sf.k = sf.ebps;
+    if (kind == 1) return 0;
+    if (order > n) return kind == 2 ? 47u : 48u;   // InvalidFixedOrder / InvalidLpcOrder
+    sf.ev_s = order;
+    return 0;
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
+                                                        const FrameCand* __restrict__ cands, uint32_t ncand, int32_t* __restrict__ planes,
+                                                        SubRec* __restrict__ subs, DecRec* __restrict__ recs)
+{
+    const uint32_t c = blockIdx.x * PARSE_THREADS + threadIdx.x;
+    const bool exists = c < ncand;
+    FrameCand fc;
+    fc.off = 0; fc.block_size = 0; fc.seg = 0; fc.hdr_len = 0; fc.assignment = 0;
+    if (exists) fc = cands[c];
+    const uint32_t ca = fc.assignment;
+    const bool wide = exists && ca >= 8 && cfg.bps == 32;   // 33-bit side channel: k_decode handles the frame
+    unsigned long long endbit = 0, byte_end = 0;
+    LaneBits br;
+    br.init(bytes, cfg.nbytes, 0);
+    const uint32_t n = fc.block_size;
+    uint32_t err = 0;
+    bool live = exists && !wide;
+    if (live) {
+        const DecSeg sg = segs[fc.seg];
+        byte_end = sg.byte_end;
+        endbit = byte_end * 8;
+        br.init(bytes, cfg.nbytes, (fc.off + fc.hdr_len) * 8);
+        if (n > cfg.bstride) { err = 25; live = false; }   // cannot happen when max_block_size was honoured
+    }
+    const uint32_t nch = ca <= 7 ? ca + 1 : 2;
+    SubRec* const myrec = subs + (size_t)(exists ? c : 0) * cfg.channels;
+    if (exists && wide)
+        for (uint32_t ch = 0; ch < cfg.channels; ch++) myrec[ch].kind = 0xFF;
+    int32_t* const base = planes + (size_t)(exists ? c : 0) * cfg.nslots * cfg.bstride;
+    const uint32_t nch_max = __reduce_max_sync(0xffffffffu, live ? nch : 0u);
+    for (uint32_t ch = 0; ch < nch_max; ch++) {
+        bool act = live && ch < nch;
+        LaneSub sf;
+        sf.kind = 0; sf.order = 0; sf.n = 0; sf.tk = TK_FILL; sf.k = 0; sf.fill = 0; sf.ev_s = 0xFFFFFFFFu; sf.started = 1;
+        sf.hb = 4; sf.esc = 15; sf.chunk = 1; sf.ebps = 1;
+        SubRec* rec = myrec + (act ? ch : 0);
+        if (act) {
+            // 8: left, side   9: side, right   10: mid, side   (src/decode.rs:1512-1626): the side channel has one bit more
+            const bool is_side = ca >= 8 && ((ch == 0) == (ca == 9));
+            const uint32_t e = parse_subframe_header(br, sf, is_side ? cfg.bps + 1 : cfg.bps, n, endbit, rec);
+            if (e) { err = e; live = act = false; }
+        }
+        int32_t* const plane = base + (size_t)ch * cfg.bstride;
+        const uint32_t n4 = __reduce_max_sync(0xffffffffu, act ? (n + 3u) & ~3u : 0u);
+        uint32_t nlane = act ? n : 0u;   // 0 once the lane has failed: it keeps walking the loop without reading
+        for (uint32_t s0 = 0; s0 < n4; s0 += 4) {
+            int32_t o[4];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; e4++) {
+                const uint32_t s = s0 + e4;
+                int32_t v = 0;
+                if (s < nlane) {
+                    if (s == sf.ev_s) {
+                        const uint32_t e = parse_event(br, sf, endbit, rec);
+                        if (e) { err = e; nlane = 0; sf.tk = TK_FILL; sf.fill = 0; sf.ev_s = 0xFFFFFFFFu; }
+                    }
+                    if (sf.tk == TK_RICE) {
+                        const uint32_t win = br.window();
+                        const uint32_t lz = (uint32_t)__clz((int)win);
+                        const uint32_t total = lz + 1 + sf.k;
+                        uint32_t u;
+                        if (total <= 32) {   // the whole code sits in the window (win != 0)
+                            const uint32_t lsb = __funnelshift_lc((win << lz) << 1, 0, sf.k);
+                            u = (lz << sf.k) | lsb;   // src/decode.rs:1827
+                            br.skip(total);
+                        } else {
+                            uint32_t msb = 0;
+                            uint32_t w2 = win;
+                            while (w2 == 0) {
+                                msb += 32;
+                                br.skip(32);
+                                if (br.position() > endbit) { err = 1; nlane = 0; break; }
+                                w2 = br.window();
+                            }
+                            const uint32_t lz2 = w2 ? (uint32_t)__clz((int)w2) : 0u;
+                            br.skip(w2 ? lz2 + 1 : 0u);
+                            msb += lz2;
+                            u = (msb << sf.k) | br.get(sf.k);
+                        }
+                        v = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+                    } else if (sf.tk == TK_RAW) {
+                        v = br.get_signed(sf.k);
+                    } else {
+                        v = sf.fill;
+                    }
+                }
+                o[e4] = v;
+            }
+            if (s0 < nlane) *reinterpret_cast<int4*>(plane + s0) = make_int4(o[0], o[1], o[2], o[3]);
+        }
+        if (err) live = act = false;
+        if (act) {
+            // a predictive subframe with order == n never reaches s == order inside the loop: its headers still have to be read
+            if (!sf.started) {
+                const uint32_t e = parse_event(br, sf, endbit, rec);
+                if (e) { err = e; live = act = false; }
+            }
+            if (act && br.position() > endbit) { err = 1; live = act = false; }
+        }
+    }
+    if (exists && !wide) {
+        DecRec r;
+        r.err = err;
+        r.wide = 0;
+        r.end = 0;
+        if (!err) {
+            const unsigned long long end = ((br.position() + 7) >> 3) + 2;   // byte_align; CRC-16  (:1629-1630)
+            if (end > byte_end) r.err = 1;
+            r.end = end;
+        }
+        recs[c] = r;
+    }
+}
+
+// predict (src/decode.rs:1738-1752) over one plane, HB = predictor length (multiple of 4)
+template <int HB>
+__device__ __forceinline__ void restore_plane(int32_t* __restrict__ plane, uint32_t n4, uint32_t nmax4, uint32_t order, uint32_t shift,
+                                              uint32_t wasted, const SubRec* __restrict__ rec)
+{
+    constexpr int W = HB > 0 ? HB : 1;
+    int32_t q[W], w[W + 4];
+#pragma unroll
+    for (int j = 0; j < W; j++) q[j] = (HB > 0 && (uint32_t)j < order) ? (int32_t)rec->coef[j] : 0;
+#pragma unroll
+    for (int j = 0; j < W + 4; j++) w[j] = 0;
+    int4 a_next = make_int4(0, 0, 0, 0);
+    if (n4) a_next = *reinterpret_cast<const int4*>(plane);
+    for (uint32_t s0 = 0; s0 < nmax4; s0 += 4) {
+        const bool on = s0 < n4;
+        const int4 a = a_next;
+        if (s0 + 4 < n4) a_next = *reinterpret_cast<const int4*>(plane + s0 + 4);   // in flight while this group is restored
+        const int32_t v[4] = {a.x, a.y, a.z, a.w};
+        int32_t x[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            int32_t xe = v[e];
+            if (HB > 0) {
+                long long sum = 0;
+#pragma unroll
+                for (int j = 0; j < W; j++) sum = mad_wide_s32(w[W + e - 1 - j], q[j], sum);
+                const uint32_t pred = __funnelshift_r((uint32_t)(unsigned long long)sum, (uint32_t)((unsigned long long)sum >> 32), shift);
+                if (s0 + e >= order) xe = (int32_t)((uint32_t)xe + pred);   // warm-up samples are stored as they are
+                w[W + e] = xe;
+            }
+            x[e] = (int32_t)((uint32_t)xe << wasted);   // `<<= wasted_bps`  src/decode.rs:1671
+        }
+        if (on && (HB > 0 || wasted)) *reinterpret_cast<int4*>(plane + s0) = make_int4(x[0], x[1], x[2], x[3]);
+        if (HB > 0) {
+#pragma unroll
+            for (int j = 0; j < W; j++) w[j] = w[j + 4];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const FrameCand* __restrict__ cands, uint32_t ncand,
+                                                            const SubRec* __restrict__ subs, const DecRec* __restrict__ recs,
+                                                            int32_t* __restrict__ planes)
+{
+    const uint32_t t = blockIdx.x * RESTORE_THREADS + threadIdx.x;
+    const uint32_t c = t / cfg.channels, ch = t % cfg.channels;
+    uint32_t n = 0, order = 0, shift = 0, wasted = 0;
+    const SubRec* rec = subs;
+    if (c < ncand) {
+        const FrameCand fc = cands[c];
+        const uint32_t nch = fc.assignment <= 7 ? fc.assignment + 1u : 2u;
+        rec = subs + (size_t)c * cfg.channels + ch;
+        if (ch < nch && recs[c].err == 0 && rec->kind != 0xFF) {
+            n = fc.block_size;
+            order = rec->order;
+            shift = rec->shift;
+            wasted = rec->wasted;
+            if (order == 0 && wasted == 0) n = 0;   // constant / verbatim / fixed order 0: the plane already holds the samples
+        }
+    }
+    int32_t* plane = planes + ((size_t)(c < ncand ? c : 0) * cfg.nslots + ch) * cfg.bstride;
+    const uint32_t n4 = (n + 3u) & ~3u;
+    const uint32_t nmax4 = __reduce_max_sync(0xffffffffu, n4);
+    const uint32_t cls = __reduce_max_sync(0xffffffffu, n ? (order + 3u) >> 2 : 0u);
+    if (nmax4 == 0) return;
+    switch (cls) {
+    case 0: restore_plane<0>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    case 1: restore_plane<4>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    case 2: restore_plane<8>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    case 3: restore_plane<12>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    case 4: restore_plane<16>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    case 5: restore_plane<20>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    case 6: restore_plane<24>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    case 7: restore_plane<28>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    default: restore_plane<32>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    }
+}
+
+void launch_parse_restore(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes,
+                          SubRec* subs, DecRec* recs, cudaStream_t st)
+{
+    k_parse<<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs);
+    const uint32_t threads = n * cfg.channels;
+    k_restore<<<(threads + RESTORE_THREADS - 1) / RESTORE_THREADS, RESTORE_THREADS, 0, st>>>(cfg, cands, n, subs, recs, planes);
+}
+
+}   // namespace flacb200

@@ -43,7 +43,9 @@ cudaError_t launch_synth(uint8_t* pcm, unsigned long long first_track, unsigned 
 uint32_t find_tiles(unsigned long long nbytes);
 void launch_find_count(const DecCfg&, const uint8_t*, const DecSeg*, uint32_t*, uint32_t*, uint32_t*, cudaStream_t);
 void launch_find_write(const DecCfg&, const uint8_t*, const DecSeg*, const uint32_t*, FrameCand*, cudaStream_t);
-void launch_decode(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, DecRec*, cudaStream_t);
+void launch_decode(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, DecRec*, bool, cudaStream_t);
+// decode_parse.cu
+void launch_parse_restore(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, SubRec*, DecRec*, cudaStream_t);
 void launch_crc16f(const uint8_t*, const FrameCand*, uint32_t, DecRec*, cudaStream_t);
 cudaError_t launch_chain(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, DecRec*, uint32_t, const FrameCand*, uint32_t,
                          unsigned long long*, ChainState*, cudaStream_t);
@@ -746,13 +748,24 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     uint32_t group = (uint32_t)std::min<size_t>(std::max<size_t>(budget / per_frame, 1), std::max<uint32_t>(ncand, 1));
     if (e->chunk_frames) group = std::min<uint32_t>(group, e->chunk_frames);
     ENS(e->dec[9], (size_t)group * per_frame);
+    // FLACB200_LEGACY bit 64: the thread-per-frame decoder (k_decode) for everything; default: k_parse + k_restore, and
+    // k_decode only for frames with a 33-bit side channel (32-bit stereo streams)
+    const char* legacy_env = getenv("FLACB200_LEGACY");
+    const bool split_decode = !(legacy_env && (strtoul(legacy_env, nullptr, 0) & 64u));
+    const bool maybe_wide = cfg.channels == 2 && cfg.bps == 32;
+    if (split_decode) ENS(e->dec[10], (size_t)group * cfg.channels * sizeof(SubRec));
     size_t ngroups = 0;
     uint32_t g0 = 0;
     do {
         const uint32_t n = std::min<uint32_t>(group, ncand - g0);
         const FrameCand* after = g0 + n < ncand ? d_cands + g0 + n : nullptr;
         if (n) {
-            launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, st);
+            if (split_decode) {
+                launch_parse_restore(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, (SubRec*)e->dec[10].p, d_recs + g0, st);
+                if (maybe_wide) launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, true, st);
+            } else {
+                launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, false, st);
+            }
             time_mark(e, ev++);
             launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, st);
             time_mark(e, ev++);
@@ -762,7 +775,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
             time_mark(e, ev++);
             launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
             time_mark(e, ev++);
-            launches += 4;
+            launches += split_decode ? (maybe_wide ? 6 : 5) : 4;
             ngroups++;
         } else {
             launches += 1;

@@ -51,7 +51,7 @@ struct Md5 {
     w = rol(w, sft) + x;
 #define FLACB200_F(x, y, z) (z ^ (x & (y ^ z)))
 #define FLACB200_G(x, y, z) (y ^ (z & (x ^ y)))
-#define FLACB200_H(x, y, z) (x ^ y ^ z)
+#define FLACB200_MD5_H(x, y, z) (x ^ y ^ z)
 #define FLACB200_I(x, y, z) (y ^ (x | ~z))
         FLACB200_MD5_STEP(FLACB200_F, A, B, C, D, 0, 0xd76aa478u, 7)  FLACB200_MD5_STEP(FLACB200_F, D, A, B, C, 1, 0xe8c7b756u, 12)
         FLACB200_MD5_STEP(FLACB200_F, C, D, A, B, 2, 0x242070dbu, 17) FLACB200_MD5_STEP(FLACB200_F, B, C, D, A, 3, 0xc1bdceeeu, 22)
@@ -69,14 +69,14 @@ struct Md5 {
         FLACB200_MD5_STEP(FLACB200_G, C, D, A, B, 3, 0xf4d50d87u, 14) FLACB200_MD5_STEP(FLACB200_G, B, C, D, A, 8, 0x455a14edu, 20)
         FLACB200_MD5_STEP(FLACB200_G, A, B, C, D, 13, 0xa9e3e905u, 5) FLACB200_MD5_STEP(FLACB200_G, D, A, B, C, 2, 0xfcefa3f8u, 9)
         FLACB200_MD5_STEP(FLACB200_G, C, D, A, B, 7, 0x676f02d9u, 14) FLACB200_MD5_STEP(FLACB200_G, B, C, D, A, 12, 0x8d2a4c8au, 20)
-        FLACB200_MD5_STEP(FLACB200_H, A, B, C, D, 5, 0xfffa3942u, 4)  FLACB200_MD5_STEP(FLACB200_H, D, A, B, C, 8, 0x8771f681u, 11)
-        FLACB200_MD5_STEP(FLACB200_H, C, D, A, B, 11, 0x6d9d6122u, 16) FLACB200_MD5_STEP(FLACB200_H, B, C, D, A, 14, 0xfde5380cu, 23)
-        FLACB200_MD5_STEP(FLACB200_H, A, B, C, D, 1, 0xa4beea44u, 4)  FLACB200_MD5_STEP(FLACB200_H, D, A, B, C, 4, 0x4bdecfa9u, 11)
-        FLACB200_MD5_STEP(FLACB200_H, C, D, A, B, 7, 0xf6bb4b60u, 16) FLACB200_MD5_STEP(FLACB200_H, B, C, D, A, 10, 0xbebfbc70u, 23)
-        FLACB200_MD5_STEP(FLACB200_H, A, B, C, D, 13, 0x289b7ec6u, 4) FLACB200_MD5_STEP(FLACB200_H, D, A, B, C, 0, 0xeaa127fau, 11)
-        FLACB200_MD5_STEP(FLACB200_H, C, D, A, B, 3, 0xd4ef3085u, 16) FLACB200_MD5_STEP(FLACB200_H, B, C, D, A, 6, 0x04881d05u, 23)
-        FLACB200_MD5_STEP(FLACB200_H, A, B, C, D, 9, 0xd9d4d039u, 4)  FLACB200_MD5_STEP(FLACB200_H, D, A, B, C, 12, 0xe6db99e5u, 11)
-        FLACB200_MD5_STEP(FLACB200_H, C, D, A, B, 15, 0x1fa27cf8u, 16) FLACB200_MD5_STEP(FLACB200_H, B, C, D, A, 2, 0xc4ac5665u, 23)
+        FLACB200_MD5_STEP(FLACB200_MD5_H, A, B, C, D, 5, 0xfffa3942u, 4)  FLACB200_MD5_STEP(FLACB200_MD5_H, D, A, B, C, 8, 0x8771f681u, 11)
+        FLACB200_MD5_STEP(FLACB200_MD5_H, C, D, A, B, 11, 0x6d9d6122u, 16) FLACB200_MD5_STEP(FLACB200_MD5_H, B, C, D, A, 14, 0xfde5380cu, 23)
+        FLACB200_MD5_STEP(FLACB200_MD5_H, A, B, C, D, 1, 0xa4beea44u, 4)  FLACB200_MD5_STEP(FLACB200_MD5_H, D, A, B, C, 4, 0x4bdecfa9u, 11)
+        FLACB200_MD5_STEP(FLACB200_MD5_H, C, D, A, B, 7, 0xf6bb4b60u, 16) FLACB200_MD5_STEP(FLACB200_MD5_H, B, C, D, A, 10, 0xbebfbc70u, 23)
+        FLACB200_MD5_STEP(FLACB200_MD5_H, A, B, C, D, 13, 0x289b7ec6u, 4) FLACB200_MD5_STEP(FLACB200_MD5_H, D, A, B, C, 0, 0xeaa127fau, 11)
+        FLACB200_MD5_STEP(FLACB200_MD5_H, C, D, A, B, 3, 0xd4ef3085u, 16) FLACB200_MD5_STEP(FLACB200_MD5_H, B, C, D, A, 6, 0x04881d05u, 23)
+        FLACB200_MD5_STEP(FLACB200_MD5_H, A, B, C, D, 9, 0xd9d4d039u, 4)  FLACB200_MD5_STEP(FLACB200_MD5_H, D, A, B, C, 12, 0xe6db99e5u, 11)
+        FLACB200_MD5_STEP(FLACB200_MD5_H, C, D, A, B, 15, 0x1fa27cf8u, 16) FLACB200_MD5_STEP(FLACB200_MD5_H, B, C, D, A, 2, 0xc4ac5665u, 23)
         FLACB200_MD5_STEP(FLACB200_I, A, B, C, D, 0, 0xf4292244u, 6)  FLACB200_MD5_STEP(FLACB200_I, D, A, B, C, 7, 0x432aff97u, 10)
         FLACB200_MD5_STEP(FLACB200_I, C, D, A, B, 14, 0xab9423a7u, 15) FLACB200_MD5_STEP(FLACB200_I, B, C, D, A, 5, 0xfc93a039u, 21)
         FLACB200_MD5_STEP(FLACB200_I, A, B, C, D, 12, 0x655b59c3u, 6) FLACB200_MD5_STEP(FLACB200_I, D, A, B, C, 3, 0x8f0ccc92u, 10)
@@ -88,7 +88,7 @@ struct Md5 {
 #undef FLACB200_MD5_STEP
 #undef FLACB200_F
 #undef FLACB200_G
-#undef FLACB200_H
+#undef FLACB200_MD5_H
 #undef FLACB200_I
         a += A; b += B; c += C; d += D;
     }

@@ -21,6 +21,16 @@ def eng():
     e.close()
 
 
+@pytest.fixture(autouse=True, params=["parse+restore", "thread-per-frame"])
+def decode_path(request, monkeypatch):
+    """Every test runs over both decoders: k_parse + k_restore (default) and k_decode (FLACB200_LEGACY bit 64)."""
+    if request.param == "thread-per-frame":
+        monkeypatch.setenv("FLACB200_LEGACY", "64")
+    else:
+        monkeypatch.delenv("FLACB200_LEGACY", raising=False)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def fo():
     from oracle import oracle
