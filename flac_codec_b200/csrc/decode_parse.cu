@@ -39,40 +39,56 @@ __constant__ int16_t c_fixed_coeffs[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1,
 // are in flight as raw little-endian loads (r1, r2) and are byte-swapped only when they move into w1, so that a load
 // has two word periods to land.  Words are addressed relative to the lane's first word (32-bit index, one compare
 // against the number of whole words left in the buffer).
-// the last, partial word of the buffer (little-endian like a whole-word load); zero beyond it.  A free function taking
-// values: a member would take the address of the lane state and push all of it into local memory.
-static __device__ __noinline__ uint32_t load_tail_word(const uint8_t* bytes, unsigned long long nbytes, unsigned long long word)
+// Bit window of one lane: two consecutive big-endian words of the stream (w0, w1) and a bit offset pos < 32 into w0.
+// The stream behind them is staged through a per-lane ring of PARSE_RING words in shared memory that cp.async fills
+// PARSE_RING - 1 words ahead of the window: a lane walks its own frame, so every load of a warp touches 32 different
+// sectors and a few lanes miss L1 in every word period -- with the loads in registers the whole (lockstep) warp waited
+// for DRAM once per word (ncu: 60 % of all stall samples).  Words are addressed relative to the lane's first word; the
+// copy's src-size (0..4 bytes, rest zero-filled) keeps it inside the buffer, whatever its length.
+constexpr uint32_t PARSE_RING = 32;   // words per lane
+
+__device__ __forceinline__ void cp_async_word(uint32_t smem_addr, const void* gptr, uint32_t src_bytes)
 {
-    const unsigned long long b = word << 2;
-    uint32_t v = 0;
-    for (uint32_t k = 0; k < 4; k++)
-        if (b + k < nbytes) v |= (uint32_t)bytes[b + k] << (8 * k);
-    return v;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 struct LaneBits {
     const uint32_t* base;         // word `first` of the buffer
-    const uint8_t* bytes;
-    unsigned long long nbytes, first;
+    unsigned long long first;
     uint32_t limit;               // whole words available from `first` on (clamped to 32 bits)
+    uint32_t tail_bytes;          // bytes of the partial word at index `limit` (0..3)
+    uint32_t ring;                // shared-memory address of this lane's ring word 0 (words are PARSE_THREADS * 4 bytes apart)
     uint32_t rel;                 // w0 is word first + rel
-    uint32_t w0, w1, r1, r2, pos;
+    uint32_t w0, w1, r1, pos;     // r1: word rel + 2, still little-endian
 
-    __device__ __forceinline__ uint32_t load_raw(uint32_t i) const { return i < limit ? __ldg(base + i) : load_tail_word(bytes, nbytes, first + i); }
-    __device__ __forceinline__ void init(const uint8_t* buf, unsigned long long buf_bytes, unsigned long long bitpos)
+    __device__ __forceinline__ void request(uint32_t i)   // word first + i -> ring slot i % PARSE_RING
     {
-        bytes = buf;
-        nbytes = buf_bytes;
+        const uint32_t src = i < limit ? 4u : (i == limit ? tail_bytes : 0u);
+        cp_async_word(ring + (i & (PARSE_RING - 1)) * (PARSE_THREADS * 4), base + (i <= limit ? i : limit), src);
+    }
+    __device__ __forceinline__ uint32_t slot(uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + (i & (PARSE_RING - 1)) * (PARSE_THREADS * 4)) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void init(const uint8_t* buf, unsigned long long buf_bytes, unsigned long long bitpos, uint32_t ring_addr)
+    {
         first = bitpos >> 5;
-        base = reinterpret_cast<const uint32_t*>(buf) + first;
         const unsigned long long whole = buf_bytes >> 2;
-        limit = whole > first ? (uint32_t)min(whole - first, 0xFFFFFFFFull) : 0u;
+        limit = whole > first ? (uint32_t)min(whole - first, 0xFFFFFFF0ull) : 0u;
+        tail_bytes = whole >= first ? (uint32_t)(buf_bytes & 3) : 0u;
+        if (whole < first) first = whole;   // (never: a candidate starts inside the buffer)
+        base = reinterpret_cast<const uint32_t*>(buf) + first;
+        ring = ring_addr;
         rel = 0;
         pos = (uint32_t)(bitpos & 31);
-        w0 = __byte_perm(load_raw(0), 0, 0x0123);
-        w1 = __byte_perm(load_raw(1), 0, 0x0123);
-        r1 = load_raw(2);
-        r2 = load_raw(3);
+        for (uint32_t i = 0; i < PARSE_RING; i++) request(i);
+        asm volatile("cp.async.wait_group %0;" ::"n"(PARSE_RING - 3) : "memory");
+        w0 = __byte_perm(slot(0), 0, 0x0123);
+        w1 = __byte_perm(slot(1), 0, 0x0123);
+        r1 = slot(2);
     }
     __device__ __forceinline__ unsigned long long position() const { return ((first + rel) << 5) + pos; }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(w1, w0, pos); }   // the next 32 bits
@@ -82,9 +98,12 @@ struct LaneBits {
         if (pos >= 32) {
             w0 = w1;
             w1 = __byte_perm(r1, 0, 0x0123);
-            r1 = r2;
             rel++;
-            r2 = load_raw(rel + 3);
+            // PARSE_RING + rel - 1 words have been requested so far, one group each: word rel + 2 is complete once at
+            // most PARSE_RING - 4 groups are pending
+            asm volatile("cp.async.wait_group %0;" ::"n"(PARSE_RING - 4) : "memory");
+            r1 = slot(rel + 2);
+            request(rel + PARSE_RING - 1);   // into the slot of the word that just left the window
             pos -= 32;
         }
     }
@@ -225,8 +244,11 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
     const uint32_t ca = fc.assignment;
     const bool wide = exists && ca >= 8 && cfg.bps == 32;   // 33-bit side channel: k_decode handles the frame
     unsigned long long endbit = 0, byte_end = 0;
+    __shared__ uint32_t s_ring[PARSE_RING * PARSE_THREADS];
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x);
     LaneBits br;
-    br.init(bytes, cfg.nbytes, 0);
+    br.base = reinterpret_cast<const uint32_t*>(bytes);
+    br.first = 0; br.limit = 0; br.tail_bytes = 0; br.ring = ring_addr; br.rel = 0; br.w0 = br.w1 = br.r1 = 0; br.pos = 0;
     const uint32_t n = fc.block_size;
     uint32_t err = 0;
     bool live = exists && !wide;
@@ -234,7 +256,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
         const DecSeg sg = segs[fc.seg];
         byte_end = sg.byte_end;
         endbit = byte_end * 8;
-        br.init(bytes, cfg.nbytes, (fc.off + fc.hdr_len) * 8);
+        br.init(bytes, cfg.nbytes, (fc.off + fc.hdr_len) * 8, ring_addr);
         if (n > cfg.bstride) { err = 25; live = false; }   // cannot happen when max_block_size was honoured
     }
     const uint32_t nch = ca <= 7 ? ca + 1 : 2;
@@ -327,10 +349,14 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
     }
 }
 
-// predict (src/decode.rs:1738-1752) over one plane, HB = predictor length (multiple of 4)
+// predict (src/decode.rs:1738-1752) over one plane, HB = predictor length (multiple of 4).  The plane is read through
+// a ring of RESTORE_RING 128-bit groups per lane in shared memory, filled by cp.async RESTORE_RING groups ahead: every
+// lane reads its own plane, so a load in registers exposed the whole warp to DRAM latency once per group.
+constexpr uint32_t RESTORE_RING = 8;
+
 template <int HB>
 __device__ __forceinline__ void restore_plane(int32_t* __restrict__ plane, uint32_t n4, uint32_t nmax4, uint32_t order, uint32_t shift,
-                                              uint32_t wasted, const SubRec* __restrict__ rec)
+                                              uint32_t wasted, const SubRec* __restrict__ rec, int4* ring)
 {
     constexpr int W = HB > 0 ? HB : 1;
     int32_t q[W], w[W + 4];
@@ -338,12 +364,21 @@ __device__ __forceinline__ void restore_plane(int32_t* __restrict__ plane, uint3
     for (int j = 0; j < W; j++) q[j] = (HB > 0 && (uint32_t)j < order) ? (int32_t)rec->coef[j] : 0;
 #pragma unroll
     for (int j = 0; j < W + 4; j++) w[j] = 0;
-    int4 a_next = make_int4(0, 0, 0, 0);
-    if (n4) a_next = *reinterpret_cast<const int4*>(plane);
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
+    auto request = [&](uint32_t s0) {   // group at sample s0 -> slot (s0 / 4) % RESTORE_RING; one commit per call
+        if (s0 < n4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_addr + ((s0 >> 2) & (RESTORE_RING - 1)) * (RESTORE_THREADS * 16)),
+                         "l"(plane + s0)
+                         : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (uint32_t g = 0; g < RESTORE_RING; g++) request(g * 4);
     for (uint32_t s0 = 0; s0 < nmax4; s0 += 4) {
         const bool on = s0 < n4;
-        const int4 a = a_next;
-        if (s0 + 4 < n4) a_next = *reinterpret_cast<const int4*>(plane + s0 + 4);   // in flight while this group is restored
+        asm volatile("cp.async.wait_group %0;" ::"n"(RESTORE_RING - 1) : "memory");
+        int4 a = make_int4(0, 0, 0, 0);
+        if (on) a = ring[((s0 >> 2) & (RESTORE_RING - 1)) * RESTORE_THREADS];
         const int32_t v[4] = {a.x, a.y, a.z, a.w};
         int32_t x[4];
 #pragma unroll
@@ -360,17 +395,21 @@ __device__ __forceinline__ void restore_plane(int32_t* __restrict__ plane, uint3
             x[e] = (int32_t)((uint32_t)xe << wasted);   // `<<= wasted_bps`  src/decode.rs:1671
         }
         if (on && (HB > 0 || wasted)) *reinterpret_cast<int4*>(plane + s0) = make_int4(x[0], x[1], x[2], x[3]);
+        request(s0 + 4 * RESTORE_RING);   // into the slot just read (its value is in registers: x depends on it)
         if (HB > 0) {
 #pragma unroll
             for (int j = 0; j < W; j++) w[j] = w[j + 4];
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const FrameCand* __restrict__ cands, uint32_t ncand,
                                                             const SubRec* __restrict__ subs, const DecRec* __restrict__ recs,
                                                             int32_t* __restrict__ planes)
 {
+    __shared__ int4 s_ring[RESTORE_RING * RESTORE_THREADS];
+    int4* const ring = s_ring + threadIdx.x;
     const uint32_t t = blockIdx.x * RESTORE_THREADS + threadIdx.x;
     const uint32_t c = t / cfg.channels, ch = t % cfg.channels;
     uint32_t n = 0, order = 0, shift = 0, wasted = 0;
@@ -393,15 +432,15 @@ __global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const F
     const uint32_t cls = __reduce_max_sync(0xffffffffu, n ? (order + 3u) >> 2 : 0u);
     if (nmax4 == 0) return;
     switch (cls) {
-    case 0: restore_plane<0>(plane, n4, nmax4, order, shift, wasted, rec); break;
-    case 1: restore_plane<4>(plane, n4, nmax4, order, shift, wasted, rec); break;
-    case 2: restore_plane<8>(plane, n4, nmax4, order, shift, wasted, rec); break;
-    case 3: restore_plane<12>(plane, n4, nmax4, order, shift, wasted, rec); break;
-    case 4: restore_plane<16>(plane, n4, nmax4, order, shift, wasted, rec); break;
-    case 5: restore_plane<20>(plane, n4, nmax4, order, shift, wasted, rec); break;
-    case 6: restore_plane<24>(plane, n4, nmax4, order, shift, wasted, rec); break;
-    case 7: restore_plane<28>(plane, n4, nmax4, order, shift, wasted, rec); break;
-    default: restore_plane<32>(plane, n4, nmax4, order, shift, wasted, rec); break;
+    case 0: restore_plane<0>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
+    case 1: restore_plane<4>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
+    case 2: restore_plane<8>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
+    case 3: restore_plane<12>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
+    case 4: restore_plane<16>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
+    case 5: restore_plane<20>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
+    case 6: restore_plane<24>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
+    case 7: restore_plane<28>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
+    default: restore_plane<32>(plane, n4, nmax4, order, shift, wasted, rec, ring); break;
     }
 }
 
