@@ -13,7 +13,8 @@
 //              constant -- with the rare events (LPC parameters + residual coding header at s == order, partition headers
 //              at s == j * (n >> partition order); :1698-1733, :1800-1822) handled when a lane reaches them.  The bit
 //              window is two 32-bit big-endian words and a bit offset (one funnel shift per look), the word after them
-//              is requested one word ahead.  Output: the plane of each subframe holds [warm-up | residuals] (stored as
+//              comes from a shared-memory ring that cp.async fills seven 16-byte chunks ahead.  Groups of four samples
+//              in which every lane decodes plain Rice codes take a fast path without event or kind checks.  Output: the plane of each subframe holds [warm-up | residuals] (stored as
 //              aligned 128-bit groups, every lane at the same s), plus a SubRec (kind, order, shift, wasted bits,
 //              coefficients) per subframe and the DecRec (end offset, error) per frame.
 //   k_restore  lane per subframe: predict (:1738-1752) in place over the plane, coefficients and a sliding window of
@@ -39,73 +40,101 @@ __constant__ int16_t c_fixed_coeffs[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1,
 // are in flight as raw little-endian loads (r1, r2) and are byte-swapped only when they move into w1, so that a load
 // has two word periods to land.  Words are addressed relative to the lane's first word (32-bit index, one compare
 // against the number of whole words left in the buffer).
-// Bit window of one lane: two consecutive big-endian words of the stream (w0, w1) and a bit offset pos < 32 into w0.
-// The stream behind them is staged through a per-lane ring of PARSE_RING words in shared memory that cp.async fills
-// PARSE_RING - 1 words ahead of the window: a lane walks its own frame, so every load of a warp touches 32 different
-// sectors and a few lanes miss L1 in every word period -- with the loads in registers the whole (lockstep) warp waited
-// for DRAM once per word (ncu: 60 % of all stall samples).  Words are addressed relative to the lane's first word; the
-// copy's src-size (0..4 bytes, rest zero-filled) keeps it inside the buffer, whatever its length.
-constexpr uint32_t PARSE_RING = 32;   // words per lane
-
-__device__ __forceinline__ void cp_async_word(uint32_t smem_addr, const void* gptr, uint32_t src_bytes)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
+// Bit window of one lane: two consecutive big-endian words of the stream (w0, w1) and a bit offset pos < 32 into w0;
+// r1 is the word after them (still little-endian), read from shared memory one word period before it is needed.
+// The stream is staged through a per-lane ring of PARSE_CHUNKS 16-byte chunks in shared memory ([chunk][lane] layout),
+// filled by cp.async seven chunks ahead of the window.  A lane walks its own frame, so every load of a warp touches 32
+// different sectors and some lanes miss L1 in every word period: with the loads in registers the whole (lockstep) warp
+// waited for DRAM once per word (ncu: 60 % of all stall samples).
+//   * Requests are made at GROUP granularity (four samples): once per group every lane that has room requests one
+//     chunk, then ALL lanes commit one cp.async group and wait until at most three groups are pending.  The commit must be
+//     uniform: the hardware counts groups per warp, so with per-lane commits "all but the newest N" reached only a
+//     token or two back and every word waited for a fresh DRAM request.  A group consumes at most one chunk (4 x 32
+//     bits) in the common paths; the code that can consume more (subframe/LPC headers, unary runs longer than the
+//     window) calls ensure_now(), which tops the ring up and waits for everything.
+//   * Consuming bits is branch-free: pos += n; if that crossed a word, the window registers shift by selects and pos
+//     wraps with a mask -- a divergent `if` would be taken by some lane at almost every token.
+// Words are addressed relative to the chunk that holds the lane's first word; a request's src-size (0..16 bytes, rest
+// zero-filled) keeps it inside the buffer, whatever its length.
+constexpr uint32_t PARSE_CHUNKS = 8;                      // 128 bytes per lane
+constexpr uint32_t PARSE_SLOT = PARSE_THREADS * 16;       // bytes between consecutive chunks of a lane
+constexpr uint32_t PARSE_LEAD = PARSE_CHUNKS - 1;
 
 struct LaneBits {
-    const uint32_t* base;         // word `first` of the buffer
-    unsigned long long first;
-    uint32_t limit;               // whole words available from `first` on (clamped to 32 bits)
-    uint32_t tail_bytes;          // bytes of the partial word at index `limit` (0..3)
-    uint32_t ring;                // shared-memory address of this lane's ring word 0 (words are PARSE_THREADS * 4 bytes apart)
+    const uint4* base16;          // the 16-byte chunk that holds the lane's first word
+    unsigned long long first;     // word index of base16's first word
+    uint32_t nfull;               // whole chunks available from base16 on (clamped to 32 bits)
+    uint32_t tail_bytes;          // bytes of the partial chunk at index nfull (0..15)
+    uint32_t ring;                // shared-memory address of this lane's chunk slot 0
+    uint32_t req;                 // chunks 0 .. req - 1 have been requested
+    uint32_t roff;                // ring byte offset of word rel + 3 (the next one to become r1)
     uint32_t rel;                 // w0 is word first + rel
-    uint32_t w0, w1, r1, pos;     // r1: word rel + 2, still little-endian
+    uint32_t w0, w1, r1, pos;
 
-    __device__ __forceinline__ void request(uint32_t i)   // word first + i -> ring slot i % PARSE_RING
+    __device__ __forceinline__ void request_chunk()   // chunk req -> slot req % PARSE_CHUNKS (no commit)
     {
-        const uint32_t src = i < limit ? 4u : (i == limit ? tail_bytes : 0u);
-        cp_async_word(ring + (i & (PARSE_RING - 1)) * (PARSE_THREADS * 4), base + (i <= limit ? i : limit), src);
+        const uint32_t src = req < nfull ? 16u : (req == nfull ? tail_bytes : 0u);
+        const uint4* g = base16 + (req < nfull ? req : nfull);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(ring + (req & (PARSE_CHUNKS - 1)) * PARSE_SLOT), "l"(g), "r"(src)
+                     : "memory");
+        req++;
     }
-    __device__ __forceinline__ uint32_t slot(uint32_t i) const
+    // start of a group of four samples, executed by all lanes together
+    __device__ __forceinline__ void ensure_group()
+    {
+        if ((int32_t)(req - ((rel + 3) >> 2)) < (int32_t)PARSE_LEAD) request_chunk();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 3;" ::: "memory");
+        // (one-sample partitions with escaped residuals consume a little more than a chunk per group: catch up)
+        if ((int32_t)(req - ((rel + 3) >> 2)) < (int32_t)PARSE_LEAD - 2) ensure_now();
+    }
+    // before code that may consume more than a chunk at once
+    __device__ __forceinline__ void ensure_now()
+    {
+        while ((int32_t)(req - ((rel + 3) >> 2)) < (int32_t)PARSE_LEAD) request_chunk();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    static __device__ __forceinline__ uint32_t lds(uint32_t addr)
     {
         uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + (i & (PARSE_RING - 1)) * (PARSE_THREADS * 4)) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
         return v;
     }
+    static __device__ __forceinline__ uint32_t word_off(uint32_t w) { return ((w >> 2) & (PARSE_CHUNKS - 1)) * PARSE_SLOT + (w & 3) * 4; }
     __device__ __forceinline__ void init(const uint8_t* buf, unsigned long long buf_bytes, unsigned long long bitpos, uint32_t ring_addr)
     {
-        first = bitpos >> 5;
-        const unsigned long long whole = buf_bytes >> 2;
-        limit = whole > first ? (uint32_t)min(whole - first, 0xFFFFFFF0ull) : 0u;
-        tail_bytes = whole >= first ? (uint32_t)(buf_bytes & 3) : 0u;
-        if (whole < first) first = whole;   // (never: a candidate starts inside the buffer)
-        base = reinterpret_cast<const uint32_t*>(buf) + first;
+        const unsigned long long word = bitpos >> 5;
+        first = word & ~3ull;
+        const unsigned long long whole = buf_bytes >> 4, c0 = first >> 2;
+        nfull = whole > c0 ? (uint32_t)min(whole - c0, 0xFFFFFF00ull) : 0u;
+        tail_bytes = whole >= c0 ? (uint32_t)(buf_bytes & 15) : 0u;
+        base16 = reinterpret_cast<const uint4*>(buf) + (whole >= c0 ? c0 : whole);
         ring = ring_addr;
-        rel = 0;
+        req = 0;
+        rel = (uint32_t)(word & 3);
         pos = (uint32_t)(bitpos & 31);
-        for (uint32_t i = 0; i < PARSE_RING; i++) request(i);
-        asm volatile("cp.async.wait_group %0;" ::"n"(PARSE_RING - 3) : "memory");
-        w0 = __byte_perm(slot(0), 0, 0x0123);
-        w1 = __byte_perm(slot(1), 0, 0x0123);
-        r1 = slot(2);
+        ensure_now();   // chunks 0 .. 6
+        w0 = __byte_perm(lds(ring + word_off(rel)), 0, 0x0123);
+        w1 = __byte_perm(lds(ring + word_off(rel + 1)), 0, 0x0123);
+        r1 = lds(ring + word_off(rel + 2));
+        roff = word_off(rel + 3);
     }
     __device__ __forceinline__ unsigned long long position() const { return ((first + rel) << 5) + pos; }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(w1, w0, pos); }   // the next 32 bits
     __device__ __forceinline__ void skip(uint32_t n)   // n <= 32
     {
         pos += n;
-        if (pos >= 32) {
-            w0 = w1;
-            w1 = __byte_perm(r1, 0, 0x0123);
-            rel++;
-            // PARSE_RING + rel - 1 words have been requested so far, one group each: word rel + 2 is complete once at
-            // most PARSE_RING - 4 groups are pending
-            asm volatile("cp.async.wait_group %0;" ::"n"(PARSE_RING - 4) : "memory");
-            r1 = slot(rel + 2);
-            request(rel + PARSE_RING - 1);   // into the slot of the word that just left the window
-            pos -= 32;
-        }
+        const bool adv = pos >= 32;
+        const uint32_t nw = lds(ring + roff);   // (always a valid slot; used only when the window moves)
+        const uint32_t t = roff + 4;
+        const uint32_t nroff = (t & 12u) ? t : ((t + PARSE_SLOT - 16) & (PARSE_CHUNKS * PARSE_SLOT - 1));
+        w0 = adv ? w1 : w0;
+        w1 = adv ? __byte_perm(r1, 0, 0x0123) : w1;
+        r1 = adv ? nw : r1;
+        roff = adv ? nroff : roff;
+        rel += adv ? 1u : 0u;
+        pos &= 31u;
     }
     __device__ __forceinline__ uint32_t get(uint32_t n)   // n in 0..=32
     {
@@ -138,6 +167,7 @@ __device__ __forceinline__ uint32_t parse_event(LaneBits& br, LaneSub& sf, unsig
 {
     if (!sf.started) {
         sf.started = 1;
+        br.ensure_now();   // up to 4 + 5 + 32 * 15 bits of LPC parameters follow
         if (sf.kind == 3) {
             const uint32_t prec = br.get(4) + 1;
             if (prec > 15) return 49;   // InvalidQlpPrecision
@@ -150,6 +180,7 @@ __device__ __forceinline__ uint32_t parse_event(LaneBits& br, LaneSub& sf, unsig
             for (uint32_t j = 0; j < sf.order; j++) rec->coef[j] = c_fixed_coeffs[sf.order][j];
         }
         if (br.position() > endbit) return 1;
+        br.ensure_now();
         const uint32_t method = br.get(2);
         if (method > 1) return 45;   // InvalidCodingMethod
         sf.hb = method ? 5u : 4u;
@@ -179,6 +210,7 @@ __device__ __forceinline__ uint32_t parse_event(LaneBits& br, LaneSub& sf, unsig
 __device__ __forceinline__ uint32_t parse_subframe_header(LaneBits& br, LaneSub& sf, uint32_t bps, uint32_t n, unsigned long long endbit,
                                                            SubRec* __restrict__ rec)
 {
+    br.ensure_now();
     const uint32_t h = br.get(8);
     if (h & 0x80) return 41;   // InvalidSubframeHeader
     const uint32_t type = (h >> 1) & 0x3f;
@@ -195,9 +227,11 @@ __device__ __forceinline__ uint32_t parse_subframe_header(LaneBits& br, LaneSub&
             }
             q += 32;
             br.skip(32);
+            br.ensure_now();
             if (br.position() > endbit) return 1;
         }
         wasted = q + 1;
+        br.ensure_now();
     }
     uint32_t kind, order = 0;
     if (type == 0) kind = 0;
@@ -244,11 +278,11 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
     const uint32_t ca = fc.assignment;
     const bool wide = exists && ca >= 8 && cfg.bps == 32;   // 33-bit side channel: k_decode handles the frame
     unsigned long long endbit = 0, byte_end = 0;
-    __shared__ uint32_t s_ring[PARSE_RING * PARSE_THREADS];
+    __shared__ uint4 s_ring[PARSE_CHUNKS * PARSE_THREADS];
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x);
     LaneBits br;
-    br.base = reinterpret_cast<const uint32_t*>(bytes);
-    br.first = 0; br.limit = 0; br.tail_bytes = 0; br.ring = ring_addr; br.rel = 0; br.w0 = br.w1 = br.r1 = 0; br.pos = 0;
+    br.base16 = reinterpret_cast<const uint4*>(bytes);
+    br.first = 0; br.nfull = 0; br.tail_bytes = 0; br.ring = ring_addr; br.req = 0; br.roff = 0; br.rel = 0; br.w0 = br.w1 = br.r1 = 0; br.pos = 0;
     const uint32_t n = fc.block_size;
     uint32_t err = 0;
     bool live = exists && !wide;
@@ -280,8 +314,45 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
         int32_t* const plane = base + (size_t)ch * cfg.bstride;
         const uint32_t n4 = __reduce_max_sync(0xffffffffu, act ? (n + 3u) & ~3u : 0u);
         uint32_t nlane = act ? n : 0u;   // 0 once the lane has failed: it keeps walking the loop without reading
+        // one Rice code (src/decode.rs:1825-1827) of this lane; a code longer than the 32-bit window takes the slow branch
+        auto rice_token = [&]() -> int32_t {
+            const uint32_t win = br.window();
+            const uint32_t lz = (uint32_t)__clz((int)win);
+            const uint32_t total = lz + 1 + sf.k;
+            uint32_t u;
+            if (total <= 32) {   // the whole code sits in the window (win != 0)
+                const uint32_t lsb = __funnelshift_lc((win << lz) << 1, 0, sf.k);
+                u = (lz << sf.k) | lsb;
+                br.skip(total);
+            } else {
+                uint32_t msb = 0;
+                uint32_t w2 = win;
+                while (w2 == 0) {
+                    msb += 32;
+                    br.skip(32);
+                    br.ensure_now();
+                    if (br.position() > endbit) { err = 1; nlane = 0; break; }
+                    w2 = br.window();
+                }
+                const uint32_t lz2 = w2 ? (uint32_t)__clz((int)w2) : 0u;
+                br.skip(w2 ? lz2 + 1 : 0u);
+                msb += lz2;
+                br.ensure_now();
+                u = (msb << sf.k) | br.get(sf.k);
+            }
+            return (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+        };
         for (uint32_t s0 = 0; s0 < n4; s0 += 4) {
             int32_t o[4];
+            br.ensure_group();
+            // the common group: every lane of the warp is alive, inside a Rice partition, and has no event before s0 + 4
+            const bool plain = s0 + 4 <= nlane && sf.tk == TK_RICE && sf.ev_s - s0 >= 4;
+            if (__all_sync(0xffffffffu, plain)) {
+#pragma unroll
+                for (int e4 = 0; e4 < 4; e4++) o[e4] = rice_token();
+                *reinterpret_cast<int4*>(plane + s0) = make_int4(o[0], o[1], o[2], o[3]);
+                continue;
+            }
 #pragma unroll
             for (int e4 = 0; e4 < 4; e4++) {
                 const uint32_t s = s0 + e4;
@@ -291,35 +362,9 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
                         const uint32_t e = parse_event(br, sf, endbit, rec);
                         if (e) { err = e; nlane = 0; sf.tk = TK_FILL; sf.fill = 0; sf.ev_s = 0xFFFFFFFFu; }
                     }
-                    if (sf.tk == TK_RICE) {
-                        const uint32_t win = br.window();
-                        const uint32_t lz = (uint32_t)__clz((int)win);
-                        const uint32_t total = lz + 1 + sf.k;
-                        uint32_t u;
-                        if (total <= 32) {   // the whole code sits in the window (win != 0)
-                            const uint32_t lsb = __funnelshift_lc((win << lz) << 1, 0, sf.k);
-                            u = (lz << sf.k) | lsb;   // src/decode.rs:1827
-                            br.skip(total);
-                        } else {
-                            uint32_t msb = 0;
-                            uint32_t w2 = win;
-                            while (w2 == 0) {
-                                msb += 32;
-                                br.skip(32);
-                                if (br.position() > endbit) { err = 1; nlane = 0; break; }
-                                w2 = br.window();
-                            }
-                            const uint32_t lz2 = w2 ? (uint32_t)__clz((int)w2) : 0u;
-                            br.skip(w2 ? lz2 + 1 : 0u);
-                            msb += lz2;
-                            u = (msb << sf.k) | br.get(sf.k);
-                        }
-                        v = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-                    } else if (sf.tk == TK_RAW) {
-                        v = br.get_signed(sf.k);
-                    } else {
-                        v = sf.fill;
-                    }
+                    if (sf.tk == TK_RICE) v = rice_token();
+                    else if (sf.tk == TK_RAW) v = br.get_signed(sf.k);
+                    else v = sf.fill;
                 }
                 o[e4] = v;
             }
