@@ -75,7 +75,7 @@ struct LaneBits {
     {
         const uint32_t src = req < nfull ? 16u : (req == nfull ? tail_bytes : 0u);
         const uint4* g = base16 + (req < nfull ? req : nfull);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(ring + (req & (PARSE_CHUNKS - 1)) * PARSE_SLOT), "l"(g), "r"(src)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring + (req & (PARSE_CHUNKS - 1)) * PARSE_SLOT), "l"(g), "r"(src)
                      : "memory");
         req++;
     }
@@ -126,12 +126,13 @@ struct LaneBits {
     {
         pos += n;
         const bool adv = pos >= 32;
-        const uint32_t nw = lds(ring + roff);   // (always a valid slot; used only when the window moves)
+        uint32_t nw = r1;
+        if (adv) nw = lds(ring + roff);
         const uint32_t t = roff + 4;
         const uint32_t nroff = (t & 12u) ? t : ((t + PARSE_SLOT - 16) & (PARSE_CHUNKS * PARSE_SLOT - 1));
         w0 = adv ? w1 : w0;
         w1 = adv ? __byte_perm(r1, 0, 0x0123) : w1;
-        r1 = adv ? nw : r1;
+        r1 = nw;
         roff = adv ? nroff : roff;
         rel += adv ? 1u : 0u;
         pos &= 31u;
@@ -489,10 +490,14 @@ __global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const F
     }
 }
 
-void launch_parse_restore(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes,
-                          SubRec* subs, DecRec* recs, cudaStream_t st)
+void launch_parse(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes, SubRec* subs,
+                  DecRec* recs, cudaStream_t st)
 {
     k_parse<<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs);
+}
+
+void launch_restore(const DecCfg& cfg, const FrameCand* cands, uint32_t n, const SubRec* subs, const DecRec* recs, int32_t* planes, cudaStream_t st)
+{
     const uint32_t threads = n * cfg.channels;
     k_restore<<<(threads + RESTORE_THREADS - 1) / RESTORE_THREADS, RESTORE_THREADS, 0, st>>>(cfg, cands, n, subs, recs, planes);
 }

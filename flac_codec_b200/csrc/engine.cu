@@ -45,7 +45,8 @@ void launch_find_count(const DecCfg&, const uint8_t*, const DecSeg*, uint32_t*, 
 void launch_find_write(const DecCfg&, const uint8_t*, const DecSeg*, const uint32_t*, FrameCand*, cudaStream_t);
 void launch_decode(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, DecRec*, bool, cudaStream_t);
 // decode_parse.cu
-void launch_parse_restore(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, SubRec*, DecRec*, cudaStream_t);
+void launch_parse(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, SubRec*, DecRec*, cudaStream_t);
+void launch_restore(const DecCfg&, const FrameCand*, uint32_t, const SubRec*, const DecRec*, int32_t*, cudaStream_t);
 void launch_crc16f(const uint8_t*, const FrameCand*, uint32_t, DecRec*, cudaStream_t);
 cudaError_t launch_chain(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, DecRec*, uint32_t, const FrameCand*, uint32_t,
                          unsigned long long*, ChainState*, cudaStream_t);
@@ -759,26 +760,52 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     do {
         const uint32_t n = std::min<uint32_t>(group, ncand - g0);
         const FrameCand* after = g0 + n < ncand ? d_cands + g0 + n : nullptr;
-        if (n) {
-            if (split_decode) {
-                launch_parse_restore(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, (SubRec*)e->dec[10].p, d_recs + g0, st);
-                if (maybe_wide) launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, true, st);
-            } else {
-                launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, false, st);
+        if (n && split_decode) {
+            // k_parse, then two independent tails that meet before k_emit: predictor restoration over the planes on the
+            // engine's stream, and CRC-16 + the frame chain (which need only the end offsets k_parse found) on a second one
+            cudaStream_t aux = e->copy_in;
+            while (e->pipe_ev.size() < 3 * (ngroups + 1)) {
+                cudaEvent_t pe;
+                CK(cudaEventCreateWithFlags(&pe, cudaEventDisableTiming));
+                e->pipe_ev.push_back(pe);
             }
+            launch_parse(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, (SubRec*)e->dec[10].p, d_recs + g0, st);
+            if (maybe_wide) launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, true, st);
             time_mark(e, ev++);
-            launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, st);
+            // (k_chain is one CTA that wants a whole SM's shared memory: it has to be resident before k_restore floods the
+            // SMs, or it only starts when k_restore has drained -- so k_restore is held back until k_crc16f is done)
+            CK(cudaEventRecord(e->pipe_ev[3 * ngroups], st));
+            CK(cudaStreamWaitEvent(aux, e->pipe_ev[3 * ngroups], 0));
+            launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, aux);
+            CK(cudaEventRecord(e->pipe_ev[3 * ngroups + 1], aux));
+            CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, aux));
+            CK(cudaEventRecord(e->pipe_ev[3 * ngroups + 2], aux));
+            CK(cudaStreamWaitEvent(st, e->pipe_ev[3 * ngroups + 1], 0));
+            launch_restore(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, (int32_t*)e->dec[9].p, st);
+            CK(cudaStreamWaitEvent(st, e->pipe_ev[3 * ngroups + 2], 0));
             time_mark(e, ev++);
-        }
-        CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, st));
-        if (n) {
             time_mark(e, ev++);
             launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
             time_mark(e, ev++);
-            launches += split_decode ? (maybe_wide ? 6 : 5) : 4;
+            launches += maybe_wide ? 6 : 5;
             ngroups++;
         } else {
-            launches += 1;
+            if (n) {
+                launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, false, st);
+                time_mark(e, ev++);
+                launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, st);
+                time_mark(e, ev++);
+            }
+            CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, st));
+            if (n) {
+                time_mark(e, ev++);
+                launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
+                time_mark(e, ev++);
+                launches += 4;
+                ngroups++;
+            } else {
+                launches += 1;
+            }
         }
         g0 += n;
     } while (g0 < ncand);
