@@ -96,7 +96,7 @@ EXPORTS = [
     "flacb200_writer_write_bytes", "flacb200_writer_write_samples", "flacb200_writer_write_channels", "flacb200_writer_drain",
     "flacb200_writer_flush", "flacb200_writer_finalize", "flacb200_writer_get_stats", "flacb200_read_streaminfo",
     "flacb200_reader_open", "flacb200_reader_close", "flacb200_reader_info", "flacb200_reader_seektable", "flacb200_reader_read",
-    "flacb200_reader_seek", "flacb200_reader_verify", "flacb200_md5",
+    "flacb200_reader_seek", "flacb200_reader_verify", "flacb200_md5", "flacb200_md5_batch",
     "flacb200_options_default", "flacb200_options_fast", "flacb200_options_best", "flacb200_engine_create",
     "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_engine_set_keep_info", "flacb200_encode",
     "flacb200_encode_bound", "flacb200_encode_last_info", "flacb200_decode", "flacb200_set_profiling",
@@ -188,6 +188,9 @@ def lib():
     L.flacb200_reader_verify.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint8 * 16)]
     L.flacb200_md5.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint8 * 16)]
     L.flacb200_md5.restype = None
+    L.flacb200_md5_batch.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(Segment), C.c_size_t,
+                                     C.POINTER(C.c_uint8)]
+    L.flacb200_md5_batch.restype = C.c_int
     _lib = L
     return L
 

@@ -51,6 +51,15 @@ void launch_crc16f(const uint8_t*, const FrameCand*, uint32_t, DecRec*, cudaStre
 cudaError_t launch_chain(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, DecRec*, uint32_t, const FrameCand*, uint32_t,
                          unsigned long long*, ChainState*, cudaStream_t);
 void launch_emit(const DecCfg&, const FrameCand*, const DecRec*, const unsigned long long*, const int32_t*, uint32_t, uint8_t*, cudaStream_t);
+// md5.cu
+struct Md5Seg {
+    unsigned long long pcm_off, n_pcm;
+};
+struct Md5Cfg {
+    uint32_t channels, bytes_per_sample, pcm_kind, nseg;
+    unsigned long long planar_stride;
+};
+cudaError_t launch_md5(const Md5Cfg&, const uint8_t*, const Md5Seg*, uint32_t*, cudaStream_t);
 }   // namespace flacb200
 
 using namespace flacb200;
@@ -845,6 +854,55 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
         if (bad_frame) *bad_frame = state.err_frame;
         return state.err == 0x80000000u ? FLACB200_E_OUTPUT_TOO_SMALL : (int)state.err;
     }
+    return 0;
+}
+
+extern "C" int flacb200_md5_batch(flacb200_engine* e, const void* pcm, size_t pcm_bytes, int pcm_kind, int pcm_location, uint64_t planar_stride,
+                            uint32_t channels, uint32_t bits_per_sample, const flacb200_segment* segments, size_t n_segments, uint8_t* digests)
+{
+    if (!e || !segments || !digests || (!pcm && pcm_bytes)) return FLACB200_E_BAD_ARGUMENT;
+    if (channels < 1 || channels > 8) return 30;                 // ExcessiveChannels
+    if (bits_per_sample < 1 || bits_per_sample > 32) return 33;  // InvalidBitsPerSample
+    if (pcm_kind < 0 || pcm_kind > 3 || n_segments > 0xFFFFFFF0ull) return FLACB200_E_BAD_ARGUMENT;
+    if (n_segments == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    Md5Cfg cfg{};
+    cfg.channels = channels;
+    cfg.bytes_per_sample = (bits_per_sample + 7) / 8;   // of the MESSAGE (src/encode.rs:1292); int32 input is narrowed to it
+    cfg.pcm_kind = (uint32_t)pcm_kind;
+    cfg.nseg = (uint32_t)n_segments;
+    cfg.planar_stride = planar_stride;
+    const size_t in_sample_bytes = pcm_kind <= 1 ? cfg.bytes_per_sample : 4;
+    std::vector<Md5Seg> segs(n_segments);
+    for (size_t s = 0; s < n_segments; s++) {
+        const uint64_t end = segments[s].pcm_offset + segments[s].n_pcm_frames;
+        if (end < segments[s].pcm_offset) return FLACB200_E_BAD_ARGUMENT;
+        if (pcm_kind == FLACB200_PCM_I32_PLANAR) {
+            if (end > planar_stride || (size_t)planar_stride * channels * 4 > pcm_bytes) return FLACB200_E_BAD_ARGUMENT;
+        } else if (end * channels * in_sample_bytes > pcm_bytes) {
+            return FLACB200_E_BAD_ARGUMENT;
+        }
+        segs[s] = Md5Seg{segments[s].pcm_offset, segments[s].n_pcm_frames};
+    }
+    const uint8_t* d_pcm = (const uint8_t*)pcm;
+    if (pcm_location == FLACB200_HOST) {
+        ENS(e->pcm, pcm_bytes + 16);
+        CK(cudaMemcpyAsync(e->pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
+        d_pcm = (const uint8_t*)e->pcm.p;
+    }
+    ENS(e->dec[11], n_segments * (sizeof(Md5Seg) + 16));
+    Md5Seg* d_segs = (Md5Seg*)e->dec[11].p;
+    uint32_t* d_dig = (uint32_t*)((uint8_t*)e->dec[11].p + n_segments * sizeof(Md5Seg));
+    CK(cudaMemcpyAsync(d_segs, segs.data(), n_segments * sizeof(Md5Seg), cudaMemcpyHostToDevice, st));
+    cudaEventRecord(e->ev[22], st);
+    CK(launch_md5(cfg, d_pcm, d_segs, d_dig, st));
+    cudaEventRecord(e->ev[23], st);
+    CK(cudaMemcpyAsync(digests, d_dig, n_segments * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memset(&e->tm, 0, sizeof(e->tm));
+    cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
+    e->tm.launches = 1;
     return 0;
 }
 

@@ -186,6 +186,16 @@ class Engine:
         check(L.flacb200_encode_last_info(self._h, infos, n.value, C.byref(n)), "last_info")
         return infos, n.value
 
+    # -- MD5 of many streams (update_md5, src/encode.rs:1292; verify, src/decode.rs:1291) --
+    def md5(self, bps: int, channels: int, pcm, pcm_bytes: int, pcm_kind: int, segments: Sequence[tuple], *,
+            pcm_location: int = HOST, planar_stride: int = 0):
+        """segments: (pcm_offset, n_pcm_frames).  Returns one 16-byte digest per segment."""
+        segs = (Segment * len(segments))(*[Segment(s[0], s[1], 0) for s in segments])
+        out = np.zeros(16 * max(len(segments), 1), dtype=np.uint8)
+        check(_abi.lib().flacb200_md5_batch(self._h, _ptr(pcm), pcm_bytes, pcm_kind, pcm_location, planar_stride, channels, bps, segs,
+                                            len(segments), out.ctypes.data_as(C.POINTER(C.c_uint8))), "flacb200_md5_batch")
+        return [out[16 * i: 16 * i + 16].tobytes() for i in range(len(segments))]
+
     # -- decode --
     def decode(self, rate: int, bps: int, channels: int, max_block_size: int, frames, frames_bytes: int,
                segments: Sequence[tuple], pcm_out, pcm_out_bytes: int, pcm_kind: int, *, frames_location: int = HOST,

@@ -154,6 +154,17 @@ int flacb200_decode(flacb200_engine* e, const flacb200_stream_params* params, co
                     size_t n_segments, void* pcm_out, size_t pcm_out_bytes, int pcm_kind, int pcm_location,
                     uint64_t planar_stride, uint64_t* n_frames, uint64_t* n_pcm_frames, uint64_t* bad_frame);
 
+/*
+ * MD5 of many streams at once: the STREAMINFO signature the reference computes while encoding (update_md5,
+ * src/encode.rs:1292-1318) and checks in verify (src/decode.rs:1291-1309) -- MD5 over the samples as little-endian
+ * interleaved bytes, ceil(bits_per_sample / 8) bytes each.  One digest (16 bytes, host memory) per segment;
+ * segment.first_frame_number is ignored.  MD5 is serial per stream: the kernel runs one thread per segment, so this
+ * pays for batches (hundreds of tracks), not for a single stream.
+ */
+int flacb200_md5_batch(flacb200_engine* e, const void* pcm, size_t pcm_bytes, int pcm_kind, int pcm_location,
+                 uint64_t planar_stride, uint32_t channels, uint32_t bits_per_sample,
+                 const flacb200_segment* segments, size_t n_segments, uint8_t* digests);
+
 /* Device-side timing of the most recent encode/decode call, measured with CUDA events on the
  * engine's stream (milliseconds; kernels only, no copies). */
 typedef struct flacb200_timings {

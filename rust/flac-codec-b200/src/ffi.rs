@@ -98,6 +98,11 @@ unsafe extern "C" {
         n_pcm_frames: *mut u64, bad_frame: *mut u64,
     ) -> c_int;
     pub fn flacb200_strerror(code: c_int) -> *const c_char;
+    /// MD5 of many streams (update_md5, src/encode.rs:1292): one 16-byte digest per segment
+    pub fn flacb200_md5_batch(
+        e: *mut flacb200_engine, pcm: *const c_void, pcm_bytes: usize, pcm_kind: c_int, pcm_location: c_int, planar_stride: u64,
+        channels: u32, bits_per_sample: u32, segments: *const flacb200_segment, n_segments: usize, digests: *mut u8,
+    ) -> c_int;
 
     pub fn flacb200_writer_open(
         e: *mut flacb200_engine, opt: *const flacb200_writer_options, sample_rate: u32, bits_per_sample: u32, channels: u32,
