@@ -220,6 +220,8 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # keeps NCCL's banner out of stdout: rank 0 prints ONE line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from flac_codec_b200 import Engine, Options, _abi
