@@ -297,8 +297,10 @@ class FlacByteReader(_Reader):
     def read(self, size: int = -1) -> bytes:
         chunks = []
         want = size if size >= 0 else 1 << 62
+        known = self.decoded_len()
         while want > 0:
-            cap = min(want, 1 << 24)
+            # one call for the whole stream when its length is known (a fresh 16 MB buffer per call costs more than the decode)
+            cap = min(want, max(known, 1) if known is not None and size < 0 and not chunks else 1 << 24)
             buf = np.empty(cap, dtype=np.uint8)
             n = C.c_size_t(0)
             check(self._L.flacb200_reader_read(self._h, C.c_void_p(buf.ctypes.data), cap, self._kind, C.byref(n)), "read")

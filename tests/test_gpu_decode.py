@@ -242,6 +242,121 @@ def test_33_bit_side_channel(eng, fo):
         assert np.array_equal(planar.T, want)
 
 
+def put_residuals(b, rng, nres_first, nparts, chunk, method, kinds):
+    """Residual block (src/decode.rs:1800-1856) with one partition kind per partition, cycling through `kinds`:
+    ("rice", k, max_quotient) | ("raw", width) | ("zero",)."""
+    b.put(2, method)
+    porder = nparts.bit_length() - 1
+    b.put(4, porder)
+    pbits, esc = (5, 31) if method else (4, 15)
+    for p in range(nparts):
+        cnt = nres_first if p == 0 else chunk
+        kind = kinds[p % len(kinds)]
+        if kind[0] == "rice":
+            k, qmax = kind[1], kind[2]
+            b.put(pbits, k)
+            for _ in range(cnt):
+                q = int(rng.integers(0, qmax + 1))
+                b.put(q, 0)
+                b.put(1, 1)
+                if k:
+                    b.put(k, int(rng.integers(0, 1 << k)))
+        elif kind[0] == "raw":
+            w = kind[1]
+            b.put(pbits, esc)
+            b.put(5, w)
+            for _ in range(cnt):
+                b.put(w, int(rng.integers(0, 1 << w)))
+        else:
+            b.put(pbits, esc)
+            b.put(5, 0)
+
+
+def build_predictive_frame(fo, rng, frame_number, block, order, lpc, porder, method, kinds, wasted=0):
+    """One mono 32-bit frame with a FIXED (lpc=None) or LPC (lpc=(precision, shift)) subframe built bit by bit."""
+    b = Bits()
+    b.put(15, 0b111111111111100)
+    b.put(1, 0)
+    b.put(4, 0b0110 if block <= 256 else 0b0111)
+    b.put(4, 0b1001)
+    b.put(4, 0)        # one channel
+    b.put(3, 0b111)    # 32 bits per sample
+    b.put(1, 0)
+    b.put(8, frame_number)
+    b.put(8 if block <= 256 else 16, block - 1)
+    b.put(8, fo.crc8(b.bytes()))
+    b.put(1, 0)
+    b.put(6, (31 + order) if lpc else (8 + order))
+    if wasted:
+        b.put(1, 1)
+        b.put(wasted - 1, 0)
+        b.put(1, 1)
+    else:
+        b.put(1, 0)
+    ebps = 32 - wasted
+    for _ in range(order):
+        b.put(ebps, int(rng.integers(0, 1 << min(ebps, 20))))
+    if lpc:
+        prec, shift = lpc
+        b.put(4, prec - 1)
+        b.put(5, shift)
+        for _ in range(order):
+            b.put(prec, int(rng.integers(0, 1 << prec)))
+    nparts, chunk = 1 << porder, block >> porder
+    put_residuals(b, rng, chunk - order, nparts, chunk, method, kinds)
+    body = b.bytes()
+    return body + fo.crc16(body).to_bytes(2, "big")
+
+
+def test_hand_built_predictive_frames(eng, fo):
+    """Shapes no encoder here emits: one-sample partitions, Rice parameters up to 30, unary runs longer than the bit window,
+    raw (escaped) partitions of every width, LPC order 32 with 15-bit coefficients, wasted bits -- the GPU must produce
+    what the oracle's serial decoder produces for the same bytes."""
+    from flac_codec_b200 import _abi
+
+    rng = np.random.default_rng(99)
+    all_rice = [("rice", k, 3) for k in range(0, 31)]
+    long_runs = [("rice", 0, 200), ("rice", 3, 90), ("rice", 14, 40), ("rice", 30, 5)]
+    raws = [("raw", w) for w in range(1, 32)] + [("zero",)]
+    frames = [
+        build_predictive_frame(fo, rng, 0, 256, 0, None, 8, 1, all_rice + raws),               # one sample per partition
+        build_predictive_frame(fo, rng, 1, 256, 1, None, 7, 1, raws + long_runs),              # first partition: one residual
+        build_predictive_frame(fo, rng, 2, 256, 4, None, 5, 0, [("rice", k, 6) for k in range(15)] + [("raw", 9), ("zero",)]),
+        build_predictive_frame(fo, rng, 3, 256, 32, (15, 14), 2, 1, long_runs + [("raw", 31)]),
+        build_predictive_frame(fo, rng, 4, 256, 32, (15, 0), 0, 0, [("rice", 7, 70)]),
+        build_predictive_frame(fo, rng, 5, 256, 12, (12, 9), 3, 1, all_rice, wasted=5),
+        build_predictive_frame(fo, rng, 6, 256, 2, None, 6, 1, [("raw", 31), ("raw", 1), ("rice", 29, 2)], wasted=1),
+    ]
+    want = []
+    for f in frames:
+        planar, h, used = fo.decode_frame(f, None, 0)
+        assert used == len(f)
+        want.append(planar[0])
+    buf = np.frombuffer(b"".join(frames), dtype=np.uint8).copy()
+    n = 256 * len(frames)
+    out = np.zeros(n, dtype=np.int32)
+    nf, ns = eng.decode(44100, 32, 1, 256, buf, buf.size, [(0, buf.size, 0, n)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert (nf, ns) == (len(frames), n)
+    for k, w in enumerate(want):
+        assert np.array_equal(out[k * 256:(k + 1) * 256], w), k
+    # the same frames many times over, so that whole warps walk them in lockstep at different phases
+    reps = 70
+    order = rng.integers(0, len(frames), size=reps)
+    rebuilt = []   # re-numbered 0..69: CRC-8 and CRC-16 have to be rebuilt
+    for k, i in enumerate(order):
+        f = bytearray(frames[int(i)])
+        f[4] = k
+        f[6] = fo.crc8(bytes(f[:6]))
+        f[-2:] = fo.crc16(bytes(f[:-2])).to_bytes(2, "big")
+        rebuilt.append(bytes(f))
+    buf = np.frombuffer(b"".join(rebuilt), dtype=np.uint8).copy()
+    out = np.zeros(256 * reps, dtype=np.int32)
+    nf, ns = eng.decode(44100, 32, 1, 256, buf, buf.size, [(0, buf.size, 0, 256 * reps)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+    assert (nf, ns) == (reps, 256 * reps)
+    for k, i in enumerate(order):
+        assert np.array_equal(out[k * 256:(k + 1) * 256], want[int(i)]), (k, int(i))
+
+
 def test_sync_code_inside_payload_is_skipped(eng, fo):
     """A complete, CRC-8-valid frame header embedded in a VERBATIM payload is a false candidate: the walk that
     follows frame ends must skip it, exactly as the reference's serial reader never sees it."""
