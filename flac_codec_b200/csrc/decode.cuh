@@ -15,6 +15,17 @@ struct DecCfg {
     unsigned long long out_samples;  // capacity of the PCM output in inter-channel samples
 };
 
+// Scratch planes (decoded subframes before stereo restoration).  The 32 candidates of a bundle (candidate index / 32)
+// are interleaved in units of four samples: a warp whose lanes walk 32 frames (k_parse) or 32 subframes (k_restore) in
+// lockstep then reads and writes 512 contiguous bytes per step instead of 16 bytes in each of 32 planes.
+// Sample s of plane (c, ch) lives at int32 index plane_base(cfg, c, ch) + plane_off(s); groups of four samples
+// (s % 4 == 0) are 16-byte aligned.
+__host__ __device__ inline size_t plane_base(const DecCfg& cfg, uint32_t c, uint32_t ch)
+{
+    return (((size_t)(c >> 5) * cfg.nslots + ch) * (cfg.bstride >> 2) * 32 + (c & 31)) * 4;
+}
+__host__ __device__ inline uint32_t plane_off(uint32_t s) { return (s >> 2) * 128 + (s & 3); }
+
 struct DecSeg {
     unsigned long long byte_off, byte_end, pcm_off, n_pcm;
 };

@@ -365,15 +365,15 @@ struct PlaneWriter {
         if (ph == 0) o0 = v;
         else if (ph == 1) o1 = v;
         else if (ph == 2) o2 = v;
-        else *reinterpret_cast<int4*>(plane + (i - 3)) = make_int4(o0, o1, o2, v);
+        else *reinterpret_cast<int4*>(plane + plane_off(i - 3)) = make_int4(o0, o1, o2, v);
         i++;
     }
     __device__ inline void flush()
     {
         const uint32_t ph = i & 3, b = i - ph;
-        if (ph >= 1) plane[b] = o0;
-        if (ph >= 2) plane[b + 1] = o1;
-        if (ph >= 3) plane[b + 2] = o2;
+        if (ph >= 1) plane[plane_off(b)] = o0;
+        if (ph >= 2) plane[plane_off(b + 1)] = o1;
+        if (ph >= 3) plane[plane_off(b + 2)] = o2;
     }
 };
 
@@ -499,7 +499,7 @@ __device__ __forceinline__ uint32_t residual_loop_body(BitReader& br, PlaneWrite
             x = (int32_t)((uint32_t)r + (uint32_t)(unsigned long long)(sum >> rs.shift));
             hist[(sidx & 31) * DEC_THREADS] = x;
         }
-        plane[sidx] = (int32_t)((uint32_t)x << wasted);   // `<<= wasted_bps`  src/decode.rs:1671
+        plane[plane_off(sidx)] = (int32_t)((uint32_t)x << wasted);   // `<<= wasted_bps`  src/decode.rs:1671
     };
     while (idx < rs.nres && ((rs.order + idx) & 3u) != 0) {
         single();
@@ -530,7 +530,7 @@ __device__ __forceinline__ uint32_t residual_loop_body(BitReader& br, PlaneWrite
             xs[e] = (int32_t)((uint32_t)x << wasted);
         }
         if (fail) return fail;
-        *reinterpret_cast<int4*>(plane + sidx) = make_int4(xs[0], xs[1], xs[2], xs[3]);
+        *reinterpret_cast<int4*>(plane + plane_off(sidx)) = make_int4(xs[0], xs[1], xs[2], xs[3]);
         if (HB > 0) {
 #pragma unroll
             for (int j = 0; j < W; j++) w[j] = w[j + BLK];
@@ -639,10 +639,10 @@ __device__ uint32_t decode_subframe_wide(BitReader& br, uint32_t bps, uint32_t n
     if (wasted >= bps) return 43;
     const uint32_t ebps = bps - wasted;
     auto put = [&](uint32_t i, long long v) {
-        plane[i] = (int32_t)(uint32_t)(unsigned long long)v;
-        plane_hi[i] = (int32_t)(v >> 32);
+        plane[plane_off(i)] = (int32_t)(uint32_t)(unsigned long long)v;
+        plane_hi[plane_off(i)] = (int32_t)(v >> 32);
     };
-    auto at = [&](uint32_t i) -> long long { return (long long)(((unsigned long long)(uint32_t)plane_hi[i] << 32) | (uint32_t)plane[i]); };
+    auto at = [&](uint32_t i) -> long long { return (long long)(((unsigned long long)(uint32_t)plane_hi[plane_off(i)] << 32) | (uint32_t)plane[plane_off(i)]); };
     if (kind == 0) {
         const long long v = br.get_signed64(ebps);
         for (uint32_t i = 0; i < n; i++) put(i, v);
@@ -722,7 +722,6 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecCfg cfg, const uint8_
     br.endbit = sg.byte_end * 8;
     br.init((fc.off + fc.hdr_len) * 8);
     const uint32_t n = fc.block_size;
-    int32_t* base = planes + (size_t)c * cfg.nslots * cfg.bstride;
     int32_t* hist = s_hist + threadIdx.x;
     int16_t* coef = s_coef + threadIdx.x;
     uint32_t err = 0, wide = 0;
@@ -730,15 +729,15 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecCfg cfg, const uint8_
     const uint32_t ca = fc.assignment;
     if (!err) {
         if (ca <= 7) {
-            for (uint32_t ch = 0; ch <= ca && !err; ch++) err = decode_subframe(br, cfg.bps, n, base + (size_t)ch * cfg.bstride, hist, coef);
+            for (uint32_t ch = 0; ch <= ca && !err; ch++) err = decode_subframe(br, cfg.bps, n, planes + plane_base(cfg, c, ch), hist, coef);
         } else {
             // 8: left, side   9: side, right   10: mid, side   (src/decode.rs:1512-1626)
             const uint32_t side_first = ca == 9;
             wide = cfg.bps == 32;
             for (uint32_t ch = 0; ch < 2 && !err; ch++) {
                 const bool is_side = (ch == 0) == (side_first != 0);
-                if (is_side && wide) err = decode_subframe_wide(br, cfg.bps + 1, n, base + (size_t)ch * cfg.bstride, base + (size_t)2 * cfg.bstride);
-                else err = decode_subframe(br, is_side ? cfg.bps + 1 : cfg.bps, n, base + (size_t)ch * cfg.bstride, hist, coef);
+                if (is_side && wide) err = decode_subframe_wide(br, cfg.bps + 1, n, planes + plane_base(cfg, c, ch), planes + plane_base(cfg, c, 2));
+                else err = decode_subframe(br, is_side ? cfg.bps + 1 : cfg.bps, n, planes + plane_base(cfg, c, ch), hist, coef);
             }
         }
     }
@@ -1119,16 +1118,16 @@ __global__ void __launch_bounds__(256) k_emit(DecCfg cfg, const FrameCand* __res
     const FrameCand fc = cands[c];
     const uint32_t i = blockIdx.y * 256 + threadIdx.x;
     if (i >= fc.block_size) return;
-    const int32_t* base = planes + (size_t)c * cfg.nslots * cfg.bstride;
     const uint32_t ca = fc.assignment;
+    const uint32_t po = plane_off(i);
     if (ca <= 7) {
-        for (uint32_t ch = 0; ch <= ca; ch++) store_sample(out, cfg, p + i, ch, base[(size_t)ch * cfg.bstride + i]);
+        for (uint32_t ch = 0; ch <= ca; ch++) store_sample(out, cfg, p + i, ch, planes[plane_base(cfg, c, ch) + po]);
         return;
     }
-    const int32_t a = base[i], b = base[cfg.bstride + i];
+    const int32_t a = planes[plane_base(cfg, c, 0) + po], b = planes[plane_base(cfg, c, 1) + po];
     int32_t l, r;
     if (recs[c].wide) {
-        const long long hi = base[(size_t)2 * cfg.bstride + i];
+        const long long hi = planes[plane_base(cfg, c, 2) + po];
         if (ca == 8) {          // left, side(33 bit): right = left - side
             const long long side = (long long)(((unsigned long long)hi << 32) | (uint32_t)b);
             l = a;
@@ -1200,73 +1199,109 @@ cudaError_t launch_chain(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* 
     return cudaGetLastError();
 }
 
-// k_emit4: the common layouts (1 or 2 channels, 2 or 3 bytes per sample, packed bytes) with four samples per thread:
-// 128-bit plane loads, the group's 4 * C * B output bytes assembled in registers and stored as whole 32-bit words.
-// A frame whose output position is not word aligned falls back to sample-by-sample stores.
+// k_emit4: the common layouts (1 or 2 channels, 2 or 3 bytes per sample, packed bytes).  One CTA takes a bundle of 32
+// frames over 32 groups of four samples.  Phase 1 reads the interleaved planes the way they lie (a warp = 32 frames at
+// one group: 512 contiguous bytes per load), restores stereo (src/decode.rs:1524-1626), narrows and packs the group's
+// 4 * C * B output bytes (Frame::to_buf, src/audio.rs:110-134) into a shared-memory tile [frame][group]; phase 2 writes
+// every frame's run of the tile (up to 128 samples = 32 * C * B words) with whole-warp contiguous stores.
+constexpr uint32_t EMIT_GROUPS = 32;   // groups of four samples per tile
+
 template <int C, int B>
-__global__ void __launch_bounds__(256) k_emit4(DecCfg cfg, const FrameCand* __restrict__ cands, const DecRec* __restrict__ recs,
+__global__ void __launch_bounds__(256) k_emit4(DecCfg cfg, const FrameCand* __restrict__ cands, uint32_t ncand, const DecRec* __restrict__ recs,
                                                const unsigned long long* __restrict__ pos, const int32_t* __restrict__ planes,
                                                uint8_t* __restrict__ out)
 {
-    const uint32_t c = blockIdx.x;
-    const unsigned long long p = pos[c];
-    if (p == ~0ull) return;
-    const FrameCand fc = cands[c];
-    const uint32_t i = (blockIdx.y * 256 + threadIdx.x) * 4;
-    if (i >= fc.block_size) return;
-    const int32_t* base = planes + (size_t)c * cfg.nslots * cfg.bstride;
-    const uint32_t ca = fc.assignment;
-    int32_t v[4][C];
+    constexpr uint32_t CB = C * B;                       // words per group of four samples
+    constexpr uint32_t ROW = EMIT_GROUPS * CB + 1;       // words per frame row (+1: phase-1 stores of 32 frames hit 32 banks)
+    __shared__ uint32_t tile[32 * ROW];
+    __shared__ unsigned long long s_byte0[32];           // output byte of the frame's first sample in this tile (~0: nothing)
+    __shared__ uint32_t s_bytes[32];                     // valid bytes of the frame in this tile
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t c0 = blockIdx.x * 32;
+    const uint32_t i0 = blockIdx.y * EMIT_GROUPS * 4;    // first sample of the tile
+    const bool be = cfg.pcm_kind == 1;
     {
-        const int4 a = *reinterpret_cast<const int4*>(base + i);
-        const int32_t av[4] = {a.x, a.y, a.z, a.w};
-        if (C == 1) {
+        const uint32_t c = c0 + lane;
+        unsigned long long p = ~0ull;
+        uint32_t bs = 0, ca = 0;
+        if (c < ncand) {
+            p = pos[c];
+            const FrameCand fc = cands[c];
+            bs = fc.block_size;
+            ca = fc.assignment;
+        }
+        const bool live = p != ~0ull && i0 < bs;
+        if (wid == 0) {
+            s_byte0[lane] = live ? (p + i0) * (unsigned long long)(C * B) : ~0ull;
+            s_bytes[lane] = live ? min(bs - i0, EMIT_GROUPS * 4u) * (C * B) : 0u;
+        }
+        if (live) {
+            const int32_t* pa = planes + plane_base(cfg, c, 0);
+            const int32_t* pb = planes + plane_base(cfg, c, C - 1);
 #pragma unroll
-            for (int s = 0; s < 4; s++) v[s][0] = av[s];
-        } else {
-            const int4 b = *reinterpret_cast<const int4*>(base + cfg.bstride + i);
-            const int32_t bv[4] = {b.x, b.y, b.z, b.w};
+            for (uint32_t r = 0; r < EMIT_GROUPS / 8; r++) {
+                const uint32_t g = wid + 8 * r, i = i0 + 4 * g;
+                if (i >= bs) continue;
+                const int4 a = *reinterpret_cast<const int4*>(pa + plane_off(i));
+                const int32_t av[4] = {a.x, a.y, a.z, a.w};
+                int32_t v[4][C];
+                if (C == 1) {
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                int32_t l, r;
-                if (ca <= 7) { l = av[s]; r = bv[s]; }
-                else if (ca == 8) { l = av[s]; r = (int32_t)((uint32_t)av[s] - (uint32_t)bv[s]); }    // src/decode.rs:1524-1626
-                else if (ca == 9) { l = (int32_t)((uint32_t)av[s] + (uint32_t)bv[s]); r = bv[s]; }
-                else {
-                    const int32_t sum = (int32_t)((uint32_t)av[s] * 2u + (uint32_t)(bv[s] & 1));
-                    l = (int32_t)((uint32_t)sum + (uint32_t)bv[s]) >> 1;
-                    r = (int32_t)((uint32_t)sum - (uint32_t)bv[s]) >> 1;
+                    for (int s = 0; s < 4; s++) v[s][0] = av[s];
+                } else {
+                    const int4 b4 = *reinterpret_cast<const int4*>(pb + plane_off(i));
+                    const int32_t bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        int32_t l, rr;
+                        if (ca <= 7) { l = av[s]; rr = bv[s]; }
+                        else if (ca == 8) { l = av[s]; rr = (int32_t)((uint32_t)av[s] - (uint32_t)bv[s]); }
+                        else if (ca == 9) { l = (int32_t)((uint32_t)av[s] + (uint32_t)bv[s]); rr = bv[s]; }
+                        else {
+                            const int32_t sum = (int32_t)((uint32_t)av[s] * 2u + (uint32_t)(bv[s] & 1));
+                            l = (int32_t)((uint32_t)sum + (uint32_t)bv[s]) >> 1;
+                            rr = (int32_t)((uint32_t)sum - (uint32_t)bv[s]) >> 1;
+                        }
+                        v[s][0] = l;
+                        v[s][C - 1] = rr;
+                    }
                 }
-                v[s][0] = l;
-                v[s][C - 1] = r;
+                uint32_t w[CB];
+#pragma unroll
+                for (uint32_t k = 0; k < CB; k++) w[k] = 0;
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++)
+#pragma unroll
+                        for (int k = 0; k < B; k++) {
+                            const int idx = (s * C + ch) * B + k;
+                            const uint32_t byte = ((uint32_t)v[s][ch] >> (8 * (be ? B - 1 - k : k))) & 0xffu;
+                            w[idx >> 2] |= byte << (8 * (idx & 3));
+                        }
+#pragma unroll
+                for (uint32_t k = 0; k < CB; k++) tile[lane * ROW + g * CB + k] = w[k];
             }
         }
     }
-    const unsigned long long byte0 = (p + i) * (unsigned long long)(C * B);
-    const bool be = cfg.pcm_kind == 1;
-    if ((byte0 & 3) == 0 && i + 4 <= fc.block_size) {
-        uint32_t w[C * B];   // Frame::to_buf (src/audio.rs:110-134): 4 samples x C channels x B bytes
+    __syncthreads();
+    // phase 2: warp w writes frames 4w .. 4w + 3
 #pragma unroll
-        for (int k = 0; k < C * B; k++) w[k] = 0;
-#pragma unroll
-        for (int s = 0; s < 4; s++)
-#pragma unroll
-            for (int ch = 0; ch < C; ch++)
-#pragma unroll
-                for (int k = 0; k < B; k++) {
-                    const int idx = (s * C + ch) * B + k;
-                    const uint32_t byte = ((uint32_t)v[s][ch] >> (8 * (be ? B - 1 - k : k))) & 0xffu;
-                    w[idx >> 2] |= byte << (8 * (idx & 3));
-                }
-        uint32_t* dst = reinterpret_cast<uint32_t*>(out + byte0);
-#pragma unroll
-        for (int k = 0; k < C * B; k++) dst[k] = w[k];
-    } else {
-#pragma unroll
-        for (int s = 0; s < 4; s++)
-            if (i + s < fc.block_size)
-#pragma unroll
-                for (int ch = 0; ch < C; ch++) store_sample(out, cfg, p + i + s, ch, v[s][ch]);
+    for (uint32_t j = 0; j < 4; j++) {
+        const uint32_t f = wid * 4 + j;
+        const unsigned long long byte0 = s_byte0[f];
+        const uint32_t nbytes = s_bytes[f];
+        if (byte0 == ~0ull || nbytes == 0) continue;
+        const uint32_t* row = tile + f * ROW;
+        if (((reinterpret_cast<uintptr_t>(out) + byte0) & 3) == 0) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(out + byte0);
+            const uint32_t nw = nbytes >> 2;
+            for (uint32_t k = lane; k < nw; k += 32) dst[k] = row[k];
+            const uint32_t tail = nbytes & 3;   // a block that ends inside a word
+            if (lane < tail) out[byte0 + nw * 4 + lane] = (uint8_t)(row[nw] >> (8 * lane));
+        } else {
+            for (uint32_t k = lane; k < nbytes; k += 32) out[byte0 + k] = (uint8_t)(row[k >> 2] >> (8 * (k & 3)));
+        }
     }
 }
 
@@ -1276,11 +1311,11 @@ void launch_emit(const DecCfg& cfg, const FrameCand* cands, const DecRec* recs, 
     const bool packed = cfg.pcm_kind <= 1 && cfg.nslots == cfg.channels && (cfg.bytes_per_sample == 2 || cfg.bytes_per_sample == 3) &&
                         (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (cfg.bstride & 3) == 0;
     if (packed && cfg.channels <= 2) {
-        dim3 grid(n, (cfg.bstride / 4 + 255) / 256);
-        if (cfg.channels == 1 && cfg.bytes_per_sample == 2) k_emit4<1, 2><<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
-        else if (cfg.channels == 1) k_emit4<1, 3><<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
-        else if (cfg.bytes_per_sample == 2) k_emit4<2, 2><<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
-        else k_emit4<2, 3><<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
+        dim3 grid((n + 31) / 32, (cfg.bstride / 4 + EMIT_GROUPS - 1) / EMIT_GROUPS);
+        if (cfg.channels == 1 && cfg.bytes_per_sample == 2) k_emit4<1, 2><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
+        else if (cfg.channels == 1) k_emit4<1, 3><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
+        else if (cfg.bytes_per_sample == 2) k_emit4<2, 2><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
+        else k_emit4<2, 3><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
         return;
     }
     dim3 grid(n, (cfg.bstride + 255) / 256);

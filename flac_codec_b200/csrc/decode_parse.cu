@@ -298,7 +298,6 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
     SubRec* const myrec = subs + (size_t)(exists ? c : 0) * cfg.channels;
     if (exists && wide)
         for (uint32_t ch = 0; ch < cfg.channels; ch++) myrec[ch].kind = 0xFF;
-    int32_t* const base = planes + (size_t)(exists ? c : 0) * cfg.nslots * cfg.bstride;
     const uint32_t nch_max = __reduce_max_sync(0xffffffffu, live ? nch : 0u);
     for (uint32_t ch = 0; ch < nch_max; ch++) {
         bool act = live && ch < nch;
@@ -312,7 +311,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
             const uint32_t e = parse_subframe_header(br, sf, is_side ? cfg.bps + 1 : cfg.bps, n, endbit, rec);
             if (e) { err = e; live = act = false; }
         }
-        int32_t* const plane = base + (size_t)ch * cfg.bstride;
+        int32_t* const plane = planes + plane_base(cfg, exists ? c : 0, ch);   // groups of four samples are 128 words apart
         const uint32_t n4 = __reduce_max_sync(0xffffffffu, act ? (n + 3u) & ~3u : 0u);
         uint32_t nlane = act ? n : 0u;   // 0 once the lane has failed: it keeps walking the loop without reading
         // one Rice code (src/decode.rs:1825-1827) of this lane; a code longer than the 32-bit window takes the slow branch
@@ -351,7 +350,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
             if (__all_sync(0xffffffffu, plain)) {
 #pragma unroll
                 for (int e4 = 0; e4 < 4; e4++) o[e4] = rice_token();
-                *reinterpret_cast<int4*>(plane + s0) = make_int4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<int4*>(plane + plane_off(s0)) = make_int4(o[0], o[1], o[2], o[3]);
                 continue;
             }
 #pragma unroll
@@ -369,7 +368,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
                 }
                 o[e4] = v;
             }
-            if (s0 < nlane) *reinterpret_cast<int4*>(plane + s0) = make_int4(o[0], o[1], o[2], o[3]);
+            if (s0 < nlane) *reinterpret_cast<int4*>(plane + plane_off(s0)) = make_int4(o[0], o[1], o[2], o[3]);
         }
         if (err) live = act = false;
         if (act) {
@@ -414,7 +413,7 @@ __device__ __forceinline__ void restore_plane(int32_t* __restrict__ plane, uint3
     auto request = [&](uint32_t s0) {   // group at sample s0 -> slot (s0 / 4) % RESTORE_RING; one commit per call
         if (s0 < n4)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_addr + ((s0 >> 2) & (RESTORE_RING - 1)) * (RESTORE_THREADS * 16)),
-                         "l"(plane + s0)
+                         "l"(plane + plane_off(s0))
                          : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -440,7 +439,7 @@ __device__ __forceinline__ void restore_plane(int32_t* __restrict__ plane, uint3
             }
             x[e] = (int32_t)((uint32_t)xe << wasted);   // `<<= wasted_bps`  src/decode.rs:1671
         }
-        if (on && (HB > 0 || wasted)) *reinterpret_cast<int4*>(plane + s0) = make_int4(x[0], x[1], x[2], x[3]);
+        if (on && (HB > 0 || wasted)) *reinterpret_cast<int4*>(plane + plane_off(s0)) = make_int4(x[0], x[1], x[2], x[3]);
         request(s0 + 4 * RESTORE_RING);   // into the slot just read (its value is in registers: x depends on it)
         if (HB > 0) {
 #pragma unroll
@@ -456,8 +455,10 @@ __global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const F
 {
     __shared__ int4 s_ring[RESTORE_RING * RESTORE_THREADS];
     int4* const ring = s_ring + threadIdx.x;
+    // a warp = one channel of the 32 frames of a bundle: its plane accesses are 512 contiguous bytes
     const uint32_t t = blockIdx.x * RESTORE_THREADS + threadIdx.x;
-    const uint32_t c = t / cfg.channels, ch = t % cfg.channels;
+    const uint32_t wg = t >> 5;
+    const uint32_t c = (wg / cfg.channels) * 32 + (t & 31), ch = wg % cfg.channels;
     uint32_t n = 0, order = 0, shift = 0, wasted = 0;
     const SubRec* rec = subs;
     if (c < ncand) {
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const F
             if (order == 0 && wasted == 0) n = 0;   // constant / verbatim / fixed order 0: the plane already holds the samples
         }
     }
-    int32_t* plane = planes + ((size_t)(c < ncand ? c : 0) * cfg.nslots + ch) * cfg.bstride;
+    int32_t* plane = planes + plane_base(cfg, c < ncand ? c : 0, ch);
     const uint32_t n4 = (n + 3u) & ~3u;
     const uint32_t nmax4 = __reduce_max_sync(0xffffffffu, n4);
     const uint32_t cls = __reduce_max_sync(0xffffffffu, n ? (order + 3u) >> 2 : 0u);
@@ -498,7 +499,7 @@ void launch_parse(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, c
 
 void launch_restore(const DecCfg& cfg, const FrameCand* cands, uint32_t n, const SubRec* subs, const DecRec* recs, int32_t* planes, cudaStream_t st)
 {
-    const uint32_t threads = n * cfg.channels;
+    const uint32_t threads = ((n + 31) / 32) * 32 * cfg.channels;
     k_restore<<<(threads + RESTORE_THREADS - 1) / RESTORE_THREADS, RESTORE_THREADS, 0, st>>>(cfg, cands, n, subs, recs, planes);
 }
 

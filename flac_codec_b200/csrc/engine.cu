@@ -757,7 +757,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     size_t budget = (size_t)6 << 30;
     uint32_t group = (uint32_t)std::min<size_t>(std::max<size_t>(budget / per_frame, 1), std::max<uint32_t>(ncand, 1));
     if (e->chunk_frames) group = std::min<uint32_t>(group, e->chunk_frames);
-    ENS(e->dec[9], (size_t)group * per_frame);
+    ENS(e->dec[9], (size_t)((group + 31u) & ~31u) * per_frame);   // whole bundles of 32 interleaved planes
     // FLACB200_LEGACY bit 64: the thread-per-frame decoder (k_decode) for everything; default: k_parse + k_restore, and
     // k_decode only for frames with a 33-bit side channel (32-bit stereo streams)
     const char* legacy_env = getenv("FLACB200_LEGACY");
