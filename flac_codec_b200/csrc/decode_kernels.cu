@@ -1079,6 +1079,208 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(DecCfg cfg, const uint8
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_chain_fast: the frame walk of a group in which nothing is wrong.  Candidates are of two kinds: frames, and false
+// positives (a sync pattern with a valid CRC-8 inside a payload -- a few hundred in a 3.6 GB batch) that fail to decode.
+// The group is REGULAR when
+//   (1) every candidate that decoded and passed its CRC-16 starts a segment, or starts exactly where the nearest
+//       error-free candidate before it ends (or where the previous group said the walk continues);
+//   (2) it ends at the end of its segment, or exactly at a later candidate of its segment, and that candidate (if it
+//       belongs to this group) is error-free;
+//   (3) no failed candidate is a segment head or the expected continuation; every segment that starts in the group's
+//       byte range has its head among the candidates; no stream-end rule (src/decode.rs:1402-1410) fires.
+// Then the error-free candidates are exactly the frames the reference's serial reader visits (walk backwards from any of
+// them: offsets strictly decrease, so the predecessors end at a head), in candidate order, and the output positions
+// are a segmented prefix sum of their block sizes: no binary searches, no pointer jumping.  Anything else leaves
+// *clean != 1 and the group to k_chain, which reproduces the reference's error semantics.  Single CTA; unlike k_chain
+// it needs next to no shared memory, so it runs beside the kernels of the other stream.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t CHAINF_PER = 4;
+constexpr uint32_t CHAINF_SCAN = 16;   // false candidates skipped when looking for a neighbour (more: not regular)
+
+__global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const DecSeg* __restrict__ segs, const FrameCand* __restrict__ cands,
+                                                             const DecRec* __restrict__ recs, uint32_t n, uint32_t n_all,
+                                                             uint32_t group_first, unsigned long long* __restrict__ pos_out,
+                                                             ChainState* __restrict__ state, uint32_t* __restrict__ clean)
+{
+    __shared__ unsigned long long w_sum[32];
+    __shared__ uint32_t w_has[32];
+    __shared__ unsigned long long s_carry, s_samples;
+    __shared__ uint32_t s_bad, s_heads, s_mine, s_cont, s_last, s_frames;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const ChainState st = *state;
+    if (tid == 0) {
+        s_bad = (st.err != 0 || n == 0) ? 2u : 0u;
+        s_heads = 0;
+        s_mine = 0;
+        s_cont = 0;
+        s_frames = 0;
+        s_last = 0xFFFFFFFFu;
+        s_samples = 0;
+        s_carry = st.active ? st.seg_samples : 0;
+    }
+    __syncthreads();
+    if (n == 0) {
+        if (tid == 0) *clean = 0x102u;
+        return;
+    }
+    const unsigned long long first_off = cands[0].off, next_off = n < n_all ? cands[n].off : ~0ull;
+    {   // segments whose first byte lies in this group's byte range
+        uint32_t mine = 0;
+        for (uint32_t sgi = tid; sgi < cfg.nseg; sgi += CHAIN_THREADS) {
+            const DecSeg sg = segs[sgi];
+            if (sg.byte_end <= sg.byte_off) continue;
+            if ((group_first || sg.byte_off >= first_off) && sg.byte_off < next_off) mine++;
+        }
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0 && mine) atomicAdd(&s_mine, mine);
+    }
+    uint32_t bad = 0, heads = 0, frames = 0;
+    unsigned long long samples = 0;
+    for (uint32_t base = 0; base < n; base += CHAIN_THREADS * CHAINF_PER) {
+        unsigned long long ex[CHAINF_PER];   // samples of the open segment before candidate k, counted from the thread's start
+        uint32_t hb = 0, gb = 0;             // bit k: candidate k is a segment head / is a frame
+        unsigned long long sum = 0;
+        uint32_t has = 0;
+        uint32_t bs[CHAINF_PER];
+#pragma unroll
+        for (uint32_t k = 0; k < CHAINF_PER; k++) {
+            const uint32_t c = base + tid * CHAINF_PER + k;
+            ex[k] = 0;
+            bs[k] = 0;
+            if (c >= n) continue;
+            const FrameCand fc = cands[c];
+            const DecRec r = recs[c];
+            const DecSeg sg = segs[fc.seg];
+            const bool head = fc.off == sg.byte_off;
+            const bool expected = st.active && fc.seg == st.expect_seg && fc.off == st.expect_off;
+            if (r.err) {   // must be a false positive
+                if (head || expected) bad |= 4;
+                continue;
+            }
+            gb |= 1u << k;
+            frames++;
+            if (!head) {   // (1)
+                int j = (int)c - 1;
+                uint32_t steps = 0;
+                while (j >= 0 && recs[j].err != 0 && steps < CHAINF_SCAN) { j--; steps++; }
+                if (j < 0) {
+                    if (expected) atomicOr(&s_cont, 1u);
+                    else bad |= 8;
+                } else if (recs[j].err != 0 || cands[j].seg != fc.seg || recs[j].end != fc.off) {
+                    bad |= 8;
+                }
+            }
+            if (r.end != sg.byte_end) {   // (2)
+                uint32_t j = c + 1, steps = 0;
+                while (j < n_all && cands[j].off < r.end && steps < CHAINF_SCAN) { j++; steps++; }
+                if (!(j < n_all && cands[j].off == r.end && cands[j].seg == fc.seg)) bad |= 16;
+                else if (j < n) { if (recs[j].err) bad |= 16; }
+                else s_last = c;   // the walk leaves the group here (only one frame can)
+            }
+            if (head) {
+                hb |= 1u << k;
+                heads++;
+                sum = 0;
+                has = 1;
+            }
+            ex[k] = sum;
+            bs[k] = fc.block_size;
+            sum += fc.block_size;
+            samples += fc.block_size;
+        }
+        // block-wide inclusive segmented scan of (sum, has); exclusive value = what the threads before contribute
+        unsigned long long isum = sum;
+        uint32_t ihas = has;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long ts = __shfl_up_sync(0xffffffffu, isum, o);
+            const uint32_t th = __shfl_up_sync(0xffffffffu, ihas, o);
+            if (lane >= (uint32_t)o) {
+                if (!ihas) isum += ts;
+                ihas |= th;
+            }
+        }
+        __syncthreads();   // (w_sum / w_has of the previous chunk have been consumed)
+        if (lane == 31) {
+            w_sum[wid] = isum;
+            w_has[wid] = ihas;
+        }
+        __syncthreads();
+        // what precedes this thread inside the chunk: warps before it, then lanes before it
+        unsigned long long psum = 0;
+        uint32_t phas = 0;
+        for (uint32_t w = 0; w < wid; w++) {
+            if (w_has[w]) { psum = w_sum[w]; phas = 1; }
+            else psum += w_sum[w];
+        }
+        {
+            unsigned long long ls = __shfl_up_sync(0xffffffffu, isum, 1);
+            uint32_t lh = __shfl_up_sync(0xffffffffu, ihas, 1);
+            if (lane == 0) { ls = 0; lh = 0; }
+            if (lh) { psum = ls; phas = 1; }
+            else psum += ls;
+        }
+        const unsigned long long before = phas ? psum : s_carry + psum;   // samples of the open segment before this thread
+        uint32_t seen = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < CHAINF_PER; k++) {
+            const uint32_t c = base + tid * CHAINF_PER + k;
+            if (c >= n) continue;
+            if (!(gb & (1u << k))) {
+                pos_out[c] = ~0ull;
+                continue;
+            }
+            if (hb & (1u << k)) seen = 1;
+            const unsigned long long pos = seen ? ex[k] : before + ex[k];
+            const FrameCand fc = cands[c];
+            const DecSeg sg = segs[fc.seg];
+            if (sg.n_pcm) {   // (3) the rules of src/decode.rs:1402-1410 must all be silent
+                if (pos >= sg.n_pcm) bad |= 32;
+                else {
+                    const unsigned long long remaining = sg.n_pcm - pos;
+                    if (!(bs[k] == remaining || bs[k] > 14) || bs[k] > remaining) bad |= 32;
+                }
+                if (recs[c].end == sg.byte_end && pos + bs[k] < sg.n_pcm) bad |= 32;   // the bytes end early
+            }
+            if (sg.pcm_off + pos + bs[k] > cfg.out_samples) bad |= 64;
+            pos_out[c] = sg.pcm_off + pos;
+        }
+        __syncthreads();
+        if (tid == CHAIN_THREADS - 1) s_carry = has ? sum : (phas ? psum + sum : s_carry + psum + sum);   // the open segment at the end of the chunk
+        __syncthreads();
+    }
+    heads = __reduce_add_sync(0xffffffffu, heads);
+    frames = __reduce_add_sync(0xffffffffu, frames);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    samples = warp_sum_u64(samples);
+    if (lane == 0) {
+        if (heads) atomicAdd(&s_heads, heads);
+        if (frames) atomicAdd(&s_frames, frames);
+        if (bad) atomicOr(&s_bad, bad);
+        atomicAdd(&s_samples, samples);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const bool ok = s_bad == 0 && s_heads == s_mine && (st.active != 0) == (s_cont != 0);
+        *clean = ok ? 1u : (0x100u | s_bad | (s_heads != s_mine ? 128u : 0u) | ((st.active != 0) != (s_cont != 0) ? 0x200u : 0u));   // why not: FLACB200_DEBUG
+        if (ok) {
+            ChainState ns = st;
+            ns.frames_total = st.frames_total + s_frames;
+            ns.samples_total = st.samples_total + s_samples;
+            ns.active = 0;
+            if (s_last != 0xFFFFFFFFu) {   // the walk continues in the next group
+                const FrameCand fl = cands[s_last];
+                ns.active = 1;
+                ns.expect_seg = fl.seg;
+                ns.expect_off = recs[s_last].end;
+                ns.seg_samples = pos_out[s_last] - segs[fl.seg].pcm_off + fl.block_size;
+            }
+            *state = ns;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_emit: stereo restoration (src/decode.rs:1524-1626) + Frame::to_buf (src/audio.rs:110-134)
 // ------------------------------------------------------------------------------------------------
 __device__ inline void store_sample(uint8_t* __restrict__ out, const DecCfg& cfg, unsigned long long idx, uint32_t ch, int32_t v)
@@ -1197,6 +1399,12 @@ cudaError_t launch_chain(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* 
     }
     k_chain<<<1, CHAIN_THREADS, sizeof(ChainSmem), st>>>(cfg, bytes, segs, cands, recs, n, after, group_first, pos, state);
     return cudaGetLastError();
+}
+
+void launch_chain_fast(const DecCfg& cfg, const DecSeg* segs, const FrameCand* cands, const DecRec* recs, uint32_t n, uint32_t n_all,
+                       uint32_t group_first, unsigned long long* pos, ChainState* state, uint32_t* clean, cudaStream_t st)
+{
+    k_chain_fast<<<1, CHAIN_THREADS, 0, st>>>(cfg, segs, cands, recs, n, n_all, group_first, pos, state, clean);
 }
 
 // k_emit4: the common layouts (1 or 2 channels, 2 or 3 bytes per sample, packed bytes).  One CTA takes a bundle of 32

@@ -51,6 +51,8 @@ void launch_crc16f(const uint8_t*, const FrameCand*, uint32_t, DecRec*, cudaStre
 cudaError_t launch_chain(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, DecRec*, uint32_t, const FrameCand*, uint32_t,
                          unsigned long long*, ChainState*, cudaStream_t);
 void launch_emit(const DecCfg&, const FrameCand*, const DecRec*, const unsigned long long*, const int32_t*, uint32_t, uint8_t*, cudaStream_t);
+void launch_chain_fast(const DecCfg&, const DecSeg*, const FrameCand*, const DecRec*, uint32_t, uint32_t, uint32_t, unsigned long long*, ChainState*,
+                       uint32_t*, cudaStream_t);
 // md5.cu
 struct Md5Seg {
     unsigned long long pcm_off, n_pcm;
@@ -781,22 +783,28 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
             launch_parse(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, (SubRec*)e->dec[10].p, d_recs + g0, st);
             if (maybe_wide) launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, true, st);
             time_mark(e, ev++);
-            // (k_chain is one CTA that wants a whole SM's shared memory: it has to be resident before k_restore floods the
-            // SMs, or it only starts when k_restore has drained -- so k_restore is held back until k_crc16f is done)
+            // The tails: predictor restoration on the engine's stream; CRC-16 and the frame walk on the second one.  The
+            // walk is k_chain_fast when the candidates are exactly the frames (the host reads its verdict: a 4-byte copy and
+            // a sync of the second stream, while k_restore keeps the GPU busy), else k_chain -- one CTA that wants a whole
+            // SM's shared memory and therefore only starts once k_restore has drained.
+            uint32_t* d_clean = (uint32_t*)((uint8_t*)e->dec[5].p + 192);
             CK(cudaEventRecord(e->pipe_ev[3 * ngroups], st));
+            launch_restore(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, (int32_t*)e->dec[9].p, st);
             CK(cudaStreamWaitEvent(aux, e->pipe_ev[3 * ngroups], 0));
             launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, aux);
-            CK(cudaEventRecord(e->pipe_ev[3 * ngroups + 1], aux));
-            CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, aux));
+            launch_chain_fast(cfg, d_segs, d_cands + g0, d_recs + g0, n, ncand - g0, g0 == 0, d_pos + g0, d_state, d_clean, aux);
+            uint32_t clean = 0;
+            CK(cudaMemcpyAsync(&clean, d_clean, 4, cudaMemcpyDeviceToHost, aux));
+            CK(cudaStreamSynchronize(aux));
+            if (clean != 1 && getenv("FLACB200_DEBUG")) fprintf(stderr, "flacb200: k_chain_fast declined group at %u (reason 0x%x)\n", g0, clean);
+            if (clean != 1) CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, aux));
             CK(cudaEventRecord(e->pipe_ev[3 * ngroups + 2], aux));
-            CK(cudaStreamWaitEvent(st, e->pipe_ev[3 * ngroups + 1], 0));
-            launch_restore(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, (int32_t*)e->dec[9].p, st);
             CK(cudaStreamWaitEvent(st, e->pipe_ev[3 * ngroups + 2], 0));
             time_mark(e, ev++);
             time_mark(e, ev++);
             launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
             time_mark(e, ev++);
-            launches += maybe_wide ? 6 : 5;
+            launches += 5u + (maybe_wide ? 1u : 0u) + (clean == 1 ? 0u : 1u);
             ngroups++;
         } else {
             if (n) {

@@ -34,7 +34,7 @@ def run(eng, name, rate, bps, ch, secs, opt, block):
     tm = eng.timings()
     assert np.array_equal(out, x)
     print(json.dumps({"stream": name, "frames": int(nf), "call_ms": best * 1e3,
-                      "kernel_ms": {DN[k]: round(tm.kernel_ms[k], 3) for k in range(5) if DN[k]}, "h2d_ms": tm.h2d_ms, "d2h_ms": tm.d2h_ms,
+                      "kernel_ms": {DN[k]: round(tm.kernel_ms[k], 3) for k in range(5) if DN[k]}, "launches": tm.launches, "h2d_ms": tm.h2d_ms, "d2h_ms": tm.d2h_ms,
                       "msamples_per_s": x.size / best / 1e6}), flush=True)
 
 
