@@ -54,17 +54,28 @@ __constant__ int16_t c_fixed_coeffs[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1,
 //     window) calls ensure_now(), which tops the ring up and waits for everything.
 //   * Consuming bits is branch-free: pos += n; if that crossed a word, the window registers shift by selects and pos
 //     wraps with a mask -- a divergent `if` would be taken by some lane at almost every token.
-// Words are addressed relative to the chunk that holds the lane's first word; a request's src-size (0..16 bytes, rest
-// zero-filled) keeps it inside the buffer, whatever its length.
+// Words are addressed relative to the chunk that holds the lane's first word; chunks at and beyond the end of the
+// buffer are filled synchronously from the bytes that exist, so no access leaves the buffer, whatever its length.
 constexpr uint32_t PARSE_CHUNKS = 8;                      // 128 bytes per lane
 constexpr uint32_t PARSE_SLOT = PARSE_THREADS * 16;       // bytes between consecutive chunks of a lane
 constexpr uint32_t PARSE_LEAD = PARSE_CHUNKS - 1;
 
+// the chunks at and beyond the end of the buffer: the bytes that exist, zeros after them, stored synchronously (a
+// 16-byte cp.async with a short src-size would still be a 16-byte access that crosses the end of the caller's buffer)
+static __device__ __noinline__ void fill_tail_chunk(uint32_t smem_addr, const uint8_t* bytes, unsigned long long nbytes, unsigned long long byte_off)
+{
+    uint32_t t[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < 16; i++)
+        if (byte_off + i < nbytes) t[i >> 2] |= (uint32_t)bytes[byte_off + i] << (8 * (i & 3));
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]) : "memory");
+}
+
 struct LaneBits {
     const uint4* base16;          // the 16-byte chunk that holds the lane's first word
+    const uint8_t* bytes;         // the whole buffer (only the chunks at its end are read through this)
+    unsigned long long nbytes;
     unsigned long long first;     // word index of base16's first word
     uint32_t nfull;               // whole chunks available from base16 on (clamped to 32 bits)
-    uint32_t tail_bytes;          // bytes of the partial chunk at index nfull (0..15)
     uint32_t ring;                // shared-memory address of this lane's chunk slot 0
     uint32_t req;                 // chunks 0 .. req - 1 have been requested
     uint32_t roff;                // ring byte offset of word rel + 3 (the next one to become r1)
@@ -73,10 +84,9 @@ struct LaneBits {
 
     __device__ __forceinline__ void request_chunk()   // chunk req -> slot req % PARSE_CHUNKS (no commit)
     {
-        const uint32_t src = req < nfull ? 16u : (req == nfull ? tail_bytes : 0u);
-        const uint4* g = base16 + (req < nfull ? req : nfull);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring + (req & (PARSE_CHUNKS - 1)) * PARSE_SLOT), "l"(g), "r"(src)
-                     : "memory");
+        const uint32_t slot = ring + (req & (PARSE_CHUNKS - 1)) * PARSE_SLOT;
+        if (req < nfull) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(base16 + req) : "memory");
+        else fill_tail_chunk(slot, bytes, nbytes, ((first >> 2) + req) << 4);
         req++;
     }
     // start of a group of four samples, executed by all lanes together
@@ -108,8 +118,9 @@ struct LaneBits {
         first = word & ~3ull;
         const unsigned long long whole = buf_bytes >> 4, c0 = first >> 2;
         nfull = whole > c0 ? (uint32_t)min(whole - c0, 0xFFFFFF00ull) : 0u;
-        tail_bytes = whole >= c0 ? (uint32_t)(buf_bytes & 15) : 0u;
-        base16 = reinterpret_cast<const uint4*>(buf) + (whole >= c0 ? c0 : whole);
+        bytes = buf;
+        nbytes = buf_bytes;
+        base16 = reinterpret_cast<const uint4*>(buf) + c0;   // (only dereferenced for chunks below nfull)
         ring = ring_addr;
         req = 0;
         rel = (uint32_t)(word & 3);
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x);
     LaneBits br;
     br.base16 = reinterpret_cast<const uint4*>(bytes);
-    br.first = 0; br.nfull = 0; br.tail_bytes = 0; br.ring = ring_addr; br.req = 0; br.roff = 0; br.rel = 0; br.w0 = br.w1 = br.r1 = 0; br.pos = 0;
+    br.bytes = bytes; br.nbytes = cfg.nbytes; br.first = 0; br.nfull = 0; br.ring = ring_addr; br.req = 0; br.roff = 0; br.rel = 0; br.w0 = br.w1 = br.r1 = 0; br.pos = 0;
     const uint32_t n = fc.block_size;
     uint32_t err = 0;
     bool live = exists && !wide;
