@@ -16,7 +16,7 @@ from flac_codec_b200 import Engine, _abi, stream  # noqa: E402
 from flacb200_testutil import synth_pcm  # noqa: E402
 from oracle import oracle as fo  # noqa: E402
 
-DN = ["k_find+k_scan", "k_parse", "k_restore || k_crc16f+k_chain", None, "k_emit"]
+DN = ["k_find+k_scan", "k_parse", "k_restore || k_crc16f+k_chain_fast", None, "k_emit"]
 
 
 def run(eng, name, rate, bps, ch, secs, opt, block):
