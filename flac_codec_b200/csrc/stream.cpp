@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <mutex>
 #include <vector>
 
 #include "../../include/flacb200_stream.h"
@@ -151,6 +152,42 @@ struct SeekPt {
 };
 
 // growable byte buffer, pinned when a device is present (cudaMemcpyAsync from pageable memory is staged and slow)
+// Pinning host memory costs milliseconds (cudaHostAlloc of the 15 MB a one-minute stream decodes to: 3-5 ms, more than the
+// decode itself), and readers/writers are opened and closed per stream: released pinned buffers are parked here and handed
+// to the next handle that asks for about that size.
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<uint8_t*, size_t>> parked;
+    size_t parked_bytes = 0;
+    static constexpr size_t LIMIT = (size_t)512 << 20;
+    uint8_t* take(size_t want, size_t* cap)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        size_t best = parked.size();
+        for (size_t i = 0; i < parked.size(); i++)
+            if (parked[i].second >= want && parked[i].second <= want * 2 + (1 << 20) && (best == parked.size() || parked[i].second < parked[best].second)) best = i;
+        if (best == parked.size()) return nullptr;
+        uint8_t* p = parked[best].first;
+        *cap = parked[best].second;
+        parked_bytes -= parked[best].second;
+        parked.erase(parked.begin() + (long)best);
+        return p;
+    }
+    void give(uint8_t* p, size_t cap)
+    {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (parked_bytes + cap <= LIMIT && parked.size() < 64) {
+                parked.emplace_back(p, cap);
+                parked_bytes += cap;
+                return;
+            }
+        }
+        flacb200_host_free(p);
+    }
+};
+static PinnedPool g_pinned_pool;
+
 struct HostBuf {
     uint8_t* p = nullptr;
     size_t cap = 0, len = 0;
@@ -159,7 +196,7 @@ struct HostBuf {
     void release()
     {
         if (!p) return;
-        if (pinned) flacb200_host_free(p);
+        if (pinned) g_pinned_pool.give(p, cap);
         else free(p);
         p = nullptr;
         cap = len = 0;
@@ -171,7 +208,8 @@ struct HostBuf {
         uint8_t* np = nullptr;
         bool npinned = false;
         if (try_pinned) {
-            np = (uint8_t*)flacb200_host_alloc(ncap);
+            np = g_pinned_pool.take(ncap, &ncap);
+            if (!np) np = (uint8_t*)flacb200_host_alloc(ncap);
             npinned = np != nullptr;
         }
         if (!np) np = (uint8_t*)malloc(ncap);
