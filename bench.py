@@ -159,6 +159,29 @@ def ncu_traffic(kernel):
     return None
 
 
+def ncu_pipes(kernel):
+    """Issue-slot and pipe utilisation (% of peak while active) of `kernel` from the newest committed ncu summary, or None:
+    what bounds a kernel that is far from the HBM roofline (the north star asks for FP64 / INT32 pipe utilisation)."""
+    import csv
+    import glob
+
+    keys = {"issue_slots": "smsp__issue_active.avg.pct_of_peak_sustained_active", "alu": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "fma": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fp64": "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+            "lsu": "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "warps_active": "sm__warps_active.avg.pct_of_peak_sustained_active"}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full_summary.csv")), reverse=True):
+        try:
+            with open(path, newline="") as f:
+                rows = list(csv.reader(f))
+            hdr = rows[0]
+            ik = hdr.index("Kernel Name")
+            for r in rows[2:]:
+                if kernel.split("+")[0] in r[ik]:
+                    return {"source": os.path.basename(path), **{k: float(r[hdr.index(v)]) for k, v in keys.items() if v in hdr}}
+        except (OSError, ValueError, IndexError):
+            continue
+    return None
+
+
 def host_tracks_numpy(n_tracks, seconds):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from flacb200_testutil import synth_pcm
@@ -299,7 +322,7 @@ def run_gpu(args):
     achieved = alg_bytes_launch / (avg_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": ncu_traffic(names[top]), "algorithmic_bytes_per_launch": alg_bytes_launch, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        "traffic": ncu_traffic(names[top]), "pipe_util_pct": ncu_pipes(names[top]), "algorithmic_bytes_per_launch": alg_bytes_launch, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
         "algorithmic_bytes_per_sample": alg_bytes_step / samples_per_step,
         "kernel_share_of_step": {names[k]: kernel_ms[k] / max(kernel_ms[:5].sum(), 1e-9) for k in range(5)},
         "kernel_ms_per_step": {names[k]: kernel_ms[k] / args.steps for k in range(5)},
