@@ -420,6 +420,29 @@ def run_gpu(args):
                        "h2d_bytes_per_step": int(pcm_bytes), "d2h_bytes_per_step": int(total + 4 * len(sizes)),
                        "ms_per_step": e2e_ms, "steps": args.e2e_steps, "pinned_copy_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs},
                        "api": "flacb200_encode(host PCM -> host frames + frame sizes)"}
+        # decode, end to end: the frames just downloaded (pinned host memory) -> PCM in pinned host memory
+        if not args.no_decode and "decode" in line:
+            per_track = (n + 4095) // 4096
+            offs = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
+            dsegs = [(int(offs[t * per_track]), int(offs[(t + 1) * per_track] - offs[t * per_track]), t * n, n) for t in range(n_tracks)]
+
+            def e2e_dstep():
+                return eng.decode(RATE, BPS, CH, 4096, h_out_p, total, dsegs, h_pcm_p, pcm_bytes, _abi.PCM_BYTES_LE,
+                                  frames_location=_abi.HOST, pcm_location=_abi.HOST)
+
+            e2e_dstep()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                nf, ns = e2e_dstep()
+            torch.cuda.synchronize()
+            ddt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(ddt, op=dist.ReduceOp.MAX)
+            d_ms = float(ddt.item()) / args.e2e_steps * 1e3
+            line["decode"]["e2e"] = {"value": samples_per_step * world / (d_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": d_ms,
+                                     "h2d_bytes_per_step": int(total), "d2h_bytes_per_step": int(pcm_bytes),
+                                     "api": "flacb200_decode(host frames -> host PCM)", "pcm_frames_decoded": int(ns)}
         L.flacb200_host_free(h_pcm_p)
         L.flacb200_host_free(h_out_p)
 
