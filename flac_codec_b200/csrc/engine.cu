@@ -75,6 +75,14 @@ struct flacb200_engine {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host<->device copies overlapped with the kernels of other launch groups
+    cudaStream_t aux = nullptr;                            // decode: CRC-16 and the frame walk beside the predictor restoration
+    // small host<->device messages of the decode path (segment table up; candidate count, walk verdict, walk state down) go
+    // through pinned mapped memory and a tiny copy kernel, not through the copy engines: behind a 350 MB upload or download
+    // of another batch a 4-byte cudaMemcpyAsync waits for milliseconds
+    uint8_t* mbox_h = nullptr;
+    uint8_t* mbox_d = nullptr;
+    size_t mbox_cap = 0;
+    std::vector<cudaEvent_t> batch_ev;                     // decode with host buffers: upload of segment batch b landed
     std::vector<cudaEvent_t> pipe_ev;                      // per group: input landed, group done
     unsigned long long* h_totals = nullptr;                // pinned + mapped: cumulative output bytes after each group,
     unsigned long long* d_h_totals = nullptr;              // written by k_scan itself (no trip through the copy queue)
@@ -180,6 +188,7 @@ int flacb200_engine_create(int device, flacb200_engine** out)
     e->stream = e->own_stream;
     cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking);
     for (auto& ev : e->ev) cudaEventCreate(&ev);
     *out = e;
     return 0;
@@ -201,7 +210,10 @@ void flacb200_engine_destroy(flacb200_engine* e)
     for (auto& ev : e->evpool) cudaEventDestroy(ev);
     if (e->host_stage) cudaFreeHost(e->host_stage);
     if (e->h_totals) cudaFreeHost(e->h_totals);
+    if (e->mbox_h) cudaFreeHost(e->mbox_h);
     for (auto& ev : e->pipe_ev) cudaEventDestroy(ev);
+    for (auto& ev : e->batch_ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(e->aux);
     cudaStreamDestroy(e->copy_in);
     cudaStreamDestroy(e->copy_out);
     cudaStreamDestroy(e->own_stream);
@@ -655,6 +667,114 @@ extern "C" int flacb200_encode_last_info(flacb200_engine* e, flacb200_frame_info
     return 0;
 }
 
+__global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t nwords)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+static int mbox_reserve(flacb200_engine* e, size_t bytes)
+{
+    if (bytes <= e->mbox_cap) return 0;
+    if (e->mbox_h) {
+        cudaStreamSynchronize(e->stream);
+        cudaFreeHost(e->mbox_h);
+        e->mbox_h = nullptr;
+        e->mbox_cap = 0;
+    }
+    const size_t cap = std::max<size_t>((bytes + 4095) & ~(size_t)4095, 65536);
+    CK(cudaHostAlloc((void**)&e->mbox_h, cap, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&e->mbox_d, e->mbox_h, 0));
+    e->mbox_cap = cap;
+    return 0;
+}
+// the first 256 bytes of the mailbox are the download slots, uploads start at 256
+constexpr size_t MBOX_UP = 256;
+
+// bytes (a multiple of 4) of device memory -> mailbox slot `off`, on stream st; read e->mbox_h + off after syncing st
+static void mbox_post(flacb200_engine* e, size_t off, const void* d_src, size_t bytes, cudaStream_t st)
+{
+    k_copy_words<<<1, 64, 0, st>>>((uint32_t*)(e->mbox_d + off), (const uint32_t*)d_src, bytes / 4);
+}
+
+// Host frames -> host PCM for many streams: the segments (independent streams) are cut into batches by bytes; the upload
+// of batch b + 1, the kernels of batch b and the download of batch b - 1 overlap (three streams, one whole-size device
+// buffer each for frames and PCM; every batch is an ordinary flacb200_decode call on device-resident ranges).  Only for
+// calls whose segments announce their sample counts and write disjoint, increasing PCM ranges; returns -9999 when the
+// call does not qualify.
+static int decode_batched(flacb200_engine* e, const flacb200_stream_params* params, const uint8_t* frames, size_t frames_bytes,
+                          const flacb200_decode_segment* segments, size_t n_segments, uint8_t* pcm_out, size_t pcm_out_bytes, int pcm_kind,
+                          uint64_t* n_frames_out, uint64_t* n_pcm_out, uint64_t* bad_frame)
+{
+    size_t MIN_BYTES = (size_t)64 << 20, BATCH_BYTES = (size_t)192 << 20;
+    if (const char* bb = getenv("FLACB200_BATCH_BYTES")) {   // tests: small batches
+        BATCH_BYTES = std::max<size_t>((size_t)strtoull(bb, nullptr, 0), 1);
+        MIN_BYTES = 0;
+    }
+    if (n_segments < 4 || frames_bytes < MIN_BYTES || pcm_kind == FLACB200_PCM_I32_PLANAR || getenv("FLACB200_NO_BATCH")) return -9999;
+    const size_t fb = (size_t)params->channels * (pcm_kind <= 1 ? (params->bits_per_sample + 7) / 8 : 4);
+    uint64_t prev_end = 0, prev_pcm = 0;
+    for (size_t s = 0; s < n_segments; s++) {
+        const flacb200_decode_segment& g = segments[s];
+        if (g.n_pcm_frames == 0 || g.byte_offset < prev_end || g.byte_offset + g.byte_length > frames_bytes || g.pcm_offset < prev_pcm ||
+            (g.pcm_offset + g.n_pcm_frames) * fb > pcm_out_bytes)
+            return -9999;
+        prev_end = g.byte_offset + g.byte_length;
+        prev_pcm = g.pcm_offset + g.n_pcm_frames;
+    }
+    struct Batch { size_t s0, s1; uint64_t lo, hi; };
+    std::vector<Batch> batches;
+    for (size_t s = 0; s < n_segments;) {
+        Batch b{s, s, segments[s].byte_offset & ~15ull, 0};
+        uint64_t bytes = 0;
+        while (b.s1 < n_segments && (bytes < BATCH_BYTES || b.s1 == b.s0)) bytes += segments[b.s1++].byte_length;
+        b.hi = segments[b.s1 - 1].byte_offset + segments[b.s1 - 1].byte_length;
+        batches.push_back(b);
+        s = b.s1;
+    }
+    if (batches.size() < 2) return -9999;
+    CK(cudaSetDevice(e->device));
+    ENS(e->dec[0], frames_bytes + 64);
+    ENS(e->dec[1], pcm_out_bytes + 64);
+    uint8_t* d_frames = (uint8_t*)e->dec[0].p;
+    uint8_t* d_pcm = (uint8_t*)e->dec[1].p;
+    while (e->batch_ev.size() < batches.size()) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->batch_ev.push_back(ev);
+    }
+    for (size_t b = 0; b < batches.size(); b++) {   // all uploads are queued now; each batch's kernels wait for theirs
+        CK(cudaMemcpyAsync(d_frames + batches[b].lo, frames + batches[b].lo, batches[b].hi - batches[b].lo, cudaMemcpyHostToDevice, e->copy_in));
+        CK(cudaEventRecord(e->batch_ev[b], e->copy_in));
+    }
+    uint64_t frames_total = 0, pcm_total = 0;
+    int rc = 0, first_err = 0;
+    std::vector<flacb200_decode_segment> sub;
+    for (size_t b = 0; b < batches.size(); b++) {
+        const Batch& bt = batches[b];
+        sub.assign(segments + bt.s0, segments + bt.s1);
+        for (auto& g : sub) g.byte_offset -= bt.lo;
+        CK(cudaStreamWaitEvent(e->stream, e->batch_ev[b], 0));
+        uint64_t nf = 0, ns = 0, bad = 0;
+        rc = flacb200_decode(e, params, d_frames + bt.lo, bt.hi - bt.lo, FLACB200_DEVICE, sub.data(), sub.size(), d_pcm, pcm_out_bytes, pcm_kind,
+                             FLACB200_DEVICE, 0, &nf, &ns, &bad);
+        if (rc < 0) break;
+        if (rc > 0 && first_err == 0) {   // the first error in stream order; later streams are still decoded, as in one call
+            first_err = rc;
+            if (bad_frame) *bad_frame = frames_total + bad;
+        }
+        frames_total += nf;
+        pcm_total += ns;
+        // the batch's PCM (the kernels are done: the call above returns after its last readback)
+        const size_t a = (size_t)segments[bt.s0].pcm_offset * fb, z = (size_t)(segments[bt.s1 - 1].pcm_offset + segments[bt.s1 - 1].n_pcm_frames) * fb;
+        CK(cudaMemcpyAsync(pcm_out + a, d_pcm + a, z - a, cudaMemcpyDeviceToHost, e->copy_out));
+    }
+    cudaStreamSynchronize(e->copy_in);
+    CK(cudaStreamSynchronize(e->copy_out));
+    if (n_frames_out) *n_frames_out = frames_total;
+    if (n_pcm_out) *n_pcm_out = pcm_total;
+    return rc < 0 ? rc : first_err;
+}
+
 extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params* params, const void* frames, size_t frames_bytes,
                                int frames_location, const flacb200_decode_segment* segments, size_t n_segments, void* pcm_out,
                                size_t pcm_out_bytes, int pcm_kind, int pcm_location, uint64_t planar_stride, uint64_t* n_frames_out,
@@ -664,12 +784,17 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     if (params->channels < 1 || params->channels > 8) return 30;
     if (params->bits_per_sample < 1 || params->bits_per_sample > 32) return 33;
     if (pcm_kind < 0 || pcm_kind > 3 || n_segments > 0xFFFFFFF0ull) return FLACB200_E_BAD_ARGUMENT;
-    CK(cudaSetDevice(e->device));
-    cudaStream_t st = e->stream;
-    memset(&e->tm, 0, sizeof(e->tm));
     if (n_frames_out) *n_frames_out = 0;
     if (n_pcm_out) *n_pcm_out = 0;
     if (bad_frame) *bad_frame = 0;
+    if (frames_location == FLACB200_HOST && pcm_location == FLACB200_HOST) {
+        const int rb = decode_batched(e, params, (const uint8_t*)frames, frames_bytes, segments, n_segments, (uint8_t*)pcm_out, pcm_out_bytes, pcm_kind,
+                                      n_frames_out, n_pcm_out, bad_frame);
+        if (rb != -9999) return rb;
+    }
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    memset(&e->tm, 0, sizeof(e->tm));
 
     DecCfg cfg{};
     cfg.channels = params->channels;
@@ -722,7 +847,14 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
         d_out = (uint8_t*)pcm_out;
     }
     ENS(e->dec[2], n_segments * sizeof(DecSeg));
-    CK(cudaMemcpyAsync(e->dec[2].p, segs.data(), n_segments * sizeof(DecSeg), cudaMemcpyHostToDevice, st));
+    {
+        const int rm = mbox_reserve(e, MBOX_UP + n_segments * sizeof(DecSeg));
+        if (rm) return rm;
+        CK(cudaStreamSynchronize(st));   // (the previous call's kernel may still be reading the upload area)
+        memcpy(e->mbox_h + MBOX_UP, segs.data(), n_segments * sizeof(DecSeg));
+        k_copy_words<<<(unsigned)std::min<size_t>((n_segments * sizeof(DecSeg) / 4 + 255) / 256, 64), 256, 0, st>>>(
+            (uint32_t*)e->dec[2].p, (const uint32_t*)(e->mbox_d + MBOX_UP), n_segments * sizeof(DecSeg) / 4);
+    }
     if (e->profiling) cudaEventRecord(e->ev[21], st);
     const DecSeg* d_segs = (const DecSeg*)e->dec[2].p;
     const uint32_t tiles = find_tiles(frames_bytes);
@@ -738,9 +870,11 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     time_mark(e, ev++);
     launch_find_count(cfg, d_bytes, d_segs, (uint32_t*)e->dec[3].p, (uint32_t*)e->dec[4].p, d_maxbs, st);
     uint32_t ncand = 0, max_bs = 0;
-    CK(cudaMemcpyAsync(&ncand, (uint32_t*)e->dec[4].p + tiles, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&max_bs, d_maxbs, 4, cudaMemcpyDeviceToHost, st));
+    mbox_post(e, 0, (uint32_t*)e->dec[4].p + tiles, 4, st);
+    mbox_post(e, 4, d_maxbs, 4, st);
     CK(cudaStreamSynchronize(st));
+    ncand = ((const uint32_t*)e->mbox_h)[0];
+    max_bs = ((const uint32_t*)e->mbox_h)[1];
     uint32_t launches = 2;
     ENS(e->dec[6], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(FrameCand));
     ENS(e->dec[7], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(DecRec));
@@ -774,7 +908,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
         if (n && split_decode) {
             // k_parse, then two independent tails that meet before k_emit: predictor restoration over the planes on the
             // engine's stream, and CRC-16 + the frame chain (which need only the end offsets k_parse found) on a second one
-            cudaStream_t aux = e->copy_in;
+            cudaStream_t aux = e->aux;
             while (e->pipe_ev.size() < 3 * (ngroups + 1)) {
                 cudaEvent_t pe;
                 CK(cudaEventCreateWithFlags(&pe, cudaEventDisableTiming));
@@ -793,9 +927,9 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
             CK(cudaStreamWaitEvent(aux, e->pipe_ev[3 * ngroups], 0));
             launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, aux);
             launch_chain_fast(cfg, d_segs, d_cands + g0, d_recs + g0, n, ncand - g0, g0 == 0, d_pos + g0, d_state, d_clean, aux);
-            uint32_t clean = 0;
-            CK(cudaMemcpyAsync(&clean, d_clean, 4, cudaMemcpyDeviceToHost, aux));
+            mbox_post(e, 8, d_clean, 4, aux);
             CK(cudaStreamSynchronize(aux));
+            const uint32_t clean = ((const uint32_t*)e->mbox_h)[2];
             if (clean != 1 && getenv("FLACB200_DEBUG")) fprintf(stderr, "flacb200: k_chain_fast declined group at %u (reason 0x%x)\n", g0, clean);
             if (clean != 1) CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, aux));
             CK(cudaEventRecord(e->pipe_ev[3 * ngroups + 2], aux));
@@ -829,8 +963,10 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     cudaEventRecord(e->ev[23], st);
     CK(cudaGetLastError());
     ChainState state;
-    CK(cudaMemcpyAsync(&state, d_state, sizeof(state), cudaMemcpyDeviceToHost, st));
+    static_assert(sizeof(ChainState) % 4 == 0 && sizeof(ChainState) <= 128, "mailbox slot");
+    mbox_post(e, 64, d_state, sizeof(state), st);
     CK(cudaStreamSynchronize(st));
+    memcpy(&state, e->mbox_h + 64, sizeof(state));
     if (n_frames_out) *n_frames_out = state.frames_total;
     if (n_pcm_out) *n_pcm_out = state.samples_total;
     cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);

@@ -181,6 +181,51 @@ def test_multi_segment_batch(eng, fo):
     eng.device_free(d_out)
 
 
+def test_batched_host_decode_equals_one_call(eng, fo, monkeypatch):
+    """Host frames -> host PCM of many streams is cut into batches of segments whose upload, kernels and download overlap
+    (decode_batched in engine.cu; 192 MB batches by default, tiny ones here): same PCM, counts and error as one call."""
+    from flac_codec_b200 import _abi
+
+    rate, bps, ch = 44100, 16, 2
+    tracks = [synth_pcm(40 + t, ch, 9000 + 1234 * t, rate, bps) for t in range(9)]
+    blobs = [fo.encode_frames_only(fo.options("default"), rate, bps, ch, x.reshape(-1))[0] for x in tracks]
+
+    def run(buf, segs, total):
+        out = np.zeros(total * ch, dtype=np.int32)
+        try:
+            nf, ns = eng.decode(rate, bps, ch, 4096, buf, buf.size, segs, out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+            return out, nf, ns, 0, 0
+        except _abi.FlacB200Error as e:
+            return out, None, None, e.code, e.bad_frame
+
+    for damaged in (False, True):
+        parts = [bytearray(b) for b in blobs]
+        if damaged:
+            parts[4][len(parts[4]) // 2] ^= 0x10
+        segs, boff, poff = [], 3, 0   # (a gap in front: batch starts are not 16-byte aligned)
+        for x, b in zip(tracks, parts):
+            segs.append((boff, len(b), poff, x.shape[0]))
+            boff += len(b) + 5
+            poff += x.shape[0]
+        buf = np.zeros(boff, dtype=np.uint8)
+        for (o, n, _, _), b in zip(segs, parts):
+            buf[o:o + n] = np.frombuffer(bytes(b), dtype=np.uint8)
+        monkeypatch.setenv("FLACB200_NO_BATCH", "1")
+        ref = run(buf, segs, poff)
+        monkeypatch.delenv("FLACB200_NO_BATCH")
+        monkeypatch.setenv("FLACB200_BATCH_BYTES", "30000")
+        got = run(buf, segs, poff)
+        monkeypatch.delenv("FLACB200_BATCH_BYTES")
+        assert got[1:] == ref[1:], (got[1:], ref[1:])
+        if not damaged:
+            assert ref[3] == 0 and np.array_equal(got[0], ref[0])
+            assert np.array_equal(got[0].reshape(-1, ch), np.concatenate(tracks))
+        else:
+            assert ref[3] != 0
+            good = sum(x.shape[0] for x in tracks[:4]) * ch   # the streams in front of the damaged one
+            assert np.array_equal(got[0][:good], ref[0][:good])
+
+
 # ---- hand-built frames ----
 class Bits:
     def __init__(self):
