@@ -354,6 +354,14 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
 #pragma unroll
                     for (int e = 0; e < 16; e++) ta[e >> 2] += zigzag32(rf[e]) >> codef;
                     bits_f += ((unsigned long long)ta[0] + ta[1]) + ((unsigned long long)ta[2] + ta[3]) + 16u * (1u + codef);
+                } else if (!tail && i0 == 0 && cpf >= 16 && codef < 0x40) {
+                    // the block's first tile: its first `fo` samples are warm-up, the rest belongs to partition 0 (one lane
+                    // per candidate takes this branch; through the sample-by-sample fallback it held its warp for a whole
+                    // extra round)
+                    uint32_t ta[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int e = 0; e < 16; e++) ta[e >> 2] += (uint32_t)e >= fo ? zigzag32(rf[e]) >> codef : 0u;
+                    bits_f += ((unsigned long long)ta[0] + ta[1]) + ((unsigned long long)ta[2] + ta[3]) + (16u - fo) * (1u + codef);
                 } else {
                     int32_t tmp[16];
 #pragma unroll
@@ -379,6 +387,11 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                             for (int e = 0; e < 16; e++) bits_l = acc_u32(bits_l, zigzag32(rl[e]) >> codel);
                             bits_l += 16u * (1u + codel);
                         }
+                    } else if (!tail && i0 == 0 && cpl >= 16 && order <= 16 && codel < 0x40) {   // first tile: `order` warm-up samples
+#pragma unroll
+                        for (int e = 0; e < 16; e++)
+                            if ((uint32_t)e >= order) bits_l = acc_u32(bits_l, zigzag32(rl[e]) >> codel);
+                        bits_l += (16u - order) * (1u + codel);
                     } else {
                         int32_t tmp[16];
 #pragma unroll
