@@ -139,17 +139,23 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
         // ---- code lengths of this lane's tile ----
         const uint32_t lo_i = max(i0, order), hi_i = min(i0 + 16u, n);   // residuals exist for [lo_i, hi_i)
         const uint32_t pj = live ? udiv(i0, dcp) : 0u;
-        const bool uniform = live && i0 >= order && i0 + 16 <= n && (cp16 || udiv(i0 + 15, dcp) == pj);
+        // the common tile: one Rice parameter for all its residuals (:3845-3851).  The block's first tile belongs here too --
+        // its first `order` samples are warm-up and carry no code (skip) -- or its lane would hold the warp in the general
+        // path for the length of five ordinary rounds.
+        const bool uniform = live && (i0 >= order || (i0 == 0 && order <= 16)) && i0 + 16 <= n && (cp16 || udiv(i0 + 15, dcp) == pj);
         const uint32_t cc0 = cr.rice[live ? min(pj - j0, (uint32_t)MAX_PARTS - 1) : 0u];
+        const uint32_t first_res = max(pj * cp, order);                         // first residual of the tile's partition
+        const uint32_t skip = first_res > i0 ? min(first_res - i0, 16u) : 0u;   // nonzero only in the first tile
+        const bool hdr_here = first_res >= i0 && first_res < i0 + 16;          // ResidualPartitionHeader (src/stream.rs:1603-1619) rides in front
         uint32_t tsum = 0;
         uint32_t len[16];
-        if (uniform && cc0 < 0x40) {   // the common tile: one Rice parameter for all 16 residuals (:3845-3851)
+        if (uniform && cc0 < 0x40) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                len[e] = (zigzag32(r[e]) >> cc0) + 1u + cc0;
+                len[e] = (uint32_t)e >= skip ? (zigzag32(r[e]) >> cc0) + 1u + cc0 : 0u;
                 tsum += len[e];
             }
-            if (i0 == max(pj * cp, order)) tsum += hb;   // ResidualPartitionHeader (src/stream.rs:1603-1619) rides in front
+            if (hdr_here) tsum += hb;
         } else if (live) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
@@ -180,7 +186,7 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
         base += __shfl_sync(0xffffffffu, incl, 31);
         // ---- emission ----
         if (uniform && cc0 < 0x40) {
-            if (i0 == max(pj * cp, order)) {
+            if (hdr_here) {
                 p3_put(words, p, hb, cc0);
                 p += hb;
             }
@@ -188,7 +194,8 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 const uint32_t u = zigzag32(r[e]);
-                p3_put(words, p + (u >> cc0), cc0 + 1u, stop | (u & mask));   // unary zeros, stop bit, cc0 LSBs
+                // unary zeros, stop bit, cc0 LSBs; a warm-up sample ORs nothing (its length is 0: p stays)
+                p3_put(words, p + ((uint32_t)e >= skip ? u >> cc0 : 0u), cc0 + 1u, (uint32_t)e >= skip ? stop | (u & mask) : 0u);
                 p += len[e];
             }
         } else if (live) {
