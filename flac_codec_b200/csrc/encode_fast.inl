@@ -260,6 +260,11 @@ __device__ void aw_candidate(const EncCfg& cfg, const FrameDesc& d, const uint8_
 #pragma unroll
                     for (int e = 0; e < 16; e++) bits_f = acc_u32(bits_f, zigzag32(rf[e]) >> codef);
                     bits_f += 16u * (1u + codef);
+                } else if (!tail && i0 == 0 && cpf >= 16 && codef < 0x40) {   // the block's first tile: `fo` warm-up samples, then partition 0
+#pragma unroll
+                    for (int e = 0; e < 16; e++)
+                        if ((uint32_t)e >= fo) bits_f = acc_u32(bits_f, zigzag32(rf[e]) >> codef);
+                    bits_f += (16u - fo) * (1u + codef);
                 } else {
                     int32_t tmp[16];
 #pragma unroll
@@ -278,6 +283,11 @@ __device__ void aw_candidate(const EncCfg& cfg, const FrameDesc& d, const uint8_
 #pragma unroll
                         for (int e = 0; e < 16; e++) bits_l = acc_u32(bits_l, zigzag32(rl[e]) >> codel);
                         bits_l += 16u * (1u + codel);
+                    } else if (!tail && i0 == 0 && cpl >= 16 && order <= 16 && codel < 0x40) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++)
+                            if ((uint32_t)e >= order) bits_l = acc_u32(bits_l, zigzag32(rl[e]) >> codel);
+                        bits_l += (16u - order) * (1u + codel);
                     } else {
                         int32_t tmp[16];
 #pragma unroll
