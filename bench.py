@@ -231,6 +231,33 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: keep the rank (and the pinned host buffers it is about to allocate) on the NUMA node its GPU
+    hangs off.  With several ranks pulling 55 GB/s each, buffers on the far socket turn the end-to-end step into a
+    cross-socket copy.  Returns a short description for the JSON line; does nothing when the topology is not visible."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa node {node}: no usable cpus"
+        os.sched_setaffinity(0, cpus)
+        return f"rank bound to numa node {node} ({len(cpus)} cpus) of GPU {bdf}"
+    except (OSError, ValueError, AttributeError, RuntimeError) as e:
+        return f"not bound ({type(e).__name__})"
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -241,10 +268,11 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound (the cpu_baseline leg uses every core)"
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # keeps NCCL's banner out of stdout: rank 0 prints ONE line
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL's log (the image sets NCCL_DEBUG=VERSION: a banner on stdout) goes to stderr: rank 0 prints ONE line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from flac_codec_b200 import Engine, Options, _abi
@@ -333,7 +361,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i32/i64 residuals, f64 LPC analysis", "data": "synthetic", "config": workload_config(args, world),
-        "clocks": clk, "gpu_launches": int(launches), "roofline": roofline,
+        "clocks": clk, "gpu_launches": int(launches), "host_affinity": numa, "roofline": roofline,
         "compression_ratio": flac_bytes / pcm_bytes,
     }
 
