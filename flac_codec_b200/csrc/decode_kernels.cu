@@ -758,11 +758,20 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecCfg cfg, const uint8_
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t CRCF_THREADS = 256;
 
+__device__ Crc16Tables g_dec_crc16_tabs;   // built once per device (building them per CTA cost a third of k_crc16f)
+
+__global__ void k_dec_crc16_tables_init()
+{
+    crc16_tables_init(g_dec_crc16_tabs);
+}
+
 __global__ void __launch_bounds__(CRCF_THREADS) k_crc16f(const uint8_t* __restrict__ bytes, const FrameCand* __restrict__ cands, uint32_t ncand,
                                                         DecRec* __restrict__ recs)
 {
     __shared__ Crc16Tables tabs;
-    crc16_tables_init(tabs);
+    static_assert(sizeof(Crc16Tables) % 2 == 0, "copied as 16-bit words");
+    for (uint32_t i = threadIdx.x; i < sizeof(Crc16Tables) / 2; i += CRCF_THREADS)
+        reinterpret_cast<uint16_t*>(&tabs)[i] = reinterpret_cast<const uint16_t*>(&g_dec_crc16_tabs)[i];
     __syncthreads();
     const uint32_t c = blockIdx.x * (CRCF_THREADS / 32) + (threadIdx.x >> 5);
     if (c >= ncand) return;
@@ -1385,6 +1394,13 @@ void launch_decode(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, 
 
 void launch_crc16f(const uint8_t* bytes, const FrameCand* cands, uint32_t n, DecRec* recs, cudaStream_t st)
 {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool ready[64] = {};
+    if (dev >= 0 && dev < 64 && !ready[dev]) {
+        k_dec_crc16_tables_init<<<1, 256, 0, st>>>();
+        ready[dev] = true;
+    }
     k_crc16f<<<(n + CRCF_THREADS / 32 - 1) / (CRCF_THREADS / 32), CRCF_THREADS, 0, st>>>(bytes, cands, n, recs);
 }
 
