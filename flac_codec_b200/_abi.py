@@ -98,9 +98,9 @@ EXPORTS = [
     "flacb200_reader_open", "flacb200_reader_close", "flacb200_reader_info", "flacb200_reader_seektable", "flacb200_reader_read",
     "flacb200_reader_seek", "flacb200_reader_verify", "flacb200_md5", "flacb200_md5_batch",
     "flacb200_options_default", "flacb200_options_fast", "flacb200_options_best", "flacb200_engine_create",
-    "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_engine_set_keep_info", "flacb200_encode",
+    "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_engine_set_keep_info", "flacb200_engine_set_option", "flacb200_encode",
     "flacb200_encode_bound", "flacb200_encode_last_info", "flacb200_decode", "flacb200_set_profiling",
-    "flacb200_last_timings", "flacb200_synth_pcm", "flacb200_host_alloc", "flacb200_host_free",
+    "flacb200_last_timings", "flacb200_debug_libm", "flacb200_synth_pcm", "flacb200_host_alloc", "flacb200_host_free",
     "flacb200_device_alloc", "flacb200_device_free", "flacb200_memcpy", "flacb200_synchronize", "flacb200_strerror",
     "flacb200_version",
 ]
@@ -134,6 +134,7 @@ def lib():
     L.flacb200_engine_set_stream.argtypes = [vp, vp]
     L.flacb200_engine_set_chunk_frames.argtypes = [vp, C.c_uint32]
     L.flacb200_engine_set_keep_info.argtypes = [vp, C.c_int]
+    L.flacb200_engine_set_option.argtypes = [vp, C.c_char_p, C.c_uint64]
     L.flacb200_encode.argtypes = [vp, C.POINTER(Options), C.POINTER(StreamParams), vp, C.c_size_t, C.c_int, C.c_int,
                                   C.c_uint64, C.POINTER(Segment), C.c_size_t, vp, C.c_size_t, C.c_int, u32p, C.c_size_t,
                                   u64p, u64p]
@@ -146,6 +147,7 @@ def lib():
     L.flacb200_last_timings.argtypes = [vp, C.POINTER(Timings)]
     L.flacb200_synth_pcm.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint64]
+    L.flacb200_debug_libm.argtypes = [vp, C.c_int, vp, vp, C.c_size_t]
     L.flacb200_host_alloc.argtypes = [C.c_size_t]
     L.flacb200_host_alloc.restype = vp
     L.flacb200_host_free.argtypes = [vp]

@@ -1392,26 +1392,19 @@ void launch_decode(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, 
     k_decode<<<(n + DEC_THREADS - 1) / DEC_THREADS, DEC_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, recs, only_wide ? 1u : 0u);
 }
 
+void init_decode_tables(cudaStream_t st) { k_dec_crc16_tables_init<<<1, 256, 0, st>>>(); }
+
 void launch_crc16f(const uint8_t* bytes, const FrameCand* cands, uint32_t n, DecRec* recs, cudaStream_t st)
 {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    static bool ready[64] = {};
-    if (dev >= 0 && dev < 64 && !ready[dev]) {
-        k_dec_crc16_tables_init<<<1, 256, 0, st>>>();
-        ready[dev] = true;
-    }
     k_crc16f<<<(n + CRCF_THREADS / 32 - 1) / (CRCF_THREADS / 32), CRCF_THREADS, 0, st>>>(bytes, cands, n, recs);
 }
 
 cudaError_t launch_chain(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, DecRec* recs, uint32_t n,
                          const FrameCand* after, uint32_t group_first, unsigned long long* pos, ChainState* state, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    {
         cudaError_t e = cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem));
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     k_chain<<<1, CHAIN_THREADS, sizeof(ChainSmem), st>>>(cfg, bytes, segs, cands, recs, n, after, group_first, pos, state);
     return cudaGetLastError();

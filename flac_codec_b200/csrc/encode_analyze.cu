@@ -580,7 +580,7 @@ cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uin
                             unsigned long long* abssum, cudaStream_t st)
 {
     const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
-    static const size_t pad_ = getenv("FLACB200_A3_SMEM_PAD") ? (size_t)atoi(getenv("FLACB200_A3_SMEM_PAD")) : 0;   // occupancy experiments
+    constexpr size_t pad_ = 0;
 #define FLACB200_A3(HBV, ST)                                                                                                          \
     do {                                                                                                                              \
         const size_t smem_ = a3_smem_bytes<ST>() + pad_;                                                                              \

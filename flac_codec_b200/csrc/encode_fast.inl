@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(32 * L2_WARPS) k_lpc2(EncCfg cfg, const FrameD
         const double error_scale = __ddiv_rn(0.5, (double)n);
         const double divisor = 2.0 * 0.693147180559945309417232121458176568;
         for (uint32_t o = 4 * m + 1; o <= min(4 * m + 4, M); o++) {
-            const double bpr = __ddiv_rn(log(__dmul_rn(my.err[o - 1], error_scale)), divisor);
+            const double bpr = __ddiv_rn(glibc_log(__dmul_rn(my.err[o - 1], error_scale)), divisor);
             my.bits[o - 1] = fma(bpr, (double)(n - o), (double)(o * (bps + precision)));
         }
     }
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(32 * L2_WARPS) k_lpc2(EncCfg cfg, const FrameD
             }
             if (l > 0.0) {
                 const int32_t max_coeff = (1 << (precision - 1)) - 1, min_coeff = -(1 << (precision - 1));
-                const int32_t lg = f64_as_i32_sat(floor(log2(l)));
+                const int32_t lg = f64_as_i32_sat(floor(glibc_log2(l)));
                 long long sh = (long long)((int32_t)precision - 1) - (long long)lg - 1;   // :3360
                 if (sh > 15) sh = 15;
                 if (sh >= -16) {
@@ -739,11 +739,9 @@ cudaError_t launch_lpc2(const EncCfg& cfg, const FrameDesc* descs, const uint8_t
     const uint32_t ncand = cfg.nframes * cfg.nslots;
     const uint32_t nwarps = (ncand + cpw - 1) / cpw;
     const size_t smem = (size_t)L2_WARPS * cpw * lpc2_cand_doubles(cfg.max_lpc_order) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // per device, so on every launch (a process may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(k_lpc2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     k_lpc2<<<(nwarps + L2_WARPS - 1) / L2_WARPS, 32 * L2_WARPS, smem, st>>>(cfg, descs, pcm, winpool, lpcs, cpw, ncand);
     return cudaGetLastError();
@@ -1027,12 +1025,10 @@ cudaError_t launch_pack2_crc(const EncCfg& cfg, const FrameDesc* descs, const ui
     const uint32_t nsub_max = cfg.mode == MODE_INDEPENDENT ? cfg.channels : 2;
     const uint32_t cap_words = pack_cap_words(cfg);
     const size_t smem = (size_t)cap_words * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    {
         cudaError_t e = cudaFuncSetAttribute(k_pack2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pack2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     if (cfg.mode != MODE_INDEPENDENT)
         k_pack2<true><<<cfg.nframes * nsub_max, AN_THREADS, smem, st>>>(cfg, nsub_max, cap_words, descs, pcm, cands, frecs, out);

@@ -352,6 +352,9 @@ __global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words
     }
 }
 
+// once per device, from flacb200_engine_create (synchronised there: no kernel can see half-built tables)
+void init_encode_tables(cudaStream_t st) { k_crc16_tables_init<<<1, 256, 0, st>>>(); }
+
 uint32_t pack3_cap_words(const EncCfg& cfg)
 {
     const uint32_t nsub = cfg.mode == MODE_INDEPENDENT ? cfg.channels : 2;
@@ -368,13 +371,6 @@ cudaError_t launch_pack3(const EncCfg& cfg, const FrameDesc* descs, const uint8_
     const uint32_t nsub = cfg.mode == MODE_INDEPENDENT ? cfg.channels : 2;
     const uint32_t cap_words = pack3_cap_words(cfg);
     const size_t smem = (size_t)cap_words * 4;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    static bool ready[64] = {};
-    if (dev >= 0 && dev < 64 && !ready[dev]) {
-        k_crc16_tables_init<<<1, 256, 0, st>>>();
-        ready[dev] = true;
-    }
     const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
 #define FLACB200_P3(HBV, ST)                                                                                                         \
     do {                                                                                                                             \

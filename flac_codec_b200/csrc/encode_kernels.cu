@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "glibc_log.cuh"
 #include "crc.cuh"
 #include "tiles.cuh"
 #include "rice.cuh"
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(32 * LPC_WARPS) k_lpc(EncCfg cfg, const FrameD
         for (uint32_t o = 1; o <= M; o++) {
             const double e = sm.err[o - 1];
             if (!(e > 0.0)) break;   // take_while  :3668
-            const double bpr = __ddiv_rn(log(__dmul_rn(e, error_scale)), divisor);   // :3674-3675
+            const double bpr = __ddiv_rn(glibc_log(__dmul_rn(e, error_scale)), divisor);   // :3674-3675
             const double bits = fma(bpr, (double)(n - o), (double)(o * (bps + precision)));   // :3677
             if (best == 0 || total_key(bits) < total_key(best_bits)) {
                 best = (int)o;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(32 * LPC_WARPS) k_lpc(EncCfg cfg, const FrameD
         }
         if (!(l > 0.0)) return;   // ZeroLpCoefficients
         const int32_t max_coeff = (1 << (precision - 1)) - 1, min_coeff = -(1 << (precision - 1));
-        const int32_t lg = f64_as_i32_sat(floor(log2(l)));
+        const int32_t lg = f64_as_i32_sat(floor(glibc_log2(l)));
         long long sh = (long long)((int32_t)precision - 1) - (long long)lg - 1;   // :3360
         if (sh > 15) sh = 15;
         if (sh < -16) return;     // LpNegativeShiftError
@@ -955,11 +956,9 @@ cudaError_t launch_residual(const EncCfg& cfg, const FrameDesc* descs, const int
     const uint32_t ncand = cfg.nframes * cfg.nslots;
     if (residual_uses_smem(cfg)) {
         const size_t smem = (size_t)cfg.bpad * 8;
-        static bool attr_set = false;
-        if (!attr_set) {
+        {
             cudaError_t e = cudaFuncSetAttribute(k_residual<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             if (e != cudaSuccess) return e;
-            attr_set = true;
         }
         k_residual<true><<<ncand, RES_THREADS, smem, st>>>(cfg, descs, planes, ormask, abssum, lpcs, cands, nullptr);
     } else {
@@ -987,11 +986,9 @@ cudaError_t launch_pack_crc(const EncCfg& cfg, const FrameDesc* descs, const int
     const uint32_t cap_words = pack_cap_words(cfg);
     if (pack_uses_smem(cfg)) {
         const size_t smem = (size_t)cfg.bpad * 4 + (size_t)cap_words * 4;
-        static bool attr_set = false;
-        if (!attr_set) {
+        {
             cudaError_t e = cudaFuncSetAttribute(k_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             if (e != cudaSuccess) return e;
-            attr_set = true;
         }
         k_pack<true><<<cfg.nframes * nsub_max, PACK_THREADS, smem, st>>>(cfg, nsub_max, cap_words, descs, planes, cands, frecs, out);
     } else {

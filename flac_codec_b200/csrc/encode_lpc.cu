@@ -11,6 +11,7 @@
 // tile being computed; the lanes never wait on a global load inside the FP64 loop (k_lpc2 spent a third of its stall
 // cycles there), and no registers are held for prefetched samples.
 #include "common.cuh"
+#include "glibc_log.cuh"
 #include "tiles.cuh"
 
 namespace flacb200 {
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const Fra
         const double error_scale = __ddiv_rn(0.5, (double)n);
         const double divisor = 2.0 * 0.693147180559945309417232121458176568;
         for (uint32_t o = 4 * m + 1; o <= min(4 * m + 4, M); o++) {
-            const double bpr = __ddiv_rn(log(__dmul_rn(errv[o - 1], error_scale)), divisor);
+            const double bpr = __ddiv_rn(glibc_log(__dmul_rn(errv[o - 1], error_scale)), divisor);
             bitsv[o - 1] = fma(bpr, (double)(n - o), (double)(o * (bps + precision)));
         }
     }
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const Fra
             }
             if (l > 0.0) {
                 const int32_t max_coeff = (1 << (precision - 1)) - 1, min_coeff = -(1 << (precision - 1));
-                const int32_t lg = f64_as_i32_sat(floor(log2(l)));
+                const int32_t lg = f64_as_i32_sat(floor(glibc_log2(l)));
                 long long sh = (long long)((int32_t)precision - 1) - (long long)lg - 1;   // :3360
                 if (sh > 15) sh = 15;
                 if (sh >= -16) {

@@ -9,12 +9,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/flacb200.h"
 #include "common.cuh"
 #include "decode.cuh"
+#include "glibc_log.cuh"
 
 namespace flacb200 {
 // encode_kernels.cu
@@ -36,6 +38,8 @@ bool analyze_fast_ok(const EncCfg&);
 cudaError_t launch_pack2_crc(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 cudaError_t launch_lpc2(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, cudaStream_t);
 cudaError_t launch_analyze(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, cudaStream_t);
+void init_encode_tables(cudaStream_t);   // encode_frame.cu
+void init_decode_tables(cudaStream_t);   // decode_kernels.cu
 // synth.cu
 cudaError_t launch_synth(uint8_t* pcm, unsigned long long first_track, unsigned long long n_tracks, unsigned long long n_pcm_frames,
                          uint32_t channels, uint32_t sample_rate, uint32_t bps, unsigned long long seed, const int32_t* lut, cudaStream_t st);
@@ -89,6 +93,11 @@ struct flacb200_engine {
     size_t h_totals_cap = 0;
     uint32_t chunk_frames = 0;
     bool profiling = false, keep_info = true;
+    // runtime knobs: defaults from the environment, read ONCE at engine creation;
+    // flacb200_engine_set_option changes them afterwards
+    unsigned legacy = 0;
+    bool no_batch = false, debug = false;
+    size_t batch_bytes = 0;   // 0 = default
     DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, dec[12];
     std::map<uint32_t, uint32_t> win_off;   // block length -> offset in doubles
     std::vector<double> win_host;
@@ -190,6 +199,25 @@ int flacb200_engine_create(int device, flacb200_engine** out)
     cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking);
     for (auto& ev : e->ev) cudaEventCreate(&ev);
+    if (const char* v = getenv("FLACB200_LEGACY")) e->legacy = (unsigned)strtoul(v, nullptr, 0);
+    if (const char* v = getenv("FLACB200_BATCH_BYTES")) e->batch_bytes = std::max<size_t>((size_t)strtoull(v, nullptr, 0), 1);
+    e->no_batch = getenv("FLACB200_NO_BATCH") != nullptr;
+    e->debug = getenv("FLACB200_DEBUG") != nullptr;
+    // the CRC tables in device memory are built once per device, before any engine on it can launch a kernel that reads them
+    static std::once_flag tables_once[64];
+    static cudaError_t tables_err[64];
+    if (device < 64) {
+        std::call_once(tables_once[device], [&] {
+            init_encode_tables(e->own_stream);
+            init_decode_tables(e->own_stream);
+            tables_err[device] = cudaStreamSynchronize(e->own_stream);
+        });
+        if (tables_err[device] != cudaSuccess) {
+            const int rc = cuda_err(tables_err[device]);
+            flacb200_engine_destroy(e);
+            return rc;
+        }
+    }
     *out = e;
     return 0;
 }
@@ -231,6 +259,17 @@ int flacb200_engine_set_chunk_frames(flacb200_engine* e, uint32_t frames)
 {
     if (!e) return FLACB200_E_BAD_ARGUMENT;
     e->chunk_frames = frames;
+    return 0;
+}
+
+int flacb200_engine_set_option(flacb200_engine* e, const char* key, uint64_t value)
+{
+    if (!e || !key) return FLACB200_E_BAD_ARGUMENT;
+    if (!strcmp(key, "legacy")) e->legacy = (unsigned)value;
+    else if (!strcmp(key, "batch_bytes")) e->batch_bytes = (size_t)value;
+    else if (!strcmp(key, "no_batch")) e->no_batch = value != 0;
+    else if (!strcmp(key, "debug")) e->debug = value != 0;
+    else return FLACB200_E_BAD_ARGUMENT;
     return 0;
 }
 
@@ -429,8 +468,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     // ---- device buffers ----
     // kernel selection: the register-tiled kernels cover the common shapes; FLACB200_LEGACY (bit mask: 1 analyze,
     // 2 lpc, 4 pack) forces the generic kernels, which the parity tests use to cover both paths
-    const char* legacy_env = getenv("FLACB200_LEGACY");
-    const unsigned legacy = legacy_env ? (unsigned)strtoul(legacy_env, nullptr, 0) : 0u;
+    const unsigned legacy = e->legacy;
     const bool fast_analyze = analyze_fast_ok(cfg) && !(legacy & 1u);
     const bool fast_lpc = cfg.max_lpc_order >= 1 && !(legacy & 2u);
     const bool fast_pack = analyze_fast_ok(cfg) && !(legacy & 4u);
@@ -706,11 +744,11 @@ static int decode_batched(flacb200_engine* e, const flacb200_stream_params* para
                           uint64_t* n_frames_out, uint64_t* n_pcm_out, uint64_t* bad_frame)
 {
     size_t MIN_BYTES = (size_t)64 << 20, BATCH_BYTES = (size_t)192 << 20;
-    if (const char* bb = getenv("FLACB200_BATCH_BYTES")) {   // tests: small batches
-        BATCH_BYTES = std::max<size_t>((size_t)strtoull(bb, nullptr, 0), 1);
+    if (e->batch_bytes) {   // FLACB200_BATCH_BYTES / "batch_bytes" (tests: small batches)
+        BATCH_BYTES = e->batch_bytes;
         MIN_BYTES = 0;
     }
-    if (n_segments < 4 || frames_bytes < MIN_BYTES || pcm_kind == FLACB200_PCM_I32_PLANAR || getenv("FLACB200_NO_BATCH")) return -9999;
+    if (n_segments < 4 || frames_bytes < MIN_BYTES || pcm_kind == FLACB200_PCM_I32_PLANAR || e->no_batch) return -9999;
     const size_t fb = (size_t)params->channels * (pcm_kind <= 1 ? (params->bits_per_sample + 7) / 8 : 4);
     uint64_t prev_end = 0, prev_pcm = 0;
     for (size_t s = 0; s < n_segments; s++) {
@@ -896,8 +934,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     ENS(e->dec[9], (size_t)((group + 31u) & ~31u) * per_frame);   // whole bundles of 32 interleaved planes
     // FLACB200_LEGACY bit 64: the thread-per-frame decoder (k_decode) for everything; default: k_parse + k_restore, and
     // k_decode only for frames with a 33-bit side channel (32-bit stereo streams)
-    const char* legacy_env = getenv("FLACB200_LEGACY");
-    const bool split_decode = !(legacy_env && (strtoul(legacy_env, nullptr, 0) & 64u));
+    const bool split_decode = !(e->legacy & 64u);
     const bool maybe_wide = cfg.channels == 2 && cfg.bps == 32;
     if (split_decode) ENS(e->dec[10], (size_t)group * cfg.channels * sizeof(SubRec));
     size_t ngroups = 0;
@@ -930,7 +967,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
             mbox_post(e, 8, d_clean, 4, aux);
             CK(cudaStreamSynchronize(aux));
             const uint32_t clean = ((const uint32_t*)e->mbox_h)[2];
-            if (clean != 1 && getenv("FLACB200_DEBUG")) fprintf(stderr, "flacb200: k_chain_fast declined group at %u (reason 0x%x)\n", g0, clean);
+            if (clean != 1 && e->debug) fprintf(stderr, "flacb200: k_chain_fast declined group at %u (reason 0x%x)\n", g0, clean);
             if (clean != 1) CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, aux));
             CK(cudaEventRecord(e->pipe_ev[3 * ngroups + 2], aux));
             CK(cudaStreamWaitEvent(st, e->pipe_ev[3 * ngroups + 2], 0));
@@ -1047,6 +1084,28 @@ extern "C" int flacb200_md5_batch(flacb200_engine* e, const void* pcm, size_t pc
     memset(&e->tm, 0, sizeof(e->tm));
     cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
     e->tm.launches = 1;
+    return 0;
+}
+
+// the device build of glibc_log.cuh over an array (parity tooling: tests/test_gpu_libm.py compares it with the C library)
+__global__ void k_debug_libm(int fn, const double* __restrict__ in, double* __restrict__ out, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = fn == 0 ? glibc_log(in[i]) : glibc_log2(in[i]);
+}
+
+extern "C" int flacb200_debug_libm(flacb200_engine* e, int fn, const double* in, double* out, size_t n)
+{
+    if (!e || !in || !out || fn < 0 || fn > 1) return FLACB200_E_BAD_ARGUMENT;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    ENS(e->scratch, 2 * n * sizeof(double));
+    double* d_in = (double*)e->scratch.p;
+    double* d_out = d_in + n;
+    CK(cudaMemcpyAsync(d_in, in, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    k_debug_libm<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, e->stream>>>(fn, d_in, d_out, n);
+    CK(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
 

@@ -124,6 +124,10 @@ class Engine:
     def set_keep_info(self, on: bool):
         check(_abi.lib().flacb200_engine_set_keep_info(self._h, int(on)), "set_keep_info")
 
+    def set_option(self, key: str, value: int):
+        """Runtime knobs ("legacy", "batch_bytes", "no_batch", "debug"); the environment is only read at creation."""
+        check(_abi.lib().flacb200_engine_set_option(self._h, key.encode(), int(value)), f"set_option({key})")
+
     def set_profiling(self, on: bool):
         check(_abi.lib().flacb200_set_profiling(self._h, int(on)), "set_profiling")
 
@@ -131,6 +135,13 @@ class Engine:
         t = Timings()
         check(_abi.lib().flacb200_last_timings(self._h, C.byref(t)), "last_timings")
         return t
+
+    def debug_libm(self, fn: int, x: np.ndarray) -> np.ndarray:
+        """Device-side glibc_log (fn 0) / glibc_log2 (fn 1) of a float64 array (parity tooling)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        check(_abi.lib().flacb200_debug_libm(self._h, fn, _ptr(x), _ptr(out), x.size), "debug_libm")
+        return out
 
     def synchronize(self):
         check(_abi.lib().flacb200_synchronize(self._h), "synchronize")

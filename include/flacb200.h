@@ -86,6 +86,10 @@ void flacb200_engine_destroy(flacb200_engine* e);
 int flacb200_engine_set_stream(flacb200_engine* e, void* cuda_stream);
 /* Frames processed per internal launch group (bounds scratch memory); 0 = default */
 int flacb200_engine_set_chunk_frames(flacb200_engine* e, uint32_t frames);
+/* Runtime knobs for tests and experiments.  Their defaults come from the environment
+ * (FLACB200_LEGACY, FLACB200_BATCH_BYTES, FLACB200_NO_BATCH, FLACB200_DEBUG), which is read once, at
+ * flacb200_engine_create; keys: "legacy", "batch_bytes", "no_batch", "debug". */
+int flacb200_engine_set_option(flacb200_engine* e, const char* key, uint64_t value);
 /* Keep per-subframe decisions of each encode call for flacb200_encode_last_info (default on, calls of
  * at most 65536 frames); switch off on throughput paths -- it costs a device-to-host copy per group. */
 int flacb200_engine_set_keep_info(flacb200_engine* e, int enable);
@@ -183,6 +187,11 @@ int flacb200_last_timings(flacb200_engine* e, flacb200_timings* t);
 int flacb200_synth_pcm(flacb200_engine* e, void* pcm_device, uint64_t first_track, uint64_t n_tracks,
                        uint64_t n_pcm_frames, uint32_t channels, uint32_t sample_rate, uint32_t bits_per_sample,
                        uint64_t seed);
+
+/* Parity tooling: evaluates the engine's device-side log (fn = 0) / log2 (fn = 1) -- the restatement of glibc's
+ * functions that the LPC order estimate and coefficient shift use (src/encode.rs:3674, :3360) -- over n doubles
+ * (host pointers), so that a test can compare them bit for bit with the C library. */
+int flacb200_debug_libm(flacb200_engine* e, int fn, const double* in, double* out, size_t n);
 
 /* pinned host memory for the end-to-end path */
 void* flacb200_host_alloc(size_t bytes);

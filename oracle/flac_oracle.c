@@ -43,6 +43,12 @@ static void init_tables(void)
     tables_ready = 1;
 }
 
+void fo_libm(int fn, const double* in, double* out, size_t n)
+{
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) out[i] = fn == 0 ? log(in[i]) : log2(in[i]);
+}
+
 uint8_t fo_crc8(const uint8_t* p, size_t n)
 {
     init_tables();

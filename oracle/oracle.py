@@ -18,9 +18,8 @@ _LIB_PATH = os.path.join(_HERE, "libflac_oracle.so")
 def build(force: bool = False) -> str:
     """Compile the oracle with the recipe in oracle/Makefile (gcc only)."""
     src = os.path.join(_HERE, "flac_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or (
-        os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH)
-    ):
+    deps = [p for p in (src, os.path.join(_HERE, "flac_oracle.h"), os.path.join(_HERE, "Makefile")) if os.path.exists(p)]
+    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in deps):
         subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CC": "gcc"})
     return _LIB_PATH
 
@@ -286,6 +285,17 @@ def decode_frames_mt(frames: bytes, offsets: np.ndarray, si: Streaminfo, nthread
     if r < 0:
         raise OracleError(-r)
     return out[: total_samples * si.channels]
+
+
+def libm(fn: int, x: np.ndarray) -> np.ndarray:
+    """glibc's log (fn 0) / log2 (fn 1), elementwise (numpy's own log is a SIMD implementation, not the C library's)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    L = lib()
+    L.fo_libm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.fo_libm.restype = None
+    L.fo_libm(fn, x.ctypes.data, out.ctypes.data, x.size)
+    return out
 
 
 def md5(b: bytes) -> bytes:

@@ -22,13 +22,11 @@ def eng():
 
 
 @pytest.fixture(autouse=True, params=["parse+restore", "thread-per-frame"])
-def decode_path(request, monkeypatch):
-    """Every test runs over both decoders: k_parse + k_restore (default) and k_decode (FLACB200_LEGACY bit 64)."""
-    if request.param == "thread-per-frame":
-        monkeypatch.setenv("FLACB200_LEGACY", "64")
-    else:
-        monkeypatch.delenv("FLACB200_LEGACY", raising=False)
-    return request.param
+def decode_path(request, eng):
+    """Every test runs over both decoders: k_parse + k_restore (default) and k_decode ("legacy" bit 64)."""
+    eng.set_option("legacy", 64 if request.param == "thread-per-frame" else 0)
+    yield request.param
+    eng.set_option("legacy", 0)
 
 
 @pytest.fixture(scope="module")
@@ -181,7 +179,7 @@ def test_multi_segment_batch(eng, fo):
     eng.device_free(d_out)
 
 
-def test_batched_host_decode_equals_one_call(eng, fo, monkeypatch):
+def test_batched_host_decode_equals_one_call(eng, fo):
     """Host frames -> host PCM of many streams is cut into batches of segments whose upload, kernels and download overlap
     (decode_batched in engine.cu; 192 MB batches by default, tiny ones here): same PCM, counts and error as one call."""
     from flac_codec_b200 import _abi
@@ -210,12 +208,12 @@ def test_batched_host_decode_equals_one_call(eng, fo, monkeypatch):
         buf = np.zeros(boff, dtype=np.uint8)
         for (o, n, _, _), b in zip(segs, parts):
             buf[o:o + n] = np.frombuffer(bytes(b), dtype=np.uint8)
-        monkeypatch.setenv("FLACB200_NO_BATCH", "1")
+        eng.set_option("no_batch", 1)
         ref = run(buf, segs, poff)
-        monkeypatch.delenv("FLACB200_NO_BATCH")
-        monkeypatch.setenv("FLACB200_BATCH_BYTES", "30000")
+        eng.set_option("no_batch", 0)
+        eng.set_option("batch_bytes", 30000)
         got = run(buf, segs, poff)
-        monkeypatch.delenv("FLACB200_BATCH_BYTES")
+        eng.set_option("batch_bytes", 0)
         assert got[1:] == ref[1:], (got[1:], ref[1:])
         if not damaged:
             assert ref[3] == 0 and np.array_equal(got[0], ref[0])

@@ -263,7 +263,7 @@ def test_argument_errors(eng):
     assert total == 0 and len(sizes) == 0
 
 
-def test_generic_kernels_give_the_same_bytes(eng, fo, monkeypatch):
+def test_generic_kernels_give_the_same_bytes(eng, fo):
     """The engine picks register-tiled kernels for blocks <= 4096 / samples <= 28 bits / LPC order <= 16 and generic
     ones otherwise; FLACB200_LEGACY forces the generic kernels so that both paths are checked on the same inputs."""
     from flac_codec_b200 import Options
@@ -279,10 +279,10 @@ def test_generic_kernels_give_the_same_bytes(eng, fo, monkeypatch):
     # 1/2/4: generic analyze / lpc / pack; 8: k_pack2 instead of k_pack3; 16: k_analyze instead of k_analyze3;
     # 32: k_lpc2 instead of k_lpc3; 56: all second-generation register-tiled kernels; 63: everything generic
     for mask in ("7", "1", "2", "4", "8", "16", "32", "56", "63"):
-        monkeypatch.setenv("FLACB200_LEGACY", mask)
+        eng.set_option("legacy", int(mask))
         for label, opt, rate, bps, ch, x in cases:
             check(eng, fo, opt, rate, bps, ch, x, f"legacy={mask} {label}")
-    monkeypatch.delenv("FLACB200_LEGACY")
+    eng.set_option("legacy", 0)
 
 
 def test_frame_kernels_edge_shapes(eng, fo):

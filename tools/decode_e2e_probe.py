@@ -24,10 +24,10 @@ def main():
     res = {}
     for mb in (0, 96, 192, 384, 768, 1536):
         if mb == 0:
-            os.environ["FLACB200_NO_BATCH"] = "1"
+            eng.set_option("no_batch", 1)
         else:
-            os.environ.pop("FLACB200_NO_BATCH", None)
-            os.environ["FLACB200_BATCH_BYTES"] = str(mb << 20)
+            eng.set_option("no_batch", 0)
+            eng.set_option("batch_bytes", mb << 20)
         best = 1e9
         for _ in range(3):
             t0 = time.perf_counter()

@@ -75,10 +75,7 @@ def run(iters, seed, eng=None):
                 break
             off += int(sz)
         for legacy in ("", "64"):
-            if legacy:
-                os.environ["FLACB200_LEGACY"] = legacy
-            else:
-                os.environ.pop("FLACB200_LEGACY", None)
+            eng.set_option("legacy", int(legacy or 0))
             out = np.zeros(x.size, dtype=np.int32)
             buf = np.frombuffer(ref, dtype=np.uint8).copy()
             try:
@@ -86,15 +83,15 @@ def run(iters, seed, eng=None):
             except _abi.FlacB200Error as e:
                 if want_err == (e.code, e.bad_frame):
                     continue   # same error at the same frame as the reference decoder
-                os.environ.pop("FLACB200_LEGACY", None)
+                eng.set_option("legacy", 0)
                 return f"DECODE ERROR {desc} ({'k_decode' if legacy else 'k_parse+k_restore'}): {e}; the oracle: {want_err}"
             if want_err is not None:
-                os.environ.pop("FLACB200_LEGACY", None)
+                eng.set_option("legacy", 0)
                 return f"DECODE ACCEPTED what the oracle rejects {desc} ({'k_decode' if legacy else 'k_parse+k_restore'}): {want_err}"
             if ns != n or not np.array_equal(out.reshape(-1, ch), x):
-                os.environ.pop("FLACB200_LEGACY", None)
+                eng.set_option("legacy", 0)
                 return f"DECODE MISMATCH {desc} ({'k_decode' if legacy else 'k_parse+k_restore'}, {ns} samples)"
-        os.environ.pop("FLACB200_LEGACY", None)
+        eng.set_option("legacy", 0)
     return None
 
 
