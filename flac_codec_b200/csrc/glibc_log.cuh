@@ -37,9 +37,11 @@ static inline double gl_dbl_host(uint64_t u) { double x; memcpy(&x, &u, 8); retu
 #define GL_DBL(u) gl_dbl_host(u)
 #endif
 
-#ifndef __CUDACC__
+#ifdef __CUDACC__
+#define GL_FN __device__ inline
+#else
 #define __device__
-#define __host__
+#define GL_FN static inline
 #endif
 
 namespace flacb200 {
@@ -48,7 +50,7 @@ namespace flacb200 {
 
 // log(x) for finite x > 0 (the encoder never passes anything else: take_while(err > 0) precedes the call; zero,
 // negative, infinite and NaN arguments return what IEEE arithmetic makes of them below, not glibc's errno paths)
-__host__ __device__ inline double glibc_log(double x)
+GL_FN double glibc_log(double x)
 {
     uint64_t ix = GL_BITS(x);
     const uint64_t LO = 0x3fee000000000000ull;              // asuint64(1.0 - 0x1p-4)
@@ -101,7 +103,7 @@ __host__ __device__ inline double glibc_log(double x)
 }
 
 // log2(x), same contract
-__host__ __device__ inline double glibc_log2(double x)
+GL_FN double glibc_log2(double x)
 {
     uint64_t ix = GL_BITS(x);
     const uint64_t LO = 0x3feea4af00000000ull;              // asuint64(1.0 - 0x1.5b51p-5)

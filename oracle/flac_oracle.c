@@ -2024,6 +2024,17 @@ int fo_read_streaminfo(const uint8_t* f, size_t len, fo_streaminfo* si)
 
 int64_t fo_decode_stream(const uint8_t* flac, size_t len, int32_t* out, size_t out_cap, fo_streaminfo* si_out, uint8_t md5_out[16])
 {
+    return fo_decode_stream_ex(flac, len, out, out_cap, si_out, md5_out, NULL, NULL);
+}
+
+/* as fo_decode_stream; also reports how far the serial reader got: frames delivered before the error (= index of the failing
+ * frame) and interleaved samples written -- Decoder::read_frame hands every good frame out before it fails (src/decode.rs:1388) */
+int64_t fo_decode_stream_ex(const uint8_t* flac, size_t len, int32_t* out, size_t out_cap, fo_streaminfo* si_out, uint8_t md5_out[16],
+                            uint64_t* frames_done, uint64_t* samples_done)
+{
+    uint64_t nframes = 0;
+    if (frames_done) *frames_done = 0;
+    if (samples_done) *samples_done = 0;
     fo_streaminfo si;
     memset(&si, 0, sizeof(si));
     int rc = fo_read_streaminfo(flac, len, &si);
@@ -2059,8 +2070,11 @@ int64_t fo_decode_stream(const uint8_t* flac, size_t len, int32_t* out, size_t o
             for (uint32_t c = 0; c < h.channels; c++) out[written + (size_t)i * h.channels + c] = planar[(size_t)c * h.block_size + i];
         written += cnt;
         current += h.block_size;
+        nframes++;
     }
     free(planar);
+    if (frames_done) *frames_done = nframes;
+    if (samples_done) *samples_done = written;
     if (result < 0) return result;
     if (md5_out) {
         uint32_t bytes_per_sample = ((uint32_t)si.bps + 7) / 8;

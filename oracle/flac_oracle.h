@@ -202,6 +202,8 @@ int fo_lpc_residuals(uint32_t order, uint32_t shift, const int32_t* qcoefs, cons
 void fo_predict(const int64_t* coefficients, uint32_t order, uint32_t shift, int32_t* channel, uint32_t n);
 void fo_window(const fo_options* opt, uint32_t n, double* out);
 uint32_t fo_rice_parameter_f64(uint64_t sum, uint32_t samples); /* ceil(log2(sum/samples)) as the reference computes it */
+int64_t fo_decode_stream_ex(const uint8_t* flac, size_t len, int32_t* out, size_t out_cap, fo_streaminfo* si_out, uint8_t md5_out[16],
+                            uint64_t* frames_done, uint64_t* samples_done);
 /* the C library's log (fn 0) / log2 (fn 1) over an array: what f64::ln / f64::log2 of the reference resolve to on Linux */
 void fo_libm(int fn, const double* in, double* out, size_t n);
 uint8_t fo_crc8(const uint8_t* p, size_t n);

@@ -262,6 +262,22 @@ def decode_stream(flac: bytes, want_md5: bool = False):
     return res + (md5.tobytes(),) if want_md5 else res
 
 
+def decode_stream_ex(flac: bytes):
+    """The serial reader's full verdict: (error code or 0, frames delivered before the error, interleaved samples
+    delivered, the samples).  Decoder::read_frame hands out every good frame before it fails (src/decode.rs:1388)."""
+    L = lib()
+    L.fo_decode_stream_ex.restype = C.c_int64
+    L.fo_decode_stream_ex.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Streaminfo), C.c_void_p,
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    a = np.frombuffer(flac, dtype=np.uint8)
+    si = read_streaminfo(flac)
+    cap = si.total_samples * si.channels if si.total_samples else max(len(flac) * 64, 1 << 16)
+    out = np.zeros(cap, dtype=np.int32)
+    nf, ns = C.c_uint64(0), C.c_uint64(0)
+    r = L.fo_decode_stream_ex(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(si), None, C.byref(nf), C.byref(ns))
+    return (int(-r) if r < 0 else 0), nf.value, ns.value, out[: ns.value]
+
+
 def decode_frame(data: bytes, si: Streaminfo | None = None, remaining: int = 0):
     """Returns (planar int32 [channels, block], FrameHeader, bytes_consumed)."""
     L = lib()
