@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1/C2/C3/C5 legs (tests/config_legs.py)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     return ap.parse_args()
 
@@ -471,47 +472,92 @@ def run_gpu(args):
             line["decode"]["e2e"] = {"value": samples_per_step * world / (d_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": d_ms,
                                      "h2d_bytes_per_step": int(total), "d2h_bytes_per_step": int(pcm_bytes),
                                      "api": "flacb200_decode(host frames -> host PCM)", "pcm_frames_decoded": int(ns)}
+
+    # ---- CPU baseline on rank 0 at N=1: the oracle on all host cores, and parity of EVERY frame of the shard ----
+    # With the e2e leg's host buffers at hand this is one pass of the oracle over the whole shard (all tracks, every
+    # frame compared with what the GPU returned through the C ABI); without them (--no-e2e) a bounded sample.
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        from oracle import oracle as fo
+
+        if not args.no_e2e:
+            import ctypes
+
+            per_track = (n + 4095) // 4096
+            goff = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
+            h_pcm = np.ctypeslib.as_array((ctypes.c_uint8 * pcm_bytes).from_address(h_pcm_p))
+            h_out = np.ctypeslib.as_array((ctypes.c_uint8 * int(total)).from_address(h_out_p))
+            tb = n * bytes_per_pcm_frame
+            ofo = fo.options("best")
+            t_cpu, frames, same, ref_total, tracks_same = 0.0, 0, 0, 0, 0
+            for t in range(n_tracks):
+                x = fo.bytes_to_samples(h_pcm[t * tb:(t + 1) * tb].tobytes(), 3)
+                t0 = time.perf_counter()
+                data, rsizes = fo.encode_frames_only(ofo, RATE, BPS, CH, x, nthreads=cores)
+                t_cpu += time.perf_counter() - t0
+                ref_total += len(data)
+                g = h_out[goff[t * per_track]:goff[(t + 1) * per_track]].tobytes()
+                frames += len(rsizes)
+                if g == data:
+                    same += len(rsizes)
+                    tracks_same += 1
+                else:   # count the frames that do agree
+                    roff = np.concatenate([[0], np.cumsum(rsizes.astype(np.int64))])
+                    g0 = int(goff[t * per_track])
+                    for f in range(len(rsizes)):
+                        a, b = int(goff[t * per_track + f]) - g0, int(goff[t * per_track + f + 1]) - g0
+                        same += int(g[a:b] == data[roff[f]:roff[f + 1]])
+            line["cpu_baseline"] = {"value": samples_per_step / t_cpu / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"the whole shard once: {n_tracks} tracks x {args.seconds} s ({samples_per_step} samples), "
+                                              f"{t_cpu:.1f} s of oracle time on {cores} threads (frames of a track encoded concurrently)"}
+            line["parity_vs_cpu_port"] = {"frames_compared": frames, "byte_identical_frames": same, "identical_fraction": same / max(frames, 1),
+                                          "tracks_identical": tracks_same, "fraction_of_workload_compared": 1.0,
+                                          "size_delta": (int(total) - ref_total) / max(ref_total, 1),
+                                          "note": "encoder bytes are pinned to the oracle (CPU restatement); the reference's own tests only round-trip"}
+        else:
+            take = min(n, RATE * 60)
+            take -= take % 4096
+            ntr = min(n_tracks, 8)
+            xs = []
+            for t in range(ntr):
+                host = np.zeros(take * bytes_per_pcm_frame, dtype=np.uint8)
+                eng.memcpy(host, d_pcm + t * n * bytes_per_pcm_frame, host.nbytes, 2)
+                xs.append(fo.bytes_to_samples(host.tobytes(), 3))
+            v, sample, ref = cpu_encode_rate(xs, cores, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            gdata, gsizes, gtotal = eng.encode(opt, RATE, BPS, CH, d_pcm, pcm_bytes, _abi.PCM_BYTES_LE, [(t * n, take, 0) for t in range(ntr)],
+                                               pcm_location=_abi.DEVICE)
+            gbytes = gdata.tobytes()
+            goff = np.concatenate([[0], np.cumsum(gsizes.astype(np.int64))])
+            frames = same = 0
+            ref_total = 0
+            k = 0
+            for data, rsizes in ref:
+                roff = np.concatenate([[0], np.cumsum(rsizes.astype(np.int64))])
+                ref_total += len(data)
+                for f in range(len(rsizes)):
+                    frames += 1
+                    if k < len(gsizes) and gbytes[goff[k]:goff[k + 1]] == data[roff[f]:roff[f + 1]]:
+                        same += 1
+                    k += 1
+            line["parity_vs_cpu_port"] = {"frames_compared": frames, "byte_identical_frames": same, "identical_fraction": same / max(frames, 1),
+                                          "fraction_of_workload_compared": frames / max(n_tracks * ((n + 4095) // 4096), 1),
+                                          "size_delta": (gtotal - ref_total) / max(ref_total, 1)}
+    if not args.no_e2e:
         L.flacb200_host_free(h_pcm_p)
         L.flacb200_host_free(h_out_p)
 
-    # ---- CPU baseline on rank 0 at N=1: the oracle on all host cores over a bounded sample ----
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        take = min(n, RATE * 60)
-        take -= take % 4096
-        ntr = min(n_tracks, 8)
-        from oracle import oracle as fo
-
-        xs = []
-        for t in range(ntr):
-            host = np.zeros(take * bytes_per_pcm_frame, dtype=np.uint8)
-            eng.memcpy(host, d_pcm + t * n * bytes_per_pcm_frame, host.nbytes, 2)
-            xs.append(fo.bytes_to_samples(host.tobytes(), 3))
-        v, sample, ref = cpu_encode_rate(xs, cores, args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        # parity on that sample: the GPU's frames for the same blocks against the oracle's, frame by frame
-        eng.set_keep_info(False)
-        gdata, gsizes, gtotal = eng.encode(opt, RATE, BPS, CH, d_pcm, pcm_bytes, _abi.PCM_BYTES_LE, [(t * n, take, 0) for t in range(ntr)],
-                                           pcm_location=_abi.DEVICE)
-        gbytes = gdata.tobytes()
-        goff = np.concatenate([[0], np.cumsum(gsizes.astype(np.int64))])
-        frames = same = 0
-        ref_total = 0
-        k = 0
-        for data, sizes in ref:
-            roff = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
-            ref_total += len(data)
-            for f in range(len(sizes)):
-                frames += 1
-                if k < len(gsizes) and gbytes[goff[k]:goff[k + 1]] == data[roff[f]:roff[f + 1]]:
-                    same += 1
-                k += 1
-        line["parity_vs_cpu_port"] = {"frames_compared": frames, "byte_identical_frames": same,
-                                      "identical_fraction": same / max(frames, 1),
-                                      "size_delta": (gtotal - ref_total) / max(ref_total, 1)}
-
     eng.device_free(d_pcm)
     eng.device_free(d_out)
+    # ---- the other BASELINE configs at their stated sizes (rank 0 at N=1): GPU through the C ABI / stream facades, checked
+    # against the oracle (tests/config_legs.py; the same legs are asserted on by tests/test_gpu_configs.py) ----
+    if world == 1 and rank == 0 and not args.no_configs and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import config_legs
+        from oracle import oracle as fo
+
+        eng.set_profiling(False)
+        line["configs"] = config_legs.all_legs(eng, fo, reps=2)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,155 @@
+"""BASELINE.json's configurations other than the bench workload (C4), each at its STATED size: run through the C ABI /
+the stream facades on the GPU and checked against the CPU oracle.  Test infrastructure: tests/test_gpu_configs.py
+asserts on the results, bench.py adds them to its JSON line as `configs` (the oracle is the checker here, never the
+thing measured).
+
+  C1  wav2flac-equivalent: 60 s 44.1 kHz/16-bit stereo, Options::default(), whole .flac file (metadata, seek table,
+      MD5, frames) == the oracle's file
+  C2  flac2wav-equivalent: that file decoded through FlacByteReader == the input PCM == the oracle's decoder
+  C3  60 s 96 kHz/24-bit 8-channel, Options::best(): all 1407 frames byte-identical
+  C5  192 kHz/32-bit streams at max LPC order 32, blocks 4096 and 16384, 2 and 8 channels (encode byte-identical, decode
+      bit-exact, both decoders), plus the decoder over the reference's own .flac fixtures (the IETF testbench the config
+      names is not in the reference tree)
+
+Every leg returns {"name", "msamples_per_s", "identical", "frames", ...}; times are wall clock around the call with HOST
+buffers (best of `reps`), single-channel samples per second.
+"""
+from __future__ import annotations
+
+import hashlib
+import io
+import os
+import time
+
+import numpy as np
+
+from flacb200_testutil import ref_file, synth_pcm
+
+C5_SHAPES = ((2, 4096, 30), (2, 16384, 30), (8, 4096, 10), (8, 16384, 10))   # channels, block size, seconds
+
+
+def _best(fn, reps):
+    best, out = 1e30, None
+    for _ in range(max(reps, 1)):
+        t0 = time.perf_counter()
+        out = fn()
+        best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+def c1_c2(eng, fo, reps=2, seconds=60):
+    from flac_codec_b200 import Options, stream
+
+    rate, bps, ch = 44100, 16, 2
+    x = synth_pcm(0, ch, rate * seconds, rate, bps).reshape(-1)
+    raw = fo.samples_to_bytes(x, 2)
+    cores = os.cpu_count() or 1
+    ref, ref_sizes = fo.encode_stream(fo.options("default"), rate, bps, ch, x, total_known=True, nthreads=cores)
+
+    def enc():
+        sink = io.BytesIO()
+        w = stream.FlacByteWriter(sink, Options.default(), rate, bps, ch, len(raw), engine=eng, launch_frames=1024)
+        w.write(raw)
+        w.finalize()
+        w.close()
+        return sink.getvalue()
+
+    enc()
+    t, flac = _best(enc, reps)
+    si = fo.read_streaminfo(flac)
+    legs = [{"name": f"C1 wav2flac {seconds} s 44.1k/16/2 default, whole file via FlacByteWriter", "msamples_per_s": x.size / t / 1e6,
+             "ms": t * 1e3, "identical": flac == ref, "frames": int(len(ref_sizes)), "file_bytes": len(flac),
+             "md5_ok": bytes(si.md5) == hashlib.md5(raw).digest()}]
+
+    def dec():
+        r = stream.FlacByteReader(flac, engine=eng)
+        b = r.read()
+        r.close()
+        return b
+
+    dec()
+    t, pcm = _best(dec, reps)
+    want, _ = fo.decode_stream(ref)
+    legs.append({"name": "C2 flac2wav of the C1 file via FlacByteReader", "msamples_per_s": x.size / t / 1e6, "ms": t * 1e3,
+                 "identical": pcm == raw and np.array_equal(want, x), "frames": int(len(ref_sizes))})
+    return legs
+
+
+def c3(eng, fo, reps=2, seconds=60):
+    from flac_codec_b200 import Options, _abi
+
+    rate, bps, ch = 96000, 24, 8
+    n = rate * seconds
+    x = synth_pcm(3, ch, n, rate, bps).reshape(-1)
+    raw = np.frombuffer(fo.samples_to_bytes(x, 3), dtype=np.uint8).copy()
+    cores = os.cpu_count() or 1
+    ref, ref_sizes = fo.encode_frames_only(fo.options("best"), rate, bps, ch, x, nthreads=cores)
+
+    def enc():
+        return eng.encode(Options.best(), rate, bps, ch, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, n, 0)])
+
+    enc()
+    t, (data, sizes, total) = _best(enc, reps)
+    ident = data.tobytes() == ref
+    same = int((np.asarray(sizes) == np.asarray(ref_sizes)).sum()) if len(sizes) == len(ref_sizes) else 0
+    return [{"name": f"C3 {seconds} s 96k/24/8ch best, all frames", "msamples_per_s": x.size / t / 1e6, "ms": t * 1e3, "identical": ident,
+             "frames": int(len(ref_sizes)), "equal_frame_sizes": same, "size_delta": (total - len(ref)) / len(ref)}]
+
+
+def c5(eng, fo, reps=1, shapes=C5_SHAPES):
+    from flac_codec_b200 import Options, _abi, stream
+
+    rate, bps = 192000, 32
+    cores = os.cpu_count() or 1
+    legs = []
+    for ch, block, seconds in shapes:
+        n = rate * seconds
+        x = synth_pcm(5, ch, n, rate, bps).reshape(-1)
+        raw = np.frombuffer(fo.samples_to_bytes(x, 4), dtype=np.uint8).copy()
+        opt5 = fo.options("best", max_lpc_order=32, block_size=block)
+        flac5, sizes5 = fo.encode_stream(opt5, rate, bps, ch, x, total_known=True, nthreads=cores)
+        ref, _ = fo.encode_frames_only(opt5, rate, bps, ch, x, nthreads=cores)
+        o5 = Options.best().max_lpc_order(32).block_size(block)
+
+        def enc():
+            return eng.encode(o5, rate, bps, ch, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, n, 0)])
+
+        enc()
+        t, (data, _, total) = _best(enc, reps)
+        legs.append({"name": f"C5 encode {seconds} s 192k/32/{ch}ch LPC<=32 block {block}", "msamples_per_s": x.size / t / 1e6,
+                     "ms": t * 1e3, "identical": data.tobytes() == ref, "frames": int(len(sizes5))})
+        for legacy, label in ((0, "k_parse+k_restore"), (64, "k_decode")):
+            eng.set_option("legacy", legacy)
+            try:
+                def dec():
+                    r = stream.FlacSampleReader(flac5, engine=eng)
+                    y = r.read_to_end()
+                    r.close()
+                    return y
+
+                dec()
+                t, y = _best(dec, reps)
+            finally:
+                eng.set_option("legacy", 0)
+            legs.append({"name": f"C5 decode {seconds} s 192k/32/{ch}ch order 32 block {block} ({label})",
+                         "msamples_per_s": x.size / t / 1e6, "ms": t * 1e3, "identical": bool(np.array_equal(y, x)), "frames": int(len(sizes5))})
+    # the reference's own .flac fixtures (what stands in for the decoder testbench here)
+    for name in ("sine.flac", "all-frames.flac", "cuesheet.flac", "seektable.flac"):
+        flac = ref_file(name)
+        si = fo.read_streaminfo(flac)
+
+        def dec():
+            r = stream.FlacByteReader(flac, engine=eng)
+            b = r.read()
+            r.close()
+            return b
+
+        dec()
+        t, pcm = _best(dec, reps)
+        legs.append({"name": f"C5 decode fixture {name}", "msamples_per_s": si.total_samples * si.channels / t / 1e6, "ms": t * 1e3,
+                     "identical": hashlib.md5(pcm).digest() == bytes(si.md5), "frames": None})
+    return legs
+
+
+def all_legs(eng, fo, reps=2):
+    return c1_c2(eng, fo, reps) + c3(eng, fo, reps) + c5(eng, fo, 1)

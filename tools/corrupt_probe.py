@@ -30,7 +30,16 @@ def main():
     path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "ref_data", "sine.flac")
     trials = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1234
-    flac = bytearray(open(path, "rb").read())
+    if path.startswith("synth:"):   # synth:<bps>:<channels>:<preset>:<pcm frames>[:<block size>]
+        from flacb200_testutil import synth_pcm
+        f = path.split(":")
+        bps, nch, preset, n = int(f[1]), int(f[2]), f[3], int(f[4])
+        kw = {"block_size": int(f[5])} if len(f) > 5 else {}
+        rate = 48000
+        x = synth_pcm(11, nch, n, rate, bps)
+        flac = bytearray(fo.encode_stream(fo.options(preset, **kw), rate, bps, nch, x.reshape(-1))[0])
+    else:
+        flac = bytearray(open(path, "rb").read())
     si = fo.read_streaminfo(bytes(flac))
     offs = frame_offsets(bytes(flac), si)
     eng = Engine(0)
