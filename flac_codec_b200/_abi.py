@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflacb200.so")
+LIB_PATH = os.environ.get("FLACB200_LIB") or os.path.join(_HERE, "libflacb200.so")   # FLACB200_LIB: A/B builds of the same library
 
 HOST, DEVICE = 0, 1
 PCM_BYTES_LE, PCM_BYTES_BE, PCM_I32_INTERLEAVED, PCM_I32_PLANAR = 0, 1, 2, 3
@@ -90,6 +90,17 @@ class SeekPoint(C.Structure):
                 ("placeholder", C.c_uint32)]
 
 
+class FrameEntry(C.Structure):
+    _fields_ = [("byte_offset", C.c_uint64), ("pcm_offset", C.c_uint64), ("byte_length", C.c_uint32), ("block_size", C.c_uint32)]
+
+
+class FrameBuf(C.Structure):
+    _fields_ = [("samples", C.POINTER(C.c_int32)), ("n_samples", C.c_size_t), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("bits_per_sample", C.c_uint32), ("block_size", C.c_uint32)]
+
+
+NEED_DATA = -10
+
 EXPORTS = [
     "flacb200_writer_options_default", "flacb200_writer_options_fast", "flacb200_writer_options_best", "flacb200_writer_open",
     "flacb200_writer_close", "flacb200_total_from_bytes", "flacb200_total_from_samples", "flacb200_writer_header",
@@ -97,6 +108,10 @@ EXPORTS = [
     "flacb200_writer_flush", "flacb200_writer_finalize", "flacb200_writer_get_stats", "flacb200_read_streaminfo",
     "flacb200_reader_open", "flacb200_reader_close", "flacb200_reader_info", "flacb200_reader_seektable", "flacb200_reader_read",
     "flacb200_reader_seek", "flacb200_reader_verify", "flacb200_md5", "flacb200_md5_batch",
+    "flacb200_reader_open_stream", "flacb200_reader_feed", "flacb200_reader_set_window", "flacb200_reader_fill_buf",
+    "flacb200_reader_consume", "flacb200_reader_fill_channels", "flacb200_reader_consume_channels", "flacb200_stream_write",
+    "flacb200_stream_reader_open", "flacb200_stream_reader_close", "flacb200_stream_reader_feed", "flacb200_stream_reader_read",
+    "flacb200_decode_last_frames",
     "flacb200_options_default", "flacb200_options_fast", "flacb200_options_best", "flacb200_engine_create",
     "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_engine_set_keep_info", "flacb200_engine_set_option", "flacb200_encode",
     "flacb200_encode_bound", "flacb200_encode_last_info", "flacb200_decode", "flacb200_set_profiling",
@@ -188,6 +203,21 @@ def lib():
     L.flacb200_reader_read.argtypes = [vp, vp, C.c_size_t, C.c_int, szp]
     L.flacb200_reader_seek.argtypes = [vp, C.c_uint64]
     L.flacb200_reader_verify.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint8 * 16)]
+    L.flacb200_reader_open_stream.argtypes = [vp, C.POINTER(vp)]
+    L.flacb200_reader_feed.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    L.flacb200_reader_set_window.argtypes = [vp, C.c_size_t, C.c_uint64]
+    i32p = C.POINTER(C.c_int32)
+    L.flacb200_reader_fill_buf.argtypes = [vp, C.POINTER(i32p), szp]
+    L.flacb200_reader_consume.argtypes = [vp, C.c_size_t]
+    L.flacb200_reader_fill_channels.argtypes = [vp, C.POINTER(C.POINTER(i32p)), szp]
+    L.flacb200_reader_consume_channels.argtypes = [vp, C.c_size_t]
+    L.flacb200_stream_write.argtypes = [vp, C.POINTER(Options), C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_size_t, C.c_uint64, vp, C.c_size_t, szp]
+    L.flacb200_stream_reader_open.argtypes = [vp, C.POINTER(vp)]
+    L.flacb200_stream_reader_close.argtypes = [vp]
+    L.flacb200_stream_reader_close.restype = None
+    L.flacb200_stream_reader_feed.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    L.flacb200_stream_reader_read.argtypes = [vp, C.POINTER(FrameBuf)]
+    L.flacb200_decode_last_frames.argtypes = [vp, C.POINTER(FrameEntry), C.c_size_t, u64p]
     L.flacb200_md5.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint8 * 16)]
     L.flacb200_md5.restype = None
     L.flacb200_md5_batch.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(Segment), C.c_size_t,

@@ -94,4 +94,41 @@ __device__ inline uint32_t crc16_warp(const Crc16Tables& t, const uint8_t* __res
     return part & 0xffffu;
 }
 
+// ---- wide folding: 8 message bytes per step, look-ups independent of one another -----------------------------------
+// T[j][b] = b(x) * x^(16 + 8 j) mod P: the CRC of byte b followed by j zero bytes.  For 8 message bytes b0..b7 (b0 first)
+// F8 = T[7][b0] ^ T[6][b1] ^ ... ^ T[0][b7] is the CRC of those 8 bytes; a lane that owns every 32nd group of 8 bytes folds
+// acc = acc * x^2048 + F8 (two more look-ups, the only ones that depend on the previous step).
+struct Crc16Fold {
+    uint16_t T[8][256];
+    uint16_t m_lo[256], m_hi[256];   // (i) * x^2048, (i << 8) * x^2048
+    uint16_t xd2[33];                // x^(64 d), d = 0..32
+    uint16_t xd[33];                 // x^(32 d), d = 0..32
+};
+
+__device__ inline void crc16_fold_init(Crc16Fold& t)
+{
+    const uint32_t x2048 = gf16_xpow8(256);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = crc16_table_entry(i);
+        for (int j = 0; j < 8; j++) {
+            t.T[j][i] = (uint16_t)c;
+            c = gf16_mulmod(c, 0x0100);   // one more zero byte
+        }
+        t.m_lo[i] = (uint16_t)gf16_mulmod(i, x2048);
+        t.m_hi[i] = (uint16_t)gf16_mulmod(i << 8, x2048);
+    }
+    for (uint32_t i = threadIdx.x; i < 33; i += blockDim.x) {
+        t.xd2[i] = (uint16_t)gf16_xpow8(8 * i);
+        t.xd[i] = (uint16_t)gf16_xpow8(4 * i);
+    }
+}
+
+// CRC of 8 message bytes held as two big-endian words (hi = the first four bytes)
+__device__ inline uint32_t crc16_f8(const Crc16Fold& t, uint32_t hi, uint32_t lo)
+{
+    const uint32_t a = t.T[7][hi >> 24] ^ t.T[6][(hi >> 16) & 0xff], b = t.T[5][(hi >> 8) & 0xff] ^ t.T[4][hi & 0xff];
+    const uint32_t c = t.T[3][lo >> 24] ^ t.T[2][(lo >> 16) & 0xff], d = t.T[1][(lo >> 8) & 0xff] ^ t.T[0][lo & 0xff];
+    return (a ^ b) ^ (c ^ d);
+}
+
 }   // namespace flacb200

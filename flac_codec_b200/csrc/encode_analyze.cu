@@ -26,7 +26,10 @@ namespace flacb200 {
 
 bool analyze_fast_ok(const EncCfg& cfg);   // encode_kernels.cu
 
-constexpr int A3_WPC = 2;        // warps per candidate
+#ifndef FLACB200_A3_WPC
+#define FLACB200_A3_WPC 2
+#endif
+constexpr int A3_WPC = FLACB200_A3_WPC;   // warps per candidate
 constexpr int A3_SETS = 6;       // fixed orders 0..4, LPC
 constexpr int A3_PLANE = 4096;   // samples per plane (largest block of the register-tiled kernels)
 
@@ -169,7 +172,7 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                 }
                 aw_choose_partitions(cfg, n, fo, p_max, sm.tree[0], sm.part_est[0], sm.part_code[0], sm.choice[0]);
                 if (lane == 0) sm.fo = fo;
-            } else {           // second warp: the LPC predictor
+            } else if (wsub == 1) {   // second warp: the LPC predictor
                 lpc_ok = have_lpc && sm.ovf == 0;   // ResidualOverflow
                 if (lpc_ok) {
                     for (uint32_t j = lane; j < nleaf; j += 32)

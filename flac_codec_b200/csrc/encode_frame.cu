@@ -19,24 +19,25 @@ namespace flacb200 {
 
 bool analyze_fast_ok(const EncCfg& cfg);   // encode_kernels.cu
 
-__device__ Crc16Tables g_crc16_tabs;   // built once per device by k_crc16_tables_init
+__device__ Crc16Fold g_crc16_tabs;   // built once per device by k_crc16_tables_init
 
 __device__ uint16_t g_crc16_xblk[1024];   // x^(1024 j) mod P: shifts a CRC over j blocks of 32 words
 
 __global__ void k_crc16_tables_init()
 {
-    crc16_tables_init(g_crc16_tabs);
+    crc16_fold_init(g_crc16_tabs);
     for (uint32_t j = threadIdx.x; j < 1024; j += blockDim.x) g_crc16_xblk[j] = (uint16_t)gf16_xpow8(128 * j);
 }
 
 // OR the low nbits (1..32) of v into the big-endian bit image `words` at bit position pos
-__device__ inline void p3_put(uint32_t* words, uint32_t pos, uint32_t nbits, uint32_t v)
+__device__ inline void p3_put(uint32_t words_sa, uint32_t pos, uint32_t nbits, uint32_t v)
 {
     const uint32_t w = pos >> 5, off = pos & 31;
     const unsigned long long wide = ((unsigned long long)v) << (64u - nbits - off);
     const uint32_t hi = (uint32_t)(wide >> 32), lo = (uint32_t)wide;
-    // reductions without a return value; the second word is touched only when the code straddles (predicated, no branch)
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(words + w);
+    // reductions without a return value; the second word is touched only when the code straddles (predicated, no branch);
+    // words_sa: shared-window address of the image (converted once per kernel, not per code)
+    const uint32_t a = words_sa + 4u * w;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "red.shared.or.b32 [%0], %1;\n\t"
@@ -45,38 +46,43 @@ __device__ inline void p3_put(uint32_t* words, uint32_t pos, uint32_t nbits, uin
         ::"r"(a), "r"(hi), "r"(lo) : "memory");
 }
 
-__device__ inline void p3_put_masked(uint32_t* words, uint32_t pos, uint32_t nbits, uint32_t v)
+__device__ inline void p3_put_masked(uint32_t words_sa, uint32_t pos, uint32_t nbits, uint32_t v)
 {
     if (nbits == 0) return;
     if (nbits < 32) v &= (1u << nbits) - 1u;
-    p3_put(words, pos, nbits, v);
+    p3_put(words_sa, pos, nbits, v);
 }
 
-// CRC-16 of the message bytes held in words[w0 .. w0 + nw) (big-endian words: the first message byte is the top byte).
-// One warp, all lanes call and get the result.
-__device__ inline uint32_t p3_crc_words(const Crc16Tables& t, const uint32_t* words, uint32_t w0, uint32_t nw)
+// CRC-16 of the message bytes held in words[w0 .. w0 + nw) (big-endian words: the first message byte is the top byte;
+// w0 even).  One warp, all lanes call and get the result.  A lane folds every 32nd PAIR of words (crc.cuh); an odd last
+// word is appended by the classic byte steps.
+__device__ inline uint32_t p3_crc_words(const Crc16Fold& t, const uint32_t* words, uint32_t w0, uint32_t nw)
 {
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t np = nw >> 1;
+    const uint2* pairs = reinterpret_cast<const uint2*>(words + w0);
     uint32_t acc = 0, last = 0;
     bool any = false;
-    for (uint32_t i = lane; i < nw; i += 32) {
-        const uint32_t v = words[w0 + i];
-        uint32_t f = t.byte_tab[v >> 24];
-        f = crc16_byte(t, f, (v >> 16) & 0xff);
-        f = crc16_byte(t, f, (v >> 8) & 0xff);
-        f = crc16_byte(t, f, v & 0xff);
-        acc = (t.mul_hi[acc >> 8] ^ t.mul_lo[acc & 0xff]) ^ f;   // acc * x^1024 + F(word): 32 words lie between two words of a lane
+    for (uint32_t i = lane; i < np; i += 32) {
+        const uint2 v = pairs[i];
+        const uint32_t f = crc16_f8(t, v.x, v.y);
+        acc = (t.m_hi[acc >> 8] ^ t.m_lo[acc & 0xff]) ^ f;   // acc * x^2048 + F8: 32 pairs lie between two pairs of a lane
         last = i;
         any = true;
     }
-    uint32_t part = any ? gf16_mulmod(acc, t.xd[nw - 1 - last]) : 0u;
+    uint32_t part = any ? gf16_mulmod(acc, t.xd2[np - 1 - last]) : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
+    part &= 0xffffu;
+    if (nw & 1u) {   // the odd word: shift by four bytes, add its CRC
+        const uint32_t v = words[w0 + nw - 1];
+        part = gf16_mulmod(part, t.xd[1]) ^ t.T[3][v >> 24] ^ t.T[2][(v >> 16) & 0xff] ^ t.T[1][(v >> 8) & 0xff] ^ t.T[0][v & 0xff];
+    }
     return part & 0xffffu;
 }
 
 struct P3Smem {
-    Crc16Tables tabs;
+    Crc16Fold tabs;
     uint32_t crc_part[MAX_CH];
     FrameRec fr;
     CandRec cr[MAX_CH];
@@ -85,7 +91,7 @@ struct P3Smem {
 // the residual block of one FIXED / LPC subframe; pos = bit position of the first residual partition header
 template <int HB, bool STEREO>
 __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const uint8_t* __restrict__ pcm, uint32_t slot, const CandRec& cr,
-                                    uint32_t* words, uint32_t pos)
+                                    uint32_t words_sa, uint32_t pos)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n = d.n, wasted = cr.wasted, order = cr.order, shift = cr.shift;
@@ -187,7 +193,7 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
         // ---- emission ----
         if (uniform && cc0 < 0x40) {
             if (hdr_here) {
-                p3_put(words, p, hb, cc0);
+                p3_put(words_sa, p, hb, cc0);
                 p += hb;
             }
             const uint32_t stop = 1u << cc0, mask = stop - 1u;
@@ -195,7 +201,7 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
             for (int e = 0; e < 16; e++) {
                 const uint32_t u = zigzag32(r[e]);
                 // unary zeros, stop bit, cc0 LSBs; a warm-up sample ORs nothing (its length is 0: p stays)
-                p3_put(words, p + ((uint32_t)e >= skip ? u >> cc0 : 0u), cc0 + 1u, (uint32_t)e >= skip ? stop | (u & mask) : 0u);
+                p3_put(words_sa, p + ((uint32_t)e >= skip ? u >> cc0 : 0u), cc0 + 1u, (uint32_t)e >= skip ? stop | (u & mask) : 0u);
                 p += len[e];
             }
         } else if (live) {
@@ -207,14 +213,14 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
                 const uint32_t cc = cr.rice[pi - j0];
                 uint32_t at = p;
                 if (i == max(pi * cp, order)) {
-                    if (cc < 0x40) { p3_put(words, at, hb, cc); at += hb; }
-                    else { p3_put(words, at, hb, escape_code); p3_put_masked(words, at + hb, 5, (cc & 0x40) ? (cc & 31u) : 0u); at += hb + 5; }
+                    if (cc < 0x40) { p3_put(words_sa, at, hb, cc); at += hb; }
+                    else { p3_put(words_sa, at, hb, escape_code); p3_put_masked(words_sa, at + hb, 5, (cc & 0x40) ? (cc & 31u) : 0u); at += hb + 5; }
                 }
                 if (cc < 0x40) {
                     const uint32_t u = zigzag32(r[e]);
-                    p3_put(words, at + (u >> cc), cc + 1u, (1u << cc) | (u & ((1u << cc) - 1u)));
+                    p3_put(words_sa, at + (u >> cc), cc + 1u, (1u << cc) | (u & ((1u << cc) - 1u)));
                 } else if (cc & 0x40) {
-                    p3_put_masked(words, at, cc & 31u, (uint32_t)r[e]);   // escaped: raw two's complement (:3857)
+                    p3_put_masked(words_sa, at, cc & 31u, (uint32_t)r[e]);   // escaped: raw two's complement (:3857)
                 }
                 p += len[e];
             }
@@ -223,16 +229,25 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
 }
 
 // grid = frames of the launch group; block = 32 * (subframes per frame); dynamic smem = image words
+// Two launches share the work: the first with a shared-memory image sized for ordinary frames (min_words = 0, cap_words =
+// P3_SMALL_WORDS: more CTAs per SM), the second with room for the worst case, for the few frames that need more
+// (min_words = P3_SMALL_WORDS); a CTA whose frame belongs to the other launch exits at once.
 template <int HB, bool STEREO>
-__global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
-                                              const CandRec* __restrict__ cands, const FrameRec* __restrict__ frecs, uint8_t* __restrict__ out)
+__global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? 9 : 2)
+    k_pack3(EncCfg cfg, uint32_t min_words, uint32_t cap_words, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
+            const CandRec* __restrict__ cands, const FrameRec* __restrict__ frecs, uint8_t* __restrict__ out)
 {
     extern __shared__ __align__(16) uint32_t p3_words[];
     __shared__ P3Smem sm;
     const uint32_t f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const uint32_t words_sa = (uint32_t)__cvta_generic_to_shared(p3_words);
+    {
+        const uint32_t need = (frecs[f].frame_bytes + 3) / 4 + 2;
+        if (need <= min_words || (need > cap_words && min_words == 0)) return;   // the other launch's frame
+    }
     // ---- stage the frame record, its subframes' candidate records and the CRC tables; clear the image ----
     for (uint32_t i = tid; i < sizeof(FrameRec) / 4; i += nthreads) reinterpret_cast<uint32_t*>(&sm.fr)[i] = reinterpret_cast<const uint32_t*>(frecs + f)[i];
-    for (uint32_t i = tid; i < sizeof(Crc16Tables) / 4; i += nthreads)
+    for (uint32_t i = tid; i < sizeof(Crc16Fold) / 4; i += nthreads)
         reinterpret_cast<uint32_t*>(&sm.tabs)[i] = reinterpret_cast<const uint32_t*>(&g_crc16_tabs)[i];
     __syncthreads();
     const FrameRec& fr = sm.fr;
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words
     const FrameDesc d = descs[f];
     const uint32_t n = d.n;
     // ---- frame header (src/stream.rs:242-276; bytes prepared by k_decide) ----
-    if (tid < fr.hdr_len) p3_put(p3_words, 8 * tid, 8, fr.hdr[tid]);
+    if (tid < fr.hdr_len) p3_put(words_sa, 8 * tid, 8, fr.hdr[tid]);
     // ---- subframes: one warp each ----
     for (uint32_t c = wid; c < nsub; c += nwarps) {
         const CandRec& cr = sm.cr[c];
@@ -258,15 +273,15 @@ __global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words
         uint32_t pos = fr.sub_bit[c];
         if (lane == 0) {   // SubframeHeader (src/stream.rs:1397-1413): pad, 6-bit type, wasted flag, unary(wasted - 1)
             const uint32_t code = type == 0 ? 0u : type == 1 ? 1u : type == 2 ? 8u + order : 31u + order;
-            p3_put_masked(p3_words, pos, 8, (code << 1) | (wasted ? 1u : 0u));
-            if (wasted) p3_put(p3_words, pos + 8 + (wasted - 1), 1, 1);
+            p3_put_masked(words_sa, pos, 8, (code << 1) | (wasted ? 1u : 0u));
+            if (wasted) p3_put(words_sa, pos + 8 + (wasted - 1), 1, 1);
         }
         pos += 8 + wasted;
         if (type == 0) {   // CONSTANT (:2982-2998): the first sample
             if (lane == 0) {
                 int32_t x[16];
                 aw_load_tile<STEREO>(cfg, d, pcm, slot, 0, x);
-                p3_put_masked(p3_words, pos, bps, (uint32_t)(x[0] >> wasted));
+                p3_put_masked(words_sa, pos, bps, (uint32_t)(x[0] >> wasted));
             }
             continue;
         }
@@ -276,7 +291,7 @@ __global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words
                 aw_load_tile<STEREO>(cfg, d, pcm, slot, i0, x);
 #pragma unroll
                 for (int e = 0; e < 16; e++)
-                    if (i0 + e < n) p3_put_masked(p3_words, pos + (i0 + e) * bps, bps, (uint32_t)(x[e] >> wasted));
+                    if (i0 + e < n) p3_put_masked(words_sa, pos + (i0 + e) * bps, bps, (uint32_t)(x[e] >> wasted));
             }
             continue;
         }
@@ -285,32 +300,32 @@ __global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words
             aw_load_tile<STEREO>(cfg, d, pcm, slot, 0, x);
 #pragma unroll
             for (int e = 0; e < 16; e++)
-                if ((uint32_t)e < order) p3_put_masked(p3_words, pos + e * bps, bps, (uint32_t)(x[e] >> wasted));
+                if ((uint32_t)e < order) p3_put_masked(words_sa, pos + e * bps, bps, (uint32_t)(x[e] >> wasted));
         }
         pos += order * bps;
         if (type == 3) {   // :3122-3133
             const uint32_t prec = cr.precision;
             if (lane == 0) {
-                p3_put_masked(p3_words, pos, 4, prec - 1);
-                p3_put_masked(p3_words, pos + 4, 5, cr.shift);
+                p3_put_masked(words_sa, pos, 4, prec - 1);
+                p3_put_masked(words_sa, pos + 4, 5, cr.shift);
             }
-            if (lane < order) p3_put_masked(p3_words, pos + 9 + lane * prec, prec, (uint32_t)(int32_t)cr.q[lane]);
+            if (lane < order) p3_put_masked(words_sa, pos + 9 + lane * prec, prec, (uint32_t)(int32_t)cr.q[lane]);
             pos += 9 + order * prec;
         }
         if (lane == 0) {   // residual block header (:3944-3961)
-            p3_put_masked(p3_words, pos, 2, cr.method);
-            p3_put_masked(p3_words, pos + 2, 4, cr.porder_w);
+            p3_put_masked(words_sa, pos, 2, cr.method);
+            p3_put_masked(words_sa, pos + 2, 4, cr.porder_w);
         }
         pos += 6;
-        p3_residuals<HB, STEREO>(cfg, d, pcm, slot, cr, p3_words, pos);
+        p3_residuals<HB, STEREO>(cfg, d, pcm, slot, cr, words_sa, pos);
     }
     __syncthreads();
     // ---- CRC-16 over everything but the last two bytes (src/encode.rs:2408-2409) ----
     const uint32_t body = frame_bytes - 2;
     const uint32_t bw = body >> 2, btail = body & 3;
     {
-        // warp w takes words [w * per, (w + 1) * per), per a multiple of 32
-        const uint32_t per = (((bw + nwarps - 1) / nwarps) + 31u) & ~31u;
+        // warp w takes words [w * per, (w + 1) * per), per a multiple of 64 (whole rounds of 32 pairs)
+        const uint32_t per = (((bw + nwarps - 1) / nwarps) + 63u) & ~63u;
         const uint32_t a = min(wid * per, bw), b = min(a + per, bw);
         const uint32_t part = p3_crc_words(sm.tabs, p3_words, a, b - a);
         if (lane == 0) sm.crc_part[wid] = part;
@@ -326,8 +341,8 @@ __global__ void __launch_bounds__(256, 2) k_pack3(EncCfg cfg, uint32_t cap_words
                     crc ^= sm.crc_part[w];
                 }
             }
-            for (uint32_t t = 0; t < btail; t++) crc = crc16_byte(sm.tabs, crc, (p3_words[bw] >> (24 - 8 * t)) & 0xff);
-            p3_put(p3_words, body * 8, 16, crc);
+            for (uint32_t t = 0; t < btail; t++) crc = (sm.tabs.T[0][((crc >> 8) ^ (p3_words[bw] >> (24 - 8 * t))) & 0xff] ^ (crc << 8)) & 0xffffu;
+            p3_put(words_sa, body * 8, 16, crc);
         }
         __syncthreads();
     }
@@ -370,13 +385,15 @@ cudaError_t launch_pack3(const EncCfg& cfg, const FrameDesc* descs, const uint8_
 {
     const uint32_t nsub = cfg.mode == MODE_INDEPENDENT ? cfg.channels : 2;
     const uint32_t cap_words = pack3_cap_words(cfg);
-    const size_t smem = (size_t)cap_words * 4;
+    // ordinary frames compress to well under 3/4 of the raw size: a smaller image lets more CTAs share an SM
+    const uint32_t small_words = (cap_words * 3u / 4u) & ~1u;
     const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
 #define FLACB200_P3(HBV, ST)                                                                                                         \
     do {                                                                                                                             \
         cudaError_t e_ = cudaFuncSetAttribute(k_pack3<HBV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);            \
         if (e_ != cudaSuccess) return e_;                                                                                            \
-        k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, smem, st>>>(cfg, cap_words, descs, pcm, cands, frecs, out);                       \
+        k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)small_words * 4, st>>>(cfg, 0u, small_words, descs, pcm, cands, frecs, out);    \
+        k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)cap_words * 4, st>>>(cfg, small_words, cap_words, descs, pcm, cands, frecs, out); \
     } while (0)
     if (cfg.mode != MODE_INDEPENDENT) {
         switch (hb) {

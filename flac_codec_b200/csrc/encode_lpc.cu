@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const Fra
     extern __shared__ __align__(16) uint8_t l3_dyn[];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t M = cfg.max_lpc_order;
-    const uint32_t f0 = (blockIdx.x * L3_WARPS + wid) * 2;   // first frame of this warp
-    if (f0 >= nframes) return;
+    // a warp takes pairs of frames; the grid may be smaller than the work (persistent launch: a few CTAs per SM that run
+    // beside the integer kernels of the previous launch group, see flacb200_encode)
+    for (uint32_t pair = blockIdx.x * L3_WARPS + wid; 2 * pair < nframes; pair += gridDim.x * L3_WARPS) {
+    const uint32_t f0 = pair * 2;   // first frame of this warp
     const uint32_t nfr = min(2u, nframes - f0);
     uint8_t* wsm = l3_dyn + (size_t)wid * (L3_CANDS * L3_CD * 8 + L3_STAGE_BYTES);
     double* wbase = reinterpret_cast<double*>(wsm);
@@ -316,6 +318,8 @@ __global__ void __launch_bounds__(32 * L3_WARPS, 3) k_lpc3(EncCfg cfg, const Fra
             }
         }
     }
+    __syncwarp();   // the next pair's rings overwrite R[] and the coefficient sets
+    }
 }
 
 // stereo frames (L, R, M, S slots), packed byte PCM, 16-byte aligned blocks, order <= 15 (four lanes x four lags)
@@ -325,13 +329,17 @@ bool lpc3_ok(const EncCfg& cfg, bool blocks_aligned16)
            blocks_aligned16;
 }
 
-cudaError_t launch_lpc3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const double* winpool, LpcRec* lpcs, cudaStream_t st)
+// max_ctas: 0 = one warp per pair of frames; else a persistent grid of at most that many CTAs
+cudaError_t launch_lpc3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const double* winpool, LpcRec* lpcs, uint32_t max_ctas,
+                        cudaStream_t st)
 {
     const size_t smem = (size_t)L3_WARPS * (L3_CANDS * L3_CD * 8 + L3_STAGE_BYTES);
     cudaError_t e = cudaFuncSetAttribute(k_lpc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint32_t nwarps = (cfg.nframes + 1) / 2;
-    k_lpc3<<<(nwarps + L3_WARPS - 1) / L3_WARPS, 32 * L3_WARPS, smem, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes);
+    uint32_t grid = (nwarps + L3_WARPS - 1) / L3_WARPS;
+    if (max_ctas && grid > max_ctas) grid = max_ctas;
+    k_lpc3<<<grid, 32 * L3_WARPS, smem, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes);
     return cudaGetLastError();
 }
 

@@ -30,7 +30,7 @@ void launch_decide_scan(const EncCfg&, const FrameDesc*, const CandRec*, const u
 bool pack3_ok(const EncCfg&);
 bool analyze3_ok(const EncCfg&);
 bool lpc3_ok(const EncCfg&, bool);
-cudaError_t launch_lpc3(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, cudaStream_t);
+cudaError_t launch_lpc3(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, uint32_t, cudaStream_t);
 cudaError_t launch_analyze3(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, cudaStream_t);
 cudaError_t launch_pack3(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
@@ -98,6 +98,9 @@ struct flacb200_engine {
     unsigned legacy = 0;
     bool no_batch = false, debug = false;
     size_t batch_bytes = 0;   // 0 = default
+    uint32_t lpc_overlap = 1;   // CTAs per SM of the persistent k_lpc3 that runs beside the previous group's integer kernels; 0 = off
+    int sm_count = 148;
+    std::vector<cudaEvent_t> lpc_ev;   // per group: LPC parameters ready, analysis done (the two LpcRec buffers alternate)
     DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, dec[12];
     std::map<uint32_t, uint32_t> win_off;   // block length -> offset in doubles
     std::vector<double> win_host;
@@ -111,6 +114,7 @@ struct flacb200_engine {
     std::vector<FrameRec> info_frecs;
     EncCfg info_cfg{};
     uint64_t info_frames = 0;
+    uint32_t last_ncand = 0;   // candidates of the most recent decode call (flacb200_decode_last_frames)
     void* host_stage = nullptr;
     size_t host_stage_cap = 0;
     std::vector<FrameDesc> descs_host;
@@ -199,6 +203,8 @@ int flacb200_engine_create(int device, flacb200_engine** out)
     cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking);
     for (auto& ev : e->ev) cudaEventCreate(&ev);
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char* v = getenv("FLACB200_LPC_OVERLAP")) e->lpc_overlap = (uint32_t)strtoul(v, nullptr, 0);
     if (const char* v = getenv("FLACB200_LEGACY")) e->legacy = (unsigned)strtoul(v, nullptr, 0);
     if (const char* v = getenv("FLACB200_BATCH_BYTES")) e->batch_bytes = std::max<size_t>((size_t)strtoull(v, nullptr, 0), 1);
     e->no_batch = getenv("FLACB200_NO_BATCH") != nullptr;
@@ -241,6 +247,7 @@ void flacb200_engine_destroy(flacb200_engine* e)
     if (e->mbox_h) cudaFreeHost(e->mbox_h);
     for (auto& ev : e->pipe_ev) cudaEventDestroy(ev);
     for (auto& ev : e->batch_ev) cudaEventDestroy(ev);
+    for (auto& ev : e->lpc_ev) cudaEventDestroy(ev);
     cudaStreamDestroy(e->aux);
     cudaStreamDestroy(e->copy_in);
     cudaStreamDestroy(e->copy_out);
@@ -269,6 +276,7 @@ int flacb200_engine_set_option(flacb200_engine* e, const char* key, uint64_t val
     else if (!strcmp(key, "batch_bytes")) e->batch_bytes = (size_t)value;
     else if (!strcmp(key, "no_batch")) e->no_batch = value != 0;
     else if (!strcmp(key, "debug")) e->debug = value != 0;
+    else if (!strcmp(key, "lpc_overlap")) e->lpc_overlap = (uint32_t)value;
     else return FLACB200_E_BAD_ARGUMENT;
     return 0;
 }
@@ -486,7 +494,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     ENS(e->descs, nframes * sizeof(FrameDesc));
     if (need_planes) ENS(e->planes, ncand_chunk * cfg.bpad * sizeof(int32_t));
     ENS(e->masks, (size_t)chunk * (cfg.nslots * sizeof(uint32_t) + 4 * sizeof(unsigned long long)) + 64);
-    ENS(e->lpcs, ncand_chunk * sizeof(LpcRec));
+    ENS(e->lpcs, 2 * ncand_chunk * sizeof(LpcRec));   // two buffers: k_lpc3 of group g + 1 runs beside the integer kernels of group g
     ENS(e->cands, ncand_chunk * sizeof(CandRec));
     ENS(e->frecs, (size_t)chunk * sizeof(FrameRec));
     ENS(e->fbytes, nframes * sizeof(uint32_t));
@@ -567,27 +575,59 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     uint32_t launches = 0;
     size_t nchunks = 0;
     bool pipe_overflow = false;
-    cudaEventRecord(e->ev[22], st);
-    for (uint64_t base = 0; base < nframes; base += chunk) {
+    // FP64 / integer overlap: k_lpc3 of group g + 1 is launched on a second stream as a PERSISTENT grid (a few CTAs per SM --
+    // small enough to be resident next to the CTAs of k_analyze3 / k_pack3 of group g, which leave the FP64 pipe idle); a
+    // full-size grid on a second stream would only start when the first kernel's last CTA has been dispatched
+    const bool overlap = staged_lpc && frame_analyze && frame_pack && e->lpc_overlap != 0 && ngroups > 1;
+    LpcRec* lpc_buf[2] = {(LpcRec*)e->lpcs.p, (LpcRec*)e->lpcs.p + ncand_chunk};
+    if (overlap)
+        while (e->lpc_ev.size() < 2 * ngroups) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->lpc_ev.push_back(ev);
+        }
+    auto group_cfg = [&](uint64_t base) {
         EncCfg c = cfg;
         c.nframes = (uint32_t)std::min<uint64_t>(chunk, nframes - base);
+        return c;
+    };
+    cudaEventRecord(e->ev[22], st);
+    for (uint64_t base = 0; base < nframes; base += chunk) {
+        const EncCfg c = group_cfg(base);
         const FrameDesc* dd = (const FrameDesc*)e->descs.p + base;
+        LpcRec* lp = overlap ? lpc_buf[nchunks & 1] : lpc_buf[0];
         if (pipe_in) CK(cudaStreamWaitEvent(st, e->pipe_ev[2 * nchunks], 0));
         CK(cudaMemsetAsync(e->masks.p, 0, masks_bytes, st));
         const size_t eb = nchunks * 6;
         time_mark(e, eb + 0);
         if (need_planes) launch_planes(c, dd, d_pcm, (int32_t*)e->planes.p, d_ormask, d_abssum, st);
         time_mark(e, eb + 1);
-        if (staged_lpc) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st));
-        else if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st));
-        else launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, (LpcRec*)e->lpcs.p, st);
+        if (overlap) {
+            if (nchunks == 0) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
+            else CK(cudaStreamWaitEvent(st, e->lpc_ev[2 * nchunks], 0));   // launched beside the previous group
+        } else if (staged_lpc) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
+        else if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, lp, st));
+        else launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, lp, st);
         time_mark(e, eb + 2);
-        if (frame_analyze) CK(launch_analyze3(c, dd, d_pcm, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p, d_abssum, st));
-        else if (fast_analyze) CK(launch_analyze(c, dd, d_pcm, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p, d_abssum, st));
+        if (frame_analyze) CK(launch_analyze3(c, dd, d_pcm, lp, (CandRec*)e->cands.p, d_abssum, st));
+        else if (fast_analyze) CK(launch_analyze(c, dd, d_pcm, lp, (CandRec*)e->cands.p, d_abssum, st));
         else
-            CK(launch_residual(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const LpcRec*)e->lpcs.p, (CandRec*)e->cands.p,
-                               (int32_t*)e->scratch.p, st));
+            CK(launch_residual(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, lp, (CandRec*)e->cands.p, (int32_t*)e->scratch.p, st));
         time_mark(e, eb + 3);
+        if (overlap) {
+            CK(cudaEventRecord(e->lpc_ev[2 * nchunks + 1], st));   // this group's LpcRec buffer may be reused by group g + 2
+            const uint64_t nb = base + chunk;
+            if (nb < nframes) {
+                cudaStream_t sb = e->aux;
+                if (nchunks >= 1) CK(cudaStreamWaitEvent(sb, e->lpc_ev[2 * (nchunks - 1) + 1], 0));   // buffer (g + 1) & 1 was read by group g - 1
+                else CK(cudaStreamWaitEvent(sb, e->lpc_ev[1], 0));   // (orders stream B behind this call's uploads on the main stream)
+                if (pipe_in) CK(cudaStreamWaitEvent(sb, e->pipe_ev[2 * (nchunks + 1)], 0));
+                const EncCfg cn = group_cfg(nb);
+                CK(launch_lpc3(cn, (const FrameDesc*)e->descs.p + nb, d_pcm, (const double*)e->winpool.p, lpc_buf[(nchunks + 1) & 1],
+                               e->lpc_overlap * (uint32_t)e->sm_count, sb));
+                CK(cudaEventRecord(e->lpc_ev[2 * (nchunks + 1)], sb));
+            }
+        }
         launch_decide_scan(c, dd, (const CandRec*)e->cands.p, d_abssum, (FrameRec*)e->frecs.p, (uint32_t*)e->fbytes.p + base,
                            (unsigned long long*)e->totals.p, pipe_out ? e->d_h_totals + nchunks : nullptr, d_out, !frame_pack, st);
         time_mark(e, eb + 4);
@@ -865,6 +905,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
         if (g.n_pcm_frames) extent = std::max<uint64_t>(extent, g.pcm_offset + g.n_pcm_frames);
         else extent_known = false;
     }
+    e->last_ncand = 0;
     if (n_segments == 0 || frames_bytes == 0) return 0;
 
     // ---- buffers ----
@@ -1006,6 +1047,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     memcpy(&state, e->mbox_h + 64, sizeof(state));
     if (n_frames_out) *n_frames_out = state.frames_total;
     if (n_pcm_out) *n_pcm_out = state.samples_total;
+    e->last_ncand = ncand;
     cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
     e->tm.launches = launches;
     if (e->profiling) {
@@ -1025,6 +1067,8 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
         size_t bytes = pcm_out_bytes;
         if (extent_known && pcm_kind != FLACB200_PCM_I32_PLANAR)
             bytes = std::min<size_t>(bytes, (size_t)extent * cfg.channels * cfg.bytes_per_sample);
+        if (n_segments == 1 && pcm_kind != FLACB200_PCM_I32_PLANAR)   // one stream: nothing lies behind what the walk delivered
+            bytes = std::min<size_t>(bytes, (size_t)(segs[0].pcm_off + state.samples_total) * cfg.channels * cfg.bytes_per_sample);
         if (e->profiling) cudaEventRecord(e->ev[24], st);
         CK(cudaMemcpyAsync(pcm_out, d_out, bytes, cudaMemcpyDeviceToHost, st));
         if (e->profiling) cudaEventRecord(e->ev[25], st);
@@ -1035,6 +1079,30 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
         if (bad_frame) *bad_frame = state.err_frame;
         return state.err == 0x80000000u ? FLACB200_E_OUTPUT_TOO_SMALL : (int)state.err;
     }
+    return 0;
+}
+
+extern "C" int flacb200_decode_last_frames(flacb200_engine* e, flacb200_frame_entry* table, size_t capacity, uint64_t* n_entries)
+{
+    if (!e || !n_entries || (!table && capacity)) return FLACB200_E_BAD_ARGUMENT;
+    *n_entries = 0;
+    const uint32_t n = e->last_ncand;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    std::vector<FrameCand> cands(n);
+    std::vector<DecRec> recs(n);
+    std::vector<unsigned long long> pos(n);
+    CK(cudaMemcpyAsync(cands.data(), e->dec[6].p, (size_t)n * sizeof(FrameCand), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(recs.data(), e->dec[7].p, (size_t)n * sizeof(DecRec), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(pos.data(), e->dec[8].p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    uint64_t k = 0;
+    for (uint32_t c = 0; c < n; c++) {
+        if (pos[c] == ~0ull || recs[c].err) continue;   // a false candidate, or a frame the walk never reached
+        if (k < capacity) table[k] = flacb200_frame_entry{cands[c].off, pos[c], (uint32_t)(recs[c].end - cands[c].off), cands[c].block_size};
+        k++;
+    }
+    *n_entries = k;
     return 0;
 }
 

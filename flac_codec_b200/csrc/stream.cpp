@@ -655,21 +655,42 @@ void flacb200_md5(const uint8_t* data, size_t len, uint8_t out[16])
 }   // extern "C"
 
 // =================================================================================================
-// reader
+// reader: Decoder (src/decode.rs:1311-1491) behind the FlacByteReader / FlacSampleReader / FlacChannelReader facades
 // =================================================================================================
+// The reference's Decoder pulls one frame at a time out of `R: Read`.  Here the unit of GPU work is a WINDOW: a run of
+// bytes starting at a frame boundary (at most window_bytes of them, decoding to at most window_pcm samples) goes through
+// one flacb200_decode call; flacb200_decode_last_frames says where its frames lie, the reader hands them out one frame at
+// a time (fill_buf) and starts the next window where the last good frame ended.  A frame cut by the window's end -- or
+// one that does not fit the PCM budget -- fails in this window and is simply decoded again as the first frame of the next;
+// an error that is still there at the head of a window is genuine and is returned at that point: after every good frame
+// in front of it has been delivered, as with the serial reader.  Memory is bounded by the window, not by the stream.
+// The bytes come from a caller-owned file image, or are fed chunk by chunk (flacb200_reader_feed: an `R: Read`).
 struct flacb200_reader {
     flacb200_engine* engine = nullptr;
-    const uint8_t* flac = nullptr;
-    size_t len = 0;
+    const uint8_t* image = nullptr;   // image mode: the whole file, caller-owned
+    size_t image_len = 0;
+    bool fed_mode = false, fed_eof = false, meta_done = false;
+    std::vector<uint8_t> fed;         // feed mode: fed[0] is the byte at absolute offset fed_base
+    uint64_t fed_base = 0;
     flacb200_streaminfo si{};
     std::vector<flacb200_seekpoint> seektable;
-    HostBuf pcm;                 // decoded PCM of the whole stream: packed little-endian bytes, or i32 when the first read asked for that
-    int cached_kind = FLACB200_PCM_BYTES_LE;
-    bool decoded = false;
-    int decode_error = 0;        // error of the first bad frame ...
-    uint64_t valid_pcm = 0;      // ... which the reference reaches after this many inter-channel samples
-    uint64_t total_pcm = 0;
-    uint64_t pos = 0;            // read position in single-channel samples
+    size_t window_bytes = (size_t)32 << 20;
+    uint64_t window_pcm = (uint64_t)8 << 20;   // inter-channel samples per window
+    uint64_t next_byte = 0;           // absolute offset of the next frame to decode
+    uint64_t decoded_samples = 0;     // inter-channel samples in front of the current window's end
+    HostBuf win;                      // the window's PCM: int32 interleaved, or packed little-endian bytes --
+    int win_kind = FLACB200_PCM_I32_INTERLEAVED;   // whichever the access that triggered the decode asked for (a byte reader
+                                      // gets its bytes with one memcpy, a sample reader its i32 without a conversion pass)
+    std::vector<int32_t> conv;        // current frame as i32 when the window holds bytes
+    std::vector<flacb200_frame_entry> frames;
+    size_t cur = 0;                   // frame being handed out
+    uint32_t cur_off = 0;             // inter-channel samples of it already consumed
+    bool at_end = false;
+    int sticky_error = 0;
+    bool verifying = false;           // flacb200_reader_verify in progress (a fed reader returns FLACB200_NEED_DATA in between)
+    Md5 verify_md5;
+    std::vector<int32_t> planar;      // FlacChannelReader view of the current frame
+    std::vector<const int32_t*> planar_ptrs;
 };
 
 namespace {
@@ -683,6 +704,7 @@ int parse_metadata(const uint8_t* f, size_t len, flacb200_streaminfo* si, std::v
     size_t p = 4;
     bool first = true, seektable_seen = false;
     memset(si, 0, sizeof(*si));
+    if (table) table->clear();
     for (;;) {
         if (p + 4 > len) return first ? E_MISSING_STREAMINFO : E_IO;
         const bool last = (f[p] >> 7) != 0;
@@ -690,7 +712,8 @@ int parse_metadata(const uint8_t* f, size_t len, flacb200_streaminfo* si, std::v
         const size_t blen = (size_t)get_be(f + p + 1, 3);
         p += 4;
         if (first) {
-            if (type != 0 || blen != 34 || p + blen > len) return E_MISSING_STREAMINFO;
+            if (type != 0 || blen != 34) return E_MISSING_STREAMINFO;
+            if (p + blen > len) return E_IO;
             const uint8_t* b = f + p;
             si->min_block_size = (uint16_t)get_be(b, 2);
             si->max_block_size = (uint16_t)get_be(b + 2, 2);
@@ -735,40 +758,178 @@ int parse_metadata(const uint8_t* f, size_t len, flacb200_streaminfo* si, std::v
     return 0;
 }
 
-int reader_decode_all(flacb200_reader& r, int want_kind)
+// bytes available from absolute offset `off`
+inline const uint8_t* reader_bytes(const flacb200_reader& r, uint64_t off, size_t* avail)
 {
-    if (r.decoded) return 0;
+    if (!r.fed_mode) {
+        *avail = off < r.image_len ? r.image_len - (size_t)off : 0;
+        return r.image + off;
+    }
+    const uint64_t end = r.fed_base + r.fed.size();
+    *avail = off < end ? (size_t)(end - off) : 0;
+    return r.fed.data() + (off - r.fed_base);
+}
+
+// feed mode: the metadata blocks must have arrived before anything else can happen.  Returns FLACB200_NEED_DATA while they
+// have not.
+int reader_ensure_meta(flacb200_reader& r)
+{
+    if (r.meta_done) return 0;
+    const int rc = parse_metadata(r.fed.data(), r.fed.size(), &r.si, &r.seektable);
+    if ((rc == E_IO || (rc == E_MISSING_STREAMINFO && r.fed.size() < 42)) && !r.fed_eof) return FLACB200_NEED_DATA;
+    if (rc) return rc;
+    r.meta_done = true;
+    r.next_byte = r.si.frames_start;
+    return 0;
+}
+
+// Decodes the next window.  0: frames[] refilled (or at_end set); FLACB200_NEED_DATA: feed mode, nothing decodable is
+// buffered yet; else the error the serial reader would return at this point.
+int reader_next_window(flacb200_reader& r, int want_kind)
+{
+    r.frames.clear();
+    r.cur = 0;
+    r.cur_off = 0;
+    if (r.sticky_error) return r.sticky_error;
+    if (r.at_end) return 0;
     if (!r.engine) return FLACB200_E_NO_DEVICE;
     const flacb200_streaminfo& si = r.si;
-    r.cached_kind = want_kind == FLACB200_PCM_I32_INTERLEAVED ? FLACB200_PCM_I32_INTERLEAVED : FLACB200_PCM_BYTES_LE;
-    const size_t B = r.cached_kind == FLACB200_PCM_I32_INTERLEAVED ? 4 : (si.bits_per_sample + 7) / 8, fb = B * si.channels;
-    const size_t nbytes = r.len - (size_t)si.frames_start;
+    const uint64_t total = si.total_samples;
+    if (total && r.decoded_samples >= total) {   // Some(0) => Ok(None)  (src/decode.rs:1402)
+        r.at_end = true;
+        return 0;
+    }
     flacb200_stream_params prm{};
     prm.sample_rate = si.sample_rate;
     prm.bits_per_sample = si.bits_per_sample;
     prm.channels = si.channels;
     prm.max_block_size = si.max_block_size;
-    uint64_t cap_pcm = si.total_samples ? si.total_samples : std::max<uint64_t>((uint64_t)nbytes * 8 / fb + si.max_block_size, 65536);
-    for (int attempt = 0; attempt < 12; attempt++) {
-        if (!r.pcm.reserve((size_t)cap_pcm * fb + 64, true)) return FLACB200_E_OUT_OF_MEMORY;
-        flacb200_decode_segment seg{0, nbytes, 0, si.total_samples};
+    size_t want = r.window_bytes;
+    uint64_t cap_pcm = std::max<uint64_t>(r.window_pcm, (uint64_t)si.max_block_size);
+    for (int attempt = 0; attempt < 24; attempt++) {
+        size_t avail = 0;
+        const uint8_t* src = reader_bytes(r, r.next_byte, &avail);
+        const bool source_done = !r.fed_mode || r.fed_eof;
+        if (avail == 0) {
+            if (!source_done) return FLACB200_NEED_DATA;
+            if (total) return r.sticky_error = E_IO;   // FrameHeader::read hits EOF with samples outstanding
+            r.at_end = true;                           // unsized stream: EOF at a frame boundary ends it (:1416)
+            return 0;
+        }
+        const size_t take = std::min(avail, want);
+        const bool last_window = take == avail && source_done;
+        const uint64_t remaining = total ? total - r.decoded_samples : 0;
+        // the PCM budget of the window; with a known total the final window must be able to hold everything that remains
+        uint64_t cap = cap_pcm;
+        if (total) cap = std::min<uint64_t>(cap, remaining + si.max_block_size);
+        r.win_kind = want_kind == FLACB200_PCM_I32_INTERLEAVED ? FLACB200_PCM_I32_INTERLEAVED : FLACB200_PCM_BYTES_LE;
+        const size_t fb = (size_t)si.channels * (r.win_kind == FLACB200_PCM_I32_INTERLEAVED ? 4 : (si.bits_per_sample + 7) / 8);
+        if (!r.win.reserve((size_t)cap * fb + 64, true)) return FLACB200_E_OUT_OF_MEMORY;
+        flacb200_decode_segment seg{0, take, 0, remaining};
         uint64_t nf = 0, ns = 0, bad = 0;
-        const int rc = flacb200_decode(r.engine, &prm, r.flac + si.frames_start, nbytes, FLACB200_HOST, &seg, 1, r.pcm.p, (size_t)cap_pcm * fb,
-                                       r.cached_kind, FLACB200_HOST, 0, &nf, &ns, &bad);
-        if (rc == FLACB200_E_OUTPUT_TOO_SMALL && !si.total_samples) {   // unsized stream: grow and retry
-            cap_pcm *= 4;
+        const int rc = flacb200_decode(r.engine, &prm, src, take, FLACB200_HOST, &seg, 1, r.win.p, (size_t)cap * fb, r.win_kind, FLACB200_HOST, 0,
+                                       &nf, &ns, &bad);
+        if (rc < 0 && rc != FLACB200_E_OUTPUT_TOO_SMALL) return rc;   // CUDA / argument errors are not stream errors
+        uint64_t ntab = 0;
+        r.frames.resize((size_t)nf);
+        if (nf) {
+            const int rt = flacb200_decode_last_frames(r.engine, r.frames.data(), r.frames.size(), &ntab);
+            if (rt) return rt;
+            if (ntab != nf) return FLACB200_E_BAD_ARGUMENT;   // (cannot happen: both count the frames of the walk)
+        }
+        if (nf) {   // deliver these; whatever stopped the walk shows up again at the head of the next window
+            const flacb200_frame_entry& l = r.frames.back();
+            r.next_byte += l.byte_offset + l.byte_length;
+            r.decoded_samples += ns;
+            return 0;
+        }
+        // nothing decoded
+        if (rc == 0) {   // unsized stream whose last bytes are no frame (fewer than 16: EOF inside a header, :1416), or an empty window
+            if (last_window) {
+                r.at_end = true;
+                return 0;
+            }
+            if (r.fed_mode && take == avail) return FLACB200_NEED_DATA;
+            want *= 2;
             continue;
         }
-        if (rc < 0) return rc;
-        r.decoded = true;
-        r.decode_error = rc;
-        // frames in front of the first bad one are delivered before the error surfaces, as with the serial reader
-        r.valid_pcm = rc ? std::min<uint64_t>(ns, (si.min_block_size == si.max_block_size ? bad * si.max_block_size : 0)) : ns;
-        r.total_pcm = r.valid_pcm;
-        r.pcm.len = (size_t)r.valid_pcm * fb;
-        return 0;
+        const bool cut = rc == E_IO || rc == FLACB200_E_OUTPUT_TOO_SMALL;   // the first frame did not fit the window
+        if (cut && !last_window && rc == E_IO) {
+            if (r.fed_mode && take == avail) return FLACB200_NEED_DATA;
+            want *= 2;
+            continue;
+        }
+        if (rc == FLACB200_E_OUTPUT_TOO_SMALL) {
+            cap_pcm *= 2;
+            continue;
+        }
+        return r.sticky_error = rc;   // genuine: the frame at next_byte fails
     }
     return FLACB200_E_OUTPUT_TOO_SMALL;
+}
+
+// makes frames[cur] a frame with unconsumed samples; 0 with at_end set when the stream is over
+int reader_current_frame(flacb200_reader& r, int want_kind)
+{
+    for (;;) {
+        if (r.cur < r.frames.size()) {
+            if (r.cur_off < r.frames[r.cur].block_size) return 0;
+            r.cur++;
+            r.cur_off = 0;
+            continue;
+        }
+        if (r.at_end) return 0;
+        const int rc = reader_next_window(r, want_kind);
+        if (rc) return rc;
+        if (r.frames.empty() && r.at_end) return 0;
+    }
+}
+
+// the unconsumed part of the current frame as int32 (converted into r.conv when the window holds packed bytes)
+inline const int32_t* reader_frame_samples(flacb200_reader& r)
+{
+    const flacb200_frame_entry& f = r.frames[r.cur];
+    const size_t ch = r.si.channels, first = (size_t)(f.pcm_offset + r.cur_off) * ch;
+    if (r.win_kind == FLACB200_PCM_I32_INTERLEAVED) return reinterpret_cast<const int32_t*>(r.win.p) + first;
+    const size_t B = (r.si.bits_per_sample + 7) / 8, n = (size_t)(f.block_size - r.cur_off) * ch;
+    const uint32_t sh = 32 - 8 * (uint32_t)B;
+    r.conv.resize(n);
+    const uint8_t* src = r.win.p + first * B;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t v = 0;
+        for (size_t k = 0; k < B; k++) v |= (uint32_t)src[i * B + k] << (8 * k);
+        r.conv[i] = (int32_t)(v << sh) >> sh;
+    }
+    return r.conv.data();
+}
+
+// the same span as packed little-endian bytes, when the window holds them
+inline const uint8_t* reader_frame_bytes(const flacb200_reader& r)
+{
+    const flacb200_frame_entry& f = r.frames[r.cur];
+    return r.win.p + (size_t)(f.pcm_offset + r.cur_off) * r.si.channels * ((r.si.bits_per_sample + 7) / 8);
+}
+
+// Decoder::seek (src/decode.rs:1452-1491): the last defined seek point at or before `sample`, else the first frame
+uint64_t reader_seek_point(flacb200_reader& r, uint64_t sample)
+{
+    uint64_t at_sample = 0, at_byte = 0;
+    for (size_t i = r.seektable.size(); i-- > 0;) {
+        const flacb200_seekpoint& p = r.seektable[i];
+        if (!p.placeholder && p.sample_offset <= sample) {
+            at_sample = p.sample_offset;
+            at_byte = p.byte_offset;
+            break;
+        }
+    }
+    r.next_byte = r.si.frames_start + at_byte;
+    r.decoded_samples = at_sample;
+    r.frames.clear();
+    r.cur = 0;
+    r.cur_off = 0;
+    r.at_end = false;
+    r.sticky_error = 0;
+    return at_sample;
 }
 
 }   // namespace
@@ -786,22 +947,61 @@ int flacb200_reader_open(flacb200_engine* engine, const uint8_t* flac, size_t le
     if (!flac || !out) return FLACB200_E_BAD_ARGUMENT;
     flacb200_reader* r = new flacb200_reader();
     r->engine = engine;
-    r->flac = flac;
-    r->len = len;
+    r->image = flac;
+    r->image_len = len;
     const int rc = parse_metadata(flac, len, &r->si, &r->seektable);
     if (rc) {
         delete r;
         return rc;
     }
+    r->meta_done = true;
+    r->next_byte = r->si.frames_start;
     *out = r;
+    return 0;
+}
+
+int flacb200_reader_open_stream(flacb200_engine* engine, flacb200_reader** out)
+{
+    if (!out) return FLACB200_E_BAD_ARGUMENT;
+    flacb200_reader* r = new flacb200_reader();
+    r->engine = engine;
+    r->fed_mode = true;
+    *out = r;
+    return 0;
+}
+
+int flacb200_reader_feed(flacb200_reader* r, const uint8_t* bytes, size_t len, int eof)
+{
+    if (!r || !r->fed_mode || (!bytes && len)) return FLACB200_E_BAD_ARGUMENT;
+    if (r->fed_eof && len) return FLACB200_E_BAD_ARGUMENT;
+    // bytes in front of the next frame have been decoded: drop them (a window's PCM lives in its own buffer)
+    if (r->meta_done && r->next_byte > r->fed_base) {
+        const size_t drop = (size_t)std::min<uint64_t>(r->next_byte - r->fed_base, r->fed.size());
+        r->fed.erase(r->fed.begin(), r->fed.begin() + (long)drop);
+        r->fed_base += drop;
+    }
+    r->fed.insert(r->fed.end(), bytes, bytes + len);
+    if (eof) r->fed_eof = true;
     return 0;
 }
 
 void flacb200_reader_close(flacb200_reader* r) { delete r; }
 
+int flacb200_reader_set_window(flacb200_reader* r, size_t window_bytes, uint64_t window_pcm_frames)
+{
+    if (!r) return FLACB200_E_BAD_ARGUMENT;
+    if (window_bytes) r->window_bytes = std::max<size_t>(window_bytes, 64);
+    if (window_pcm_frames) r->window_pcm = window_pcm_frames;
+    return 0;
+}
+
 int flacb200_reader_info(flacb200_reader* r, flacb200_streaminfo* si)
 {
     if (!r || !si) return FLACB200_E_BAD_ARGUMENT;
+    if (r->fed_mode) {
+        const int rc = reader_ensure_meta(*r);
+        if (rc) return rc;
+    }
     *si = r->si;
     return 0;
 }
@@ -809,10 +1009,77 @@ int flacb200_reader_info(flacb200_reader* r, flacb200_streaminfo* si)
 int flacb200_reader_seektable(flacb200_reader* r, flacb200_seekpoint* points, size_t capacity, size_t* n_points)
 {
     if (!r) return FLACB200_E_BAD_ARGUMENT;
+    if (r->fed_mode) {
+        const int rc = reader_ensure_meta(*r);
+        if (rc) return rc;
+    }
     if (n_points) *n_points = r->seektable.size();
     if (points)
         for (size_t i = 0; i < r->seektable.size() && i < capacity; i++) points[i] = r->seektable[i];
     return 0;
+}
+
+// FlacSampleReader::fill_buf (src/decode.rs:466-486): the unconsumed samples of the current frame, interleaved
+int flacb200_reader_fill_buf(flacb200_reader* r, const int32_t** samples, size_t* n_samples)
+{
+    if (!r || !samples || !n_samples) return FLACB200_E_BAD_ARGUMENT;
+    *samples = nullptr;
+    *n_samples = 0;
+    if (r->fed_mode) {
+        const int rm = reader_ensure_meta(*r);
+        if (rm) return rm;
+    }
+    const int rc = reader_current_frame(*r, FLACB200_PCM_I32_INTERLEAVED);
+    if (rc) return rc;
+    if (r->cur >= r->frames.size()) return 0;   // end of stream: an empty buffer
+    *samples = reader_frame_samples(*r);
+    *n_samples = (size_t)(r->frames[r->cur].block_size - r->cur_off) * r->si.channels;
+    return 0;
+}
+
+// FlacSampleReader::consume (:487): n_samples counts all channels and must be a multiple of the channel count
+int flacb200_reader_consume(flacb200_reader* r, size_t n_samples)
+{
+    if (!r) return FLACB200_E_BAD_ARGUMENT;
+    if (r->cur >= r->frames.size()) return n_samples ? FLACB200_E_BAD_ARGUMENT : 0;
+    const size_t ch = r->si.channels;
+    const size_t left = (size_t)(r->frames[r->cur].block_size - r->cur_off) * ch;
+    if (n_samples > left || n_samples % ch) return FLACB200_E_BAD_ARGUMENT;
+    r->cur_off += (uint32_t)(n_samples / ch);
+    return 0;
+}
+
+// FlacChannelReader::fill_buf (:917-944): one slice per channel over the unconsumed part of the current frame
+int flacb200_reader_fill_channels(flacb200_reader* r, const int32_t* const** channels, size_t* n_per_channel)
+{
+    if (!r || !channels || !n_per_channel) return FLACB200_E_BAD_ARGUMENT;
+    *n_per_channel = 0;
+    if (r->fed_mode) {
+        const int rm = reader_ensure_meta(*r);
+        if (rm) return rm;
+    }
+    const int rc = reader_current_frame(*r, FLACB200_PCM_I32_INTERLEAVED);
+    if (rc) return rc;
+    const size_t ch = r->si.channels;
+    r->planar_ptrs.assign(ch, nullptr);
+    *channels = r->planar_ptrs.data();
+    if (r->cur >= r->frames.size()) return 0;   // vec![&[]; channels]
+    const size_t n = r->frames[r->cur].block_size - r->cur_off;
+    r->planar.resize(n * ch);
+    const int32_t* s = reader_frame_samples(*r);
+    for (size_t c = 0; c < ch; c++) {
+        int32_t* d = r->planar.data() + c * n;
+        for (size_t i = 0; i < n; i++) d[i] = s[i * ch + c];
+        r->planar_ptrs[c] = d;
+    }
+    *n_per_channel = n;
+    return 0;
+}
+
+int flacb200_reader_consume_channels(flacb200_reader* r, size_t n_per_channel)
+{
+    if (!r) return FLACB200_E_BAD_ARGUMENT;
+    return flacb200_reader_consume(r, n_per_channel * r->si.channels);
 }
 
 int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm_kind, size_t* n_out)
@@ -821,84 +1088,408 @@ int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm
     if (pcm_kind != FLACB200_PCM_BYTES_LE && pcm_kind != FLACB200_PCM_BYTES_BE && pcm_kind != FLACB200_PCM_I32_INTERLEAVED)
         return FLACB200_E_BAD_ARGUMENT;
     *n_out = 0;
-    int rc = reader_decode_all(*r, pcm_kind);
-    if (rc) return rc;
-    const size_t B = (r->si.bits_per_sample + 7) / 8;          // bytes per sample of the byte layouts
-    const bool cache_i32 = r->cached_kind == FLACB200_PCM_I32_INTERLEAVED;
-    const size_t CB = cache_i32 ? 4 : B;                        // bytes per sample in the cache
-    const uint64_t end = r->valid_pcm * r->si.channels;   // in single-channel samples
-    if (r->pos >= end) return r->decode_error;             // the bad frame is reached only now (0 = clean end of stream)
-    const uint8_t* src = r->pcm.p + (size_t)r->pos * CB;
-    size_t n;
-    if (pcm_kind == FLACB200_PCM_I32_INTERLEAVED) {
-        n = (size_t)std::min<uint64_t>(capacity, end - r->pos);
-        int32_t* o = (int32_t*)out;
-        if (cache_i32) memcpy(o, src, n * 4);
-        else {
-            const uint32_t sh = 32 - 8 * (uint32_t)B;
-            for (size_t i = 0; i < n; i++) {
-                uint32_t v = 0;
-                for (size_t k = 0; k < B; k++) v |= (uint32_t)src[i * B + k] << (8 * k);
-                o[i] = (int32_t)(v << sh) >> sh;
+    if (r->fed_mode) {
+        const int rm = reader_ensure_meta(*r);
+        if (rm) return rm;
+    }
+    const size_t B = (r->si.bits_per_sample + 7) / 8, ch = r->si.channels;
+    const bool as_i32 = pcm_kind == FLACB200_PCM_I32_INTERLEAVED, be = pcm_kind == FLACB200_PCM_BYTES_BE;
+    size_t room = as_i32 ? capacity : capacity / B;   // single-channel samples that still fit
+    room -= room % ch;   // whole PCM frames only: the position stays on a frame of all channels
+    size_t done = 0;
+    while (room) {
+        const int rc = reader_current_frame(*r, pcm_kind);
+        if (rc) {
+            if (done) break;   // deliver what precedes the error; it surfaces at the next call
+            return rc;
+        }
+        if (r->cur >= r->frames.size()) break;   // end of stream
+        const size_t n = std::min<size_t>(room, (size_t)(r->frames[r->cur].block_size - r->cur_off) * ch);
+        if (!as_i32 && r->win_kind == FLACB200_PCM_BYTES_LE) {   // Frame::to_buf (src/audio.rs:110-134) was done on the device
+            const uint8_t* src = reader_frame_bytes(*r);
+            uint8_t* o = (uint8_t*)out + done * B;
+            if (!be || B == 1) memcpy(o, src, n * B);
+            else
+                for (size_t i = 0; i < n; i++)
+                    for (size_t k = 0; k < B; k++) o[i * B + k] = src[i * B + B - 1 - k];
+        } else {
+            const int32_t* s = reader_frame_samples(*r);
+            if (as_i32) memcpy((int32_t*)out + done, s, n * 4);
+            else {
+                uint8_t* o = (uint8_t*)out + done * B;
+                for (size_t i = 0; i < n; i++) {
+                    const uint32_t v = (uint32_t)s[i];
+                    for (size_t k = 0; k < B; k++) o[i * B + k] = (uint8_t)(v >> (8 * (be ? B - 1 - k : k)));
+                }
             }
         }
-        *n_out = n;
-    } else {
-        n = (size_t)std::min<uint64_t>(capacity / B, end - r->pos);
-        uint8_t* o = (uint8_t*)out;
-        const bool be = pcm_kind == FLACB200_PCM_BYTES_BE;
-        if (!cache_i32 && (!be || B == 1)) memcpy(o, src, n * B);
-        else
-            for (size_t i = 0; i < n; i++)      // Frame::to_buf (src/audio.rs:110-134)
-                for (size_t k = 0; k < B; k++) o[i * B + k] = src[i * CB + (be ? B - 1 - k : k)];
-        *n_out = n * B;
+        r->cur_off += (uint32_t)(n / ch);
+        done += n;
+        room -= n;
     }
-    r->pos += n;
+    *n_out = as_i32 ? done : done * B;
     return 0;
 }
 
+// FlacSampleReader::seek / FlacChannelReader::seek (:823-860, :1021-1057): Decoder::seek to the last seek point at or before
+// the sample (the stream start without a table), then frames are decoded and skipped up to the sample itself; running out of
+// stream first is InvalidSeek.  (FlacByteReader's io::Seek (:715-820) is the same walk in bytes.)
 int flacb200_reader_seek(flacb200_reader* r, uint64_t pcm_frame)
 {
     if (!r) return FLACB200_E_BAD_ARGUMENT;
-    // Decoder::seek (src/decode.rs:1452-1491): a sample beyond the stream is InvalidSeek
-    const uint64_t total = r->si.total_samples;
-    if (total) {
-        if (pcm_frame > total) return E_INVALID_SEEK;
-    } else {
-        const int rc = reader_decode_all(*r, r->cached_kind);
+    if (r->fed_mode) return E_IO;   // a plain `R: Read` source is not seekable (frames_start: None -> ErrorKind::NotSeekable)
+    uint64_t pos = reader_seek_point(*r, pcm_frame);
+    while (pcm_frame > pos) {
+        const int rc = reader_current_frame(*r, r->win_kind);
         if (rc) return rc;
-        if (pcm_frame > r->total_pcm) return E_INVALID_SEEK;
+        if (r->cur >= r->frames.size()) return E_INVALID_SEEK;
+        const uint64_t take = std::min<uint64_t>(r->frames[r->cur].block_size - r->cur_off, pcm_frame - pos);
+        r->cur_off += (uint32_t)take;
+        pos += take;
     }
-    r->pos = pcm_frame * r->si.channels;
     return 0;
 }
 
+// verify_reader (src/decode.rs:1291-1309): decode everything from the current position, MD5 of the little-endian PCM
 int flacb200_reader_verify(flacb200_reader* r, int* result, uint8_t md5_out[16])
 {
     if (!r || !result) return FLACB200_E_BAD_ARGUMENT;
-    int rc = reader_decode_all(*r, r->cached_kind);
-    if (rc) return rc;
-    if (r->decode_error) return r->decode_error;
-    uint8_t sum[16];
-    if (r->cached_kind == FLACB200_PCM_I32_INTERLEAVED) {   // MD5 runs over the packed little-endian form (src/decode.rs:1297)
-        const size_t B = (r->si.bits_per_sample + 7) / 8, total = (size_t)r->valid_pcm * r->si.channels;
-        Md5 m;
-        uint8_t buf[4096 * 4];
-        for (size_t done = 0; done < total;) {
-            const size_t take = std::min<size_t>(4096, total - done);
-            for (size_t i = 0; i < take; i++)
-                for (size_t k = 0; k < B; k++) buf[i * B + k] = r->pcm.p[(done + i) * 4 + k];
-            m.update(buf, take * B);
-            done += take;
-        }
-        m.final(sum);
-    } else {
-        flacb200_md5(r->pcm.p, r->pcm.len, sum);
+    if (r->fed_mode) {
+        const int rm = reader_ensure_meta(*r);
+        if (rm) return rm;
     }
+    if (!r->verifying) {
+        if (!r->fed_mode) reader_seek_point(*r, 0);   // the whole stream, wherever the reads have got to
+        else if (r->decoded_samples || r->next_byte != r->si.frames_start) return FLACB200_E_BAD_ARGUMENT;   // a fed stream cannot rewind
+        r->verify_md5 = Md5();
+        r->verifying = true;
+    }
+    const size_t B = (r->si.bits_per_sample + 7) / 8, ch = r->si.channels;
+    Md5& m = r->verify_md5;
+    std::vector<uint8_t> buf;
+    for (;;) {
+        const int rc = reader_current_frame(*r, FLACB200_PCM_BYTES_LE);
+        if (rc) {
+            if (rc != FLACB200_NEED_DATA) r->verifying = false;
+            return rc;
+        }
+        if (r->cur >= r->frames.size()) break;
+        const size_t n = (size_t)(r->frames[r->cur].block_size - r->cur_off) * ch;
+        if (r->win_kind == FLACB200_PCM_BYTES_LE) {
+            // frames of a window are contiguous: hash to the end of the window in one go
+            const flacb200_frame_entry& l = r->frames.back();
+            const uint8_t* a = reader_frame_bytes(*r);
+            const uint8_t* z = r->win.p + (size_t)(l.pcm_offset + l.block_size) * ch * B;
+            m.update(a, (size_t)(z - a));
+            r->cur = r->frames.size() - 1;
+        } else {
+            const int32_t* s = reader_frame_samples(*r);
+            buf.resize(n * B);
+            for (size_t i = 0; i < n; i++)
+                for (size_t k = 0; k < B; k++) buf[i * B + k] = (uint8_t)((uint32_t)s[i] >> (8 * k));
+            m.update(buf.data(), buf.size());
+        }
+        r->cur_off = r->frames[r->cur].block_size;
+    }
+    uint8_t sum[16];
+    m.final(sum);
+    r->verifying = false;
     if (md5_out) memcpy(md5_out, sum, 16);
     static const uint8_t zero[16] = {0};
     if (memcmp(r->si.md5, zero, 16) == 0) *result = 2;        // Verified::NoMD5
     else *result = memcmp(r->si.md5, sum, 16) == 0 ? 0 : 1;   // MD5Match / MD5Mismatch
+    return 0;
+}
+
+}   // extern "C"
+
+// =================================================================================================
+// FlacStreamReader (src/decode.rs:1149-1240): subset frames without metadata, parameters read from every frame header
+// =================================================================================================
+// The reference scans for a sync code, parses ONE frame and returns it with the parameters of its header, which may change
+// from frame to frame.  Here the host does the scan and parses the first header (a few bytes of bit twiddling), then the GPU
+// decodes the RUN of frames that follows with the same channel count and sample width in one flacb200_decode call
+// (params.subset = 1); the frames of the run are handed out one by one.  A frame with other parameters, or bytes that are no
+// frame, end the run -- the next read starts a new scan there, as the serial reader's next read would.
+struct flacb200_stream_reader {
+    flacb200_engine* engine = nullptr;
+    std::vector<uint8_t> fed;
+    bool eof = false;
+    size_t pos = 0;                      // scan position in fed
+    HostBuf win;                         // decoded run: int32 interleaved
+    std::vector<flacb200_frame_entry> frames;
+    std::vector<uint32_t> rates;         // sample rate of every frame of the run (the one parameter a run may mix)
+    size_t cur = 0;
+    size_t run_base = 0;                 // offset in fed of the run's first byte
+    uint32_t channels = 0, bps = 0;
+    size_t window_bytes = (size_t)16 << 20;
+};
+
+namespace {
+
+struct SubsetHeader {
+    uint32_t block_size, sample_rate, channels, bps, hdr_len;
+};
+
+// FrameHeader::read_subset (src/stream.rs:166-181, :214-240) over p[0..avail).  Returns 0, E_IO (ran out of bytes) or the
+// parse error; *consumed = bytes the reference's reader has taken from the stream at that point (its BitReader pulls whole
+// bytes as it goes: a failed parse leaves the stream behind the last byte it touched).
+int parse_subset_header(const uint8_t* p, size_t avail, SubsetHeader* h, size_t* consumed)
+{
+    auto need = [&](size_t n) { return avail >= n; };
+    *consumed = std::min<size_t>(avail, 2);
+    if (!need(2)) return E_IO;
+    if (p[0] != 0xFF || (p[1] & 0xFE) != 0xF8) return 23;   // InvalidSyncCode
+    *consumed = std::min<size_t>(avail, 3);
+    if (!need(3)) return E_IO;
+    const uint32_t bsc = p[2] >> 4, src = p[2] & 15;
+    if (bsc == 0) return 24;                                 // InvalidBlockSize
+    uint32_t rate = 0, rate_kind = 0;
+    static const uint32_t rates[12] = {0, 88200, 176400, 192000, 8000, 16000, 22050, 24000, 32000, 44100, 48000, 96000};
+    if (src == 0) return 27;                                 // NonSubsetSampleRate
+    if (src <= 11) rate = rates[src];
+    else if (src <= 14) rate_kind = src - 11;
+    else return 26;                                          // InvalidSampleRate
+    *consumed = std::min<size_t>(avail, 4);
+    if (!need(4)) return E_IO;
+    const uint32_t ca = p[3] >> 4, bpc = (p[3] >> 1) & 7;
+    if (ca > 10) return 31;                                  // InvalidChannels
+    uint32_t bps;
+    switch (bpc) {
+    case 0: return 28;                                       // NonSubsetBitsPerSample
+    case 1: bps = 8; break;
+    case 2: bps = 12; break;
+    case 3: return 33;                                       // InvalidBitsPerSample
+    case 4: bps = 16; break;
+    case 5: bps = 20; break;
+    case 6: bps = 24; break;
+    default: bps = 32; break;
+    }
+    size_t n = 4;
+    *consumed = std::min<size_t>(avail, 5);
+    if (!need(5)) return E_IO;
+    const uint32_t f0 = p[4];
+    uint32_t ones = 0;
+    while (ones < 8 && (f0 & (0x80u >> ones))) ones++;
+    if (ones == 0) n += 1;
+    else {
+        if (ones == 1 || ones > 7) return 36;                // InvalidFrameNumber
+        for (uint32_t i = 1; i < ones; i++) {
+            *consumed = std::min<size_t>(avail, 4 + i + 1);
+            if (!need(4 + i + 1)) return E_IO;
+            if ((p[4 + i] & 0xC0) != 0x80) return 36;
+        }
+        n += ones;
+    }
+    uint32_t bs;
+    if (bsc == 6) {
+        *consumed = std::min<size_t>(avail, n + 1);
+        if (!need(n + 1)) return E_IO;
+        bs = (uint32_t)p[n] + 1;
+        n += 1;
+    } else if (bsc == 7) {
+        *consumed = std::min<size_t>(avail, n + 2);
+        if (!need(n + 2)) return E_IO;
+        const uint32_t v = ((uint32_t)p[n] << 8) | p[n + 1];
+        if (v == 0xFFFF) return 24;
+        bs = v + 1;
+        n += 2;
+    } else {
+        bs = bsc == 1 ? 192u : bsc <= 5 ? (576u << (bsc - 2)) : (256u << (bsc - 8));
+    }
+    if (rate_kind == 1) {
+        *consumed = std::min<size_t>(avail, n + 1);
+        if (!need(n + 1)) return E_IO;
+        rate = (uint32_t)p[n] * 1000;
+        n += 1;
+    } else if (rate_kind) {
+        *consumed = std::min<size_t>(avail, n + 2);
+        if (!need(n + 2)) return E_IO;
+        rate = ((uint32_t)p[n] << 8) | p[n + 1];
+        if (rate_kind == 3) rate *= 10;
+        n += 2;
+    }
+    *consumed = std::min<size_t>(avail, n + 1);
+    if (!need(n + 1)) return E_IO;
+    n += 1;
+    uint8_t crc = 0;
+    for (size_t i = 0; i < n; i++) {   // Crc8 (src/crc.rs:104), poly 0x07
+        crc ^= p[i];
+        for (int b = 0; b < 8; b++) crc = (uint8_t)((crc & 0x80) ? ((crc << 1) ^ 0x07) : (crc << 1));
+    }
+    if (crc != 0) return 39;                                 // Crc8Mismatch
+    h->block_size = bs;
+    h->sample_rate = rate;
+    h->channels = ca <= 7 ? ca + 1 : 2;
+    h->bps = bps;
+    h->hdr_len = (uint32_t)n;
+    return 0;
+}
+
+// Finds the next frame the reference's scan loop (src/decode.rs:1186-1222) would accept, starting at r.pos, and decodes the
+// run of frames behind it.  0: frames[] refilled; FLACB200_NEED_DATA; E_IO at the end of the stream; or the frame's error.
+int stream_reader_next_run(flacb200_stream_reader& r)
+{
+    r.frames.clear();
+    r.rates.clear();
+    r.cur = 0;
+    if (!r.engine) return FLACB200_E_NO_DEVICE;
+    const uint8_t* f = r.fed.data();
+    const size_t len = r.fed.size();
+    SubsetHeader h{};
+    for (;;) {
+        // skip_until(0xFF): consumes through the first 0xFF
+        const uint8_t* q = r.pos < len ? (const uint8_t*)memchr(f + r.pos, 0xFF, len - r.pos) : nullptr;
+        if (!q) {
+            r.pos = len;
+            return r.eof ? E_IO : FLACB200_NEED_DATA;   // "eof looking for frame sync" (:1198)
+        }
+        const size_t at = (size_t)(q - f);
+        if (at + 1 >= len) {   // the byte behind the 0xFF is not here yet
+            r.pos = at;
+            return r.eof ? E_IO : FLACB200_NEED_DATA;
+        }
+        if ((f[at + 1] >> 1) != 0x7C) {   // Ok(_) => continue: nothing but the 0xFF was consumed
+            r.pos = at + 1;
+            continue;
+        }
+        size_t consumed = 0;
+        const int rc = parse_subset_header(f + at, len - at, &h, &consumed);
+        if (rc == E_IO && !r.eof) {   // the header is not complete yet
+            r.pos = at;
+            return FLACB200_NEED_DATA;
+        }
+        if (rc != 0) {   // `if let Ok(header)` fails: scan on behind what the parser took
+            r.pos = at + std::max<size_t>(consumed, 1);
+            continue;
+        }
+        r.pos = at;
+        break;
+    }
+    // ---- decode the run ----
+    flacb200_stream_params prm{};
+    prm.sample_rate = h.sample_rate;
+    prm.bits_per_sample = h.bps;
+    prm.channels = h.channels;
+    prm.subset = 1;
+    r.channels = h.channels;
+    r.bps = h.bps;
+    size_t want = r.window_bytes;
+    uint64_t cap_pcm = (uint64_t)4 << 20;
+    for (int attempt = 0; attempt < 24; attempt++) {
+        const size_t avail = len - r.pos, take = std::min(avail, want);
+        const bool last_window = take == avail && r.eof;
+        cap_pcm = std::max<uint64_t>(cap_pcm, h.block_size);
+        if (!r.win.reserve((size_t)cap_pcm * h.channels * 4 + 64, true)) return FLACB200_E_OUT_OF_MEMORY;
+        flacb200_decode_segment seg{0, take, 0, 0};
+        uint64_t nf = 0, ns = 0, bad = 0;
+        const int rc = flacb200_decode(r.engine, &prm, f + r.pos, take, FLACB200_HOST, &seg, 1, r.win.p, (size_t)cap_pcm * h.channels * 4,
+                                       FLACB200_PCM_I32_INTERLEAVED, FLACB200_HOST, 0, &nf, &ns, &bad);
+        if (rc < 0 && rc != FLACB200_E_OUTPUT_TOO_SMALL) return rc;
+        if (nf) {
+            uint64_t ntab = 0;
+            r.frames.resize((size_t)nf);
+            const int rt = flacb200_decode_last_frames(r.engine, r.frames.data(), r.frames.size(), &ntab);
+            if (rt) return rt;
+            if (ntab != nf) return FLACB200_E_BAD_ARGUMENT;
+            r.run_base = r.pos;
+            for (const flacb200_frame_entry& e : r.frames) {   // the rate is each frame's own
+                SubsetHeader fh{};
+                size_t c = 0;
+                parse_subset_header(f + r.pos + e.byte_offset, len - r.pos - (size_t)e.byte_offset, &fh, &c);
+                r.rates.push_back(fh.sample_rate);
+            }
+            const flacb200_frame_entry& l = r.frames.back();
+            r.pos += (size_t)(l.byte_offset + l.byte_length);
+            return 0;
+        }
+        if (rc == FLACB200_E_OUTPUT_TOO_SMALL) {
+            cap_pcm *= 2;
+            continue;
+        }
+        if ((rc == E_IO || rc == 0) && !last_window) {   // the first frame is cut by the window / by what has been fed
+            if (take == avail) return FLACB200_NEED_DATA;
+            want *= 2;
+            continue;
+        }
+        // the frame at the head fails: the serial reader returns that error and has consumed the frame's bytes; the next
+        // read scans on behind its sync code
+        r.pos += 2;
+        return rc ? rc : E_IO;
+    }
+    return FLACB200_E_OUTPUT_TOO_SMALL;
+}
+
+}   // namespace
+
+extern "C" {
+
+int flacb200_stream_reader_open(flacb200_engine* engine, flacb200_stream_reader** out)
+{
+    if (!out) return FLACB200_E_BAD_ARGUMENT;
+    flacb200_stream_reader* r = new flacb200_stream_reader();
+    r->engine = engine;
+    *out = r;
+    return 0;
+}
+
+void flacb200_stream_reader_close(flacb200_stream_reader* r) { delete r; }
+
+int flacb200_stream_reader_feed(flacb200_stream_reader* r, const uint8_t* bytes, size_t len, int eof)
+{
+    if (!r || (!bytes && len) || (r->eof && len)) return FLACB200_E_BAD_ARGUMENT;
+    if (r->cur >= r->frames.size() && r->pos) {   // nothing borrowed from the buffer: drop what has been scanned
+        r->fed.erase(r->fed.begin(), r->fed.begin() + (long)r->pos);
+        r->pos = 0;
+    }
+    r->fed.insert(r->fed.end(), bytes, bytes + len);
+    if (eof) r->eof = true;
+    return 0;
+}
+
+int flacb200_stream_reader_read(flacb200_stream_reader* r, flacb200_framebuf* out)
+{
+    if (!r || !out) return FLACB200_E_BAD_ARGUMENT;
+    memset(out, 0, sizeof(*out));
+    if (r->cur >= r->frames.size()) {
+        const int rc = stream_reader_next_run(*r);
+        if (rc) return rc;
+    }
+    const flacb200_frame_entry& e = r->frames[r->cur];
+    out->samples = reinterpret_cast<const int32_t*>(r->win.p) + (size_t)e.pcm_offset * r->channels;
+    out->n_samples = (size_t)e.block_size * r->channels;
+    out->sample_rate = r->rates[r->cur];
+    out->channels = r->channels;
+    out->bits_per_sample = r->bps;
+    out->block_size = e.block_size;
+    r->cur++;
+    return 0;
+}
+
+// FlacStreamWriter::write (src/encode.rs:1094-1274): one subset frame from one call's interleaved samples
+int flacb200_stream_write(flacb200_engine* e, const flacb200_options* opt, uint32_t sample_rate, uint32_t channels, uint32_t bits_per_sample,
+                          const int32_t* samples, size_t n_samples, uint64_t frame_number, uint8_t* out, size_t out_capacity, size_t* out_len)
+{
+    if (!e || !opt || !out_len || (!samples && n_samples)) return FLACB200_E_BAD_ARGUMENT;
+    *out_len = 0;
+    if (channels == 0 || n_samples % channels) return E_SAMPLES_NOT_DIVISIBLE;   // :1103
+    const size_t n = n_samples / channels;
+    if (n == 0) return 0;
+    if (n > 65535) return 24;   // InvalidBlockSize: a frame holds at most 65535 samples per channel (:1118)
+    flacb200_options o = *opt;
+    o.block_size = (uint16_t)n;
+    flacb200_stream_params prm{};
+    prm.sample_rate = sample_rate;
+    prm.bits_per_sample = bits_per_sample;
+    prm.channels = channels;
+    prm.subset = 1;
+    flacb200_segment seg{0, n, frame_number};
+    uint64_t nf = 0, total = 0;
+    flacb200_engine_set_keep_info(e, 0);
+    const int rc = flacb200_encode(e, &o, &prm, samples, n_samples * 4, FLACB200_PCM_I32_INTERLEAVED, FLACB200_HOST, 0, &seg, 1, out, out_capacity,
+                                   FLACB200_HOST, nullptr, 0, &nf, &total);
+    if (rc) return rc;
+    *out_len = (size_t)total;
     return 0;
 }
 

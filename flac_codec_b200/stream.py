@@ -8,6 +8,7 @@ All work happens in libflacb200.so; nothing here falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import io
 from typing import Optional, Sequence
 
 import numpy as np
@@ -196,7 +197,8 @@ class FlacChannelWriter(_Writer):
 
 
 class FlacStreamWriter:
-    """FlacStreamWriter<W> (src/encode.rs:1063-1290): subset frames only, no metadata, parameters per call."""
+    """FlacStreamWriter<W> (src/encode.rs:1063-1290): subset frames only, no metadata, parameters per call
+    (flacb200_stream_write)."""
 
     def __init__(self, writer, options: Options, *, engine: Optional[Engine] = None):
         self._sink, self._opt = writer, options
@@ -205,22 +207,15 @@ class FlacStreamWriter:
 
     def write(self, sample_rate: int, channels: int, bits_per_sample: int, samples):
         a = np.ascontiguousarray(samples, dtype=np.int32).reshape(-1)
-        if channels == 0 or a.size % channels:
-            raise FlacB200Error(61, "FlacStreamWriter::write")   # SamplesNotDivisibleByChannels (:1103)
-        n = a.size // channels
-        if n == 0:
-            return
-        if n > 65535:
-            raise FlacB200Error(24, "FlacStreamWriter::write")   # InvalidBlockSize: one frame per call (:1118)
-        from .engine import Options as _O   # a copy with the block size of this call
-
-        opt = _O("default")
-        C.memmove(C.byref(opt.c), C.byref(self._opt.c), C.sizeof(opt.c))
-        opt.c.block_size = max(n, 1)
-        data, sizes, total = self._engine.encode(opt, sample_rate, bits_per_sample, channels, a, a.nbytes,
-                                                 _abi.PCM_I32_INTERLEAVED, [(0, n, self._frame_number)], subset=True)
-        self._frame_number += 1
-        self._sink.write(data.tobytes())
+        cap = a.size * 5 + 1024
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        check(_abi.lib().flacb200_stream_write(self._engine._h, C.byref(self._opt.c), sample_rate, channels, bits_per_sample,
+                                               C.c_void_p(a.ctypes.data if a.size else 0), a.size, self._frame_number,
+                                               C.c_void_p(out.ctypes.data), cap, C.byref(n)), "FlacStreamWriter::write")
+        if n.value:
+            self._frame_number += 1
+            self._sink.write(out[: n.value].tobytes())
 
     def write_cdda(self, samples):
         self.write(44100, 2, 16, samples)
@@ -228,16 +223,44 @@ class FlacStreamWriter:
 
 # ---------------------------------------------------------------------------------------------------------------
 class _Reader:
-    def __init__(self, reader, *, engine: Optional[Engine] = None):
+    """Decoder (src/decode.rs:1311-1491) behind flacb200_reader.
+
+    `reader` is a bytes-like file image or a file object with read() [+ seek()].  A seekable source (new_seekable / open)
+    is held as an image; with `streaming=True` (the reference's plain `new(R: Read)`) the bytes are fed to the handle in
+    chunks of `chunk` bytes as the decoder asks for them, and the reader cannot seek."""
+
+    def __init__(self, reader, *, engine: Optional[Engine] = None, streaming: bool = False, chunk: int = 1 << 20,
+                 window_bytes: int = 0, window_pcm_frames: int = 0):
         self._L = _abi.lib()
-        data = reader if isinstance(reader, (bytes, bytearray, memoryview)) else reader.read()
-        self._image = np.frombuffer(bytes(data), dtype=np.uint8)   # kept alive: the handle borrows it
         self._engine = engine if engine is not None else default_engine()
         self._h = C.c_void_p()
-        check(self._L.flacb200_reader_open(self._engine._h, C.c_void_p(self._image.ctypes.data), self._image.size,
-                                           C.byref(self._h)), "FlacReader::new")
+        self._src, self._chunk, self._eof = None, chunk, False
+        if streaming:
+            self._src = io.BytesIO(bytes(reader)) if isinstance(reader, (bytes, bytearray, memoryview)) else reader
+            check(self._L.flacb200_reader_open_stream(self._engine._h, C.byref(self._h)), "FlacReader::new")
+        else:
+            data = reader if isinstance(reader, (bytes, bytearray, memoryview)) else reader.read()
+            self._image = np.frombuffer(bytes(data), dtype=np.uint8)   # kept alive: the handle borrows it
+            check(self._L.flacb200_reader_open(self._engine._h, C.c_void_p(self._image.ctypes.data), self._image.size,
+                                               C.byref(self._h)), "FlacReader::new")
+        if window_bytes or window_pcm_frames:
+            check(self._L.flacb200_reader_set_window(self._h, window_bytes, window_pcm_frames), "set_window")
         self._si = _abi.Streaminfo()
-        check(self._L.flacb200_reader_info(self._h, C.byref(self._si)), "reader_info")
+        self._call(lambda: self._L.flacb200_reader_info(self._h, C.byref(self._si)), "BlockList::read")
+
+    def _call(self, fn, what: str):
+        """Runs one handle call; in streaming mode FLACB200_NEED_DATA is answered by feeding the next chunk of the source."""
+        while True:
+            rc = fn()
+            if rc != _abi.NEED_DATA:
+                check(rc, what)
+                return
+            if self._src is None or self._eof:
+                check(1, what)   # Io: the source ended inside a frame
+            b = self._src.read(self._chunk)
+            a = np.frombuffer(b, dtype=np.uint8)
+            self._eof = a.size == 0
+            check(self._L.flacb200_reader_feed(self._h, C.c_void_p(a.ctypes.data if a.size else 0), a.size, int(self._eof)), "feed")
 
     # Metadata trait (src/metadata/mod.rs:48-105)
     def channel_count(self) -> int:
@@ -267,13 +290,19 @@ class _Reader:
         check(self._L.flacb200_reader_seektable(self._h, pts, n.value, C.byref(n)), "seektable")
         return [(p.sample_offset, p.byte_offset, p.frame_samples, bool(p.placeholder)) for p in pts[: n.value]]
 
-    def seek(self, sample: int):   # Decoder::seek (src/decode.rs:1452): inter-channel sample index
-        check(self._L.flacb200_reader_seek(self._h, sample), "seek")
+    def seek(self, sample: int):
+        """FlacSampleReader::seek / FlacChannelReader::seek (src/decode.rs:823, :1021): inter-channel sample index."""
+        self._call(lambda: self._L.flacb200_reader_seek(self._h, sample), "seek")
 
     def verify(self):
         res, md5 = C.c_int(0), (C.c_uint8 * 16)()
-        check(self._L.flacb200_reader_verify(self._h, C.byref(res), C.byref(md5)), "verify")
+        self._call(lambda: self._L.flacb200_reader_verify(self._h, C.byref(res), C.byref(md5)), "verify")
         return ("MD5Match", "MD5Mismatch", "NoMD5")[res.value], bytes(md5)
+
+    def _read(self, buf: np.ndarray, capacity: int, kind: int) -> int:
+        n = C.c_size_t(0)
+        self._call(lambda: self._L.flacb200_reader_read(self._h, C.c_void_p(buf.ctypes.data), capacity, kind, C.byref(n)), "read")
+        return n.value
 
     def close(self):
         if self._h:
@@ -288,11 +317,12 @@ class _Reader:
 
 
 class FlacByteReader(_Reader):
-    """FlacByteReader<R, E> (src/decode.rs:103-371)."""
+    """FlacByteReader<R, E> (src/decode.rs:103-371): io::Read + io::BufRead + io::Seek over the decoded PCM bytes."""
 
     def __init__(self, reader, *, endian: str = "little", **kw):
         super().__init__(reader, **kw)
         self._kind = _abi.PCM_BYTES_LE if endian == "little" else _abi.PCM_BYTES_BE
+        self._pos = 0   # byte position, for io::Seek
 
     def read(self, size: int = -1) -> bytes:
         chunks = []
@@ -302,13 +332,40 @@ class FlacByteReader(_Reader):
             # one call for the whole stream when its length is known (a fresh 16 MB buffer per call costs more than the decode)
             cap = min(want, max(known, 1) if known is not None and size < 0 and not chunks else 1 << 24)
             buf = np.empty(cap, dtype=np.uint8)
-            n = C.c_size_t(0)
-            check(self._L.flacb200_reader_read(self._h, C.c_void_p(buf.ctypes.data), cap, self._kind, C.byref(n)), "read")
-            if n.value == 0:
+            n = self._read(buf, cap, self._kind)
+            if n == 0:
                 break
-            chunks.append(buf[: n.value].tobytes())
-            want -= n.value
-        return b"".join(chunks)
+            chunks.append(buf[:n].tobytes())
+            want -= n
+        out = b"".join(chunks)
+        self._pos += len(out)
+        return out
+
+    def seek_bytes(self, offset: int, whence: int = 0) -> int:
+        """io::Seek (src/decode.rs:715-820): byte positions of the decoded stream; truncated to whole PCM frames' worth of
+        decoding, then bytes are skipped up to the position."""
+        bpf = ((self._si.bits_per_sample + 7) // 8) * self._si.channels
+        if whence == 0:
+            want = offset
+        elif whence == 1:
+            want = self._pos + offset
+        else:
+            if not self._si.total_samples:
+                raise OSError("total samples not known")
+            if offset > 0:
+                raise OSError("cannot seek beyond end of file")
+            want = self._si.total_samples * bpf + offset
+        if want < 0:
+            raise OSError("cannot seek below byte 0")
+        self.seek(want // bpf)
+        self._pos = (want // bpf) * bpf
+        skip = want - self._pos
+        if skip:   # a position inside a PCM frame: the remaining bytes of that frame are consumed from the buffer
+            got = self.read(bpf)
+            if len(got) < bpf:
+                raise EOFError("stream exhausted before sample reached")
+            self._pos = want   # (the rest of this PCM frame is dropped, as BufRead::consume would)
+        return want
 
 
 class FlacSampleReader(_Reader):
@@ -316,10 +373,7 @@ class FlacSampleReader(_Reader):
 
     def read(self, n_samples: int) -> np.ndarray:
         buf = np.empty(max(n_samples, 1), dtype=np.int32)
-        n = C.c_size_t(0)
-        check(self._L.flacb200_reader_read(self._h, C.c_void_p(buf.ctypes.data), n_samples, _abi.PCM_I32_INTERLEAVED,
-                                           C.byref(n)), "read")
-        return buf[: n.value]
+        return buf[: self._read(buf, n_samples, _abi.PCM_I32_INTERLEAVED)]
 
     def read_to_end(self) -> np.ndarray:
         out = []
@@ -330,22 +384,76 @@ class FlacSampleReader(_Reader):
             out.append(a.copy())
         return np.concatenate(out) if out else np.zeros(0, dtype=np.int32)
 
+    def fill_buf(self) -> np.ndarray:
+        """The unconsumed interleaved samples of the current frame (:466); empty at the end of the stream."""
+        p, n = C.POINTER(C.c_int32)(), C.c_size_t(0)
+        self._call(lambda: self._L.flacb200_reader_fill_buf(self._h, C.byref(p), C.byref(n)), "fill_buf")
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, dtype=np.int32)
+
+    def consume(self, amt: int):
+        check(self._L.flacb200_reader_consume(self._h, amt), "consume")
+
+    def __iter__(self):
+        """FlacSampleIterator (:667-712): one sample at a time."""
+        while True:
+            buf = self.fill_buf()
+            if buf.size == 0:
+                return
+            self.consume(buf.size)
+            yield from (int(v) for v in buf)
+
+
+class FlacChannelReader(_Reader):
+    """FlacChannelReader<R> (src/decode.rs:880-1065): one slice per channel."""
+
+    def fill_buf(self):
+        pp, n = C.POINTER(C.POINTER(C.c_int32))(), C.c_size_t(0)
+        self._call(lambda: self._L.flacb200_reader_fill_channels(self._h, C.byref(pp), C.byref(n)), "fill_buf")
+        return [np.ctypeslib.as_array(pp[c], shape=(n.value,)).copy() if n.value else np.zeros(0, dtype=np.int32)
+                for c in range(self._si.channels)]
+
+    def consume(self, amt: int):
+        check(self._L.flacb200_reader_consume_channels(self._h, amt), "consume")
+
 
 class FlacStreamReader:
-    """FlacStreamReader<R> (src/decode.rs:1158-1268): subset frames without metadata; all frames of the image are
-    decoded in one batch and handed out one FrameBuf at a time."""
+    """FlacStreamReader<R> (src/decode.rs:1149-1268): subset frames without metadata.  read() returns the next frame as
+    (samples, sample_rate, channels, bits_per_sample) -- FrameBuf -- with the parameters of that frame's own header."""
 
-    def __init__(self, reader, sample_rate: int, channels: int, bits_per_sample: int, *, engine: Optional[Engine] = None):
-        data = reader if isinstance(reader, (bytes, bytearray, memoryview)) else reader.read()
-        self._image = np.frombuffer(bytes(data), dtype=np.uint8)
+    def __init__(self, reader, *, engine: Optional[Engine] = None, chunk: int = 1 << 20):
+        self._L = _abi.lib()
         self._engine = engine if engine is not None else default_engine()
-        self.sample_rate, self.channels, self.bits_per_sample = sample_rate, channels, bits_per_sample
+        self._src = io.BytesIO(bytes(reader)) if isinstance(reader, (bytes, bytearray, memoryview)) else reader
+        self._chunk, self._eof = chunk, False
+        self._h = C.c_void_p()
+        check(self._L.flacb200_stream_reader_open(self._engine._h, C.byref(self._h)), "FlacStreamReader::new")
 
-    def read_all(self, max_pcm_frames: int) -> np.ndarray:
-        out = np.zeros(max_pcm_frames * self.channels, dtype=np.int32)
-        nf, ns = self._engine.decode(self.sample_rate, self.bits_per_sample, self.channels, 0, self._image, self._image.size,
-                                     [(0, self._image.size, 0, 0)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED, subset=True)
-        return out[: ns * self.channels]
+    def read(self):
+        fb = _abi.FrameBuf()
+        while True:
+            rc = self._L.flacb200_stream_reader_read(self._h, C.byref(fb))
+            if rc != _abi.NEED_DATA:
+                check(rc, "FlacStreamReader::read")
+                break
+            if self._eof:
+                check(1, "FlacStreamReader::read")
+            b = self._src.read(self._chunk)
+            a = np.frombuffer(b, dtype=np.uint8)
+            self._eof = a.size == 0
+            check(self._L.flacb200_stream_reader_feed(self._h, C.c_void_p(a.ctypes.data if a.size else 0), a.size, int(self._eof)), "feed")
+        samples = np.ctypeslib.as_array(fb.samples, shape=(fb.n_samples,)).copy()
+        return samples, fb.sample_rate, fb.channels, fb.bits_per_sample
+
+    def close(self):
+        if self._h:
+            self._L.flacb200_stream_reader_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def verify(reader, **kw):

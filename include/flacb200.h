@@ -158,6 +158,19 @@ int flacb200_decode(flacb200_engine* e, const flacb200_stream_params* params, co
                     size_t n_segments, void* pcm_out, size_t pcm_out_bytes, int pcm_kind, int pcm_location,
                     uint64_t planar_stride, uint64_t* n_frames, uint64_t* n_pcm_frames, uint64_t* bad_frame);
 
+/* Where the frames of the most recent flacb200_decode call were found, in stream order (the frames the serial reader
+ * would have visited, up to the first error): what Decoder::read_frame learns one frame at a time -- byte position,
+ * block size (FrameHeader::block_size), running sample position (Decoder::current_sample, src/decode.rs:1432).  The
+ * readers of flacb200_stream.h use it to hand out frame-sized buffers (fill_buf) and to continue a stream window by
+ * window.  Valid for a call that was not split into batches (fewer than four segments, or device buffers). */
+typedef struct flacb200_frame_entry {
+    uint64_t byte_offset;  /* of the frame's sync code in the `frames` buffer */
+    uint64_t pcm_offset;   /* inter-channel sample index in the PCM output where the frame's samples start */
+    uint32_t byte_length;  /* header .. CRC-16 */
+    uint32_t block_size;   /* inter-channel samples */
+} flacb200_frame_entry;
+int flacb200_decode_last_frames(flacb200_engine* e, flacb200_frame_entry* table, size_t capacity, uint64_t* n_entries);
+
 /*
  * MD5 of many streams at once: the STREAMINFO signature the reference computes while encoding (update_md5,
  * src/encode.rs:1292-1318) and checks in verify (src/decode.rs:1291-1309) -- MD5 over the samples as little-endian

@@ -113,23 +113,72 @@ typedef struct flacb200_seekpoint {
 
 typedef struct flacb200_reader flacb200_reader;
 
-/* FlacByteReader::new / FlacSampleReader::new over a file image that stays valid while the reader lives.
+/* Returned by the reader calls in feed mode when the bytes buffered so far hold no complete frame (or not yet all
+ * metadata blocks): feed more and call again.  Not an error of the stream. */
+#define FLACB200_NEED_DATA (-10)
+
+/* The reader is the reference's Decoder (src/decode.rs:1311-1491) behind FlacByteReader / FlacSampleReader /
+ * FlacChannelReader.  It decodes WINDOW by window: a run of bytes that starts at a frame boundary goes through one
+ * flacb200_decode call, its frames are handed out one at a time, and the next window starts where the last good frame
+ * ended -- memory is bounded by the window (default 32 MiB of frames / 8 Mi inter-channel samples), not by the stream.
+ * An error of the stream is returned when the reader gets to the failing frame, after every frame in front of it has been
+ * delivered (Decoder::read_frame's behaviour), and is sticky from then on.
+ *
+ * Two sources:
+ *   flacb200_reader_open         `R: Read + Seek` (new_seekable / open): a file image that stays valid while the reader lives
+ *   flacb200_reader_open_stream  `R: Read` (new): bytes arrive through flacb200_reader_feed; calls return FLACB200_NEED_DATA
+ *                                until enough has been fed; decoded bytes are dropped; not seekable
  * engine may be NULL for metadata-only use. */
 int flacb200_reader_open(flacb200_engine* engine, const uint8_t* flac, size_t len, flacb200_reader** out);
+int flacb200_reader_open_stream(flacb200_engine* engine, flacb200_reader** out);
+int flacb200_reader_feed(flacb200_reader* r, const uint8_t* bytes, size_t len, int eof);
 void flacb200_reader_close(flacb200_reader* r);
+/* window limits: bytes of frames / inter-channel samples per GPU call; 0 keeps the current value */
+int flacb200_reader_set_window(flacb200_reader* r, size_t window_bytes, uint64_t window_pcm_frames);
 int flacb200_reader_info(flacb200_reader* r, flacb200_streaminfo* si);
 int flacb200_reader_seektable(flacb200_reader* r, flacb200_seekpoint* points, size_t capacity, size_t* n_points);
 
-/* Decodes the whole stream on the GPU at the first call (all frames in one batch), then serves PCM like
- * FlacSampleReader::read / FlacByteReader::read: up to `capacity` single-channel samples (or bytes) from the
- * current position, *n_out = how many were delivered (0 at the end of the stream).
+/* FlacSampleReader::read / FlacByteReader::read (src/decode.rs:274-303, :420-450): up to `capacity` single-channel samples
+ * (or bytes) from the current position, whole PCM frames only; *n_out = how many were delivered (0 at the end of the stream).
  * pcm_kind: FLACB200_PCM_BYTES_LE / _BE (capacity and *n_out in bytes) or FLACB200_PCM_I32_INTERLEAVED (in samples). */
 int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm_kind, size_t* n_out);
-/* Decoder::seek (src/decode.rs:1452): position in inter-channel samples; beyond the end -> InvalidSeek */
+/* FlacSampleReader::fill_buf / consume (:466-492): the unconsumed interleaved samples of the current frame (a borrow that
+ * lives until the next call on r; empty at the end of the stream); consume counts samples of all channels. */
+int flacb200_reader_fill_buf(flacb200_reader* r, const int32_t** samples, size_t* n_samples);
+int flacb200_reader_consume(flacb200_reader* r, size_t n_samples);
+/* FlacChannelReader::fill_buf / consume (:917-949): one pointer per channel over the unconsumed part of the current frame
+ * (*channels: array of streaminfo.channels pointers, n_per_channel samples each), consume counts samples per channel. */
+int flacb200_reader_fill_channels(flacb200_reader* r, const int32_t* const** channels, size_t* n_per_channel);
+int flacb200_reader_consume_channels(flacb200_reader* r, size_t n_per_channel);
+/* FlacSampleReader::seek / FlacChannelReader::seek / io::Seek of FlacByteReader (:715-860, :1021-1057): Decoder::seek
+ * (:1452-1491) repositions to the last SEEKTABLE point at or before the sample (the first frame without a table) and the
+ * frames up to the sample are decoded and skipped.  pcm_frame: inter-channel samples; beyond the end -> InvalidSeek. */
 int flacb200_reader_seek(flacb200_reader* r, uint64_t pcm_frame);
-/* verify (src/decode.rs:1282-1309): decode everything and compare the MD5 of the little-endian PCM with STREAMINFO.
- * *result: 0 MD5Match, 1 MD5Mismatch, 2 NoMD5 (all-zero sum stored) */
+/* verify_reader (src/decode.rs:1291-1309): decode from the current position to the end, MD5 of the little-endian PCM against
+ * STREAMINFO.  *result: 0 MD5Match, 1 MD5Mismatch, 2 NoMD5 (all-zero sum stored) */
 int flacb200_reader_verify(flacb200_reader* r, int* result, uint8_t md5_out[16]);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* FlacStreamWriter::write (src/encode.rs:1094-1274): one subset frame (no metadata, parameters in every header) from the
+ * n_samples interleaved samples of one call; frame_number is the writer's running count.  The frame goes to out. */
+int flacb200_stream_write(flacb200_engine* e, const flacb200_options* opt, uint32_t sample_rate, uint32_t channels,
+                          uint32_t bits_per_sample, const int32_t* samples, size_t n_samples, uint64_t frame_number,
+                          uint8_t* out, size_t out_capacity, size_t* out_len);
+
+/* FlacStreamReader (src/decode.rs:1149-1268): subset frames without metadata; every FrameBuf carries the parameters of its
+ * own frame header (FrameBuf, :1253-1268) -- the caller passes none.  Bytes are fed like an `R: BufRead`; read returns the
+ * next frame, FLACB200_NEED_DATA when more bytes are needed, the frame's error, or Io at the end of the stream ("eof looking
+ * for frame sync", :1198).  Runs of frames with the same channel count and sample width are decoded in one GPU call. */
+typedef struct flacb200_stream_reader flacb200_stream_reader;
+typedef struct flacb200_framebuf {
+    const int32_t* samples;   /* interleaved; valid until the next call on the reader */
+    size_t n_samples;         /* block_size * channels */
+    uint32_t sample_rate, channels, bits_per_sample, block_size;
+} flacb200_framebuf;
+int flacb200_stream_reader_open(flacb200_engine* engine, flacb200_stream_reader** out);
+void flacb200_stream_reader_close(flacb200_stream_reader* r);
+int flacb200_stream_reader_feed(flacb200_stream_reader* r, const uint8_t* bytes, size_t len, int eof);
+int flacb200_stream_reader_read(flacb200_stream_reader* r, flacb200_framebuf* out);
 
 /* MD5 as the encoder/verify use it (host); exported for the shim and the tests */
 void flacb200_md5(const uint8_t* data, size_t len, uint8_t out[16]);

@@ -171,8 +171,15 @@ def test_stream_writer_subset_frames(fo, st):
     for k, blk in enumerate((x[:1000], x[1000:])):
         ref += fo.encode_frame(fo.options("default", block_size=len(blk)), 44100, 16, blk.T, frame_number=k, subset=True)
     assert sink.getvalue() == ref
-    r = st.FlacStreamReader(sink.getvalue(), 44100, 2, 16)
-    assert np.array_equal(r.read_all(3000).reshape(-1, 2), x)
+    r = st.FlacStreamReader(sink.getvalue())
+    a, rate, ch, bps = r.read()
+    assert (rate, ch, bps) == (44100, 2, 16) and np.array_equal(a.reshape(-1, 2), x[:1000])
+    b, rate, ch, bps = r.read()
+    assert (rate, ch, bps) == (44100, 2, 16) and np.array_equal(b.reshape(-1, 2), x[1000:])
+    with pytest.raises(FlacB200Error) as e:
+        r.read()
+    assert e.value.code == 1     # Io: "eof looking for frame sync" (src/decode.rs:1198)
+    r.close()
     with pytest.raises(FlacB200Error) as e:
         w.write(44100, 2, 17, x[:10].reshape(-1))     # NonSubsetBitsPerSample (:1134)
     assert e.value.code == 28
@@ -265,3 +272,179 @@ def test_cpp_host_front_end_wav2flac_roundtrip(fo, tmp_path):
     assert (tmp_path / "out.flac").read_bytes() == ref
     subprocess.check_call([exe, "decode", str(tmp_path / "out.flac"), str(tmp_path / "back.wav")])
     assert (tmp_path / "back.wav").read_bytes() == wav
+
+
+# ---- the reader handle: windows, feeding, seek through the SEEKTABLE, fill_buf / consume, channels ----
+def _long_stream(fo, seconds=20, rate=44100, bps=16, ch=2, **optkw):
+    x = synth_pcm(21, ch, rate * seconds + 777, rate, bps).reshape(-1)
+    flac, sizes = fo.encode_stream(fo.options("default", **optkw), rate, bps, ch, x, total_known=True)
+    return x, flac, sizes
+
+
+def test_reader_windows_are_invisible(fo, st):
+    """A stream decoded in many small windows (frames cut by the window ends, tiny PCM budgets) is the stream."""
+    x, flac, sizes = _long_stream(fo)
+    for wb, wp in ((1 << 16, 0), (5000, 0), (1 << 20, 4096), (12345, 9000)):
+        r = st.FlacSampleReader(flac, window_bytes=wb, window_pcm_frames=wp)
+        assert np.array_equal(r.read_to_end(), x), (wb, wp)
+        assert r.verify()[0] == "MD5Match"
+        r.close()
+    rb = st.FlacByteReader(flac, window_bytes=70000)
+    assert rb.read() == fo.samples_to_bytes(x, 2)
+    rb.close()
+
+
+def test_reader_fed_in_chunks_like_a_plain_read(fo, st):
+    """FlacSampleReader::new(R: Read): the file arrives in chunks, decoded bytes are dropped, seeking is refused."""
+    from flac_codec_b200._abi import FlacB200Error
+
+    x, flac, _ = _long_stream(fo, seconds=8)
+    for chunk in (1000, 65536, 1 << 22):
+        r = st.FlacSampleReader(io.BytesIO(flac), streaming=True, chunk=chunk, window_bytes=1 << 17)
+        assert r.total_samples() == x.size // 2 and r.sample_rate() == 44100
+        got = []
+        while True:
+            a = r.read(50000)
+            if a.size == 0:
+                break
+            got.append(a.copy())
+        assert np.array_equal(np.concatenate(got), x), chunk
+        with pytest.raises(FlacB200Error):
+            r.seek(0)
+        r.close()
+    assert st.FlacByteReader(io.BytesIO(flac), streaming=True, chunk=4096).verify()[0] == "MD5Match"
+    # a source that ends inside a frame: the frames in front are delivered, then Io
+    r = st.FlacSampleReader(io.BytesIO(flac[: len(flac) * 2 // 3]), streaming=True, chunk=30000)
+    got = []
+    with pytest.raises(FlacB200Error) as e:
+        while True:
+            a = r.read(1 << 20)
+            if a.size == 0:
+                break
+            got.append(a.copy())
+    assert e.value.code == 1
+    n = sum(a.size for a in got)
+    assert n > 0 and n % (4096 * 2) == 0 and np.array_equal(np.concatenate(got), x[:n])
+    r.close()
+
+
+def test_seek_uses_the_seektable(fo, st):
+    """Decoder::seek (src/decode.rs:1452-1491): jump to the last seek point <= sample, decode and skip from there.  With a
+    window of one frame the number of frames decoded after a seek shows that the jump happened."""
+    from flac_codec_b200._abi import FlacB200Error
+
+    x, flac, sizes = _long_stream(fo, seconds=35)     # default seek table: every 10 s
+    total = x.size // 2
+    r = st.FlacSampleReader(flac)
+    pts = [p for p in r.seektable() if not p[3]]
+    assert len(pts) == 4 and pts[1][0] > 0
+    for pos in (0, 5, 4096 * 3 + 17, pts[1][0] - 1, pts[1][0], pts[2][0] + 4096 * 5 + 1, total - 1, total):
+        r.seek(pos)
+        assert np.array_equal(r.read(6000), x[pos * 2:pos * 2 + 6000]), pos
+    with pytest.raises(FlacB200Error) as e:
+        r.seek(total + 1)
+    assert e.value.code == 37
+    r.close()
+    # the same file with its seek points blanked out: still correct, from the start of the stream
+    si = fo.read_streaminfo(flac)
+    blank = bytearray(flac)
+    at = 4 + 4 + 34 + 4
+    for i in range(si.n_seekpoints if hasattr(si, "n_seekpoints") else len(pts)):
+        blank[at + 18 * i: at + 18 * i + 8] = b"\xff" * 8
+    r = st.FlacSampleReader(bytes(blank))
+    assert all(p[3] for p in r.seektable())
+    r.seek(pts[2][0] + 100)
+    assert np.array_equal(r.read(1000), x[(pts[2][0] + 100) * 2:(pts[2][0] + 100) * 2 + 1000])
+    r.close()
+    # FlacByteReader's io::Seek, in bytes (src/decode.rs:715-820)
+    rb = st.FlacByteReader(flac)
+    raw = fo.samples_to_bytes(x, 2)
+    for off in (0, 4 * 1000, 4 * (pts[1][0] + 3), len(raw) - 8):
+        assert rb.seek_bytes(off) == off
+        assert rb.read(4000) == raw[off:off + 4000]
+    assert rb.seek_bytes(-400, 2) == len(raw) - 400 and rb.read() == raw[-400:]
+    rb.close()
+
+
+def test_fill_buf_consume_and_channel_reader(fo, st):
+    """fill_buf hands out one frame at a time (FlacSampleReader :466, FlacChannelReader :917); block sizes vary in
+    all-frames.flac."""
+    for name in ("all-frames.flac", "sine.flac"):
+        flac = ref_file(name)
+        y, si = fo.decode_stream(flac)
+        ch = si.channels
+        # frame sizes as the serial reader sees them
+        sizes, p, cur = [], si.frames_start, 0
+        while cur < si.total_samples:
+            _, h, used = fo.decode_frame(flac[p:], si, si.total_samples - cur)
+            sizes.append(h.block_size)
+            p += used
+            cur += h.block_size
+        r = st.FlacSampleReader(flac)
+        pos = 0
+        for k, bs in enumerate(sizes):
+            buf = r.fill_buf()
+            assert buf.size == bs * ch, (name, k)
+            assert np.array_equal(buf, y[pos:pos + bs * ch])
+            if bs > 1:     # partial consume: the rest of the same frame comes back
+                r.consume(ch)
+                assert np.array_equal(r.fill_buf(), y[pos + ch:pos + bs * ch])
+                r.consume((bs - 1) * ch)
+            else:
+                r.consume(ch)
+            pos += bs * ch
+        assert r.fill_buf().size == 0
+        r.close()
+        rc = st.FlacChannelReader(flac)
+        pos = 0
+        for bs in sizes:
+            chans = rc.fill_buf()
+            assert len(chans) == ch and all(c.size == bs for c in chans)
+            for c in range(ch):
+                assert np.array_equal(chans[c], y[pos + c:pos + bs * ch:ch])
+            rc.consume(bs)
+            pos += bs * ch
+        assert all(c.size == 0 for c in rc.fill_buf())
+        rc.seek(sizes[0] + 1)
+        chans = rc.fill_buf()
+        assert np.array_equal(chans[0], y[(sizes[0] + 1) * ch:(sizes[0] + sizes[1]) * ch:ch])
+        rc.close()
+    # FlacSampleIterator (:667)
+    flac = ref_file("all-frames.flac")
+    y, si = fo.decode_stream(flac)
+    assert list(st.FlacSampleReader(flac)) == y.tolist()
+
+
+def test_stream_reader_takes_its_parameters_from_the_frames(fo, st):
+    """FlacStreamReader::read (src/decode.rs:1175-1240): no metadata, no parameters from the caller; rate, channels and
+    bits per sample change from frame to frame; junk between frames is skipped by the sync scan."""
+    from flac_codec_b200 import Options
+    from flac_codec_b200._abi import FlacB200Error
+
+    sink = io.BytesIO()
+    w = st.FlacStreamWriter(sink, Options.default())
+    plan = [(44100, 2, 16, 1000), (44100, 2, 16, 4096), (48000, 2, 16, 777), (96000, 1, 24, 2000), (96000, 1, 24, 2000), (8000, 4, 8, 333)]
+    blocks = []
+    for k, (rate, ch, bps, n) in enumerate(plan):
+        x = synth_pcm(40 + k, ch, n, rate, bps)
+        blocks.append(x)
+        w.write(rate, ch, bps, x.reshape(-1))
+    data = sink.getvalue()
+    for chunk in (1 << 20, 997):
+        r = st.FlacStreamReader(io.BytesIO(data), chunk=chunk)
+        for (rate, ch, bps, n), x in zip(plan, blocks):
+            a, grate, gch, gbps = r.read()
+            assert (grate, gch, gbps) == (rate, ch, bps)
+            assert np.array_equal(a.reshape(-1, ch), x)
+        with pytest.raises(FlacB200Error) as e:
+            r.read()
+        assert e.value.code == 1
+        r.close()
+    # junk in front and between two frames
+    f0 = fo.encode_frame(fo.options("default", block_size=500), 44100, 16, blocks[0][:500].T, frame_number=0, subset=True)
+    f1 = fo.encode_frame(fo.options("default", block_size=300), 44100, 16, blocks[0][500:800].T, frame_number=1, subset=True)
+    r = st.FlacStreamReader(b"\x00\x01\xff\x00junk" + f0 + b"\xff\xf8\x00garbage\xff" + f1)
+    a, *_ = r.read()
+    b, *_ = r.read()
+    assert np.array_equal(a.reshape(-1, 2), blocks[0][:500]) and np.array_equal(b.reshape(-1, 2), blocks[0][500:800])
+    r.close()
