@@ -99,6 +99,21 @@ class FrameBuf(C.Structure):
                 ("bits_per_sample", C.c_uint32), ("block_size", C.c_uint32)]
 
 
+class Track(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("n_pcm_frames", C.c_uint64), ("sample_rate", C.c_uint32), ("bits_per_sample", C.c_uint32),
+                ("channels", C.c_uint32), ("pcm_kind", C.c_int32)]
+
+
+class File(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("capacity", C.c_size_t), ("len", C.c_size_t), ("status", C.c_int32), ("frames", C.c_uint32),
+                ("md5", C.c_uint8 * 16)]
+
+
+class Pcm(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("capacity", C.c_size_t), ("len", C.c_size_t), ("status", C.c_int32), ("verified", C.c_int32),
+                ("info", Streaminfo)]
+
+
 NEED_DATA = -10
 
 EXPORTS = [
@@ -111,7 +126,8 @@ EXPORTS = [
     "flacb200_reader_open_stream", "flacb200_reader_feed", "flacb200_reader_set_window", "flacb200_reader_fill_buf",
     "flacb200_reader_consume", "flacb200_reader_fill_channels", "flacb200_reader_consume_channels", "flacb200_stream_write",
     "flacb200_stream_reader_open", "flacb200_stream_reader_close", "flacb200_stream_reader_feed", "flacb200_stream_reader_read",
-    "flacb200_decode_last_frames",
+    "flacb200_decode_last_frames", "flacb200_md5_many", "flacb200_encode_batch_bound", "flacb200_encode_batch", "flacb200_files_free",
+    "flacb200_decode_batch", "flacb200_pcm_free", "flacb200_build_stream_header",
     "flacb200_options_default", "flacb200_options_fast", "flacb200_options_best", "flacb200_engine_create",
     "flacb200_engine_destroy", "flacb200_engine_set_stream", "flacb200_engine_set_chunk_frames", "flacb200_engine_set_keep_info", "flacb200_engine_set_option", "flacb200_encode",
     "flacb200_encode_bound", "flacb200_encode_last_info", "flacb200_decode", "flacb200_set_profiling",
@@ -218,6 +234,16 @@ def lib():
     L.flacb200_stream_reader_feed.argtypes = [vp, vp, C.c_size_t, C.c_int]
     L.flacb200_stream_reader_read.argtypes = [vp, C.POINTER(FrameBuf)]
     L.flacb200_decode_last_frames.argtypes = [vp, C.POINTER(FrameEntry), C.c_size_t, u64p]
+    L.flacb200_md5_many.argtypes = [C.POINTER(vp), szp, C.c_size_t, vp, C.c_uint]
+    L.flacb200_md5_many.restype = None
+    L.flacb200_encode_batch_bound.argtypes = [C.POINTER(Track), C.POINTER(WriterOptions)]
+    L.flacb200_encode_batch_bound.restype = C.c_size_t
+    L.flacb200_encode_batch.argtypes = [C.POINTER(Track), C.c_size_t, C.POINTER(WriterOptions), C.POINTER(C.c_int), C.c_int, C.POINTER(File)]
+    L.flacb200_files_free.argtypes = [C.POINTER(File), C.c_size_t]
+    L.flacb200_files_free.restype = None
+    L.flacb200_decode_batch.argtypes = [C.POINTER(vp), szp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(Pcm)]
+    L.flacb200_pcm_free.argtypes = [C.POINTER(Pcm), C.c_size_t]
+    L.flacb200_pcm_free.restype = None
     L.flacb200_md5.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint8 * 16)]
     L.flacb200_md5.restype = None
     L.flacb200_md5_batch.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(Segment), C.c_size_t,

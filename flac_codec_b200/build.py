@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "..", "build", "flacb200")
 LIB = os.path.join(HERE, "libflacb200.so")
-SOURCES = ["engine.cu", "encode_kernels.cu", "decode_kernels.cu", "synth.cu", "stream.cpp", "encode_frame.cu", "encode_analyze.cu", "encode_lpc.cu", "decode_parse.cu", "md5.cu"]
+SOURCES = ["engine.cu", "encode_kernels.cu", "decode_kernels.cu", "synth.cu", "stream.cpp", "encode_frame.cu", "encode_analyze.cu", "encode_lpc.cu", "decode_parse.cu", "md5.cu", "md5_mb.cpp", "batch.cpp"]
 HEADERS = [os.path.join(HERE, "..", "include", h) for h in ("flacb200.h", "flacb200_stream.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

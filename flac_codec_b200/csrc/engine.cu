@@ -98,7 +98,7 @@ struct flacb200_engine {
     unsigned legacy = 0;
     bool no_batch = false, debug = false;
     size_t batch_bytes = 0;   // 0 = default
-    uint32_t lpc_overlap = 1;   // CTAs per SM of the persistent k_lpc3 that runs beside the previous group's integer kernels; 0 = off
+    uint32_t lpc_overlap = 0;   // (experiment, off: measured no gain -- both sides are occupancy-bound) CTAs per SM of the persistent k_lpc3 that runs beside the previous group's integer kernels; 0 = off
     int sm_count = 148;
     std::vector<cudaEvent_t> lpc_ev;   // per group: LPC parameters ready, analysis done (the two LpcRec buffers alternate)
     DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, dec[12];

@@ -1494,3 +1494,42 @@ int flacb200_stream_write(flacb200_engine* e, const flacb200_options* opt, uint3
 }
 
 }   // extern "C"
+
+// The metadata blocks of a finished stream from its frame sizes: Encoder::finalize_inner's bookkeeping (src/encode.rs:2024-2110)
+// without a writer handle -- for callers that encoded the frames of many streams in one batch (batch.cpp).
+extern "C" int flacb200_build_stream_header(const flacb200_writer_options* opt, uint32_t sample_rate, uint32_t bits_per_sample, uint32_t channels,
+                                            uint64_t total_pcm_frames, int total_known_at_open, const uint32_t* frame_sizes, uint64_t n_frames,
+                                            const uint8_t md5[16], uint8_t* out, size_t capacity, size_t* len)
+{
+    if (!opt || !len || (!frame_sizes && n_frames)) return FLACB200_E_BAD_ARGUMENT;
+    flacb200_writer* w = nullptr;
+    int rc = flacb200_writer_open(nullptr, opt, sample_rate, bits_per_sample, channels, total_known_at_open ? total_pcm_frames : 0, &w);
+    if (rc) return rc;
+    if (frame_sizes) {
+        uint64_t done = 0, bytes = 0;
+        for (uint64_t f = 0; f < n_frames; f++) {
+            const uint32_t n = (uint32_t)std::min<uint64_t>(w->block_size, total_pcm_frames - done), s = frame_sizes[f];
+            w->points.push_back(SeekPt{done, bytes, n});
+            bytes += s;
+            if (s < MAX_FRAME_SIZE && s != 0) {
+                w->min_frame = w->min_frame == 0 ? s : std::min(w->min_frame, s);
+                w->max_frame = w->max_frame == 0 ? s : std::max(w->max_frame, s);
+            }
+            done += n;
+        }
+        w->pcm_frames_encoded = total_pcm_frames;
+        if (md5) {
+            memcpy(w->md5_final, md5, 16);
+            w->md5_known = true;
+        }
+        build_header(*w, true);
+    }
+    *len = w->header.size();
+    rc = 0;
+    if (out) {
+        if (capacity < w->header.size()) rc = FLACB200_E_OUTPUT_TOO_SMALL;
+        else memcpy(out, w->header.data(), w->header.size());
+    }
+    flacb200_writer_close(w);
+    return rc;
+}

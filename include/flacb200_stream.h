@@ -182,6 +182,68 @@ int flacb200_stream_reader_read(flacb200_stream_reader* r, flacb200_framebuf* ou
 
 /* MD5 as the encoder/verify use it (host); exported for the shim and the tests */
 void flacb200_md5(const uint8_t* data, size_t len, uint8_t out[16]);
+/* The same sum for many buffers at once: eight streams advance in the lanes of one AVX2 register per host thread
+ * (csrc/md5_mb.h); threads = 0: all hardware threads.  digests: 16 bytes per buffer. */
+void flacb200_md5_many(const uint8_t* const* data, const size_t* len, size_t n, uint8_t* digests, unsigned threads);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* Whole-file batches over one or several GPUs: the file-level fan-out the reference does with rayon
+ * (examples/flac2wav.rs:31-38, examples/flac-split.rs:84-87) -- many independent streams, each one a complete
+ * FlacByteWriter / FlacSampleWriter run (Encoder::new .. finalize_inner, src/encode.rs:1882-2110) or FlacByteReader run.
+ *
+ * Tracks are dealt to the devices by size; every device has its own host thread and engine and works through its share
+ * in sub-batches (upload of sub-batch k + 1, kernels of k and download of k - 1 overlap).  The only cross-device step is
+ * on the host: per-track frame sizes are summed (an exclusive scan per track) to place each track's frames behind its
+ * metadata blocks in its own file image -- no collective, no device-to-device traffic.  The MD5 of
+ * every track is computed meanwhile on the remaining host threads (flacb200_md5_many); STREAMINFO (min/max frame size,
+ * total samples, MD5), SEEKTABLE and PADDING are then written as Encoder::finalize_inner would.
+ */
+/* The metadata blocks of a finished stream from its frame sizes -- Encoder::finalize_inner's bookkeeping (src/encode.rs:2024-2110:
+ * min/max frame size, total samples, MD5, seek points filtered by the table interval, placeholder table or a table carved from
+ * the padding) without a writer handle, for callers that encoded the frames of many streams in one batch.  frame_sizes NULL:
+ * the blocks as Encoder::new writes them (same length).  out NULL: only *len. */
+int flacb200_build_stream_header(const flacb200_writer_options* opt, uint32_t sample_rate, uint32_t bits_per_sample,
+                                 uint32_t channels, uint64_t total_pcm_frames, int total_known_at_open,
+                                 const uint32_t* frame_sizes, uint64_t n_frames, const uint8_t md5[16], uint8_t* out,
+                                 size_t capacity, size_t* len);
+
+typedef struct flacb200_track {
+    const void* pcm;            /* host memory (pinned memory uploads at full link speed); interleaved samples */
+    uint64_t n_pcm_frames;      /* inter-channel samples */
+    uint32_t sample_rate, bits_per_sample, channels;
+    int32_t pcm_kind;           /* FLACB200_PCM_BYTES_LE, _BYTES_BE or _I32_INTERLEAVED */
+} flacb200_track;
+
+typedef struct flacb200_file {
+    uint8_t* data;              /* in: NULL (the library allocates; release with flacb200_files_free) or a caller buffer */
+    size_t capacity;            /* in: size of the caller buffer (flacb200_encode_batch_bound says how much can be needed) */
+    size_t len;                 /* out: bytes of the complete .flac file */
+    int32_t status;             /* out: 0 or the error of this track (same codes as the writer calls) */
+    uint32_t frames;            /* out */
+    uint8_t md5[16];            /* out: the STREAMINFO signature */
+} flacb200_file;
+
+size_t flacb200_encode_batch_bound(const flacb200_track* track, const flacb200_writer_options* opt);
+/* devices: CUDA device ordinals (NULL / n_devices 0: device 0).  Returns 0 when every track was encoded (files[i].status
+ * all 0), else the first failing track's status. */
+int flacb200_encode_batch(const flacb200_track* tracks, size_t n_tracks, const flacb200_writer_options* opt,
+                          const int* devices, int n_devices, flacb200_file* files);
+void flacb200_files_free(flacb200_file* files, size_t n_files);
+
+typedef struct flacb200_pcm {
+    void* data;                 /* in: NULL (library allocates) or caller buffer; out: interleaved PCM */
+    size_t capacity;
+    size_t len;                 /* out: bytes */
+    int32_t status;             /* out: 0 or this stream's error (flac_codec::Error ordinal) */
+    int32_t verified;           /* out (when verify != 0): 0 MD5Match, 1 MD5Mismatch, 2 NoMD5 */
+    flacb200_streaminfo info;   /* out */
+} flacb200_pcm;
+
+/* flac2wav-style fan-out: decodes n complete .flac images.  pcm_kind: FLACB200_PCM_BYTES_LE / _BE / _I32_INTERLEAVED.
+ * verify != 0 also checks every stream's MD5 (verify_reader, src/decode.rs:1291). */
+int flacb200_decode_batch(const uint8_t* const* flac, const size_t* flac_len, size_t n_files, int pcm_kind, int verify,
+                          const int* devices, int n_devices, flacb200_pcm* out);
+void flacb200_pcm_free(flacb200_pcm* out, size_t n);
 
 #ifdef __cplusplus
 }
