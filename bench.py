@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1/C2/C3/C5 legs (tests/config_legs.py)")
+    ap.add_argument("--no-files", action="store_true", help="skip the e2e_files leg (flacb200_encode_batch)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     return ap.parse_args()
 
@@ -431,9 +432,43 @@ def run_gpu(args):
         d2h_gbs = min(out_cap, pcm_bytes) / (time.perf_counter() - t0) / 1e9
         eng.device_free(scratch_d)
 
+        # the link itself under the same load as the step: every rank uploads its PCM and downloads as many bytes as its
+        # frames take, both directions at once, all ranks at the same time (barrier-aligned) -- the roofline of `e2e`
+        def link_probe(nbytes_up, nbytes_down, reps=2):
+            import ctypes
+
+            up_h = torch.frombuffer((ctypes.c_uint8 * nbytes_up).from_address(h_pcm_p), dtype=torch.uint8)
+            dn_h = torch.frombuffer((ctypes.c_uint8 * nbytes_down).from_address(h_out_p), dtype=torch.uint8)
+            up_d = torch.empty(nbytes_up, dtype=torch.uint8, device="cuda")
+            dn_d = torch.empty(nbytes_down, dtype=torch.uint8, device="cuda")
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+            best = 1e30
+            for _ in range(reps + 1):
+                barrier()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s_up):
+                    up_d.copy_(up_h, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    dn_h.copy_(dn_d, non_blocking=True)
+                s_up.synchronize()
+                s_dn.synchronize()
+                dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                best = min(best, float(dt.item()))
+            del up_d, dn_d
+            return best
+
+        link_s = link_probe(pcm_bytes, int(flac_bytes))
+
+        from flac_codec_b200 import shard
+
         def e2e_step():
-            return eng.encode(opt, RATE, BPS, CH, h_pcm_p, pcm_bytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.HOST,
-                              out=h_out_p, out_capacity=out_cap, out_location=_abi.HOST, want_sizes=True)
+            r = eng.encode(opt, RATE, BPS, CH, h_pcm_p, pcm_bytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.HOST,
+                           out=h_out_p, out_capacity=out_cap, out_location=_abi.HOST, want_sizes=True)
+            if world > 1:   # the one cross-GPU step: host-side gather + scan of the frame sizes -> where this rank's frames go
+                shard.place(r[1], rank, world)
+            return r
 
         e2e_step()
         barrier()
@@ -448,7 +483,11 @@ def run_gpu(args):
         line["e2e"] = {"value": samples_per_step * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": int(pcm_bytes), "d2h_bytes_per_step": int(total + 4 * len(sizes)),
                        "ms_per_step": e2e_ms, "steps": args.e2e_steps, "pinned_copy_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs},
-                       "api": "flacb200_encode(host PCM -> host frames + frame sizes)"}
+                       "link": {"ms": link_s * 1e3, "aggregate_gbs": world * (pcm_bytes + flac_bytes) / link_s / 1e9,
+                                "what": "all ranks at once: pinned upload of the step's PCM and download of as many bytes as its frames, both directions concurrently"},
+                       "link_frac": link_s * 1e3 / e2e_ms,
+                       "api": "flacb200_encode(host PCM -> host frames + frame sizes)"
+                              + ("; + host-side gather/scan of the frame sizes over gloo (shard.place)" if world > 1 else "")}
         # decode, end to end: the frames just downloaded (pinned host memory) -> PCM in pinned host memory
         if not args.no_decode and "decode" in line:
             per_track = (n + 4095) // 4096
@@ -543,6 +582,46 @@ def run_gpu(args):
             line["parity_vs_cpu_port"] = {"frames_compared": frames, "byte_identical_frames": same, "identical_fraction": same / max(frames, 1),
                                           "fraction_of_workload_compared": frames / max(n_tracks * ((n + 4095) // 4096), 1),
                                           "size_delta": (gtotal - ref_total) / max(ref_total, 1)}
+    # ---- e2e_files: host PCM -> complete .flac files in host memory (fLaC, STREAMINFO with MD5, SEEKTABLE, PADDING, frames)
+    # for every track of the shard through flacb200_encode_batch; MD5 on the host threads beside the GPU ----
+    if not args.no_e2e and not args.no_files:
+        import ctypes
+        import hashlib
+
+        from flac_codec_b200.batch import encode_files
+
+        tb = n * bytes_per_pcm_frame
+        tracks = [((h_pcm_p + t * tb, tb), n, RATE, BPS, CH, _abi.PCM_BYTES_LE) for t in range(n_tracks)]
+        per_file = out_cap // n_tracks
+        bufs = [(h_out_p + t * per_file, per_file) for t in range(n_tracks)]
+        files = encode_files(tracks, opt, devices=[local], out_buffers=bufs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            files = encode_files(tracks, opt, devices=[local], out_buffers=bufs)
+        fdt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(fdt, op=dist.ReduceOp.MAX)
+        f_ms = float(fdt.item()) / args.e2e_steps * 1e3
+        ok = all(st == 0 for _, st, _ in files)
+        md5_ok = None
+        if rank == 0:   # the signatures against hashlib (a sample: 51.8 MB per track), the STREAMINFO copy against the result
+            h_pcm = np.ctypeslib.as_array((ctypes.c_uint8 * pcm_bytes).from_address(h_pcm_p))
+            md5_ok = all(hashlib.md5(h_pcm[t * tb:(t + 1) * tb].tobytes()).digest() == files[t][2] == bytes(files[t][0][26:42])
+                         for t in range(0, n_tracks, max(n_tracks // 8, 1)))
+        line["e2e_files"] = {"value": samples_per_step * world / (f_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": f_ms,
+                             "files_per_step": n_tracks * world, "all_ok": bool(ok), "md5_vs_hashlib_sample": md5_ok,
+                             "file_bytes_per_step": int(sum(len(f[0]) for f in files if f[0] is not None)),
+                             "api": "flacb200_encode_batch(host PCM tracks -> complete .flac images; MD5 by flacb200_md5_many on the host threads)"}
+        if world == 1 and rank == 0 and not args.no_cpu_baseline:   # whole files against the oracle's FlacByteWriter restatement
+            from oracle import oracle as fo
+
+            same = 0
+            for t in (0, n_tracks - 1):
+                x = fo.bytes_to_samples(h_pcm[t * tb:(t + 1) * tb].tobytes(), 3)
+                ref_file, _ = fo.encode_stream(fo.options("best"), RATE, BPS, CH, x, total_known=True, nthreads=os.cpu_count() or 1)
+                same += int(bytes(files[t][0]) == ref_file)
+            line["e2e_files"]["files_identical_to_cpu_port"] = f"{same} of 2 compared"
     if not args.no_e2e:
         L.flacb200_host_free(h_pcm_p)
         L.flacb200_host_free(h_out_p)

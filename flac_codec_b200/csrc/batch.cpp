@@ -327,7 +327,9 @@ int flacb200_encode_batch(const flacb200_track* tracks, size_t n_tracks, const f
             ptr.push_back(d);
         }
         std::vector<uint8_t> out(16 * which.size());
-        const unsigned threads = host_threads() > (unsigned)n_devices + 1 ? host_threads() - (unsigned)n_devices : 1;
+        // every hardware thread hashes: the device threads spend their time blocked in CUDA calls, and with eight streams per
+        // group a batch rarely has more groups than threads -- one thread short doubles the rounds
+        const unsigned threads = host_threads();
         flacb200::md5_many(ptr.data(), len.data(), which.size(), reinterpret_cast<uint8_t(*)[16]>(out.data()), threads);
         for (size_t i = 0; i < which.size(); i++) memcpy(digests.data() + 16 * which[i], out.data() + 16 * i, 16);
     });

@@ -102,7 +102,7 @@ __attribute__((target("avx2"))) void blocks_avx2(State st[8], const uint8_t* con
             M[half * 8 + 7] = _mm256_permute2x128_si256(u3, u7, 0x31);
         }
         __m256i a = A, b = B, c = C, d = D;
-        for (int i = 0; i < 64; i++) {
+        for (int i = 0; i < 64; i++) {   // (unrolling changes nothing: the step is one dependent chain a -> t -> rotate -> b)
             __m256i f;
             if (i < 16) f = _mm256_xor_si256(d, _mm256_and_si256(b, _mm256_xor_si256(c, d)));
             else if (i < 32) f = _mm256_xor_si256(c, _mm256_and_si256(d, _mm256_xor_si256(b, c)));

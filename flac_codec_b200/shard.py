@@ -3,8 +3,9 @@
 A frame depends on no other frame's samples (fixed block size, frame number = block index; src/encode.rs:2285),
 so work shards by whole tracks or by contiguous block ranges of one stream.  The only cross-rank step is the one
 the north star names: gather the per-rank compressed frame sizes, exclusive-scan them, and place every rank's
-frames at its base offset in the output stream.  `torch.distributed` (NCCL on the GPU box, gloo in the CPU
-tests) carries only those size vectors -- a few bytes per frame.
+frames at its base offset in the output stream.  That exchange is HOST-side: the size vectors (a few bytes per
+frame) travel between the rank processes over a gloo group (TCP/shared memory between host processes) -- never over
+NCCL, never through device memory.  (Inside ONE process the same scan is plain C++: flacb200_encode_batch, batch.cpp.)
 """
 from __future__ import annotations
 
@@ -56,8 +57,24 @@ class Placement:
         return out[:-1]
 
 
+_HOST_GROUP = None
+
+
+def host_group():
+    """The gloo process group the size exchange runs on.  When the job's default group is NCCL (one rank per GPU, as
+    bench.py sets it up) a second, host-only group is created once; a gloo default group is used as it is."""
+    global _HOST_GROUP
+    import torch.distributed as dist
+
+    if dist.get_backend() != "nccl":
+        return None
+    if _HOST_GROUP is None:
+        _HOST_GROUP = dist.new_group(backend="gloo")
+    return _HOST_GROUP
+
+
 def place(local_sizes: Sequence[int], rank: int = 0, world: int = 1, group=None) -> Placement:
-    """Gather + exclusive scan of per-rank frame sizes.  Ranks hold consecutive block ranges in rank order."""
+    """Gather + exclusive scan of per-rank frame sizes, on the host.  Ranks hold consecutive block ranges in rank order."""
     local = np.ascontiguousarray(local_sizes, dtype=np.uint32)
     if world == 1:
         parts = [local]
@@ -65,16 +82,19 @@ def place(local_sizes: Sequence[int], rank: int = 0, world: int = 1, group=None)
         import torch
         import torch.distributed as dist
 
-        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([local.size], dtype=torch.int64, device=dev), group=group)
+        if group is None:
+            group = host_group()
+        if dist.get_backend(group) == "nccl":
+            raise RuntimeError("shard.place exchanges frame sizes between host processes: pass a gloo group")
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([local.size], dtype=torch.int64), group=group)
         counts = [int(c.item()) for c in counts]
         width = max(max(counts), 1)
-        mine = torch.zeros(width, dtype=torch.int64, device=dev)
-        mine[: local.size] = torch.from_numpy(local.astype(np.int64)).to(dev)
-        allv = [torch.zeros(width, dtype=torch.int64, device=dev) for _ in range(world)]
+        mine = torch.zeros(width, dtype=torch.int32)
+        mine[: local.size] = torch.from_numpy(local.view(np.int32))
+        allv = [torch.zeros(width, dtype=torch.int32) for _ in range(world)]
         dist.all_gather(allv, mine, group=group)
-        parts = [allv[r][: counts[r]].cpu().numpy().astype(np.uint32) for r in range(world)]
+        parts = [allv[r][: counts[r]].numpy().view(np.uint32).copy() for r in range(world)]
     rank_bytes = [int(p.astype(np.int64).sum()) for p in parts]
     sizes = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint32)
     ok = sizes[(sizes != 0) & (sizes < (1 << 24) - 1)]     # STREAMINFO min/max rule (src/encode.rs:2413-2436)
