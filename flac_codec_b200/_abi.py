@@ -115,6 +115,7 @@ class Pcm(C.Structure):
 
 
 NEED_DATA = -10
+NEED_SEEK = -11
 
 EXPORTS = [
     "flacb200_writer_options_default", "flacb200_writer_options_fast", "flacb200_writer_options_best", "flacb200_writer_open",
@@ -123,7 +124,7 @@ EXPORTS = [
     "flacb200_writer_flush", "flacb200_writer_finalize", "flacb200_writer_get_stats", "flacb200_read_streaminfo",
     "flacb200_reader_open", "flacb200_reader_close", "flacb200_reader_info", "flacb200_reader_seektable", "flacb200_reader_read",
     "flacb200_reader_seek", "flacb200_reader_verify", "flacb200_md5", "flacb200_md5_batch",
-    "flacb200_reader_open_stream", "flacb200_reader_feed", "flacb200_reader_set_window", "flacb200_reader_fill_buf",
+    "flacb200_reader_open_stream", "flacb200_reader_feed", "flacb200_reader_set_seekable", "flacb200_reader_wanted_offset", "flacb200_reader_set_window", "flacb200_reader_fill_buf",
     "flacb200_reader_consume", "flacb200_reader_fill_channels", "flacb200_reader_consume_channels", "flacb200_stream_write",
     "flacb200_stream_reader_open", "flacb200_stream_reader_close", "flacb200_stream_reader_feed", "flacb200_stream_reader_read",
     "flacb200_decode_last_frames", "flacb200_md5_many", "flacb200_encode_batch_bound", "flacb200_encode_batch", "flacb200_files_free",
@@ -221,6 +222,8 @@ def lib():
     L.flacb200_reader_verify.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint8 * 16)]
     L.flacb200_reader_open_stream.argtypes = [vp, C.POINTER(vp)]
     L.flacb200_reader_feed.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    L.flacb200_reader_set_seekable.argtypes = [vp, C.c_int]
+    L.flacb200_reader_wanted_offset.argtypes = [vp, u64p]
     L.flacb200_reader_set_window.argtypes = [vp, C.c_size_t, C.c_uint64]
     i32p = C.POINTER(C.c_int32)
     L.flacb200_reader_fill_buf.argtypes = [vp, C.POINTER(i32p), szp]

@@ -687,6 +687,9 @@ struct flacb200_reader {
     uint32_t cur_off = 0;             // inter-channel samples of it already consumed
     bool at_end = false;
     int sticky_error = 0;
+    bool seekable_source = false;     // feed mode over an `R: Read + Seek`: a seek asks the caller to reposition its source
+    bool seeking = false;             // flacb200_reader_seek in progress (NEED_SEEK / NEED_DATA in between)
+    uint64_t seek_sample = 0, seek_pos = 0, want_offset = 0;
     bool verifying = false;           // flacb200_reader_verify in progress (a fed reader returns FLACB200_NEED_DATA in between)
     Md5 verify_md5;
     std::vector<int32_t> planar;      // FlacChannelReader view of the current frame
@@ -1137,16 +1140,52 @@ int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm
 int flacb200_reader_seek(flacb200_reader* r, uint64_t pcm_frame)
 {
     if (!r) return FLACB200_E_BAD_ARGUMENT;
-    if (r->fed_mode) return E_IO;   // a plain `R: Read` source is not seekable (frames_start: None -> ErrorKind::NotSeekable)
-    uint64_t pos = reader_seek_point(*r, pcm_frame);
-    while (pcm_frame > pos) {
-        const int rc = reader_current_frame(*r, r->win_kind);
-        if (rc) return rc;
-        if (r->cur >= r->frames.size()) return E_INVALID_SEEK;
-        const uint64_t take = std::min<uint64_t>(r->frames[r->cur].block_size - r->cur_off, pcm_frame - pos);
-        r->cur_off += (uint32_t)take;
-        pos += take;
+    if (r->fed_mode && !r->seekable_source) return E_IO;   // a plain `R: Read` is not seekable (frames_start: None -> NotSeekable)
+    if (r->fed_mode) {
+        const int rm = reader_ensure_meta(*r);
+        if (rm) return rm;
     }
+    if (!(r->seeking && r->seek_sample == pcm_frame)) {
+        r->seek_pos = reader_seek_point(*r, pcm_frame);
+        r->seek_sample = pcm_frame;
+        r->seeking = true;
+        if (r->fed_mode) {   // the buffered bytes belong to another place in the file: the caller repositions its source
+            r->fed.clear();
+            r->fed_base = r->next_byte;
+            r->fed_eof = false;
+            r->want_offset = r->next_byte;
+            return FLACB200_NEED_SEEK;
+        }
+    }
+    while (pcm_frame > r->seek_pos) {
+        const int rc = reader_current_frame(*r, r->win_kind);
+        if (rc) {
+            if (rc != FLACB200_NEED_DATA) r->seeking = false;
+            return rc;
+        }
+        if (r->cur >= r->frames.size()) {
+            r->seeking = false;
+            return E_INVALID_SEEK;
+        }
+        const uint64_t take = std::min<uint64_t>(r->frames[r->cur].block_size - r->cur_off, pcm_frame - r->seek_pos);
+        r->cur_off += (uint32_t)take;
+        r->seek_pos += take;
+    }
+    r->seeking = false;
+    return 0;
+}
+
+int flacb200_reader_set_seekable(flacb200_reader* r, int seekable)
+{
+    if (!r) return FLACB200_E_BAD_ARGUMENT;
+    r->seekable_source = seekable != 0;
+    return 0;
+}
+
+int flacb200_reader_wanted_offset(flacb200_reader* r, uint64_t* offset)
+{
+    if (!r || !offset) return FLACB200_E_BAD_ARGUMENT;
+    *offset = r->want_offset;
     return 0;
 }
 
@@ -1160,7 +1199,8 @@ int flacb200_reader_verify(flacb200_reader* r, int* result, uint8_t md5_out[16])
     }
     if (!r->verifying) {
         if (!r->fed_mode) reader_seek_point(*r, 0);   // the whole stream, wherever the reads have got to
-        else if (r->decoded_samples || r->next_byte != r->si.frames_start) return FLACB200_E_BAD_ARGUMENT;   // a fed stream cannot rewind
+        else if (r->decoded_samples || r->next_byte != r->si.frames_start || r->cur < r->frames.size())
+            return FLACB200_E_BAD_ARGUMENT;   // a fed stream is verified from its start (seek to 0 first when the source can)
         r->verify_md5 = Md5();
         r->verifying = true;
     }

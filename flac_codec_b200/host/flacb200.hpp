@@ -202,13 +202,16 @@ private:
 
 enum class Verified { MD5Match, MD5Mismatch, NoMD5 };
 
-// FlacSampleReader<R> / FlacByteReader<R, E> (src/decode.rs:103-620): the stream is drained at construction
+// FlacSampleReader<R> / FlacByteReader<R, E> / FlacChannelReader<R> (src/decode.rs:103-1065) over a std::istream: the handle
+// is FED from the stream chunk by chunk as its decode windows ask for bytes (FLACB200_NEED_DATA) and repositions a seekable
+// stream when a seek asks for it (FLACB200_NEED_SEEK) -- the file is never held in memory.
 class FlacReader {
 public:
-    FlacReader(std::istream& r, Engine& eng) : image_(std::istreambuf_iterator<char>(r), std::istreambuf_iterator<char>())
+    FlacReader(std::istream& r, Engine& eng, bool seekable = true) : in_(r), chunk_(1 << 20)
     {
-        check(flacb200_reader_open(eng.get(), reinterpret_cast<const uint8_t*>(image_.data()), image_.size(), &h_), "FlacReader::new");
-        check(flacb200_reader_info(h_, &si_), "reader_info");
+        check(flacb200_reader_open_stream(eng.get(), &h_), "FlacReader::new");
+        if (seekable) check(flacb200_reader_set_seekable(h_, 1), "set_seekable");
+        call([&] { return flacb200_reader_info(h_, &si_); }, "BlockList::read");
     }
     ~FlacReader() { flacb200_reader_close(h_); }
     FlacReader(const FlacReader&) = delete;
@@ -222,27 +225,125 @@ public:
     size_t read(int32_t* samples, size_t n)   // FlacSampleReader::read
     {
         size_t got = 0;
-        check(flacb200_reader_read(h_, samples, n, FLACB200_PCM_I32_INTERLEAVED, &got), "FlacSampleReader::read");
+        call([&] { return flacb200_reader_read(h_, samples, n, FLACB200_PCM_I32_INTERLEAVED, &got); }, "FlacSampleReader::read");
         return got;
     }
     size_t read_bytes(uint8_t* buf, size_t n, bool big_endian = false)   // FlacByteReader::read
     {
         size_t got = 0;
-        check(flacb200_reader_read(h_, buf, n, big_endian ? FLACB200_PCM_BYTES_BE : FLACB200_PCM_BYTES_LE, &got), "FlacByteReader::read");
+        call([&] { return flacb200_reader_read(h_, buf, n, big_endian ? FLACB200_PCM_BYTES_BE : FLACB200_PCM_BYTES_LE, &got); }, "FlacByteReader::read");
         return got;
     }
-    void seek(uint64_t sample) { check(flacb200_reader_seek(h_, sample), "seek"); }
+    // FlacSampleReader::fill_buf / consume (:466-492): the unconsumed interleaved samples of the current frame
+    std::pair<const int32_t*, size_t> fill_buf()
+    {
+        const int32_t* p = nullptr;
+        size_t n = 0;
+        call([&] { return flacb200_reader_fill_buf(h_, &p, &n); }, "fill_buf");
+        return {p, n};
+    }
+    void consume(size_t n_samples) { check(flacb200_reader_consume(h_, n_samples), "consume"); }
+    // FlacChannelReader::fill_buf / consume (:917-949): one pointer per channel, n samples each
+    std::pair<const int32_t* const*, size_t> fill_channels()
+    {
+        const int32_t* const* pp = nullptr;
+        size_t n = 0;
+        call([&] { return flacb200_reader_fill_channels(h_, &pp, &n); }, "FlacChannelReader::fill_buf");
+        return {pp, n};
+    }
+    void consume_channels(size_t n_per_channel) { check(flacb200_reader_consume_channels(h_, n_per_channel), "consume"); }
+    void seek(uint64_t sample) { call([&] { return flacb200_reader_seek(h_, sample); }, "seek"); }
     Verified verify()
     {
         int res = 0;
-        check(flacb200_reader_verify(h_, &res, nullptr), "verify");
+        call([&] { return flacb200_reader_verify(h_, &res, nullptr); }, "verify");
         return res == 0 ? Verified::MD5Match : res == 1 ? Verified::MD5Mismatch : Verified::NoMD5;
     }
 
 private:
-    std::string image_;
+    template <class F>
+    void call(F f, const char* what)
+    {
+        for (;;) {
+            const int rc = f();
+            if (rc == FLACB200_NEED_DATA) {
+                if (eof_) throw Error(1, what);   // Io: the stream ended inside a frame
+                in_.read(chunk_.data(), (std::streamsize)chunk_.size());
+                const size_t n = (size_t)in_.gcount();
+                eof_ = n == 0;
+                check(flacb200_reader_feed(h_, reinterpret_cast<const uint8_t*>(chunk_.data()), n, eof_), "feed");
+            } else if (rc == FLACB200_NEED_SEEK) {
+                uint64_t off = 0;
+                check(flacb200_reader_wanted_offset(h_, &off), "wanted_offset");
+                in_.clear();
+                in_.seekg((std::streamoff)off);
+                eof_ = false;
+            } else {
+                check(rc, what);
+                return;
+            }
+        }
+    }
+    std::istream& in_;
+    std::vector<char> chunk_;
+    bool eof_ = false;
     flacb200_reader* h_ = nullptr;
     flacb200_streaminfo si_{};
+};
+
+// FlacStreamWriter<W> (src/encode.rs:1063-1290): one subset frame per call, parameters in every header
+class FlacStreamWriter {
+public:
+    FlacStreamWriter(std::ostream& w, Engine& eng, const Options& o) : w_(w), eng_(eng), o_(o) {}
+    void write(uint32_t sample_rate, uint8_t channels, uint32_t bits_per_sample, const int32_t* samples, size_t n_samples)
+    {
+        buf_.resize(n_samples * 5 + 1024);
+        size_t n = 0;
+        check(flacb200_stream_write(eng_.get(), &o_.o.frame, sample_rate, channels, bits_per_sample, samples, n_samples, frame_number_, buf_.data(),
+                                    buf_.size(), &n), "FlacStreamWriter::write");
+        if (n) {
+            frame_number_++;
+            w_.write(reinterpret_cast<const char*>(buf_.data()), (std::streamsize)n);
+        }
+    }
+
+private:
+    std::ostream& w_;
+    Engine& eng_;
+    Options o_;
+    uint64_t frame_number_ = 0;
+    std::vector<uint8_t> buf_;
+};
+
+// FlacStreamReader<R> (src/decode.rs:1149-1268): read() returns the next frame with the parameters of its own header
+class FlacStreamReader {
+public:
+    FlacStreamReader(std::istream& r, Engine& eng) : in_(r), chunk_(1 << 20) { check(flacb200_stream_reader_open(eng.get(), &h_), "FlacStreamReader::new"); }
+    ~FlacStreamReader() { flacb200_stream_reader_close(h_); }
+    FlacStreamReader(const FlacStreamReader&) = delete;
+    FlacStreamReader& operator=(const FlacStreamReader&) = delete;
+    flacb200_framebuf read()
+    {
+        flacb200_framebuf fb{};
+        for (;;) {
+            const int rc = flacb200_stream_reader_read(h_, &fb);
+            if (rc != FLACB200_NEED_DATA) {
+                check(rc, "FlacStreamReader::read");
+                return fb;
+            }
+            if (eof_) throw Error(1, "eof looking for frame sync");
+            in_.read(chunk_.data(), (std::streamsize)chunk_.size());
+            const size_t n = (size_t)in_.gcount();
+            eof_ = n == 0;
+            check(flacb200_stream_reader_feed(h_, reinterpret_cast<const uint8_t*>(chunk_.data()), n, eof_), "feed");
+        }
+    }
+
+private:
+    std::istream& in_;
+    std::vector<char> chunk_;
+    bool eof_ = false;
+    flacb200_stream_reader* h_ = nullptr;
 };
 
 }   // namespace flacb200

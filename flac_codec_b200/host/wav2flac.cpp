@@ -29,8 +29,10 @@ int encode(const flacb200::Options& opt, const char* in, const char* out)
         if (!f) { std::cerr << "no data chunk\n"; return 2; }
         const uint32_t len = le32(ch + 4);
         if (!memcmp(ch, "fmt ", 4)) {
+            if (len < 16 || len > 4096) { std::cerr << "bad fmt chunk\n"; return 2; }   // WAVEFORMAT is 16 bytes, EXTENSIBLE 40
             std::vector<uint8_t> fmt(len);
             f.read((char*)fmt.data(), len);
+            if ((uint32_t)f.gcount() != len) { std::cerr << "short fmt chunk\n"; return 2; }
             const uint16_t tag = le16(fmt.data());
             if (tag != 1 && tag != 0xFFFE) { std::cerr << "not PCM\n"; return 2; }
             channels = le16(fmt.data() + 2);
@@ -44,6 +46,7 @@ int encode(const flacb200::Options& opt, const char* in, const char* out)
             f.ignore(len + (len & 1));
         }
     }
+    if (channels < 1 || channels > 8 || bps < 1 || bps > 32) { std::cerr << "unsupported channel count / sample width\n"; return 2; }
     flacb200::Engine eng(0);
     std::ofstream o(out, std::ios::binary | std::ios::trunc);
     flacb200::FlacByteWriter w(o, eng, opt, rate, bps, (uint8_t)channels, data_len);

@@ -230,7 +230,7 @@ class _Reader:
     chunks of `chunk` bytes as the decoder asks for them, and the reader cannot seek."""
 
     def __init__(self, reader, *, engine: Optional[Engine] = None, streaming: bool = False, chunk: int = 1 << 20,
-                 window_bytes: int = 0, window_pcm_frames: int = 0):
+                 window_bytes: int = 0, window_pcm_frames: int = 0, seekable: bool = False):
         self._L = _abi.lib()
         self._engine = engine if engine is not None else default_engine()
         self._h = C.c_void_p()
@@ -238,6 +238,8 @@ class _Reader:
         if streaming:
             self._src = io.BytesIO(bytes(reader)) if isinstance(reader, (bytes, bytearray, memoryview)) else reader
             check(self._L.flacb200_reader_open_stream(self._engine._h, C.byref(self._h)), "FlacReader::new")
+            if seekable:   # new_seekable over a source that stays on disk: seeks reposition the source, nothing is held
+                check(self._L.flacb200_reader_set_seekable(self._h, 1), "set_seekable")
         else:
             data = reader if isinstance(reader, (bytes, bytearray, memoryview)) else reader.read()
             self._image = np.frombuffer(bytes(data), dtype=np.uint8)   # kept alive: the handle borrows it
@@ -252,6 +254,12 @@ class _Reader:
         """Runs one handle call; in streaming mode FLACB200_NEED_DATA is answered by feeding the next chunk of the source."""
         while True:
             rc = fn()
+            if rc == _abi.NEED_SEEK:
+                off = C.c_uint64(0)
+                check(self._L.flacb200_reader_wanted_offset(self._h, C.byref(off)), "wanted_offset")
+                self._src.seek(off.value)
+                self._eof = False
+                continue
             if rc != _abi.NEED_DATA:
                 check(rc, what)
                 return

@@ -116,6 +116,10 @@ typedef struct flacb200_reader flacb200_reader;
 /* Returned by the reader calls in feed mode when the bytes buffered so far hold no complete frame (or not yet all
  * metadata blocks): feed more and call again.  Not an error of the stream. */
 #define FLACB200_NEED_DATA (-10)
+/* Returned by flacb200_reader_seek on a fed reader whose source can seek (flacb200_reader_set_seekable): reposition the
+ * source to the absolute file offset flacb200_reader_wanted_offset reports, then call flacb200_reader_seek again with the
+ * same sample and keep feeding from there. */
+#define FLACB200_NEED_SEEK (-11)
 
 /* The reader is the reference's Decoder (src/decode.rs:1311-1491) behind FlacByteReader / FlacSampleReader /
  * FlacChannelReader.  It decodes WINDOW by window: a run of bytes that starts at a frame boundary goes through one
@@ -154,6 +158,9 @@ int flacb200_reader_consume_channels(flacb200_reader* r, size_t n_per_channel);
  * (:1452-1491) repositions to the last SEEKTABLE point at or before the sample (the first frame without a table) and the
  * frames up to the sample are decoded and skipped.  pcm_frame: inter-channel samples; beyond the end -> InvalidSeek. */
 int flacb200_reader_seek(flacb200_reader* r, uint64_t pcm_frame);
+/* feed mode over an `R: Read + Seek` (new_seekable without holding the file in memory): see FLACB200_NEED_SEEK */
+int flacb200_reader_set_seekable(flacb200_reader* r, int seekable);
+int flacb200_reader_wanted_offset(flacb200_reader* r, uint64_t* offset);
 /* verify_reader (src/decode.rs:1291-1309): decode from the current position to the end, MD5 of the little-endian PCM against
  * STREAMINFO.  *result: 0 MD5Match, 1 MD5Mismatch, 2 NoMD5 (all-zero sum stored) */
 int flacb200_reader_verify(flacb200_reader* r, int* result, uint8_t md5_out[16]);

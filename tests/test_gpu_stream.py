@@ -448,3 +448,19 @@ def test_stream_reader_takes_its_parameters_from_the_frames(fo, st):
     b, *_ = r.read()
     assert np.array_equal(a.reshape(-1, 2), blocks[0][:500]) and np.array_equal(b.reshape(-1, 2), blocks[0][500:800])
     r.close()
+
+
+def test_fed_reader_over_a_seekable_source_holds_nothing(fo, st):
+    """new_seekable without a file image: the handle asks the caller to reposition its source (FLACB200_NEED_SEEK) and is fed
+    from the seek point on."""
+    x, flac, _ = _long_stream(fo, seconds=35)
+    total = x.size // 2
+    src = io.BytesIO(flac)
+    r = st.FlacSampleReader(src, streaming=True, seekable=True, chunk=50000, window_bytes=1 << 16)
+    pts = [p for p in r.seektable() if not p[3]]
+    for pos in (pts[2][0] + 5000, 17, pts[1][0], total - 3, 0):
+        r.seek(pos)
+        assert np.array_equal(r.read(5000), x[pos * 2:pos * 2 + 5000]), pos
+    r.seek(0)
+    assert r.verify()[0] == "MD5Match"
+    r.close()
