@@ -19,6 +19,8 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "frame_decide.cuh"
+#include "pack_bits.cuh"
 #include "tiles.cuh"
 #include "rice.cuh"
 
@@ -43,6 +45,7 @@ struct A3Cand {   // per candidate, shared by its warps
     unsigned long long bits_f, bits_l;
     uint32_t mask, ovf, bad16, bad_f, bad_l;
     uint32_t fo, lpc_ok;               // decisions of the first warp, read by the second
+    uint32_t round_bits[2][8];         // pass 2: code bits per round of 32 tiles, [fixed | LPC] (k_frame4 places its warps with them)
 };
 
 __device__ inline void a3_pair_sync(uint32_t cand)
@@ -204,7 +207,8 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
         }
         for (uint32_t rd = wsub; rd < rounds; rd += A3_WPC) {
             const uint32_t t = rd * 32 + lane, i0 = t * 16;
-            if (i0 >= n) continue;
+            const unsigned long long rb_f0 = bits_f, rb_l0 = bits_l;
+            if (i0 < n) {
             const bool tail = i0 + 16 > n;   // tile cut by the block end: rare, sample-by-sample path
             const bool fir = lpc_ok && (stage < 2 || !use16);
             int32_t x[16], h[16];
@@ -405,6 +409,14 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                         bits_l += tb;
                         bad_l |= tbad;
                     }
+                }
+            }
+            }
+            if (stage == 2 && rd < 8) {   // (all lanes of the warp are here: the body above is a plain `if`)
+                const uint32_t rf_ = __reduce_add_sync(0xffffffffu, (uint32_t)(bits_f - rb_f0)), rl_ = __reduce_add_sync(0xffffffffu, (uint32_t)(bits_l - rb_l0));
+                if (lane == 0) {
+                    sm.round_bits[0][rd] = rf_;
+                    sm.round_bits[1][rd] = rl_;
                 }
             }
         }
@@ -608,6 +620,511 @@ cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uin
         }
     }
 #undef FLACB200_A3
+    return cudaGetLastError();
+}
+
+
+// =====================================================================================================================
+// k_frame4: encode_frame (src/encode.rs:2259-2439) for one stereo frame in ONE CTA -- analysis, decision and packing.
+//
+// k_analyze3 + k_decide + k_scan + k_pack3 in one kernel: the unpacked planes and the int16 copy of the LPC residuals stay
+// in shared memory from the analysis through the packing, so the packer neither unpacks the PCM again nor runs the FIR a
+// second time (k_pack3 spent a quarter of its instructions on those), and every warp of the CTA packs: the four warps of a
+// subframe first add up the code lengths of their rounds, then emit at the bit positions that follow from the round totals.
+//   1. planes (as k_analyze3), then a3_candidate for L, R, M, S: two warps each; the winning encodings land in shared memory
+//   2. thread 0: channel assignment, frame header, CRC-8, subframe bit offsets, frame size (decide_frame)
+//   3. the frame's size is published for the frames behind it (decoupled look-back: one 64-bit word per frame holding a flag
+//      and either the frame's own size or the inclusive prefix of all sizes up to it)
+//   4. bit image in shared memory -- on top of the analysis scratch, which is dead by now --, CRC-16 folded over it
+//   5. warp 0 resolves the frame's byte offset: it sums the sizes of the frames in front of it that are still in flight
+//      until it meets one that knows its prefix (CTAs start in index order, so every predecessor is running or done)
+//   6. coalesced copy-out
+// =====================================================================================================================
+enum : unsigned long long { F4_FLAG_SIZE = 1ull << 62, F4_FLAG_PREFIX = 2ull << 62, F4_VALUE = (1ull << 62) - 1 };
+
+struct F4Static {
+    Crc16Fold tabs;
+    CandRec cr[4];
+    FrameRec fr;
+    unsigned long long abs4[4];
+    unsigned long long out_off;
+    uint32_t bad16[4];
+    uint32_t round_bits[2][8];   // per subframe: bits of every round of its residual block, partition headers included
+    uint32_t crc_part[8];
+    uint32_t placed;             // the look-back has succeeded
+};
+
+// sample i of candidate `slot` (0 L, 1 R, 2 mid, 3 side) from the tile-transposed planes
+__device__ inline int32_t f4_sample(const int32_t* __restrict__ planes, uint32_t slot, uint32_t i)
+{
+    const uint32_t w = a3_tile_base(i >> 4) + ((i >> 2) & 3u) * 128u + (i & 3u);
+    const int32_t a = planes[w], b = planes[A3_PLANE + w];
+    return slot == 0 ? a : slot == 1 ? b : slot == 2 ? (a + b) >> 1 : a - b;
+}
+
+// the LPC residuals of tile t recomputed from the planes (only for a subframe whose residuals did not fit the int16 copy)
+template <int HB>
+static __device__ __noinline__ void f4_fir_tile(const int32_t* __restrict__ planes, uint32_t slot, uint32_t t, const int16_t* __restrict__ qc,
+                                                uint32_t order, uint32_t shift, uint32_t wasted, int32_t* __restrict__ r)
+{
+    int32_t x[16], h[16], q[HB];
+#pragma unroll
+    for (int j = 0; j < HB; j++) q[j] = (uint32_t)j < order ? (int32_t)qc[j] : 0;
+    a3_tile<true>(planes, slot, t, 0, x);
+#pragma unroll
+    for (int e = 0; e < 16; e++) h[e] = 0;
+    if (t > 0) a3_tile<true>(planes, slot, t - 1, 4 - HB / 4, h);
+#pragma unroll
+    for (int e = 0; e < 16; e++) { x[e] >>= wasted; h[e] >>= wasted; }
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        long long sum = 0;
+#pragma unroll
+        for (int j = 0; j < HB; j++) sum = mad_wide_s32(e - 1 - j >= 0 ? x[e - 1 - j >= 0 ? e - 1 - j : 0] : h[16 + e - 1 - j >= 0 ? 16 + e - 1 - j : 0], q[j], sum);
+        r[e] = (int32_t)((uint32_t)x[e] - (uint32_t)(unsigned long long)(sum >> shift));
+    }
+}
+
+// One round (32 tiles, one per lane) of a subframe's residual block: residuals, code lengths, and -- EMIT -- the codes at
+// the bit positions that start at `base`.  Returns the round's bit total (all lanes).
+template <int HB, bool EMIT>
+__device__ inline uint32_t f4_round(const int32_t* __restrict__ planes, const uint4* __restrict__ res16, uint32_t slot, const CandRec& cr, bool use16,
+                                    uint32_t n, uint32_t rd, uint32_t words_sa, uint32_t base)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wasted = cr.wasted, order = cr.order;
+    const bool lpc = cr.type == 3;
+    const uint32_t cp = n >> cr.porder_g, j0 = (1u << cr.porder_g) - cr.nparts;
+    const bool cp16 = (cp & 15u) == 0;
+    const UDiv dcp = udiv_make(cp);
+    const uint32_t hb = cr.method ? 5u : 4u, escape_code = cr.method ? 31u : 15u;
+    const uint32_t t = rd * 32 + lane, i0 = t * 16;
+    const bool live = i0 < n;
+    int32_t r[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) r[e] = 0;
+    if (live) {
+        if (lpc) {
+            if (use16) {   // the int16 copy k_analyze's first pass parked (two 16-byte chunks per tile)
+                const uint4 lo4 = res16[(rd * 2 + 0) * 32 + lane], hi4 = res16[(rd * 2 + 1) * 32 + lane];
+                const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    r[2 * k] = (int32_t)(w[k] << 16) >> 16;
+                    r[2 * k + 1] = (int32_t)w[k] >> 16;
+                }
+            } else {
+                int32_t tmp[16];
+                f4_fir_tile<HB>(planes, slot, t, cr.q, order, cr.shift, wasted, tmp);
+#pragma unroll
+                for (int e = 0; e < 16; e++) r[e] = tmp[e];
+            }
+        } else {   // fixed differences (:3039-3060) from the planes
+            int32_t x[16], h[16];
+            a3_tile<true>(planes, slot, t, 0, x);
+#pragma unroll
+            for (int e = 0; e < 16; e++) h[e] = 0;
+            if (t > 0) a3_tile<true>(planes, slot, t - 1, 3, h);
+            int32_t x1 = h[15] >> wasted, x2 = h[14] >> wasted, x3 = h[13] >> wasted, x4 = h[12] >> wasted;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int32_t x0 = x[e] >> wasted;
+                r[e] = order == 0 ? x0 : order == 1 ? x0 - x1 : order == 2 ? x0 - 2 * x1 + x2 : order == 3 ? x0 - 3 * x1 + 3 * x2 - x3
+                                                                                                           : x0 - 4 * x1 + 6 * x2 - 4 * x3 + x4;
+                x4 = x3; x3 = x2; x2 = x1; x1 = x0;
+            }
+        }
+    }
+    // ---- code lengths of this lane's tile (as k_pack3) ----
+    const uint32_t lo_i = max(i0, order), hi_i = min(i0 + 16u, n);   // residuals exist for [lo_i, hi_i)
+    const uint32_t pj = live ? udiv(i0, dcp) : 0u;
+    const bool uniform = live && (i0 >= order || (i0 == 0 && order <= 16)) && i0 + 16 <= n && (cp16 || udiv(i0 + 15, dcp) == pj);
+    const uint32_t cc0 = cr.rice[live ? min(pj - j0, (uint32_t)MAX_PARTS - 1) : 0u];
+    const uint32_t first_res = max(pj * cp, order);
+    const uint32_t skip = first_res > i0 ? min(first_res - i0, 16u) : 0u;
+    const bool hdr_here = first_res >= i0 && first_res < i0 + 16;
+    uint32_t tsum = 0;
+    uint32_t len[16];
+    if (uniform && cc0 < 0x40) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            len[e] = (uint32_t)e >= skip ? (zigzag32(r[e]) >> cc0) + 1u + cc0 : 0u;
+            tsum += len[e];
+        }
+        if (hdr_here) tsum += hb;
+    } else if (live) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const uint32_t i = i0 + e;
+            uint32_t l = 0;
+            if (i >= lo_i && i < hi_i) {
+                const uint32_t p = udiv(i, dcp);
+                const uint32_t cc = cr.rice[p - j0];
+                if (cc < 0x40) l = (zigzag32(r[e]) >> cc) + 1u + cc;
+                else if (cc & 0x40) l = cc & 31u;
+                if (i == max(p * cp, order)) l += (cc < 0x40) ? hb : hb + 5u;
+            }
+            len[e] = l;
+            tsum += l;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; e++) len[e] = 0;
+    }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += up;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!EMIT) return total;
+    uint32_t p = base + incl - tsum;
+    if (uniform && cc0 < 0x40) {
+        if (hdr_here) {
+            p3_put(words_sa, p, hb, cc0);
+            p += hb;
+        }
+        const uint32_t stop = 1u << cc0, mask = stop - 1u;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const uint32_t u = zigzag32(r[e]);
+            p3_put(words_sa, p + ((uint32_t)e >= skip ? u >> cc0 : 0u), cc0 + 1u, (uint32_t)e >= skip ? stop | (u & mask) : 0u);
+            p += len[e];
+        }
+    } else if (live) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const uint32_t i = i0 + e;
+            if (i < lo_i || i >= hi_i) continue;
+            const uint32_t pi = udiv(i, dcp);
+            const uint32_t cc = cr.rice[pi - j0];
+            uint32_t at = p;
+            if (i == max(pi * cp, order)) {
+                if (cc < 0x40) { p3_put(words_sa, at, hb, cc); at += hb; }
+                else { p3_put(words_sa, at, hb, escape_code); p3_put_masked(words_sa, at + hb, 5, (cc & 0x40) ? (cc & 31u) : 0u); at += hb + 5; }
+            }
+            if (cc < 0x40) {
+                const uint32_t u = zigzag32(r[e]);
+                p3_put(words_sa, at + (u >> cc), cc + 1u, (1u << cc) | (u & ((1u << cc) - 1u)));
+            } else if (cc & 0x40) {
+                p3_put_masked(words_sa, at, cc & 31u, (uint32_t)r[e]);   // escaped: raw two's complement (:3857)
+            }
+            p += len[e];
+        }
+    }
+    return total;
+}
+
+// Decoupled look-back (one warp): the byte offset of frame f = base + the sizes of all frames in front of it.  Every frame
+// publishes its size as soon as it is known and its inclusive prefix as soon as its own look-back has succeeded; the walk
+// goes back over published sizes until it meets a prefix.  spin = false: give up when a word that is needed has not been
+// published yet (the caller tries again later -- and publishes its prefix at the first success, so resolution spreads
+// forward while everybody is still packing).  Frames start in index order, so a spinning caller always makes progress.
+__device__ inline bool f4_lookback(unsigned long long* state, uint32_t f, const unsigned long long* __restrict__ base_in, bool spin,
+                                   unsigned long long* excl_out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if (f == 0) {
+        *excl_out = *base_in;
+        return true;
+    }
+    // 128 predecessors per step: lane l looks at the four frames at distances 4 l + 1 .. 4 l + 4 (nearest first) -- a whole
+    // wave of resident CTAs is covered in two or three steps instead of ten
+    unsigned long long excl = 0;
+    long long i = (long long)f - 1;   // nearest frame not yet accounted for
+    for (;;) {
+        unsigned long long mine;      // sizes of this lane's frames in front of its first prefix (that prefix included)
+        uint32_t have, stop;
+        bool found;
+        for (;;) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const long long idx = i - (long long)(4 * lane + k);
+                v[k] = idx >= 0 ? *reinterpret_cast<volatile unsigned long long*>(state + idx) : F4_FLAG_PREFIX;   // (in front of frame 0: nothing)
+            }
+            mine = 0;
+            found = false;
+            bool missing = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t fl = (uint32_t)(v[k] >> 62);
+                if (!found) {
+                    if (fl == 0) missing = true;
+                    else mine += v[k] & F4_VALUE;
+                    if (fl == 2) found = true;
+                }
+            }
+            have = __ballot_sync(0xffffffffu, found);
+            stop = have ? (uint32_t)__ffs((int)have) - 1u : 32u;   // nearest lane that holds a prefix
+            if (!__any_sync(0xffffffffu, lane <= stop && missing)) break;
+            if (!spin) return false;
+        }
+        excl += warp_sum_u64(lane <= stop ? mine : 0ull);
+        if (have) break;   // (the virtual frames in front of frame 0 carry the prefix flag with value 0: frame 0's own word is a prefix)
+        i -= 128;
+    }
+    *excl_out = excl;
+    return true;
+}
+
+// grid = frames of the launch group, block = 256 (4 candidates x 2 warps).  state: one word per frame, zeroed before the
+// launch; base_in / total_out: running byte total of the call before / after this launch group.
+template <int HB>
+__global__ void __launch_bounds__(256, 2)
+    k_frame4(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm, const LpcRec* __restrict__ lpcs,
+             CandRec* __restrict__ cands_out, FrameRec* __restrict__ frecs_out, unsigned long long* __restrict__ abssum, unsigned long long* state,
+             const unsigned long long* __restrict__ base_in, unsigned long long* __restrict__ total_out, unsigned long long* __restrict__ mapped_total,
+             unsigned long long* __restrict__ err_word, uint32_t* __restrict__ frame_bytes_out, uint8_t* __restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t a3_dyn[];
+    int32_t* planes = reinterpret_cast<int32_t*>(a3_dyn);
+    uint4* res16_all = reinterpret_cast<uint4*>(a3_dyn + (size_t)2 * A3_PLANE * 4);
+    A3Cand* cands_sm = reinterpret_cast<A3Cand*>(a3_dyn + (size_t)2 * A3_PLANE * 4 + (size_t)4 * A3_PLANE * 2);
+    uint32_t* words = reinterpret_cast<uint32_t*>(cands_sm);   // the frame image reuses the analysis scratch
+    constexpr uint32_t cap_words = (uint32_t)(4 * sizeof(A3Cand) / 4);
+    __shared__ F4Static S;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t f = blockIdx.x;
+    const FrameDesc d = descs[f];
+    const uint32_t n = d.n;
+    const bool fast_modes = cfg.mode == MODE_FAST_MID_SIDE || cfg.mode == MODE_FAST_SIDE;
+    if (tid < 4) S.abs4[tid] = 0;
+    for (uint32_t i = tid; i < sizeof(Crc16Fold) / 4; i += 256) reinterpret_cast<uint32_t*>(&S.tabs)[i] = reinterpret_cast<const uint32_t*>(&g_crc16_tabs)[i];
+    if (fast_modes) __syncthreads();
+    // ---- 1a. unpack the two source channels once (Frame::fill_from_buf, src/audio.rs:149-187) ----
+    {
+        unsigned long long sl = 0, sr = 0, smid = 0, sside = 0;
+        const uint32_t ntiles = (n + 15) / 16;
+        for (uint32_t t = tid; t < ntiles; t += 256) {
+            int32_t a[16], b[16];
+            load_thread_samples<2>(cfg, d, pcm, t * 16, 0, a, b);
+            const uint32_t w = a3_tile_base(t);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                *reinterpret_cast<int4*>(planes + w + c * 128) = make_int4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+                *reinterpret_cast<int4*>(planes + A3_PLANE + w + c * 128) = make_int4(b[4 * c], b[4 * c + 1], b[4 * c + 2], b[4 * c + 3]);
+            }
+            if (fast_modes) {   // correlate_channels abs sums (:2475-2503)
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    sl += uabs32(a[e]); sr += uabs32(b[e]); smid += uabs32((a[e] + b[e]) >> 1); sside += uabs32(a[e] - b[e]);
+                }
+            }
+        }
+        if (fast_modes) {
+            sl = warp_sum_u64(sl); sr = warp_sum_u64(sr); smid = warp_sum_u64(smid); sside = warp_sum_u64(sside);
+            if (lane == 0) { atomicAdd(&S.abs4[0], sl); atomicAdd(&S.abs4[1], sr); atomicAdd(&S.abs4[2], smid); atomicAdd(&S.abs4[3], sside); }
+        }
+    }
+    __syncthreads();
+    // ---- 1b. the four candidates ----
+    {
+        const uint32_t cand = wid / A3_WPC, wsub = wid % A3_WPC, slot = cand;
+        CandRec* rec = &S.cr[cand];
+        bool active = true;
+        if (fast_modes) {
+            unsigned long long sums[4] = {S.abs4[0], S.abs4[1], S.abs4[2], S.abs4[3]};
+            if (tid < 4 && abssum) abssum[(size_t)f * 4 + tid] = sums[tid];
+            active = slot_active(cfg, sums, slot);
+        } else if (cfg.mode == MODE_EXH_SIDE && slot == 2) {
+            active = false;
+        }
+        if (!active) {
+            if (wsub == 0 && lane == 0) { rec->type = 0xFF; rec->bits = 0; }
+        } else {
+            const LpcRec lp = lpcs[(size_t)f * 4 + slot];
+            a3_candidate<HB, true>(cfg, d, planes, res16_all + (size_t)cand * (A3_PLANE * 2 / 16), slot, slot, cand, wsub, cand_bps(cfg, slot), lp,
+                                   cands_sm[cand], rec);
+        }
+    }
+    __syncthreads();
+    // ---- 2. decisions of the frame ----
+    if (tid < 4) S.bad16[tid] = cands_sm[tid].bad16;
+    if (tid == 0) {
+        S.placed = 0;
+        decide_frame(cfg, d, S.cr, S.abs4, S.fr);
+        const uint32_t need = (S.fr.frame_bytes + 3) / 4 + 2;
+        if (need > cap_words) S.fr.err = 1;
+        if (S.fr.err) *err_word = 1;   // sticky error word read back by the host
+        frame_bytes_out[f] = S.fr.frame_bytes;
+        // ---- 3. publish the size (frame 0 knows its prefix at once) ----
+        const unsigned long long mine = S.fr.frame_bytes;
+        *reinterpret_cast<volatile unsigned long long*>(state + f) = f == 0 ? (F4_FLAG_PREFIX | ((*base_in + mine) & F4_VALUE)) : (F4_FLAG_SIZE | mine);
+    }
+    if (cands_out)   // flacb200_encode_last_info
+        for (uint32_t i = tid; i < 4 * sizeof(CandRec) / 4; i += 256) reinterpret_cast<uint32_t*>(cands_out + (size_t)f * 4)[i] = reinterpret_cast<const uint32_t*>(S.cr)[i];
+    __syncthreads();
+    if (tid < 16) {   // the code bits per round of the two chosen encodings, before the analysis scratch becomes the frame image
+        const uint32_t sb = tid >> 3, rd = tid & 7;
+        const CandRec& c = S.cr[S.fr.slot[sb]];
+        S.round_bits[sb][rd] = c.type >= 2 ? cands_sm[S.fr.slot[sb]].round_bits[c.type == 3 ? 1 : 0][rd] : 0u;
+    }
+    __syncthreads();   // (also: every warp is done with the analysis scratch)
+    const FrameRec& fr = S.fr;
+    const uint32_t frame_bytes = fr.frame_bytes;
+    // warp 0 tries to place the frame at several points of the packing; the first success publishes the prefix
+    auto place = [&](bool spin) {
+        if (S.placed) return;
+        unsigned long long excl = 0;
+        if (!f4_lookback(state, f, base_in, spin, &excl)) return;
+        if (lane == 0) {
+            const unsigned long long incl = excl + frame_bytes;
+            if (f != 0) *reinterpret_cast<volatile unsigned long long*>(state + f) = F4_FLAG_PREFIX | (incl & F4_VALUE);
+            S.out_off = excl;
+            S.placed = 1;
+            if (f + 1 == cfg.nframes) {
+                *total_out = incl;
+                if (mapped_total) *mapped_total = incl;
+            }
+            if (frecs_out) {
+                FrameRec g = S.fr;
+                g.out_off = excl;
+                frecs_out[f] = g;
+            }
+        }
+        __syncwarp();
+    };
+    if (wid == 0) place(false);
+    const uint32_t words_sa = (uint32_t)__cvta_generic_to_shared(words);
+    const uint32_t img_words = min((frame_bytes + 3) / 4 + 2, cap_words);
+    const bool ok = fr.err == 0;
+    // ---- 4. the bit image ----
+    for (uint32_t i = tid; i < img_words; i += 256) words[i] = 0;
+    __syncthreads();
+    const uint32_t sub = wid >> 2, wq = wid & 3;   // subframe of this warp, warp within the subframe
+    const CandRec& cr = S.cr[fr.slot[sub]];
+    const uint32_t slot = fr.slot[sub];
+    const uint32_t type = cr.type, order = type >= 2 ? cr.order : 0u, wasted = cr.wasted, bps = cr.bps;
+    const bool use16 = S.bad16[slot] == 0;
+    const uint32_t rounds = ((n + 15) / 16 + 31) / 32;
+    uint32_t res_start = 0;
+    if (ok) {
+        if (tid < fr.hdr_len) p3_put(words_sa, 8 * tid, 8, fr.hdr[tid]);
+        uint32_t pos = fr.sub_bit[sub];
+        if (wq == 0 && lane == 0) {   // SubframeHeader (src/stream.rs:1397-1413)
+            const uint32_t code = type == 0 ? 0u : type == 1 ? 1u : type == 2 ? 8u + order : 31u + order;
+            p3_put_masked(words_sa, pos, 8, (code << 1) | (wasted ? 1u : 0u));
+            if (wasted) p3_put(words_sa, pos + 8 + (wasted - 1), 1, 1);
+        }
+        pos += 8 + wasted;
+        if (type == 0) {   // CONSTANT (:2982-2998)
+            if (wq == 0 && lane == 0) p3_put_masked(words_sa, pos, bps, (uint32_t)(f4_sample(planes, slot, 0) >> wasted));
+        } else if (type == 1) {   // VERBATIM (:3000-3018), all four warps
+            for (uint32_t i = wq * 32 + lane; i < n; i += 128) p3_put_masked(words_sa, pos + i * bps, bps, (uint32_t)(f4_sample(planes, slot, i) >> wasted));
+        } else {
+            if (wq == 0 && lane < order) p3_put_masked(words_sa, pos + lane * bps, bps, (uint32_t)(f4_sample(planes, slot, lane) >> wasted));   // warm-up
+            pos += order * bps;
+            if (type == 3) {   // :3122-3133
+                const uint32_t prec = cr.precision;
+                if (wq == 0 && lane == 0) {
+                    p3_put_masked(words_sa, pos, 4, prec - 1);
+                    p3_put_masked(words_sa, pos + 4, 5, cr.shift);
+                }
+                if (wq == 1 && lane < order) p3_put_masked(words_sa, pos + 9 + lane * prec, prec, (uint32_t)(int32_t)cr.q[lane]);
+                pos += 9 + order * prec;
+            }
+            if (wq == 2 && lane == 0) {   // residual block header (:3944-3961)
+                p3_put_masked(words_sa, pos, 2, cr.method);
+                p3_put_masked(words_sa, pos + 2, 4, cr.porder_w);
+            }
+            res_start = pos + 6;
+            // the round totals of the analysis count the codes; the partition headers (src/stream.rs:1603-1619) ride in front of
+            // the first residual of their partition
+            if (wq == 3) {
+                const uint32_t cp = n >> cr.porder_g, j0 = (1u << cr.porder_g) - cr.nparts, hb = cr.method ? 5u : 4u;
+                for (uint32_t j = lane; j < cr.nparts; j += 32) {
+                    const uint32_t first = max((j + j0) * cp, order);
+                    if (first < n) atomicAdd(&S.round_bits[sub][first >> 9], cr.rice[j] < 0x40 ? hb : hb + 5u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (ok && type >= 2) {
+        for (uint32_t rd = wq; rd < rounds; rd += 4) {
+            uint32_t base = res_start;
+            for (uint32_t k = 0; k < rd; k++) base += S.round_bits[sub][k];
+            f4_round<HB, true>(planes, res16_all + (size_t)slot * (A3_PLANE * 2 / 16), slot, cr, use16, n, rd, words_sa, base);
+        }
+    }
+    if (wid == 0) place(false);
+    __syncthreads();
+    // ---- CRC-16 over everything but the last two bytes (src/encode.rs:2408-2409) ----
+    const uint32_t body = frame_bytes - 2, bw = body >> 2, btail = body & 3;
+    const uint32_t per = (((bw + 7) / 8) + 63u) & ~63u;   // words per warp, whole rounds of 32 pairs
+    if (ok) {
+        const uint32_t a = min(wid * per, bw), b = min(a + per, bw);
+        uint32_t part = p3_crc_words(S.tabs, words, a, b - a);
+        if (lane == 0) {   // every warp shifts its own part to the end of the whole words: x^(32 * words behind it)
+            const uint32_t after = bw - b;
+            if (b > a && after) {
+                part = gf16_mulmod(part, g_crc16_xblk[after >> 5]);
+                if (after & 31u) part = gf16_mulmod(part, S.tabs.xd[after & 31u]);
+            }
+            S.crc_part[wid] = b > a ? part : 0u;
+        }
+    }
+    __syncthreads();
+    if (ok && tid == 0) {
+        uint32_t crc = 0;
+        for (uint32_t w = 0; w < 8; w++) crc ^= S.crc_part[w];
+        for (uint32_t t = 0; t < btail; t++) crc = (S.tabs.T[0][((crc >> 8) ^ (words[bw] >> (24 - 8 * t))) & 0xff] ^ (crc << 8)) & 0xffffu;
+        p3_put(words_sa, body * 8, 16, crc);
+    }
+    // ---- 5. where the frame goes ----
+    if (wid == 0) place(true);
+    __syncthreads();
+    if (!ok) return;
+    // ---- 6. copy out (as k_pack3) ----
+    const unsigned long long o = S.out_off;
+    const unsigned long long A = (o + 3) & ~3ull, B = (o + frame_bytes) & ~3ull;
+    auto frame_byte = [&](uint32_t b) -> uint8_t { return (uint8_t)(words[b >> 2] >> (24 - 8 * (b & 3))); };
+    if (A >= B) {
+        for (uint32_t b = tid; b < frame_bytes; b += 256) out[o + b] = frame_byte(b);
+        return;
+    }
+    const uint32_t head = (uint32_t)(A - o), tail0 = (uint32_t)(B - o);
+    if (tid < head) out[o + tid] = frame_byte(tid);
+    if (tid < frame_bytes - tail0) out[B + tid] = frame_byte(tail0 + tid);
+    uint32_t* gw = reinterpret_cast<uint32_t*>(out + A);
+    const uint32_t nfull = (uint32_t)((B - A) >> 2);
+    const uint32_t sh = head & 3;
+    for (uint32_t j = tid; j < nfull; j += 256) {
+        const uint32_t b = head + 4 * j, idx = b >> 2;
+        const uint32_t be = sh ? __funnelshift_l(words[idx + 1], words[idx], 8 * sh) : words[idx];
+        gw[j] = __byte_perm(be, 0, 0x0123);
+    }
+}
+
+void init_fused_tables(cudaStream_t st) { k_crc16_tables_init<<<1, 256, 0, st>>>(); }
+
+// stereo frames the CTA-per-frame analysis covers (k_analyze3's shapes with four candidate slots)
+bool frame4_ok(const EncCfg& cfg) { return analyze3_ok(cfg) && cfg.mode != MODE_INDEPENDENT && cfg.nslots == 4; }
+
+cudaError_t launch_frame4(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const LpcRec* lpcs, CandRec* cands_out, FrameRec* frecs_out,
+                          unsigned long long* abssum, unsigned long long* state, const unsigned long long* base_in, unsigned long long* total_out,
+                          unsigned long long* mapped_total, unsigned long long* err_word, uint32_t* frame_bytes_out, uint8_t* out, cudaStream_t st)
+{
+    const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
+    const size_t smem = a3_smem_bytes<true>();
+    cudaError_t e = cudaMemsetAsync(state, 0, (size_t)cfg.nframes * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+#define FLACB200_F4(HBV)                                                                                                             \
+    do {                                                                                                                             \
+        e = cudaFuncSetAttribute(k_frame4<HBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
+        if (e != cudaSuccess) return e;                                                                                              \
+        k_frame4<HBV><<<cfg.nframes, 256, smem, st>>>(cfg, descs, pcm, lpcs, cands_out, frecs_out, abssum, state, base_in, total_out, \
+                                                      mapped_total, err_word, frame_bytes_out, out);                                 \
+    } while (0)
+    switch (hb) {
+    case 1: FLACB200_F4(4); break;
+    case 2: FLACB200_F4(8); break;
+    case 3: FLACB200_F4(12); break;
+    default: FLACB200_F4(16); break;
+    }
+#undef FLACB200_F4
     return cudaGetLastError();
 }
 

@@ -39,6 +39,10 @@ cudaError_t launch_pack2_crc(const EncCfg&, const FrameDesc*, const uint8_t*, co
 cudaError_t launch_lpc2(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, cudaStream_t);
 cudaError_t launch_analyze(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, cudaStream_t);
 void init_encode_tables(cudaStream_t);   // encode_frame.cu
+void init_fused_tables(cudaStream_t);    // encode_analyze.cu
+bool frame4_ok(const EncCfg&);
+cudaError_t launch_frame4(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, FrameRec*, unsigned long long*, unsigned long long*,
+                          const unsigned long long*, unsigned long long*, unsigned long long*, unsigned long long*, uint32_t*, uint8_t*, cudaStream_t);
 void init_decode_tables(cudaStream_t);   // decode_kernels.cu
 // synth.cu
 cudaError_t launch_synth(uint8_t* pcm, unsigned long long first_track, unsigned long long n_tracks, unsigned long long n_pcm_frames,
@@ -99,9 +103,11 @@ struct flacb200_engine {
     bool no_batch = false, debug = false;
     size_t batch_bytes = 0;   // 0 = default
     uint32_t lpc_overlap = 0;   // (experiment, off: measured no gain -- both sides are occupancy-bound) CTAs per SM of the persistent k_lpc3 that runs beside the previous group's integer kernels; 0 = off
+    bool fused_frame = false;   // k_frame4 (analysis + decision + packing in one kernel): parity-green, measured SLOWER than the three
+                                // kernels on C4 (45 vs 41 ms per step), so it is an option, not the default
     int sm_count = 148;
     std::vector<cudaEvent_t> lpc_ev;   // per group: LPC parameters ready, analysis done (the two LpcRec buffers alternate)
-    DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, dec[12];
+    DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, lookback, dec[12];
     std::map<uint32_t, uint32_t> win_off;   // block length -> offset in doubles
     std::vector<double> win_host;
     flacb200_options win_opt{};
@@ -205,6 +211,7 @@ int flacb200_engine_create(int device, flacb200_engine** out)
     for (auto& ev : e->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char* v = getenv("FLACB200_LPC_OVERLAP")) e->lpc_overlap = (uint32_t)strtoul(v, nullptr, 0);
+    if (const char* v = getenv("FLACB200_FUSED")) e->fused_frame = strtoul(v, nullptr, 0) != 0;
     if (const char* v = getenv("FLACB200_LEGACY")) e->legacy = (unsigned)strtoul(v, nullptr, 0);
     if (const char* v = getenv("FLACB200_BATCH_BYTES")) e->batch_bytes = std::max<size_t>((size_t)strtoull(v, nullptr, 0), 1);
     e->no_batch = getenv("FLACB200_NO_BATCH") != nullptr;
@@ -215,6 +222,7 @@ int flacb200_engine_create(int device, flacb200_engine** out)
     if (device < 64) {
         std::call_once(tables_once[device], [&] {
             init_encode_tables(e->own_stream);
+            init_fused_tables(e->own_stream);
             init_decode_tables(e->own_stream);
             tables_err[device] = cudaStreamSynchronize(e->own_stream);
         });
@@ -234,7 +242,7 @@ void flacb200_engine_destroy(flacb200_engine* e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pcm, &e->planes, &e->masks, &e->lpcs, &e->cands, &e->frecs, &e->descs, &e->out, &e->fbytes, &e->totals, &e->winpool,
-                      &e->scratch, &e->lut};
+                      &e->scratch, &e->lut, &e->lookback};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto& b : e->dec)
@@ -277,6 +285,7 @@ int flacb200_engine_set_option(flacb200_engine* e, const char* key, uint64_t val
     else if (!strcmp(key, "no_batch")) e->no_batch = value != 0;
     else if (!strcmp(key, "debug")) e->debug = value != 0;
     else if (!strcmp(key, "lpc_overlap")) e->lpc_overlap = (uint32_t)value;
+    else if (!strcmp(key, "fused")) e->fused_frame = value != 0;
     else return FLACB200_E_BAD_ARGUMENT;
     return 0;
 }
@@ -482,6 +491,8 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     const bool fast_pack = analyze_fast_ok(cfg) && !(legacy & 4u);
     const bool frame_analyze = fast_analyze && analyze3_ok(cfg) && !(legacy & 16u);   // k_analyze3: CTA per frame, shared unpack
     const bool frame_pack = fast_pack && pack3_ok(cfg) && !(legacy & 8u);   // k_pack3: whole frames, CRC fused, no pre-zeroed output
+    // k_frame4: analysis, decision and packing of a stereo frame in one kernel (option "fused")
+    const bool fused = e->fused_frame && frame_analyze && frame_pack && frame4_ok(cfg);
     const bool need_planes = !(fast_analyze && fast_pack && (fast_lpc || cfg.max_lpc_order == 0));
     // launch group: without the int32 planes a group costs ~250 bytes per candidate, so it can be large enough to fill
     // the GPU even for the warp-per-8-candidates LPC kernel; with planes it is sized to stay near the L2 capacity
@@ -499,6 +510,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     ENS(e->frecs, (size_t)chunk * sizeof(FrameRec));
     ENS(e->fbytes, nframes * sizeof(uint32_t));
     ENS(e->totals, 64);
+    if (fused) ENS(e->lookback, (size_t)chunk * sizeof(unsigned long long));
     if (!(out && out_location == FLACB200_DEVICE && out_capacity >= bound + 64 && ((uintptr_t)out & 15) == 0)) ENS(e->out, bound + 64);
     const bool need_scratch = !residual_uses_smem(cfg);
     if (need_scratch) ENS(e->scratch, ncand_chunk * 2 * cfg.bpad * sizeof(int32_t));
@@ -578,7 +590,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     // FP64 / integer overlap: k_lpc3 of group g + 1 is launched on a second stream as a PERSISTENT grid (a few CTAs per SM --
     // small enough to be resident next to the CTAs of k_analyze3 / k_pack3 of group g, which leave the FP64 pipe idle); a
     // full-size grid on a second stream would only start when the first kernel's last CTA has been dispatched
-    const bool overlap = staged_lpc && frame_analyze && frame_pack && e->lpc_overlap != 0 && ngroups > 1;
+    const bool overlap = staged_lpc && frame_analyze && frame_pack && !fused && e->lpc_overlap != 0 && ngroups > 1;
     LpcRec* lpc_buf[2] = {(LpcRec*)e->lpcs.p, (LpcRec*)e->lpcs.p + ncand_chunk};
     if (overlap)
         while (e->lpc_ev.size() < 2 * ngroups) {
@@ -609,6 +621,16 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         else if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, lp, st));
         else launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, lp, st);
         time_mark(e, eb + 2);
+        if (fused) {
+            // the running byte total alternates between two words of `totals`: a late look-back of this group must still find
+            // the total the group started from
+            unsigned long long* tt = (unsigned long long*)e->totals.p;
+            CK(launch_frame4(c, dd, d_pcm, lp, keep ? (CandRec*)e->cands.p : nullptr, keep ? (FrameRec*)e->frecs.p : nullptr, d_abssum,
+                             (unsigned long long*)e->lookback.p, tt + 4 + (nchunks & 1), tt + 4 + ((nchunks + 1) & 1),
+                             pipe_out ? e->d_h_totals + nchunks : nullptr, tt + 3, (uint32_t*)e->fbytes.p + base, d_out, st));
+            time_mark(e, eb + 3);
+            time_mark(e, eb + 4);
+        } else {
         if (frame_analyze) CK(launch_analyze3(c, dd, d_pcm, lp, (CandRec*)e->cands.p, d_abssum, st));
         else if (fast_analyze) CK(launch_analyze(c, dd, d_pcm, lp, (CandRec*)e->cands.p, d_abssum, st));
         else
@@ -634,6 +656,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         if (frame_pack) CK(launch_pack3(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
         else if (fast_pack) CK(launch_pack2_crc(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
         else CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
+        }
         time_mark(e, eb + 5);
         if (pipe_out) {
             // frames of this group occupy [h_totals[g - 1], h_totals[g]); the host learns the bounds one group late and
@@ -651,7 +674,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
             }
         }
         nchunks++;
-        launches += (need_planes ? 1u : 0u) + (frame_pack ? 5u : 7u);
+        launches += fused ? 2u : (need_planes ? 1u : 0u) + (frame_pack ? 6u : 7u);
         if (keep) {
             CK(cudaMemcpyAsync(e->info_cands.data() + base * cfg.nslots, e->cands.p, (size_t)c.nframes * cfg.nslots * sizeof(CandRec),
                                cudaMemcpyDeviceToHost, st));
@@ -663,6 +686,8 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
 
     // ---- results ----
     unsigned long long totals[4] = {0, 0, 0, 0};
+    if (fused)   // the final byte total sits in the word the last group wrote
+        CK(cudaMemcpyAsync(e->totals.p, (unsigned long long*)e->totals.p + 4 + (nchunks & 1), sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(totals, e->totals.p, sizeof(totals), cudaMemcpyDeviceToHost, st));
     if (frame_bytes) {
         const size_t cnt = std::min<size_t>(frame_bytes_capacity, nframes);

@@ -88,7 +88,8 @@ int flacb200_engine_set_stream(flacb200_engine* e, void* cuda_stream);
 int flacb200_engine_set_chunk_frames(flacb200_engine* e, uint32_t frames);
 /* Runtime knobs for tests and experiments.  Their defaults come from the environment
  * (FLACB200_LEGACY, FLACB200_BATCH_BYTES, FLACB200_NO_BATCH, FLACB200_DEBUG), which is read once, at
- * flacb200_engine_create; keys: "legacy", "batch_bytes", "no_batch", "debug". */
+ * flacb200_engine_create; keys: "legacy", "batch_bytes", "no_batch", "debug", "fused" (FLACB200_FUSED: the single-kernel
+ * stereo frame encoder k_frame4 instead of k_analyze3 + k_decide + k_scan + k_pack3), "lpc_overlap". */
 int flacb200_engine_set_option(flacb200_engine* e, const char* key, uint64_t value);
 /* Keep per-subframe decisions of each encode call for flacb200_encode_last_info (default on, calls of
  * at most 65536 frames); switch off on throughput paths -- it costs a device-to-host copy per group. */

@@ -283,6 +283,20 @@ def test_generic_kernels_give_the_same_bytes(eng, fo):
         for label, opt, rate, bps, ch, x in cases:
             check(eng, fo, opt, rate, bps, ch, x, f"legacy={mask} {label}")
     eng.set_option("legacy", 0)
+    # the single-kernel stereo frame encoder (k_frame4: analysis + decision + look-back placement + packing in one CTA)
+    eng.set_option("fused", 1)
+    try:
+        for label, opt, rate, bps, ch, x in cases:
+            check(eng, fo, opt, rate, bps, ch, x, f"fused {label}")
+        big = synth_pcm(9, 2, 4096 * 700 + 1234, 48000, 24)     # many frames: the look-back walks over whole waves of CTAs
+        check(eng, fo, Options.best(), 48000, 24, 2, big, "fused 24b stereo best, 701 frames")
+        for label, opt, rate, bps, ch, x in (("wasted bits", Options.best(), 48000, 24, 2, synth_pcm(3, 2, 20000, 48000, 16) * 256),
+                                            ("noise 24b", Options.best(), 48000, 24, 2, np.random.default_rng(3).integers(-(1 << 23), 1 << 23, (9000, 2)).astype(np.int32)),
+                                            ("silence", Options.default(), 44100, 16, 2, np.zeros((10000, 2), dtype=np.int32)),
+                                            ("bs 4095", Options.best().block_size(4095), 44100, 16, 2, synth_pcm(5, 2, 30000, 44100, 16))):
+            check(eng, fo, opt, rate, bps, ch, x, f"fused {label}")
+    finally:
+        eng.set_option("fused", 0)
 
 
 def test_frame_kernels_edge_shapes(eng, fo):
