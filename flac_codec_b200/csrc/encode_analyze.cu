@@ -144,7 +144,6 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                 return;
             }
             bps = full_bps - wasted;
-            const uint32_t nleaf = 1u << p_max;
             if (wsub == 0) {   // first warp: the fixed predictor
                 unsigned long long s0, s1, s2, s3, s4;
                 {   // sums over the common tail = everything set k counted, minus its samples before kmax
@@ -165,28 +164,12 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     if (kmax >= 3 && s3 < best) { best = s3; fo = 3; }
                     if (kmax >= 4 && s4 < best) { best = s4; fo = 4; }
                 }
-                for (uint32_t j = lane; j < nleaf; j += 32)
-                    sm.tree[0][nleaf - 1 + j] = (unsigned long long)sm.limb_lo[fo][j] + ((unsigned long long)sm.limb_hi[fo][j] << 24);
-                __syncwarp();
-                for (int p = (int)p_max - 1; p >= 0; p--) {
-                    const uint32_t base = (1u << p) - 1, child = (2u << p) - 1;
-                    for (uint32_t j = lane; j < (1u << p); j += 32) sm.tree[0][base + j] = sm.tree[0][child + 2 * j] + sm.tree[0][child + 2 * j + 1];
-                    __syncwarp();
-                }
-                aw_choose_partitions(cfg, n, fo, p_max, sm.tree[0], sm.part_est[0], sm.part_code[0], sm.choice[0]);
+                aw_choose_partitions_flat(cfg, n, fo, p_max, sm.limb_lo[fo], sm.limb_hi[fo], sm.tree[0], sm.part_code[0], sm.choice[0]);
                 if (lane == 0) sm.fo = fo;
             } else if (wsub == 1) {   // second warp: the LPC predictor
                 lpc_ok = have_lpc && sm.ovf == 0;   // ResidualOverflow
                 if (lpc_ok) {
-                    for (uint32_t j = lane; j < nleaf; j += 32)
-                        sm.tree[1][nleaf - 1 + j] = (unsigned long long)sm.limb_lo[5][j] + ((unsigned long long)sm.limb_hi[5][j] << 24);
-                    __syncwarp();
-                    for (int p = (int)p_max - 1; p >= 0; p--) {
-                        const uint32_t base = (1u << p) - 1, child = (2u << p) - 1;
-                        for (uint32_t j = lane; j < (1u << p); j += 32) sm.tree[1][base + j] = sm.tree[1][child + 2 * j] + sm.tree[1][child + 2 * j + 1];
-                        __syncwarp();
-                    }
-                    aw_choose_partitions(cfg, n, order, p_max, sm.tree[1], sm.part_est[1], sm.part_code[1], sm.choice[1]);
+                    aw_choose_partitions_flat(cfg, n, order, p_max, sm.limb_lo[5], sm.limb_hi[5], sm.tree[1], sm.part_code[1], sm.choice[1]);
                 }
                 if (lane == 0) sm.lpc_ok = lpc_ok ? 1u : 0u;
             }

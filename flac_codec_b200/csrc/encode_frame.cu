@@ -21,7 +21,6 @@ namespace flacb200 {
 bool analyze_fast_ok(const EncCfg& cfg);   // encode_kernels.cu
 
 struct P3Smem {
-    Crc16Fold tabs;
     uint32_t crc_part[MAX_CH];
     FrameRec fr;
     CandRec cr[MAX_CH];
@@ -172,7 +171,13 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
 // P3_SMALL_WORDS: more CTAs per SM), the second with room for the worst case, for the few frames that need more
 // (min_words = P3_SMALL_WORDS); a CTA whose frame belongs to the other launch exits at once.
 template <int HB, bool STEREO>
-__global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? 9 : 2)
+#ifndef FLACB200_P3_MINB
+#define FLACB200_P3_MINB 9
+#endif
+#ifndef FLACB200_P3_SMALL
+#define FLACB200_P3_SMALL 6
+#endif
+__global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? FLACB200_P3_MINB : 2)
     k_pack3(EncCfg cfg, uint32_t min_words, uint32_t cap_words, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
             const CandRec* __restrict__ cands, const FrameRec* __restrict__ frecs, uint8_t* __restrict__ out)
 {
@@ -186,8 +191,6 @@ __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? 9 : 2)
     }
     // ---- stage the frame record, its subframes' candidate records and the CRC tables; clear the image ----
     for (uint32_t i = tid; i < sizeof(FrameRec) / 4; i += nthreads) reinterpret_cast<uint32_t*>(&sm.fr)[i] = reinterpret_cast<const uint32_t*>(frecs + f)[i];
-    for (uint32_t i = tid; i < sizeof(Crc16Fold) / 4; i += nthreads)
-        reinterpret_cast<uint32_t*>(&sm.tabs)[i] = reinterpret_cast<const uint32_t*>(&g_crc16_tabs)[i];
     __syncthreads();
     const FrameRec& fr = sm.fr;
     const uint32_t nsub = fr.nsub;
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? 9 : 2)
         // warp w takes words [w * per, (w + 1) * per), per a multiple of 64 (whole rounds of 32 pairs)
         const uint32_t per = (((bw + nwarps - 1) / nwarps) + 63u) & ~63u;
         const uint32_t a = min(wid * per, bw), b = min(a + per, bw);
-        const uint32_t part = p3_crc_words(sm.tabs, p3_words, a, b - a);
+        const uint32_t part = p3_crc_words(g_crc16_tabs, p3_words, a, b - a);
         if (lane == 0) sm.crc_part[wid] = part;
         __syncthreads();
         if (tid == 0) {
@@ -276,11 +279,11 @@ __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? 9 : 2)
                 if (wb > wa) {   // ranges are whole blocks of 32 words except the last: shift by the table, then by the odd words
                     const uint32_t len = wb - wa;
                     crc = gf16_mulmod(crc, g_crc16_xblk[len >> 5]);
-                    if (len & 31u) crc = gf16_mulmod(crc, sm.tabs.xd[len & 31u]);
+                    if (len & 31u) crc = gf16_mulmod(crc, g_crc16_tabs.xd[len & 31u]);
                     crc ^= sm.crc_part[w];
                 }
             }
-            for (uint32_t t = 0; t < btail; t++) crc = (sm.tabs.T[0][((crc >> 8) ^ (p3_words[bw] >> (24 - 8 * t))) & 0xff] ^ (crc << 8)) & 0xffffu;
+            for (uint32_t t = 0; t < btail; t++) crc = (g_crc16_tabs.T[0][((crc >> 8) ^ (p3_words[bw] >> (24 - 8 * t))) & 0xff] ^ (crc << 8)) & 0xffffu;
             p3_put(words_sa, body * 8, 16, crc);
         }
         __syncthreads();
@@ -325,7 +328,7 @@ cudaError_t launch_pack3(const EncCfg& cfg, const FrameDesc* descs, const uint8_
     const uint32_t nsub = cfg.mode == MODE_INDEPENDENT ? cfg.channels : 2;
     const uint32_t cap_words = pack3_cap_words(cfg);
     // ordinary frames compress to well under 3/4 of the raw size: a smaller image lets more CTAs share an SM
-    const uint32_t small_words = (cap_words * 3u / 4u) & ~1u;
+    const uint32_t small_words = (cap_words * FLACB200_P3_SMALL / 8u) & ~1u;
     const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
 #define FLACB200_P3(HBV, ST)                                                                                                         \
     do {                                                                                                                             \

@@ -174,4 +174,106 @@ static __device__ void aw_choose_partitions(const EncCfg& cfg, uint32_t n, uint3
     __syncwarp();
 }
 
+
+// best_partitions + try_reduce_rice (src/encode.rs:3865-3942) for one residual set, by one warp, from the sums of the FINEST
+// partitions (lo/hi: 24-bit limbs per leaf, 1 << p_max leaves).  Same result as the tree walk of aw_choose_partitions, in a
+// fraction of the instructions: the sum of partition j at order p is a difference of two entries of the prefix sums over
+// the leaves, every (order, partition) node is evaluated once in registers (four per lane), the per-order totals come from
+// warp reductions that all lanes receive -- no level-by-level tree, no per-order loops.  `pref` (65 entries) and `codes`
+// (127 bytes) are the warp's scratch in shared memory.
+static __device__ void aw_choose_partitions_flat(const EncCfg& cfg, uint32_t n, uint32_t o, uint32_t p_max, const uint32_t* lo, const uint32_t* hi,
+                                                unsigned long long* pref, uint8_t* codes, RiceChoice& ch)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t rice_max = cfg.use_rice2 ? 31u : 15u;
+    const uint32_t nleaf = 1u << p_max;
+    // ---- prefix sums over the leaves: lane l owns leaves 2 l and 2 l + 1 ----
+    const unsigned long long v0 = 2 * lane < nleaf ? (unsigned long long)lo[2 * lane] + ((unsigned long long)hi[2 * lane] << 24) : 0ull;
+    const unsigned long long v1 = 2 * lane + 1 < nleaf ? (unsigned long long)lo[2 * lane + 1] + ((unsigned long long)hi[2 * lane + 1] << 24) : 0ull;
+    unsigned long long incl = v0 + v1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    pref[2 * lane] = incl - v0 - v1;
+    pref[2 * lane + 1] = incl - v1;
+    if (lane == 31) pref[64] = incl;
+    __syncwarp();
+    // ---- every node (order p, partition j) once: t = (1 << p) - 1 + j, four nodes per lane ----
+    uint32_t est[4];
+    uint8_t code[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t t = lane + 32u * k;
+        const uint32_t p = 31u - (uint32_t)__clz((int)(t + 1));
+        const uint32_t j = t + 1 - (1u << p);
+        code[k] = 0xFE;
+        est[k] = 0;
+        if (t < 127 && p <= p_max) {
+            const uint32_t cp = n >> p, a = j * cp, b = a + cp, w = nleaf >> p;
+            if (b > o) code[k] = partition_code(pref[(j + 1) * w] - pref[j * w], b - max(a, o), rice_max, &est[k]);
+        }
+        if (t < 127) codes[t] = code[k];
+    }
+    // ---- totals per order (nodes of order p: t in [2^p - 1, 2^(p+1) - 2]); every lane gets all of them ----
+    // order 0..4 live in slot 0 (lanes 0, 1-2, 3-6, 7-14, 15-30), order 5 = slot 0 lane 31 + slot 1 lanes 0-30, order 6 = the rest
+    const uint32_t p0 = 31u - (uint32_t)__clz((int)(lane + 1));   // order of the slot-0 node of this lane (5 for lane 31)
+    uint32_t e_tot[7], cntw0 = 0, cntw1 = 0, badm = 0;
+#pragma unroll
+    for (int p = 0; p < 5; p++) e_tot[p] = __reduce_add_sync(0xffffffffu, p0 == (uint32_t)p ? est[0] : 0u);
+    e_tot[5] = __reduce_add_sync(0xffffffffu, (lane == 31 ? est[0] : 0u) + (lane < 31 ? est[1] : 0u));
+    e_tot[6] = __reduce_add_sync(0xffffffffu, (lane == 31 ? est[1] : 0u) + est[2] + (lane < 31 ? est[3] : 0u));
+    {   // partition counts (8-bit fields: at most 64 per order) and "a partition of this order cannot be coded" flags
+        auto tally = [&](uint8_t c, uint32_t p) {
+            if (c == 0xFE) return;
+            if (c == 0xFF) badm |= 1u << p;
+            if (p < 4) cntw0 += 1u << (8 * p);
+            else cntw1 += 1u << (8 * (p - 4));
+        };
+        tally(code[0], p0);
+        tally(code[1], lane == 31 ? 6u : 5u);
+        tally(code[2], 6u);
+        if (lane < 31) tally(code[3], 6u);
+        cntw0 = __reduce_add_sync(0xffffffffu, cntw0);
+        cntw1 = __reduce_add_sync(0xffffffffu, cntw1);
+        badm = __reduce_or_sync(0xffffffffu, badm);
+    }
+    uint32_t best_p = 0xFFFFFFFFu, best_est = 0, best_count = 0;
+#pragma unroll
+    for (int p = 0; p < 7; p++) {
+        const uint32_t cnt = p < 4 ? (cntw0 >> (8 * p)) & 0xffu : (cntw1 >> (8 * (p - 4))) & 0xffu;
+        const bool ok = (uint32_t)p <= p_max && !((badm >> p) & 1u) && cnt != 0 && (cnt & (cnt - 1)) == 0;   // :3880-3881
+        if (ok && (best_p == 0xFFFFFFFFu || e_tot[p] < best_est)) {   // first minimum :3885
+            best_p = (uint32_t)p;
+            best_est = e_tot[p];
+            best_count = cnt;
+        }
+    }
+    __syncwarp();
+    if (best_p == 0xFFFFFFFFu) {   // unwrap_or_else (:3887): one partition escaped at 31 bits
+        if (lane == 0) {
+            ch.porder_g = 0; ch.porder_w = 0; ch.nparts = 1; ch.rice[0] = 0x40 | 31;
+            ch.method = cfg.use_rice2 ? 1 : 0;
+        }
+        __syncwarp();
+        return;
+    }
+    const uint32_t base = (1u << best_p) - 1, j0 = (1u << best_p) - best_count;
+    uint32_t big = 0;
+    for (uint32_t j = lane; j < best_count; j += 32) {
+        const uint8_t c = codes[base + j0 + j];
+        ch.rice[j] = c;
+        if (c < 0x40 && c >= 15) big = 1;
+    }
+    big = __any_sync(0xffffffffu, big);
+    if (lane == 0) {
+        ch.porder_g = (uint8_t)best_p;
+        ch.nparts = (uint8_t)best_count;
+        ch.porder_w = (uint8_t)(31u - (uint32_t)__clz((int)best_count));   // partitions.len().ilog2() :3902
+        ch.method = (cfg.use_rice2 && big) ? 1 : 0;                         // try_reduce_rice :3929-3942
+    }
+    __syncwarp();
+}
+
 }   // namespace flacb200
