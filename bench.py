@@ -271,6 +271,8 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound (the cpu_baseline leg uses every core)"
+    if world > 1:   # the ranks of one host share its cores: each hashes (flacb200_md5_many) with its share
+        os.environ.setdefault("FLACB200_HOST_THREADS", str(max((os.cpu_count() or 1) // world, 1)))
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL's log (the image sets NCCL_DEBUG=VERSION: a banner on stdout) goes to stderr: rank 0 prints ONE line

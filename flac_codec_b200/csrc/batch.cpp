@@ -94,7 +94,19 @@ struct Key {
     bool operator<(const Key& o) const { return std::tie(rate, bps, ch, kind) < std::tie(o.rate, o.bps, o.ch, o.kind); }
 };
 
-unsigned host_threads() { return std::max(1u, std::thread::hardware_concurrency()); }
+// host threads this process may use for hashing: all of them, unless FLACB200_HOST_THREADS says otherwise (several rank
+// processes on one host share its cores)
+unsigned host_threads()
+{
+    static const unsigned n = [] {
+        if (const char* v = getenv("FLACB200_HOST_THREADS")) {
+            const unsigned long k = strtoul(v, nullptr, 0);
+            if (k) return (unsigned)k;
+        }
+        return std::max(1u, std::thread::hardware_concurrency());
+    }();
+    return n;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // encode

@@ -120,6 +120,63 @@ __attribute__((target("avx2"))) void blocks_avx2(State st[8], const uint8_t* con
 }
 #endif
 
+// sixteen streams in the lanes of AVX-512 registers: native rotate, one ternary-logic instruction per round function
+__attribute__((target("avx512f"))) void blocks_avx512(State st[16], const uint8_t* const p[16], size_t nblocks)
+{
+    alignas(64) uint32_t ta[16], tb[16], tc[16], td[16];
+    for (int l = 0; l < 16; l++) { ta[l] = st[l].a; tb[l] = st[l].b; tc[l] = st[l].c; td[l] = st[l].d; }
+    __m512i A = _mm512_load_si512(ta), B = _mm512_load_si512(tb), C = _mm512_load_si512(tc), D = _mm512_load_si512(td);
+    for (size_t blk = 0; blk < nblocks; blk++) {
+        // 16 streams x 16 message words -> 16 registers of 16 lanes (a 16 x 16 transpose of 32-bit words)
+        __m512i r[16], t[16];
+        for (int l = 0; l < 16; l++) r[l] = _mm512_loadu_si512(p[l] + blk * 64);
+        for (int i = 0; i < 16; i += 2) {
+            t[i] = _mm512_unpacklo_epi32(r[i], r[i + 1]);
+            t[i + 1] = _mm512_unpackhi_epi32(r[i], r[i + 1]);
+        }
+        for (int i = 0; i < 16; i += 4) {
+            r[i] = _mm512_unpacklo_epi64(t[i], t[i + 2]);
+            r[i + 1] = _mm512_unpackhi_epi64(t[i], t[i + 2]);
+            r[i + 2] = _mm512_unpacklo_epi64(t[i + 1], t[i + 3]);
+            r[i + 3] = _mm512_unpackhi_epi64(t[i + 1], t[i + 3]);
+        }
+        // r[4 g + k] holds, per 128-bit lane q, word 4 q + k of streams 4 g .. 4 g + 3
+        for (int k = 0; k < 4; k++) {
+            t[k] = _mm512_shuffle_i32x4(r[k], r[4 + k], 0x88);        // lanes 0, 2 of streams 0-3 | 4-7
+            t[4 + k] = _mm512_shuffle_i32x4(r[k], r[4 + k], 0xdd);    // lanes 1, 3
+            t[8 + k] = _mm512_shuffle_i32x4(r[8 + k], r[12 + k], 0x88);
+            t[12 + k] = _mm512_shuffle_i32x4(r[8 + k], r[12 + k], 0xdd);
+        }
+        __m512i M[16];
+        for (int k = 0; k < 4; k++) {
+            M[k] = _mm512_shuffle_i32x4(t[k], t[8 + k], 0x88);            // word k      (128-bit lane 0 of every stream group)
+            M[8 + k] = _mm512_shuffle_i32x4(t[k], t[8 + k], 0xdd);        // word 8 + k  (lane 2)
+            M[4 + k] = _mm512_shuffle_i32x4(t[4 + k], t[12 + k], 0x88);   // word 4 + k  (lane 1)
+            M[12 + k] = _mm512_shuffle_i32x4(t[4 + k], t[12 + k], 0xdd);  // word 12 + k (lane 3)
+        }
+        __m512i a = A, b = B, c = C, d = D;
+        for (int i = 0; i < 64; i++) {
+            __m512i f;
+            if (i < 16) f = _mm512_ternarylogic_epi32(b, c, d, 0xCA);        // (b & c) | (~b & d)
+            else if (i < 32) f = _mm512_ternarylogic_epi32(b, c, d, 0xE4);   // (b & d) | (c & ~d)
+            else if (i < 48) f = _mm512_ternarylogic_epi32(b, c, d, 0x96);   // b ^ c ^ d
+            else f = _mm512_ternarylogic_epi32(b, c, d, 0x39);               // c ^ (b | ~d)
+            const __m512i tt = _mm512_add_epi32(_mm512_add_epi32(a, f), _mm512_add_epi32(_mm512_set1_epi32((int)K[i]), M[msg_index(i)]));
+            a = d; d = c; c = b;
+            b = _mm512_add_epi32(b, _mm512_rolv_epi32(tt, _mm512_set1_epi32(S[i])));
+        }
+        A = _mm512_add_epi32(A, a); B = _mm512_add_epi32(B, b); C = _mm512_add_epi32(C, c); D = _mm512_add_epi32(D, d);
+    }
+    _mm512_store_si512(ta, A); _mm512_store_si512(tb, B); _mm512_store_si512(tc, C); _mm512_store_si512(td, D);
+    for (int l = 0; l < 16; l++) { st[l].a = ta[l]; st[l].b = tb[l]; st[l].c = tc[l]; st[l].d = td[l]; }
+}
+
+bool have_avx512()
+{
+    static const bool v = __builtin_cpu_supports("avx512f");
+    return v;
+}
+
 bool have_avx2()
 {
 #ifdef FLACB200_HAVE_X86
@@ -130,13 +187,25 @@ bool have_avx2()
 #endif
 }
 
-// one group of up to eight streams
+// one group of up to sixteen (AVX-512) / eight (AVX2) streams
 void md5_group(const uint8_t* const* data, const size_t* len, const size_t* idx, size_t n, uint8_t (*digests)[16])
 {
-    State st[8];
+    State st[16];
     size_t done = 0;
 #ifdef FLACB200_HAVE_X86
-    if (n > 1 && have_avx2()) {
+    if (n > 8 && have_avx512()) {
+        size_t common = ~(size_t)0;
+        for (size_t l = 0; l < n; l++) common = std::min(common, len[idx[l]] / 64);
+        const uint8_t* p[16];
+        for (size_t l = 0; l < 16; l++) p[l] = data[idx[l < n ? l : 0]];
+        const size_t CH = 4096;
+        for (size_t b0 = 0; b0 < common; b0 += CH) {
+            const uint8_t* q[16];
+            for (int l = 0; l < 16; l++) q[l] = p[l] + b0 * 64;
+            blocks_avx512(st, q, std::min(CH, common - b0));
+        }
+        done = common * 64;
+    } else if (n > 1 && have_avx2()) {
         size_t common = ~(size_t)0;
         for (size_t l = 0; l < n; l++) common = std::min(common, len[idx[l]] / 64);
         const uint8_t* p[8];
@@ -168,6 +237,9 @@ void md5_many(const uint8_t* const* data, const size_t* len, size_t n, uint8_t (
     // enough groups for every thread: groups narrower than eight when streams are few (a lane costs nothing, a thread does)
     threads = std::max(1u, threads);
     size_t width = 8;
+#ifdef FLACB200_HAVE_X86
+    if (have_avx512()) width = 16;
+#endif
     while (width > 1 && (n + width - 1) / width < threads) width /= 2;
     const size_t ngroups = (n + width - 1) / width;
     std::atomic<size_t> next{0};
