@@ -348,7 +348,7 @@ def run_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes_step = pcm_bytes + flac_bytes          # PCM read once + frames written once
-    groups = max(int(kernel_launches[top] // max({0: 1, 1: 1, 2: 1, 3: 2, 4: 1}[top], 1)), 1)
+    groups = max(int(kernel_launches[top] // max({0: 1, 1: 1, 2: 1, 3: 2, 4: 2}[top], 1)), 1)
     avg_ms = kernel_ms[top] / groups                 # average duration of one launch (group) of the top kernel
     alg_bytes_launch = alg_bytes_step * args.steps / groups
     achieved = alg_bytes_launch / (avg_ms * 1e-3) / 1e9

@@ -15,6 +15,11 @@
 
 namespace flacb200 {
 
+// every kernel launch of the library passes through here: flacb200_timings::launches is a count, not an estimate
+// (per host thread: an engine call runs on its caller's thread, so the difference across a call is that call's count)
+extern thread_local unsigned long long g_kernel_launches;
+inline void count_launch() { g_kernel_launches++; }
+
 constexpr int MAX_LPC = 32;
 constexpr int MAX_PARTS = 64;   // MAX_PARTITIONS, src/encode.rs:3756
 constexpr int MAX_PORDER = 6;   // the reference overflows its 64-entry ArrayVec above this

@@ -1377,26 +1377,26 @@ void launch_find_count(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* se
                        cudaStream_t st)
 {
     const uint32_t tiles = find_tiles(cfg.nbytes);
-    k_find<0><<<tiles, FIND_THREADS, 0, st>>>(cfg, bytes, segs, tile_counts, nullptr, nullptr, max_bs);
-    k_scan_u32<<<1, 1024, 0, st>>>(tiles, tile_counts, tile_base);
+    count_launch(), k_find<0><<<tiles, FIND_THREADS, 0, st>>>(cfg, bytes, segs, tile_counts, nullptr, nullptr, max_bs);
+    count_launch(), k_scan_u32<<<1, 1024, 0, st>>>(tiles, tile_counts, tile_base);
 }
 
 void launch_find_write(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const uint32_t* tile_base, FrameCand* cands, cudaStream_t st)
 {
-    k_find<1><<<find_tiles(cfg.nbytes), FIND_THREADS, 0, st>>>(cfg, bytes, segs, nullptr, tile_base, cands, nullptr);
+    count_launch(), k_find<1><<<find_tiles(cfg.nbytes), FIND_THREADS, 0, st>>>(cfg, bytes, segs, nullptr, tile_base, cands, nullptr);
 }
 
 void launch_decode(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes, DecRec* recs,
                    bool only_wide, cudaStream_t st)
 {
-    k_decode<<<(n + DEC_THREADS - 1) / DEC_THREADS, DEC_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, recs, only_wide ? 1u : 0u);
+    count_launch(), k_decode<<<(n + DEC_THREADS - 1) / DEC_THREADS, DEC_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, recs, only_wide ? 1u : 0u);
 }
 
 void init_decode_tables(cudaStream_t st) { k_dec_crc16_tables_init<<<1, 256, 0, st>>>(); }
 
 void launch_crc16f(const uint8_t* bytes, const FrameCand* cands, uint32_t n, DecRec* recs, cudaStream_t st)
 {
-    k_crc16f<<<(n + CRCF_THREADS / 32 - 1) / (CRCF_THREADS / 32), CRCF_THREADS, 0, st>>>(bytes, cands, n, recs);
+    count_launch(), k_crc16f<<<(n + CRCF_THREADS / 32 - 1) / (CRCF_THREADS / 32), CRCF_THREADS, 0, st>>>(bytes, cands, n, recs);
 }
 
 cudaError_t launch_chain(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, DecRec* recs, uint32_t n,
@@ -1406,14 +1406,14 @@ cudaError_t launch_chain(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* 
         cudaError_t e = cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem));
         if (e != cudaSuccess) return e;
     }
-    k_chain<<<1, CHAIN_THREADS, sizeof(ChainSmem), st>>>(cfg, bytes, segs, cands, recs, n, after, group_first, pos, state);
+    count_launch(), k_chain<<<1, CHAIN_THREADS, sizeof(ChainSmem), st>>>(cfg, bytes, segs, cands, recs, n, after, group_first, pos, state);
     return cudaGetLastError();
 }
 
 void launch_chain_fast(const DecCfg& cfg, const DecSeg* segs, const FrameCand* cands, const DecRec* recs, uint32_t n, uint32_t n_all,
                        uint32_t group_first, unsigned long long* pos, ChainState* state, uint32_t* clean, cudaStream_t st)
 {
-    k_chain_fast<<<1, CHAIN_THREADS, 0, st>>>(cfg, segs, cands, recs, n, n_all, group_first, pos, state, clean);
+    count_launch(), k_chain_fast<<<1, CHAIN_THREADS, 0, st>>>(cfg, segs, cands, recs, n, n_all, group_first, pos, state, clean);
 }
 
 // k_emit4: the common layouts (1 or 2 channels, 2 or 3 bytes per sample, packed bytes).  One CTA takes a bundle of 32
@@ -1529,14 +1529,14 @@ void launch_emit(const DecCfg& cfg, const FrameCand* cands, const DecRec* recs, 
                         (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (cfg.bstride & 3) == 0;
     if (packed && cfg.channels <= 2) {
         dim3 grid((n + 31) / 32, (cfg.bstride / 4 + EMIT_GROUPS - 1) / EMIT_GROUPS);
-        if (cfg.channels == 1 && cfg.bytes_per_sample == 2) k_emit4<1, 2><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
-        else if (cfg.channels == 1) k_emit4<1, 3><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
-        else if (cfg.bytes_per_sample == 2) k_emit4<2, 2><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
-        else k_emit4<2, 3><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
+        if (cfg.channels == 1 && cfg.bytes_per_sample == 2) count_launch(), k_emit4<1, 2><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
+        else if (cfg.channels == 1) count_launch(), k_emit4<1, 3><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
+        else if (cfg.bytes_per_sample == 2) count_launch(), k_emit4<2, 2><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
+        else count_launch(), k_emit4<2, 3><<<grid, 256, 0, st>>>(cfg, cands, n, recs, pos, planes, out);
         return;
     }
     dim3 grid(n, (cfg.bstride + 255) / 256);
-    k_emit<<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
+    count_launch(), k_emit<<<grid, 256, 0, st>>>(cfg, cands, recs, pos, planes, out);
 }
 
 

@@ -505,13 +505,13 @@ __global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const F
 void launch_parse(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes, SubRec* subs,
                   DecRec* recs, cudaStream_t st)
 {
-    k_parse<<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs);
+    count_launch(), k_parse<<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs);
 }
 
 void launch_restore(const DecCfg& cfg, const FrameCand* cands, uint32_t n, const SubRec* subs, const DecRec* recs, int32_t* planes, cudaStream_t st)
 {
     const uint32_t threads = ((n + 31) / 32) * 32 * cfg.channels;
-    k_restore<<<(threads + RESTORE_THREADS - 1) / RESTORE_THREADS, RESTORE_THREADS, 0, st>>>(cfg, cands, n, subs, recs, planes);
+    count_launch(), k_restore<<<(threads + RESTORE_THREADS - 1) / RESTORE_THREADS, RESTORE_THREADS, 0, st>>>(cfg, cands, n, subs, recs, planes);
 }
 
 }   // namespace flacb200

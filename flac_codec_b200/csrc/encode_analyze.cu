@@ -585,7 +585,7 @@ cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uin
         cudaError_t e_ = cudaFuncSetAttribute(k_analyze3<HBV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);          \
         if (e_ != cudaSuccess) return e_;                                                                                             \
         const uint32_t groups_ = ST ? 1u : (cfg.channels + 1u) / 2u;                                                                  \
-        k_analyze3<HBV, ST><<<cfg.nframes * groups_, 32 * A3_WPC * (ST ? 4 : 2), smem_, st>>>(cfg, descs, pcm, lpcs, cands, abssum);  \
+        count_launch(), k_analyze3<HBV, ST><<<cfg.nframes * groups_, 32 * A3_WPC * (ST ? 4 : 2), smem_, st>>>(cfg, descs, pcm, lpcs, cands, abssum);  \
     } while (0)
     if (cfg.mode != MODE_INDEPENDENT) {
         switch (hb) {
@@ -1098,7 +1098,7 @@ cudaError_t launch_frame4(const EncCfg& cfg, const FrameDesc* descs, const uint8
     do {                                                                                                                             \
         e = cudaFuncSetAttribute(k_frame4<HBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
         if (e != cudaSuccess) return e;                                                                                              \
-        k_frame4<HBV><<<cfg.nframes, 256, smem, st>>>(cfg, descs, pcm, lpcs, cands_out, frecs_out, abssum, state, base_in, total_out, \
+        count_launch(), k_frame4<HBV><<<cfg.nframes, 256, smem, st>>>(cfg, descs, pcm, lpcs, cands_out, frecs_out, abssum, state, base_in, total_out, \
                                                       mapped_total, err_word, frame_bytes_out, out);                                 \
     } while (0)
     switch (hb) {

@@ -407,8 +407,8 @@ cudaError_t launch_analyze(const EncCfg& cfg, const FrameDesc* descs, const uint
 {
     const uint32_t ncand = cfg.nframes * cfg.nslots;
     const uint32_t grid = (ncand + AW_WARPS - 1) / AW_WARPS;
-    if (cfg.mode != MODE_INDEPENDENT) k_analyze<true><<<grid, 32 * AW_WARPS, 0, st>>>(cfg, descs, pcm, lpcs, cands, abssum, ncand);
-    else k_analyze<false><<<grid, 32 * AW_WARPS, 0, st>>>(cfg, descs, pcm, lpcs, cands, abssum, ncand);
+    if (cfg.mode != MODE_INDEPENDENT) count_launch(), k_analyze<true><<<grid, 32 * AW_WARPS, 0, st>>>(cfg, descs, pcm, lpcs, cands, abssum, ncand);
+    else count_launch(), k_analyze<false><<<grid, 32 * AW_WARPS, 0, st>>>(cfg, descs, pcm, lpcs, cands, abssum, ncand);
     return cudaGetLastError();
 }
 
@@ -743,7 +743,7 @@ cudaError_t launch_lpc2(const EncCfg& cfg, const FrameDesc* descs, const uint8_t
         cudaError_t e = cudaFuncSetAttribute(k_lpc2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         if (e != cudaSuccess) return e;
     }
-    k_lpc2<<<(nwarps + L2_WARPS - 1) / L2_WARPS, 32 * L2_WARPS, smem, st>>>(cfg, descs, pcm, winpool, lpcs, cpw, ncand);
+    count_launch(), k_lpc2<<<(nwarps + L2_WARPS - 1) / L2_WARPS, 32 * L2_WARPS, smem, st>>>(cfg, descs, pcm, winpool, lpcs, cpw, ncand);
     return cudaGetLastError();
 }
 
@@ -1031,9 +1031,9 @@ cudaError_t launch_pack2_crc(const EncCfg& cfg, const FrameDesc* descs, const ui
         if (e != cudaSuccess) return e;
     }
     if (cfg.mode != MODE_INDEPENDENT)
-        k_pack2<true><<<cfg.nframes * nsub_max, AN_THREADS, smem, st>>>(cfg, nsub_max, cap_words, descs, pcm, cands, frecs, out);
+        count_launch(), k_pack2<true><<<cfg.nframes * nsub_max, AN_THREADS, smem, st>>>(cfg, nsub_max, cap_words, descs, pcm, cands, frecs, out);
     else
-        k_pack2<false><<<cfg.nframes * nsub_max, AN_THREADS, smem, st>>>(cfg, nsub_max, cap_words, descs, pcm, cands, frecs, out);
-    k_crc16w<<<(cfg.nframes + 7) / 8, 256, 0, st>>>(frecs, cfg.nframes, out);
+        count_launch(), k_pack2<false><<<cfg.nframes * nsub_max, AN_THREADS, smem, st>>>(cfg, nsub_max, cap_words, descs, pcm, cands, frecs, out);
+    count_launch(), k_crc16w<<<(cfg.nframes + 7) / 8, 256, 0, st>>>(frecs, cfg.nframes, out);
     return cudaGetLastError();
 }

@@ -334,8 +334,8 @@ cudaError_t launch_pack3(const EncCfg& cfg, const FrameDesc* descs, const uint8_
     do {                                                                                                                             \
         cudaError_t e_ = cudaFuncSetAttribute(k_pack3<HBV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);            \
         if (e_ != cudaSuccess) return e_;                                                                                            \
-        k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)small_words * 4, st>>>(cfg, 0u, small_words, descs, pcm, cands, frecs, out);    \
-        k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)cap_words * 4, st>>>(cfg, small_words, cap_words, descs, pcm, cands, frecs, out); \
+        count_launch(), k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)small_words * 4, st>>>(cfg, 0u, small_words, descs, pcm, cands, frecs, out);    \
+        count_launch(), k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)cap_words * 4, st>>>(cfg, small_words, cap_words, descs, pcm, cands, frecs, out); \
     } while (0)
     if (cfg.mode != MODE_INDEPENDENT) {
         switch (hb) {

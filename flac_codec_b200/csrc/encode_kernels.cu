@@ -849,14 +849,14 @@ void launch_planes(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm
                    unsigned long long* abssum, cudaStream_t st)
 {
     dim3 grid((cfg.block_size + 255) / 256, cfg.nframes);
-    k_planes<<<grid, 256, 0, st>>>(cfg, descs, pcm, planes, ormask, abssum);
+    count_launch(), k_planes<<<grid, 256, 0, st>>>(cfg, descs, pcm, planes, ormask, abssum);
 }
 
 void launch_lpc(const EncCfg& cfg, const FrameDesc* descs, const int32_t* planes, const uint32_t* ormask,
                 const unsigned long long* abssum, const double* winpool, LpcRec* lpcs, cudaStream_t st)
 {
     const uint32_t ncand = cfg.nframes * cfg.nslots;
-    k_lpc<<<(ncand + LPC_WARPS - 1) / LPC_WARPS, 32 * LPC_WARPS, 0, st>>>(cfg, descs, planes, ormask, abssum, winpool, lpcs, ncand);
+    count_launch(), k_lpc<<<(ncand + LPC_WARPS - 1) / LPC_WARPS, 32 * LPC_WARPS, 0, st>>>(cfg, descs, planes, ormask, abssum, winpool, lpcs, ncand);
 }
 
 bool residual_uses_smem(const EncCfg& cfg) { return (size_t)cfg.bpad * 8 <= 96 * 1024; }
@@ -871,9 +871,9 @@ cudaError_t launch_residual(const EncCfg& cfg, const FrameDesc* descs, const int
             cudaError_t e = cudaFuncSetAttribute(k_residual<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             if (e != cudaSuccess) return e;
         }
-        k_residual<true><<<ncand, RES_THREADS, smem, st>>>(cfg, descs, planes, ormask, abssum, lpcs, cands, nullptr);
+        count_launch(), k_residual<true><<<ncand, RES_THREADS, smem, st>>>(cfg, descs, planes, ormask, abssum, lpcs, cands, nullptr);
     } else {
-        k_residual<false><<<ncand, RES_THREADS, 0, st>>>(cfg, descs, planes, ormask, abssum, lpcs, cands, scratch);
+        count_launch(), k_residual<false><<<ncand, RES_THREADS, 0, st>>>(cfg, descs, planes, ormask, abssum, lpcs, cands, scratch);
     }
     return cudaGetLastError();
 }
@@ -882,9 +882,9 @@ void launch_decide_scan(const EncCfg& cfg, const FrameDesc* descs, const CandRec
                         FrameRec* frecs, uint32_t* frame_bytes_out, unsigned long long* totals, unsigned long long* mapped_total, uint8_t* out,
                         bool zero_output, cudaStream_t st)
 {
-    k_decide<<<(cfg.nframes + 127) / 128, 128, 0, st>>>(cfg, descs, cands, abssum, frecs);
-    k_scan<<<1, 1024, 0, st>>>(cfg.nframes, frecs, frame_bytes_out, totals, mapped_total);
-    if (zero_output) k_zero<<<148 * 4, 256, 0, st>>>(out, totals);   // the OR-ing packers need it; k_pack3 writes whole frames
+    count_launch(), k_decide<<<(cfg.nframes + 127) / 128, 128, 0, st>>>(cfg, descs, cands, abssum, frecs);
+    count_launch(), k_scan<<<1, 1024, 0, st>>>(cfg.nframes, frecs, frame_bytes_out, totals, mapped_total);
+    if (zero_output) count_launch(), k_zero<<<148 * 4, 256, 0, st>>>(out, totals);   // the OR-ing packers need it; k_pack3 writes whole frames
 }
 
 uint32_t pack_cap_words(const EncCfg& cfg) { return (uint32_t)(((size_t)cfg.bpad * (cfg.bps + 1) + 512) / 32 + 8); }
@@ -901,11 +901,11 @@ cudaError_t launch_pack_crc(const EncCfg& cfg, const FrameDesc* descs, const int
             cudaError_t e = cudaFuncSetAttribute(k_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             if (e != cudaSuccess) return e;
         }
-        k_pack<true><<<cfg.nframes * nsub_max, PACK_THREADS, smem, st>>>(cfg, nsub_max, cap_words, descs, planes, cands, frecs, out);
+        count_launch(), k_pack<true><<<cfg.nframes * nsub_max, PACK_THREADS, smem, st>>>(cfg, nsub_max, cap_words, descs, planes, cands, frecs, out);
     } else {
-        k_pack<false><<<cfg.nframes * nsub_max, PACK_THREADS, 0, st>>>(cfg, nsub_max, cap_words, descs, planes, cands, frecs, out);
+        count_launch(), k_pack<false><<<cfg.nframes * nsub_max, PACK_THREADS, 0, st>>>(cfg, nsub_max, cap_words, descs, planes, cands, frecs, out);
     }
-    k_crc16<<<cfg.nframes, CRC_THREADS, 0, st>>>(frecs, out);
+    count_launch(), k_crc16<<<cfg.nframes, CRC_THREADS, 0, st>>>(frecs, out);
     return cudaGetLastError();
 }
 

@@ -339,7 +339,7 @@ cudaError_t launch_lpc3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t
     const uint32_t nwarps = (cfg.nframes + 1) / 2;
     uint32_t grid = (nwarps + L3_WARPS - 1) / L3_WARPS;
     if (max_ctas && grid > max_ctas) grid = max_ctas;
-    k_lpc3<<<grid, 32 * L3_WARPS, smem, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes);
+    count_launch(), k_lpc3<<<grid, 32 * L3_WARPS, smem, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes);
     return cudaGetLastError();
 }
 

@@ -72,6 +72,9 @@ struct Md5Cfg {
 cudaError_t launch_md5(const Md5Cfg&, const uint8_t*, const Md5Seg*, uint32_t*, cudaStream_t);
 }   // namespace flacb200
 
+namespace flacb200 {
+thread_local unsigned long long g_kernel_launches = 0;
+}
 using namespace flacb200;
 
 struct DevBuf {
@@ -584,7 +587,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     } else {
         e->info_frames = 0;
     }
-    uint32_t launches = 0;
+    const unsigned long long launches0 = g_kernel_launches;
     size_t nchunks = 0;
     bool pipe_overflow = false;
     // FP64 / integer overlap: k_lpc3 of group g + 1 is launched on a second stream as a PERSISTENT grid (a few CTAs per SM --
@@ -674,7 +677,6 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
             }
         }
         nchunks++;
-        launches += fused ? 2u : (need_planes ? 1u : 0u) + (frame_pack ? 6u : 7u);
         if (keep) {
             CK(cudaMemcpyAsync(e->info_cands.data() + base * cfg.nslots, e->cands.p, (size_t)c.nframes * cfg.nslots * sizeof(CandRec),
                                cudaMemcpyDeviceToHost, st));
@@ -714,9 +716,9 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         CK(cudaStreamSynchronize(st));
     }
     cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
-    e->tm.launches = launches;
+    e->tm.launches = (uint32_t)(g_kernel_launches - launches0);
     if (e->profiling) {
-        const uint32_t per_chunk[5] = {need_planes ? 1u : 0u, 1, 1, frame_pack ? 2u : 3u, frame_pack ? 1u : 2u};   // planes, lpc, analyze, decide+scan(+zero), pack(+crc16)
+        const uint32_t per_chunk[5] = {need_planes ? 1u : 0u, 1, 1, frame_pack ? 2u : 3u, 2u};   // planes, lpc, analyze, decide+scan(+zero), pack(+crc16)
         for (size_t ck = 0; ck < nchunks; ck++)
             for (int k = 0; k < 5; k++) {
                 float ms = 0;
@@ -796,7 +798,7 @@ constexpr size_t MBOX_UP = 256;
 // bytes (a multiple of 4) of device memory -> mailbox slot `off`, on stream st; read e->mbox_h + off after syncing st
 static void mbox_post(flacb200_engine* e, size_t off, const void* d_src, size_t bytes, cudaStream_t st)
 {
-    k_copy_words<<<1, 64, 0, st>>>((uint32_t*)(e->mbox_d + off), (const uint32_t*)d_src, bytes / 4);
+    count_launch(), k_copy_words<<<1, 64, 0, st>>>((uint32_t*)(e->mbox_d + off), (const uint32_t*)d_src, bytes / 4);
 }
 
 // Host frames -> host PCM for many streams: the segments (independent streams) are cut into batches by bytes; the upload
@@ -956,7 +958,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
         if (rm) return rm;
         CK(cudaStreamSynchronize(st));   // (the previous call's kernel may still be reading the upload area)
         memcpy(e->mbox_h + MBOX_UP, segs.data(), n_segments * sizeof(DecSeg));
-        k_copy_words<<<(unsigned)std::min<size_t>((n_segments * sizeof(DecSeg) / 4 + 255) / 256, 64), 256, 0, st>>>(
+        count_launch(), k_copy_words<<<(unsigned)std::min<size_t>((n_segments * sizeof(DecSeg) / 4 + 255) / 256, 64), 256, 0, st>>>(
             (uint32_t*)e->dec[2].p, (const uint32_t*)(e->mbox_d + MBOX_UP), n_segments * sizeof(DecSeg) / 4);
     }
     if (e->profiling) cudaEventRecord(e->ev[21], st);
@@ -979,7 +981,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     CK(cudaStreamSynchronize(st));
     ncand = ((const uint32_t*)e->mbox_h)[0];
     max_bs = ((const uint32_t*)e->mbox_h)[1];
-    uint32_t launches = 2;
+    const unsigned long long launches0 = g_kernel_launches;
     ENS(e->dec[6], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(FrameCand));
     ENS(e->dec[7], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(DecRec));
     ENS(e->dec[8], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(unsigned long long));
@@ -988,7 +990,6 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     unsigned long long* d_pos = (unsigned long long*)e->dec[8].p;
     if (ncand) {
         launch_find_write(cfg, d_bytes, d_segs, (const uint32_t*)e->dec[4].p, d_cands, st);
-        launches++;
     }
     time_mark(e, ev++);
     cfg.bstride = (std::max<uint32_t>(max_bs, 4) + 3u) & ~3u;
@@ -1041,7 +1042,6 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
             time_mark(e, ev++);
             launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
             time_mark(e, ev++);
-            launches += 5u + (maybe_wide ? 1u : 0u) + (clean == 1 ? 0u : 1u);
             ngroups++;
         } else {
             if (n) {
@@ -1055,10 +1055,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
                 time_mark(e, ev++);
                 launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
                 time_mark(e, ev++);
-                launches += 4;
                 ngroups++;
-            } else {
-                launches += 1;
             }
         }
         g0 += n;
@@ -1074,7 +1071,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     if (n_pcm_out) *n_pcm_out = state.samples_total;
     e->last_ncand = ncand;
     cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
-    e->tm.launches = launches;
+    e->tm.launches = (uint32_t)(g_kernel_launches - launches0);
     if (e->profiling) {
         float ms = 0;
         cudaEventElapsedTime(&ms, e->evpool[0], e->evpool[1]);
@@ -1196,7 +1193,7 @@ extern "C" int flacb200_debug_libm(flacb200_engine* e, int fn, const double* in,
     double* d_in = (double*)e->scratch.p;
     double* d_out = d_in + n;
     CK(cudaMemcpyAsync(d_in, in, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    k_debug_libm<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, e->stream>>>(fn, d_in, d_out, n);
+    count_launch(), k_debug_libm<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, e->stream>>>(fn, d_in, d_out, n);
     CK(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return 0;

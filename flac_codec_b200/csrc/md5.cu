@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(32) k_md5(Md5Cfg cfg, const uint8_t* __restric
 cudaError_t launch_md5(const Md5Cfg& cfg, const uint8_t* pcm, const Md5Seg* segs, uint32_t* digests, cudaStream_t st)
 {
     if (cfg.nseg == 0) return cudaSuccess;
-    k_md5<<<(cfg.nseg + 31) / 32, 32, 0, st>>>(cfg, pcm, segs, digests);
+    count_launch(), k_md5<<<(cfg.nseg + 31) / 32, 32, 0, st>>>(cfg, pcm, segs, digests);
     return cudaGetLastError();
 }
 

@@ -76,7 +76,7 @@ cudaError_t launch_synth(uint8_t* pcm, unsigned long long first_track, unsigned 
     p.bytes_per_sample = (bps + 7) / 8;
     const unsigned long long total = n_tracks * n_pcm_frames;
     if (total == 0) return cudaSuccess;
-    k_synth<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, lut, pcm);
+    count_launch(), k_synth<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, lut, pcm);
     return cudaGetLastError();
 }
 

@@ -28,6 +28,52 @@ from flacb200_testutil import ref_file, synth_pcm
 C5_SHAPES = ((2, 4096, 30), (2, 16384, 30), (8, 4096, 10), (8, 16384, 10))   # channels, block size, seconds
 
 
+class _Pinned:
+    """Pinned host buffers for the batch-ABI legs (pageable memory would time the driver's staging copies)."""
+
+    def __init__(self):
+        from flac_codec_b200 import _abi
+
+        self.L, self.ptrs = _abi.lib(), []
+
+    def buf(self, nbytes, src=None):
+        import ctypes
+
+        p = self.L.flacb200_host_alloc(nbytes)
+        if not p:
+            raise MemoryError("flacb200_host_alloc")
+        self.ptrs.append(p)
+        a = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(p))
+        if src is not None:
+            a[:] = src
+        return p, a
+
+    def free(self):
+        for p in self.ptrs:
+            self.L.flacb200_host_free(p)
+        self.ptrs = []
+
+
+def _encode_pinned(eng, opt, rate, bps, ch, raw, n, reps):
+    """eng.encode of one stream with pinned PCM in and pinned frames out; returns (seconds, frame bytes, sizes, total)."""
+    from flac_codec_b200 import _abi
+
+    pin = _Pinned()
+    try:
+        hp, _ = pin.buf(raw.nbytes, raw)
+        cap = raw.nbytes + raw.nbytes // 8 + (1 << 20)
+        ho, hout = pin.buf(cap)
+
+        def enc():
+            return eng.encode(opt, rate, bps, ch, hp, raw.nbytes, _abi.PCM_BYTES_LE, [(0, n, 0)], out=ho, out_capacity=cap)
+
+        enc()
+        t, (_, sizes, total) = _best(enc, reps)
+        return t, hout[:total].tobytes(), sizes, total
+    finally:
+        pin.free()
+
+
 def _best(fn, reps):
     best, out = 1e30, None
     for _ in range(max(reps, 1)):
@@ -85,12 +131,8 @@ def c3(eng, fo, reps=2, seconds=60):
     cores = os.cpu_count() or 1
     ref, ref_sizes = fo.encode_frames_only(fo.options("best"), rate, bps, ch, x, nthreads=cores)
 
-    def enc():
-        return eng.encode(Options.best(), rate, bps, ch, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, n, 0)])
-
-    enc()
-    t, (data, sizes, total) = _best(enc, reps)
-    ident = data.tobytes() == ref
+    t, data, sizes, total = _encode_pinned(eng, Options.best(), rate, bps, ch, raw, n, reps)
+    ident = data == ref
     same = int((np.asarray(sizes) == np.asarray(ref_sizes)).sum()) if len(sizes) == len(ref_sizes) else 0
     return [{"name": f"C3 {seconds} s 96k/24/8ch best, all frames", "msamples_per_s": x.size / t / 1e6, "ms": t * 1e3, "identical": ident,
              "frames": int(len(ref_sizes)), "equal_frame_sizes": same, "size_delta": (total - len(ref)) / len(ref)}]
@@ -111,13 +153,9 @@ def c5(eng, fo, reps=1, shapes=C5_SHAPES):
         ref, _ = fo.encode_frames_only(opt5, rate, bps, ch, x, nthreads=cores)
         o5 = Options.best().max_lpc_order(32).block_size(block)
 
-        def enc():
-            return eng.encode(o5, rate, bps, ch, raw, raw.nbytes, _abi.PCM_BYTES_LE, [(0, n, 0)])
-
-        enc()
-        t, (data, _, total) = _best(enc, reps)
+        t, data, _, total = _encode_pinned(eng, o5, rate, bps, ch, raw, n, reps)
         legs.append({"name": f"C5 encode {seconds} s 192k/32/{ch}ch LPC<=32 block {block}", "msamples_per_s": x.size / t / 1e6,
-                     "ms": t * 1e3, "identical": data.tobytes() == ref, "frames": int(len(sizes5))})
+                     "ms": t * 1e3, "identical": data == ref, "frames": int(len(sizes5))})
         for legacy, label in ((0, "k_parse+k_restore"), (64, "k_decode")):
             eng.set_option("legacy", legacy)
             try:
