@@ -932,15 +932,40 @@ __device__ void chain_slice(ChainSmem& sm, const DecCfg& cfg, const uint8_t* __r
         if (active && fc.seg == st.expect_seg) pos += st.seg_samples;
         DecRec r = recs[c];
         uint32_t err = r.err;
-        if (sg.n_pcm && pos >= sg.n_pcm) {   // Some(0) => Ok(None): the stream was already complete
-            pos_out[c] = ~0ull;
-            sm.mark[c] = 0;
-            continue;
+        if (sg.n_pcm && pos >= sg.n_pcm) {
+            // Some(0) => Ok(None): the reader stops at the frame that would start exactly at the announced total, and at
+            // everything behind it.  A frame beyond the total is reached only when an earlier one overshot the total (then no
+            // frame ever starts exactly there): look for the total among the running sums of this segment in front of c.
+            bool stopped = pos == sg.n_pcm;
+            if (!stopped) {
+                const unsigned long long off = (active && fc.seg == st.expect_seg) ? st.seg_samples : 0ull;
+                if (sg.n_pcm >= off) {
+                    const unsigned long long base = lo ? sm.pref[lo - 1] : 0u;
+                    const unsigned long long V = sg.n_pcm - off + base;
+                    if (V == base) stopped = true;
+                    else {
+                        uint32_t a = lo, b = c;
+                        while (a < b) {
+                            const uint32_t mid = (a + b) >> 1;
+                            if (sm.pref[mid] < V) a = mid + 1;
+                            else b = mid;
+                        }
+                        stopped = a < c && sm.pref[a] == V;
+                    }
+                }
+            }
+            if (stopped) {
+                pos_out[c] = ~0ull;
+                sm.mark[c] = 0;
+                continue;
+            }
         }
         if (sg.n_pcm) {
-            const unsigned long long remaining = sg.n_pcm - pos;
+            // `total - current_sample` in u64 (src/decode.rs:1400): a frame that overshoots the announced total is accepted when it
+            // has more than 14 samples, and from then on the difference has wrapped -- the reader never sees Some(0) again and
+            // runs into the end of the bytes (Io) after delivering every frame (release builds; a debug build panics)
+            const unsigned long long remaining = sg.n_pcm - pos;   // wraps like the reference's
             if (!(fc.block_size == remaining || fc.block_size > 14)) err = 21;   // ShortBlock
-            else if (fc.block_size > remaining && err == 0) err = 59;             // SampleCountMismatch
         }
         if (err == 0 && sg.pcm_off + pos + fc.block_size > cfg.out_samples) err = 0x80000000u;   // output too small
         recs[c].err = err;
@@ -950,7 +975,7 @@ __device__ void chain_slice(ChainSmem& sm, const DecCfg& cfg, const uint8_t* __r
             ebits |= 1u << k;
             continue;
         }
-        const bool done = sg.n_pcm != 0 && pos + fc.block_size >= sg.n_pcm;
+        const bool done = sg.n_pcm != 0 && pos + fc.block_size == sg.n_pcm;
         if (sm.flag[c] & 2) {   // the bytes after this frame are not a valid frame header
             uint32_t bs, hl, ca;
             uint32_t he = parse_frame_header(bytes + r.end, sg.byte_end - r.end, cfg, &bs, &hl, &ca);

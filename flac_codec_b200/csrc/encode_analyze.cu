@@ -578,7 +578,10 @@ cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uin
                             unsigned long long* abssum, cudaStream_t st)
 {
     const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
-    constexpr size_t pad_ = 0;
+#ifndef FLACB200_A3_PAD
+#define FLACB200_A3_PAD 0
+#endif
+    constexpr size_t pad_ = FLACB200_A3_PAD;   // occupancy experiments (tools/build_variant.sh)
 #define FLACB200_A3(HBV, ST)                                                                                                          \
     do {                                                                                                                              \
         const size_t smem_ = a3_smem_bytes<ST>() + pad_;                                                                              \

@@ -1087,10 +1087,10 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     }
     if (pcm_location == FLACB200_HOST) {
         size_t bytes = pcm_out_bytes;
-        if (extent_known && pcm_kind != FLACB200_PCM_I32_PLANAR)
-            bytes = std::min<size_t>(bytes, (size_t)extent * cfg.channels * cfg.bytes_per_sample);
         if (n_segments == 1 && pcm_kind != FLACB200_PCM_I32_PLANAR)   // one stream: nothing lies behind what the walk delivered
             bytes = std::min<size_t>(bytes, (size_t)(segs[0].pcm_off + state.samples_total) * cfg.channels * cfg.bytes_per_sample);
+        else if (extent_known && pcm_kind != FLACB200_PCM_I32_PLANAR)   // (+ one block: a last frame may overshoot its announced total)
+            bytes = std::min<size_t>(bytes, (size_t)(extent + 65536) * cfg.channels * cfg.bytes_per_sample);
         if (e->profiling) cudaEventRecord(e->ev[24], st);
         CK(cudaMemcpyAsync(pcm_out, d_out, bytes, cudaMemcpyDeviceToHost, st));
         if (e->profiling) cudaEventRecord(e->ev[25], st);

@@ -798,10 +798,13 @@ int reader_next_window(flacb200_reader& r, int want_kind)
     if (!r.engine) return FLACB200_E_NO_DEVICE;
     const flacb200_streaminfo& si = r.si;
     const uint64_t total = si.total_samples;
-    if (total && r.decoded_samples >= total) {   // Some(0) => Ok(None)  (src/decode.rs:1402)
+    if (total && r.decoded_samples == total) {   // Some(0) => Ok(None)  (src/decode.rs:1402)
         r.at_end = true;
         return 0;
     }
+    // (a last frame that overshot the announced total: `total - current_sample` has wrapped in the reference (:1400), its reader
+    // goes on until the bytes end and fails there with Io; here the rest is decoded as a stream of unknown length, then Io)
+    const bool overshot = total && r.decoded_samples > total;
     flacb200_stream_params prm{};
     prm.sample_rate = si.sample_rate;
     prm.bits_per_sample = si.bits_per_sample;
@@ -815,16 +818,16 @@ int reader_next_window(flacb200_reader& r, int want_kind)
         const bool source_done = !r.fed_mode || r.fed_eof;
         if (avail == 0) {
             if (!source_done) return FLACB200_NEED_DATA;
-            if (total) return r.sticky_error = E_IO;   // FrameHeader::read hits EOF with samples outstanding
+            if (total) return r.sticky_error = E_IO;   // FrameHeader::read hits EOF with samples outstanding (or after an overshoot)
             r.at_end = true;                           // unsized stream: EOF at a frame boundary ends it (:1416)
             return 0;
         }
         const size_t take = std::min(avail, want);
         const bool last_window = take == avail && source_done;
-        const uint64_t remaining = total ? total - r.decoded_samples : 0;
+        const uint64_t remaining = (total && !overshot) ? total - r.decoded_samples : 0;
         // the PCM budget of the window; with a known total the final window must be able to hold everything that remains
         uint64_t cap = cap_pcm;
-        if (total) cap = std::min<uint64_t>(cap, remaining + si.max_block_size);
+        if (total && !overshot) cap = std::min<uint64_t>(cap, remaining + si.max_block_size);
         r.win_kind = want_kind == FLACB200_PCM_I32_INTERLEAVED ? FLACB200_PCM_I32_INTERLEAVED : FLACB200_PCM_BYTES_LE;
         const size_t fb = (size_t)si.channels * (r.win_kind == FLACB200_PCM_I32_INTERLEAVED ? 4 : (si.bits_per_sample + 7) / 8);
         if (!r.win.reserve((size_t)cap * fb + 64, true)) return FLACB200_E_OUT_OF_MEMORY;
@@ -849,6 +852,7 @@ int reader_next_window(flacb200_reader& r, int want_kind)
         // nothing decoded
         if (rc == 0) {   // unsized stream whose last bytes are no frame (fewer than 16: EOF inside a header, :1416), or an empty window
             if (last_window) {
+                if (overshot) return r.sticky_error = E_IO;
                 r.at_end = true;
                 return 0;
             }

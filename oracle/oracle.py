@@ -271,7 +271,8 @@ def decode_stream_ex(flac: bytes):
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     a = np.frombuffer(flac, dtype=np.uint8)
     si = read_streaminfo(flac)
-    cap = si.total_samples * si.channels if si.total_samples else max(len(flac) * 64, 1 << 16)
+    # (room for frames that overshoot an understated total: the serial reader delivers them before it fails)
+    cap = (si.total_samples + 4 * 65536) * si.channels if si.total_samples else max(len(flac) * 64, 1 << 16)
     out = np.zeros(cap, dtype=np.int32)
     nf, ns = C.c_uint64(0), C.c_uint64(0)
     r = L.fo_decode_stream_ex(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(si), None, C.byref(nf), C.byref(ns))

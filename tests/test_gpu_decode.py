@@ -530,3 +530,39 @@ def test_encode_decode_round_trip_at_bench_shape(eng, fo):
     assert np.array_equal(a, b)
     for p in (d_pcm, d_flac, d_back):
         eng.device_free(p)
+
+
+def test_last_frame_overshoots_an_understated_total(eng, fo, decode_path):
+    """STREAMINFO announces fewer samples than the frames hold: `total - current_sample` (src/decode.rs:1400) passes the
+    ShortBlock rule for a block of more than 14 samples, the frame is delivered, the difference wraps (release build) and the
+    reader runs into the end of the bytes: every frame comes out, then Io.  The GPU walk and the reader handle do the same."""
+    import io
+
+    from flac_codec_b200 import _abi, stream as st
+
+    x = synth_pcm(31, 2, 4096 * 5 + 3000, 44100, 16).reshape(-1)
+    flac, sizes = fo.encode_stream(fo.options("default", padding=None), 44100, 16, 2, x, total_known=True)
+    si = fo.read_streaminfo(flac)
+    for short_by in (100, 4096 * 2 + 50):
+        lied = bytearray(flac)
+        v = int.from_bytes(lied[4 + 4 + 10:4 + 4 + 18], "big")
+        total = (v & 0xFFFFFFFFF) - short_by
+        lied[4 + 4 + 10:4 + 4 + 18] = ((v & ~0xFFFFFFFFF) | total).to_bytes(8, "big")
+        code, nf, ns, ref = fo.decode_stream_ex(bytes(lied))
+        assert (code, nf) == (1, len(sizes)) and np.array_equal(ref, x)      # all frames, then Io
+        frames = np.frombuffer(bytes(lied), dtype=np.uint8)[si.frames_start:].copy()
+        out = np.zeros(x.size + 8192, dtype=np.int32)
+        with pytest.raises(_abi.FlacB200Error) as ei:
+            eng.decode(44100, 16, 2, 4096, frames, frames.size, [(0, frames.size, 0, total)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+        assert (ei.value.code, ei.value.bad_frame) == (1, len(sizes))
+        assert np.array_equal(out[: x.size], x)
+        r = st.FlacSampleReader(bytes(lied), engine=eng, window_bytes=20000)
+        got = []
+        with pytest.raises(_abi.FlacB200Error) as ei:
+            while True:
+                a = r.read(10000)
+                if a.size == 0:
+                    break
+                got.append(a.copy())
+        assert ei.value.code == 1 and np.array_equal(np.concatenate(got), x)
+        r.close()
