@@ -135,7 +135,12 @@ __device__ inline uint32_t find_segment(const DecSeg* __restrict__ segs, uint32_
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t FIND_THREADS = 256;
 constexpr uint32_t FIND_TILE = FIND_THREADS * 32;
+constexpr uint32_t FIND_SLOTS = 8;   // candidates a tile (8 KB of frames) can park; ordinary streams have one or two
 
+// WRITE = 0: count per tile.  1: write the candidates at their ordered rank (tile_base from the scan of the counts).
+// 2: count AND park the tile's first FIND_SLOTS candidates in its slots (cands = the slot array): the bytes are read once;
+// k_find_compact then moves the parked records to their ordered places.  A tile with more candidates raises max_bs[1] and
+// the host falls back to the second pass (streams of very small blocks).
 template <int WRITE>
 __global__ void __launch_bounds__(FIND_THREADS) k_find(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
                                                        uint32_t* __restrict__ tile_counts, const uint32_t* __restrict__ tile_base,
@@ -179,9 +184,8 @@ __global__ void __launch_bounds__(FIND_THREADS) k_find(DecCfg cfg, const uint8_t
             c.off = off; c.block_size = bs; c.seg = s; c.hdr_len = (uint8_t)hl; c.assignment = (uint8_t)ca;
             c.pad0 = c.pad1 = 0; c.pad2 = 0;
             found[nfound++] = c;
-        } else {
-            atomicMax(max_bs, bs);
         }
+        if (WRITE != 1) atomicMax(max_bs, bs);
     }
     // ordered rank of this thread's candidates inside the tile
     uint32_t incl = valid;
@@ -197,12 +201,27 @@ __global__ void __launch_bounds__(FIND_THREADS) k_find(DecCfg cfg, const uint8_t
         if (k < wid) before += wsum[k];
         total += wsum[k];
     }
-    if (!WRITE) {
-        if (tid == 0) tile_counts[blockIdx.x] = total;
-        return;
+    if (WRITE != 1) {
+        if (tid == 0) {
+            tile_counts[blockIdx.x] = total;
+            if (WRITE == 2 && total > FIND_SLOTS) max_bs[1] = 1;
+        }
+        if (WRITE == 0) return;
     }
-    uint32_t rank = tile_base[blockIdx.x] + before + incl - valid;
-    for (uint32_t k = 0; k < nfound; k++) cands[rank + k] = found[k];
+    const uint32_t rank = (WRITE == 1 ? tile_base[blockIdx.x] : 0u) + before + incl - valid;
+    for (uint32_t k = 0; k < nfound; k++) {
+        if (WRITE == 1) cands[rank + k] = found[k];
+        else if (rank + k < FIND_SLOTS) cands[(size_t)blockIdx.x * FIND_SLOTS + rank + k] = found[k];
+    }
+}
+
+// parked candidates -> their ordered places
+__global__ void __launch_bounds__(256) k_find_compact(uint32_t tiles, const uint32_t* __restrict__ tile_counts, const uint32_t* __restrict__ tile_base,
+                                                      const FrameCand* __restrict__ slots, FrameCand* __restrict__ cands)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t tile = (uint32_t)(i / FIND_SLOTS), s = (uint32_t)(i % FIND_SLOTS);
+    if (tile < tiles && s < tile_counts[tile]) cands[tile_base[tile] + s] = slots[i];
 }
 
 // exclusive scan of n counts (single CTA of 1024 threads); total written to out[n]
@@ -1404,6 +1423,24 @@ void launch_find_count(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* se
     const uint32_t tiles = find_tiles(cfg.nbytes);
     count_launch(), k_find<0><<<tiles, FIND_THREADS, 0, st>>>(cfg, bytes, segs, tile_counts, nullptr, nullptr, max_bs);
     count_launch(), k_scan_u32<<<1, 1024, 0, st>>>(tiles, tile_counts, tile_base);
+}
+
+size_t find_slots_bytes(unsigned long long nbytes) { return (size_t)find_tiles(nbytes) * FIND_SLOTS * sizeof(FrameCand); }
+
+// single pass: counts, parked candidates, scan of the counts
+void launch_find_park(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, uint32_t* tile_counts, uint32_t* tile_base, FrameCand* slots,
+                      uint32_t* max_bs, cudaStream_t st)
+{
+    const uint32_t tiles = find_tiles(cfg.nbytes);
+    count_launch(), k_find<2><<<tiles, FIND_THREADS, 0, st>>>(cfg, bytes, segs, tile_counts, nullptr, slots, max_bs);
+    count_launch(), k_scan_u32<<<1, 1024, 0, st>>>(tiles, tile_counts, tile_base);
+}
+
+void launch_find_compact(const DecCfg& cfg, const uint32_t* tile_counts, const uint32_t* tile_base, const FrameCand* slots, FrameCand* cands, cudaStream_t st)
+{
+    const uint32_t tiles = find_tiles(cfg.nbytes);
+    const size_t n = (size_t)tiles * FIND_SLOTS;
+    count_launch(), k_find_compact<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tiles, tile_counts, tile_base, slots, cands);
 }
 
 void launch_find_write(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const uint32_t* tile_base, FrameCand* cands, cudaStream_t st)

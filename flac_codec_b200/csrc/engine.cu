@@ -51,6 +51,9 @@ cudaError_t launch_synth(uint8_t* pcm, unsigned long long first_track, unsigned 
 uint32_t find_tiles(unsigned long long nbytes);
 void launch_find_count(const DecCfg&, const uint8_t*, const DecSeg*, uint32_t*, uint32_t*, uint32_t*, cudaStream_t);
 void launch_find_write(const DecCfg&, const uint8_t*, const DecSeg*, const uint32_t*, FrameCand*, cudaStream_t);
+size_t find_slots_bytes(unsigned long long nbytes);
+void launch_find_park(const DecCfg&, const uint8_t*, const DecSeg*, uint32_t*, uint32_t*, FrameCand*, uint32_t*, cudaStream_t);
+void launch_find_compact(const DecCfg&, const uint32_t*, const uint32_t*, const FrameCand*, FrameCand*, cudaStream_t);
 void launch_decode(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, DecRec*, bool, cudaStream_t);
 // decode_parse.cu
 void launch_parse(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, SubRec*, DecRec*, cudaStream_t);
@@ -110,7 +113,7 @@ struct flacb200_engine {
                                 // kernels on C4 (45 vs 41 ms per step), so it is an option, not the default
     int sm_count = 148;
     std::vector<cudaEvent_t> lpc_ev;   // per group: LPC parameters ready, analysis done (the two LpcRec buffers alternate)
-    DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, lookback, dec[12];
+    DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, lookback, find_slots, dec[12];
     std::map<uint32_t, uint32_t> win_off;   // block length -> offset in doubles
     std::vector<double> win_host;
     flacb200_options win_opt{};
@@ -245,7 +248,7 @@ void flacb200_engine_destroy(flacb200_engine* e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pcm, &e->planes, &e->masks, &e->lpcs, &e->cands, &e->frecs, &e->descs, &e->out, &e->fbytes, &e->totals, &e->winpool,
-                      &e->scratch, &e->lut, &e->lookback};
+                      &e->scratch, &e->lut, &e->lookback, &e->find_slots};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto& b : e->dec)
@@ -974,13 +977,22 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     cudaEventRecord(e->ev[22], st);
     size_t ev = 0;
     time_mark(e, ev++);
-    launch_find_count(cfg, d_bytes, d_segs, (uint32_t*)e->dec[3].p, (uint32_t*)e->dec[4].p, d_maxbs, st);
+    // frame discovery reads the bytes ONCE: every tile counts its candidates and parks them in its slots; the second pass over
+    // the bytes only runs when a tile had more candidates than slots (legacy bit 256 forces it, for the tests)
+    const bool park = !(e->legacy & 256u);
+    if (park) {
+        ENS(e->find_slots, find_slots_bytes(frames_bytes) + 64);
+        launch_find_park(cfg, d_bytes, d_segs, (uint32_t*)e->dec[3].p, (uint32_t*)e->dec[4].p, (FrameCand*)e->find_slots.p, d_maxbs, st);
+    } else {
+        launch_find_count(cfg, d_bytes, d_segs, (uint32_t*)e->dec[3].p, (uint32_t*)e->dec[4].p, d_maxbs, st);
+    }
     uint32_t ncand = 0, max_bs = 0;
     mbox_post(e, 0, (uint32_t*)e->dec[4].p + tiles, 4, st);
-    mbox_post(e, 4, d_maxbs, 4, st);
+    mbox_post(e, 4, d_maxbs, 8, st);   // max block size, slot overflow flag
     CK(cudaStreamSynchronize(st));
     ncand = ((const uint32_t*)e->mbox_h)[0];
     max_bs = ((const uint32_t*)e->mbox_h)[1];
+    const bool parked = park && ((const uint32_t*)e->mbox_h)[2] == 0;
     const unsigned long long launches0 = g_kernel_launches;
     ENS(e->dec[6], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(FrameCand));
     ENS(e->dec[7], (size_t)std::max<uint32_t>(ncand, 1) * sizeof(DecRec));
@@ -989,7 +1001,8 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     DecRec* d_recs = (DecRec*)e->dec[7].p;
     unsigned long long* d_pos = (unsigned long long*)e->dec[8].p;
     if (ncand) {
-        launch_find_write(cfg, d_bytes, d_segs, (const uint32_t*)e->dec[4].p, d_cands, st);
+        if (parked) launch_find_compact(cfg, (const uint32_t*)e->dec[3].p, (const uint32_t*)e->dec[4].p, (const FrameCand*)e->find_slots.p, d_cands, st);
+        else launch_find_write(cfg, d_bytes, d_segs, (const uint32_t*)e->dec[4].p, d_cands, st);
     }
     time_mark(e, ev++);
     cfg.bstride = (std::max<uint32_t>(max_bs, 4) + 3u) & ~3u;

@@ -566,3 +566,28 @@ def test_last_frame_overshoots_an_understated_total(eng, fo, decode_path):
                 got.append(a.copy())
         assert ei.value.code == 1 and np.array_equal(np.concatenate(got), x)
         r.close()
+
+
+def test_single_pass_frame_discovery_equals_two_passes(eng, fo, decode_path):
+    """k_find parks a tile's candidates while it counts them (the bytes are read once); a tile with more candidates than
+    slots -- streams of tiny blocks -- sends the call back to the second pass.  Both give the same frames (legacy bit 256 forces
+    the two-pass form)."""
+    from flac_codec_b200 import _abi
+
+    base = 64 if decode_path == "thread-per-frame" else 0
+    cases = [(synth_pcm(50, 2, 4096 * 40 + 99, 44100, 16), fo.options("default"), 44100, 16),              # one or two candidates per tile
+             (synth_pcm(51, 1, 16 * 3000 + 5, 44100, 16), fo.options("default", block_size=16), 44100, 16),   # hundreds per tile: second pass
+             (synth_pcm(52, 2, 192 * 500, 48000, 24), fo.options("best", block_size=192), 48000, 24)]
+    for x, opt, rate, bps in cases:
+        ch = x.shape[1]
+        frames, sizes = fo.encode_frames_only(opt, rate, bps, ch, x.reshape(-1))
+        buf = np.frombuffer(frames, dtype=np.uint8).copy()
+        outs = []
+        for legacy in (base, base | 256):
+            eng.set_option("legacy", legacy)
+            out = np.zeros(x.size, dtype=np.int32)
+            nf, ns = eng.decode(rate, bps, ch, opt.block_size, buf, buf.size, [(0, buf.size, 0, x.shape[0])], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+            assert (nf, ns) == (len(sizes), x.shape[0])
+            outs.append(out)
+        eng.set_option("legacy", base)
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0].reshape(-1, ch), x)
