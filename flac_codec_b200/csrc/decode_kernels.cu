@@ -777,26 +777,21 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecCfg cfg, const uint8_
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t CRCF_THREADS = 256;
 
-__device__ Crc16Tables g_dec_crc16_tabs;   // built once per device (building them per CTA cost a third of k_crc16f)
+__device__ Crc16Fold g_dec_crc16_tabs;   // built once per device, read through L1 (no per-CTA copy)
 
 __global__ void k_dec_crc16_tables_init()
 {
-    crc16_tables_init(g_dec_crc16_tabs);
+    crc16_fold_init(g_dec_crc16_tabs);
 }
 
 __global__ void __launch_bounds__(CRCF_THREADS) k_crc16f(const uint8_t* __restrict__ bytes, const FrameCand* __restrict__ cands, uint32_t ncand,
                                                         DecRec* __restrict__ recs)
 {
-    __shared__ Crc16Tables tabs;
-    static_assert(sizeof(Crc16Tables) % 2 == 0, "copied as 16-bit words");
-    for (uint32_t i = threadIdx.x; i < sizeof(Crc16Tables) / 2; i += CRCF_THREADS)
-        reinterpret_cast<uint16_t*>(&tabs)[i] = reinterpret_cast<const uint16_t*>(&g_dec_crc16_tabs)[i];
-    __syncthreads();
     const uint32_t c = blockIdx.x * (CRCF_THREADS / 32) + (threadIdx.x >> 5);
     if (c >= ncand) return;
     if (recs[c].err) return;
     const unsigned long long off = cands[c].off, end = recs[c].end;
-    const uint32_t crc = crc16_warp(tabs, bytes, off, end - off);
+    const uint32_t crc = crc16_warp_fold(g_dec_crc16_tabs, bytes, off, end - off);
     if ((threadIdx.x & 31) == 0 && crc != 0) recs[c].err = 40;   // Crc16Mismatch
 }
 
