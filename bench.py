@@ -406,7 +406,8 @@ def run_gpu(args):
 
         src, back = dev_u8(d_pcm, pcm_bytes), dev_u8(d_back, pcm_bytes)
         exact = bool(torch.equal(src, back)) and ns == n_tracks * n
-        dnames = ["k_find+k_scan", "k_parse", "k_restore || k_crc16f+k_chain_fast", None, "k_emit"]
+        # packed 24-bit stereo output: k_parse, CRC-16 + the frame walk, then the fused restoration + emit pass (engine.cu)
+        dnames = ["k_find+k_scan", "k_parse", "k_crc16f+k_chain_fast", "k_restore_emit", "fallback (k_chain, k_restore+k_emit)"]
         line["decode"] = {"metric": "decode_msamples_per_s", "value": samples_per_step * world / (dms_step * 1e-3) / 1e6, "unit": UNIT,
                           "ms_per_step": dms_step, "frames": int(nf), "bit_exact_vs_input": exact,
                           "kernel_ms_per_step": {dnames[k]: dk[k] / args.steps for k in range(5) if dnames[k]},

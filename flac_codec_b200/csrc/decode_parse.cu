@@ -31,6 +31,7 @@ namespace flacb200 {
 
 constexpr uint32_t PARSE_THREADS = 64;
 constexpr uint32_t RESTORE_THREADS = 64;
+constexpr uint32_t RE_MAX_ORDER = 16;   // longest predictor of the fused restoration + emit kernel (k_restore_emit)
 
 enum : uint32_t { TK_RAW = 0, TK_RICE = 1, TK_FILL = 2 };
 
@@ -278,9 +279,9 @@ __device__ __forceinline__ uint32_t parse_subframe_header(LaneBits& br, LaneSub&
     return 0;
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
+__global__ void __launch_bounds__(PARSE_THREADS, 16) k_parse(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
                                                         const FrameCand* __restrict__ cands, uint32_t ncand, int32_t* __restrict__ planes,
-                                                        SubRec* __restrict__ subs, DecRec* __restrict__ recs)
+                                                        SubRec* __restrict__ subs, DecRec* __restrict__ recs, uint32_t* __restrict__ high_order)
 {
     const uint32_t c = blockIdx.x * PARSE_THREADS + threadIdx.x;
     const bool exists = c < ncand;
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) k_parse(DecCfg cfg, const uint8
             const bool is_side = ca >= 8 && ((ch == 0) == (ca == 9));
             const uint32_t e = parse_subframe_header(br, sf, is_side ? cfg.bps + 1 : cfg.bps, n, endbit, rec);
             if (e) { err = e; live = act = false; }
+            else if (sf.order > RE_MAX_ORDER) atomicOr(high_order, 1u);   // k_restore_emit keeps two predictors of at most this length in registers
         }
         int32_t* const plane = planes + plane_base(cfg, exists ? c : 0, ch);   // groups of four samples are 128 words apart
         const uint32_t n4 = __reduce_max_sync(0xffffffffu, act ? (n + 3u) & ~3u : 0u);
@@ -502,10 +504,257 @@ __global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const F
     }
 }
 
-void launch_parse(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes, SubRec* subs,
-                  DecRec* recs, cudaStream_t st)
+
+// ---- k_restore_emit: predictor restoration, stereo restoration and the packed PCM write in ONE pass over the planes --------
+// k_restore rewrote every plane in place (one read + one write of 4 bytes per sample) and k_emit4 read it again.  Here a warp
+// owns a bundle of 32 frames: lane = frame, BOTH channels of it -- two independent predictor chains per lane (the recurrence is
+// latency-bound: a second chain fills its bubbles) and the mid/side arithmetic of src/decode.rs:1524-1626 needs no exchange
+// between lanes.  Per step a lane restores one group of four samples per channel (coefficients and sliding windows in
+// registers, planes staged by cp.async RE_RING groups ahead), restores stereo, narrows and packs the 4 * C * B bytes
+// (Frame::to_buf, src/audio.rs:110-134) into the warp's shared-memory tile [frame][group]; every RE_TG groups the warp writes
+// each frame's run of the tile (32 samples = 8 * C * B words) with contiguous stores.  The planes are read once and nothing is
+// written back: per sample 4 bytes in + B bytes out instead of 4 + 4 + 4 + B.
+// It needs every frame's output position, so it runs after the frame walk (k_chain_fast / k_chain), not beside it.
+// Shapes: 1-2 channels, 2-3 bytes per sample, packed output; predictors longer than RE_MAX_ORDER (k_parse raises *high_order)
+// leave the launch group to k_restore + k_emit.
+constexpr uint32_t RE_RING = 4;     // groups of four samples in flight per lane and channel
+constexpr uint32_t RE_TG = 8;       // groups per output tile
+constexpr uint32_t RE_WARPS = 2;    // independent bundles per CTA
+
+template <int C, int B, int HB>
+__device__ __forceinline__ void restore_emit_run(const int32_t* const (&plane)[C], uint32_t n, uint32_t nmax4, const uint32_t (&order)[C],
+                                                 const uint32_t (&shift)[C], const uint32_t (&wasted)[C], const SubRec* const (&rec)[C], uint32_t ca,
+                                                 bool be, int4* ring, uint32_t* tile, const unsigned long long* s_base, const uint32_t* s_n,
+                                                 uint8_t* __restrict__ out)
 {
-    count_launch(), k_parse<<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs);
+    constexpr int W = HB > 0 ? HB : 1;
+    // the sample window is a circular buffer of W + 4 registers with STATIC indices: U steps of four samples bring it back to
+    // where it started, so the step loop is unrolled U times and a tile holds a multiple of U steps (no register moves)
+    constexpr int WN = W + 4;
+    constexpr uint32_t U = HB > 0 ? WN / 4 : 1;
+    constexpr uint32_t TG = (RE_TG / U) * U;    // groups per output tile
+    constexpr uint32_t CB = C * B;              // bytes per inter-channel sample = words per group of four
+    constexpr uint32_t RW = TG * CB, ROW = RW + 1;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n4 = (n + 3u) & ~3u;
+    int32_t q[C][W], w[C][W + 4];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) {
+#pragma unroll
+        for (int j = 0; j < W; j++) q[ch][j] = (HB > 0 && (uint32_t)j < order[ch]) ? (int32_t)rec[ch]->coef[j] : 0;
+#pragma unroll
+        for (int j = 0; j < WN; j++) w[ch][j] = 0;
+    }
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+    auto request = [&](uint32_t s0) {   // the group at sample s0 of both planes -> slot (s0 / 4) % RE_RING; one commit per call
+        if (s0 < n4) {
+#pragma unroll
+            for (int ch = 0; ch < C; ch++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_addr + (((s0 >> 2) & (RE_RING - 1)) * C + ch) * 512u),
+                             "l"(plane[ch] + plane_off(s0))
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (uint32_t g = 0; g < RE_RING; g++) request(g * 4);
+    const bool ms = ca == 10;
+    const uint32_t add_b = ca == 9 ? 0xFFFFFFFFu : 0u, sub_b = ca == 8 ? 0xFFFFFFFFu : 0u;
+    // this lane's frame can take the fast copy-out of a tile: a 4-byte aligned run of whole words
+    const bool row_ok = s_base[lane] != ~0ull && ((reinterpret_cast<uintptr_t>(out) + s_base[lane]) & 3) == 0;
+    for (uint32_t t0 = 0; t0 < nmax4; t0 += 4 * TG) {
+        const uint32_t gmax = min(TG, (nmax4 - t0) >> 2);
+#pragma unroll 1
+        for (uint32_t g0 = 0; g0 < gmax; g0 += U) {
+#pragma unroll
+          for (uint32_t u = 0; u < U; u++) {
+            const uint32_t g = g0 + u;
+            if (g >= gmax) break;
+            const uint32_t s0 = t0 + 4 * g;
+            const bool on = s0 < n4;
+            asm volatile("cp.async.wait_group %0;" ::"n"(RE_RING - 1) : "memory");
+            int32_t x[C][4];
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) {
+                int4 a = make_int4(0, 0, 0, 0);
+                if (on) a = ring[(((s0 >> 2) & (RE_RING - 1)) * C + ch) * 32 + lane];
+                const int32_t v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    int32_t xe = v[e];
+                    if (HB > 0) {
+                        long long sum = 0;
+#pragma unroll
+                        for (int j = 0; j < W; j++) sum = mad_wide_s32(w[ch][(W + 4 * u + e - 1 - j + WN) % WN], q[ch][j], sum);
+                        const uint32_t pred = __funnelshift_r((uint32_t)(unsigned long long)sum, (uint32_t)((unsigned long long)sum >> 32), shift[ch]);
+                        if (s0 + e >= order[ch]) xe = (int32_t)((uint32_t)xe + pred);   // warm-up samples are stored as they are
+                        w[ch][(W + 4 * u + e) % WN] = xe;
+                    }
+                    x[ch][e] = (int32_t)((uint32_t)xe << wasted[ch]);   // `<<= wasted_bps`  src/decode.rs:1671
+                }
+            }
+            request(s0 + 4 * RE_RING);   // into the slot just read
+            // stereo restoration (src/decode.rs:1524-1626) without branches -- the lanes of a warp are different frames with
+            // different channel assignments -- then the sample's B low bytes in the caller's byte order
+            uint32_t val[4 * C];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (C == 1) val[e] = (uint32_t)x[0][e];
+                else {
+                    const uint32_t av = (uint32_t)x[0][e], bv = (uint32_t)x[C - 1][e];
+                    const uint32_t sum = av * 2u + (bv & 1u);                       // mid/side: `mid` with the bit the encoder dropped
+                    const uint32_t lm = (uint32_t)((int32_t)(sum + bv) >> 1), rm = (uint32_t)((int32_t)(sum - bv) >> 1);
+                    const uint32_t l = av + (bv & add_b);                           // side/right: left = side + right
+                    const uint32_t r = bv + ((av - bv - bv) & sub_b);               // left/side: right = left - side
+                    val[e * C] = ms ? lm : l;
+                    val[e * C + C - 1] = ms ? rm : r;
+                }
+            }
+            if (be) {
+#pragma unroll
+                for (int i = 0; i < 4 * C; i++) val[i] = __byte_perm(val[i], 0, B == 3 ? 0x3012 : 0x3201);
+            }
+            uint32_t* const dst = tile + lane * ROW + g * CB;
+            if (B == 3) {
+#pragma unroll
+                for (int i = 0; i < C; i++) {   // four samples -> three words
+                    dst[3 * i + 0] = __byte_perm(val[4 * i + 0], val[4 * i + 1], 0x4210);
+                    dst[3 * i + 1] = __byte_perm(val[4 * i + 1], val[4 * i + 2], 0x5421);
+                    dst[3 * i + 2] = __byte_perm(val[4 * i + 2], val[4 * i + 3], 0x6542);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2 * C; i++) dst[i] = __byte_perm(val[2 * i], val[2 * i + 1], 0x5410);
+            }
+          }
+        }
+        __syncwarp();
+        // the warp writes every frame's run of the tile
+        if (__all_sync(0xffffffffu, row_ok && n >= t0 + 4 * TG)) {   // the usual tile: 32 whole, aligned runs
+            uint8_t* const lane_out = out + (size_t)t0 * CB + lane * 4;
+#pragma unroll 8
+            for (uint32_t f = 0; f < 32; f++) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(lane_out + s_base[f]);
+                const uint32_t* row = tile + f * ROW + lane;
+                dst[0] = row[0];
+                if (RW > 32 && lane < RW - 32) dst[32] = row[32];
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t f = 0; f < 32; f++) {
+                const unsigned long long base = s_base[f];
+                const uint32_t nf = s_n[f];
+                if (base == ~0ull || nf <= t0) continue;
+                const uint32_t nbytes = min(nf - t0, 4 * TG) * CB;
+                const unsigned long long byte0 = base + (unsigned long long)t0 * CB;
+                const uint32_t* row = tile + f * ROW;
+                if (((reinterpret_cast<uintptr_t>(out) + byte0) & 3) == 0) {
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(out + byte0);
+                    const uint32_t nw = nbytes >> 2;
+                    if (lane < nw) dst[lane] = row[lane];
+                    if (RW > 32 && lane + 32 < nw) dst[lane + 32] = row[lane + 32];
+                    const uint32_t tail = nbytes & 3;   // a block that ends inside a word
+                    if (lane < tail) out[byte0 + nw * 4 + lane] = (uint8_t)(row[nw] >> (8 * lane));
+                } else {
+                    for (uint32_t k = lane; k < nbytes; k += 32) out[byte0 + k] = (uint8_t)(row[k >> 2] >> (8 * (k & 3)));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int C, int B>
+__global__ void __launch_bounds__(32 * RE_WARPS, 8) k_restore_emit(DecCfg cfg, const FrameCand* __restrict__ cands, uint32_t ncand,
+                                                                   const SubRec* __restrict__ subs, const DecRec* __restrict__ recs,
+                                                                   const unsigned long long* __restrict__ pos, const int32_t* __restrict__ planes,
+                                                                   uint8_t* __restrict__ out, const uint32_t* __restrict__ flags, uint32_t need_clean)
+{
+    static_assert(RE_TG * C * B <= 64, "a frame's run of the tile is written with at most two stores per lane");
+    // flags[0]: k_chain_fast's verdict (1: pos[] is final); flags[1]: a predictor longer than RE_MAX_ORDER was seen
+    if (flags[1] != 0 || (need_clean && flags[0] != 1)) return;
+    constexpr uint32_t ROW = RE_TG * C * B + 1;
+    __shared__ int4 s_ring[RE_WARPS][RE_RING * C * 32];
+    __shared__ uint32_t s_tile[RE_WARPS][32 * ROW];
+    __shared__ unsigned long long s_base[RE_WARPS][32];
+    __shared__ uint32_t s_n[RE_WARPS][32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t c = (blockIdx.x * RE_WARPS + wid) * 32 + lane;
+    uint32_t n = 0, ca = 0, order[C], shift[C], wasted[C];
+    const SubRec* rec[C];
+    const int32_t* plane[C];
+    unsigned long long base = ~0ull;
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) {
+        order[ch] = shift[ch] = wasted[ch] = 0;
+        rec[ch] = subs;
+        plane[ch] = planes + plane_base(cfg, c < ncand ? c : 0, ch);
+    }
+    if (c < ncand) {
+        const FrameCand fc = cands[c];
+        const unsigned long long p = pos[c];
+        const uint32_t nch = fc.assignment <= 7 ? fc.assignment + 1u : 2u;
+        bool ok = p != ~0ull && nch == (uint32_t)C && recs[c].err == 0;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) {
+            rec[ch] = subs + (size_t)c * cfg.channels + ch;
+            ok = ok && rec[ch]->kind != 0xFF;
+        }
+        if (ok) {
+            n = fc.block_size;
+            ca = fc.assignment;
+            base = p * (unsigned long long)(C * B);
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) {
+                order[ch] = rec[ch]->order;
+                shift[ch] = rec[ch]->shift;
+                wasted[ch] = rec[ch]->wasted;
+            }
+        }
+    }
+    s_base[wid][lane] = base;
+    s_n[wid][lane] = n;
+    __syncwarp();
+    uint32_t omax = 0;
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) omax = max(omax, order[ch]);
+    const uint32_t nmax4 = __reduce_max_sync(0xffffffffu, (n + 3u) & ~3u);
+    const uint32_t cls = __reduce_max_sync(0xffffffffu, n ? (omax + 3u) >> 2 : 0u);
+    if (nmax4 == 0) return;
+    const bool be = cfg.pcm_kind == 1;
+#define FLACB200_RE(HBV) restore_emit_run<C, B, HBV>(plane, n, nmax4, order, shift, wasted, rec, ca, be, s_ring[wid], s_tile[wid], s_base[wid], s_n[wid], out)
+    switch (cls) {
+    case 0: FLACB200_RE(0); break;
+    case 1: FLACB200_RE(4); break;
+    case 2: FLACB200_RE(8); break;
+    case 3: FLACB200_RE(12); break;
+    default: FLACB200_RE(16); break;   // (cls <= 4: flags[1] is raised otherwise)
+    }
+#undef FLACB200_RE
+}
+
+bool restore_emit_ok(const DecCfg& cfg, const uint8_t* out)
+{
+    return cfg.pcm_kind <= 1 && cfg.nslots == cfg.channels && cfg.channels <= 2 && (cfg.bytes_per_sample == 2 || cfg.bytes_per_sample == 3) &&
+           (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (cfg.bstride & 3) == 0;
+}
+
+void launch_restore_emit(const DecCfg& cfg, const FrameCand* cands, uint32_t n, const SubRec* subs, const DecRec* recs, const unsigned long long* pos,
+                         const int32_t* planes, uint8_t* out, const uint32_t* flags, bool need_clean, cudaStream_t st)
+{
+    const uint32_t bundles = (n + 31) / 32, grid = (bundles + RE_WARPS - 1) / RE_WARPS;
+    const uint32_t nc = need_clean ? 1u : 0u;
+    if (cfg.channels == 1 && cfg.bytes_per_sample == 2) count_launch(), k_restore_emit<1, 2><<<grid, 32 * RE_WARPS, 0, st>>>(cfg, cands, n, subs, recs, pos, planes, out, flags, nc);
+    else if (cfg.channels == 1) count_launch(), k_restore_emit<1, 3><<<grid, 32 * RE_WARPS, 0, st>>>(cfg, cands, n, subs, recs, pos, planes, out, flags, nc);
+    else if (cfg.bytes_per_sample == 2) count_launch(), k_restore_emit<2, 2><<<grid, 32 * RE_WARPS, 0, st>>>(cfg, cands, n, subs, recs, pos, planes, out, flags, nc);
+    else count_launch(), k_restore_emit<2, 3><<<grid, 32 * RE_WARPS, 0, st>>>(cfg, cands, n, subs, recs, pos, planes, out, flags, nc);
+}
+
+void launch_parse(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes, SubRec* subs,
+                  DecRec* recs, uint32_t* high_order, cudaStream_t st)
+{
+    count_launch(), k_parse<<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs, high_order);
 }
 
 void launch_restore(const DecCfg& cfg, const FrameCand* cands, uint32_t n, const SubRec* subs, const DecRec* recs, int32_t* planes, cudaStream_t st)

@@ -56,7 +56,10 @@ void launch_find_park(const DecCfg&, const uint8_t*, const DecSeg*, uint32_t*, u
 void launch_find_compact(const DecCfg&, const uint32_t*, const uint32_t*, const FrameCand*, FrameCand*, cudaStream_t);
 void launch_decode(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, DecRec*, bool, cudaStream_t);
 // decode_parse.cu
-void launch_parse(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, SubRec*, DecRec*, cudaStream_t);
+void launch_parse(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, uint32_t, int32_t*, SubRec*, DecRec*, uint32_t*, cudaStream_t);
+bool restore_emit_ok(const DecCfg&, const uint8_t*);
+void launch_restore_emit(const DecCfg&, const FrameCand*, uint32_t, const SubRec*, const DecRec*, const unsigned long long*, const int32_t*, uint8_t*,
+                         const uint32_t*, bool, cudaStream_t);
 void launch_restore(const DecCfg&, const FrameCand*, uint32_t, const SubRec*, const DecRec*, int32_t*, cudaStream_t);
 void launch_crc16f(const uint8_t*, const FrameCand*, uint32_t, DecRec*, cudaStream_t);
 cudaError_t launch_chain(const DecCfg&, const uint8_t*, const DecSeg*, const FrameCand*, DecRec*, uint32_t, const FrameCand*, uint32_t,
@@ -1031,14 +1034,45 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
                 CK(cudaEventCreateWithFlags(&pe, cudaEventDisableTiming));
                 e->pipe_ev.push_back(pe);
             }
-            launch_parse(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, (SubRec*)e->dec[10].p, d_recs + g0, st);
+            uint32_t* d_clean = (uint32_t*)((uint8_t*)e->dec[5].p + 192);   // [0] k_chain_fast's verdict, [1] a predictor longer than k_restore_emit's
+            launch_parse(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, (SubRec*)e->dec[10].p, d_recs + g0, d_clean + 1, st);
             if (maybe_wide) launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, true, st);
             time_mark(e, ev++);
-            // The tails: predictor restoration on the engine's stream; CRC-16 and the frame walk on the second one.  The
+            if (restore_emit_ok(cfg, d_out) && !(e->legacy & 512u)) {
+                // packed 16/24-bit mono/stereo output: CRC-16 and the frame walk first (they need only the end offsets k_parse
+                // found), then ONE pass over the planes that restores the predictors and the stereo pair and writes the packed
+                // PCM (k_restore_emit).  It is queued before the host has read the walk's verdict and checks it itself; when
+                // k_chain_fast declined the group the general walk runs and the kernel is launched again, and a launch group
+                // with predictors beyond its register budget goes through k_restore + k_emit.
+                launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, st);
+                launch_chain_fast(cfg, d_segs, d_cands + g0, d_recs + g0, n, ncand - g0, g0 == 0, d_pos + g0, d_state, d_clean, st);
+                mbox_post(e, 8, d_clean, 8, st);
+                CK(cudaEventRecord(e->pipe_ev[3 * ngroups], st));
+                time_mark(e, ev++);
+                launch_restore_emit(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, d_out,
+                                    d_clean, true, st);
+                CK(cudaEventSynchronize(e->pipe_ev[3 * ngroups]));
+                const uint32_t clean = ((const uint32_t*)e->mbox_h)[2], high = ((const uint32_t*)e->mbox_h)[3];
+                if (clean != 1 && e->debug) fprintf(stderr, "flacb200: k_chain_fast declined group at %u (reason 0x%x)\n", g0, clean);
+                time_mark(e, ev++);
+                if (clean != 1) CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, st));
+                if (high) {
+                    launch_restore(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, (int32_t*)e->dec[9].p, st);
+                    launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
+                } else if (clean != 1) {
+                    launch_restore_emit(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p,
+                                        d_out, d_clean, false, st);
+                }
+                time_mark(e, ev++);
+                ngroups++;
+                g0 += n;
+                continue;
+            }
+            // other layouts: two independent tails that meet before k_emit -- predictor restoration on the engine's stream; CRC-16
+            // and the frame walk on the second one.  The
             // walk is k_chain_fast when the candidates are exactly the frames (the host reads its verdict: a 4-byte copy and
             // a sync of the second stream, while k_restore keeps the GPU busy), else k_chain -- one CTA that wants a whole
             // SM's shared memory and therefore only starts once k_restore has drained.
-            uint32_t* d_clean = (uint32_t*)((uint8_t*)e->dec[5].p + 192);
             CK(cudaEventRecord(e->pipe_ev[3 * ngroups], st));
             launch_restore(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, (int32_t*)e->dec[9].p, st);
             CK(cudaStreamWaitEvent(aux, e->pipe_ev[3 * ngroups], 0));

@@ -384,7 +384,23 @@ class FlacSampleReader(_Reader):
         return buf[: self._read(buf, n_samples, _abi.PCM_I32_INTERLEAVED)]
 
     def read_to_end(self) -> np.ndarray:
-        out = []
+        total = self._si.total_samples * self._si.channels
+        if total:   # announced length: one buffer, filled in place (no per-chunk copies); an understated total falls through
+            buf = np.empty(total, dtype=np.int32)
+            got = 0
+            while got < total:
+                n = self._read(buf[got:], total - got, _abi.PCM_I32_INTERLEAVED)
+                if n == 0:
+                    break
+                got += n
+            if got < total:
+                return buf[:got]
+            rest = self.read(1 << 16)
+            if rest.size == 0:
+                return buf
+            out = [buf, rest.copy()]
+        else:
+            out = []
         while True:
             a = self.read(1 << 22)
             if a.size == 0:

@@ -69,6 +69,16 @@ def _encode_pinned(eng, opt, rate, bps, ch, raw, n, reps):
 
         enc()
         t, (_, sizes, total) = _best(enc, reps)
+        eng.set_profiling(True)   # one more call with the engine's own stage clock: what the wall time is made of
+        try:
+            enc()
+            tm = eng.timings()
+            _encode_pinned.engine_ms = {"h2d": round(float(tm.h2d_ms), 3), "planes": round(float(tm.kernel_ms[0]), 3),
+                                        "lpc": round(float(tm.kernel_ms[1]), 3), "analysis": round(float(tm.kernel_ms[2]), 3),
+                                        "decide_scan": round(float(tm.kernel_ms[3]), 3), "pack": round(float(tm.kernel_ms[4]), 3),
+                                        "d2h": round(float(tm.d2h_ms), 3)}
+        finally:
+            eng.set_profiling(False)
         return t, hout[:total].tobytes(), sizes, total
     finally:
         pin.free()
@@ -135,7 +145,8 @@ def c3(eng, fo, reps=2, seconds=60):
     ident = data == ref
     same = int((np.asarray(sizes) == np.asarray(ref_sizes)).sum()) if len(sizes) == len(ref_sizes) else 0
     return [{"name": f"C3 {seconds} s 96k/24/8ch best, all frames", "msamples_per_s": x.size / t / 1e6, "ms": t * 1e3, "identical": ident,
-             "frames": int(len(ref_sizes)), "equal_frame_sizes": same, "size_delta": (total - len(ref)) / len(ref)}]
+             "frames": int(len(ref_sizes)), "equal_frame_sizes": same, "size_delta": (total - len(ref)) / len(ref),
+             "engine_ms": _encode_pinned.engine_ms}]
 
 
 def c5(eng, fo, reps=1, shapes=C5_SHAPES):
@@ -155,7 +166,7 @@ def c5(eng, fo, reps=1, shapes=C5_SHAPES):
 
         t, data, _, total = _encode_pinned(eng, o5, rate, bps, ch, raw, n, reps)
         legs.append({"name": f"C5 encode {seconds} s 192k/32/{ch}ch LPC<=32 block {block}", "msamples_per_s": x.size / t / 1e6,
-                     "ms": t * 1e3, "identical": data == ref, "frames": int(len(sizes5))})
+                     "ms": t * 1e3, "identical": data == ref, "frames": int(len(sizes5)), "engine_ms": _encode_pinned.engine_ms})
         for legacy, label in ((0, "k_parse+k_restore"), (64, "k_decode")):
             eng.set_option("legacy", legacy)
             try:

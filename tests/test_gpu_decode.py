@@ -21,10 +21,11 @@ def eng():
     e.close()
 
 
-@pytest.fixture(autouse=True, params=["parse+restore", "thread-per-frame"])
+@pytest.fixture(autouse=True, params=["parse+restore", "thread-per-frame", "unfused"])
 def decode_path(request, eng):
-    """Every test runs over both decoders: k_parse + k_restore (default) and k_decode ("legacy" bit 64)."""
-    eng.set_option("legacy", 64 if request.param == "thread-per-frame" else 0)
+    """Every test runs over both decoders: k_parse + k_restore (default; packed 16/24-bit mono/stereo output goes through the
+    fused k_restore_emit) and k_decode ("legacy" bit 64); "unfused" (bit 512) keeps k_restore + k_emit4 for those layouts."""
+    eng.set_option("legacy", {"thread-per-frame": 64, "unfused": 512}.get(request.param, 0))
     yield request.param
     eng.set_option("legacy", 0)
 
@@ -458,6 +459,17 @@ def test_bit_flips_give_the_reference_verdict(eng, fo):
                 got = (e.code, e.bad_frame)
             assert got == (code, nf), (name, t, pos, got, (code, nf))
             assert np.array_equal(out[:ns], ref), (name, t, pos)
+            if si.bps <= 24 and si.channels <= 2 and t % 2 == 0:   # the packed-bytes layout (k_restore_emit after whichever walk ran)
+                nb = (si.bps + 7) // 8
+                outb = np.zeros(si.total_samples * si.channels * nb, dtype=np.uint8)
+                got = (0, nf)
+                try:
+                    eng.decode(si.sample_rate, si.bps, si.channels, si.max_block_size, frames, frames.size,
+                               [(0, frames.size, 0, si.total_samples)], outb, outb.nbytes, _abi.PCM_BYTES_LE)
+                except _abi.FlacB200Error as e:
+                    got = (e.code, e.bad_frame)
+                assert got == (code, nf), (name, t, pos, got, (code, nf), "bytes")
+                assert np.array_equal(fo.bytes_to_samples(outb[: ns * nb].tobytes(), nb), ref), (name, t, pos, "bytes")
             flac[pos >> 3] ^= 0x80 >> (pos & 7)
 
 

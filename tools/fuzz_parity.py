@@ -74,23 +74,26 @@ def run(iters, seed, eng=None):
                 want_err = (oe.code, fi)
                 break
             off += int(sz)
-        for legacy in ("", "64"):
-            eng.set_option("legacy", int(legacy or 0))
-            out = np.zeros(x.size, dtype=np.int32)
+        packed = bps <= 24 and ch <= 2   # packed little-endian bytes: k_restore_emit (default) and k_restore + k_emit4 (bit 512)
+        for legacy, kind in ((0, _abi.PCM_I32_INTERLEAVED), (64, _abi.PCM_I32_INTERLEAVED)) + (((0, _abi.PCM_BYTES_LE), (512, _abi.PCM_BYTES_LE)) if packed else ()):
+            label = {0: "k_parse+k_restore", 64: "k_decode", 512: "unfused"}[legacy] + (" bytes" if kind == _abi.PCM_BYTES_LE else "")
+            eng.set_option("legacy", legacy)
+            out = np.zeros(x.size, dtype=np.int32) if kind == _abi.PCM_I32_INTERLEAVED else np.zeros(x.size * nb, dtype=np.uint8)
             buf = np.frombuffer(ref, dtype=np.uint8).copy()
             try:
-                nf, ns = eng.decode(rate, bps, ch, block, buf, buf.size, [(0, buf.size, 0, n)], out, out.nbytes, _abi.PCM_I32_INTERLEAVED)
+                nf, ns = eng.decode(rate, bps, ch, block, buf, buf.size, [(0, buf.size, 0, n)], out, out.nbytes, kind)
             except _abi.FlacB200Error as e:
                 if want_err == (e.code, e.bad_frame):
                     continue   # same error at the same frame as the reference decoder
                 eng.set_option("legacy", 0)
-                return f"DECODE ERROR {desc} ({'k_decode' if legacy else 'k_parse+k_restore'}): {e}; the oracle: {want_err}"
+                return f"DECODE ERROR {desc} ({label}): {e}; the oracle: {want_err}"
             if want_err is not None:
                 eng.set_option("legacy", 0)
-                return f"DECODE ACCEPTED what the oracle rejects {desc} ({'k_decode' if legacy else 'k_parse+k_restore'}): {want_err}"
-            if ns != n or not np.array_equal(out.reshape(-1, ch), x):
+                return f"DECODE ACCEPTED what the oracle rejects {desc} ({label}): {want_err}"
+            got = out if kind == _abi.PCM_I32_INTERLEAVED else fo.bytes_to_samples(out.tobytes(), nb)
+            if ns != n or not np.array_equal(np.asarray(got).reshape(-1, ch), x):
                 eng.set_option("legacy", 0)
-                return f"DECODE MISMATCH {desc} ({'k_decode' if legacy else 'k_parse+k_restore'}, {ns} samples)"
+                return f"DECODE MISMATCH {desc} ({label}, {ns} samples)"
         eng.set_option("legacy", 0)
     return None
 

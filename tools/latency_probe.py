@@ -80,6 +80,32 @@ def main():
                 "host_stages_ms": {s: round(float(tmh.kernel_ms[i]), 3) for i, s in enumerate(STAGES)},
                 "host_h2d_ms": round(float(tmh.h2d_ms), 3), "host_d2h_ms": round(float(tmh.d2h_ms), 3),
                 "host_msamples_per_s": n * ch / t_host / 1e6, "resident_msamples_per_s": n * ch / t_res / 1e6}
+        # decode of the same frames: host frames -> host PCM (pinned), then device-resident
+        hq = L.flacb200_host_alloc(nbytes + 64)
+        d_back = eng.device_alloc(nbytes + 64)
+        eng.memcpy(d_out, ho, total, 1)
+        bsz = opt.c.block_size
+
+        def dec_host():
+            return eng.decode(rate, bps, ch, bsz, ho, total, [(0, total, 0, n)], hq, nbytes, _abi.PCM_BYTES_LE)
+
+        def dec_res():
+            return eng.decode(rate, bps, ch, bsz, d_out, total, [(0, total, 0, n)], d_back, nbytes, _abi.PCM_BYTES_LE,
+                              frames_location=_abi.DEVICE, pcm_location=_abi.DEVICE)
+
+        dec_host(), dec_res()
+        td_host, (nf, ns) = best(dec_host)
+        td_res, _ = best(dec_res)
+        same = bytes((ctypes.c_uint8 * nbytes).from_address(hq)) == bytes((ctypes.c_uint8 * nbytes).from_address(hp))
+        eng.set_profiling(True)
+        dec_res()
+        td = eng.timings()
+        eng.set_profiling(False)
+        line["decode"] = {"host_ms": td_host * 1e3, "resident_ms": td_res * 1e3, "frames": int(nf), "bit_exact": bool(same and ns == n),
+                          "launches": int(td.launches), "resident_stages_ms": [round(float(v), 3) for v in td.kernel_ms[:6]],
+                          "host_msamples_per_s": n * ch / td_host / 1e6, "resident_msamples_per_s": n * ch / td_res / 1e6}
+        L.flacb200_host_free(hq)
+        eng.device_free(d_back)
         print(json.dumps(line), flush=True)
         eng.device_free(d_pcm)
         eng.device_free(d_out)
