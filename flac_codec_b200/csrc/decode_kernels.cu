@@ -160,12 +160,16 @@ __global__ void __launch_bounds__(FIND_THREADS) k_find(DecCfg cfg, const uint8_t
         for (uint32_t i = 0; i < 33; i++)
             if (p0 + i < cfg.nbytes) w[i >> 2] |= (uint32_t)bytes[p0 + i] << (8 * (i & 3));
     }
-    // bit i of `hits`: bytes p0+i, p0+i+1 look like a sync code (0xFF, 0b1111100x)
+    // bit i of `hits`: bytes p0+i, p0+i+1 look like a sync code (0xFF, 0b1111100x).  Four byte positions per step: d has a
+    // zero byte exactly where the byte is 0xFF and its successor is 0xF8 or 0xF9; an exact zero-byte test marks those bytes
+    // with 0x80 and a multiplication gathers the four marks into a nibble
     uint32_t hits = 0;
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-        const uint32_t pair = __funnelshift_r(w[i >> 2], w[(i >> 2) + 1], 8 * (i & 3)) & 0xffffu;
-        if ((pair & 0xfeffu) == 0xf8ffu) hits |= 1u << i;
+    for (int k = 0; k < 8; k++) {
+        const uint32_t u = __funnelshift_r(w[k], w[k + 1], 8);                                   // the bytes one position on
+        const uint32_t d = ~w[k] | ((u & 0xfefefefeu) ^ 0xf8f8f8f8u);
+        const uint32_t z = ~(((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d | 0x7f7f7f7fu);               // 0x80 in exactly the zero bytes of d
+        hits |= ((((z >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * k);                            // bits 0, 8, 16, 24 -> a nibble
     }
     uint32_t valid = 0;
     FrameCand found[4];   // at most 4 candidates per 32 bytes are kept (a header is >= 6 bytes; both passes apply the same cap)

@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "../../include/flacb200.h"
@@ -389,7 +390,7 @@ static uint32_t window_offset(flacb200_engine* e, const flacb200_options& o, uin
 
 // per-kernel timing: events are recorded back to back on the engine's stream and read after the call's
 // final synchronisation, so profiling adds no host synchronisation inside the timed region
-static void time_mark(flacb200_engine* e, size_t idx)
+static void time_mark(flacb200_engine* e, size_t idx, cudaStream_t on = nullptr)
 {
     if (!e->profiling) return;
     while (e->evpool.size() <= idx) {
@@ -397,7 +398,7 @@ static void time_mark(flacb200_engine* e, size_t idx)
         cudaEventCreate(&ev);
         e->evpool.push_back(ev);
     }
-    cudaEventRecord(e->evpool[idx], e->stream);
+    cudaEventRecord(e->evpool[idx], on ? on : e->stream);
 }
 
 extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, const flacb200_stream_params* params, const void* pcm,
@@ -1014,17 +1015,95 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     size_t budget = (size_t)6 << 30;
     uint32_t group = (uint32_t)std::min<size_t>(std::max<size_t>(budget / per_frame, 1), std::max<uint32_t>(ncand, 1));
     if (e->chunk_frames) group = std::min<uint32_t>(group, e->chunk_frames);
-    ENS(e->dec[9], (size_t)((group + 31u) & ~31u) * per_frame);   // whole bundles of 32 interleaved planes
     // FLACB200_LEGACY bit 64: the thread-per-frame decoder (k_decode) for everything; default: k_parse + k_restore, and
     // k_decode only for frames with a 33-bit side channel (32-bit stereo streams)
     const bool split_decode = !(e->legacy & 64u);
     const bool maybe_wide = cfg.channels == 2 && cfg.bps == 32;
-    if (split_decode) ENS(e->dec[10], (size_t)group * cfg.channels * sizeof(SubRec));
+    // stage spans of the profile: {event a, event b, stage} (stages overlap in the pipelined path)
+    std::vector<std::array<size_t, 3>> spans;
+    spans.push_back({0, 1, 0});
     size_t ngroups = 0;
     uint32_t g0 = 0;
+    const bool fuse = split_decode && ncand && restore_emit_ok(cfg, d_out) && !(e->legacy & 512u);
+    if (fuse) {
+        // Packed 16/24-bit mono/stereo output.  Per launch group: k_parse; CRC-16 and the frame walk (they need only the end
+        // offsets k_parse found); then ONE pass over the planes that restores the predictors and the stereo pair and writes the
+        // packed PCM (k_restore_emit).  The groups are software-pipelined over two plane buffers: k_parse of group g + 1 runs
+        // on the engine's stream beside the tail of group g on the second stream -- the single-CTA frame walk, the host's look
+        // at its verdict and the drain of every kernel are hidden behind the other stream's work.  k_restore_emit is queued
+        // before the host has read the walk's verdict and checks it itself; when k_chain_fast declined the group the general
+        // walk runs and the kernel is launched again; predictors beyond its register budget: k_restore + k_emit.
+        cudaStream_t aux = e->aux;
+        size_t buf_budget = (size_t)3 << 30;
+        uint32_t pg = (uint32_t)std::min<size_t>(std::max<size_t>(buf_budget / per_frame, 1), ncand);
+        if (e->chunk_frames) pg = std::min<uint32_t>(pg, e->chunk_frames);
+        if (pg < ncand && (size_t)pg * 2 >= ncand) pg = (ncand + 1) / 2;   // two groups: equal halves
+        const uint32_t nbuf = pg < ncand ? 2u : 1u;
+        const size_t plane_stride = (size_t)((pg + 31u) & ~31u) * cfg.nslots * cfg.bstride;   // int32 per buffer
+        const size_t sub_stride = (size_t)pg * cfg.channels;
+        ENS(e->dec[9], nbuf * plane_stride * sizeof(int32_t));
+        ENS(e->dec[10], nbuf * sub_stride * sizeof(SubRec));
+        const size_t G = (ncand + pg - 1) / pg;
+        while (e->pipe_ev.size() < 3 * G) {
+            cudaEvent_t pe;
+            CK(cudaEventCreateWithFlags(&pe, cudaEventDisableTiming));
+            e->pipe_ev.push_back(pe);
+        }
+        uint32_t* d_clean = (uint32_t*)((uint8_t*)e->dec[5].p + 192);   // [0] k_chain_fast's verdict, [1] a predictor longer than k_restore_emit's
+        auto planes_of = [&](size_t g) { return (int32_t*)e->dec[9].p + (g & (nbuf - 1)) * plane_stride; };
+        auto subs_of = [&](size_t g) { return (SubRec*)e->dec[10].p + (g & (nbuf - 1)) * sub_stride; };
+        auto parse = [&](size_t g) {
+            const uint32_t f0 = (uint32_t)(g * pg), n = std::min<uint32_t>(pg, ncand - f0);
+            if (g >= 2) cudaStreamWaitEvent(st, e->pipe_ev[3 * (g - 2) + 2], 0);   // the buffer's previous group has been emitted
+            const size_t a = ev++;
+            time_mark(e, a);
+            launch_parse(cfg, d_bytes, d_segs, d_cands + f0, n, planes_of(g), subs_of(g), d_recs + f0, d_clean + 1, st);
+            time_mark(e, ev++);
+            spans.push_back({a, a + 1, 1});
+            cudaEventRecord(e->pipe_ev[3 * g], st);
+        };
+        parse(0);
+        for (size_t g = 0; g < G; g++) {
+            const uint32_t f0 = (uint32_t)(g * pg), n = std::min<uint32_t>(pg, ncand - f0);
+            const FrameCand* after = f0 + n < ncand ? d_cands + f0 + n : nullptr;
+            CK(cudaStreamWaitEvent(aux, e->pipe_ev[3 * g], 0));
+            const size_t t0 = ev;
+            ev += 4;
+            time_mark(e, t0, aux);
+            launch_crc16f(d_bytes, d_cands + f0, n, d_recs + f0, aux);
+            launch_chain_fast(cfg, d_segs, d_cands + f0, d_recs + f0, n, ncand - f0, f0 == 0, d_pos + f0, d_state, d_clean, aux);
+            mbox_post(e, 8, d_clean, 8, aux);
+            CK(cudaEventRecord(e->pipe_ev[3 * g + 1], aux));
+            time_mark(e, t0 + 1, aux);
+            launch_restore_emit(cfg, d_cands + f0, n, subs_of(g), d_recs + f0, d_pos + f0, planes_of(g), d_out, d_clean, true, aux);
+            time_mark(e, t0 + 2, aux);
+            if (g + 1 < G) parse(g + 1);
+            CK(cudaEventSynchronize(e->pipe_ev[3 * g + 1]));
+            const uint32_t clean = ((const uint32_t*)e->mbox_h)[2], high = ((const uint32_t*)e->mbox_h)[3];
+            if (clean != 1 && e->debug) fprintf(stderr, "flacb200: k_chain_fast declined group at %u (reason 0x%x)\n", f0, clean);
+            if (clean != 1) CK(launch_chain(cfg, d_bytes, d_segs, d_cands + f0, d_recs + f0, n, after, f0 == 0, d_pos + f0, d_state, aux));
+            if (high) {
+                launch_restore(cfg, d_cands + f0, n, subs_of(g), d_recs + f0, planes_of(g), aux);
+                launch_emit(cfg, d_cands + f0, d_recs + f0, d_pos + f0, planes_of(g), n, d_out, aux);
+            } else if (clean != 1) {
+                launch_restore_emit(cfg, d_cands + f0, n, subs_of(g), d_recs + f0, d_pos + f0, planes_of(g), d_out, d_clean, false, aux);
+            }
+            time_mark(e, t0 + 3, aux);
+            spans.push_back({t0, t0 + 1, 2});
+            spans.push_back({t0 + 1, t0 + 2, 3});
+            spans.push_back({t0 + 2, t0 + 3, 4});
+            CK(cudaEventRecord(e->pipe_ev[3 * g + 2], aux));
+            ngroups++;
+        }
+        CK(cudaStreamWaitEvent(st, e->pipe_ev[3 * (G - 1) + 2], 0));
+        g0 = ncand;
+    } else {
+    ENS(e->dec[9], (size_t)((group + 31u) & ~31u) * per_frame);   // whole bundles of 32 interleaved planes
+    if (split_decode) ENS(e->dec[10], (size_t)group * cfg.channels * sizeof(SubRec));
     do {
         const uint32_t n = std::min<uint32_t>(group, ncand - g0);
         const FrameCand* after = g0 + n < ncand ? d_cands + g0 + n : nullptr;
+        const size_t b0 = ev - 1;   // the four stage marks of this group follow the last one recorded
         if (n && split_decode) {
             // k_parse, then two independent tails that meet before k_emit: predictor restoration over the planes on the
             // engine's stream, and CRC-16 + the frame chain (which need only the end offsets k_parse found) on a second one
@@ -1038,38 +1117,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
             launch_parse(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, (SubRec*)e->dec[10].p, d_recs + g0, d_clean + 1, st);
             if (maybe_wide) launch_decode(cfg, d_bytes, d_segs, d_cands + g0, n, (int32_t*)e->dec[9].p, d_recs + g0, true, st);
             time_mark(e, ev++);
-            if (restore_emit_ok(cfg, d_out) && !(e->legacy & 512u)) {
-                // packed 16/24-bit mono/stereo output: CRC-16 and the frame walk first (they need only the end offsets k_parse
-                // found), then ONE pass over the planes that restores the predictors and the stereo pair and writes the packed
-                // PCM (k_restore_emit).  It is queued before the host has read the walk's verdict and checks it itself; when
-                // k_chain_fast declined the group the general walk runs and the kernel is launched again, and a launch group
-                // with predictors beyond its register budget goes through k_restore + k_emit.
-                launch_crc16f(d_bytes, d_cands + g0, n, d_recs + g0, st);
-                launch_chain_fast(cfg, d_segs, d_cands + g0, d_recs + g0, n, ncand - g0, g0 == 0, d_pos + g0, d_state, d_clean, st);
-                mbox_post(e, 8, d_clean, 8, st);
-                CK(cudaEventRecord(e->pipe_ev[3 * ngroups], st));
-                time_mark(e, ev++);
-                launch_restore_emit(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, d_out,
-                                    d_clean, true, st);
-                CK(cudaEventSynchronize(e->pipe_ev[3 * ngroups]));
-                const uint32_t clean = ((const uint32_t*)e->mbox_h)[2], high = ((const uint32_t*)e->mbox_h)[3];
-                if (clean != 1 && e->debug) fprintf(stderr, "flacb200: k_chain_fast declined group at %u (reason 0x%x)\n", g0, clean);
-                time_mark(e, ev++);
-                if (clean != 1) CK(launch_chain(cfg, d_bytes, d_segs, d_cands + g0, d_recs + g0, n, after, g0 == 0, d_pos + g0, d_state, st));
-                if (high) {
-                    launch_restore(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, (int32_t*)e->dec[9].p, st);
-                    launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
-                } else if (clean != 1) {
-                    launch_restore_emit(cfg, d_cands + g0, n, (const SubRec*)e->dec[10].p, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p,
-                                        d_out, d_clean, false, st);
-                }
-                time_mark(e, ev++);
-                ngroups++;
-                g0 += n;
-                continue;
-            }
-            // other layouts: two independent tails that meet before k_emit -- predictor restoration on the engine's stream; CRC-16
-            // and the frame walk on the second one.  The
+            // The tails: predictor restoration on the engine's stream; CRC-16 and the frame walk on the second one.  The
             // walk is k_chain_fast when the candidates are exactly the frames (the host reads its verdict: a 4-byte copy and
             // a sync of the second stream, while k_restore keeps the GPU busy), else k_chain -- one CTA that wants a whole
             // SM's shared memory and therefore only starts once k_restore has drained.
@@ -1089,6 +1137,7 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
             time_mark(e, ev++);
             launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
             time_mark(e, ev++);
+            for (size_t k = 0; k < 4; k++) spans.push_back({b0 + k, b0 + k + 1, 1 + k});
             ngroups++;
         } else {
             if (n) {
@@ -1102,11 +1151,13 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
                 time_mark(e, ev++);
                 launch_emit(cfg, d_cands + g0, d_recs + g0, d_pos + g0, (const int32_t*)e->dec[9].p, n, d_out, st);
                 time_mark(e, ev++);
+                for (size_t k = 0; k < 4; k++) spans.push_back({b0 + k, b0 + k + 1, 1 + k});
                 ngroups++;
             }
         }
         g0 += n;
     } while (g0 < ncand);
+    }
     cudaEventRecord(e->ev[23], st);
     CK(cudaGetLastError());
     ChainState state;
@@ -1120,16 +1171,12 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
     cudaEventElapsedTime(&e->tm.total_ms, e->ev[22], e->ev[23]);
     e->tm.launches = (uint32_t)(g_kernel_launches - launches0);
     if (e->profiling) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e->evpool[0], e->evpool[1]);
-        e->tm.kernel_ms[0] = ms;
-        e->tm.kernel_launches[0] = ncand ? 3 : 2;
-        for (size_t g = 0; g < ngroups; g++)
-            for (int k = 0; k < 4; k++) {
-                cudaEventElapsedTime(&ms, e->evpool[1 + g * 4 + k], e->evpool[2 + g * 4 + k]);
-                e->tm.kernel_ms[1 + k] += ms;
-                e->tm.kernel_launches[1 + k] += 1;
-            }
+        for (const auto& sp : spans) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e->evpool[sp[0]], e->evpool[sp[1]]);
+            e->tm.kernel_ms[sp[2]] += ms;
+            e->tm.kernel_launches[sp[2]] += sp[2] == 0 ? (ncand ? 3 : 2) : 1;
+        }
         cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[20], e->ev[21]);
     }
     if (pcm_location == FLACB200_HOST) {
