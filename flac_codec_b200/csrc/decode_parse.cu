@@ -57,9 +57,10 @@ __constant__ int16_t c_fixed_coeffs[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1,
 //     wraps with a mask -- a divergent `if` would be taken by some lane at almost every token.
 // Words are addressed relative to the chunk that holds the lane's first word; chunks at and beyond the end of the
 // buffer are filled synchronously from the bytes that exist, so no access leaves the buffer, whatever its length.
-constexpr uint32_t PARSE_CHUNKS = 8;                      // 128 bytes per lane
+// Ring depth: 8 chunks (128 bytes per lane) when the launch fills the GPU -- with 32 warps per SM a group of four samples takes
+// far longer than a DRAM access; 16 chunks for small launches (one stream, a few hundred frames: one or two warps per SM, a
+// group takes ~200 cycles and three groups in flight did not cover the latency of the chunk they wait for).
 constexpr uint32_t PARSE_SLOT = PARSE_THREADS * 16;       // bytes between consecutive chunks of a lane
-constexpr uint32_t PARSE_LEAD = PARSE_CHUNKS - 1;
 
 // the chunks at and beyond the end of the buffer: the bytes that exist, zeros after them, stored synchronously (a
 // 16-byte cp.async with a short src-size would still be a 16-byte access that crosses the end of the caller's buffer)
@@ -71,7 +72,9 @@ static __device__ __noinline__ void fill_tail_chunk(uint32_t smem_addr, const ui
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]) : "memory");
 }
 
+template <uint32_t PARSE_CHUNKS>
 struct LaneBits {
+    static constexpr uint32_t PARSE_LEAD = PARSE_CHUNKS - 1;
     const uint4* base16;          // the 16-byte chunk that holds the lane's first word
     const uint8_t* bytes;         // the whole buffer (only the chunks at its end are read through this)
     unsigned long long nbytes;
@@ -95,7 +98,7 @@ struct LaneBits {
     {
         if ((int32_t)(req - ((rel + 3) >> 2)) < (int32_t)PARSE_LEAD) request_chunk();
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 3;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(PARSE_CHUNKS - 5) : "memory");
         // (one-sample partitions with escaped residuals consume a little more than a chunk per group: catch up)
         if ((int32_t)(req - ((rel + 3) >> 2)) < (int32_t)PARSE_LEAD - 2) ensure_now();
     }
@@ -176,7 +179,8 @@ struct LaneSub {
 // the events of a predictive subframe: at s == order the LPC parameters (:1706-1729) and the residual coding header
 // (:1806-1822), then (and at every later partition boundary) a ResidualPartitionHeader (src/stream.rs:1586-1600).
 // Returns 0 or the Error ordinal.
-__device__ __forceinline__ uint32_t parse_event(LaneBits& br, LaneSub& sf, unsigned long long endbit, SubRec* __restrict__ rec)
+template <class LaneBitsT>
+__device__ __forceinline__ uint32_t parse_event(LaneBitsT& br, LaneSub& sf, unsigned long long endbit, SubRec* __restrict__ rec)
 {
     if (!sf.started) {
         sf.started = 1;
@@ -220,7 +224,8 @@ __device__ __forceinline__ uint32_t parse_event(LaneBits& br, LaneSub& sf, unsig
 }
 
 // SubframeHeader (src/stream.rs:1382-1395, :1537-1553) and what precedes the sample loop.  Returns 0 or the ordinal.
-__device__ __forceinline__ uint32_t parse_subframe_header(LaneBits& br, LaneSub& sf, uint32_t bps, uint32_t n, unsigned long long endbit,
+template <class LaneBitsT>
+__device__ __forceinline__ uint32_t parse_subframe_header(LaneBitsT& br, LaneSub& sf, uint32_t bps, uint32_t n, unsigned long long endbit,
                                                            SubRec* __restrict__ rec)
 {
     br.ensure_now();
@@ -279,7 +284,8 @@ __device__ __forceinline__ uint32_t parse_subframe_header(LaneBits& br, LaneSub&
     return 0;
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS, 16) k_parse(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
+template <uint32_t PARSE_CHUNKS>
+__global__ void __launch_bounds__(PARSE_THREADS, PARSE_CHUNKS == 8 ? 16 : 8) k_parse(DecCfg cfg, const uint8_t* __restrict__ bytes, const DecSeg* __restrict__ segs,
                                                         const FrameCand* __restrict__ cands, uint32_t ncand, int32_t* __restrict__ planes,
                                                         SubRec* __restrict__ subs, DecRec* __restrict__ recs, uint32_t* __restrict__ high_order)
 {
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, 16) k_parse(DecCfg cfg, const u
     unsigned long long endbit = 0, byte_end = 0;
     __shared__ uint4 s_ring[PARSE_CHUNKS * PARSE_THREADS];
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x);
-    LaneBits br;
+    LaneBits<PARSE_CHUNKS> br;
     br.base16 = reinterpret_cast<const uint4*>(bytes);
     br.bytes = bytes; br.nbytes = cfg.nbytes; br.first = 0; br.nfull = 0; br.ring = ring_addr; br.req = 0; br.roff = 0; br.rel = 0; br.w0 = br.w1 = br.r1 = 0; br.pos = 0;
     const uint32_t n = fc.block_size;
@@ -754,7 +760,9 @@ void launch_restore_emit(const DecCfg& cfg, const FrameCand* cands, uint32_t n, 
 void launch_parse(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* segs, const FrameCand* cands, uint32_t n, int32_t* planes, SubRec* subs,
                   DecRec* recs, uint32_t* high_order, cudaStream_t st)
 {
-    count_launch(), k_parse<<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs, high_order);
+    // (148 SMs x 16 CTAs of 64 lanes fill the GPU; below a quarter of that the walk is latency-bound)
+    if (n >= 37888u) count_launch(), k_parse<8><<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs, high_order);
+    else count_launch(), k_parse<16><<<(n + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(cfg, bytes, segs, cands, n, planes, subs, recs, high_order);
 }
 
 void launch_restore(const DecCfg& cfg, const FrameCand* cands, uint32_t n, const SubRec* subs, const DecRec* recs, int32_t* planes, cudaStream_t st)
