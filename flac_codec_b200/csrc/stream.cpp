@@ -685,6 +685,10 @@ struct flacb200_reader {
     std::vector<flacb200_frame_entry> frames;
     size_t cur = 0;                   // frame being handed out
     uint32_t cur_off = 0;             // inter-channel samples of it already consumed
+    // a read that ended inside a PCM frame (io::Read of an odd byte count, FlacSampleReader::read of one sample of a stereo
+    // stream: the reference's buffers are byte- and sample-granular): `part` units of the PCM frame at cur_off are gone
+    uint32_t part = 0;                // bytes (byte kinds) or samples (i32) consumed of that PCM frame
+    int part_kind = 0;                // the layout those units were counted in
     bool at_end = false;
     int sticky_error = 0;
     bool seekable_source = false;     // feed mode over an `R: Read + Seek`: a seek asks the caller to reposition its source
@@ -793,6 +797,7 @@ int reader_next_window(flacb200_reader& r, int want_kind)
     r.frames.clear();
     r.cur = 0;
     r.cur_off = 0;
+    r.part = 0;
     if (r.sticky_error) return r.sticky_error;
     if (r.at_end) return 0;
     if (!r.engine) return FLACB200_E_NO_DEVICE;
@@ -934,6 +939,7 @@ uint64_t reader_seek_point(flacb200_reader& r, uint64_t sample)
     r.frames.clear();
     r.cur = 0;
     r.cur_off = 0;
+    r.part = 0;
     r.at_end = false;
     r.sticky_error = 0;
     return at_sample;
@@ -1039,20 +1045,25 @@ int flacb200_reader_fill_buf(flacb200_reader* r, const int32_t** samples, size_t
     const int rc = reader_current_frame(*r, FLACB200_PCM_I32_INTERLEAVED);
     if (rc) return rc;
     if (r->cur >= r->frames.size()) return 0;   // end of stream: an empty buffer
-    *samples = reader_frame_samples(*r);
-    *n_samples = (size_t)(r->frames[r->cur].block_size - r->cur_off) * r->si.channels;
+    if (r->part && r->part_kind != FLACB200_PCM_I32_INTERLEAVED) return FLACB200_E_BAD_ARGUMENT;   // (a byte read stopped inside a PCM frame)
+    *samples = reader_frame_samples(*r) + r->part;
+    *n_samples = (size_t)(r->frames[r->cur].block_size - r->cur_off) * r->si.channels - r->part;
     return 0;
 }
 
-// FlacSampleReader::consume (:487): n_samples counts all channels and must be a multiple of the channel count
+// FlacSampleReader::consume (:487): n_samples counts all channels; any amount up to what fill_buf returned (VecDeque::drain)
 int flacb200_reader_consume(flacb200_reader* r, size_t n_samples)
 {
     if (!r) return FLACB200_E_BAD_ARGUMENT;
     if (r->cur >= r->frames.size()) return n_samples ? FLACB200_E_BAD_ARGUMENT : 0;
+    if (r->part && r->part_kind != FLACB200_PCM_I32_INTERLEAVED) return FLACB200_E_BAD_ARGUMENT;
     const size_t ch = r->si.channels;
-    const size_t left = (size_t)(r->frames[r->cur].block_size - r->cur_off) * ch;
-    if (n_samples > left || n_samples % ch) return FLACB200_E_BAD_ARGUMENT;
-    r->cur_off += (uint32_t)(n_samples / ch);
+    const size_t left = (size_t)(r->frames[r->cur].block_size - r->cur_off) * ch - r->part;
+    if (n_samples > left) return FLACB200_E_BAD_ARGUMENT;
+    const size_t adv = r->part + n_samples;
+    r->cur_off += (uint32_t)(adv / ch);
+    r->part = (uint32_t)(adv % ch);
+    r->part_kind = FLACB200_PCM_I32_INTERLEAVED;
     return 0;
 }
 
@@ -1067,6 +1078,7 @@ int flacb200_reader_fill_channels(flacb200_reader* r, const int32_t* const** cha
     }
     const int rc = reader_current_frame(*r, FLACB200_PCM_I32_INTERLEAVED);
     if (rc) return rc;
+    if (r->part) return FLACB200_E_BAD_ARGUMENT;   // (an interleaved read stopped inside a PCM frame: not a channel reader's state)
     const size_t ch = r->si.channels;
     r->planar_ptrs.assign(ch, nullptr);
     *channels = r->planar_ptrs.data();
@@ -1101,29 +1113,63 @@ int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm
     }
     const size_t B = (r->si.bits_per_sample + 7) / 8, ch = r->si.channels;
     const bool as_i32 = pcm_kind == FLACB200_PCM_I32_INTERLEAVED, be = pcm_kind == FLACB200_PCM_BYTES_BE;
-    size_t room = as_i32 ? capacity : capacity / B;   // single-channel samples that still fit
-    room -= room % ch;   // whole PCM frames only: the position stays on a frame of all channels
+    const size_t unit = as_i32 ? 4 : 1;         // bytes of `out` per unit (a sample, or a byte of the packed layouts)
+    const size_t U = as_i32 ? ch : ch * B;      // units of one PCM frame
+    size_t units = 0;                           // units delivered
+    // one PCM frame (the one at cur_off) in the caller's layout
+    auto pcm_frame = [&](uint8_t* tmp) {
+        if (as_i32) memcpy(tmp, reader_frame_samples(*r), ch * 4);
+        else if (r->win_kind == FLACB200_PCM_BYTES_LE) {
+            const uint8_t* src = reader_frame_bytes(*r);
+            for (size_t i = 0; i < ch; i++)
+                for (size_t k = 0; k < B; k++) tmp[i * B + k] = src[i * B + (be ? B - 1 - k : k)];
+        } else {
+            const int32_t* sm = reader_frame_samples(*r);
+            for (size_t i = 0; i < ch; i++)
+                for (size_t k = 0; k < B; k++) tmp[i * B + k] = (uint8_t)((uint32_t)sm[i] >> (8 * (be ? B - 1 - k : k)));
+        }
+    };
+    uint8_t tmp[8 * 4];
+    if (r->part && capacity) {   // the rest of the PCM frame the previous read stopped in
+        if (r->part_kind != pcm_kind) return FLACB200_E_BAD_ARGUMENT;
+        const int rc = reader_current_frame(*r, pcm_kind);
+        if (rc) return rc;
+        if (r->cur < r->frames.size()) {
+            pcm_frame(tmp);
+            const size_t n = std::min<size_t>(capacity, U - r->part);
+            memcpy(out, tmp + r->part * unit, n * unit);
+            units = n;
+            r->part += (uint32_t)n;
+            if (r->part == U) {
+                r->part = 0;
+                r->cur_off++;
+            }
+        }
+    }
+    size_t room = r->part ? 0 : ((capacity - units) / U) * ch;   // single-channel samples of the whole PCM frames that still fit
+    const size_t head_bytes = units * unit;
     size_t done = 0;
+    bool stopped = false;   // end of stream, or an error that surfaces at the next call
     while (room) {
         const int rc = reader_current_frame(*r, pcm_kind);
         if (rc) {
-            if (done) break;   // deliver what precedes the error; it surfaces at the next call
+            if (done || units) { stopped = true; break; }   // deliver what precedes the error; it surfaces at the next call
             return rc;
         }
-        if (r->cur >= r->frames.size()) break;   // end of stream
+        if (r->cur >= r->frames.size()) { stopped = true; break; }   // end of stream
         const size_t n = std::min<size_t>(room, (size_t)(r->frames[r->cur].block_size - r->cur_off) * ch);
         if (!as_i32 && r->win_kind == FLACB200_PCM_BYTES_LE) {   // Frame::to_buf (src/audio.rs:110-134) was done on the device
             const uint8_t* src = reader_frame_bytes(*r);
-            uint8_t* o = (uint8_t*)out + done * B;
+            uint8_t* o = (uint8_t*)out + head_bytes + done * B;
             if (!be || B == 1) memcpy(o, src, n * B);
             else
                 for (size_t i = 0; i < n; i++)
                     for (size_t k = 0; k < B; k++) o[i * B + k] = src[i * B + B - 1 - k];
         } else {
             const int32_t* s = reader_frame_samples(*r);
-            if (as_i32) memcpy((int32_t*)out + done, s, n * 4);
+            if (as_i32) memcpy((uint8_t*)out + head_bytes + done * 4, s, n * 4);
             else {
-                uint8_t* o = (uint8_t*)out + done * B;
+                uint8_t* o = (uint8_t*)out + head_bytes + done * B;
                 for (size_t i = 0; i < n; i++) {
                     const uint32_t v = (uint32_t)s[i];
                     for (size_t k = 0; k < B; k++) o[i * B + k] = (uint8_t)(v >> (8 * (be ? B - 1 - k : k)));
@@ -1134,7 +1180,21 @@ int flacb200_reader_read(flacb200_reader* r, void* out, size_t capacity, int pcm
         done += n;
         room -= n;
     }
-    *n_out = as_i32 ? done : done * B;
+    units += as_i32 ? done : done * B;
+    // what is left of the caller's buffer holds less than a PCM frame: hand out the head of the next one
+    const size_t rest = capacity - units;
+    if (!stopped && !r->part && rest && rest < U) {
+        const int rc = reader_current_frame(*r, pcm_kind);
+        if (rc && !units) return rc;
+        if (!rc && r->cur < r->frames.size()) {
+            pcm_frame(tmp);
+            memcpy((uint8_t*)out + units * unit, tmp, rest * unit);
+            units += rest;
+            r->part = (uint32_t)rest;
+            r->part_kind = pcm_kind;
+        }
+    }
+    *n_out = units;
     return 0;
 }
 

@@ -349,9 +349,21 @@ class FlacByteReader(_Reader):
         self._pos += len(out)
         return out
 
+    def readinto(self, buf) -> int:
+        """io::Read::read into a caller-owned buffer (numpy uint8 array / writable buffer): no intermediate copies."""
+        a = buf if isinstance(buf, np.ndarray) else np.frombuffer(buf, dtype=np.uint8)
+        got = 0
+        while got < a.size:
+            n = self._read(a[got:], a.size - got, self._kind)
+            if n == 0:
+                break
+            got += n
+        self._pos += got
+        return got
+
     def seek_bytes(self, offset: int, whence: int = 0) -> int:
-        """io::Seek (src/decode.rs:715-820): byte positions of the decoded stream; truncated to whole PCM frames' worth of
-        decoding, then bytes are skipped up to the position."""
+        """io::Seek (src/decode.rs:715-820): byte positions of the decoded stream.  The decoder seeks to the PCM frame that
+        holds the byte, then bytes are consumed up to the position itself (the next read continues inside that PCM frame)."""
         bpf = ((self._si.bits_per_sample + 7) // 8) * self._si.channels
         if whence == 0:
             want = offset
@@ -362,17 +374,17 @@ class FlacByteReader(_Reader):
                 raise OSError("total samples not known")
             if offset > 0:
                 raise OSError("cannot seek beyond end of file")
-            want = self._si.total_samples * bpf + offset
+            # (the reference takes total_samples -- PCM frames, not bytes -- as the end position, :766-768; kept as it is)
+            want = self._si.total_samples + offset
         if want < 0:
             raise OSError("cannot seek below byte 0")
         self.seek(want // bpf)
         self._pos = (want // bpf) * bpf
         skip = want - self._pos
-        if skip:   # a position inside a PCM frame: the remaining bytes of that frame are consumed from the buffer
-            got = self.read(bpf)
-            if len(got) < bpf:
+        if skip:
+            got = self.read(skip)   # (advances self._pos)
+            if len(got) < skip:
                 raise EOFError("stream exhausted before sample reached")
-            self._pos = want   # (the rest of this PCM frame is dropped, as BufRead::consume would)
         return want
 
 
@@ -382,6 +394,16 @@ class FlacSampleReader(_Reader):
     def read(self, n_samples: int) -> np.ndarray:
         buf = np.empty(max(n_samples, 1), dtype=np.int32)
         return buf[: self._read(buf, n_samples, _abi.PCM_I32_INTERLEAVED)]
+
+    def readinto(self, buf: np.ndarray) -> int:
+        """Fills a caller-owned int32 array with interleaved samples; returns how many were read."""
+        got = 0
+        while got < buf.size:
+            n = self._read(buf[got:], buf.size - got, _abi.PCM_I32_INTERLEAVED)
+            if n == 0:
+                break
+            got += n
+        return got
 
     def read_to_end(self) -> np.ndarray:
         total = self._si.total_samples * self._si.channels

@@ -524,7 +524,9 @@ impl<R: Read + Seek, E: Endianness> Seek for FlacByteReader<R, E> {
             SeekFrom::Current(d) if d < 0 => self.byte_pos.checked_sub(d.unsigned_abs()).ok_or_else(|| invalid("cannot seek below byte 0"))?,
             SeekFrom::Current(d) => self.byte_pos.checked_add(d as u64).ok_or_else(|| invalid("seek offset too large"))?,
             SeekFrom::End(d) => {
-                let max = self.decoded_len().ok_or_else(|| std::io::Error::new(std::io::ErrorKind::Unsupported, "total samples not known"))?;
+                // (the crate takes total_samples -- PCM frames, not bytes -- as the end position, :766-768; kept as it is)
+                let max = self.d.info.total_samples;
+                if max == 0 { return Err(std::io::Error::new(std::io::ErrorKind::Unsupported, "total samples not known")); }
                 if d > 0 { return Err(invalid("cannot seek beyond end of file")); }
                 max.checked_sub(d.unsigned_abs()).ok_or_else(|| invalid("cannot seek below byte 0"))?
             }

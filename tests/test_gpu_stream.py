@@ -292,6 +292,16 @@ def test_reader_windows_are_invisible(fo, st):
     rb = st.FlacByteReader(flac, window_bytes=70000)
     assert rb.read() == fo.samples_to_bytes(x, 2)
     rb.close()
+    # the same through caller-owned buffers (no intermediate copies); a buffer larger than the stream is filled to its end
+    rb = st.FlacByteReader(flac, window_bytes=70000)
+    out = np.zeros(x.size * 2 + 100, dtype=np.uint8)
+    assert rb.readinto(out) == x.size * 2 and out[: x.size * 2].tobytes() == fo.samples_to_bytes(x, 2)
+    rb.close()
+    rs = st.FlacSampleReader(flac, window_bytes=50000)
+    y = np.zeros(x.size // 2, dtype=np.int32)
+    assert rs.readinto(y) == y.size and np.array_equal(y, x[: y.size])
+    assert rs.readinto(y) == x.size - y.size and np.array_equal(y[: x.size - y.size], x[y.size:])
+    rs.close()
 
 
 def test_reader_fed_in_chunks_like_a_plain_read(fo, st):
@@ -359,11 +369,24 @@ def test_seek_uses_the_seektable(fo, st):
     # FlacByteReader's io::Seek, in bytes (src/decode.rs:715-820)
     rb = st.FlacByteReader(flac)
     raw = fo.samples_to_bytes(x, 2)
-    for off in (0, 4 * 1000, 4 * (pts[1][0] + 3), len(raw) - 8):
+    for off in (0, 4 * 1000, 4 * (pts[1][0] + 3), len(raw) - 8, 4 * 777 + 1, 4 * (pts[2][0] + 9) + 3):   # the last two: inside a PCM frame
         assert rb.seek_bytes(off) == off
         assert rb.read(4000) == raw[off:off + 4000]
-    assert rb.seek_bytes(-400, 2) == len(raw) - 400 and rb.read() == raw[-400:]
+        assert rb.read(3) == raw[off + 4000:off + 4003] and rb.read(6) == raw[off + 4003:off + 4009]   # reads are byte-granular
+    # SeekFrom::End: the reference takes total_samples (PCM frames, not bytes) as the end position (src/decode.rs:766-768)
+    total = len(raw) // 4
+    assert rb.seek_bytes(-400, 2) == total - 400 and rb.read(100) == raw[total - 400:total - 300]
     rb.close()
+    # FlacSampleReader::read (:417) hands out any number of samples, also half a stereo pair
+    rs = st.FlacSampleReader(flac)
+    assert np.array_equal(rs.read(1), x[:1]) and np.array_equal(rs.read(1), x[1:2]) and np.array_equal(rs.read(5), x[2:7])
+    buf = rs.fill_buf()
+    assert np.array_equal(buf[:9], x[7:16])
+    rs.consume(3)
+    assert np.array_equal(rs.read(4), x[10:14])
+    rs.seek(100)
+    assert np.array_equal(rs.read(3), x[200:203])
+    rs.close()
 
 
 def test_fill_buf_consume_and_channel_reader(fo, st):
