@@ -74,11 +74,16 @@ class Clocks:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_begin = index, [], None, 0.0
+
+    def begin(self):
+        """The timed region starts here: only samples that arrive from now on count (nvidia-smi itself is started before the
+        warm-up steps -- it needs a few hundred ms to print its first line, longer than a short timed region)."""
+        self.t_begin = time.perf_counter()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -88,7 +93,7 @@ class Clocks:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -99,7 +104,10 @@ class Clocks:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        inside = [r for t, r in self.rows if t >= self.t_begin]
+        # a timed region shorter than the sampling period: the samples of the warm-up steps (same kernels, same load) stand in
+        where = "timed region" if inside else "warm-up steps (the timed region was shorter than one sampling period)"
+        for r in (inside or [r for _, r in self.rows]):
             try:
                 sm.append(float(r[1]))
                 mx = max(mx, float(r[2]))
@@ -111,7 +119,7 @@ class Clocks:
         sm.sort()
         # median over the samples taken under load (upper half of the clock samples is the loaded region)
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "sampled_during": where}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -309,11 +317,12 @@ def run_gpu(args):
                           out_capacity=out_cap, out_location=_abi.DEVICE, want_sizes=False)
 
     eng.set_profiling(True)
+    clocks = Clocks(local)
+    clocks.start()
     for _ in range(args.warmup):
         _, _, flac_bytes = step()
-    clocks = Clocks(local)
     barrier()
-    clocks.start()
+    clocks.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = np.zeros(8)
     kernel_launches = np.zeros(8, dtype=np.int64)

@@ -228,17 +228,26 @@ __global__ void __launch_bounds__(256) k_find_compact(uint32_t tiles, const uint
     if (tile < tiles && s < tile_counts[tile]) cands[tile_base[tile] + s] = slots[i];
 }
 
-// exclusive scan of n counts (single CTA of 1024 threads); total written to out[n]
+// exclusive scan of n counts (single CTA of 1024 threads, eight consecutive counts per thread and pass: the loop is a chain of
+// block-wide barriers, so its time is the number of passes); total written to out[n]
+constexpr uint32_t SCAN_PER = 8;
+
 __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t n, const uint32_t* __restrict__ in, uint32_t* __restrict__ out)
 {
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t tile_total;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t carry = 0;
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + tid;
-        const uint32_t v = i < n ? in[i] : 0;
-        uint32_t incl = v;
+    for (uint32_t base = 0; base < n; base += 1024 * SCAN_PER) {
+        const uint32_t i0 = base + tid * SCAN_PER;
+        uint32_t v[SCAN_PER];
+        uint32_t mine = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < SCAN_PER; k++) {
+            v[k] = i0 + k < n ? in[i0 + k] : 0u;
+            mine += v[k];
+        }
+        uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -258,7 +267,12 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t n, const uint32_t* _
             if (lane == 31) tile_total = wi;
         }
         __syncthreads();
-        if (i < n) out[i] = carry + wsum[wid] + incl - v;
+        uint32_t run = carry + wsum[wid] + incl - mine;
+#pragma unroll
+        for (uint32_t k = 0; k < SCAN_PER; k++) {
+            if (i0 + k < n) out[i0 + k] = run;
+            run += v[k];
+        }
         carry += tile_total;
         __syncthreads();
     }

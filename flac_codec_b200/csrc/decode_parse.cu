@@ -82,9 +82,10 @@ struct LaneBits {
     uint32_t nfull;               // whole chunks available from base16 on (clamped to 32 bits)
     uint32_t ring;                // shared-memory address of this lane's chunk slot 0
     uint32_t req;                 // chunks 0 .. req - 1 have been requested
-    uint32_t roff;                // ring byte offset of word rel + 3 (the next one to become r1)
-    uint32_t rel;                 // w0 is word first + rel
-    uint32_t w0, w1, r1, pos;
+    uint32_t roff;                // ring byte offset of the word after r1 (the next one to become r1)
+    uint32_t bits;                // bits consumed since word `first`: w0 is word first + (bits >> 5), the window starts at bit bits & 31
+    uint32_t w0, w1, r1;
+    __device__ __forceinline__ uint32_t cur_chunk() const { return (bits + 96u) >> 7; }   // chunk of the word after r1
 
     __device__ __forceinline__ void request_chunk()   // chunk req -> slot req % PARSE_CHUNKS (no commit)
     {
@@ -94,18 +95,19 @@ struct LaneBits {
         req++;
     }
     // start of a group of four samples, executed by all lanes together
-    __device__ __forceinline__ void ensure_group()
+    // `check_lag`: the previous group was not a run of plain Rice codes (a plain group consumes at most one chunk and requests
+    // one, so it cannot fall behind; partition headers and one-sample partitions with escaped residuals consume a little more)
+    __device__ __forceinline__ void ensure_group(bool check_lag)
     {
-        if ((int32_t)(req - ((rel + 3) >> 2)) < (int32_t)PARSE_LEAD) request_chunk();
+        if ((int32_t)(req - cur_chunk()) < (int32_t)PARSE_LEAD) request_chunk();
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group %0;" ::"n"(PARSE_CHUNKS - 5) : "memory");
-        // (one-sample partitions with escaped residuals consume a little more than a chunk per group: catch up)
-        if ((int32_t)(req - ((rel + 3) >> 2)) < (int32_t)PARSE_LEAD - 2) ensure_now();
+        if (check_lag && (int32_t)(req - cur_chunk()) < (int32_t)PARSE_LEAD - 2) ensure_now();
     }
     // before code that may consume more than a chunk at once
     __device__ __forceinline__ void ensure_now()
     {
-        while ((int32_t)(req - ((rel + 3) >> 2)) < (int32_t)PARSE_LEAD) request_chunk();
+        while ((int32_t)(req - cur_chunk()) < (int32_t)PARSE_LEAD) request_chunk();
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
@@ -127,20 +129,21 @@ struct LaneBits {
         base16 = reinterpret_cast<const uint4*>(buf) + c0;   // (only dereferenced for chunks below nfull)
         ring = ring_addr;
         req = 0;
-        rel = (uint32_t)(word & 3);
-        pos = (uint32_t)(bitpos & 31);
-        ensure_now();   // chunks 0 .. 6
+        const uint32_t rel = (uint32_t)(word & 3);
+        bits = rel * 32u + (uint32_t)(bitpos & 31);
+        ensure_now();   // the first PARSE_LEAD chunks
         w0 = __byte_perm(lds(ring + word_off(rel)), 0, 0x0123);
         w1 = __byte_perm(lds(ring + word_off(rel + 1)), 0, 0x0123);
         r1 = lds(ring + word_off(rel + 2));
         roff = word_off(rel + 3);
     }
-    __device__ __forceinline__ unsigned long long position() const { return ((first + rel) << 5) + pos; }
-    __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(w1, w0, pos); }   // the next 32 bits
-    __device__ __forceinline__ void skip(uint32_t n)   // n <= 32
+    __device__ __forceinline__ unsigned long long position() const { return (first << 5) + bits; }
+    __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(w1, w0, bits); }   // the next 32 bits (the shift wraps at 32)
+    __device__ __forceinline__ void skip(uint32_t n)   // n <= 32: at most one word boundary is crossed
     {
-        pos += n;
-        const bool adv = pos >= 32;
+        const uint32_t nb = bits + n;
+        const bool adv = ((bits ^ nb) & ~31u) != 0;
+        bits = nb;
         uint32_t nw = r1;
         if (adv) nw = lds(ring + roff);
         const uint32_t t = roff + 4;
@@ -149,8 +152,6 @@ struct LaneBits {
         w1 = adv ? __byte_perm(r1, 0, 0x0123) : w1;
         r1 = nw;
         roff = adv ? nroff : roff;
-        rel += adv ? 1u : 0u;
-        pos &= 31u;
     }
     __device__ __forceinline__ uint32_t get(uint32_t n)   // n in 0..=32
     {
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, PARSE_CHUNKS == 8 ? 16 : 8) k_p
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x);
     LaneBits<PARSE_CHUNKS> br;
     br.base16 = reinterpret_cast<const uint4*>(bytes);
-    br.bytes = bytes; br.nbytes = cfg.nbytes; br.first = 0; br.nfull = 0; br.ring = ring_addr; br.req = 0; br.roff = 0; br.rel = 0; br.w0 = br.w1 = br.r1 = 0; br.pos = 0;
+    br.bytes = bytes; br.nbytes = cfg.nbytes; br.first = 0; br.nfull = 0; br.ring = ring_addr; br.req = 0; br.roff = 0; br.bits = 0; br.w0 = br.w1 = br.r1 = 0;
     const uint32_t n = fc.block_size;
     uint32_t err = 0;
     bool live = exists && !wide;
@@ -361,12 +362,14 @@ __global__ void __launch_bounds__(PARSE_THREADS, PARSE_CHUNKS == 8 ? 16 : 8) k_p
             }
             return (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
         };
+        bool check_lag = true;
         for (uint32_t s0 = 0; s0 < n4; s0 += 4) {
             int32_t o[4];
-            br.ensure_group();
+            br.ensure_group(check_lag);
             // the common group: every lane of the warp is alive, inside a Rice partition, and has no event before s0 + 4
             const bool plain = s0 + 4 <= nlane && sf.tk == TK_RICE && sf.ev_s - s0 >= 4;
-            if (__all_sync(0xffffffffu, plain)) {
+            check_lag = !__all_sync(0xffffffffu, plain);
+            if (!check_lag) {
 #pragma unroll
                 for (int e4 = 0; e4 < 4; e4++) o[e4] = rice_token();
                 *reinterpret_cast<int4*>(plane + plane_off(s0)) = make_int4(o[0], o[1], o[2], o[3]);
