@@ -84,6 +84,19 @@ def test_groups_and_carry(eng, fo, chunk):
     ref, _ = fo.decode_stream(flac)
     assert ns == 200000 and nf == 49
     assert np.array_equal(out.view(np.int32)[: ref.size], ref)
+    # packed bytes: the software-pipelined k_parse | CRC + walk + k_restore_emit path, two plane buffers, many groups
+    from flac_codec_b200 import _abi
+
+    out, nf, ns, si = gpu_decode_stream(eng, flac, fo, kind=_abi.PCM_BYTES_LE, chunk=chunk)
+    assert ns == 200000 and nf == 49
+    assert np.array_equal(fo.bytes_to_samples(out[: ref.size * 2].tobytes(), 2), ref)
+    # ... and with a damaged frame in the middle: the groups before it are delivered, the error is the reference's
+    bad = bytearray(flac)
+    bad[si.frames_start + 60000] ^= 0x10
+    code, nf_ok, ns_ok, ref_ok = fo.decode_stream_ex(bytes(bad))
+    with pytest.raises(_abi.FlacB200Error) as e:
+        gpu_decode_stream(eng, bytes(bad), fo, kind=_abi.PCM_BYTES_LE, chunk=chunk)
+    assert (e.value.code, e.value.bad_frame) == (code, nf_ok)
 
 
 CASES = [
