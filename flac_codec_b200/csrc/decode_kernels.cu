@@ -15,6 +15,8 @@
 //   k_chain     single CTA, slices of 16384 candidates: links, pointer jumping from the segment heads, ShortBlock/total-sample
 //               rules, output positions (segmented scan of block sizes), first error in stream order
 //   k_emit      stereo restoration + interleave + narrowing to the caller's PCM layout (Frame::to_buf)
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "crc.cuh"
 #include "decode.cuh"
@@ -1162,20 +1164,37 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(DecCfg cfg, const uint8
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t CHAINF_PER = 4;
 constexpr uint32_t CHAINF_SCAN = 16;   // false candidates skipped when looking for a neighbour (more: not regular)
+constexpr uint32_t CHAINF_THREADS = 512;
+constexpr uint32_t CHAINF_CL = 8;      // CTAs of the cluster
+constexpr uint32_t CHAINF_CHUNK = CHAINF_THREADS * CHAINF_PER;   // candidates per CTA and pass
 
-__global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const DecSeg* __restrict__ segs, const FrameCand* __restrict__ cands,
-                                                             const DecRec* __restrict__ recs, uint32_t n, uint32_t n_all,
-                                                             uint32_t group_first, unsigned long long* __restrict__ pos_out,
-                                                             ChainState* __restrict__ state, uint32_t* __restrict__ clean)
+// One thread-block CLUSTER of eight CTAs: a single CTA spent 1 ms per step pulling 130 bytes per candidate through one SM.
+// A pass covers 8 x 2048 consecutive candidates, CTA r the r-th run of them; every CTA publishes the (sum, head seen) aggregate
+// of its run in its shared memory, the cluster synchronises, and each CTA folds the aggregates of the CTAs before it -- read
+// through distributed shared memory -- into its prefix and all eight into the carry of the next pass.  The counters of the
+// verdict live in CTA 0's shared memory (remote atomics).
+__global__ void __cluster_dims__(CHAINF_CL, 1, 1) __launch_bounds__(CHAINF_THREADS)
+    k_chain_fast(DecCfg cfg, const DecSeg* __restrict__ segs, const FrameCand* __restrict__ cands, const DecRec* __restrict__ recs, uint32_t n,
+                 uint32_t n_all, uint32_t group_first, unsigned long long* __restrict__ pos_out, ChainState* __restrict__ state,
+                 uint32_t* __restrict__ clean)
 {
-    __shared__ unsigned long long w_sum[32];
-    __shared__ uint32_t w_has[32];
-    __shared__ unsigned long long s_carry, s_samples;
-    __shared__ uint32_t s_bad, s_heads, s_mine, s_cont, s_last, s_frames;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank();
+    __shared__ unsigned long long w_sum[CHAINF_THREADS / 32];
+    __shared__ uint32_t w_has[CHAINF_THREADS / 32];
+    __shared__ unsigned long long a_sum[2];   // this CTA's aggregate of the pass (double-buffered by pass parity)
+    __shared__ uint32_t a_has[2];
+    __shared__ unsigned long long s_pre, s_carry, s_samples;
+    __shared__ uint32_t s_bad, s_heads, s_mine, s_cont, s_last, s_frames;   // (CTA 0's are the cluster's)
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const ChainState st = *state;
+    if (n == 0) {   // (every CTA returns: nobody waits at a cluster barrier)
+        if (rank == 0 && tid == 0) *clean = 0x102u;
+        return;
+    }
     if (tid == 0) {
-        s_bad = (st.err != 0 || n == 0) ? 2u : 0u;
+        s_bad = st.err != 0 ? 2u : 0u;
         s_heads = 0;
         s_mine = 0;
         s_cont = 0;
@@ -1184,25 +1203,30 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
         s_samples = 0;
         s_carry = st.active ? st.seg_samples : 0;
     }
-    __syncthreads();
-    if (n == 0) {
-        if (tid == 0) *clean = 0x102u;
-        return;
-    }
+    cluster.sync();   // CTA 0's counters are initialised before anybody adds to them
+    uint32_t* const g_bad = cluster.map_shared_rank(&s_bad, 0);
+    uint32_t* const g_heads = cluster.map_shared_rank(&s_heads, 0);
+    uint32_t* const g_mine = cluster.map_shared_rank(&s_mine, 0);
+    uint32_t* const g_cont = cluster.map_shared_rank(&s_cont, 0);
+    uint32_t* const g_last = cluster.map_shared_rank(&s_last, 0);
+    uint32_t* const g_frames = cluster.map_shared_rank(&s_frames, 0);
+    unsigned long long* const g_samples = cluster.map_shared_rank(&s_samples, 0);
     const unsigned long long first_off = cands[0].off, next_off = n < n_all ? cands[n].off : ~0ull;
     {   // segments whose first byte lies in this group's byte range
         uint32_t mine = 0;
-        for (uint32_t sgi = tid; sgi < cfg.nseg; sgi += CHAIN_THREADS) {
+        for (uint32_t sgi = rank * CHAINF_THREADS + tid; sgi < cfg.nseg; sgi += CHAINF_CL * CHAINF_THREADS) {
             const DecSeg sg = segs[sgi];
             if (sg.byte_end <= sg.byte_off) continue;
             if ((group_first || sg.byte_off >= first_off) && sg.byte_off < next_off) mine++;
         }
         mine = __reduce_add_sync(0xffffffffu, mine);
-        if (lane == 0 && mine) atomicAdd(&s_mine, mine);
+        if (lane == 0 && mine) atomicAdd(g_mine, mine);
     }
     uint32_t bad = 0, heads = 0, frames = 0;
     unsigned long long samples = 0;
-    for (uint32_t base = 0; base < n; base += CHAIN_THREADS * CHAINF_PER) {
+    uint32_t pass = 0;
+    for (uint32_t base = 0; base < n; base += CHAINF_CL * CHAINF_CHUNK, pass++) {
+        const uint32_t c0 = base + rank * CHAINF_CHUNK + tid * CHAINF_PER;   // (n < 2^32 - 2^15: no wrap)
         unsigned long long ex[CHAINF_PER];   // samples of the open segment before candidate k, counted from the thread's start
         uint32_t hb = 0, gb = 0;             // bit k: candidate k is a segment head / is a frame
         unsigned long long sum = 0;
@@ -1210,7 +1234,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
         uint32_t bs[CHAINF_PER];
 #pragma unroll
         for (uint32_t k = 0; k < CHAINF_PER; k++) {
-            const uint32_t c = base + tid * CHAINF_PER + k;
+            const uint32_t c = c0 + k;
             ex[k] = 0;
             bs[k] = 0;
             if (c >= n) continue;
@@ -1230,7 +1254,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
                 uint32_t steps = 0;
                 while (j >= 0 && recs[j].err != 0 && steps < CHAINF_SCAN) { j--; steps++; }
                 if (j < 0) {
-                    if (expected) atomicOr(&s_cont, 1u);
+                    if (expected) atomicOr(g_cont, 1u);
                     else bad |= 8;
                 } else if (recs[j].err != 0 || cands[j].seg != fc.seg || recs[j].end != fc.off) {
                     bad |= 8;
@@ -1241,7 +1265,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
                 while (j < n_all && cands[j].off < r.end && steps < CHAINF_SCAN) { j++; steps++; }
                 if (!(j < n_all && cands[j].off == r.end && cands[j].seg == fc.seg)) bad |= 16;
                 else if (j < n) { if (recs[j].err) bad |= 16; }
-                else s_last = c;   // the walk leaves the group here (only one frame can)
+                else *g_last = c;   // the walk leaves the group here (only one frame can)
             }
             if (head) {
                 hb |= 1u << k;
@@ -1254,7 +1278,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
             sum += fc.block_size;
             samples += fc.block_size;
         }
-        // block-wide inclusive segmented scan of (sum, has); exclusive value = what the threads before contribute
+        // CTA-wide inclusive segmented scan of (sum, has); exclusive value = what the threads before contribute
         unsigned long long isum = sum;
         uint32_t ihas = has;
 #pragma unroll
@@ -1266,13 +1290,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
                 ihas |= th;
             }
         }
-        __syncthreads();   // (w_sum / w_has of the previous chunk have been consumed)
         if (lane == 31) {
             w_sum[wid] = isum;
             w_has[wid] = ihas;
         }
         __syncthreads();
-        // what precedes this thread inside the chunk: warps before it, then lanes before it
+        // what precedes this thread inside the CTA's run: warps before it, then lanes before it
         unsigned long long psum = 0;
         uint32_t phas = 0;
         for (uint32_t w = 0; w < wid; w++) {
@@ -1286,11 +1309,39 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
             if (lh) { psum = ls; phas = 1; }
             else psum += ls;
         }
-        const unsigned long long before = phas ? psum : s_carry + psum;   // samples of the open segment before this thread
+        if (tid == CHAINF_THREADS - 1) {   // the run's aggregate
+            a_sum[pass & 1] = has ? sum : psum + sum;
+            a_has[pass & 1] = has | phas;
+        }
+        cluster.sync();   // every CTA's aggregate of this pass is in place (and w_sum / w_has have been consumed)
+        if (wid == 0) {
+            // lane r holds CTA r's aggregate; fold the carry and the runs before this CTA's, and all of them for the next pass
+            unsigned long long as = 0;
+            uint32_t ah = 0;
+            if (lane < CHAINF_CL) {
+                as = *cluster.map_shared_rank(&a_sum[pass & 1], lane);
+                ah = *cluster.map_shared_rank(&a_has[pass & 1], lane);
+            }
+            unsigned long long acc = s_carry, pre = 0;
+#pragma unroll
+            for (uint32_t r = 0; r < CHAINF_CL; r++) {
+                if (r == rank) pre = acc;
+                const unsigned long long rs = __shfl_sync(0xffffffffu, as, r);
+                const uint32_t rh = __shfl_sync(0xffffffffu, ah, r);
+                if (rh) acc = rs;
+                else acc += rs;
+            }
+            if (lane == 0) {
+                s_pre = pre;       // samples of the open segment before this CTA's run (the carry included unless a head came first)
+                s_carry = acc;     // ... and at the end of the pass
+            }
+        }
+        __syncthreads();
+        const unsigned long long before = phas ? psum : s_pre + psum;   // samples of the open segment before this thread
         uint32_t seen = 0;
 #pragma unroll
         for (uint32_t k = 0; k < CHAINF_PER; k++) {
-            const uint32_t c = base + tid * CHAINF_PER + k;
+            const uint32_t c = c0 + k;
             if (c >= n) continue;
             if (!(gb & (1u << k))) {
                 pos_out[c] = ~0ull;
@@ -1311,22 +1362,21 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
             if (sg.pcm_off + pos + bs[k] > cfg.out_samples) bad |= 64;
             pos_out[c] = sg.pcm_off + pos;
         }
-        __syncthreads();
-        if (tid == CHAIN_THREADS - 1) s_carry = has ? sum : (phas ? psum + sum : s_carry + psum + sum);   // the open segment at the end of the chunk
-        __syncthreads();
+        __syncthreads();   // (s_pre is rewritten in the next pass)
     }
     heads = __reduce_add_sync(0xffffffffu, heads);
     frames = __reduce_add_sync(0xffffffffu, frames);
     bad = __reduce_or_sync(0xffffffffu, bad);
     samples = warp_sum_u64(samples);
     if (lane == 0) {
-        if (heads) atomicAdd(&s_heads, heads);
-        if (frames) atomicAdd(&s_frames, frames);
-        if (bad) atomicOr(&s_bad, bad);
-        atomicAdd(&s_samples, samples);
+        if (heads) atomicAdd(g_heads, heads);
+        if (frames) atomicAdd(g_frames, frames);
+        if (bad) atomicOr(g_bad, bad);
+        atomicAdd(g_samples, samples);
     }
-    __syncthreads();
-    if (tid == 0) {
+    __threadfence();   // pos_out of every CTA is visible to CTA 0's last look
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
         const bool ok = s_bad == 0 && s_heads == s_mine && (st.active != 0) == (s_cont != 0);
         *clean = ok ? 1u : (0x100u | s_bad | (s_heads != s_mine ? 128u : 0u) | ((st.active != 0) != (s_cont != 0) ? 0x200u : 0u));   // why not: FLACB200_DEBUG
         if (ok) {
@@ -1339,7 +1389,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_fast(DecCfg cfg, const 
                 ns.active = 1;
                 ns.expect_seg = fl.seg;
                 ns.expect_off = recs[s_last].end;
-                ns.seg_samples = pos_out[s_last] - segs[fl.seg].pcm_off + fl.block_size;
+                ns.seg_samples = *(volatile unsigned long long*)(pos_out + s_last) - segs[fl.seg].pcm_off + fl.block_size;
             }
             *state = ns;
         }
@@ -1488,7 +1538,7 @@ cudaError_t launch_chain(const DecCfg& cfg, const uint8_t* bytes, const DecSeg* 
 void launch_chain_fast(const DecCfg& cfg, const DecSeg* segs, const FrameCand* cands, const DecRec* recs, uint32_t n, uint32_t n_all,
                        uint32_t group_first, unsigned long long* pos, ChainState* state, uint32_t* clean, cudaStream_t st)
 {
-    count_launch(), k_chain_fast<<<1, CHAIN_THREADS, 0, st>>>(cfg, segs, cands, recs, n, n_all, group_first, pos, state, clean);
+    count_launch(), k_chain_fast<<<CHAINF_CL, CHAINF_THREADS, 0, st>>>(cfg, segs, cands, recs, n, n_all, group_first, pos, state, clean);
 }
 
 // k_emit4: the common layouts (1 or 2 channels, 2 or 3 bytes per sample, packed bytes).  One CTA takes a bundle of 32

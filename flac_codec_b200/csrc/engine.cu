@@ -112,6 +112,7 @@ struct flacb200_engine {
     unsigned legacy = 0;
     bool no_batch = false, debug = false;
     size_t batch_bytes = 0;   // 0 = default
+    uint32_t plane_mb = 12288;   // decode: MB of scratch planes per launch group (two such buffers when the input needs several groups: they are pipelined)
     uint32_t lpc_overlap = 0;   // (experiment, off: measured no gain -- both sides are occupancy-bound) CTAs per SM of the persistent k_lpc3 that runs beside the previous group's integer kernels; 0 = off
     bool fused_frame = false;   // k_frame4 (analysis + decision + packing in one kernel): parity-green, measured SLOWER than the three
                                 // kernels on C4 (45 vs 41 ms per step), so it is an option, not the default
@@ -221,6 +222,7 @@ int flacb200_engine_create(int device, flacb200_engine** out)
     for (auto& ev : e->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char* v = getenv("FLACB200_LPC_OVERLAP")) e->lpc_overlap = (uint32_t)strtoul(v, nullptr, 0);
+    if (const char* v = getenv("FLACB200_PLANE_MB")) e->plane_mb = std::max<uint32_t>((uint32_t)strtoul(v, nullptr, 0), 1);
     if (const char* v = getenv("FLACB200_FUSED")) e->fused_frame = strtoul(v, nullptr, 0) != 0;
     if (const char* v = getenv("FLACB200_LEGACY")) e->legacy = (unsigned)strtoul(v, nullptr, 0);
     if (const char* v = getenv("FLACB200_BATCH_BYTES")) e->batch_bytes = std::max<size_t>((size_t)strtoull(v, nullptr, 0), 1);
@@ -295,6 +297,7 @@ int flacb200_engine_set_option(flacb200_engine* e, const char* key, uint64_t val
     else if (!strcmp(key, "no_batch")) e->no_batch = value != 0;
     else if (!strcmp(key, "debug")) e->debug = value != 0;
     else if (!strcmp(key, "lpc_overlap")) e->lpc_overlap = (uint32_t)value;
+    else if (!strcmp(key, "plane_mb")) e->plane_mb = std::max<uint32_t>((uint32_t)value, 1);
     else if (!strcmp(key, "fused")) e->fused_frame = value != 0;
     else return FLACB200_E_BAD_ARGUMENT;
     return 0;
@@ -1034,7 +1037,9 @@ extern "C" int flacb200_decode(flacb200_engine* e, const flacb200_stream_params*
         // before the host has read the walk's verdict and checks it itself; when k_chain_fast declined the group the general
         // walk runs and the kernel is launched again; predictors beyond its register budget: k_restore + k_emit.
         cudaStream_t aux = e->aux;
-        size_t buf_budget = (size_t)3 << 30;
+        // a group should fill the GPU's 148 x 16 x 64 k_parse lanes as nearly as its frames allow: the walk of a group takes about
+        // as long half full as full (2.4 ms for 73 k frames, 2.7 ms for 98 k, profiles/r02_v2_dec_summary.csv)
+        size_t buf_budget = (size_t)e->plane_mb << 20;
         uint32_t pg = (uint32_t)std::min<size_t>(std::max<size_t>(buf_budget / per_frame, 1), ncand);
         if (e->chunk_frames) pg = std::min<uint32_t>(pg, e->chunk_frames);
         if (pg < ncand && (size_t)pg * 2 >= ncand) pg = (ncand + 1) / 2;   // two groups: equal halves
