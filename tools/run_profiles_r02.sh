@@ -15,3 +15,7 @@ for k in k_lpc3 k_analyze3 k_pack3; do python tools/sass_hist.py gpurun_out/${ta
 python tools/sass_hist.py gpurun_out/${tag}_fused.ncu-rep k_frame4 25 > gpurun_out/${tag}_sass_k_frame4.txt 2>&1
 rm -f gpurun_out/${tag}_enc.ncu-rep gpurun_out/${tag}_dec.ncu-rep gpurun_out/${tag}_fused.ncu-rep
 ls -la gpurun_out/${tag}_*
+# single streams (C1 / C3 / C5 shapes): stage clocks and the launch list of the same command
+python tools/latency_probe.py > gpurun_out/${tag}_latency.jsonl 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_latency_launches.csv python tools/latency_probe.py > /dev/null 2>&1
+python tools/ncu_summary.py list gpurun_out/${tag}_latency_launches.csv gpurun_out/${tag}_latency_launches.md
