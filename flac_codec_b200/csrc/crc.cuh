@@ -133,43 +133,64 @@ __device__ inline uint32_t crc16_f8(const Crc16Fold& t, uint32_t hi, uint32_t lo
 
 
 // CRC-16 of bytes[start, start + len) in global memory by one warp with the wide folding above (all 32 lanes call, all get
-// the result).  `bytes` must be 8-byte aligned (the buffer base); start and len are arbitrary.  Lane l folds every 32nd group
-// of eight bytes; the bytes in front of the first aligned group ride on lane 0's first term, the bytes behind the last group
-// are appended by classic byte steps.
+// the result).  `bytes` must be 8-byte aligned (the buffer base); start and len are arbitrary (len < 2^34).  Lane l folds every
+// 32nd group of eight bytes; the bytes in front of the first aligned group ride on lane 0's first term, the bytes behind the
+// last group are appended by classic byte steps.
+// F8 of a group straight from the two little-endian words of the load (message byte 0 = low byte of lo): one PRMT per byte
+__device__ __forceinline__ uint32_t crc16_f8_le(const Crc16Fold& t, uint32_t w0, uint32_t w1)
+{
+    const uint32_t a = t.T[7][__byte_perm(w0, 0, 0x4440)] ^ t.T[6][__byte_perm(w0, 0, 0x4441)];
+    const uint32_t b = t.T[5][__byte_perm(w0, 0, 0x4442)] ^ t.T[4][__byte_perm(w0, 0, 0x4443)];
+    const uint32_t c = t.T[3][__byte_perm(w1, 0, 0x4440)] ^ t.T[2][__byte_perm(w1, 0, 0x4441)];
+    const uint32_t d = t.T[1][__byte_perm(w1, 0, 0x4442)] ^ t.T[0][__byte_perm(w1, 0, 0x4443)];
+    return (a ^ b) ^ (c ^ d);
+}
+
 __device__ inline uint32_t crc16_warp_fold(const Crc16Fold& t, const uint8_t* __restrict__ bytes, unsigned long long start, unsigned long long len)
 {
     const uint32_t lane = threadIdx.x & 31;
     const unsigned long long end = start + len;
     auto byte_step = [&](uint32_t crc, uint32_t b) { return (t.T[0][((crc >> 8) ^ b) & 0xff] ^ (crc << 8)) & 0xffffu; };
+    auto fold = [&](uint32_t acc, uint32_t f) { return (uint32_t)(t.m_hi[acc >> 8] ^ t.m_lo[acc & 0xff]) ^ f; };
     unsigned long long a = (start + 7) & ~7ull;
     if (a > end) a = end;
     const uint32_t head = (uint32_t)(a - start);
-    const unsigned long long npairs = (end - a) >> 3;
+    const uint32_t npairs = (uint32_t)((end - a) >> 3);
     const uint32_t tail = (uint32_t)((end - a) & 7);
     const uint2* pairs = reinterpret_cast<const uint2*>(bytes + a);
+    // this lane's groups: lane, lane + 32, ...
+    const uint32_t mine = npairs > lane ? (npairs - 1 - lane) / 32 + 1 : 0;
     uint32_t acc = 0;
-    unsigned long long last = 0;
-    bool any = false;
-    for (unsigned long long i = lane; i < npairs; i += 32) {
-        const uint2 v = pairs[i];   // memory order = message order: byte 0 is the low byte of v.x
-        uint32_t f = crc16_f8(t, __byte_perm(v.x, 0, 0x0123), __byte_perm(v.y, 0, 0x0123));
-        if (i == 0 && head) {       // CRC(head || group 0) = CRC(head) * x^64 + F8(group 0)
+    uint32_t i = lane;
+    if (mine) {   // the first group, with the head bytes on lane 0: CRC(head || group 0) = CRC(head) * x^64 + F8(group 0)
+        const uint2 v = pairs[i];
+        acc = crc16_f8_le(t, v.x, v.y);
+        if (lane == 0 && head) {
             uint32_t h = 0;
             for (uint32_t k = 0; k < head; k++) h = byte_step(h, bytes[start + k]);
             for (uint32_t k = 0; k < 8; k++) h = byte_step(h, 0);
-            f ^= h;
+            acc ^= h;
         }
-        acc = (t.m_hi[acc >> 8] ^ t.m_lo[acc & 0xff]) ^ f;
-        last = i;
-        any = true;
+        i += 32;
     }
-    uint32_t part = any ? gf16_mulmod(acc, t.xd2[(uint32_t)(npairs - 1 - last)]) : 0u;
+    uint32_t left = mine ? mine - 1 : 0;
+    for (; left >= 2; left -= 2, i += 64) {   // two groups per turn: the loads and the sixteen look-ups are independent
+        const uint2 v = pairs[i], w = pairs[i + 32];
+        const uint32_t f0 = crc16_f8_le(t, v.x, v.y), f1 = crc16_f8_le(t, w.x, w.y);
+        acc = fold(fold(acc, f0), f1);
+    }
+    if (left) {
+        const uint2 v = pairs[i];
+        acc = fold(acc, crc16_f8_le(t, v.x, v.y));
+    }
+    const uint32_t last = lane + 32 * (mine - 1);   // (only used when mine != 0)
+    uint32_t part = mine ? gf16_mulmod(acc, t.xd2[npairs - 1 - last]) : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
     part &= 0xffffu;
     if (npairs == 0)   // no aligned group at all: the head bytes still have to go in
         for (uint32_t k = 0; k < head; k++) part = byte_step(part, bytes[start + k]);
-    for (uint32_t k = 0; k < tail; k++) part = byte_step(part, bytes[a + npairs * 8 + k]);
+    for (uint32_t k = 0; k < tail; k++) part = byte_step(part, bytes[a + (unsigned long long)npairs * 8 + k]);
     return part;
 }
 
