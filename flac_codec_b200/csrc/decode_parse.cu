@@ -529,6 +529,9 @@ __global__ void __launch_bounds__(RESTORE_THREADS) k_restore(DecCfg cfg, const F
 constexpr uint32_t RE_RING = 4;     // groups of four samples in flight per lane and channel
 constexpr uint32_t RE_TG = 8;       // groups per output tile
 constexpr uint32_t RE_WARPS = 2;    // independent bundles per CTA
+#ifndef FLACB200_RE_OCC
+#define FLACB200_RE_OCC 8            // CTAs per SM the register budget is cut for
+#endif
 
 template <int C, int B, int HB>
 __device__ __forceinline__ void restore_emit_run(const int32_t* const (&plane)[C], uint32_t n, uint32_t nmax4, const uint32_t (&order)[C],
@@ -675,7 +678,7 @@ __device__ __forceinline__ void restore_emit_run(const int32_t* const (&plane)[C
 }
 
 template <int C, int B>
-__global__ void __launch_bounds__(32 * RE_WARPS, 8) k_restore_emit(DecCfg cfg, const FrameCand* __restrict__ cands, uint32_t ncand,
+__global__ void __launch_bounds__(32 * RE_WARPS, FLACB200_RE_OCC) k_restore_emit(DecCfg cfg, const FrameCand* __restrict__ cands, uint32_t ncand,
                                                                    const SubRec* __restrict__ subs, const DecRec* __restrict__ recs,
                                                                    const unsigned long long* __restrict__ pos, const int32_t* __restrict__ planes,
                                                                    uint8_t* __restrict__ out, const uint32_t* __restrict__ flags, uint32_t need_clean)

@@ -91,7 +91,8 @@ __device__ inline void a3_tile(const int32_t* __restrict__ planes, uint32_t slot
 // HB: the launch's max LPC order rounded up to 4/8/12/16
 template <int HB, bool STEREO>
 __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_t* __restrict__ planes, uint4* __restrict__ res16, uint32_t slot,
-                             uint32_t pslot, uint32_t cand, uint32_t wsub, uint32_t full_bps, const LpcRec& lp, A3Cand& sm, CandRec* __restrict__ rec)
+                             uint32_t pslot, uint32_t cand, uint32_t wsub, uint32_t full_bps, const LpcRec& lp, A3Cand& sm, CandRec* __restrict__ rec,
+                             uint4* __restrict__ gres16 = nullptr)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n = d.n;
@@ -432,6 +433,11 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
         if (bad_l) atomicOr(&sm.bad_l, 1u);
     }
     a3_pair_sync(cand);
+    // The LPC residuals as the int16 copy the first pass parked, for k_pack3, which reads them back instead of unpacking the PCM
+    // and running the FIR a second time (a quarter of its instructions).  Both warps copy (8 KB per candidate) before the
+    // first one goes on to the decision; whether the subframe really is an LPC subframe is said by CandRec::pad0 below.
+    if (gres16 != nullptr && lpc_ok && use16)
+        for (uint32_t k = wsub * 32 + lane; k < rounds * 64; k += 32 * A3_WPC) gres16[k] = res16[k];
     if (wsub != 0) return;
     const RiceChoice& cf_ = sm.choice[0];
     const RiceChoice& cl_ = sm.choice[1];
@@ -475,6 +481,8 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
         for (uint32_t j = lane; j < MAX_PARTS; j += 32) rec->rice[j] = ch.rice[j];
         if (lane < MAX_LPC) rec->q[lane] = lp.q[lane];
     }
+    // k_pack3 may use the stored residuals: an LPC subframe whose residuals all fit 16 bits
+    if (lane == 0) rec->pad0 = (gres16 != nullptr && pick == 1 && use16) ? 1 : 0;
 }
 
 template <bool STEREO>
@@ -490,7 +498,7 @@ __host__ __device__ constexpr size_t a3_smem_bytes()
 template <int HB, bool STEREO>
 __global__ void __launch_bounds__(32 * A3_WPC * (STEREO ? 4 : 2), STEREO ? 2 : 4)
     k_analyze3(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm, const LpcRec* __restrict__ lpcs,
-               CandRec* __restrict__ out, unsigned long long* __restrict__ abssum)
+               CandRec* __restrict__ out, unsigned long long* __restrict__ abssum, uint4* __restrict__ gres16)
 {
     constexpr int NC = a3_cands<STEREO>();
     extern __shared__ __align__(16) uint8_t a3_dyn[];
@@ -564,7 +572,7 @@ __global__ void __launch_bounds__(32 * A3_WPC * (STEREO ? 4 : 2), STEREO ? 2 : 4
     const uint32_t full_bps = STEREO ? cand_bps(cfg, slot) : cfg.bps;
     const LpcRec lp = lpcs[(size_t)f * cfg.nslots + slot];
     a3_candidate<HB, STEREO>(cfg, d, planes, res16_all + (size_t)cand * (A3_PLANE * 2 / 16), slot, STEREO ? slot : cand, cand, wsub, full_bps, lp,
-                             cands_sm[cand], rec);
+                             cands_sm[cand], rec, gres16 ? gres16 + ((size_t)f * cfg.nslots + slot) * (A3_PLANE * 2 / 16) : nullptr);
 }
 
 // the 32-bit per-tile sums of the fixed residuals (passes 1 and 2) need |x| < 2^24: 24-bit stereo with its 25-bit side
@@ -575,7 +583,7 @@ bool analyze3_ok(const EncCfg& cfg)
 }
 
 cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const LpcRec* lpcs, CandRec* cands,
-                            unsigned long long* abssum, cudaStream_t st)
+                            unsigned long long* abssum, uint4* gres16, cudaStream_t st)
 {
     const uint32_t hb = cfg.max_lpc_order ? (cfg.max_lpc_order + 3u) >> 2 : 1u;
 #ifndef FLACB200_A3_PAD
@@ -588,7 +596,7 @@ cudaError_t launch_analyze3(const EncCfg& cfg, const FrameDesc* descs, const uin
         cudaError_t e_ = cudaFuncSetAttribute(k_analyze3<HBV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);          \
         if (e_ != cudaSuccess) return e_;                                                                                             \
         const uint32_t groups_ = ST ? 1u : (cfg.channels + 1u) / 2u;                                                                  \
-        count_launch(), k_analyze3<HBV, ST><<<cfg.nframes * groups_, 32 * A3_WPC * (ST ? 4 : 2), smem_, st>>>(cfg, descs, pcm, lpcs, cands, abssum);  \
+        count_launch(), k_analyze3<HBV, ST><<<cfg.nframes * groups_, 32 * A3_WPC * (ST ? 4 : 2), smem_, st>>>(cfg, descs, pcm, lpcs, cands, abssum, gres16);  \
     } while (0)
     if (cfg.mode != MODE_INDEPENDENT) {
         switch (hb) {

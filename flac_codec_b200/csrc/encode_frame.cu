@@ -29,7 +29,7 @@ struct P3Smem {
 // the residual block of one FIXED / LPC subframe; pos = bit position of the first residual partition header
 template <int HB, bool STEREO>
 __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const uint8_t* __restrict__ pcm, uint32_t slot, const CandRec& cr,
-                                    uint32_t words_sa, uint32_t pos)
+                                    uint32_t words_sa, uint32_t pos, const uint4* __restrict__ res16)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n = d.n, wasted = cr.wasted, order = cr.order, shift = cr.shift;
@@ -50,6 +50,20 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
     for (uint32_t rd = 0; rd < rounds; rd++) {
         const uint32_t i0 = (rd * 32 + lane) * 16;
         const bool live = i0 < n;
+        int32_t r[16];
+        if (res16 != nullptr) {   // the residuals k_analyze3 left behind (int16 pairs, two 16-byte chunks per tile)
+            uint4 lo4 = make_uint4(0, 0, 0, 0), hi4 = lo4;
+            if (live) {
+                lo4 = res16[(rd * 2 + 0) * 32 + lane];
+                hi4 = res16[(rd * 2 + 1) * 32 + lane];
+            }
+            const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                r[2 * k] = (int32_t)(w[k] << 16) >> 16;
+                r[2 * k + 1] = (int32_t)w[k] >> 16;
+            }
+        } else {
         int32_t x[16], h[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = 0;
@@ -61,7 +75,6 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
             h[e] = lane == 0 ? carry[e] : up;
             carry[e] = __shfl_sync(0xffffffffu, x[e], 31);
         }
-        int32_t r[16];
         if (lpc) {   // LpcSubframeParameters::encode_residuals (:3174-3203)
 #pragma unroll
             for (int e = 0; e < 16; e++) {
@@ -79,6 +92,7 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
                                                                                                            : x0 - 4 * x1 + 6 * x2 - 4 * x3 + x4;
                 x4 = x3; x3 = x2; x2 = x1; x1 = x0;
             }
+        }
         }
         // ---- code lengths of this lane's tile ----
         const uint32_t lo_i = max(i0, order), hi_i = min(i0 + 16u, n);   // residuals exist for [lo_i, hi_i)
@@ -179,7 +193,7 @@ template <int HB, bool STEREO>
 #endif
 __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? FLACB200_P3_MINB : 2)
     k_pack3(EncCfg cfg, uint32_t min_words, uint32_t cap_words, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
-            const CandRec* __restrict__ cands, const FrameRec* __restrict__ frecs, uint8_t* __restrict__ out)
+            const CandRec* __restrict__ cands, const FrameRec* __restrict__ frecs, uint8_t* __restrict__ out, const uint4* __restrict__ gres16)
 {
     extern __shared__ __align__(16) uint32_t p3_words[];
     __shared__ P3Smem sm;
@@ -259,7 +273,9 @@ __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? FLACB200_P3_MINB :
             p3_put_masked(words_sa, pos + 2, 4, cr.porder_w);
         }
         pos += 6;
-        p3_residuals<HB, STEREO>(cfg, d, pcm, slot, cr, words_sa, pos);
+        // (CandRec::pad0: k_analyze3 stored this LPC subframe's residuals; 512 16-byte chunks per candidate)
+        const uint4* r16 = (gres16 != nullptr && cr.type == 3 && cr.pad0 == 1) ? gres16 + ((size_t)f * cfg.nslots + slot) * 512 : nullptr;
+        p3_residuals<HB, STEREO>(cfg, d, pcm, slot, cr, words_sa, pos, r16);
     }
     __syncthreads();
     // ---- CRC-16 over everything but the last two bytes (src/encode.rs:2408-2409) ----
@@ -323,7 +339,7 @@ uint32_t pack3_cap_words(const EncCfg& cfg)
 bool pack3_ok(const EncCfg& cfg) { return analyze_fast_ok(cfg) && (size_t)pack3_cap_words(cfg) * 4 <= 200 * 1024; }
 
 cudaError_t launch_pack3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const CandRec* cands, const FrameRec* frecs, uint8_t* out,
-                         cudaStream_t st)
+                         const uint4* gres16, cudaStream_t st)
 {
     const uint32_t nsub = cfg.mode == MODE_INDEPENDENT ? cfg.channels : 2;
     const uint32_t cap_words = pack3_cap_words(cfg);
@@ -334,8 +350,8 @@ cudaError_t launch_pack3(const EncCfg& cfg, const FrameDesc* descs, const uint8_
     do {                                                                                                                             \
         cudaError_t e_ = cudaFuncSetAttribute(k_pack3<HBV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);            \
         if (e_ != cudaSuccess) return e_;                                                                                            \
-        count_launch(), k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)small_words * 4, st>>>(cfg, 0u, small_words, descs, pcm, cands, frecs, out);    \
-        count_launch(), k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)cap_words * 4, st>>>(cfg, small_words, cap_words, descs, pcm, cands, frecs, out); \
+        count_launch(), k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)small_words * 4, st>>>(cfg, 0u, small_words, descs, pcm, cands, frecs, out, gres16);    \
+        count_launch(), k_pack3<HBV, ST><<<cfg.nframes, 32 * nsub, (size_t)cap_words * 4, st>>>(cfg, small_words, cap_words, descs, pcm, cands, frecs, out, gres16); \
     } while (0)
     if (cfg.mode != MODE_INDEPENDENT) {
         switch (hb) {

@@ -32,8 +32,8 @@ bool pack3_ok(const EncCfg&);
 bool analyze3_ok(const EncCfg&);
 bool lpc3_ok(const EncCfg&, bool);
 cudaError_t launch_lpc3(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, uint32_t, cudaStream_t);
-cudaError_t launch_analyze3(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, cudaStream_t);
-cudaError_t launch_pack3(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
+cudaError_t launch_analyze3(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, uint4*, cudaStream_t);
+cudaError_t launch_pack3(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, const uint4*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
 bool analyze_fast_ok(const EncCfg&);
 cudaError_t launch_pack2_crc(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
@@ -118,7 +118,7 @@ struct flacb200_engine {
                                 // kernels on C4 (45 vs 41 ms per step), so it is an option, not the default
     int sm_count = 148;
     std::vector<cudaEvent_t> lpc_ev;   // per group: LPC parameters ready, analysis done (the two LpcRec buffers alternate)
-    DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, lookback, find_slots, dec[12];
+    DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, lookback, find_slots, res16, dec[12];
     std::map<uint32_t, uint32_t> win_off;   // block length -> offset in doubles
     std::vector<double> win_host;
     flacb200_options win_opt{};
@@ -254,7 +254,7 @@ void flacb200_engine_destroy(flacb200_engine* e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->pcm, &e->planes, &e->masks, &e->lpcs, &e->cands, &e->frecs, &e->descs, &e->out, &e->fbytes, &e->totals, &e->winpool,
-                      &e->scratch, &e->lut, &e->lookback, &e->find_slots};
+                      &e->scratch, &e->lut, &e->lookback, &e->find_slots, &e->res16};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto& b : e->dec)
@@ -524,6 +524,10 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     ENS(e->fbytes, nframes * sizeof(uint32_t));
     ENS(e->totals, 64);
     if (fused) ENS(e->lookback, (size_t)chunk * sizeof(unsigned long long));
+    // k_analyze3 -> k_pack3: the int16 LPC residuals of every candidate of the launch group (8 KB each)
+    const bool keep_res16 = frame_analyze && frame_pack && !fused && !(legacy & 1024u);
+    if (keep_res16) ENS(e->res16, ncand_chunk * 8192);
+    uint4* const d_res16 = keep_res16 ? (uint4*)e->res16.p : nullptr;
     if (!(out && out_location == FLACB200_DEVICE && out_capacity >= bound + 64 && ((uintptr_t)out & 15) == 0)) ENS(e->out, bound + 64);
     const bool need_scratch = !residual_uses_smem(cfg);
     if (need_scratch) ENS(e->scratch, ncand_chunk * 2 * cfg.bpad * sizeof(int32_t));
@@ -644,7 +648,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
             time_mark(e, eb + 3);
             time_mark(e, eb + 4);
         } else {
-        if (frame_analyze) CK(launch_analyze3(c, dd, d_pcm, lp, (CandRec*)e->cands.p, d_abssum, st));
+        if (frame_analyze) CK(launch_analyze3(c, dd, d_pcm, lp, (CandRec*)e->cands.p, d_abssum, d_res16, st));
         else if (fast_analyze) CK(launch_analyze(c, dd, d_pcm, lp, (CandRec*)e->cands.p, d_abssum, st));
         else
             CK(launch_residual(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, lp, (CandRec*)e->cands.p, (int32_t*)e->scratch.p, st));
@@ -666,7 +670,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         launch_decide_scan(c, dd, (const CandRec*)e->cands.p, d_abssum, (FrameRec*)e->frecs.p, (uint32_t*)e->fbytes.p + base,
                            (unsigned long long*)e->totals.p, pipe_out ? e->d_h_totals + nchunks : nullptr, d_out, !frame_pack, st);
         time_mark(e, eb + 4);
-        if (frame_pack) CK(launch_pack3(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
+        if (frame_pack) CK(launch_pack3(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, d_res16, st));
         else if (fast_pack) CK(launch_pack2_crc(c, dd, d_pcm, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
         else CK(launch_pack_crc(c, dd, (const int32_t*)e->planes.p, (const CandRec*)e->cands.p, (const FrameRec*)e->frecs.p, d_out, st));
         }
