@@ -32,6 +32,23 @@ bool analyze_fast_ok(const EncCfg& cfg);   // encode_kernels.cu
 #define FLACB200_A3_WPC 2
 #endif
 constexpr int A3_WPC = FLACB200_A3_WPC;   // warps per candidate
+// LPC residual FIR of k_analyze3: 0 = IMAD.WIDE chains, 1 = DFMA chains, outputs in two halves of 8, 2 = DFMA, 16 outputs at once
+#ifndef FLACB200_A3_FIR
+#define FLACB200_A3_FIR 1
+#endif
+constexpr int A3_FIR_OUT = FLACB200_A3_FIR == 2 ? 16 : 8;
+// int32 -> double without the conversion unit: 2^52 + 2^31 + v is exact bit-pasting, the subtraction is one DADD
+#ifndef FLACB200_A3_I2F
+#define FLACB200_A3_I2F 0
+#endif
+__device__ inline double a3_i2d(int32_t v)
+{
+#if FLACB200_A3_I2F
+    return (double)v;
+#else
+    return __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)), 4503601774854144.0);
+#endif
+}
 constexpr int A3_SETS = 6;       // fixed orders 0..4, LPC
 constexpr int A3_PLANE = 4096;   // samples per plane (largest block of the register-tiled kernels)
 
@@ -107,9 +124,15 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
     const uint32_t kmax = min(4u, n - 1);
     const bool have_lpc = lp.ok != 0;
     const uint32_t order = have_lpc ? lp.order : 0, shift = lp.shift;
+#if FLACB200_A3_FIR == 0
     int32_t q[HB];
 #pragma unroll
     for (int j = 0; j < HB; j++) q[j] = (have_lpc && (uint32_t)j < order) ? (int32_t)lp.q[j] : 0;
+#else
+    double qd[HB];   // the coefficients as doubles: the FIR runs on the FP64 pipe (see a3_fir_f64)
+#pragma unroll
+    for (int j = 0; j < HB; j++) qd[j] = (have_lpc && (uint32_t)j < order) ? (double)lp.q[j] : 0.0;
+#endif
 
     uint32_t wasted = 0, fo = 0, bps = full_bps;
     bool lpc_ok = have_lpc, use16 = false;
@@ -214,6 +237,7 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
             int32_t rl[16];
             if (fir) {
                 uint32_t oacc = 0, sacc = 0;   // OR of the checked_sub overflow signs / of the bits that do not fit int16
+#if FLACB200_A3_FIR == 0
 #pragma unroll
                 for (int e = 0; e < 16; e++) {
                     long long sum = 0;
@@ -225,6 +249,39 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     oacc |= (uint32_t)((x[e] ^ pred) & (x[e] ^ rr));   // checked_sub: sign bit set when it overflowed
                     sacc |= (uint32_t)rr + 0x8000u;
                 }
+#else
+                // The i64 dot product (:3187) as DFMAs: |q| < 2^15, |x| < 2^25, <= 16 taps -- every partial sum is an integer
+                // below 2^45 and exact in a double.  The accumulators start at 1.5 * 2^52, so the two's complement bits of the sum
+                // sit in the mantissa (ulp = 1) and `(sum >> shift) as i32` is one funnel shift over the two words (shift <= 15
+                // reaches bit 46 at most; the 2^51 of the bias is above that).  One instruction per tap on the FP64 pipe, which
+                // this kernel leaves idle, instead of IMAD.WIDE + carry adds on the two integer pipes that bound it.  Inputs are
+                // the outer loop: consecutive DFMAs go to different accumulators.
+#pragma unroll
+                for (int half = 0; half < 16; half += A3_FIR_OUT) {
+                    double acc[A3_FIR_OUT];
+#pragma unroll
+                    for (int e = 0; e < A3_FIR_OUT; e++) acc[e] = 6755399441055744.0;
+#pragma unroll
+                    for (int i = half - HB; i < half + A3_FIR_OUT - 1; i++) {
+                        const int32_t v = i >= 0 ? x[i >= 0 ? i : 0] : h[16 + i >= 0 ? 16 + i : 0];
+                        const double dv = a3_i2d(v);
+#pragma unroll
+                        for (int e = 0; e < A3_FIR_OUT; e++) {
+                            const int j = half + e - 1 - i;   // tap of output half + e that reads input i
+                            if (j >= 0 && j < HB) acc[e] = fma(qd[j >= 0 && j < HB ? j : 0], dv, acc[e]);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < A3_FIR_OUT; e++) {
+                        const int32_t pred = (int32_t)__funnelshift_r((uint32_t)__double2loint(acc[e]), (uint32_t)__double2hiint(acc[e]), shift);
+                        const int32_t xe = x[half + e];
+                        const int32_t rr = (int32_t)((uint32_t)xe - (uint32_t)pred);
+                        rl[half + e] = rr;
+                        oacc |= (uint32_t)((xe ^ pred) & (xe ^ rr));   // checked_sub: sign bit set when it overflowed
+                        sacc |= (uint32_t)rr + 0x8000u;
+                    }
+                }
+#endif
                 if (stage < 2) {
                     if (((oacc >> 31) | (sacc >> 16)) != 0) {   // rare: look again, only samples in [order, n) count
                         const uint32_t first = order > i0 ? min(order - i0, 16u) : 0u, last = min(16u, n - i0);
