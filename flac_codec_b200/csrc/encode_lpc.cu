@@ -343,4 +343,336 @@ cudaError_t launch_lpc3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t
     return cudaGetLastError();
 }
 
+
+// =====================================================================================================================
+// k_lpc4: the same analysis with ONE LANE PER CANDIDATE -- a warp takes eight stereo frames (32 candidates).
+//
+// k_lpc3 spreads a candidate's lags over four lanes x four lags: 16 lag slots for the 13 lags of Options::best, a ring of
+// windowed doubles in shared memory that every lane reads back, and an unpack/convert/store phase that costs as many issue
+// slots as the FP64 loop itself (FP64 pipe 67 % busy).  Here a lane owns its candidate outright:
+//   * all NL lags are NL accumulators of the lane (13 of 13 FP64 operations useful), the lagged samples are a circular
+//     window of 16 doubles in registers with static indices (the tile loop is unrolled over 16 samples);
+//   * nothing is staged as doubles: the raw PCM bytes (16 samples x 2 channels) and the window values of the eight frames
+//     travel global -> shared with cp.async, two tiles ahead; a lane pulls ITS frame's bytes with 128-bit loads, extracts
+//     left and right with one PRMT + shift each (static positions), forms its own channel combination with per-lane
+//     constants (l * ca + r * cb) >> cs, converts and multiplies by the window value -- about 12 integer instructions
+//     beside the 27 FP64 instructions of a sample;
+//   * the first tile and tiles that reach past the shortest frame of the warp run a predicated copy of the tile body
+//     (a lag only counts samples that exist: no zero terms are ever added, the sums start from -0.0 as in k_lpc3);
+//   * Levinson-Durbin, the order estimate and the quantisation run on all 32 lanes at once, fully unrolled over the
+//     template's order so that R[], the coefficient sets and the errors stay in registers; the set of the best order so
+//     far is kept as the recursion proceeds (subframe_bits_by_order only needs the error of the order just finished).
+// Arithmetic, operation for operation, is k_lpc3's (and the reference's :3478-3702).
+// =====================================================================================================================
+constexpr int L4_WARPS = 4;
+#ifndef FLACB200_L4_MINB
+#define FLACB200_L4_MINB 4
+#endif
+constexpr int L4_SLOTS = 3;
+constexpr int L4_STRIDE = 144;   // bytes per frame in a slot: <= 128 B of PCM (or 16 window doubles) + 16 B skew -> the 8 frames' LDS.128 hit distinct banks
+constexpr int L4_SLOT_BYTES = 2 * 8 * L4_STRIDE;   // PCM of 8 frames, then their window values
+
+// sample at byte offset O (static) of the words w[]: the B bytes moved to the top of a register by PRMT, then shifted down
+template <int B, int O, int NW>
+__device__ __forceinline__ int32_t l4_extract(const uint32_t (&w)[NW], const uint32_t (&sel)[4])
+{
+    constexpr int wi = O / 4, sh = O % 4;
+    constexpr int wj = (wi + 1 < NW) ? wi + 1 : wi;   // the second word is only selected from when the sample straddles
+    return (int32_t)__byte_perm(w[wi], w[wj], sel[sh]) >> (32 - 8 * B);
+}
+
+// phase A of a tile: the lane's 16 samples -> windowed doubles, parked in the lane's column of the warp's value buffer.
+// Sixteen independent chains (LDS -> PRMT -> shift -> IMAD -> I2F -> DMUL): the conversion latency is paid here, at full
+// instruction-level parallelism, and not in front of every sample's FP64 batch.
+template <int B>
+__device__ __forceinline__ void l4_convert(const uint8_t* __restrict__ spcm, const uint8_t* __restrict__ swin, double* __restrict__ vcol,
+                                           const uint32_t (&sel)[4], int32_t ca, int32_t cb, uint32_t cs, uint32_t& mask)
+{
+    constexpr int NW = 4 * B;   // words of half a tile: 8 samples x 2 channels x B bytes
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t w[NW];
+#pragma unroll
+        for (int c = 0; c < B; c++) {
+            const uint4 a = *reinterpret_cast<const uint4*>(spcm + h * 16 * B + c * 16);
+            w[4 * c] = a.x; w[4 * c + 1] = a.y; w[4 * c + 2] = a.z; w[4 * c + 3] = a.w;
+        }
+        int32_t l[8], r[8];
+        l[0] = l4_extract<B, 0 * B, NW>(w, sel); r[0] = l4_extract<B, 1 * B, NW>(w, sel);
+        l[1] = l4_extract<B, 2 * B, NW>(w, sel); r[1] = l4_extract<B, 3 * B, NW>(w, sel);
+        l[2] = l4_extract<B, 4 * B, NW>(w, sel); r[2] = l4_extract<B, 5 * B, NW>(w, sel);
+        l[3] = l4_extract<B, 6 * B, NW>(w, sel); r[3] = l4_extract<B, 7 * B, NW>(w, sel);
+        l[4] = l4_extract<B, 8 * B, NW>(w, sel); r[4] = l4_extract<B, 9 * B, NW>(w, sel);
+        l[5] = l4_extract<B, 10 * B, NW>(w, sel); r[5] = l4_extract<B, 11 * B, NW>(w, sel);
+        l[6] = l4_extract<B, 12 * B, NW>(w, sel); r[6] = l4_extract<B, 13 * B, NW>(w, sel);
+        l[7] = l4_extract<B, 14 * B, NW>(w, sel); r[7] = l4_extract<B, 15 * B, NW>(w, sel);
+#pragma unroll
+        for (int i2 = 0; i2 < 4; i2++) {
+            const double2 wv2 = *reinterpret_cast<const double2*>(swin + h * 64 + i2 * 16);
+#pragma unroll
+            for (int ii = 0; ii < 2; ii++) {
+                const int i = i2 * 2 + ii;
+                const int32_t px = (l[i] * ca + r[i] * cb) >> cs;   // L | R | (L + R) >> 1 | L - R (:2721, :2734), wasted bits shifted out (:2891)
+                mask |= (uint32_t)px;
+                vcol[(h * 8 + i) * 32] = __dmul_rn((double)px, ii ? wv2.y : wv2.x);   // Window::apply (:1799)
+            }
+        }
+    }
+}
+
+// phase B: autocorrelate (:3491-3497).  Sample s adds win[s - lag] * v_s to every lag's sum: NL independent DMULs, then NL
+// DADDs -- nothing but FP64 work and one shared-memory load per sample.
+template <int NL, bool EDGE>
+__device__ __forceinline__ void l4_accumulate(const double* __restrict__ vcol, uint32_t idx0, uint32_t n, double (&acc)[NL], double (&win)[16])
+{
+    // software pipeline: the products of sample s + 1 are formed while the sums take in the products of sample s, so no DADD
+    // ever waits on a DMUL that has just been issued
+    double p[NL];
+    {
+        const double v = vcol[0];
+        win[0] = v;
+#pragma unroll
+        for (int lag = 0; lag < NL; lag++) p[lag] = __dmul_rn(win[(0 - lag) & 15], v);
+    }
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        double pn[NL];
+        if (s + 1 < 16) {
+            const double v = vcol[(s + 1) * 32];
+            win[(s + 1) & 15] = v;
+#pragma unroll
+            for (int lag = 0; lag < NL; lag++) pn[lag] = __dmul_rn(win[(s + 1 - lag) & 15], v);
+        }
+        if (!EDGE) {
+#pragma unroll
+            for (int lag = 0; lag < NL; lag++) acc[lag] = __dadd_rn(acc[lag], p[lag]);
+        } else {   // a lag only counts the samples that exist
+            const uint32_t idx = idx0 + s;
+#pragma unroll
+            for (int lag = 0; lag < NL; lag++)
+                if (idx < n && idx >= (uint32_t)lag) acc[lag] = __dadd_rn(acc[lag], p[lag]);
+        }
+        if (s + 1 < 16) {
+#pragma unroll
+            for (int lag = 0; lag < NL; lag++) p[lag] = pn[lag];
+        }
+    }
+}
+
+template <int NL, int B>
+__global__ void __launch_bounds__(32 * L4_WARPS, FLACB200_L4_MINB) k_lpc4(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
+                                                         const double* __restrict__ winpool, LpcRec* __restrict__ out, uint32_t nframes)
+{
+    constexpr int MM = NL - 1;   // largest order of this instantiation
+    __shared__ __align__(16) uint8_t l4_sm[L4_WARPS * L4_SLOTS * L4_SLOT_BYTES];
+    __shared__ double l4_vals[L4_WARPS][16][32];   // windowed samples of the tile at hand: [sample][lane]
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t M = cfg.max_lpc_order;
+    const uint32_t unit = blockIdx.x * L4_WARPS + wid;
+    const uint32_t f0 = unit * 8;
+    if (f0 >= nframes) return;
+    const uint32_t nfr = min(8u, nframes - f0);
+    const uint32_t fl = lane >> 2, k = lane & 3;   // the lane's frame and channel combination
+    const bool live = fl < nfr;
+    const FrameDesc d = descs[f0 + (live ? fl : 0u)];
+    const uint32_t n = (live && d.n > M) ? d.n : 0u;   // n <= M: InsufficientLpcSamples (:3300), nothing to analyse
+    const uint8_t* fp = pcm + d.pcm_off * (unsigned long long)(2 * B);
+    const uint8_t* wp = reinterpret_cast<const uint8_t*>(winpool + d.win_off);
+    if (live) out[(size_t)f0 * 4 + lane].ok = 0;
+    uint32_t nmax = n, nmin = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+        nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+    }
+    const uint32_t ntiles = (nmax + 15) / 16;
+    uint8_t* wsm = l4_sm + (size_t)wid * (L4_SLOTS * L4_SLOT_BYTES);
+    const uint32_t wsm_sa = (uint32_t)__cvta_generic_to_shared(wsm);
+    const bool big = cfg.pcm_kind == 1;
+    // PRMT selectors by the sample's byte offset within its word: the B bytes end up in the register's top bytes, in value order
+    uint32_t sel[4];
+#pragma unroll
+    for (int sh = 0; sh < 4; sh++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int dst = big ? 3 - b : 4 - B + b;   // big endian: the first byte is the most significant
+            v |= (uint32_t)(sh + b) << (4 * dst);
+        }
+        sel[sh] = v;
+    }
+    const int32_t ca = k == 1 ? 0 : 1, cb = k == 0 ? 0 : (k == 3 ? -1 : 1);
+    const uint32_t cs0 = k == 2 ? 1u : 0u;
+
+    // global -> slot: the four lanes of a frame copy its 2 B + 8 sixteen-byte chunks of the tile (PCM, then window values);
+    // bytes past the end of the block are zero-filled
+    constexpr uint32_t TB = 32 * B;   // PCM bytes of a tile
+    auto issue = [&](uint32_t tile, uint32_t slot) {
+        if (tile < ntiles) {
+            const uint32_t base = wsm_sa + slot * L4_SLOT_BYTES + fl * L4_STRIDE;
+#pragma unroll
+            for (int j = 0; j < (2 * B + 8 + 3) / 4; j++) {
+                const uint32_t c = k + 4 * j;
+                if (c < 2 * B) {
+                    const uint32_t off = tile * TB + c * 16, tot = n * 2 * B;
+                    const uint32_t bytes = off < tot ? min(16u, tot - off) : 0u;
+                    l3_cp16(base + c * 16, fp + (bytes ? off : 0u), bytes);
+                } else if (c < 2 * B + 8) {
+                    const uint32_t cc = c - 2 * B;
+                    const uint32_t off = tile * 128 + cc * 16, tot = n * 8;
+                    const uint32_t bytes = off < tot ? min(16u, tot - off) : 0u;
+                    l3_cp16(base + 8 * L4_STRIDE + cc * 16, wp + (bytes ? off : 0u), bytes);
+                }
+            }
+        }
+        l3_commit();
+    };
+
+    double acc[NL];
+    uint32_t mask = 0, wasted = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1 && !__any_sync(0xffffffffu, wasted != 0)) break;   // rare pass: wasted bits shifted out (:2878-2898)
+        const uint32_t cs = cs0 + wasted;
+        double win[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) win[i] = 0.0;
+#pragma unroll
+        for (int lag = 0; lag < NL; lag++) acc[lag] = -0.0;   // Iterator::sum::<f64>() folds from -0.0
+        uint32_t m2 = 0;
+        issue(0, 0);
+        issue(1, 1);
+        uint32_t slot = 0;
+        for (uint32_t t = 0; t < ntiles; t++) {
+            issue(t + 2, slot >= 1 ? slot - 1 : 2);   // (slot + 2) % 3
+            l3_wait<2>();
+            __syncwarp();
+            const uint8_t* spcm = wsm + slot * L4_SLOT_BYTES + fl * L4_STRIDE;
+            const uint8_t* swin = spcm + 8 * L4_STRIDE;
+            double* vcol = &l4_vals[wid][0][lane];
+            l4_convert<B>(spcm, swin, vcol, sel, ca, cb, cs, m2);
+            __syncwarp();   // (the staging slot may be refilled; the value column is the lane's own)
+            if (t == 0 || (t + 1) * 16 > nmin) l4_accumulate<NL, true>(vcol, t * 16, n, acc, win);
+            else l4_accumulate<NL, false>(vcol, t * 16, n, acc, win);
+            slot = slot == 2 ? 0 : slot + 1;
+        }
+        l3_wait<0>();
+        __syncwarp();
+        if (pass == 0) {
+            mask = m2;
+            wasted = (mask == 0 || (mask & 1u)) ? 0u : (uint32_t)__ffs((int)mask) - 1u;
+        }
+    }
+    // ---- Levinson-Durbin (:3536-3580) with the order estimate (:3656-3702) folded in: all lanes, everything in registers ----
+    const bool run = n != 0 && mask != 0;   // all-zero candidates become CONSTANT (:2883)
+    if (!run) return;
+    const uint32_t bps = cand_bps(cfg, k) - wasted;
+    const uint32_t precision = lpc_precision_for(n);
+    const double error_scale = __ddiv_rn(0.5, (double)n);
+    const double divisor = 2.0 * 0.693147180559945309417232121458176568;
+    double a[MM], best_a[MM];
+#pragma unroll
+    for (int j = 0; j < MM; j++) { a[j] = 0.0; best_a[j] = 0.0; }
+    int best = 0;
+    double best_bits = 0.0, err;
+    bool alive = true;   // take_while(err > 0)
+    {
+        const double kk = __ddiv_rn(acc[1], acc[0]);
+        a[0] = kk;
+        err = __dmul_rn(acc[0], __dsub_rn(1.0, __dmul_rn(kk, kk)));
+    }
+#pragma unroll
+    for (int i = 0; i < MM; i++) {   // here a[0..i] is the set of order i + 1 and err its error
+        if ((uint32_t)i < M) {
+            alive = alive && err > 0.0;
+            if (alive) {
+                const uint32_t o = i + 1;
+                const double bpr = __ddiv_rn(glibc_log(__dmul_rn(err, error_scale)), divisor);
+                const double bits = fma(bpr, (double)(n - o), (double)(o * (bps + precision)));
+                if (best == 0 || total_key(bits) < total_key(best_bits)) {   // first minimum under total_cmp
+                    best = (int)o;
+                    best_bits = bits;
+#pragma unroll
+                    for (int j = 0; j <= i; j++) best_a[j] = a[j];
+                }
+            }
+            if (i + 1 < MM && (uint32_t)(i + 1) < M) {   // the set of order i + 2
+                double s = -0.0;
+#pragma unroll
+                for (int j = 0; j <= i; j++) s = __dadd_rn(s, __dmul_rn(acc[i + 1 - j], a[j]));
+                const double q = __dsub_rn(acc[i + 2], s);
+                const double kk = __ddiv_rn(q, err);
+                double b[MM];
+#pragma unroll
+                for (int j = 0; j <= i; j++) b[j] = __dsub_rn(a[j], __dmul_rn(kk, a[i - j]));
+#pragma unroll
+                for (int j = 0; j <= i; j++) a[j] = b[j];
+                a[i + 1] = kk;
+                err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(kk, kk)));
+            }
+        }
+    }
+    if (best == 0) return;
+    // quantize (:3334-3401)
+    double l = fabs(best_a[0]);
+#pragma unroll
+    for (int j = 1; j < MM; j++) {
+        if (j < best) {
+            const double aj = fabs(best_a[j]);
+            if (total_key(aj) >= total_key(l)) l = aj;
+        }
+    }
+    if (!(l > 0.0)) return;
+    const int32_t max_coeff = (1 << (precision - 1)) - 1, min_coeff = -(1 << (precision - 1));
+    const int32_t lg = f64_as_i32_sat(floor(glibc_log2(l)));
+    long long sh = (long long)((int32_t)precision - 1) - (long long)lg - 1;   // :3360
+    if (sh > 15) sh = 15;
+    if (sh < -16) return;
+    LpcRec rec;
+    double error = 0.0;
+    const double scale = (double)(1 << (sh >= 0 ? sh : -sh));
+#pragma unroll
+    for (int j = 0; j < MAX_LPC; j++) {
+        int32_t q = 0;
+        if (j < MM && j < best) {
+            const double sum = sh >= 0 ? fma(best_a[j < MM ? j : 0], scale, error)                        // mul_add :3372
+                                       : __dadd_rn(__ddiv_rn(best_a[j < MM ? j : 0], scale), error);   // :3391
+            q = f64_as_i32_sat(round(sum));
+            q = q < min_coeff ? min_coeff : (q > max_coeff ? max_coeff : q);
+            error = __dsub_rn(sum, (double)q);
+        }
+        rec.q[j] = (int16_t)q;
+    }
+    rec.shift = (uint8_t)(sh >= 0 ? sh : 0);
+    rec.ok = 1;
+    rec.order = (uint8_t)best;
+    rec.precision = (uint8_t)precision;
+    rec.pad = 0;
+    out[(size_t)f0 * 4 + lane] = rec;
+}
+
+// stereo frames, 16- or 24-bit packed PCM on 16-byte boundaries, order <= 15
+bool lpc4_ok(const EncCfg& cfg, bool blocks_aligned16)
+{
+    return lpc3_ok(cfg, blocks_aligned16) && (cfg.bytes_per_sample == 2 || cfg.bytes_per_sample == 3);
+}
+
+cudaError_t launch_lpc4(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const double* winpool, LpcRec* lpcs, cudaStream_t st)
+{
+    const uint32_t units = (cfg.nframes + 7) / 8;
+    const uint32_t grid = (units + L4_WARPS - 1) / L4_WARPS;
+    const uint32_t M = cfg.max_lpc_order;
+#define FLACB200_L4(NLV, BV) (count_launch(), k_lpc4<NLV, BV><<<grid, 32 * L4_WARPS, 0, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes))
+    if (cfg.bytes_per_sample == 3) {
+        if (M <= 8) FLACB200_L4(9, 3);
+        else if (M <= 12) FLACB200_L4(13, 3);
+        else FLACB200_L4(16, 3);
+    } else {
+        if (M <= 8) FLACB200_L4(9, 2);
+        else if (M <= 12) FLACB200_L4(13, 2);
+        else FLACB200_L4(16, 2);
+    }
+#undef FLACB200_L4
+    return cudaGetLastError();
+}
+
 }   // namespace flacb200

@@ -32,6 +32,8 @@ bool pack3_ok(const EncCfg&);
 bool analyze3_ok(const EncCfg&);
 bool lpc3_ok(const EncCfg&, bool);
 cudaError_t launch_lpc3(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, uint32_t, cudaStream_t);
+bool lpc4_ok(const EncCfg&, bool);
+cudaError_t launch_lpc4(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, cudaStream_t);
 cudaError_t launch_analyze3(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, uint4*, cudaStream_t);
 cudaError_t launch_pack3(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, const uint4*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
@@ -89,6 +91,11 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+struct SegRec {
+    unsigned long long pcm_offset, n_pcm_frames, first_fnum, first_frame;   // first_frame: index of the segment's first block in the call
+    uint32_t win_full, win_tail;                                            // window pool offsets of a full block and of the last, shorter one
+};
+
 struct flacb200_engine {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -118,7 +125,7 @@ struct flacb200_engine {
                                 // kernels on C4 (45 vs 41 ms per step), so it is an option, not the default
     int sm_count = 148;
     std::vector<cudaEvent_t> lpc_ev;   // per group: LPC parameters ready, analysis done (the two LpcRec buffers alternate)
-    DevBuf pcm, planes, masks, lpcs, cands, frecs, descs, out, fbytes, totals, winpool, scratch, lut, lookback, find_slots, res16, dec[12];
+    DevBuf pcm, planes, masks, lpcs, lpcs_all, cands, frecs, descs, segs, out, fbytes, totals, winpool, scratch, lut, lookback, find_slots, res16, dec[12];
     std::map<uint32_t, uint32_t> win_off;   // block length -> offset in doubles
     std::vector<double> win_host;
     flacb200_options win_opt{};
@@ -135,6 +142,7 @@ struct flacb200_engine {
     void* host_stage = nullptr;
     size_t host_stage_cap = 0;
     std::vector<FrameDesc> descs_host;
+    std::vector<SegRec> segs_host;
 };
 
 static int cuda_err(cudaError_t e) { return e == cudaSuccess ? 0 : FLACB200_E_CUDA_BASE - (int)e; }
@@ -166,6 +174,32 @@ static int ensure(DevBuf& b, size_t bytes)
         int _r = ensure(buf, bytes);     \
         if (_r) return _r;               \
     } while (0)
+
+// ---- frame descriptors built on the device ---------------------------------------------------------------------------
+// With the PCM resident on the device nothing on the host needs the per-frame table: the host describes the segments
+// (one record each) and a thread per frame finds its segment by binary search over the segments' first frame indices.
+// (A 270 000-frame call spent more than a millisecond building and uploading 6.5 MB of descriptors before its first kernel.)
+
+__global__ void k_descs(const SegRec* __restrict__ segs, uint32_t nseg, uint32_t bs, FrameDesc* __restrict__ out, unsigned long long nframes)
+{
+    const unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    uint32_t lo = 0, hi = nseg - 1;   // the LAST segment whose first_frame <= f (empty segments share their successor's index)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (segs[mid].first_frame <= f) lo = mid;
+        else hi = mid - 1;
+    }
+    const SegRec sg = segs[lo];
+    const unsigned long long k = f - sg.first_frame, done = k * bs;
+    const unsigned long long left = sg.n_pcm_frames - done;
+    FrameDesc d;
+    d.pcm_off = sg.pcm_offset + done;
+    d.fnum = sg.first_fnum + k;
+    d.n = left < bs ? (uint32_t)left : bs;
+    d.win_off = d.n == bs ? sg.win_full : sg.win_tail;
+    out[f] = d;
+}
 
 extern "C" {
 
@@ -253,7 +287,7 @@ void flacb200_engine_destroy(flacb200_engine* e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* bufs[] = {&e->pcm, &e->planes, &e->masks, &e->lpcs, &e->cands, &e->frecs, &e->descs, &e->out, &e->fbytes, &e->totals, &e->winpool,
+    DevBuf* bufs[] = {&e->pcm, &e->planes, &e->masks, &e->lpcs, &e->lpcs_all, &e->cands, &e->frecs, &e->descs, &e->segs, &e->out, &e->fbytes, &e->totals, &e->winpool,
                       &e->scratch, &e->lut, &e->lookback, &e->find_slots, &e->res16};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -453,16 +487,45 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     }
 
     // ---- cut segments into blocks ----
-    std::vector<FrameDesc>& descs = e->descs_host;   // kept between calls: no reallocation on the steady-state path
-    descs.clear();
     const uint32_t bs = opt->block_size;
     const size_t sample_bytes = (size_t)cfg.bytes_per_sample;
+    const uint64_t pcm_frame_bytes = (uint64_t)cfg.channels * cfg.bytes_per_sample;
+    const bool dev_descs = pcm_location != FLACB200_HOST && n_segments <= 0x7FFFFFFFull;   // host PCM: the upload pipeline reads the table
+    std::vector<FrameDesc>& descs = e->descs_host;   // kept between calls: no reallocation on the steady-state path
+    std::vector<SegRec>& segrecs = e->segs_host;
+    descs.clear();
+    segrecs.clear();
     uint64_t max_index = 0, want = 0;
+    uint64_t misalign = 0;           // OR of every block's byte offset: k_lpc3 / k_lpc4 copy 16-byte chunks
+    uint32_t win_n = 0, win_o = 0;   // the window table is looked up once per distinct block length, not per frame
+    if (dev_descs) {
+        segrecs.reserve(n_segments);
+        for (size_t s = 0; s < n_segments; s++) {
+            const flacb200_segment& sg = segments[s];
+            const uint64_t nb = (sg.n_pcm_frames + bs - 1) / bs;
+            if (nb && sg.first_frame_number + (nb - 1) > 0xFFFFFFFFFull) return 38;   // ExcessiveFrameNumber
+            SegRec r;
+            r.pcm_offset = sg.pcm_offset; r.n_pcm_frames = sg.n_pcm_frames; r.first_fnum = sg.first_frame_number; r.first_frame = want;
+            r.win_full = r.win_tail = 0;
+            const uint32_t tail = (uint32_t)(sg.n_pcm_frames % bs);
+            if (opt->max_lpc_order) {
+                if (sg.n_pcm_frames >= bs) {
+                    if (win_n != bs) { win_o = window_offset(e, *opt, bs); win_n = bs; }
+                    r.win_full = win_o;
+                }
+                if (tail) {
+                    if (win_n != tail) { win_o = window_offset(e, *opt, tail); win_n = tail; }
+                    r.win_tail = win_o;
+                }
+            }
+            for (uint64_t k = 0; k < std::min<uint64_t>(nb, 16); k++) misalign |= (sg.pcm_offset + k * bs) * pcm_frame_bytes;   // (the low bits repeat every 16 blocks)
+            segrecs.push_back(r);
+            want += nb;
+            max_index = std::max<uint64_t>(max_index, sg.pcm_offset + sg.n_pcm_frames);
+        }
+    } else {
     for (size_t s = 0; s < n_segments; s++) want += (segments[s].n_pcm_frames + bs - 1) / bs;
     descs.reserve(want);
-    uint32_t win_n = 0, win_o = 0;   // the window table is looked up once per distinct block length, not per frame
-    uint64_t misalign = 0;           // OR of every block's byte offset: k_lpc3 copies 16-byte chunks
-    const uint64_t pcm_frame_bytes = (uint64_t)cfg.channels * cfg.bytes_per_sample;
     for (size_t s = 0; s < n_segments; s++) {
         const flacb200_segment& sg = segments[s];
         uint64_t done = 0, fn = sg.first_frame_number;
@@ -484,7 +547,8 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         }
         max_index = std::max<uint64_t>(max_index, sg.pcm_offset + sg.n_pcm_frames);
     }
-    const uint64_t nframes = descs.size();
+    }
+    const uint64_t nframes = dev_descs ? want : descs.size();
     if (n_frames_out) *n_frames_out = nframes;
     if (total_bytes_out) *total_bytes_out = 0;
     if (nframes == 0) return 0;
@@ -539,7 +603,15 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     }
     const uint8_t* d_pcm;
     // small uploads first: queued behind the bulk PCM copies they would hold the first launch group back
-    CK(cudaMemcpyAsync(e->descs.p, descs.data(), nframes * sizeof(FrameDesc), cudaMemcpyHostToDevice, st));
+    if (dev_descs) {
+        ENS(e->segs, segrecs.size() * sizeof(SegRec));
+        CK(cudaMemcpyAsync(e->segs.p, segrecs.data(), segrecs.size() * sizeof(SegRec), cudaMemcpyHostToDevice, st));
+        count_launch(), k_descs<<<(unsigned)((nframes + 255) / 256), 256, 0, st>>>((const SegRec*)e->segs.p, (uint32_t)segrecs.size(), bs,
+                                                                                (FrameDesc*)e->descs.p, nframes);
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(e->descs.p, descs.data(), nframes * sizeof(FrameDesc), cudaMemcpyHostToDevice, st));
+    }
     CK(cudaMemsetAsync(e->totals.p, 0, 64, st));
     if (e->profiling) cudaEventRecord(e->ev[20], st);
     const size_t ngroups = (size_t)((nframes + chunk - 1) / chunk);
@@ -608,6 +680,13 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     // small enough to be resident next to the CTAs of k_analyze3 / k_pack3 of group g, which leave the FP64 pipe idle); a
     // full-size grid on a second stream would only start when the first kernel's last CTA has been dispatched
     const bool overlap = staged_lpc && frame_analyze && frame_pack && !fused && e->lpc_overlap != 0 && ngroups > 1;
+    // k_lpc4 (a lane per candidate, eight frames per warp) where it applies; legacy bit 2048 keeps k_lpc3
+    const bool lane_lpc = staged_lpc && !overlap && !(legacy & 2048u) && lpc4_ok(cfg, true);
+    // ... over ALL frames of the call in one launch when the PCM is on the device already: at eight frames per warp a 32768-frame
+    // group is 1.7 waves of resident warps, and every group would end in its own half-empty wave
+    const bool lpc_upfront = lane_lpc && !pipe_in && ngroups > 1 && !(legacy & 4096u) && nframes <= 0xFFFFFFFFull &&
+                             (size_t)nframes * cfg.nslots * sizeof(LpcRec) <= ((size_t)1 << 30);
+    if (lpc_upfront) ENS(e->lpcs_all, (size_t)nframes * cfg.nslots * sizeof(LpcRec));
     LpcRec* lpc_buf[2] = {(LpcRec*)e->lpcs.p, (LpcRec*)e->lpcs.p + ncand_chunk};
     if (overlap)
         while (e->lpc_ev.size() < 2 * ngroups) {
@@ -621,10 +700,18 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         return c;
     };
     cudaEventRecord(e->ev[22], st);
+    const size_t ev_upfront = 6 * (size_t)ngroups + 8;
+    if (lpc_upfront) {
+        EncCfg call = cfg;
+        call.nframes = (uint32_t)nframes;
+        time_mark(e, ev_upfront);
+        CK(launch_lpc4(call, (const FrameDesc*)e->descs.p, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs_all.p, st));
+        time_mark(e, ev_upfront + 1);
+    }
     for (uint64_t base = 0; base < nframes; base += chunk) {
         const EncCfg c = group_cfg(base);
         const FrameDesc* dd = (const FrameDesc*)e->descs.p + base;
-        LpcRec* lp = overlap ? lpc_buf[nchunks & 1] : lpc_buf[0];
+        LpcRec* lp = lpc_upfront ? (LpcRec*)e->lpcs_all.p + base * cfg.nslots : (overlap ? lpc_buf[nchunks & 1] : lpc_buf[0]);
         if (pipe_in) CK(cudaStreamWaitEvent(st, e->pipe_ev[2 * nchunks], 0));
         CK(cudaMemsetAsync(e->masks.p, 0, masks_bytes, st));
         const size_t eb = nchunks * 6;
@@ -634,7 +721,9 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         if (overlap) {
             if (nchunks == 0) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
             else CK(cudaStreamWaitEvent(st, e->lpc_ev[2 * nchunks], 0));   // launched beside the previous group
-        } else if (staged_lpc) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
+        } else if (lpc_upfront) {
+        } else if (lane_lpc) CK(launch_lpc4(c, dd, d_pcm, (const double*)e->winpool.p, lp, st));
+        else if (staged_lpc) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
         else if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, lp, st));
         else launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, lp, st);
         time_mark(e, eb + 2);
@@ -740,6 +829,12 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
                 e->tm.kernel_ms[k] += ms;
                 e->tm.kernel_launches[k] += per_chunk[k];
             }
+        if (lpc_upfront) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e->evpool[ev_upfront], e->evpool[ev_upfront + 1]);
+            e->tm.kernel_ms[1] += ms;
+            e->tm.kernel_launches[1] += 1 - (uint32_t)nchunks;   // one launch instead of one per group
+        }
         cudaEventElapsedTime(&e->tm.h2d_ms, e->ev[20], e->ev[21]);
         if (out) cudaEventElapsedTime(&e->tm.d2h_ms, e->ev[24], e->ev[25]);
     }
