@@ -37,6 +37,13 @@ constexpr int A3_WPC = FLACB200_A3_WPC;   // warps per candidate
 #define FLACB200_A3_FIR 1
 #endif
 constexpr int A3_FIR_OUT = FLACB200_A3_FIR == 2 ? 16 : 8;
+#ifndef FLACB200_A3_PF
+#define FLACB200_A3_PF 1
+#endif
+#ifndef FLACB200_A3_PF_DIST
+#define FLACB200_A3_PF_DIST 296
+#endif
+constexpr uint32_t A3_PF_DIST = FLACB200_A3_PF_DIST;   // frames ahead: the CTAs resident at once (2 x 148 SMs)
 // int32 -> double without the conversion unit: 2^52 + 2^31 + v is exact bit-pasting, the subtraction is one DADD
 #ifndef FLACB200_A3_I2F
 #define FLACB200_A3_I2F 0
@@ -552,6 +559,9 @@ __host__ __device__ constexpr size_t a3_smem_bytes()
 }
 
 // STEREO: grid = frames, block = 256 (4 candidates x 2 warps).  Otherwise: grid = frames * ceil(channels / 2), block = 128.
+// (a 112-register build of this kernel -- room for a persistent two-warp k_lpc4 CTA per SM beside two of its CTAs, FP64 work
+// under the integer work -- spills 128 bytes per thread and runs 27 % slower by itself, 24.5 -> 31.0 ms per step, and the
+// two LPC warps per SM need 5 ms per launch group, longer than the integer kernels they hide behind: measured and dropped)
 template <int HB, bool STEREO>
 __global__ void __launch_bounds__(32 * A3_WPC * (STEREO ? 4 : 2), STEREO ? 2 : 4)
     k_analyze3(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm, const LpcRec* __restrict__ lpcs,
@@ -572,6 +582,13 @@ __global__ void __launch_bounds__(32 * A3_WPC * (STEREO ? 4 : 2), STEREO ? 2 : 4
     const bool fast_modes = STEREO && (cfg.mode == MODE_FAST_MID_SIDE || cfg.mode == MODE_FAST_SIDE);
     if (tid < 4) abs4[tid] = 0;
     if (fast_modes) __syncthreads();
+#if FLACB200_A3_PF
+    // The frame that will run in this CTA's place (two CTAs per SM, frames start in index order) is asked into L2 now: its CTA
+    // otherwise begins with all eight warps waiting a DRAM round trip for the 24 KB of PCM (10 % of this kernel's stall samples).
+    FrameDesc dnext;
+    const bool pf = STEREO && f + A3_PF_DIST < cfg.nframes && tid < 192;
+    if (pf) dnext = descs[f + A3_PF_DIST];
+#endif
     // ---- unpack the two source channels once (Frame::fill_from_buf, src/audio.rs:149-187) ----
     {
         unsigned long long sl = 0, sr = 0, smid = 0, sside = 0;
@@ -608,6 +625,13 @@ __global__ void __launch_bounds__(32 * A3_WPC * (STEREO ? 4 : 2), STEREO ? 2 : 4
             if (lane == 0) { atomicAdd(&abs4[0], sl); atomicAdd(&abs4[1], sr); atomicAdd(&abs4[2], smid); atomicAdd(&abs4[3], sside); }
         }
     }
+#if FLACB200_A3_PF
+    if (pf && cfg.pcm_kind <= 1) {
+        const unsigned long long fb = (unsigned long long)cfg.channels * cfg.bytes_per_sample;
+        const unsigned long long off = (unsigned long long)tid * 128u;
+        if (off < dnext.n * fb) asm volatile("prefetch.global.L2 [%0];" ::"l"(pcm + dnext.pcm_off * fb + off));
+    }
+#endif
     __syncthreads();
     const uint32_t cand = wid / A3_WPC, wsub = wid % A3_WPC;
     const uint32_t slot = STEREO ? cand : ch0 + cand;

@@ -364,7 +364,6 @@ cudaError_t launch_lpc3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t
 //     far is kept as the recursion proceeds (subframe_bits_by_order only needs the error of the order just finished).
 // Arithmetic, operation for operation, is k_lpc3's (and the reference's :3478-3702).
 // =====================================================================================================================
-constexpr int L4_WARPS = 4;
 #ifndef FLACB200_L4_MINB
 #define FLACB200_L4_MINB 4
 #endif
@@ -459,18 +458,21 @@ __device__ __forceinline__ void l4_accumulate(const double* __restrict__ vcol, u
     }
 }
 
-template <int NL, int B>
-__global__ void __launch_bounds__(32 * L4_WARPS, FLACB200_L4_MINB) k_lpc4(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
+// WARPS = 4: one CTA per 32 frames, four CTAs per SM.  WARPS = 2: the PERSISTENT form -- a grid of one small CTA per SM (8192
+// registers, 23 KB) that strides over the units and fits beside two CTAs of k_analyze3 built with a 112-register cap: the
+// FP64 pipe, which the integer kernels leave idle, works on the next launch group meanwhile (flacb200_encode, option lpc_overlap)
+template <int NL, int B, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? FLACB200_L4_MINB : 1) k_lpc4(EncCfg cfg, const FrameDesc* __restrict__ descs, const uint8_t* __restrict__ pcm,
                                                          const double* __restrict__ winpool, LpcRec* __restrict__ out, uint32_t nframes)
 {
     constexpr int MM = NL - 1;   // largest order of this instantiation
-    __shared__ __align__(16) uint8_t l4_sm[L4_WARPS * L4_SLOTS * L4_SLOT_BYTES];
-    __shared__ double l4_vals[L4_WARPS][16][32];   // windowed samples of the tile at hand: [sample][lane]
+    __shared__ __align__(16) uint8_t l4_sm[WARPS * L4_SLOTS * L4_SLOT_BYTES];
+    __shared__ double l4_vals[WARPS][16][32];   // windowed samples of the tile at hand: [sample][lane]
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t M = cfg.max_lpc_order;
-    const uint32_t unit = blockIdx.x * L4_WARPS + wid;
+    for (uint32_t unit = blockIdx.x * WARPS + wid; (unsigned long long)unit * 8 < nframes; unit += gridDim.x * WARPS) {
+    __syncwarp();   // (persistent form: every lane has left the previous unit's staging slots)
     const uint32_t f0 = unit * 8;
-    if (f0 >= nframes) return;
     const uint32_t nfr = min(8u, nframes - f0);
     const uint32_t fl = lane >> 2, k = lane & 3;   // the lane's frame and channel combination
     const bool live = fl < nfr;
@@ -564,7 +566,7 @@ __global__ void __launch_bounds__(32 * L4_WARPS, FLACB200_L4_MINB) k_lpc4(EncCfg
     }
     // ---- Levinson-Durbin (:3536-3580) with the order estimate (:3656-3702) folded in: all lanes, everything in registers ----
     const bool run = n != 0 && mask != 0;   // all-zero candidates become CONSTANT (:2883)
-    if (!run) return;
+    if (!run) continue;
     const uint32_t bps = cand_bps(cfg, k) - wasted;
     const uint32_t precision = lpc_precision_for(n);
     const double error_scale = __ddiv_rn(0.5, (double)n);
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(32 * L4_WARPS, FLACB200_L4_MINB) k_lpc4(EncCfg
             }
         }
     }
-    if (best == 0) return;
+    if (best == 0) continue;
     // quantize (:3334-3401)
     double l = fabs(best_a[0]);
 #pragma unroll
@@ -621,12 +623,12 @@ __global__ void __launch_bounds__(32 * L4_WARPS, FLACB200_L4_MINB) k_lpc4(EncCfg
             if (total_key(aj) >= total_key(l)) l = aj;
         }
     }
-    if (!(l > 0.0)) return;
+    if (!(l > 0.0)) continue;
     const int32_t max_coeff = (1 << (precision - 1)) - 1, min_coeff = -(1 << (precision - 1));
     const int32_t lg = f64_as_i32_sat(floor(glibc_log2(l)));
     long long sh = (long long)((int32_t)precision - 1) - (long long)lg - 1;   // :3360
     if (sh > 15) sh = 15;
-    if (sh < -16) return;
+    if (sh < -16) continue;
     LpcRec rec;
     double error = 0.0;
     const double scale = (double)(1 << (sh >= 0 ? sh : -sh));
@@ -648,6 +650,7 @@ __global__ void __launch_bounds__(32 * L4_WARPS, FLACB200_L4_MINB) k_lpc4(EncCfg
     rec.precision = (uint8_t)precision;
     rec.pad = 0;
     out[(size_t)f0 * 4 + lane] = rec;
+    }
 }
 
 // stereo frames, 16- or 24-bit packed PCM on 16-byte boundaries, order <= 15
@@ -656,12 +659,17 @@ bool lpc4_ok(const EncCfg& cfg, bool blocks_aligned16)
     return lpc3_ok(cfg, blocks_aligned16) && (cfg.bytes_per_sample == 2 || cfg.bytes_per_sample == 3);
 }
 
-cudaError_t launch_lpc4(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const double* winpool, LpcRec* lpcs, cudaStream_t st)
+// max_ctas: 0 = a warp per eight frames, four warps per CTA; else the persistent two-warp form with at most that many CTAs
+cudaError_t launch_lpc4(const EncCfg& cfg, const FrameDesc* descs, const uint8_t* pcm, const double* winpool, LpcRec* lpcs, uint32_t max_ctas,
+                        cudaStream_t st)
 {
     const uint32_t units = (cfg.nframes + 7) / 8;
-    const uint32_t grid = (units + L4_WARPS - 1) / L4_WARPS;
     const uint32_t M = cfg.max_lpc_order;
-#define FLACB200_L4(NLV, BV) (count_launch(), k_lpc4<NLV, BV><<<grid, 32 * L4_WARPS, 0, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes))
+#define FLACB200_L4(NLV, BV)                                                                                                                    \
+    do {                                                                                                                                        \
+        if (max_ctas) count_launch(), k_lpc4<NLV, BV, 2><<<min(max_ctas, (units + 1) / 2), 64, 0, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes); \
+        else count_launch(), k_lpc4<NLV, BV, 4><<<(units + 3) / 4, 128, 0, st>>>(cfg, descs, pcm, winpool, lpcs, cfg.nframes);                  \
+    } while (0)
     if (cfg.bytes_per_sample == 3) {
         if (M <= 8) FLACB200_L4(9, 3);
         else if (M <= 12) FLACB200_L4(13, 3);

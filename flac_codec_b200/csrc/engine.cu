@@ -33,7 +33,7 @@ bool analyze3_ok(const EncCfg&);
 bool lpc3_ok(const EncCfg&, bool);
 cudaError_t launch_lpc3(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, uint32_t, cudaStream_t);
 bool lpc4_ok(const EncCfg&, bool);
-cudaError_t launch_lpc4(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, cudaStream_t);
+cudaError_t launch_lpc4(const EncCfg&, const FrameDesc*, const uint8_t*, const double*, LpcRec*, uint32_t, cudaStream_t);
 cudaError_t launch_analyze3(const EncCfg&, const FrameDesc*, const uint8_t*, const LpcRec*, CandRec*, unsigned long long*, uint4*, cudaStream_t);
 cudaError_t launch_pack3(const EncCfg&, const FrameDesc*, const uint8_t*, const CandRec*, const FrameRec*, uint8_t*, const uint4*, cudaStream_t);
 cudaError_t launch_pack_crc(const EncCfg&, const FrameDesc*, const int32_t*, const CandRec*, const FrameRec*, uint8_t*, cudaStream_t);
@@ -101,6 +101,7 @@ struct flacb200_engine {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host<->device copies overlapped with the kernels of other launch groups
     cudaStream_t aux = nullptr;                            // decode: CRC-16 and the frame walk beside the predictor restoration
+    cudaStream_t lpc_stream = nullptr;                     // encode, option lpc_overlap: the persistent k_lpc4 grid of the next launch group (high priority)
     // small host<->device messages of the decode path (segment table up; candidate count, walk verdict, walk state down) go
     // through pinned mapped memory and a tiny copy kernel, not through the copy engines: behind a 350 MB upload or download
     // of another batch a 4-byte cudaMemcpyAsync waits for milliseconds
@@ -253,6 +254,11 @@ int flacb200_engine_create(int device, flacb200_engine** out)
     cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking);
+    {   // the persistent LPC grid of the overlap mode: its one small CTA per SM should be placed as soon as an SM has room
+        int lo_p = 0, hi_p = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        cudaStreamCreateWithPriority(&e->lpc_stream, cudaStreamNonBlocking, hi_p);
+    }
     for (auto& ev : e->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char* v = getenv("FLACB200_LPC_OVERLAP")) e->lpc_overlap = (uint32_t)strtoul(v, nullptr, 0);
@@ -303,6 +309,7 @@ void flacb200_engine_destroy(flacb200_engine* e)
     for (auto& ev : e->batch_ev) cudaEventDestroy(ev);
     for (auto& ev : e->lpc_ev) cudaEventDestroy(ev);
     cudaStreamDestroy(e->aux);
+    cudaStreamDestroy(e->lpc_stream);
     cudaStreamDestroy(e->copy_in);
     cudaStreamDestroy(e->copy_out);
     cudaStreamDestroy(e->own_stream);
@@ -681,15 +688,15 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
     // full-size grid on a second stream would only start when the first kernel's last CTA has been dispatched
     const bool overlap = staged_lpc && frame_analyze && frame_pack && !fused && e->lpc_overlap != 0 && ngroups > 1;
     // k_lpc4 (a lane per candidate, eight frames per warp) where it applies; legacy bit 2048 keeps k_lpc3
-    const bool lane_lpc = staged_lpc && !overlap && !(legacy & 2048u) && lpc4_ok(cfg, true);
+    const bool lane_lpc = staged_lpc && !(legacy & 2048u) && lpc4_ok(cfg, true);
     // ... over ALL frames of the call in one launch when the PCM is on the device already: at eight frames per warp a 32768-frame
     // group is 1.7 waves of resident warps, and every group would end in its own half-empty wave
-    const bool lpc_upfront = lane_lpc && !pipe_in && ngroups > 1 && !(legacy & 4096u) && nframes <= 0xFFFFFFFFull &&
+    const bool lpc_upfront = lane_lpc && !overlap && !pipe_in && ngroups > 1 && !(legacy & 4096u) && nframes <= 0xFFFFFFFFull &&
                              (size_t)nframes * cfg.nslots * sizeof(LpcRec) <= ((size_t)1 << 30);
     if (lpc_upfront) ENS(e->lpcs_all, (size_t)nframes * cfg.nslots * sizeof(LpcRec));
     LpcRec* lpc_buf[2] = {(LpcRec*)e->lpcs.p, (LpcRec*)e->lpcs.p + ncand_chunk};
     if (overlap)
-        while (e->lpc_ev.size() < 2 * ngroups) {
+        while (e->lpc_ev.size() < 2 * ngroups + 1) {
             cudaEvent_t ev;
             CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             e->lpc_ev.push_back(ev);
@@ -705,7 +712,7 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         EncCfg call = cfg;
         call.nframes = (uint32_t)nframes;
         time_mark(e, ev_upfront);
-        CK(launch_lpc4(call, (const FrameDesc*)e->descs.p, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs_all.p, st));
+        CK(launch_lpc4(call, (const FrameDesc*)e->descs.p, d_pcm, (const double*)e->winpool.p, (LpcRec*)e->lpcs_all.p, 0, st));
         time_mark(e, ev_upfront + 1);
     }
     for (uint64_t base = 0; base < nframes; base += chunk) {
@@ -719,14 +726,16 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
         if (need_planes) launch_planes(c, dd, d_pcm, (int32_t*)e->planes.p, d_ormask, d_abssum, st);
         time_mark(e, eb + 1);
         if (overlap) {
-            if (nchunks == 0) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
+            if (nchunks == 0) CK(lane_lpc ? launch_lpc4(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st)
+                                          : launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
             else CK(cudaStreamWaitEvent(st, e->lpc_ev[2 * nchunks], 0));   // launched beside the previous group
         } else if (lpc_upfront) {
-        } else if (lane_lpc) CK(launch_lpc4(c, dd, d_pcm, (const double*)e->winpool.p, lp, st));
+        } else if (lane_lpc) CK(launch_lpc4(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
         else if (staged_lpc) CK(launch_lpc3(c, dd, d_pcm, (const double*)e->winpool.p, lp, 0, st));
         else if (fast_lpc) CK(launch_lpc2(c, dd, d_pcm, (const double*)e->winpool.p, lp, st));
         else launch_lpc(c, dd, (const int32_t*)e->planes.p, d_ormask, d_abssum, (const double*)e->winpool.p, lp, st);
         time_mark(e, eb + 2);
+        if (overlap && nchunks == 0) CK(cudaEventRecord(e->lpc_ev[2 * ngroups], st));
         if (fused) {
             // the running byte total alternates between two words of `totals`: a late look-back of this group must still find
             // the total the group started from
@@ -746,13 +755,17 @@ extern "C" int flacb200_encode(flacb200_engine* e, const flacb200_options* opt, 
             CK(cudaEventRecord(e->lpc_ev[2 * nchunks + 1], st));   // this group's LpcRec buffer may be reused by group g + 2
             const uint64_t nb = base + chunk;
             if (nb < nframes) {
-                cudaStream_t sb = e->aux;
+                cudaStream_t sb = e->lpc_stream;
                 if (nchunks >= 1) CK(cudaStreamWaitEvent(sb, e->lpc_ev[2 * (nchunks - 1) + 1], 0));   // buffer (g + 1) & 1 was read by group g - 1
-                else CK(cudaStreamWaitEvent(sb, e->lpc_ev[1], 0));   // (orders stream B behind this call's uploads on the main stream)
+                else CK(cudaStreamWaitEvent(sb, e->lpc_ev[2 * ngroups], 0));   // (orders stream B behind this call's uploads and the first group's own LPC launch on the main stream)
                 if (pipe_in) CK(cudaStreamWaitEvent(sb, e->pipe_ev[2 * (nchunks + 1)], 0));
                 const EncCfg cn = group_cfg(nb);
-                CK(launch_lpc3(cn, (const FrameDesc*)e->descs.p + nb, d_pcm, (const double*)e->winpool.p, lpc_buf[(nchunks + 1) & 1],
-                               e->lpc_overlap * (uint32_t)e->sm_count, sb));
+                if (lane_lpc)
+                    CK(launch_lpc4(cn, (const FrameDesc*)e->descs.p + nb, d_pcm, (const double*)e->winpool.p, lpc_buf[(nchunks + 1) & 1],
+                                   e->lpc_overlap * (uint32_t)e->sm_count, sb));
+                else
+                    CK(launch_lpc3(cn, (const FrameDesc*)e->descs.p + nb, d_pcm, (const double*)e->winpool.p, lpc_buf[(nchunks + 1) & 1],
+                                   e->lpc_overlap * (uint32_t)e->sm_count, sb));
                 CK(cudaEventRecord(e->lpc_ev[2 * (nchunks + 1)], sb));
             }
         }
