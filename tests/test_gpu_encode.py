@@ -229,6 +229,46 @@ def test_multi_segment_batch_and_device_buffers(eng, fo):
     assert data.tobytes() == ref and sizes2.tolist() == sizes.tolist()
 
 
+@pytest.mark.parametrize("aligned", [True, False])
+def test_device_pcm_ragged_segments_match_host_pcm(eng, fo, aligned):
+    """Device-resident PCM: the frame table is built on the device (k_descs) and the LPC analysis of the whole call is one
+    launch (k_lpc4).  Ragged segments -- shorter than a block, a tail block, empty, out of order in the buffer, frame
+    numbers that do not start at 0 -- must give the bytes of the host-PCM call (host-built table, per-group launches)
+    and of the oracle, for one launch group and for many."""
+    from flac_codec_b200 import Options, _abi
+
+    rate, bps, ch = 44100, 16, 2
+    bs = Options.best().c.block_size
+    # aligned: every block starts on a 16-byte boundary (k_lpc4's cp.async staging); otherwise the unstaged LPC kernel runs
+    lens = [3 * bs + 16, 4, bs, 0, 2 * bs, bs - 4, 16, 7 * bs + 4000] if aligned else [3 * bs + 17, 5, bs, 0, 2 * bs, bs - 1, 16, 7 * bs + 4000]
+    total = sum(lens) + 64
+    x = synth_pcm(11, ch, total, rate, bps)
+    raw = np.frombuffer(fo.samples_to_bytes(x.reshape(-1), 2), dtype=np.uint8).copy()
+    offs, pos = [], 32
+    for n in lens:
+        offs.append(pos)
+        pos += n
+    order = [4, 0, 7, 3, 1, 6, 2, 5]                 # segments in an order that is not the buffer's
+    firsts = [0, 5, 1000, 7, 2 ** 31 - 2, 0, 3, 9]   # first frame number of each
+    segs = [(offs[i], lens[i], firsts[i]) for i in order]
+    ref = b""
+    for i in order:
+        if lens[i]:
+            r, _ = fo.encode_frames_only(fo.options("best"), rate, bps, ch, x[offs[i]:offs[i] + lens[i]].reshape(-1), first_frame_number=firsts[i])
+            ref += r
+    d_pcm = eng.device_alloc(raw.nbytes)
+    eng.memcpy(d_pcm, raw, raw.nbytes, 1)
+    for chunk in (0, 3):
+        eng.set_chunk_frames(chunk)
+        dev, sizes_d, total_d = eng.encode(Options.best(), rate, bps, ch, d_pcm, raw.nbytes, _abi.PCM_BYTES_LE, segs, pcm_location=_abi.DEVICE)
+        host, sizes_h, total_h = eng.encode(Options.best(), rate, bps, ch, raw, raw.nbytes, _abi.PCM_BYTES_LE, segs)
+        eng.set_chunk_frames(0)
+        assert dev.tobytes() == ref, f"device PCM, chunk {chunk}"
+        assert host.tobytes() == ref, f"host PCM, chunk {chunk}"
+        assert sizes_d.tolist() == sizes_h.tolist() and total_d == total_h == len(ref)
+    eng.device_free(d_pcm)
+
+
 def test_subset_stream_writer_semantics(eng, fo):
     """FlacStreamWriter::write (src/encode.rs:1094): subset header rules and errors."""
     from flac_codec_b200 import Options, _abi

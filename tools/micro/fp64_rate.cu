@@ -16,7 +16,20 @@ __global__ void __launch_bounds__(128) probe(double* out, int iters, double seed
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            if (MODE == 5) {   // DMUL only
+            if (MODE == 7) {   // DADD with two fresh register operands (no .reuse possible)
+#pragma unroll
+                for (int i = 0; i < 13; i++) { acc[i] = __dadd_rn(acc[i], win[i]); win[i] = __dadd_rn(win[i], acc[(i + 5) % 13]); }
+            } else if (MODE == 8) {   // k_lpc4's pair with the products formed a step ahead: DMUL(w, v.reuse) / DADD(acc, p) on independent data
+                v = __longlong_as_double(0x3ff0000000000000ll + (long long)(u + 1));
+                double p[13];
+#pragma unroll
+                for (int i = 0; i < 13; i++) p[i] = __dmul_rn(win[i], v);
+#pragma unroll
+                for (int i = 0; i < 13; i++) acc[i] = __dadd_rn(acc[i], p[i]);
+#pragma unroll
+                for (int i = 0; i < 12; i++) win[i] = win[i + 1];
+                win[12] = v;
+            } else if (MODE == 5) {   // DMUL only
                 v = __longlong_as_double(0x3ff0000000000000ll + (long long)(u + 1));
 #pragma unroll
                 for (int i = 0; i < 13; i++) { acc[i] = __dmul_rn(acc[i], v); win[i] = __dmul_rn(win[i], v); }
@@ -85,6 +98,8 @@ int main()
         run<3>("13 DMUL + 13 DADD + LDS.64", c, p.multiProcessorCount, ghz, 26);
         run<4>("13 DFMA(a,b,-0) + 13 DADD", c, p.multiProcessorCount, ghz, 26);
         run<5>("26 DMUL", c, p.multiProcessorCount, ghz, 26);
+        run<7>("26 DADD two fresh operands", c, p.multiProcessorCount, ghz, 26);
+        run<8>("13 DMUL(w,v) + 13 DADD(acc,p)", c, p.multiProcessorCount, ghz, 26);
         run<6>("13 DMUL, 13 DADD independent", c, p.multiProcessorCount, ghz, 26);
     }
     return 0;
