@@ -347,7 +347,7 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel: algorithmic bytes of one launch / its average duration ----
     # the C4 shape runs the CTA-per-frame kernels (encode_lpc.cu, encode_analyze.cu, encode_frame.cu); slot 0 (k_planes) is
     # only used by the generic path
-    names = ["k_planes", "k_lpc3", "k_analyze3", "k_decide+k_scan", "k_pack3"]
+    names = ["k_planes", "k_lpc4", "k_analyze3", "k_decide+k_scan", "k_pack3"]
     top = int(np.argmax(kernel_ms[:5]))
     peaks = {}
     try:

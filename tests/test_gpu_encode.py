@@ -269,6 +269,24 @@ def test_device_pcm_ragged_segments_match_host_pcm(eng, fo, aligned):
     eng.device_free(d_pcm)
 
 
+def test_lpc_overlap_option_same_bytes(eng, fo):
+    """Option lpc_overlap: the LPC analysis of launch group g + 1 as a persistent grid (k_lpc4's two-warp form, or k_lpc3)
+    on a second stream beside the integer kernels of group g -- off by default, byte-identical."""
+    from flac_codec_b200 import Options
+
+    x = synth_pcm(21, 2, 4096 * 37 + 500, 48000, 24)
+    for legacy in (0, 2048):
+        eng.set_option("legacy", legacy)
+        eng.set_option("lpc_overlap", 1)
+        eng.set_chunk_frames(5)
+        try:
+            check(eng, fo, Options.best(), 48000, 24, 2, x, f"lpc_overlap legacy={legacy}")
+        finally:
+            eng.set_chunk_frames(0)
+            eng.set_option("lpc_overlap", 0)
+            eng.set_option("legacy", 0)
+
+
 def test_subset_stream_writer_semantics(eng, fo):
     """FlacStreamWriter::write (src/encode.rs:1094): subset header rules and errors."""
     from flac_codec_b200 import Options, _abi
@@ -317,8 +335,9 @@ def test_generic_kernels_give_the_same_bytes(eng, fo):
         ("8b stereo bs 33", Options.best().block_size(33), 44100, 8, 2, synth_pcm(8, 2, 3000, 44100, 8)),
     ]
     # 1/2/4: generic analyze / lpc / pack; 8: k_pack2 instead of k_pack3; 16: k_analyze instead of k_analyze3;
-    # 32: k_lpc2 instead of k_lpc3; 56: all second-generation register-tiled kernels; 63: everything generic
-    for mask in ("7", "1", "2", "4", "8", "16", "32", "56", "63"):
+    # 32: k_lpc2 instead of k_lpc3 / k_lpc4; 56: all second-generation register-tiled kernels; 63: everything generic;
+    # 2048: k_lpc3 (four lanes per candidate) instead of k_lpc4 (a lane per candidate); 4096: k_lpc4 per launch group
+    for mask in ("7", "1", "2", "4", "8", "16", "32", "56", "63", "2048", "4096"):
         eng.set_option("legacy", int(mask))
         for label, opt, rate, bps, ch, x in cases:
             check(eng, fo, opt, rate, bps, ch, x, f"legacy={mask} {label}")
