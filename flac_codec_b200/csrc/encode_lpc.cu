@@ -380,41 +380,43 @@ __device__ __forceinline__ int32_t l4_extract(const uint32_t (&w)[NW], const uin
     return (int32_t)__byte_perm(w[wi], w[wj], sel[sh]) >> (32 - 8 * B);
 }
 
-// phase A of a tile: the lane's 16 samples -> windowed doubles, parked in the lane's column of the warp's value buffer.
-// Sixteen independent chains (LDS -> PRMT -> shift -> IMAD -> I2F -> DMUL): the conversion latency is paid here, at full
-// instruction-level parallelism, and not in front of every sample's FP64 batch.
-template <int B>
-__device__ __forceinline__ void l4_convert(const uint8_t* __restrict__ spcm, const uint8_t* __restrict__ swin, double* __restrict__ vcol,
-                                           const uint32_t (&sel)[4], int32_t ca, int32_t cb, uint32_t cs, uint32_t& mask)
+// phase A of a tile, the warp together: lane (q = lane / 8, f = lane % 8) takes samples 4 q .. 4 q + 3 of frame f -- it pulls their
+// 8 B bytes with 64/128-bit loads, extracts left and right ONCE (PRMT + shift each, static positions), forms all four channel
+// combinations, converts, multiplies by the window value and parks the 16 doubles in the columns of the frame's four candidates
+// (value buffer [sample][8 k + f], rows of 34 doubles: the stores of a half-warp fall on 16 distinct bank pairs).
+// SHIFT: the rare second pass, every candidate's wasted bits shifted out (:2891); the first pass gathers the OR masks instead.
+constexpr int L4_VROW = 34;
+template <int B, bool SHIFT>
+__device__ __forceinline__ void l4_convert(const uint8_t* __restrict__ spcm, const uint8_t* __restrict__ swin, double* __restrict__ vout,
+                                           const uint32_t (&sel)[4], const uint32_t (&wk)[4], uint32_t (&mk)[4])
 {
-    constexpr int NW = 4 * B;   // words of half a tile: 8 samples x 2 channels x B bytes
+    constexpr int NW = 2 * B;   // words of four stereo samples
+    uint32_t w[NW];
+    if (B == 2) {
+        const uint4 a = *reinterpret_cast<const uint4*>(spcm);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    } else {
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        uint32_t w[NW];
-#pragma unroll
-        for (int c = 0; c < B; c++) {
-            const uint4 a = *reinterpret_cast<const uint4*>(spcm + h * 16 * B + c * 16);
-            w[4 * c] = a.x; w[4 * c + 1] = a.y; w[4 * c + 2] = a.z; w[4 * c + 3] = a.w;
+        for (int c = 0; c < NW / 2; c++) {
+            const uint2 a = *reinterpret_cast<const uint2*>(spcm + 8 * c);
+            w[2 * c] = a.x; w[2 * c + 1] = a.y;
         }
-        int32_t l[8], r[8];
-        l[0] = l4_extract<B, 0 * B, NW>(w, sel); r[0] = l4_extract<B, 1 * B, NW>(w, sel);
-        l[1] = l4_extract<B, 2 * B, NW>(w, sel); r[1] = l4_extract<B, 3 * B, NW>(w, sel);
-        l[2] = l4_extract<B, 4 * B, NW>(w, sel); r[2] = l4_extract<B, 5 * B, NW>(w, sel);
-        l[3] = l4_extract<B, 6 * B, NW>(w, sel); r[3] = l4_extract<B, 7 * B, NW>(w, sel);
-        l[4] = l4_extract<B, 8 * B, NW>(w, sel); r[4] = l4_extract<B, 9 * B, NW>(w, sel);
-        l[5] = l4_extract<B, 10 * B, NW>(w, sel); r[5] = l4_extract<B, 11 * B, NW>(w, sel);
-        l[6] = l4_extract<B, 12 * B, NW>(w, sel); r[6] = l4_extract<B, 13 * B, NW>(w, sel);
-        l[7] = l4_extract<B, 14 * B, NW>(w, sel); r[7] = l4_extract<B, 15 * B, NW>(w, sel);
+    }
+    const double2 w01 = *reinterpret_cast<const double2*>(swin), w23 = *reinterpret_cast<const double2*>(swin + 16);
+    const double wv[4] = {w01.x, w01.y, w23.x, w23.y};
+    int32_t l[4], r[4];
+    l[0] = l4_extract<B, 0 * B, NW>(w, sel); r[0] = l4_extract<B, 1 * B, NW>(w, sel);
+    l[1] = l4_extract<B, 2 * B, NW>(w, sel); r[1] = l4_extract<B, 3 * B, NW>(w, sel);
+    l[2] = l4_extract<B, 4 * B, NW>(w, sel); r[2] = l4_extract<B, 5 * B, NW>(w, sel);
+    l[3] = l4_extract<B, 6 * B, NW>(w, sel); r[3] = l4_extract<B, 7 * B, NW>(w, sel);
 #pragma unroll
-        for (int i2 = 0; i2 < 4; i2++) {
-            const double2 wv2 = *reinterpret_cast<const double2*>(swin + h * 64 + i2 * 16);
+    for (int i = 0; i < 4; i++) {
+        const int32_t px[4] = {l[i], r[i], (l[i] + r[i]) >> 1, l[i] - r[i]};   // L | R | mid (:2721) | side (:2734)
 #pragma unroll
-            for (int ii = 0; ii < 2; ii++) {
-                const int i = i2 * 2 + ii;
-                const int32_t px = (l[i] * ca + r[i] * cb) >> cs;   // L | R | (L + R) >> 1 | L - R (:2721, :2734), wasted bits shifted out (:2891)
-                mask |= (uint32_t)px;
-                vcol[(h * 8 + i) * 32] = __dmul_rn((double)px, ii ? wv2.y : wv2.x);   // Window::apply (:1799)
-            }
+        for (int kk = 0; kk < 4; kk++) {
+            const int32_t pv = SHIFT ? px[kk] >> wk[kk] : px[kk];
+            if (!SHIFT) mk[kk] |= (uint32_t)pv;
+            vout[i * L4_VROW + 8 * kk] = __dmul_rn((double)pv, wv[i]);   // Window::apply (:1799)
         }
     }
 }
@@ -437,7 +439,7 @@ __device__ __forceinline__ void l4_accumulate(const double* __restrict__ vcol, u
     for (int s = 0; s < 16; s++) {
         double pn[NL];
         if (s + 1 < 16) {
-            const double v = vcol[(s + 1) * 32];
+            const double v = vcol[(s + 1) * L4_VROW];
             win[(s + 1) & 15] = v;
 #pragma unroll
             for (int lag = 0; lag < NL; lag++) pn[lag] = __dmul_rn(win[(s + 1 - lag) & 15], v);
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? FLACB200_L4_MINB : 1)
 {
     constexpr int MM = NL - 1;   // largest order of this instantiation
     __shared__ __align__(16) uint8_t l4_sm[WARPS * L4_SLOTS * L4_SLOT_BYTES];
-    __shared__ double l4_vals[WARPS][16][32];   // windowed samples of the tile at hand: [sample][lane]
+    __shared__ double l4_vals[WARPS][16][L4_VROW];   // windowed samples of the tile at hand: [sample][8 k + frame]
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t M = cfg.max_lpc_order;
     for (uint32_t unit = blockIdx.x * WARPS + wid; (unsigned long long)unit * 8 < nframes; unit += gridDim.x * WARPS) {
@@ -503,8 +505,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? FLACB200_L4_MINB : 1)
         }
         sel[sh] = v;
     }
-    const int32_t ca = k == 1 ? 0 : 1, cb = k == 0 ? 0 : (k == 3 ? -1 : 1);
-    const uint32_t cs0 = k == 2 ? 1u : 0u;
+    const uint32_t fa = lane & 7, qa = lane >> 3;   // phase A: the lane's frame and quarter of the tile
 
     // global -> slot: the four lanes of a frame copy its 2 B + 8 sixteen-byte chunks of the tile (PCM, then window values);
     // bytes past the end of the block are zero-filled
@@ -534,13 +535,14 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? FLACB200_L4_MINB : 1)
     uint32_t mask = 0, wasted = 0;
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1 && !__any_sync(0xffffffffu, wasted != 0)) break;   // rare pass: wasted bits shifted out (:2878-2898)
-        const uint32_t cs = cs0 + wasted;
+        uint32_t wk[4], mk[4] = {0, 0, 0, 0};   // wasted bits / OR masks of the four candidates of the lane's phase-A frame
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) wk[kk] = __shfl_sync(0xffffffffu, wasted, 4 * fa + kk);
         double win[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) win[i] = 0.0;
 #pragma unroll
         for (int lag = 0; lag < NL; lag++) acc[lag] = -0.0;   // Iterator::sum::<f64>() folds from -0.0
-        uint32_t m2 = 0;
         issue(0, 0);
         issue(1, 1);
         uint32_t slot = 0;
@@ -548,19 +550,26 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? FLACB200_L4_MINB : 1)
             issue(t + 2, slot >= 1 ? slot - 1 : 2);   // (slot + 2) % 3
             l3_wait<2>();
             __syncwarp();
-            const uint8_t* spcm = wsm + slot * L4_SLOT_BYTES + fl * L4_STRIDE;
-            const uint8_t* swin = spcm + 8 * L4_STRIDE;
-            double* vcol = &l4_vals[wid][0][lane];
-            l4_convert<B>(spcm, swin, vcol, sel, ca, cb, cs, m2);
-            __syncwarp();   // (the staging slot may be refilled; the value column is the lane's own)
+            const uint8_t* spcm = wsm + slot * L4_SLOT_BYTES + fa * L4_STRIDE;
+            double* vout = &l4_vals[wid][4 * qa][fa];
+            if (pass == 0) l4_convert<B, false>(spcm + qa * (8 * B), spcm + 8 * L4_STRIDE + qa * 32, vout, sel, wk, mk);
+            else l4_convert<B, true>(spcm + qa * (8 * B), spcm + 8 * L4_STRIDE + qa * 32, vout, sel, wk, mk);
+            __syncwarp();   // the value buffer is complete (and the staging slot may be refilled)
+            const double* vcol = &l4_vals[wid][0][8 * k + fl];
             if (t == 0 || (t + 1) * 16 > nmin) l4_accumulate<NL, true>(vcol, t * 16, n, acc, win);
             else l4_accumulate<NL, false>(vcol, t * 16, n, acc, win);
             slot = slot == 2 ? 0 : slot + 1;
         }
         l3_wait<0>();
         __syncwarp();
-        if (pass == 0) {
-            mask = m2;
+        if (pass == 0) {   // the masks of a frame's candidates: OR over its four phase-A lanes, then to the candidates' own lanes
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                mk[kk] |= __shfl_xor_sync(0xffffffffu, mk[kk], 8);
+                mk[kk] |= __shfl_xor_sync(0xffffffffu, mk[kk], 16);
+                const uint32_t t = __shfl_sync(0xffffffffu, mk[kk], fl);
+                if (k == (uint32_t)kk) mask = t;
+            }
             wasted = (mask == 0 || (mask & 1u)) ? 0u : (uint32_t)__ffs((int)mask) - 1u;
         }
     }
