@@ -69,6 +69,7 @@ struct A3Cand {   // per candidate, shared by its warps
     unsigned long long bits_f, bits_l;
     uint32_t mask, ovf, bad16, bad_f, bad_l;
     uint32_t fo, lpc_ok;               // decisions of the first warp, read by the second
+    uint32_t lb_f;                     // lower bound of the fixed predictor's residual code bits (aw_choose_partitions_flat)
     uint32_t round_bits[2][8];         // pass 2: code bits per round of 32 tiles, [fixed | LPC] (k_frame4 places its warps with them)
 };
 
@@ -148,11 +149,32 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
     uint32_t cpf = n, j0f = 0, cpl = n, j0l = 0;
     bool cpf16 = false, cpl16 = false;
     // stage 0: pass 1 assuming no wasted bits; stage 1: pass 1 again with the wasted bits shifted out (rare);
-    // stage 2: pass 2 (exact sizes).  One loop body serves all stages so that the FIR code exists once.
-    for (int stage = 0; stage < 3; stage++) {
+    // stages 2 and 3: pass 2 (exact sizes).  One loop body serves all stages so that the FIR code exists once.
+    // Pass 2 runs as two sweeps: first the LPC residuals (the int16 copy: no plane loads), then the fixed residuals -- unless
+    // the exact LPC size is already below a lower bound of the fixed size (sm.lb_f), in which case LPC wins whatever the exact
+    // fixed size is (:2929-2979) and the second sweep is not needed.  A candidate without a 16-bit LPC copy does both in stage 3.
+    uint32_t hf = 0, hl = 0;   // partition headers: 4/5-bit parameter (+ 5-bit escape width)
+    bool skip_f = false, swept_l = false;
+    for (int stage = 0; stage < 4; stage++) {
         if (stage == 1 && wasted == 0) continue;
         uint32_t mask = 0, ovf = 0, b16 = 0;
-        if (stage < 2) {
+        if (stage == 3) {
+            if (swept_l) {   // the LPC sweep's total, then the decision
+                bits_l = warp_sum_u64(bits_l);
+                bad_l = __any_sync(0xffffffffu, bad_l) ? 1u : 0u;
+                if (lane == 0) {
+                    if (bits_l) atomicAdd(&sm.bits_l, bits_l);
+                    if (bad_l) atomicOr(&sm.bad_l, 1u);
+                }
+                bits_l = 0; bad_l = 0;
+                a3_pair_sync(cand);
+                const uint32_t hdr_bits = 8 + wasted;
+                const unsigned long long lpc_bits = (unsigned long long)hdr_bits + order * bps + 4 + 5 + order * lp.precision + (sm.bits_l + hl) + 6;
+                const unsigned long long fixed_lb = (unsigned long long)hdr_bits + fo * bps + ((unsigned long long)sm.lb_f + hf) + 6;
+                skip_f = sm.bad_l == 0 && lpc_bits < fixed_lb && lpc_bits < 0xFFFFFFFFull;
+                if (skip_f) break;   // (use16 holds here: nothing else is left to count)
+            }
+        } else if (stage < 2) {
             if (wsub == 0) {
                 for (uint32_t t = lane; t < A3_SETS * MAX_PARTS; t += 32) {
                     (&sm.limb_lo[0][0])[t] = 0;
@@ -166,7 +188,7 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
             }
             a3_pair_sync(cand);
         } else {
-            // ---- between the passes: fixed order, partition trees, Rice parameters (first warp of the candidate) ----
+            // ---- between the passes (stage 2): fixed order, partition trees, Rice parameters (first warp of the candidate) ----
             if (sm.mask == 0) {   // all samples zero -> CONSTANT (:2870, :2883)
                 if (wsub == 0 && lane == 0) {
                     rec->type = 0; rec->order = 0; rec->wasted = 0; rec->bps = (uint8_t)full_bps;
@@ -195,7 +217,7 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     if (kmax >= 3 && s3 < best) { best = s3; fo = 3; }
                     if (kmax >= 4 && s4 < best) { best = s4; fo = 4; }
                 }
-                aw_choose_partitions_flat(cfg, n, fo, p_max, sm.limb_lo[fo], sm.limb_hi[fo], sm.tree[0], sm.part_code[0], sm.choice[0]);
+                aw_choose_partitions_flat(cfg, n, fo, p_max, sm.limb_lo[fo], sm.limb_hi[fo], sm.tree[0], sm.part_code[0], sm.choice[0], &sm.lb_f);
                 if (lane == 0) sm.fo = fo;
             } else if (wsub == 1) {   // second warp: the LPC predictor
                 lpc_ok = have_lpc && sm.ovf == 0;   // ResidualOverflow
@@ -218,20 +240,33 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                 cpl16 = (cpl & 15u) == 0;
                 dcpl = udiv_make(cpl);
             }
+            {
+                const RiceChoice& cf_ = sm.choice[0];
+                const RiceChoice& cl_ = sm.choice[1];
+                for (uint32_t j = lane; j < cf_.nparts; j += 32) hf += (cf_.rice[j] < 0x40) ? (cf_.method ? 5u : 4u) : (cf_.method ? 10u : 9u);
+                if (lpc_ok)
+                    for (uint32_t j = lane; j < cl_.nparts; j += 32) hl += (cl_.rice[j] < 0x40) ? (cl_.method ? 5u : 4u) : (cl_.method ? 10u : 9u);
+                hf = __reduce_add_sync(0xffffffffu, hf);
+                hl = __reduce_add_sync(0xffffffffu, hl);
+            }
+            swept_l = lpc_ok && use16;
+            if (!swept_l) continue;   // everything is counted in stage 3
         }
         for (uint32_t rd = wsub; rd < rounds; rd += A3_WPC) {
             const uint32_t t = rd * 32 + lane, i0 = t * 16;
             const unsigned long long rb_f0 = bits_f, rb_l0 = bits_l;
             if (i0 < n) {
             const bool tail = i0 + 16 > n;   // tile cut by the block end: rare, sample-by-sample path
-            const bool fir = lpc_ok && (stage < 2 || !use16);
+            const bool fir = lpc_ok && (stage < 2 || (stage == 3 && !use16));
             int32_t x[16], h[16];
-            a3_tile<STEREO>(planes, pslot, t, 0, x);
 #pragma unroll
-            for (int e = 0; e < 16; e++) h[e] = 0;
-            if (t > 0) {   // the fixed differences look back 4 samples, the FIR HB
-                if (fir) a3_tile<STEREO>(planes, pslot, t - 1, 4 - HB / 4, h);
-                else a3_tile<STEREO>(planes, pslot, t - 1, 3, h);
+            for (int e = 0; e < 16; e++) { x[e] = 0; h[e] = 0; }
+            if (stage != 2) {   // (the LPC sweep reads the int16 copy only)
+                a3_tile<STEREO>(planes, pslot, t, 0, x);
+                if (t > 0) {   // the fixed differences look back 4 samples, the FIR HB
+                    if (fir) a3_tile<STEREO>(planes, pslot, t - 1, 4 - HB / 4, h);
+                    else a3_tile<STEREO>(planes, pslot, t - 1, 3, h);
+                }
             }
             if (stage == 0) {
 #pragma unroll
@@ -309,7 +344,7 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     res16[(rd * 2 + 0) * 32 + lane] = lo4;
                     res16[(rd * 2 + 1) * 32 + lane] = hi4;
                 }
-            } else if (lpc_ok) {   // pass 2: the int16 copy
+            } else if (stage == 2) {   // pass 2, LPC sweep: the int16 copy
                 const uint4 lo4 = res16[(rd * 2 + 0) * 32 + lane], hi4 = res16[(rd * 2 + 1) * 32 + lane];
                 const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
@@ -379,6 +414,7 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                 }
             } else {
                 // ---- pass 2: exact size of both residual blocks (what Partition::to_writer will emit, :3834-3863) ----
+                if (stage == 3) {
                 int32_t rf[16];
                 {
                     int32_t prev = h[15];
@@ -427,7 +463,8 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                     bits_f += tb;
                     bad_f |= tbad;
                 }
-                if (lpc_ok) {
+                }
+                if (lpc_ok && (stage == 2 || !use16)) {
                     const RiceChoice& chl = sm.choice[1];
                     const uint32_t pl = udiv(i0, dcpl);
                     const uint32_t codel = chl.rice[pl - j0l >= chl.nparts ? 0 : pl - j0l];
@@ -460,11 +497,11 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
                 }
             }
             }
-            if (stage == 2 && rd < 8) {   // (all lanes of the warp are here: the body above is a plain `if`)
+            if (stage >= 2 && rd < 8) {   // (all lanes of the warp are here: the body above is a plain `if`)
                 const uint32_t rf_ = __reduce_add_sync(0xffffffffu, (uint32_t)(bits_f - rb_f0)), rl_ = __reduce_add_sync(0xffffffffu, (uint32_t)(bits_l - rb_l0));
                 if (lane == 0) {
-                    sm.round_bits[0][rd] = rf_;
-                    sm.round_bits[1][rd] = rl_;
+                    if (stage == 3) sm.round_bits[0][rd] = rf_;
+                    if (stage == 2 || !swept_l) sm.round_bits[1][rd] = rl_;
                 }
             }
         }
@@ -503,17 +540,8 @@ __device__ void a3_candidate(const EncCfg& cfg, const FrameDesc& d, const int32_
     if (gres16 != nullptr && lpc_ok && use16)
         for (uint32_t k = wsub * 32 + lane; k < rounds * 64; k += 32 * A3_WPC) gres16[k] = res16[k];
     if (wsub != 0) return;
-    const RiceChoice& cf_ = sm.choice[0];
-    const RiceChoice& cl_ = sm.choice[1];
-    // partition headers: 4/5-bit parameter (+ 5-bit escape width)
-    uint32_t hf = 0, hl = 0;
-    for (uint32_t j = lane; j < cf_.nparts; j += 32) hf += (cf_.rice[j] < 0x40) ? (cf_.method ? 5u : 4u) : (cf_.method ? 10u : 9u);
-    if (lpc_ok)
-        for (uint32_t j = lane; j < cl_.nparts; j += 32) hl += (cl_.rice[j] < 0x40) ? (cl_.method ? 5u : 4u) : (cl_.method ? 10u : 9u);
-    hf = __reduce_add_sync(0xffffffffu, hf);
-    hl = __reduce_add_sync(0xffffffffu, hl);
     const unsigned long long tot_f = sm.bits_f + hf, tot_l = sm.bits_l + hl;
-    const bool fixed_ok = sm.bad_f == 0;
+    const bool fixed_ok = sm.bad_f == 0 && !skip_f;   // (skipped: its exact size is not known, only that it exceeds the LPC size)
     if (sm.bad_l) lpc_ok = false;
     const uint32_t hdr_bits = 8 + wasted;   // pad + type + wasted flag (+ unary(wasted - 1)) (src/stream.rs:1397)
     const uint32_t fixed_bits = hdr_bits + fo * bps + (uint32_t)tot_f + 6;

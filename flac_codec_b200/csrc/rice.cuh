@@ -181,8 +181,11 @@ static __device__ void aw_choose_partitions(const EncCfg& cfg, uint32_t n, uint3
 // the leaves, every (order, partition) node is evaluated once in registers (four per lane), the per-order totals come from
 // warp reductions that all lanes receive -- no level-by-level tree, no per-order loops.  `pref` (65 entries) and `codes`
 // (127 bytes) are the warp's scratch in shared memory.
+// lb_out (optional): a LOWER BOUND of the exact size of the residual codes with the chosen parameters, from the partition sums
+// alone -- zig-zag u is 2|r| or 2|r| - 1, so u >> k >= 2|r| / 2^k - 1 and a partition of len samples with parameter k costs at
+// least max(0, ceil(2 S / 2^k) - len) + len (k + 1) bits; escaped and all-zero partitions are exact.
 static __device__ void aw_choose_partitions_flat(const EncCfg& cfg, uint32_t n, uint32_t o, uint32_t p_max, const uint32_t* lo, const uint32_t* hi,
-                                                unsigned long long* pref, uint8_t* codes, RiceChoice& ch)
+                                                unsigned long long* pref, uint8_t* codes, RiceChoice& ch, uint32_t* lb_out = nullptr)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t rice_max = cfg.use_rice2 ? 31u : 15u;
@@ -255,6 +258,7 @@ static __device__ void aw_choose_partitions_flat(const EncCfg& cfg, uint32_t n, 
         if (lane == 0) {
             ch.porder_g = 0; ch.porder_w = 0; ch.nparts = 1; ch.rice[0] = 0x40 | 31;
             ch.method = cfg.use_rice2 ? 1 : 0;
+            if (lb_out) *lb_out = 0;
         }
         __syncwarp();
         return;
@@ -272,6 +276,23 @@ static __device__ void aw_choose_partitions_flat(const EncCfg& cfg, uint32_t n, 
         ch.nparts = (uint8_t)best_count;
         ch.porder_w = (uint8_t)(31u - (uint32_t)__clz((int)best_count));   // partitions.len().ilog2() :3902
         ch.method = (cfg.use_rice2 && big) ? 1 : 0;                         // try_reduce_rice :3929-3942
+    }
+    if (lb_out) {
+        const uint32_t cp = n >> best_p, w = nleaf >> best_p;
+        unsigned long long lb = 0;
+        for (uint32_t j = lane; j < best_count; j += 32) {
+            const uint32_t jj = j0 + j, a = jj * cp, b = a + cp, len = b - max(a, o);
+            const uint32_t c = codes[base + jj];
+            const unsigned long long S = pref[(jj + 1) * w] - pref[jj * w];
+            if (c < 0x40) {
+                const unsigned long long t = (2 * S + ((1ull << c) - 1)) >> c;
+                lb += (t > len ? t - len : 0ull) + (unsigned long long)len * (c + 1u);
+            } else if (c & 0x40) {
+                lb += (unsigned long long)len * (c & 31u);
+            }
+        }
+        lb = warp_sum_u64(lb);
+        if (lane == 0) *lb_out = lb > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)lb;
     }
     __syncwarp();
 }
