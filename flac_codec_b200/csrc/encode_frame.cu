@@ -184,6 +184,10 @@ __device__ inline void p3_residuals(const EncCfg& cfg, const FrameDesc& d, const
 // Two launches share the work: the first with a shared-memory image sized for ordinary frames (min_words = 0, cap_words =
 // P3_SMALL_WORDS: more CTAs per SM), the second with room for the worst case, for the few frames that need more
 // (min_words = P3_SMALL_WORDS); a CTA whose frame belongs to the other launch exits at once.
+#ifndef FLACB200_P3_PF
+#define FLACB200_P3_PF 1
+#endif
+constexpr uint32_t P3_PF_DIST = 1480;   // frames ahead: the CTAs resident at once (10 x 148 SMs)
 template <int HB, bool STEREO>
 #ifndef FLACB200_P3_MINB
 #define FLACB200_P3_MINB 9
@@ -277,6 +281,18 @@ __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? FLACB200_P3_MINB :
         const uint4* r16 = (gres16 != nullptr && cr.type == 3 && cr.pad0 == 1) ? gres16 + ((size_t)f * cfg.nslots + slot) * 512 : nullptr;
         p3_residuals<HB, STEREO>(cfg, d, pcm, slot, cr, words_sa, pos, r16);
     }
+#if FLACB200_P3_PF
+    // the int16 residuals of the frame that will be packed in this CTA's place (ten CTAs per SM) are asked into L2 now: they were
+    // written by k_analyze3 a gigabyte ago and are this kernel's only DRAM read
+    if (STEREO && gres16 != nullptr && f + P3_PF_DIST < cfg.nframes) {
+        const FrameRec* fnext = frecs + f + P3_PF_DIST;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const uint4* q = gres16 + ((size_t)(f + P3_PF_DIST) * cfg.nslots + fnext->slot[c]) * 512 + tid * 8;
+            if (tid < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+    }
+#endif
     __syncthreads();
     // ---- CRC-16 over everything but the last two bytes (src/encode.rs:2408-2409) ----
     const uint32_t body = frame_bytes - 2;
