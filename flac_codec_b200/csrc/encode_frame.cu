@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? FLACB200_P3_MINB :
     const uint32_t nsub = fr.nsub;
     const uint32_t frame_bytes = fr.frame_bytes;
     const uint32_t img_words = min((frame_bytes + 3) / 4 + 2, cap_words);
-    for (uint32_t i = tid; i < img_words; i += nthreads) p3_words[i] = 0;
+    for (uint32_t i = tid; i < img_words / 4; i += nthreads) reinterpret_cast<uint4*>(p3_words)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < (img_words & 3u)) p3_words[(img_words & ~3u) + tid] = 0;
     for (uint32_t c = wid; c < nsub; c += nwarps) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(cands + (size_t)f * cfg.nslots + fr.slot[c]);
         for (uint32_t i = lane; i < sizeof(CandRec) / 4; i += 32) reinterpret_cast<uint32_t*>(&sm.cr[c])[i] = src[i];
@@ -320,9 +321,9 @@ __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? FLACB200_P3_MINB :
         }
         __syncthreads();
     }
-    // ---- copy out ----
+    // ---- copy out: bytes up to the first 16-byte boundary of the output, 128-bit stores, the rest by bytes ----
     const unsigned long long o = fr.out_off;
-    const unsigned long long A = (o + 3) & ~3ull, B = (o + frame_bytes) & ~3ull;
+    const unsigned long long A = (o + 15) & ~15ull, B = (o + frame_bytes) & ~15ull;
     auto frame_byte = [&](uint32_t b) -> uint8_t { return (uint8_t)(p3_words[b >> 2] >> (24 - 8 * (b & 3))); };
     if (A >= B) {
         for (uint32_t b = tid; b < frame_bytes; b += nthreads) out[o + b] = frame_byte(b);
@@ -331,13 +332,23 @@ __global__ void __launch_bounds__(STEREO ? 64 : 256, STEREO ? FLACB200_P3_MINB :
     const uint32_t head = (uint32_t)(A - o), tail0 = (uint32_t)(B - o);
     if (tid < head) out[o + tid] = frame_byte(tid);
     if (tid < frame_bytes - tail0) out[B + tid] = frame_byte(tail0 + tid);
-    uint32_t* gw = reinterpret_cast<uint32_t*>(out + A);
-    const uint32_t nfull = (uint32_t)((B - A) >> 2);
-    const uint32_t sh = head & 3;   // frame byte index of the first full word (mod 4)
-    for (uint32_t j = tid; j < nfull; j += nthreads) {
-        const uint32_t b = head + 4 * j, idx = b >> 2;
-        const uint32_t be = sh ? __funnelshift_l(p3_words[idx + 1], p3_words[idx], 8 * sh) : p3_words[idx];
-        gw[j] = __byte_perm(be, 0, 0x0123);
+    uint4* gq = reinterpret_cast<uint4*>(out + A);
+    const uint32_t nq = (uint32_t)((B - A) >> 4);
+    const uint32_t sh = 8 * (head & 3);   // the image's words are big-endian bit order; a 16-byte run starts `head` bytes into it
+    for (uint32_t j = tid; j < nq; j += nthreads) {
+        const uint32_t idx = (head >> 2) + 4 * j;
+        const uint32_t w0 = p3_words[idx], w1 = p3_words[idx + 1], w2 = p3_words[idx + 2], w3 = p3_words[idx + 3];
+        uint4 v;
+        if (sh) {
+            const uint32_t w4 = p3_words[idx + 4];   // (within the image: at least one byte of the frame follows this run's last word)
+            v.x = __byte_perm(__funnelshift_l(w1, w0, sh), 0, 0x0123);
+            v.y = __byte_perm(__funnelshift_l(w2, w1, sh), 0, 0x0123);
+            v.z = __byte_perm(__funnelshift_l(w3, w2, sh), 0, 0x0123);
+            v.w = __byte_perm(__funnelshift_l(w4, w3, sh), 0, 0x0123);
+        } else {
+            v.x = __byte_perm(w0, 0, 0x0123); v.y = __byte_perm(w1, 0, 0x0123); v.z = __byte_perm(w2, 0, 0x0123); v.w = __byte_perm(w3, 0, 0x0123);
+        }
+        gq[j] = v;
     }
 }
 
