@@ -352,12 +352,14 @@ cudaError_t launch_lpc3(const EncCfg& cfg, const FrameDesc* descs, const uint8_t
 // slots as the FP64 loop itself (FP64 pipe 67 % busy).  Here a lane owns its candidate outright:
 //   * all NL lags are NL accumulators of the lane (13 of 13 FP64 operations useful), the lagged samples are a circular
 //     window of 16 doubles in registers with static indices (the tile loop is unrolled over 16 samples);
-//   * nothing is staged as doubles: the raw PCM bytes (16 samples x 2 channels) and the window values of the eight frames
-//     travel global -> shared with cp.async, two tiles ahead; a lane pulls ITS frame's bytes with 128-bit loads, extracts
-//     left and right with one PRMT + shift each (static positions), forms its own channel combination with per-lane
-//     constants (l * ca + r * cb) >> cs, converts and multiplies by the window value -- about 12 integer instructions
-//     beside the 27 FP64 instructions of a sample;
-//   * the first tile and tiles that reach past the shortest frame of the warp run a predicated copy of the tile body
+//   * the raw PCM bytes (16 samples x 2 channels) and the window values of the eight frames travel global -> shared with
+//     cp.async, two tiles ahead.  Phase A of a tile is the warp's joint work: lane (q, f) takes samples 4 q .. 4 q + 3 of
+//     frame f, extracts left and right once (one PRMT + shift each, static positions), forms all four channel
+//     combinations, converts, multiplies by the window value and parks the 16 doubles in the value buffer
+//     [sample][8 k + f]; phase B is the candidate lane's own: one 64-bit shared load, NL DMULs and NL DADDs per sample,
+//     nothing else (an FP64 instruction holds the issue port for two cycles: the ~250 non-FP64 slots of a tile are what
+//     there is to save beside its 432 x 2);
+//   * the first tile and tiles that reach past the shortest frame of the warp run a predicated copy of phase B
 //     (a lag only counts samples that exist: no zero terms are ever added, the sums start from -0.0 as in k_lpc3);
 //   * Levinson-Durbin, the order estimate and the quantisation run on all 32 lanes at once, fully unrolled over the
 //     template's order so that R[], the coefficient sets and the errors stay in registers; the set of the best order so
